@@ -1,0 +1,290 @@
+"""Deterministic synthetic inputs for the art_planner hot path.
+
+Every generator is a pure function of (seed, index): a counter-based splitmix64 hash feeds all
+random draws, so the CPU oracle and the GPU path consume bit-identical arrays and any rank can
+regenerate its own shard without communication.
+
+Layer layout follows grid_map (the reference's map container; call sites
+art_planner/src/validity_checker/height_map_box_checker.cpp:41-53): a layer is a column-major
+rows x cols float32 matrix, cell (i, j) centred at
+    x = cx + Lx/2 - (i + 0.5) * res,   y = cy + Ly/2 - (j + 0.5) * res.
+`elevation` is finite everywhere; `elevation_masked` equals `elevation` where traversable and -inf
+elsewhere (art_planner/src/map/processors/basic.cpp:102-105).
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+
+import numpy as np
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+    z = x
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+    return z ^ (z >> np.uint64(31))
+
+
+def hash_u64(seed: int, stream: int, idx) -> np.ndarray:
+    """64-bit hash of (seed, stream, idx); idx may be an int array."""
+    with np.errstate(over="ignore"):
+        idx = np.asarray(idx, dtype=np.uint64)
+        k = _splitmix64(np.uint64(seed) * np.uint64(0x632BE59BD9B4E019) + np.uint64(stream))
+        return _splitmix64(idx ^ k)
+
+
+def hash_uniform(seed: int, stream: int, idx) -> np.ndarray:
+    """U[0,1) doubles, pure function of (seed, stream, idx)."""
+    return (hash_u64(seed, stream, idx) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# robot geometry presets
+# ---------------------------------------------------------------------------------------------
+@dataclasses.dataclass(frozen=True)
+class RobotParams:
+    """The fields of art_planner::Params the hot path reads (params.h:14-123)."""
+    torso_length: float
+    torso_width: float
+    torso_height: float
+    torso_off_x: float
+    torso_off_y: float
+    torso_off_z: float
+    feet_off_x: float
+    feet_off_y: float
+    feet_off_z: float
+    reach_x: float
+    reach_y: float
+    reach_z: float
+    unknown_space_untraversable: bool = True
+    use_directional_cost: bool = True
+    max_lon_vel: float = 0.5
+    max_lat_vel: float = 0.1
+    max_ang_vel: float = 0.5
+
+
+#: shipped configuration, art_planner_ros/config/params.yaml:55-71 (+ :11, :39-43)
+PARAMS_YAML = RobotParams(1.31, 0.65, 0.30, 0.0, 0.0, 0.04, 0.51, 0.20, -0.475, 0.2, 0.2, 0.2,
+                          True, True, 0.5, 0.1, 0.5)
+#: header defaults, art_planner/include/art_planner/params.h:26,73-76,90-117
+PARAMS_HEADER = RobotParams(1.05, 0.55, 0.2, 0.0, 0.0, 0.0, 0.362, 0.225, -0.525, 0.25, 0.1, 0.15,
+                            True, False, 0.5, 0.1, 0.5)
+
+
+# ---------------------------------------------------------------------------------------------
+# maps
+# ---------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class SynthMap:
+    elevation: np.ndarray          # float32 [rows, cols], Fortran (column-major) order
+    elevation_masked: np.ndarray   # float32 [rows, cols], Fortran order
+    res: float
+    cx: float
+    cy: float
+    desc: str
+
+    @property
+    def rows(self) -> int:
+        return self.elevation.shape[0]
+
+    @property
+    def cols(self) -> int:
+        return self.elevation.shape[1]
+
+    @property
+    def length(self):
+        return self.rows * self.res, self.cols * self.res
+
+    def cell_xy(self):
+        lx, ly = self.length
+        x = self.cx + 0.5 * lx - (np.arange(self.rows) + 0.5) * self.res
+        y = self.cy + 0.5 * ly - (np.arange(self.cols) + 0.5) * self.res
+        return x, y
+
+    def index_of(self, x, y):
+        """grid_map getIndexFromPosition (clamped)."""
+        lx, ly = self.length
+        i = np.floor((self.cx + 0.5 * lx - x) / self.res).astype(np.int64)
+        j = np.floor((self.cy + 0.5 * ly - y) / self.res).astype(np.int64)
+        return np.clip(i, 0, self.rows - 1), np.clip(j, 0, self.cols - 1)
+
+
+_GRAD = np.array([[1, 0], [-1, 0], [0, 1], [0, -1],
+                  [0.7071067811865476, 0.7071067811865476], [-0.7071067811865476, 0.7071067811865476],
+                  [0.7071067811865476, -0.7071067811865476], [-0.7071067811865476, -0.7071067811865476]])
+
+
+def _gradient_noise(seed: int, octave: int, u: np.ndarray, v: np.ndarray) -> np.ndarray:
+    """Classic 2-D gradient ("Perlin") noise on lattice coords (u, v), gradients hashed per node."""
+    u0 = np.floor(u)
+    v0 = np.floor(v)
+    fu = u - u0
+    fv = v - v0
+    iu = u0.astype(np.int64)
+    iv = v0.astype(np.int64)
+
+    def node(di, dj):
+        key = ((iu + di) & 0xFFFFFFFF).astype(np.uint64) << np.uint64(32) | ((iv + dj) & 0xFFFFFFFF).astype(np.uint64)
+        g = _GRAD[(hash_u64(seed, 1000 + octave, key) & np.uint64(7)).astype(np.int64)]
+        return g[..., 0] * (fu - di) + g[..., 1] * (fv - dj)
+
+    su = fu * fu * fu * (fu * (fu * 6 - 15) + 10)
+    sv = fv * fv * fv * (fv * (fv * 6 - 15) + 10)
+    n00, n10, n01, n11 = node(0, 0), node(1, 0), node(0, 1), node(1, 1)
+    a = n00 + su * (n10 - n00)
+    b = n01 + su * (n11 - n01)
+    return a + sv * (b - a)
+
+
+def fbm_height(seed: int, x: np.ndarray, y: np.ndarray, amp: float, wavelength: float = 8.0,
+               octaves: int = 5) -> np.ndarray:
+    """fBm of gradient noise: `octaves` octaves, base wavelength in metres, peak amplitude ~amp."""
+    h = np.zeros(np.broadcast(x, y).shape, dtype=np.float64)
+    a, f, norm = 1.0, 1.0 / wavelength, 0.0
+    for o in range(octaves):
+        h += a * _gradient_noise(seed, o, x * f + 0.37 * (o + 1), y * f + 0.61 * (o + 1))
+        norm += a
+        a *= 0.5
+        f *= 2.0
+    return h * (amp * 1.4142135623730951 / norm)
+
+
+def make_flat_map(rows=200, cols=200, res=0.04, height=0.0, cx=0.0, cy=0.0) -> SynthMap:
+    """C1: exactly flat, fully traversable."""
+    e = np.full((rows, cols), height, dtype=np.float32, order="F")
+    return SynthMap(e, e.copy(order="F"), res, cx, cy, f"flat {rows}x{cols}@{res} h={height}")
+
+
+def make_fbm_map(rows=1000, cols=1000, res=0.04, seed=2, amp=0.6, wavelength=8.0, octaves=5,
+                 blob_frac=0.02, n_walls=6, wall_height=0.5, cx=0.0, cy=0.0) -> SynthMap:
+    """C2/C5: fBm terrain + a few step walls; ~blob_frac of the cells in 0.3-1 m square blobs are
+    untraversable (-inf in `elevation_masked`)."""
+    m = SynthMap(np.zeros((rows, cols), np.float32, order="F"), np.zeros((1, 1), np.float32), res, cx, cy, "")
+    x, y = m.cell_xy()
+    lx, ly = m.length
+    e = fbm_height(seed, x[:, None], y[None, :], amp, wavelength, octaves)
+    # step walls: axis-aligned slabs raised by wall_height
+    for w in range(n_walls):
+        u = hash_uniform(seed, 2000 + w, np.arange(5))
+        wx = cx - 0.5 * lx + u[0] * lx
+        wy = cy - 0.5 * ly + u[1] * ly
+        length = 2.0 + 6.0 * u[2]
+        thick = 0.2 + 0.4 * u[3]
+        if u[4] < 0.5:
+            sel = (np.abs(x[:, None] - wx) < 0.5 * length) & (np.abs(y[None, :] - wy) < 0.5 * thick)
+        else:
+            sel = (np.abs(x[:, None] - wx) < 0.5 * thick) & (np.abs(y[None, :] - wy) < 0.5 * length)
+        e = np.where(sel, e + wall_height, e)
+    e32 = np.asfortranarray(e.astype(np.float32))
+    masked = e32.copy(order="F")
+    # untraversable square blobs, 0.3-1.0 m (mean area ~0.46 m^2)
+    n_blobs = int(round(blob_frac * lx * ly / 0.46))
+    if n_blobs > 0:
+        k = np.arange(n_blobs)
+        bx = cx - 0.5 * lx + hash_uniform(seed, 3001, k) * lx
+        by = cy - 0.5 * ly + hash_uniform(seed, 3002, k) * ly
+        bs = 0.3 + 0.7 * hash_uniform(seed, 3003, k)
+        i0, j1 = m.index_of(bx + 0.5 * bs, by - 0.5 * bs)
+        i1, j0 = m.index_of(bx - 0.5 * bs, by + 0.5 * bs)
+        for a in range(n_blobs):
+            masked[i0[a]:i1[a] + 1, j0[a]:j1[a] + 1] = -np.inf
+    desc = (f"fBm gradient noise {rows}x{cols}@{res} seed={seed} amp={amp} wavelength={wavelength} "
+            f"octaves={octaves} walls={n_walls}x{wall_height}m blobs={blob_frac}")
+    return SynthMap(e32, masked, res, cx, cy, desc)
+
+
+def make_fixture_map(rows=120, cols=120, res=0.05, cx=0.0, cy=0.0) -> SynthMap:
+    """The reference's only in-repo synthetic fixture recipe (art_planner/src/ode_test.cpp:24-84),
+    regenerated: 6x6 m @0.05, 0.1 m plateau with slots, a 0.8 m wall, one 0.5 m spike; the demo's
+    2x2 NaN patch becomes a -inf patch in the masked layer (and stays finite in `elevation`,
+    honouring the hot path's input contract: finite or -inf)."""
+    e = np.zeros((rows, cols), dtype=np.float32, order="F")
+    e[20:60, 20:100] = 0.1
+    e[30:34, 20:100] = 0.0
+    e[44:46, 20:100] = 0.0
+    e[80:84, 10:110] = 0.8
+    e[100, 60] = 0.5
+    masked = e.copy(order="F")
+    masked[10:12, 10:12] = -np.inf
+    masked[62:70, 40:52] = -np.inf
+    return SynthMap(e, masked, res, cx, cy, f"fixture {rows}x{cols}@{res} (ode_test.cpp recipe)")
+
+
+# ---------------------------------------------------------------------------------------------
+# samples
+# ---------------------------------------------------------------------------------------------
+def quat_from_rpy(roll, pitch, yaw):
+    """setSO3FromRPY, art_planner/include/art_planner/utils.h:100-115. Returns (x, y, z, w)."""
+    r2, p2, y2 = roll * 0.5, pitch * 0.5, yaw * 0.5
+    cr, cp, cy = np.cos(r2), np.cos(p2), np.cos(y2)
+    sr, sp, sy = np.sin(r2), np.sin(p2), np.sin(y2)
+    w = cy * cp * cr + sy * sp * sr
+    x = cy * cp * sr - sy * sp * cr
+    y = sy * cp * sr + cy * sp * cr
+    z = sy * cp * cr - cy * sp * sr
+    return x, y, z, w
+
+
+def make_flat_poses(m: SynthMap, n: int, seed: int = 1, start: int = 0, margin: float = 0.25,
+                    z_range: float = 0.15) -> np.ndarray:
+    """C1 samples: x,y ~ U(-L/2-margin, L/2+margin) (outside-map branches fire), yaw uniform,
+    roll = pitch = 0, z = U(-z_range, z_range). Returns [n, 7] float64 (x y z qx qy qz qw)."""
+    k = np.arange(start, start + n)
+    lx, ly = m.length
+    x = m.cx + (hash_uniform(seed, 1, k) - 0.5) * (lx + 2 * margin)
+    y = m.cy + (hash_uniform(seed, 2, k) - 0.5) * (ly + 2 * margin)
+    z = (hash_uniform(seed, 3, k) * 2 - 1) * z_range
+    yaw = (hash_uniform(seed, 4, k) * 2 - 1) * math.pi
+    qx, qy, qz, qw = quat_from_rpy(np.zeros(n), np.zeros(n), yaw)
+    return np.ascontiguousarray(np.stack([x, y, z, qx, qy, qz, qw], axis=1))
+
+
+def make_terrain_poses(m: SynthMap, n: int, seed: int = 3, start: int = 0, z_range: float = 0.12,
+                       roll_pert: float = math.radians(3.33), pitch_pert: float = math.radians(10.0),
+                       xy: tuple | None = None) -> np.ndarray:
+    """C2/C5 samples: x,y uniform inside the map, yaw uniform, z = cell height + U(+-z_range),
+    roll/pitch = terrain-normal aligned + U(+-pert), like SE3FromSE2Sampler::sampleUniform
+    (art_planner/src/sampler.cpp:82-131). Returns [n, 7] float64."""
+    k = np.arange(start, start + n)
+    lx, ly = m.length
+    if xy is None:
+        x = m.cx + (hash_uniform(seed, 1, k) - 0.5) * lx * 0.999
+        y = m.cy + (hash_uniform(seed, 2, k) - 0.5) * ly * 0.999
+    else:
+        x, y = xy
+    i, j = m.index_of(x, y)
+    e = m.elevation
+    z = e[i, j].astype(np.float64) + (hash_uniform(seed, 3, k) * 2 - 1) * z_range
+    yaw = (hash_uniform(seed, 4, k) * 2 - 1) * math.pi
+    # finite-difference normal (x decreases with i, y decreases with j)
+    ip, im = np.clip(i + 1, 0, m.rows - 1), np.clip(i - 1, 0, m.rows - 1)
+    jp, jm = np.clip(j + 1, 0, m.cols - 1), np.clip(j - 1, 0, m.cols - 1)
+    dzdx = (e[im, j].astype(np.float64) - e[ip, j]) / ((ip - im) * m.res)
+    dzdy = (e[i, jm].astype(np.float64) - e[i, jp]) / ((jp - jm) * m.res)
+    nrm = np.sqrt(dzdx * dzdx + dzdy * dzdy + 1.0)
+    nx, ny, nz = -dzdx / nrm, -dzdy / nrm, 1.0 / nrm
+    c, s = np.cos(yaw), np.sin(yaw)
+    nbx = c * nx + s * ny
+    nby = -s * nx + c * ny
+    roll = -np.arctan2(nby, nz) + (hash_uniform(seed, 5, k) * 2 - 1) * roll_pert
+    pitch = np.arctan2(nbx, nz) + (hash_uniform(seed, 6, k) * 2 - 1) * pitch_pert
+    qx, qy, qz, qw = quat_from_rpy(roll, pitch, yaw)
+    return np.ascontiguousarray(np.stack([x, y, z, qx, qy, qz, qw], axis=1))
+
+
+def make_edges(m: SynthMap, n: int, seed: int = 4, start: int = 0, dmin: float = 0.5, dmax: float = 2.0):
+    """C3 edges: s1 as make_terrain_poses, s2 = s1 displaced dmin..dmax m in a random heading with
+    its own z / orientation. Returns (s1, s2), each [n, 7] float64."""
+    k = np.arange(start, start + n)
+    s1 = make_terrain_poses(m, n, seed, start)
+    d = dmin + (dmax - dmin) * hash_uniform(seed, 11, k)
+    hd = (hash_uniform(seed, 12, k) * 2 - 1) * math.pi
+    lx, ly = m.length
+    x2 = np.clip(s1[:, 0] + d * np.cos(hd), m.cx - 0.4995 * lx, m.cx + 0.4995 * lx)
+    y2 = np.clip(s1[:, 1] + d * np.sin(hd), m.cy - 0.4995 * ly, m.cy + 0.4995 * ly)
+    s2 = make_terrain_poses(m, n, seed + 7919, start, xy=(x2, y2))
+    return s1, s2

@@ -1,0 +1,79 @@
+/*
+ * oracle/artp_oracle.h -- TEST INFRASTRUCTURE ONLY (CPU oracle for the art_planner hot path).
+ *
+ * Nothing in the product path (art_planner_b200/, include/) may include, link or call this.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it.
+ *
+ * Two shared libraries export the SAME C interface declared here:
+ *   oracle/liborc_port.so        -- plain-C restatement of the reference algorithm (artp_oracle.c)
+ *   oracle/_ref/liborc_ref.so    -- the reference's own vendored ODE (compiled from the sources
+ *                                   where they lie under /root/reference/ode) driven by
+ *                                   ref_harness.cpp; exists only where /root/reference exists.
+ * The pose-level wrapper arithmetic (Eigen / grid_map / OMPL restatements, none of which are in the
+ * reference tree) lives in artp_wrappers.h and is shared by both, so the two libraries differ exactly
+ * in the box-vs-heightfield collider: restated C vs. the reference's compiled ODE.
+ */
+#ifndef ARTP_ORACLE_H
+#define ARTP_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Mirrors the fields of art_planner::Params the hot path reads
+ * (art_planner/include/art_planner/params.h:14-123). All doubles, as in the reference. */
+typedef struct orc_params {
+  double torso_length, torso_width, torso_height;     /* params.h:92-94  */
+  double torso_off_x, torso_off_y, torso_off_z;       /* params.h:96-100 */
+  double feet_off_x, feet_off_y, feet_off_z;          /* params.h:106-110 */
+  double reach_x, reach_y, reach_z;                   /* params.h:112-116 */
+  int    unknown_space_untraversable;                 /* params.h:26 */
+  int    use_directional_cost;                        /* params.h:73 */
+  double max_lon_vel, max_lat_vel, max_ang_vel;       /* params.h:74-76 */
+} orc_params;
+
+typedef struct orc_handle orc_handle;
+
+orc_handle* orc_create(const orc_params* p);
+void        orc_destroy(orc_handle* h);
+
+/* Layers in grid_map layout: column-major rows x cols float, index (i,j) at data[i + j*rows].
+ * length = rows*res, cols*res (grid_map: length_ = size * resolution); centre (cx, cy).
+ * Mirrors HeightMapBoxChecker::setHeightField (height_map_box_checker.cpp:38-54). */
+int orc_set_map(orc_handle* h, const float* elevation, const float* elevation_masked,
+                int rows, int cols, double res, double cx, double cy);
+
+/* Raw dCollide(box, heightfield, 1, ...) != 0 for n box poses (height_map_box_checker.cpp:58-72).
+ * which: 0 = torso box vs `elevation`, 1 = reach box vs `elevation_masked`.
+ * origins n x 3 floats, rots n x 12 floats (row-major 3x4, dPose::rotation). out: 0/1 per pose.
+ * zone_verts (nullable): number of heightfield vertices the zone scan visits (0 if rejected before). */
+int orc_box_collide(orc_handle* h, int which, const float* origins, const float* rots, size_t n,
+                    uint8_t* hit, uint32_t* zone_verts);
+
+/* StateValidityChecker::isValid for n SE(3) states, each 7 doubles x y z qx qy qz qw
+ * (validity_checker.cpp:39-45). zone_verts (nullable): sum over the boxes the reference would
+ * actually execute (short-circuits honoured) of the zone vertex count. */
+int orc_check_poses(orc_handle* h, const double* states, size_t n, uint8_t* valid, uint32_t* zone_verts);
+
+/* Discrete motion check: valid(s2) && for j in 1..n_steps: valid(interp(s1, s2, j/(n_steps+1)))
+ * (OMPL DiscreteMotionValidator semantics with a fixed segment count). */
+int orc_check_motions(orc_handle* h, const double* s1, const double* s2, size_t n, int n_steps,
+                      uint8_t* valid, uint32_t* zone_verts);
+
+/* PathLengthObjective::motionCost (path_length_objective.cpp:26-70). */
+int orc_path_length_cost(orc_handle* h, const double* s1, const double* s2, size_t n, double* cost);
+
+/* Same as orc_check_poses but with T worker threads, each with its own collider state
+ * ("all cores" CPU baseline). */
+int orc_check_poses_mt(orc_handle* h, const double* states, size_t n, uint8_t* valid, int n_threads);
+
+/* Identifies the implementation: "port" or "reference". */
+const char* orc_kind(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,138 @@
+"""ctypes binding of the CPU oracle libraries (TEST INFRASTRUCTURE ONLY).
+
+    Oracle("port")       -> oracle/liborc_port.so     (C restatement, artp_oracle.c)
+    Oracle("reference")  -> oracle/_ref/liborc_ref.so (the reference's own compiled ODE + ref_harness.cpp)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(HERE, "liborc_port.so")
+REF_SO = os.path.join(HERE, "_ref", "liborc_ref.so")
+
+
+class OrcParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "torso_length", "torso_width", "torso_height", "torso_off_x", "torso_off_y", "torso_off_z",
+        "feet_off_x", "feet_off_y", "feet_off_z", "reach_x", "reach_y", "reach_z")] + [
+        ("unknown_space_untraversable", C.c_int), ("use_directional_cost", C.c_int),
+        ("max_lon_vel", C.c_double), ("max_lat_vel", C.c_double), ("max_ang_vel", C.c_double)]
+
+
+def build(kind: str = "port", quiet: bool = True) -> None:
+    """Compile the oracle library with oracle/Makefile (building the checker is not using it)."""
+    target = "port" if kind == "port" else "ref"
+    subprocess.run(["make", "-s", "-C", HERE, "-j8", target], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+def available(kind: str) -> bool:
+    return os.path.exists(PORT_SO if kind == "port" else REF_SO)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Oracle:
+    def __init__(self, params, kind: str = "port"):
+        path = PORT_SO if kind == "port" else REF_SO
+        if not os.path.exists(path):
+            if kind == "port" or os.path.isdir("/root/reference/ode"):
+                build(kind)
+            if not os.path.exists(path):
+                raise FileNotFoundError(path)
+        self.kind = kind
+        lib = C.CDLL(path)
+        self.lib = lib
+        lib.orc_create.restype = C.c_void_p
+        lib.orc_create.argtypes = [C.POINTER(OrcParams)]
+        lib.orc_destroy.argtypes = [C.c_void_p]
+        lib.orc_set_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double,
+                                    C.c_double, C.c_double]
+        lib.orc_box_collide.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                        C.c_void_p, C.c_void_p]
+        lib.orc_check_poses.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        lib.orc_check_motions.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                          C.c_void_p, C.c_void_p]
+        lib.orc_path_length_cost.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.orc_check_poses_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+        lib.orc_kind.restype = C.c_char_p
+        p = OrcParams()
+        for name, _ in OrcParams._fields_:
+            v = getattr(params, name)
+            setattr(p, name, int(v) if name in ("unknown_space_untraversable", "use_directional_cost") else float(v))
+        self.h = lib.orc_create(C.byref(p))
+        assert lib.orc_kind().decode() == ("port" if kind == "port" else "reference")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.orc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_map(self, m) -> None:
+        e = np.asfortranarray(m.elevation, dtype=np.float32)
+        k = np.asfortranarray(m.elevation_masked, dtype=np.float32)
+        self._keep = (e, k)
+        rc = self.lib.orc_set_map(self.h, e.ctypes.data, k.ctypes.data, e.shape[0], e.shape[1],
+                                  float(m.res), float(m.cx), float(m.cy))
+        assert rc == 0
+
+    def box_collide(self, which: int, origins, rots, want_zone=False):
+        o = np.ascontiguousarray(origins, dtype=np.float32)
+        r = np.ascontiguousarray(rots, dtype=np.float32)
+        n = o.shape[0]
+        hit = np.zeros(n, np.uint8)
+        zv = np.zeros(n, np.uint32)
+        rc = self.lib.orc_box_collide(self.h, which, o.ctypes.data, r.ctypes.data, n, hit.ctypes.data,
+                                      zv.ctypes.data)
+        assert rc == 0
+        return (hit, zv) if want_zone else hit
+
+    def check_poses(self, states, want_zone=False):
+        s = _f64(states)
+        n = s.shape[0]
+        valid = np.zeros(n, np.uint8)
+        zv = np.zeros(n, np.uint32)
+        rc = self.lib.orc_check_poses(self.h, s.ctypes.data, n, valid.ctypes.data, zv.ctypes.data)
+        assert rc == 0
+        return (valid, zv) if want_zone else valid
+
+    def check_poses_mt(self, states, n_threads: int):
+        s = _f64(states)
+        n = s.shape[0]
+        valid = np.zeros(n, np.uint8)
+        rc = self.lib.orc_check_poses_mt(self.h, s.ctypes.data, n, valid.ctypes.data, int(n_threads))
+        assert rc == 0
+        return valid
+
+    def check_motions(self, s1, s2, n_steps: int, want_zone=False):
+        a, b = _f64(s1), _f64(s2)
+        n = a.shape[0]
+        valid = np.zeros(n, np.uint8)
+        zv = np.zeros(n, np.uint32)
+        rc = self.lib.orc_check_motions(self.h, a.ctypes.data, b.ctypes.data, n, int(n_steps),
+                                        valid.ctypes.data, zv.ctypes.data)
+        assert rc == 0
+        return (valid, zv) if want_zone else valid
+
+    def path_length_cost(self, s1, s2):
+        a, b = _f64(s1), _f64(s2)
+        n = a.shape[0]
+        cost = np.zeros(n, np.float64)
+        rc = self.lib.orc_path_length_cost(self.h, a.ctypes.data, b.ctypes.data, n, cost.ctypes.data)
+        assert rc == 0
+        return cost
