@@ -1,0 +1,81 @@
+"""ctypes binding of libartp.so -- the C ABI declared in include/artp.h.
+
+The product path fails loudly when the CUDA library is missing or unusable: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libartp.so")
+
+ARTP_OK, ARTP_E_INVALID, ARTP_E_NOMAP, ARTP_E_CUDA, ARTP_E_LIMIT, ARTP_E_NOWEIGHTS = 0, -1, -2, -3, -4, -5
+
+
+class ArtpError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"artp error {code}: {msg}")
+        self.code = code
+
+
+class ArtpParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "torso_length", "torso_width", "torso_height", "torso_off_x", "torso_off_y", "torso_off_z",
+        "feet_off_x", "feet_off_y", "feet_off_z", "reach_x", "reach_y", "reach_z")] + [
+        ("unknown_space_untraversable", C.c_int), ("use_directional_cost", C.c_int),
+        ("max_lon_vel", C.c_double), ("max_lat_vel", C.c_double), ("max_ang_vel", C.c_double),
+        ("cost_w_energy", C.c_float), ("cost_w_time", C.c_float), ("cost_w_risk", C.c_float),
+        ("risk_threshold", C.c_float), ("device", C.c_int)]
+
+
+class ArtpStats(C.Structure):
+    _fields_ = [("poses_checked", C.c_uint64), ("poses_deferred", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("last_deferred", C.c_uint32), ("last_launches", C.c_uint32)]
+
+
+_lib = None
+
+
+def load():
+    """Load libartp.so (raises if it is missing: build it with art_planner_b200.build.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} not built; run `python -m art_planner_b200.build` (needs nvcc)")
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, i32, dbl = C.c_void_p, C.c_size_t, C.c_int, C.c_double
+    lib.artp_create.argtypes = [C.POINTER(ArtpParams), C.POINTER(vp)]
+    lib.artp_destroy.argtypes = [vp]
+    lib.artp_destroy.restype = None
+    lib.artp_last_error.argtypes = [vp]
+    lib.artp_last_error.restype = C.c_char_p
+    lib.artp_set_map.argtypes = [vp, vp, vp, i32, i32, dbl, dbl, dbl]
+    lib.artp_has_map.argtypes = [vp]
+    lib.artp_check_poses.argtypes = [vp, vp, sz, vp]
+    lib.artp_check_poses_device.argtypes = [vp, vp, sz, vp, vp]
+    lib.artp_check_motions.argtypes = [vp, vp, vp, sz, i32, vp]
+    lib.artp_check_motions_device.argtypes = [vp, vp, vp, sz, i32, vp, vp]
+    lib.artp_path_length_cost.argtypes = [vp, vp, vp, sz, vp]
+    lib.artp_path_length_cost_device.argtypes = [vp, vp, vp, sz, vp, vp]
+    lib.artp_compact_valid_device.argtypes = [vp, vp, sz, C.c_int64, vp, vp, vp]
+    lib.artp_get_stats.argtypes = [vp, C.POINTER(ArtpStats)]
+    lib.artp_set_mode.argtypes = [vp, i32]
+    lib.artp_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def make_params(rp, device: int = 0, cost_weights=(0.0, 1.0, 5.0), risk_threshold=0.5) -> ArtpParams:
+    p = ArtpParams()
+    for name in ("torso_length", "torso_width", "torso_height", "torso_off_x", "torso_off_y", "torso_off_z",
+                 "feet_off_x", "feet_off_y", "feet_off_z", "reach_x", "reach_y", "reach_z",
+                 "max_lon_vel", "max_lat_vel", "max_ang_vel"):
+        setattr(p, name, float(getattr(rp, name)))
+    p.unknown_space_untraversable = int(rp.unknown_space_untraversable)
+    p.use_directional_cost = int(rp.use_directional_cost)
+    p.cost_w_energy, p.cost_w_time, p.cost_w_risk = [float(x) for x in cost_weights]
+    p.risk_threshold = float(risk_threshold)
+    p.device = int(device)
+    return p

@@ -1,0 +1,205 @@
+"""Host-side mirror of the reference's plugin interface for the hot path, over the C ABI (include/artp.h).
+
+Names, argument meaning and error behaviour follow the reference:
+  StateValidityChecker   art_planner/include/art_planner/validity_checker/validity_checker.h:21-39
+                         (setMap / updateHeightField / hasMap / isValid); installed by Planner
+                         (art_planner/src/planner.cpp:125-127,162)
+  MotionValidator        ompl::base::MotionValidator::checkMotion as used at
+                         art_planner/src/planners/prm_motion_cost.cpp:652 (OMPL DiscreteMotionValidator)
+  PathLengthObjective    art_planner/src/objectives/path_length_objective.cpp:26-70
+A state is 7 doubles (x y z qx qy qz qw), the SE3StateSpace::StateType fields the reference reads
+(art_planner/include/art_planner/utils.h:25-38). Batches are [n, 7] float64 arrays; numpy arrays go through
+the host-buffer entry points (H2D/D2H inside), CUDA torch tensors through the *_device entry points on
+torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+def _is_torch_cuda(x) -> bool:
+    return hasattr(x, "is_cuda") and bool(x.is_cuda)
+
+
+class _Handle:
+    """Owns one artp_handle (one CUDA device)."""
+
+    def __init__(self, robot_params, device: int = 0, cost_weights=(0.0, 1.0, 5.0), risk_threshold=0.5):
+        self.lib = capi.load()
+        self.params = robot_params
+        self.device = device
+        p = capi.make_params(robot_params, device, cost_weights, risk_threshold)
+        h = C.c_void_p()
+        rc = self.lib.artp_create(C.byref(p), C.byref(h))
+        if rc != 0:
+            raise capi.ArtpError(rc, self.lib.artp_last_error(None).decode())
+        self.h = h
+
+    def check(self, rc: int) -> None:
+        if rc != 0:
+            raise capi.ArtpError(rc, self.lib.artp_last_error(self.h).decode())
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.artp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self) -> dict:
+        s = capi.ArtpStats()
+        self.check(self.lib.artp_get_stats(self.h, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in capi.ArtpStats._fields_}
+
+
+def _stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class StateValidityChecker:
+    """art_planner::StateValidityChecker on the GPU (validity_checker.cpp:9-45)."""
+
+    def __init__(self, params, device: int = 0, handle: _Handle | None = None):
+        self._h = handle or _Handle(params, device)
+        self._map = None
+
+    # -- reference interface ------------------------------------------------------------------
+    def setMap(self, synth_map) -> None:             # validity_checker.cpp:20-23
+        self._map = synth_map
+
+    def updateHeightField(self) -> None:             # validity_checker.cpp:27-31 -> setHeightField
+        if self._map is None:
+            raise capi.ArtpError(capi.ARTP_E_NOMAP, "setMap() was not called")
+        m = self._map
+        e = np.asfortranarray(m.elevation, dtype=np.float32)
+        k = np.asfortranarray(m.elevation_masked, dtype=np.float32)
+        if e.shape != k.shape:
+            raise capi.ArtpError(capi.ARTP_E_INVALID, "layer shapes differ")
+        self._h.check(self._h.lib.artp_set_map(self._h.h, e.ctypes.data, k.ctypes.data, e.shape[0], e.shape[1],
+                                               float(m.res), float(m.cx), float(m.cy)))
+
+    def hasMap(self) -> bool:                        # validity_checker.cpp:33-35
+        return bool(self._h.lib.artp_has_map(self._h.h))
+
+    def isValid(self, state) -> bool:                # validity_checker.cpp:39-45 (batch of 1: latency path)
+        s = np.ascontiguousarray(state, dtype=np.float64).reshape(1, 7)
+        return bool(self.isValidBatch(s)[0])
+
+    # -- batched entry points -----------------------------------------------------------------
+    def isValidBatch(self, states, out=None):
+        """states [n, 7] float64 (numpy or CUDA torch tensor) -> uint8 mask of the same kind."""
+        lib, h = self._h.lib, self._h
+        if _is_torch_cuda(states):
+            import torch
+            assert states.dtype == torch.float64 and states.is_contiguous() and states.shape[-1] == 7
+            n = states.shape[0]
+            if out is None:
+                out = torch.empty(n, dtype=torch.uint8, device=states.device)
+            h.check(lib.artp_check_poses_device(h.h, C.c_void_p(states.data_ptr()), n, C.c_void_p(out.data_ptr()),
+                                                _stream_ptr()))
+            return out
+        s = np.ascontiguousarray(states, dtype=np.float64)
+        assert s.ndim == 2 and s.shape[1] == 7
+        n = s.shape[0]
+        if out is None:
+            out = np.empty(n, dtype=np.uint8)
+        h.check(lib.artp_check_poses(h.h, s.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def isValidHostPtr(self, states_ptr: int, n: int, valid_ptr: int) -> None:
+        """Raw host pointers (e.g. pinned torch tensors): the exact call an OMPL adapter makes."""
+        self._h.check(self._h.lib.artp_check_poses(self._h.h, C.c_void_p(states_ptr), n, C.c_void_p(valid_ptr)))
+
+    def compactValid(self, valid, base: int = 0):
+        """Ordered indices (int64, base + i) of the non-zero entries of a CUDA uint8 mask; returns (indices, count)
+        as CUDA tensors -- the payload of the multi-GPU index all-gather."""
+        import torch
+        n = valid.shape[0]
+        idx = torch.empty(n, dtype=torch.int64, device=valid.device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=valid.device)
+        self._h.check(self._h.lib.artp_compact_valid_device(self._h.h, C.c_void_p(valid.data_ptr()), n, int(base),
+                                                            C.c_void_p(idx.data_ptr()), C.c_void_p(cnt.data_ptr()),
+                                                            _stream_ptr()))
+        return idx, cnt
+
+    def setMode(self, mode: int) -> None:
+        self._h.check(self._h.lib.artp_set_mode(self._h.h, int(mode)))
+
+    def stats(self) -> dict:
+        return self._h.stats()
+
+    @property
+    def handle(self) -> _Handle:
+        return self._h
+
+
+class MotionValidator:
+    """Discrete motion validation over StateValidityChecker (OMPL DiscreteMotionValidator semantics with a fixed
+    segment count): valid(s2) and valid(interpolate(s1, s2, j/(n_steps+1))) for j = 1..n_steps."""
+
+    def __init__(self, checker: StateValidityChecker, n_steps: int = 20):
+        self._c = checker
+        self.n_steps = int(n_steps)
+
+    def checkMotion(self, s1, s2) -> bool:
+        a = np.ascontiguousarray(s1, dtype=np.float64).reshape(1, 7)
+        b = np.ascontiguousarray(s2, dtype=np.float64).reshape(1, 7)
+        return bool(self.checkMotionBatch(a, b)[0])
+
+    def checkMotionBatch(self, s1, s2, out=None):
+        h, lib = self._c.handle, self._c.handle.lib
+        if _is_torch_cuda(s1):
+            import torch
+            assert s1.dtype == torch.float64 and s2.dtype == torch.float64 and s1.is_contiguous() and s2.is_contiguous()
+            n = s1.shape[0]
+            if out is None:
+                out = torch.empty(n, dtype=torch.uint8, device=s1.device)
+            h.check(lib.artp_check_motions_device(h.h, C.c_void_p(s1.data_ptr()), C.c_void_p(s2.data_ptr()), n,
+                                                  self.n_steps, C.c_void_p(out.data_ptr()), _stream_ptr()))
+            return out
+        a = np.ascontiguousarray(s1, dtype=np.float64)
+        b = np.ascontiguousarray(s2, dtype=np.float64)
+        n = a.shape[0]
+        if out is None:
+            out = np.empty(n, dtype=np.uint8)
+        h.check(lib.artp_check_motions(h.h, a.ctypes.data, b.ctypes.data, n, self.n_steps, out.ctypes.data))
+        return out
+
+
+class PathLengthObjective:
+    """art_planner::PathLengthObjective::motionCost (path_length_objective.cpp:26-70), batched."""
+
+    def __init__(self, checker: StateValidityChecker):
+        self._c = checker
+
+    def motionCost(self, s1, s2) -> float:
+        a = np.ascontiguousarray(s1, dtype=np.float64).reshape(1, 7)
+        b = np.ascontiguousarray(s2, dtype=np.float64).reshape(1, 7)
+        return float(self.motionCostBatch(a, b)[0])
+
+    def motionCostBatch(self, s1, s2, out=None):
+        h, lib = self._c.handle, self._c.handle.lib
+        if _is_torch_cuda(s1):
+            import torch
+            n = s1.shape[0]
+            if out is None:
+                out = torch.empty(n, dtype=torch.float64, device=s1.device)
+            h.check(lib.artp_path_length_cost_device(h.h, C.c_void_p(s1.data_ptr()), C.c_void_p(s2.data_ptr()), n,
+                                                     C.c_void_p(out.data_ptr()), _stream_ptr()))
+            return out
+        a = np.ascontiguousarray(s1, dtype=np.float64)
+        b = np.ascontiguousarray(s2, dtype=np.float64)
+        n = a.shape[0]
+        if out is None:
+            out = np.empty(n, dtype=np.float64)
+        h.check(lib.artp_path_length_cost(h.h, a.ctypes.data, b.ctypes.data, n, out.ctypes.data))
+        return out

@@ -1,0 +1,507 @@
+// art_planner_b200/csrc/artp_capi.cu -- C ABI (include/artp.h) over the sm_100a kernels.
+// Host side mirrors the reference's checker objects: artp_create ~ StateValidityChecker ctor,
+// artp_set_map ~ setMap + updateHeightField (HeightMapBoxChecker::setHeightField,
+// art_planner/src/validity_checker/height_map_box_checker.cpp:38-54), artp_check_* ~ isValid / checkMotion.
+// No CPU fallback: every entry point fails with ARTP_E_CUDA if the device or the kernel image is unusable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/artp.h"
+#include "artp_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Handle {
+  artp_params p;
+  int device = 0;
+  int sm_count = 0;
+  artp::Checker chk;
+  float* d_H[2] = {nullptr, nullptr};
+  int rows = 0, cols = 0;
+  bool has_map = false;
+  uint32_t* d_ctr = nullptr;        // [0] work counter, [1] defer count, [2] K2 overflow, [3] compaction total
+  uint32_t* d_defer = nullptr;      // deferred item list
+  size_t defer_cap = 0;
+  uint32_t* d_block_counts = nullptr;
+  size_t block_counts_cap = 0;
+  void* d_stage = nullptr;          // device staging for the host-buffer API
+  size_t stage_cap = 0;
+  cudaStream_t stream = nullptr;    // internal stream for the host-buffer API
+  int k1_grid = 0, k2_grid = 0, k2_smem = 0, k2_tcap = 0;
+  int mode = 0;
+  artp_stats stats{};
+  std::string err;
+  std::mutex mtx;
+};
+
+#define CU_TRY(h, expr)                                                                          \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                             \
+      return ARTP_E_CUDA;                                                                        \
+    }                                                                                            \
+  } while (0)
+
+// H[x + z*nx] = layer[x + (nz-1-z)*nx] (+0.0f canonicalises -0 like GetHeight's (h*scale)+offset,
+// ode/ode/src/heightfield.cpp:383).
+__global__ void reverse_columns_kernel(const float* __restrict__ layer, float* __restrict__ H, int nx, int nz) {
+  const size_t total = (size_t)nx * nz;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int z = (int)(i / nx), x = (int)(i - (size_t)z * nx);
+    H[i] = layer[x + (size_t)(nz - 1 - z) * nx] * 1.0f + 0.0f;
+  }
+}
+
+__global__ void fill_u8_kernel(uint8_t* p, size_t n, uint8_t v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// PathLengthObjective::motionCost (art_planner/src/objectives/path_length_objective.cpp:26-70), double.
+__global__ void path_length_kernel(const double* __restrict__ s1, const double* __restrict__ s2, size_t n,
+                                   double* __restrict__ cost, int directional, double v_lon, double v_lat,
+                                   double v_ang) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double* a = s1 + 7 * i;
+    const double* b = s2 + 7 * i;
+    const double x_dif = b[0] - a[0], y_dif = b[1] - a[1], z_dif = b[2] - a[2];
+    if (!directional) {
+      cost[i] = sqrt(x_dif * x_dif + y_dif * y_dif + z_dif * z_dif) / v_lon;
+      continue;
+    }
+    // getYawFromSO3 returns `Scalar` = float (utils.h:80-88)
+    const double yaw1 = (double)(float)atan2(2 * (a[6] * a[5] + a[3] * a[4]), 1 - 2 * (a[4] * a[4] + a[5] * a[5]));
+    const double yaw2 = (double)(float)atan2(2 * (b[6] * b[5] + b[3] * b[4]), 1 - 2 * (b[4] * b[4] + b[5] * b[5]));
+    const double d = fabs(yaw1 - yaw2);
+    const double yaw_dif = (d > 3.14159265358979323846) ? 2.0 * 3.14159265358979323846 - d : d;
+    const double lon_dif = cos(yaw1) * x_dif + sin(yaw1) * y_dif;
+    const double lat_dif = -sin(yaw1) * x_dif + cos(yaw1) * y_dif;
+    const double t_yaw = fabs(yaw_dif) / v_ang, t_lon = fabs(lon_dif) / v_lon, t_lat = fabs(lat_dif) / v_lat;
+    const double m = t_lon > t_lat ? t_lon : t_lat;
+    cost[i] = m > t_yaw ? m : t_yaw;
+  }
+}
+
+// Ordered compaction: (A) per-block counts, (B) single-block exclusive scan, (C) scatter.
+constexpr int kCompactBlock = 1024;
+__global__ void compact_count_kernel(const uint8_t* __restrict__ valid, size_t n, uint32_t* __restrict__ counts) {
+  const size_t i = (size_t)blockIdx.x * kCompactBlock + threadIdx.x;
+  const int v = (i < n) && valid[i] != 0;
+  const int c = __syncthreads_count(v);
+  if (threadIdx.x == 0) counts[blockIdx.x] = (uint32_t)c;
+}
+__global__ void compact_scan_kernel(uint32_t* counts, size_t nb, uint32_t* total) {
+  __shared__ uint32_t carry;
+  __shared__ uint32_t wsum[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (size_t b0 = 0; b0 < nb; b0 += blockDim.x) {
+    const size_t i = b0 + threadIdx.x;
+    const uint32_t v = i < nb ? counts[i] : 0u;
+    uint32_t x = v;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t s = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0u;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+      wsum[lane] = s;
+    }
+    __syncthreads();
+    const uint32_t before = carry + (wid ? wsum[wid - 1] : 0u) + x - v;
+    if (i < nb) counts[i] = before;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = before + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+__global__ void compact_scatter_kernel(const uint8_t* __restrict__ valid, size_t n, int64_t base,
+                                       const uint32_t* __restrict__ offsets, int64_t* __restrict__ out) {
+  __shared__ uint32_t wsum[32];
+  const size_t i = (size_t)blockIdx.x * kCompactBlock + threadIdx.x;
+  const int v = (i < n) && valid[i] != 0;
+  const unsigned bal = __ballot_sync(0xffffffffu, v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) wsum[wid] = __popc(bal);
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t s = wsum[lane];
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+    wsum[lane] = s;
+  }
+  __syncthreads();
+  if (v) {
+    const uint32_t pos = offsets[blockIdx.x] + (wid ? wsum[wid - 1] : 0u) + __popc(bal & ((1u << lane) - 1u));
+    out[pos] = base + (int64_t)i;
+  }
+}
+
+int ensure_defer(Handle* h, size_t n_items, cudaStream_t s) {
+  if (h->defer_cap >= n_items) return ARTP_OK;
+  CU_TRY(h, cudaStreamSynchronize(s));
+  if (h->d_defer) CU_TRY(h, cudaFree(h->d_defer));
+  h->d_defer = nullptr;
+  const size_t cap = std::max<size_t>(n_items, 1u << 16);
+  CU_TRY(h, cudaMalloc(&h->d_defer, cap * sizeof(uint32_t)));
+  h->defer_cap = cap;
+  return ARTP_OK;
+}
+
+int ensure_stage(Handle* h, size_t bytes) {
+  if (h->stage_cap >= bytes) return ARTP_OK;
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->d_stage) CU_TRY(h, cudaFree(h->d_stage));
+  h->d_stage = nullptr;
+  CU_TRY(h, cudaMalloc(&h->d_stage, bytes));
+  h->stage_cap = bytes;
+  return ARTP_OK;
+}
+
+// Launch K1 (+K2) for a prepared Work on stream s.
+int run_items(Handle* h, const artp::Work& w, cudaStream_t s) {
+  int rc = ensure_defer(h, w.n_items, s);
+  if (rc) return rc;
+  CU_TRY(h, cudaMemsetAsync(h->d_ctr, 0, 3 * sizeof(uint32_t), s));
+  artp::check_items_warp_kernel<<<h->k1_grid, artp::kWarpsPerCta * 32, 0, s>>>(h->chk, w, h->d_ctr, h->d_ctr + 1,
+                                                                                h->d_defer, h->mode == 1);
+  CU_TRY(h, cudaGetLastError());
+  artp::check_items_block_kernel<<<h->k2_grid, 256, h->k2_smem, s>>>(h->chk, w, h->d_ctr + 1, h->d_defer, h->k2_tcap,
+                                                                      h->d_ctr + 2);
+  CU_TRY(h, cudaGetLastError());
+  h->stats.kernel_launches += 2;
+  h->stats.last_launches = 2;
+  return ARTP_OK;
+}
+
+int check_common(Handle* h, size_t n) {
+  if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
+  if (n >= (size_t)0xFFFFFFF0u) { h->err = "too many items for one call"; return ARTP_E_LIMIT; }
+  return ARTP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* artp_version(void) { return "artp 0.1 sm_100a"; }
+
+const char* artp_last_error(const artp_handle* hh) {
+  if (!hh) return g_create_error.c_str();
+  return reinterpret_cast<const Handle*>(hh)->err.c_str();
+}
+
+int artp_create(const artp_params* params, artp_handle** out) {
+  if (!params || !out) { g_create_error = "null argument"; return ARTP_E_INVALID; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    return ARTP_E_CUDA;
+  }
+  if (params->device < 0 || params->device >= ndev) { g_create_error = "bad device ordinal"; return ARTP_E_INVALID; }
+  if (!(params->torso_length > 0 && params->torso_width > 0 && params->torso_height > 0 && params->reach_x > 0 &&
+        params->reach_y > 0 && params->reach_z > 0)) {
+    g_create_error = "box dimensions must be positive";
+    return ARTP_E_INVALID;
+  }
+  Handle* h = new Handle();
+  h->p = *params;
+  h->device = params->device;
+  auto fail = [&](const char* what, cudaError_t ce) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+    delete h;
+    return ARTP_E_CUDA;
+  };
+  if ((e = cudaSetDevice(h->device)) != cudaSuccess) return fail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, h->device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+  h->sm_count = prop.multiProcessorCount;
+  cudaFuncAttributes fa;
+  if ((e = cudaFuncGetAttributes(&fa, artp::check_items_warp_kernel)) != cudaSuccess)
+    return fail("no usable kernel image (built for sm_100a)", e);
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaMalloc(&h->d_ctr, 8 * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc", e);
+  int per_sm = 0;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, artp::check_items_warp_kernel,
+                                                         artp::kWarpsPerCta * 32, 0)) != cudaSuccess)
+    return fail("occupancy", e);
+  h->k1_grid = h->sm_count * std::max(per_sm, 1);
+  // checker constants (float casts as the reference's ctor/Pose3FromXYZ arguments make them)
+  artp::Checker& c = h->chk;
+  std::memset(&c, 0, sizeof(c));
+  c.side[0][0] = (float)params->torso_length; c.side[0][1] = (float)params->torso_width; c.side[0][2] = (float)params->torso_height;
+  c.side[1][0] = (float)params->reach_x; c.side[1][1] = (float)params->reach_y; c.side[1][2] = (float)params->reach_z;
+  c.torso_off[0] = (float)params->torso_off_x; c.torso_off[1] = (float)params->torso_off_y;
+  c.torso_off[2] = (float)(params->torso_off_z - params->feet_off_z);
+  c.feet_ox = (float)params->feet_off_x; c.feet_oy = (float)params->feet_off_y;
+  c.unknown_untraversable = params->unknown_space_untraversable ? 1 : 0;
+  *out = reinterpret_cast<artp_handle*>(h);
+  return ARTP_OK;
+}
+
+void artp_destroy(artp_handle* hh) {
+  if (!hh) return;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  cudaSetDevice(h->device);
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  cudaFree(h->d_H[0]); cudaFree(h->d_H[1]); cudaFree(h->d_ctr); cudaFree(h->d_defer); cudaFree(h->d_stage);
+  cudaFree(h->d_block_counts);
+  delete h;
+}
+
+int artp_has_map(const artp_handle* hh) { return hh && reinterpret_cast<const Handle*>(hh)->has_map ? 1 : 0; }
+
+int artp_set_mode(artp_handle* hh, int mode) {
+  if (!hh || mode < 0 || mode > 1) return ARTP_E_INVALID;
+  reinterpret_cast<Handle*>(hh)->mode = mode;
+  return ARTP_OK;
+}
+
+int artp_get_stats(artp_handle* hh, artp_stats* out) {
+  if (!hh || !out) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  CU_TRY(h, cudaSetDevice(h->device));
+  uint32_t ctr[3] = {0, 0, 0};
+  CU_TRY(h, cudaMemcpy(ctr, h->d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost));   // synchronises the device
+  h->stats.last_deferred = ctr[1];
+  *out = h->stats;
+  if (ctr[2] != 0) { h->err = "plane-grouping kernel overflow (zone larger than its shared-memory store)"; return ARTP_E_LIMIT; }
+  return ARTP_OK;
+}
+
+int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation_masked, int rows, int cols, double res,
+                 double cx, double cy) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (!elevation || !elevation_masked || rows < 2 || cols < 2 || !(res > 0)) { h->err = "bad map arguments"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  const size_t ncell = (size_t)rows * cols;
+  // geometry exactly as dxHeightfieldData::SetData computes it in fp32 (heightfield.cpp:130-169)
+  const double Lx = rows * res, Ly = cols * res;   // grid_map: length = size * resolution
+  artp::Field f;
+  f.nx = rows; f.nz = cols;
+  f.W = (float)Lx; f.D = (float)Ly;
+  f.hW = f.W / 2.0f; f.hD = f.D / 2.0f;
+  f.sW = f.W / (f.nx - 1.0f);
+  f.sD = f.D / (f.nz - 1.0f);
+  f.asp = f.sD / f.sW;
+  f.iW = 1.0f / f.sW;
+  f.iD = 1.0f / f.sD;
+  f.px = (float)cx; f.py = (float)cy;
+  // K2 shared-memory plane store: bound the zone of either box by its half-diagonal
+  int tcap = 0;
+  for (int k = 0; k < 2; ++k) {
+    const float* sd = h->chk.side[k];
+    const double r = 0.5 * std::sqrt((double)sd[0] * sd[0] + (double)sd[1] * sd[1] + (double)sd[2] * sd[2]);
+    const int nxm = std::min(rows, (int)std::ceil(2.0 * r * f.iW) + 4), nzm = std::min(cols, (int)std::ceil(2.0 * r * f.iD) + 4);
+    tcap = std::max(tcap, 2 * (nxm - 1) * (nzm - 1));
+  }
+  tcap = (tcap + 3) & ~3;
+  const int smem = tcap * 21 + 64;
+  if (smem > 200 * 1024) {
+    h->err = "box/map resolution combination exceeds the plane-grouping kernel's shared-memory store";
+    return ARTP_E_LIMIT;
+  }
+  CU_TRY(h, cudaFuncSetAttribute(artp::check_items_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int per_sm = 0;
+  CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, artp::check_items_block_kernel, 256, smem));
+  h->k2_smem = smem; h->k2_tcap = tcap; h->k2_grid = h->sm_count * std::max(per_sm, 1);
+  // upload
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->rows != rows || h->cols != cols) {
+    cudaFree(h->d_H[0]); cudaFree(h->d_H[1]);
+    h->d_H[0] = h->d_H[1] = nullptr;
+    CU_TRY(h, cudaMalloc(&h->d_H[0], ncell * sizeof(float)));
+    CU_TRY(h, cudaMalloc(&h->d_H[1], ncell * sizeof(float)));
+  }
+  int rc = ensure_stage(h, ncell * sizeof(float));
+  if (rc) return rc;
+  const float* src[2] = {elevation, elevation_masked};
+  for (int k = 0; k < 2; ++k) {
+    CU_TRY(h, cudaMemcpyAsync(h->d_stage, src[k], ncell * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    reverse_columns_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>((const float*)h->d_stage, h->d_H[k], rows, cols);
+    CU_TRY(h, cudaGetLastError());
+  }
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->stats.kernel_launches += 2;
+  h->rows = rows; h->cols = cols;
+  f.H = h->d_H[0]; h->chk.f[0] = f;
+  f.H = h->d_H[1]; h->chk.f[1] = f;
+  h->chk.Lx = Lx; h->chk.Ly = Ly; h->chk.cx = cx; h->chk.cy = cy;
+  h->chk.cell_margin = 0.02f + 2e-6f * (float)std::max(rows, cols);
+  h->has_map = true;
+  return ARTP_OK;
+}
+
+int artp_check_poses_device(artp_handle* hh, const double* d_states, size_t n, uint8_t* d_valid, void* stream) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  int rc = check_common(h, n);
+  if (rc) return rc;
+  if (n == 0) return ARTP_OK;
+  if (!d_states || !d_valid) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  artp::Work w;
+  w.s1 = nullptr; w.s2 = d_states; w.valid = d_valid; w.n_items = (uint32_t)n; w.steps = 0; w.edge_mode = 0;
+  rc = run_items(h, w, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->stats.poses_checked += n;
+  return ARTP_OK;
+}
+
+int artp_check_poses(artp_handle* hh, const double* states, size_t n, uint8_t* valid) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  {
+    std::lock_guard<std::mutex> lk(h->mtx);
+    int rc = check_common(h, n);
+    if (rc) return rc;
+    if (n == 0) return ARTP_OK;
+    if (!states || !valid) { h->err = "null buffer"; return ARTP_E_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t in_bytes = n * 7 * sizeof(double), out_off = (in_bytes + 255) & ~(size_t)255;
+    rc = ensure_stage(h, out_off + n);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(h->d_stage, states, in_bytes, cudaMemcpyHostToDevice, h->stream));
+  }
+  double* d_states = (double*)h->d_stage;
+  uint8_t* d_valid = (uint8_t*)h->d_stage + ((n * 7 * sizeof(double) + 255) & ~(size_t)255);
+  int rc = artp_check_poses_device(hh, d_states, n, d_valid, h->stream);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(h->mtx);
+  CU_TRY(h, cudaMemcpyAsync(valid, d_valid, n, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return ARTP_OK;
+}
+
+int artp_check_motions_device(artp_handle* hh, const double* d_s1, const double* d_s2, size_t n, int n_steps,
+                              uint8_t* d_valid, void* stream) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (n_steps < 0) { h->err = "n_steps < 0"; return ARTP_E_INVALID; }
+  const size_t items = n * ((size_t)n_steps + 1);
+  int rc = check_common(h, items);
+  if (rc) return rc;
+  if (n == 0) return ARTP_OK;
+  if (!d_s1 || !d_s2 || !d_valid) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  fill_u8_kernel<<<std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 8), 256, 0, s>>>(d_valid, n, 1);
+  CU_TRY(h, cudaGetLastError());
+  artp::Work w;
+  w.s1 = d_s1; w.s2 = d_s2; w.valid = d_valid; w.n_items = (uint32_t)items; w.steps = n_steps; w.edge_mode = 1;
+  rc = run_items(h, w, s);
+  if (rc) return rc;
+  h->stats.kernel_launches += 1;
+  h->stats.last_launches += 1;
+  h->stats.poses_checked += items;
+  return ARTP_OK;
+}
+
+int artp_check_motions(artp_handle* hh, const double* s1, const double* s2, size_t n, int n_steps, uint8_t* valid) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  const size_t sb = n * 7 * sizeof(double), sb_al = (sb + 255) & ~(size_t)255;
+  {
+    std::lock_guard<std::mutex> lk(h->mtx);
+    if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
+    if (n == 0) return ARTP_OK;
+    if (!s1 || !s2 || !valid) { h->err = "null buffer"; return ARTP_E_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_stage(h, 2 * sb_al + n);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(h->d_stage, s1, sb, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync((char*)h->d_stage + sb_al, s2, sb, cudaMemcpyHostToDevice, h->stream));
+  }
+  uint8_t* d_valid = (uint8_t*)h->d_stage + 2 * sb_al;
+  int rc = artp_check_motions_device(hh, (const double*)h->d_stage, (const double*)((char*)h->d_stage + sb_al), n, n_steps,
+                                     d_valid, h->stream);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(h->mtx);
+  CU_TRY(h, cudaMemcpyAsync(valid, d_valid, n, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return ARTP_OK;
+}
+
+int artp_path_length_cost_device(artp_handle* hh, const double* d_s1, const double* d_s2, size_t n, double* d_cost,
+                                 void* stream) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (n == 0) return ARTP_OK;
+  if (!d_s1 || !d_s2 || !d_cost) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  path_length_kernel<<<std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 8), 256, 0, (cudaStream_t)stream>>>(
+      d_s1, d_s2, n, d_cost, h->p.use_directional_cost, h->p.max_lon_vel, h->p.max_lat_vel, h->p.max_ang_vel);
+  CU_TRY(h, cudaGetLastError());
+  h->stats.kernel_launches += 1;
+  h->stats.last_launches = 1;
+  return ARTP_OK;
+}
+
+int artp_path_length_cost(artp_handle* hh, const double* s1, const double* s2, size_t n, double* cost) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  const size_t sb = n * 7 * sizeof(double), sb_al = (sb + 255) & ~(size_t)255;
+  {
+    std::lock_guard<std::mutex> lk(h->mtx);
+    if (n == 0) return ARTP_OK;
+    if (!s1 || !s2 || !cost) { h->err = "null buffer"; return ARTP_E_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_stage(h, 2 * sb_al + n * sizeof(double));
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(h->d_stage, s1, sb, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync((char*)h->d_stage + sb_al, s2, sb, cudaMemcpyHostToDevice, h->stream));
+  }
+  double* d_cost = (double*)((char*)h->d_stage + 2 * sb_al);
+  int rc = artp_path_length_cost_device(hh, (const double*)h->d_stage, (const double*)((char*)h->d_stage + sb_al), n, d_cost,
+                                        h->stream);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(h->mtx);
+  CU_TRY(h, cudaMemcpyAsync(cost, d_cost, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return ARTP_OK;
+}
+
+int artp_compact_valid_device(artp_handle* hh, const uint8_t* d_valid, size_t n, int64_t base, int64_t* d_indices,
+                              uint32_t* d_count, void* stream) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (!d_valid || !d_indices || !d_count) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n == 0) { CU_TRY(h, cudaMemsetAsync(d_count, 0, sizeof(uint32_t), s)); return ARTP_OK; }
+  const size_t nb = (n + kCompactBlock - 1) / kCompactBlock;
+  if (h->block_counts_cap < nb) {
+    CU_TRY(h, cudaStreamSynchronize(s));
+    cudaFree(h->d_block_counts);
+    h->d_block_counts = nullptr;
+    CU_TRY(h, cudaMalloc(&h->d_block_counts, nb * sizeof(uint32_t)));
+    h->block_counts_cap = nb;
+  }
+  compact_count_kernel<<<(unsigned)nb, kCompactBlock, 0, s>>>(d_valid, n, h->d_block_counts);
+  compact_scan_kernel<<<1, 1024, 0, s>>>(h->d_block_counts, nb, d_count);
+  compact_scatter_kernel<<<(unsigned)nb, kCompactBlock, 0, s>>>(d_valid, n, base, h->d_block_counts, d_indices);
+  CU_TRY(h, cudaGetLastError());
+  h->stats.kernel_launches += 3;
+  h->stats.last_launches = 3;
+  return ARTP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,561 @@
+// art_planner_b200/csrc/artp_kernels.cuh
+// Pose-validity kernels (StateValidityChecker::isValid, validity_checker.cpp:39-45, on top of the ODE
+// box-vs-heightfield decision, heightfield.cpp:973-1964) for sm_100a.
+//
+//   K1  check_items_warp_kernel   one warp per work item (pose / interpolated edge state). Lanes stride the
+//       heightfield zone with coalesced fp32 loads, min/max/finite by warp shuffles, vertex-in-box and
+//       plane tests decided by warp ballots. The reference's O(T^2) plane grouping is replaced by an exact
+//       shortcut: only triangles under one of the 8 box corners can ever own a plane-contact point, so only
+//       those "candidate" planes are built; a bloom filter on the (approximate) normal finds any earlier
+//       triangle that could epsilon-merge with a live candidate. If none exists every candidate is its own
+//       group base (exact); otherwise the item is deferred to K2.
+//   K2  check_items_block_kernel  one CTA per deferred item: the full decision including the reference's
+//       greedy, order-dependent epsilon grouping, with all planes staged in shared memory.
+// Both are bit-exact against oracle/ (tests/test_pose_gpu.py).
+#pragma once
+
+#include "artp_device.cuh"
+
+namespace artp {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kMaxCand = 64;          // 32 lanes x (Up, Down)
+constexpr int kBloomWords = 64;       // 2048-bit filter per warp
+constexpr unsigned kFull = 0xffffffffu;
+
+enum { R_FREE = 0, R_HIT = 1, R_DEFER = 2 };
+
+struct WarpScratch {
+  float cpl[kMaxCand][4];   // candidate planes (exact)
+  int cidx[kMaxCand];       // emission index of a LIVE candidate, -1 otherwise
+  uint32_t bloom[kBloomWords];
+};
+
+// Work description shared by K1/K2. EDGE mode: item w -> edge e = w / (steps+1), j = w % (steps+1);
+// j == 0 checks s2, j >= 1 checks interp(s1, s2, j/(steps+1)) (OMPL SE3 interpolation).
+struct Work {
+  const double* s1;     // EDGE: start states; POSE: unused
+  const double* s2;     // EDGE: end states;   POSE: the states
+  uint8_t* valid;       // per pose / per edge
+  uint32_t n_items;
+  int steps;            // EDGE: interior steps; POSE: 0
+  int edge_mode;
+};
+
+__device__ __forceinline__ uint32_t bloom_hash(int kx, int kz) {
+  return (((uint32_t)kx * 0x9E3779B1u) ^ ((uint32_t)kz * 0x85EBCA77u)) >> 21;   // 11 bits
+}
+constexpr float kKeyScale = 16384.0f;   // bucket width 2^-14 on n0, n2 in [-1, 1]
+constexpr float kKeyMargin = 4e-6f;     // > eps + rsqrt.approx error + quantisation error
+
+// OMPL 1.4.2 SE3StateSpace::interpolate (RealVector lerp + SO3 slerp), double.
+__device__ __forceinline__ void se3_interpolate(const double* a, const double* b, double t, double* out) {
+  for (int i = 0; i < 3; ++i) out[i] = a[i] + (b[i] - a[i]) * t;
+  const double dq = a[3] * b[3] + a[4] * b[4] + a[5] * b[5] + a[6] * b[6];
+  const double dqa = fabs(dq);
+  const double theta = (dqa > 1.0 - 1e-9) ? 0.0 : acos(dqa);
+  if (theta > 2.220446049250313e-16) {
+    const double d = 1.0 / sin(theta);
+    const double s0 = sin((1.0 - t) * theta);
+    double s1 = sin(t * theta);
+    if (dq < 0) s1 = -s1;
+    out[3] = (a[3] * s0 + b[3] * s1) * d;
+    out[4] = (a[4] * s0 + b[4] * s1) * d;
+    out[5] = (a[5] * s0 + b[5] * s1) * d;
+    out[6] = (a[6] * s0 + b[6] * s1) * d;
+  } else {
+    out[3] = a[3]; out[4] = a[4]; out[5] = a[5]; out[6] = a[6];
+  }
+}
+
+__device__ __forceinline__ void load_item_state(const Work& w, uint32_t item, double s[7]) {
+  if (!w.edge_mode) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) s[k] = w.s2[(size_t)item * 7 + k];
+    return;
+  }
+  const uint32_t per = (uint32_t)w.steps + 1u;
+  const uint32_t e = item / per, j = item - e * per;
+  double b[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) b[k] = w.s2[(size_t)e * 7 + k];
+  if (j == 0) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) s[k] = b[k];
+  } else {
+    double a[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) a[k] = w.s1[(size_t)e * 7 + k];
+    se3_interpolate(a, b, (double)j / (double)per, s);
+  }
+}
+
+__device__ __forceinline__ uint32_t item_slot(const Work& w, uint32_t item) {
+  return w.edge_mode ? item / ((uint32_t)w.steps + 1u) : item;
+}
+
+// Heights of the four corners of cell (cx, cz): A(x,z) B(x+1,z) C(x,z+1) D(x+1,z+1).
+__device__ __forceinline__ void load_cell(const Field& f, int cx, int cz, float& hA, float& hB, float& hC, float& hD) {
+  const float* p = f.H + (size_t)cz * f.nx + cx;
+  hA = __ldg(p); hB = __ldg(p + 1); hC = __ldg(p + f.nx); hD = __ldg(p + f.nx + 1);
+}
+
+// Exact plane of the Up / Down triangle of cell (cx, cz).
+__device__ __forceinline__ void cell_plane(const Field& f, bool isUp, int cx, int cz, float hA, float hB, float hC,
+                                           float hD, float pl[4]) {
+  const float xA = cx * f.sW, xB = (cx + 1) * f.sW, zA = cz * f.sD, zC = (cz + 1) * f.sD;
+  if (isUp) tri_plane(true, xA, hA, zA, xB, hB, zA, xA, hC, zC, pl);     // (A, B, C)
+  else      tri_plane(false, xB, hD, zC, xB, hB, zA, xA, hC, zC, pl);    // (D, B, C)
+}
+
+// -------------------------------------------------------------------------------------------------
+// K1: warp-level box-vs-heightfield decision. Returns R_FREE / R_HIT / R_DEFER (warp-uniform).
+// -------------------------------------------------------------------------------------------------
+__device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws, int lane, float cell_margin) {
+  const int nX = b.x1 - b.x0 + 1, nZ = b.z1 - b.z0 + 1;
+  const int nV = nX * nZ;
+  const uint32_t magicX = (nX > 1) ? (0xFFFFFFFFu / (uint32_t)nX + 1u) : 0u;
+  const float* base = f.H + (size_t)b.z0 * f.nx + b.x0;
+
+  // (1) zone scan (heightfield.cpp:1002-1026)
+  float mx = -CUDART_INF_F, mn = CUDART_INF_F;
+  bool fin = true;
+  for (int t = lane; t < nV; t += 32) {
+    const int zi = (nX > 1) ? (int)__umulhi((uint32_t)t, magicX) : t;
+    const int xi = t - zi * nX;
+    const float h = __ldg(base + (size_t)zi * f.nx + xi);
+    mx = (mx > h) ? mx : h;
+    if (finitef(h)) mn = (mn > h) ? h : mn; else fin = false;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float a = __shfl_xor_sync(kFull, mx, o), c = __shfl_xor_sync(kFull, mn, o);
+    mx = (mx > a) ? mx : a;
+    mn = (mn > c) ? c : mn;
+  }
+  const bool allFinite = __all_sync(kFull, fin);
+  const float maxY = mx, minY = mn;
+
+  // (2) early outs (heightfield.cpp:1027-1064, 1139-1160)
+  if (b.minB - maxY > -ARTP_EPS) return R_FREE;                                            // above
+  if (minY - b.maxB > -ARTP_EPS) return R_FREE;                                            // under (art_planner mod)
+  if (allFinite && minY - b.minB > -ARTP_EPS && b.maxB - maxY > -ARTP_EPS) return R_HIT;   // spans
+  if (allFinite && maxY - minY < ARTP_EPS) {
+    const float pl[4] = {0.0f, 1.0f, 0.0f, minY};
+    float cx[4], cz[4];
+    return box_plane(b, pl, 1, cx, cz) > 0 ? R_HIT : R_FREE;
+  }
+  if (nX < 2 || nZ < 2) return R_FREE;   // no cell, no triangle
+
+  // (3) vertex-in-box test of every colliding vertex of a kept triangle (heightfield.cpp:1306-1441)
+  const int nCX = nX - 1, nCZ = nZ - 1, nC = nCX * nCZ;
+  const uint32_t magicC = (nCX > 1) ? (0xFFFFFFFFu / (uint32_t)nCX + 1u) : 0u;
+  if (allFinite) {
+    // every colliding vertex belongs to some kept triangle (all finite, >= 1 cell)
+    for (int t0 = 0; t0 < nV; t0 += 32) {
+      const int t = t0 + lane;
+      bool col = false;
+      float h = 0.0f;
+      int xi = 0, zi = 0;
+      if (t < nV) {
+        zi = (nX > 1) ? (int)__umulhi((uint32_t)t, magicX) : t;
+        xi = t - zi * nX;
+        h = __ldg(base + (size_t)zi * f.nx + xi);
+        col = h > b.minB;
+      }
+      if (__any_sync(kFull, col)) {
+        const bool hit = col && vertex_inside(b, (b.x0 + xi) * f.sW, h, (b.z0 + zi) * f.sD);
+        if (__any_sync(kFull, hit)) return R_HIT;
+      }
+    }
+  } else {
+    for (int t0 = 0; t0 < nC; t0 += 32) {
+      const int t = t0 + lane;
+      bool hit = false;
+      if (t < nC) {
+        const int czi = (nCX > 1) ? (int)__umulhi((uint32_t)t, magicC) : t;   // flattened, x fastest
+        const int cxi = t - czi * nCX;
+        const int cx = b.x0 + cxi, cz = b.z0 + czi;
+        float hA, hB, hC, hD;
+        load_cell(f, cx, cz, hA, hB, hC, hD);
+        const bool fA = finitef(hA), fB = finitef(hB), fC = finitef(hC), fD = finitef(hD);
+        const bool cA = fA && hA > b.minB, cB = fB && hB > b.minB, cC = fC && hC > b.minB, cD = fD && hD > b.minB;
+        const bool keepUp = (cA || cB || cC) && (fA && fB && fC);
+        const bool keepDn = (cB || cC || cD) && (fB && fC && fD);
+        const float xA = cx * f.sW, xB = (cx + 1) * f.sW, zA = cz * f.sD, zC = (cz + 1) * f.sD;
+        if (keepUp && cA) hit = hit || vertex_inside(b, xA, hA, zA);
+        if ((keepUp || keepDn) && cB) hit = hit || vertex_inside(b, xB, hB, zA);
+        if ((keepUp || keepDn) && cC) hit = hit || vertex_inside(b, xA, hC, zC);
+        if (keepDn && cD) hit = hit || vertex_inside(b, xB, hD, zC);
+      }
+      if (__any_sync(kFull, hit)) return R_HIT;
+    }
+  }
+
+  // (4) plane stage (heightfield.cpp:1474-1617). A plane contact point is always a box corner (up to a few
+  // ulps), so only triangles in the cells under the 8 corners (+- cell_margin) can report one.
+  {
+    for (int i = lane; i < kBloomWords; i += 32) ws.bloom[i] = 0u;
+    ws.cidx[2 * lane] = -1;
+    ws.cidx[2 * lane + 1] = -1;
+    __syncwarp();
+    const int corner = lane >> 2, sub = lane & 3;
+    float px = b.P[0], pz = b.P[2];
+    {
+      const float h0 = 0.5f * b.side[0], h1 = 0.5f * b.side[1], h2 = 0.5f * b.side[2];
+      if (corner & 1) { px += h0 * b.R1[0]; pz += h0 * b.R1[6]; } else { px -= h0 * b.R1[0]; pz -= h0 * b.R1[6]; }
+      if (corner & 2) { px += h1 * b.R1[1]; pz += h1 * b.R1[7]; } else { px -= h1 * b.R1[1]; pz -= h1 * b.R1[7]; }
+      if (corner & 4) { px += h2 * b.R1[2]; pz += h2 * b.R1[8]; } else { px -= h2 * b.R1[2]; pz -= h2 * b.R1[8]; }
+    }
+    const float gx = px * f.iW, gz = pz * f.iD;
+    const int cxl = (int)floorf(gx - cell_margin), cxh = (int)floorf(gx + cell_margin);
+    const int czl = (int)floorf(gz - cell_margin), czh = (int)floorf(gz + cell_margin);
+    const int ccx = (sub & 1) ? cxh : cxl, ccz = (sub & 2) ? czh : czl;
+    bool act = !((sub & 1) && cxh == cxl) && !((sub & 2) && czh == czl);
+    act = act && ccx >= b.x0 && ccx < b.x1 && ccz >= b.z0 && ccz < b.z1;
+    bool live_any = false, hit_own = false;
+    if (act) {
+      float hA, hB, hC, hD;
+      load_cell(f, ccx, ccz, hA, hB, hC, hD);
+      const bool fA = finitef(hA), fB = finitef(hB), fC = finitef(hC), fD = finitef(hD);
+      const bool cA = fA && hA > b.minB, cB = fB && hB > b.minB, cC = fC && hC > b.minB, cD = fD && hD > b.minB;
+      const bool keep[2] = {(cA || cB || cC) && (fA && fB && fC), (cB || cC || cD) && (fB && fC && fD)};
+      const int cell_idx = ((ccx - b.x0) * nCZ + (ccz - b.z0)) * 2;   // emission order: x outer, z inner, Up, Down
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!keep[u]) continue;
+        const bool isUp = (u == 0);
+        float pl[4];
+        cell_plane(f, isUp, ccx, ccz, hA, hB, hC, hD, pl);
+        // Liveness: any plane within eps of this one changes the box-plane depth by far less than tau.
+        const float Q1 = pl[0] * b.R1[0] + pl[1] * b.R1[3] + pl[2] * b.R1[6];
+        const float Q2 = pl[0] * b.R1[1] + pl[1] * b.R1[4] + pl[2] * b.R1[7];
+        const float Q3 = pl[0] * b.R1[2] + pl[1] * b.R1[5] + pl[2] * b.R1[8];
+        const float B1 = fabsf(b.side[0] * Q1), B2 = fabsf(b.side[1] * Q2), B3 = fabsf(b.side[2] * Q3);
+        const float depth = pl[3] + 0.5f * (B1 + B2 + B3) - (pl[0] * b.P[0] + pl[1] * b.P[1] + pl[2] * b.P[2]);
+        const float tau = 16.0f * ARTP_EPS * (1.0f + b.side[0] + b.side[1] + b.side[2] + fabsf(b.P[0]) +
+                                              fabsf(b.P[1]) + fabsf(b.P[2]) + fabsf(pl[3]));
+        if (!(depth >= -tau)) continue;   // dead: no plane of its would-be group can touch the box
+        live_any = true;
+        const int slot = 2 * lane + u;
+        ws.cpl[slot][0] = pl[0]; ws.cpl[slot][1] = pl[1]; ws.cpl[slot][2] = pl[2]; ws.cpl[slot][3] = pl[3];
+        ws.cidx[slot] = cell_idx + u;
+        // bloom keys of every bucket an eps-matching normal may fall into
+        const int kx0 = (int)floorf((pl[0] - kKeyMargin + 1.0f) * kKeyScale), kx1 = (int)floorf((pl[0] + kKeyMargin + 1.0f) * kKeyScale);
+        const int kz0 = (int)floorf((pl[2] - kKeyMargin + 1.0f) * kKeyScale), kz1 = (int)floorf((pl[2] + kKeyMargin + 1.0f) * kKeyScale);
+        for (int kx = kx0; kx <= kx1; ++kx)
+          for (int kz = kz0; kz <= kz1; ++kz) {
+            const uint32_t hsh = bloom_hash(kx, kz);
+            atomicOr(&ws.bloom[hsh >> 5], 1u << (hsh & 31));
+          }
+        // contact points with the triangle's OWN plane (valid if it turns out to be its group base)
+        float cx[4], cz[4];
+        const int nc = box_plane(b, pl, 4, cx, cz);
+        const int tcx = isUp ? ccx : ccx + 1, tcz = isUp ? ccz : ccz + 1;
+        for (int i = 0; i < nc; ++i) hit_own = hit_own || on_tri(f, isUp, tcx, tcz, cx[i], cz[i]);
+      }
+    }
+    if (!__any_sync(kFull, live_any)) return R_FREE;
+    __syncwarp();
+
+    // (5) is any live candidate epsilon-mergeable with an EARLIER kept triangle? (greedy grouping,
+    // heightfield.cpp:1511-1556: a triangle is absorbed only by an earlier base that matches it.)
+    bool merge = false;
+    for (int t0 = 0; t0 < nC; t0 += 32) {
+      const int t = t0 + lane;
+      if (t < nC) {
+        const int czi = (nCX > 1) ? (int)__umulhi((uint32_t)t, magicC) : t;
+        const int cxi = t - czi * nCX;
+        const int cx = b.x0 + cxi, cz = b.z0 + czi;
+        float hA, hB, hC, hD;
+        load_cell(f, cx, cz, hA, hB, hC, hD);
+        const bool fA = finitef(hA), fB = finitef(hB), fC = finitef(hC), fD = finitef(hD);
+        const bool cA = fA && hA > b.minB, cB = fB && hB > b.minB, cC = fC && hC > b.minB, cD = fD && hD > b.minB;
+        const bool keep[2] = {(cA || cB || cC) && (fA && fB && fC), (cB || cC || cD) && (fB && fC && fD)};
+        if (keep[0] || keep[1]) {
+          const float xA = cx * f.sW, xB = (cx + 1) * f.sW, zA = cz * f.sD, zC = (cz + 1) * f.sD;
+          const int cell_idx = (cxi * nCZ + czi) * 2;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (!keep[u]) continue;
+            // un-normalised normal, same formulas as tri_plane
+            float c0, c1, c2;   // value-identical to tri_plane's cross product (zero terms dropped)
+            if (u == 0) {   // Up (A,B,C): E1 = C-A = (0, hC-hA, zC-zA), E2 = B-A = (xB-xA, hB-hA, 0); c = E1 x E2
+              const float e1y = hC - hA, e1z = zC - zA, e2x = xB - xA, e2y = hB - hA;
+              c0 = -(e1z * e2y); c1 = e1z * e2x; c2 = -(e1y * e2x);
+            } else {        // Down (D,B,C): E1 = C-D = (xA-xB, hC-hD, 0), E2 = B-D = (0, hB-hD, zA-zC); c = E2 x E1
+              const float e1x = xA - xB, e1y = hC - hD, e2y = hB - hD, e2z = zA - zC;
+              c0 = -(e2z * e1y); c1 = e2z * e1x; c2 = -(e2y * e1x);
+            }
+            const float r = rsqrtf(c0 * c0 + c1 * c1 + c2 * c2);
+            const int kx = (int)floorf((c0 * r + 1.0f) * kKeyScale), kz = (int)floorf((c2 * r + 1.0f) * kKeyScale);
+            const uint32_t hsh = bloom_hash(kx, kz);
+            if (ws.bloom[hsh >> 5] & (1u << (hsh & 31))) {
+              float pl[4];
+              cell_plane(f, u == 0, cx, cz, hA, hB, hC, hD, pl);
+              const int idx = cell_idx + u;
+              for (int s = 0; s < kMaxCand; ++s) {
+                if (ws.cidx[s] > idx && plane_match(pl, ws.cpl[s])) merge = true;
+              }
+            }
+          }
+        }
+      }
+      if (__any_sync(kFull, merge)) return R_DEFER;
+    }
+    return __any_sync(kFull, hit_own) ? R_HIT : R_FREE;
+  }
+}
+
+// Full pose decision for one work item, warp-cooperative. Returns 0 invalid / 1 valid / 2 defer.
+__device__ int pose_valid_warp(const Checker& c, const double s[7], WarpScratch& ws, int lane) {
+  float t[3], R[9], Rb[9], tt[3];
+  pose3_from_se3(s, t, R);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Rb[i] = R[i];
+  orthogonalize_r(Rb);   // dBodySetRotation of the same matrix for all five boxes
+  BoxCtx b;
+  // torso (validity_checker.cpp:41-43, validity_checker_body.cpp:27-42): valid iff NO collision
+  compose_translation(R, t, c.torso_off[0], c.torso_off[1], c.torso_off[2], tt);
+  if (is_inside(c, tt[0], tt[1])) {
+    if (box_setup(c.f[0], c.side[0], tt, Rb, b)) {
+      const int r = box_collide_warp(c.f[0], b, ws, lane, c.cell_margin);
+      if (r == R_DEFER) return 2;
+      if (r == R_HIT) return 0;
+    }
+  }
+  // feet (validity_checker_feet.cpp:32-70): every reach box MUST collide; early break
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    const float ox = (k & 2) ? -c.feet_ox : c.feet_ox, oy = (k & 1) ? -c.feet_oy : c.feet_oy;
+    compose_translation(R, t, ox, oy, 0.0f, tt);
+    if (!is_inside(c, tt[0], tt[1])) {
+      if (c.unknown_untraversable) return 0;
+      continue;
+    }
+    if (!box_setup(c.f[1], c.side[1], tt, Rb, b)) return 0;
+    const int r = box_collide_warp(c.f[1], b, ws, lane, c.cell_margin);
+    if (r == R_DEFER) return 2;
+    if (r == R_FREE) return 0;
+  }
+  return 1;
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+check_items_warp_kernel(const Checker c, const Work w, uint32_t* __restrict__ work_counter,
+                        uint32_t* __restrict__ defer_count, uint32_t* __restrict__ defer_list, int force_defer) {
+  __shared__ WarpScratch ws_all[kWarpsPerCta];
+  const int lane = threadIdx.x & 31;
+  WarpScratch& ws = ws_all[threadIdx.x >> 5];
+  for (;;) {
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(work_counter, 1u);
+    item = __shfl_sync(kFull, item, 0);
+    if (item >= w.n_items) break;
+    const uint32_t slot = item_slot(w, item);
+    if (w.edge_mode) {   // edge already invalid: nothing can change it (perf only; result is order-free)
+      int dead = 0;
+      if (lane == 0) dead = (*(volatile uint8_t*)(w.valid + slot) == 0);
+      if (__shfl_sync(kFull, dead, 0)) continue;
+    }
+    int r;
+    if (force_defer) {
+      r = 2;
+    } else {
+      double s[7];
+      load_item_state(w, item, s);
+      r = pose_valid_warp(c, s, ws, lane);
+    }
+    if (lane == 0) {
+      if (r == 2) {
+        defer_list[atomicAdd(defer_count, 1u)] = item;
+      } else if (w.edge_mode) {
+        if (r == 0) w.valid[slot] = 0;
+      } else {
+        w.valid[slot] = (uint8_t)r;
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// K2: block-level exact decision including the greedy epsilon grouping.
+// Shared memory: planes[T][4] floats, group[T] ints, state[T] bytes, T = 2 * max cells of a zone.
+// -------------------------------------------------------------------------------------------------
+struct BlockShared {
+  float* planes;     // [T][4]
+  int* group;        // [T] base index (== own index for bases); -1 for not-kept
+  uint8_t* state;    // [T] 1 = assigned
+  int T_cap;
+};
+
+__device__ __forceinline__ float block_reduce_max(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float a = __shfl_xor_sync(kFull, v, o);
+    v = is_max ? ((v > a) ? v : a) : ((v > a) ? a : v);
+  }
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) {
+    const float a = red[i];
+    r = is_max ? ((r > a) ? r : a) : ((r > a) ? a : r);
+  }
+  return r;
+}
+
+// Returns R_FREE / R_HIT, or R_DEFER if the zone does not fit the shared-memory plane store (host
+// sizes it so that this cannot happen for the configured boxes).
+__device__ int box_collide_block(const Field& f, const BoxCtx& b, const BlockShared& sh, float* red, int* s_next) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int nX = b.x1 - b.x0 + 1, nZ = b.z1 - b.z0 + 1, nV = nX * nZ;
+  const float* base = f.H + (size_t)b.z0 * f.nx + b.x0;
+  float mx = -CUDART_INF_F, mn = CUDART_INF_F;
+  int fin = 1;
+  for (int t = tid; t < nV; t += nthr) {
+    const int zi = t / nX, xi = t - zi * nX;
+    const float h = __ldg(base + (size_t)zi * f.nx + xi);
+    mx = (mx > h) ? mx : h;
+    if (finitef(h)) mn = (mn > h) ? h : mn; else fin = 0;
+  }
+  const float maxY = block_reduce_max(mx, red, true);
+  const float minY = block_reduce_max(mn, red, false);
+  const bool allFinite = __syncthreads_and(fin) != 0;
+  if (b.minB - maxY > -ARTP_EPS) return R_FREE;
+  if (minY - b.maxB > -ARTP_EPS) return R_FREE;
+  if (allFinite && minY - b.minB > -ARTP_EPS && b.maxB - maxY > -ARTP_EPS) return R_HIT;
+  if (allFinite && maxY - minY < ARTP_EPS) {
+    const float pl[4] = {0.0f, 1.0f, 0.0f, minY};
+    float cx[4], cz[4];
+    return box_plane(b, pl, 1, cx, cz) > 0 ? R_HIT : R_FREE;
+  }
+  if (nX < 2 || nZ < 2) return R_FREE;
+  const int nCX = nX - 1, nCZ = nZ - 1, nC = nCX * nCZ, T = 2 * nC;
+  if (T > sh.T_cap) return R_DEFER;
+  // triangles in emission order (x outer, z inner, Up then Down): vertex tests + planes
+  int hit = 0;
+  for (int t = tid; t < nC; t += nthr) {
+    const int cxi = t / nCZ, czi = t - cxi * nCZ;          // emission order index t = cxi*nCZ + czi
+    const int cx = b.x0 + cxi, cz = b.z0 + czi;
+    float hA, hB, hC, hD;
+    load_cell(f, cx, cz, hA, hB, hC, hD);
+    const bool fA = finitef(hA), fB = finitef(hB), fC = finitef(hC), fD = finitef(hD);
+    const bool cA = fA && hA > b.minB, cB = fB && hB > b.minB, cC = fC && hC > b.minB, cD = fD && hD > b.minB;
+    const bool keepUp = (cA || cB || cC) && (fA && fB && fC);
+    const bool keepDn = (cB || cC || cD) && (fB && fC && fD);
+    const float xA = cx * f.sW, xB = (cx + 1) * f.sW, zA = cz * f.sD, zC = (cz + 1) * f.sD;
+    if (keepUp && cA) hit |= vertex_inside(b, xA, hA, zA);
+    if ((keepUp || keepDn) && cB) hit |= vertex_inside(b, xB, hB, zA);
+    if ((keepUp || keepDn) && cC) hit |= vertex_inside(b, xA, hC, zC);
+    if (keepDn && cD) hit |= vertex_inside(b, xB, hD, zC);
+    const int i0 = 2 * t;
+    sh.state[i0] = 0; sh.state[i0 + 1] = 0;
+    sh.group[i0] = -1; sh.group[i0 + 1] = -1;
+    if (keepUp) { cell_plane(f, true, cx, cz, hA, hB, hC, hD, sh.planes + 4 * i0); sh.group[i0] = i0; }
+    if (keepDn) { cell_plane(f, false, cx, cz, hA, hB, hC, hD, sh.planes + 4 * (i0 + 1)); sh.group[i0 + 1] = i0 + 1; }
+  }
+  if (__syncthreads_or(hit)) return R_HIT;
+  // greedy grouping (heightfield.cpp:1511-1556)
+  int k = -1;
+  for (;;) {
+    if (tid == 0) {
+      int q = k + 1;
+      while (q < T && (sh.group[q] < 0 || sh.state[q])) ++q;
+      *s_next = q;
+    }
+    __syncthreads();
+    k = *s_next;
+    if (k >= T) break;
+    const float* pk = sh.planes + 4 * k;
+    const float p0 = pk[0], p1 = pk[1], p2 = pk[2], p3 = pk[3];
+    for (int m = k + 1 + tid; m < T; m += nthr) {
+      if (sh.group[m] < 0 || sh.state[m]) continue;
+      const float* pm = sh.planes + 4 * m;
+      if (fabsf(p1 - pm[1]) < ARTP_EPS && fabsf(p3 - pm[3]) < ARTP_EPS && fabsf(p0 - pm[0]) < ARTP_EPS &&
+          fabsf(p2 - pm[2]) < ARTP_EPS) {
+        sh.state[m] = 1;
+        sh.group[m] = k;
+      }
+    }
+    if (tid == 0) sh.state[k] = 1;
+    __syncthreads();
+  }
+  // per-group plane contacts vs member triangles (heightfield.cpp:1573-1617), evaluated per member
+  hit = 0;
+  for (int m = tid; m < T; m += nthr) {
+    const int g = sh.group[m];
+    if (g < 0) continue;
+    float cx[4], cz[4];
+    const int nc = box_plane(b, sh.planes + 4 * g, 4, cx, cz);
+    if (nc == 0) continue;
+    const int t = m >> 1;
+    const int cxi = t / nCZ, czi = t - cxi * nCZ;
+    const bool isUp = (m & 1) == 0;
+    const int tcx = b.x0 + cxi + (isUp ? 0 : 1), tcz = b.z0 + czi + (isUp ? 0 : 1);
+    for (int i = 0; i < nc; ++i) hit |= on_tri(f, isUp, tcx, tcz, cx[i], cz[i]);
+  }
+  return __syncthreads_or(hit) ? R_HIT : R_FREE;
+}
+
+__device__ int pose_valid_block(const Checker& c, const double s[7], const BlockShared& sh, float* red, int* s_next) {
+  float t[3], R[9], Rb[9], tt[3];
+  pose3_from_se3(s, t, R);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Rb[i] = R[i];
+  orthogonalize_r(Rb);
+  BoxCtx b;
+  compose_translation(R, t, c.torso_off[0], c.torso_off[1], c.torso_off[2], tt);
+  if (is_inside(c, tt[0], tt[1])) {
+    if (box_setup(c.f[0], c.side[0], tt, Rb, b)) {
+      const int r = box_collide_block(c.f[0], b, sh, red, s_next);
+      if (r == R_DEFER) return 2;
+      if (r == R_HIT) return 0;
+    }
+  }
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    const float ox = (k & 2) ? -c.feet_ox : c.feet_ox, oy = (k & 1) ? -c.feet_oy : c.feet_oy;
+    compose_translation(R, t, ox, oy, 0.0f, tt);
+    if (!is_inside(c, tt[0], tt[1])) {
+      if (c.unknown_untraversable) return 0;
+      continue;
+    }
+    if (!box_setup(c.f[1], c.side[1], tt, Rb, b)) return 0;
+    const int r = box_collide_block(c.f[1], b, sh, red, s_next);
+    if (r == R_DEFER) return 2;
+    if (r == R_FREE) return 0;
+  }
+  return 1;
+}
+
+__global__ void __launch_bounds__(256)
+check_items_block_kernel(const Checker c, const Work w, const uint32_t* __restrict__ defer_count,
+                         const uint32_t* __restrict__ defer_list, int T_cap, uint32_t* __restrict__ overflow) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float red[8];
+  __shared__ int s_next;
+  BlockShared sh;
+  sh.T_cap = T_cap;
+  sh.planes = reinterpret_cast<float*>(smem_raw);
+  sh.group = reinterpret_cast<int*>(smem_raw + (size_t)T_cap * 16);
+  sh.state = reinterpret_cast<uint8_t*>(smem_raw + (size_t)T_cap * 20);
+  const uint32_t count = *defer_count;
+  for (uint32_t q = blockIdx.x; q < count; q += gridDim.x) {
+    const uint32_t item = defer_list[q];
+    const uint32_t slot = item_slot(w, item);
+    double s[7];
+    load_item_state(w, item, s);
+    const int r = pose_valid_block(c, s, sh, red, &s_next);
+    if (threadIdx.x == 0) {
+      if (r == 2) { atomicAdd(overflow, 1u); }
+      else if (w.edge_mode) { if (r == 0) w.valid[slot] = 0; }
+      else w.valid[slot] = (uint8_t)r;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace artp

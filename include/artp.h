@@ -1,0 +1,115 @@
+/*
+ * include/artp.h -- C ABI of the B200-native art_planner hot path (libartp.so).
+ *
+ * Drop-in boundary: everything the reference's OMPL plugins for this path need,
+ * as plain C: pointers + sizes, no C++/torch types, no exceptions across the boundary. Every entry point
+ * returns 0 on success or a negative ARTP_E_* code; artp_last_error() gives the message.
+ * There is NO CPU fallback: if no CUDA device / kernel image is usable the calls fail with ARTP_E_CUDA.
+ *
+ * Reference interfaces each entry point replaces (paths relative to the reference tree):
+ *   artp_create / artp_destroy      art_planner::StateValidityChecker ctor (validity_checker.cpp:9-16) ->
+ *                                   ValidityCheckerBody/Feet ctors -> HeightMapBoxChecker ctor
+ *                                   (height_map_box_checker.cpp:11-26); parameters from art_planner::Params
+ *                                   (include/art_planner/params.h:14-123)
+ *   artp_set_map                    StateValidityChecker::setMap + updateHeightField (validity_checker.cpp:20-31)
+ *                                   -> HeightMapBoxChecker::setHeightField (height_map_box_checker.cpp:38-54);
+ *                                   installed at Planner::setMap (art_planner/src/planner.cpp:135-163)
+ *   artp_check_poses[_device]       ompl::base::StateValidityChecker::isValid, i.e.
+ *                                   art_planner::StateValidityChecker::isValid (validity_checker.cpp:39-45)
+ *   artp_check_motions[_device]     ompl::base::MotionValidator::checkMotion as the reference uses it: OMPL's
+ *                                   DiscreteMotionValidator over isValid (call sites prm_motion_cost.cpp:652,
+ *                                   lazy_prm_star_min_update.cpp:725) and the in-tree interpolation loop
+ *                                   PRMMotionCost::addValidMilestone (prm_motion_cost.cpp:341-372)
+ *   artp_path_length_cost[_device]  ompl::base::OptimizationObjective::motionCost ->
+ *                                   PathLengthObjective::motionCost (objectives/path_length_objective.cpp:26-70)
+ *   artp_set_cost_weights, artp_update_features, artp_motion_cost
+ *                                   the MotionCostFunc batch functor (objectives/motion_cost_objective.h:22-23)
+ *                                   = ROS service cost_query (art_planner_ros/src/planner_ros.cpp:283-308,
+ *                                   art_planner_motion_cost/scripts/cost_query_server.py:145-169,
+ *                                   predictor/predictor.py:28-44, predictor/cost_query.py:39-69)
+ *   artp_combine_cost               MotionCostObjective::getCost / isFeasible (motion_cost_objective.h:54-66)
+ */
+#ifndef ARTP_H
+#define ARTP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARTP_OK            0
+#define ARTP_E_INVALID    -1   /* bad argument */
+#define ARTP_E_NOMAP      -2   /* no map set (hasMap() == false) */
+#define ARTP_E_CUDA       -3   /* CUDA runtime error / no device */
+#define ARTP_E_LIMIT      -4   /* box/map combination exceeds a compiled limit */
+#define ARTP_E_NOWEIGHTS  -5   /* motion-cost network weights / features not set */
+
+/* art_planner::Params fields the hot path reads (include/art_planner/params.h). Doubles as in the reference. */
+typedef struct artp_params {
+  double torso_length, torso_width, torso_height;   /* params.h:92-94   */
+  double torso_off_x, torso_off_y, torso_off_z;     /* params.h:96-100  */
+  double feet_off_x, feet_off_y, feet_off_z;        /* params.h:106-110 */
+  double reach_x, reach_y, reach_z;                 /* params.h:112-116 */
+  int    unknown_space_untraversable;               /* params.h:26      */
+  int    use_directional_cost;                      /* params.h:73      */
+  double max_lon_vel, max_lat_vel, max_ang_vel;     /* params.h:74-76   */
+  float  cost_w_energy, cost_w_time, cost_w_risk;   /* params.h:57-61   */
+  float  risk_threshold;                            /* params.h:55      */
+  int    device;                                    /* CUDA device ordinal for this handle */
+} artp_params;
+
+typedef struct artp_handle artp_handle;
+
+typedef struct artp_stats {
+  uint64_t poses_checked;      /* pose checks executed since creation */
+  uint64_t poses_deferred;     /* of those, resolved by the exact plane-grouping kernel */
+  uint64_t kernel_launches;    /* kernels launched by this handle since creation */
+  uint32_t last_deferred;      /* deferred count of the most recent check call */
+  uint32_t last_launches;      /* kernels launched by the most recent call */
+} artp_stats;
+
+int  artp_create(const artp_params* params, artp_handle** out);
+void artp_destroy(artp_handle* h);
+const char* artp_last_error(const artp_handle* h);   /* h may be NULL: last creation error */
+
+/* Layers are HOST pointers in grid_map layout: column-major rows x cols floats, (i,j) at data[i + j*rows];
+ * lengths = rows*res, cols*res; centre (cx, cy). Heights must be finite or -inf. */
+int artp_set_map(artp_handle* h, const float* elevation, const float* elevation_masked,
+                 int rows, int cols, double res, double cx, double cy);
+int artp_has_map(const artp_handle* h);
+
+/* n SE(3) states, 7 doubles each (x y z qx qy qz qw) -> valid[n] (0/1). HOST buffers; H2D/D2H inside. */
+int artp_check_poses(artp_handle* h, const double* states, size_t n, uint8_t* valid);
+/* Same with DEVICE buffers on `stream` (a cudaStream_t cast to void*, may be NULL); asynchronous. */
+int artp_check_poses_device(artp_handle* h, const double* d_states, size_t n, uint8_t* d_valid, void* stream);
+
+/* Edge validity: valid(s2) && valid(interp(s1,s2,j/(n_steps+1))) for j = 1..n_steps (n_steps >= 0). */
+int artp_check_motions(artp_handle* h, const double* s1, const double* s2, size_t n, int n_steps, uint8_t* valid);
+int artp_check_motions_device(artp_handle* h, const double* d_s1, const double* d_s2, size_t n, int n_steps,
+                              uint8_t* d_valid, void* stream);
+
+/* PathLengthObjective::motionCost for n edges -> cost[n] (double). */
+int artp_path_length_cost(artp_handle* h, const double* s1, const double* s2, size_t n, double* cost);
+int artp_path_length_cost_device(artp_handle* h, const double* d_s1, const double* d_s2, size_t n,
+                                 double* d_cost, void* stream);
+
+/* Ordered compaction of a validity mask into indices (for the multi-GPU index all-gather):
+ * d_indices[k] = base + i for the k-th i with d_valid[i] != 0; *d_count = number written. Device buffers. */
+int artp_compact_valid_device(artp_handle* h, const uint8_t* d_valid, size_t n, int64_t base,
+                              int64_t* d_indices, uint32_t* d_count, void* stream);
+
+int artp_get_stats(artp_handle* h, artp_stats* out);
+
+/* Test hook: 0 = normal (warp kernel + exact grouping kernel for deferred poses),
+ *            1 = send every pose through the exact grouping kernel. */
+int artp_set_mode(artp_handle* h, int mode);
+
+/* Version string of the library / kernel image ("artp <ver> sm_100a"). */
+const char* artp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,110 @@
+"""Seeded parity cases shared by oracle/make_golden.py (generation with the compiled reference) and the tests."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from art_planner_b200 import synth
+
+
+def rot12_from_rpy(roll, pitch, yaw):
+    """dPose::rotation (row-major 3x4 float32) the way Pose3FromSE3 builds it from a quaternion (utils.h:25-38)."""
+    x, y, z, w = [a.astype(np.float32) for a in synth.quat_from_rpy(roll, pitch, yaw)]
+    tx, ty, tz = 2 * x, 2 * y, 2 * z
+    twx, twy, twz = tx * w, ty * w, tz * w
+    txx, txy, txz = tx * x, ty * x, tz * x
+    tyy, tyz, tzz = ty * y, tz * y, tz * z
+    n = x.shape[0]
+    R = np.zeros((n, 12), np.float32)
+    R[:, 0] = 1 - (tyy + tzz); R[:, 1] = txy - twz; R[:, 2] = txz + twy
+    R[:, 4] = txy + twz; R[:, 5] = 1 - (txx + tzz); R[:, 6] = tyz - twx
+    R[:, 8] = txz - twy; R[:, 9] = tyz + twx; R[:, 10] = 1 - (txx + tyy)
+    return R
+
+
+def flat_holes_terrace():
+    m = synth.make_flat_map()
+    m.elevation_masked[50:60, 50:70] = -np.inf
+    m.elevation_masked[100:103, :] = -np.inf
+    m.elevation[120:140, 120:140] = 0.25
+    m.elevation_masked[120:140, 120:140] = 0.25
+    m.desc = "flat 200x200@0.04 + -inf holes + 0.25 m terrace"
+    return m
+
+
+def ramp():
+    m = synth.make_flat_map()
+    xs, ys = m.cell_xy()
+    m.elevation[:] = (0.2 * xs[:, None] + 0.1 * ys[None, :]).astype(np.float32)
+    m.elevation_masked[:] = m.elevation
+    m.elevation_masked[30:40, 30:40] = -np.inf
+    m.desc = "planar ramp 200x200@0.04 (0.2 x + 0.1 y) + -inf hole"
+    return m
+
+
+MAPS = {
+    "flat": lambda: synth.make_flat_map(),
+    "flat_holes_terrace": flat_holes_terrace,
+    "ramp": ramp,
+    "fixture": lambda: synth.make_fixture_map(),
+    "fbm_rough": lambda: synth.make_fbm_map(400, 400, amp=0.6),
+    "fbm_gentle": lambda: synth.make_fbm_map(400, 400, amp=0.15),
+}
+
+PARAMS = {"yaml": synth.PARAMS_YAML, "header": synth.PARAMS_HEADER}
+
+# (name, map, params, pose generator)
+POSE_CASES = [
+    ("c1_flat_yaml", "flat", "yaml", lambda m: synth.make_flat_poses(m, 10000, seed=1)),
+    ("c1_flat_header", "flat", "header", lambda m: synth.make_flat_poses(m, 10000, seed=1)),
+    ("holes_yaml", "flat_holes_terrace", "yaml", lambda m: synth.make_flat_poses(m, 10000, seed=21, z_range=0.3)),
+    ("ramp_yaml", "ramp", "yaml", lambda m: synth.make_terrain_poses(m, 10000, seed=22)),
+    ("ramp_header", "ramp", "header", lambda m: synth.make_terrain_poses(m, 10000, seed=23)),
+    ("fixture_yaml", "fixture", "yaml", lambda m: synth.make_terrain_poses(m, 20000, seed=9)),
+    ("fixture_header", "fixture", "header", lambda m: synth.make_terrain_poses(m, 20000, seed=9)),
+    ("fbm_rough_yaml", "fbm_rough", "yaml", lambda m: synth.make_terrain_poses(m, 20000, seed=3)),
+    ("fbm_rough_header", "fbm_rough", "header", lambda m: synth.make_terrain_poses(m, 20000, seed=3)),
+    ("fbm_gentle_yaml", "fbm_gentle", "yaml", lambda m: synth.make_terrain_poses(m, 20000, seed=3)),
+    ("fbm_tilt_yaml", "fbm_rough", "yaml",
+     lambda m: synth.make_terrain_poses(m, 20000, seed=31, z_range=0.4, roll_pert=0.7, pitch_pert=0.7)),
+    ("ramp_tilt_header", "ramp", "header",
+     lambda m: synth.make_terrain_poses(m, 10000, seed=32, z_range=0.3, roll_pert=0.5, pitch_pert=0.5)),
+]
+
+
+def box_samples(m, n, seed, which, tilt=0.3, zr=0.3):
+    """Adversarial raw box poses: arbitrary tilt, centre near the surface (grazing contacts)."""
+    k = np.arange(n)
+    lx, ly = m.length
+    x = m.cx + (synth.hash_uniform(seed, 11, k) - 0.5) * (lx + 1.0)
+    y = m.cy + (synth.hash_uniform(seed, 12, k) - 0.5) * (ly + 1.0)
+    i, j = m.index_of(x, y)
+    layer = m.elevation if which == 0 else m.elevation_masked
+    e = layer[i, j].astype(np.float64)
+    e = np.where(np.isfinite(e), e, m.elevation[i, j])
+    z = e + (0.15 if which == 0 else 0.0) + (synth.hash_uniform(seed, 13 + which, k) * 2 - 1) * zr
+    yaw = (synth.hash_uniform(seed + which, 1, k) * 2 - 1) * math.pi
+    roll = (synth.hash_uniform(seed + which, 2, k) * 2 - 1) * tilt
+    pitch = (synth.hash_uniform(seed + which, 3, k) * 2 - 1) * tilt
+    return np.stack([x, y, z], 1).astype(np.float32), rot12_from_rpy(roll, pitch, yaw)
+
+
+# (name, map, seed, tilt, zr) -- both boxes of the yaml geometry
+BOX_CASES = [
+    ("box_flat", "flat", 1, 0.3, 0.3),
+    ("box_holes", "flat_holes_terrace", 2, 0.3, 0.3),
+    ("box_fixture", "fixture", 3, 0.3, 0.3),
+    ("box_ramp", "ramp", 4, 0.3, 0.3),
+    ("box_fbm_rough", "fbm_rough", 5, 0.3, 0.3),
+    ("box_fbm_tilt", "fbm_rough", 7, 1.2, 0.6),
+]
+BOX_N = 20000
+
+# (name, map, params, n_edges, n_steps, seed)
+EDGE_CASES = [
+    ("edges_fbm_rough_yaml", "fbm_rough", "yaml", 3000, 20, 4),
+    ("edges_fixture_header", "fixture", "header", 3000, 7, 5),
+]
+
+

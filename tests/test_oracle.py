@@ -1,0 +1,93 @@
+"""CPU-only: the oracle restatement (oracle/artp_oracle.c) against the golden masks produced by the reference's
+own compiled ODE, and -- where /root/reference exists -- against that compiled library directly."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from art_planner_b200 import synth
+
+
+def digest(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def unpack(golden, key, n):
+    return np.unpackbits(golden[key])[:n]
+
+
+@pytest.mark.parametrize("case", cases.POSE_CASES, ids=[c[0] for c in cases.POSE_CASES])
+def test_port_pose_masks_match_reference_golden(case, golden, maps, port_lib):
+    name, mk, pk, gen = case
+    m = maps(mk)
+    poses = gen(m)
+    assert digest(m.elevation, m.elevation_masked, poses) == str(golden[name + "/sha"]), "generator drift"
+    o = port_lib.Oracle(cases.PARAMS[pk], "port")
+    o.set_map(m)
+    v = o.check_poses(poses)
+    ref = unpack(golden, name + "/mask", len(v))
+    assert np.array_equal(v, ref)
+    # the multi-threaded variant must agree too
+    assert np.array_equal(o.check_poses_mt(poses, 4), ref)
+
+
+@pytest.mark.parametrize("case", cases.BOX_CASES, ids=[c[0] for c in cases.BOX_CASES])
+def test_port_box_hits_match_reference_golden(case, golden, maps, port_lib):
+    name, mk, seed, tilt, zr = case
+    m = maps(mk)
+    o = port_lib.Oracle(cases.PARAMS["yaml"], "port")
+    o.set_map(m)
+    for which in (0, 1):
+        org, rot = cases.box_samples(m, cases.BOX_N, seed, which, tilt, zr)
+        assert digest(m.elevation, m.elevation_masked, org, rot) == str(golden[f"{name}/{which}/sha"])
+        hit = o.box_collide(which, org, rot)
+        assert np.array_equal(hit, unpack(golden, f"{name}/{which}/mask", len(hit)))
+
+
+@pytest.mark.parametrize("case", cases.EDGE_CASES, ids=[c[0] for c in cases.EDGE_CASES])
+def test_port_edges_match_reference_golden(case, golden, maps, port_lib):
+    name, mk, pk, n, steps, seed = case
+    m = maps(mk)
+    o = port_lib.Oracle(cases.PARAMS[pk], "port")
+    o.set_map(m)
+    s1, s2 = synth.make_edges(m, n, seed)
+    assert digest(m.elevation, m.elevation_masked, s1, s2) == str(golden[name + "/sha"])
+    assert np.array_equal(o.check_motions(s1, s2, steps), unpack(golden, name + "/mask", n))
+    assert np.array_equal(o.path_length_cost(s1, s2), golden[name + "/cost"])
+
+
+def test_edge_with_zero_steps_is_endpoint_check(maps, port_lib):
+    m = maps("fixture")
+    o = port_lib.Oracle(cases.PARAMS["yaml"], "port")
+    o.set_map(m)
+    s1, s2 = synth.make_edges(m, 500, 77)
+    assert np.array_equal(o.check_motions(s1, s2, 0), o.check_poses(s2))
+
+
+def test_empty_batches(maps, port_lib):
+    m = maps("flat")
+    o = port_lib.Oracle(cases.PARAMS["yaml"], "port")
+    o.set_map(m)
+    assert o.check_poses(np.zeros((0, 7))).shape == (0,)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/ode"), reason="reference tree not present on this box")
+def test_port_equals_compiled_reference_on_fresh_seeds(maps, port_lib):
+    """Fresh seeds (not in the golden file): port == compiled reference ODE, pose and box level."""
+    port_lib.build("ref")
+    for mk in ("fixture", "ramp", "fbm_rough"):
+        m = maps(mk)
+        P = port_lib.Oracle(cases.PARAMS["yaml"], "port")
+        R = port_lib.Oracle(cases.PARAMS["yaml"], "reference")
+        P.set_map(m)
+        R.set_map(m)
+        poses = synth.make_terrain_poses(m, 5000, seed=1234)
+        assert np.array_equal(P.check_poses(poses), R.check_poses(poses))
+        for which in (0, 1):
+            org, rot = cases.box_samples(m, 5000, 4321, which, 0.8, 0.4)
+            assert np.array_equal(P.box_collide(which, org, rot), R.box_collide(which, org, rot))

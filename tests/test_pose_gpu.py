@@ -1,0 +1,138 @@
+"""GPU parity (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle port and the golden masks
+of the reference's compiled ODE. Bit-exact valid/invalid flags are required."""
+import numpy as np
+import pytest
+
+import cases
+from art_planner_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def unpack(golden, key, n):
+    return np.unpackbits(golden[key])[:n]
+
+
+@pytest.fixture(scope="module")
+def checkers():
+    import art_planner_b200 as ap
+    from art_planner_b200 import build
+    build.build()
+    cache = {}
+
+    def get(pk):
+        if pk not in cache:
+            cache[pk] = ap.StateValidityChecker(cases.PARAMS[pk], device=0)
+        return cache[pk]
+    return get
+
+
+def set_map(chk, m):
+    chk.setMap(m)
+    chk.updateHeightField()
+    assert chk.hasMap()
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["warp+group", "group-only"])
+@pytest.mark.parametrize("case", cases.POSE_CASES, ids=[c[0] for c in cases.POSE_CASES])
+def test_pose_masks_bit_exact(case, mode, golden, maps, port_lib, checkers):
+    name, mk, pk, gen = case
+    m = maps(mk)
+    poses = gen(m)
+    chk = checkers(pk)
+    set_map(chk, m)
+    chk.setMode(mode)
+    try:
+        got = chk.isValidBatch(poses)
+        st = chk.stats()
+    finally:
+        chk.setMode(0)
+    ref = unpack(golden, name + "/mask", len(got))
+    o = port_lib.Oracle(cases.PARAMS[pk], "port")
+    o.set_map(m)
+    port = o.check_poses(poses)
+    assert np.array_equal(port, ref)
+    bad = np.nonzero(got != ref)[0]
+    assert bad.size == 0, f"{bad.size} mismatches, first {bad[:8]}, deferred={st['last_deferred']}"
+    if mode == 1:
+        assert st["last_deferred"] == len(poses)
+
+
+def test_device_buffers_and_host_buffers_agree(maps, checkers):
+    import torch
+    m = maps("fbm_rough")
+    chk = checkers("yaml")
+    set_map(chk, m)
+    poses = synth.make_terrain_poses(m, 30000, seed=99)
+    host = chk.isValidBatch(poses)
+    dev = chk.isValidBatch(torch.from_numpy(poses).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(host, dev.cpu().numpy())
+
+
+def test_single_state_latency_path_and_edge_cases(maps, port_lib, checkers):
+    m = maps("fixture")
+    chk = checkers("yaml")
+    set_map(chk, m)
+    o = port_lib.Oracle(cases.PARAMS["yaml"], "port")
+    o.set_map(m)
+    poses = synth.make_terrain_poses(m, 64, seed=5)
+    ref = o.check_poses(poses)
+    for i in range(64):
+        assert chk.isValid(poses[i]) == bool(ref[i])
+    assert chk.isValidBatch(np.zeros((0, 7))).shape == (0,)
+    # far outside the map: torso "valid", feet decided by unknown_space_untraversable (=True -> invalid)
+    far = np.array([[1e3, -1e3, 0.0, 0, 0, 0, 1.0]])
+    assert np.array_equal(chk.isValidBatch(far), o.check_poses(far))
+    # ragged batch sizes around warp/CTA multiples
+    for n in (1, 31, 33, 255, 257):
+        assert np.array_equal(chk.isValidBatch(poses[:n] if n <= 64 else np.resize(poses, (n, 7))),
+                              o.check_poses(poses[:n] if n <= 64 else np.resize(poses, (n, 7))))
+
+
+def test_no_map_is_an_error(checkers):
+    import art_planner_b200 as ap
+    chk = ap.StateValidityChecker(cases.PARAMS["yaml"], device=0)
+    assert not chk.hasMap()
+    with pytest.raises(ap.ArtpError):
+        chk.isValidBatch(np.zeros((4, 7)))
+
+
+def test_compaction_is_ordered(maps, checkers):
+    import torch
+    m = maps("fbm_gentle")
+    chk = checkers("yaml")
+    set_map(chk, m)
+    poses = torch.from_numpy(synth.make_terrain_poses(m, 50001, seed=17)).cuda()
+    valid = chk.isValidBatch(poses)
+    idx, cnt = chk.compactValid(valid, base=1000)
+    torch.cuda.synchronize()
+    v = valid.cpu().numpy()
+    n = int(cnt.item())
+    assert n == int(v.sum())
+    assert np.array_equal(idx[:n].cpu().numpy(), np.nonzero(v)[0] + 1000)
+
+
+def test_full_size_properties_c2(checkers):
+    """BASELINE configs[1] size (1000x1000 map, 1 M samples): size-independent properties --
+    idempotence, permutation equivariance, host/device agreement on a slice -- plus a strided oracle check."""
+    import torch
+    from oracle import orc
+    m = synth.make_fbm_map(1000, 1000)
+    chk = checkers("yaml")
+    set_map(chk, m)
+    n = 1_000_000
+    poses = synth.make_terrain_poses(m, n, seed=3)
+    d = torch.from_numpy(poses).cuda()
+    a = chk.isValidBatch(d).clone()
+    b = chk.isValidBatch(d).clone()
+    perm = torch.randperm(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
+    c = chk.isValidBatch(d[perm].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    assert torch.equal(a[perm], c)
+    o = orc.Oracle(cases.PARAMS["yaml"], "port")
+    o.set_map(m)
+    sel = np.arange(0, n, 50)
+    assert np.array_equal(a.cpu().numpy()[sel], o.check_poses(poses[sel]))
+    assert 0.05 < float(a.float().mean()) < 0.95
