@@ -62,6 +62,8 @@ def load():
     lib.artp_compact_valid_device.argtypes = [vp, vp, sz, C.c_int64, vp, vp, vp]
     lib.artp_get_stats.argtypes = [vp, C.POINTER(ArtpStats)]
     lib.artp_set_mode.argtypes = [vp, i32]
+    lib.artp_set_timing.argtypes = [vp, i32]
+    lib.artp_get_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.artp_version.restype = C.c_char_p
     _lib = lib
     return lib

@@ -137,6 +137,15 @@ class StateValidityChecker:
     def stats(self) -> dict:
         return self._h.stats()
 
+    def setTiming(self, enable: bool) -> None:
+        self._h.check(self._h.lib.artp_set_timing(self._h.h, int(bool(enable))))
+
+    def lastKernelTimesMs(self):
+        """(warp kernel ms, plane-grouping kernel ms) of the most recent check call (CUDA events on its stream)."""
+        a, b = C.c_float(), C.c_float()
+        self._h.check(self._h.lib.artp_get_last_timing(self._h.h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
     @property
     def handle(self) -> _Handle:
         return self._h

@@ -37,6 +37,10 @@ struct Handle {
   cudaStream_t stream = nullptr;    // internal stream for the host-buffer API
   int k1_grid = 0, k2_grid = 0, k2_smem = 0, k2_tcap = 0;
   int mode = 0;
+  int timing = 0;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  bool ev_valid = false;
+  bool deferred_unread = false;
   artp_stats stats{};
   std::string err;
   std::mutex mtx;
@@ -172,14 +176,18 @@ int run_items(Handle* h, const artp::Work& w, cudaStream_t s) {
   int rc = ensure_defer(h, w.n_items, s);
   if (rc) return rc;
   CU_TRY(h, cudaMemsetAsync(h->d_ctr, 0, 3 * sizeof(uint32_t), s));
+  if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[0], s));
   artp::check_items_warp_kernel<<<h->k1_grid, artp::kWarpsPerCta * 32, 0, s>>>(h->chk, w, h->d_ctr, h->d_ctr + 1,
                                                                                 h->d_defer, h->mode == 1);
   CU_TRY(h, cudaGetLastError());
+  if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[1], s));
   artp::check_items_block_kernel<<<h->k2_grid, 256, h->k2_smem, s>>>(h->chk, w, h->d_ctr + 1, h->d_defer, h->k2_tcap,
                                                                       h->d_ctr + 2);
   CU_TRY(h, cudaGetLastError());
+  if (h->timing) { CU_TRY(h, cudaEventRecord(h->ev[2], s)); h->ev_valid = true; }
   h->stats.kernel_launches += 2;
   h->stats.last_launches = 2;
+  h->deferred_unread = true;
   return ARTP_OK;
 }
 
@@ -257,6 +265,7 @@ void artp_destroy(artp_handle* hh) {
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   cudaFree(h->d_H[0]); cudaFree(h->d_H[1]); cudaFree(h->d_ctr); cudaFree(h->d_defer); cudaFree(h->d_stage);
   cudaFree(h->d_block_counts);
+  for (int i = 0; i < 3; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
 }
 
@@ -268,6 +277,29 @@ int artp_set_mode(artp_handle* hh, int mode) {
   return ARTP_OK;
 }
 
+int artp_set_timing(artp_handle* hh, int enable) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (enable && !h->ev[0]) for (int i = 0; i < 3; ++i) CU_TRY(h, cudaEventCreate(&h->ev[i]));
+  h->timing = enable ? 1 : 0;
+  h->ev_valid = false;
+  return ARTP_OK;
+}
+
+int artp_get_last_timing(artp_handle* hh, float* warp_kernel_ms, float* group_kernel_ms) {
+  if (!hh || !warp_kernel_ms || !group_kernel_ms) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (!h->timing || !h->ev_valid) { h->err = "timing not enabled or no call recorded"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaEventSynchronize(h->ev[2]));
+  CU_TRY(h, cudaEventElapsedTime(warp_kernel_ms, h->ev[0], h->ev[1]));
+  CU_TRY(h, cudaEventElapsedTime(group_kernel_ms, h->ev[1], h->ev[2]));
+  return ARTP_OK;
+}
+
 int artp_get_stats(artp_handle* hh, artp_stats* out) {
   if (!hh || !out) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
@@ -276,6 +308,7 @@ int artp_get_stats(artp_handle* hh, artp_stats* out) {
   uint32_t ctr[3] = {0, 0, 0};
   CU_TRY(h, cudaMemcpy(ctr, h->d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost));   // synchronises the device
   h->stats.last_deferred = ctr[1];
+  if (h->deferred_unread) { h->stats.poses_deferred += ctr[1]; h->deferred_unread = false; }
   *out = h->stats;
   if (ctr[2] != 0) { h->err = "plane-grouping kernel overflow (zone larger than its shared-memory store)"; return ARTP_E_LIMIT; }
   return ARTP_OK;

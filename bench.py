@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- pose-validity checks/s of the art_planner hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input: BASELINE.json configs[1] -- a
+1 000 000-pose validity batch (torso + 4 feet, yaml robot geometry) on the fBm ("Perlin") 1000x1000 @0.04 m map.
+  value  poses/s with the inputs already resident in HBM (artp_check_poses_device), CUDA events, L2 flushed
+         between timed steps, max over ranks.
+  e2e    the same metric through the host-buffer C-ABI call (artp_check_poses) with pinned HOST buffers:
+         H2D of the 56 B/pose states and D2H of the 1 B/pose mask are inside the timed region.
+  N > 1  weak scaling: every rank checks its own 1 M-pose shard of the seeded sample stream against its replica of
+         the map and the ranks exchange the ordered valid-sample indices with one NCCL all-gather (+ a count
+         all-gather) inside the timed region.
+  --impl reference   the reference's own CPU path (oracle/_ref = its compiled ODE when present, else the C port)
+         on all host threads, on a bounded sample of the same workload per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MAP_N = 1000
+MAP_RES = 0.04
+POSES_PER_GPU = 1_000_000
+MAP_SEED, POSE_SEED = 2, 3
+WORKLOAD = "configs[1]: fBm 1000x1000@0.04m map (amp 0.6 m), 1M-pose validity batch, yaml robot geometry"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.lines, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(rank: int, n: int):
+    from art_planner_b200 import synth
+    m = synth.make_fbm_map(MAP_N, MAP_N, MAP_RES, seed=MAP_SEED, amp=0.6)
+    poses = synth.make_terrain_poses(m, n, seed=POSE_SEED, start=rank * n)
+    return m, poses
+
+
+def cpu_oracle(params):
+    from oracle import orc
+    kind = "reference" if orc.available("reference") else "port"
+    if kind == "port":
+        orc.build("port")
+    return orc.Oracle(params, kind), kind
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from art_planner_b200 import synth
+    cores = os.cpu_count() or 1
+    sample_n = 200_000
+    m, poses = make_inputs(0, sample_n)
+    o, kind = cpu_oracle(synth.PARAMS_YAML)
+    o.set_map(m)
+    for _ in range(max(args.warmup, 1)):
+        o.check_poses_mt(poses[:20000], cores)      # also builds the per-thread ODE worlds (one-time per map)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.check_poses_mt(poses, cores)
+    dt = time.perf_counter() - t0
+    value = sample_n * args.steps / dt
+    sample = f"first {sample_n} poses of the 1M-pose workload per step, {cores} threads, one ODE world per thread"
+    print(json.dumps({
+        "impl": "reference", "metric": "pose-validity checks/s", "value": value, "unit": "poses/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_per_step": sample_n},
+        "cpu_baseline": {"value": value, "unit": "poses/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import art_planner_b200 as apb
+    from art_planner_b200 import build, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+
+    n = POSES_PER_GPU
+    m, poses = make_inputs(rank, n)
+    chk = apb.StateValidityChecker(synth.PARAMS_YAML, device=local)
+    chk.setMap(m)
+    chk.updateHeightField()
+    chk.setTiming(True)
+
+    d_poses = torch.from_numpy(poses).cuda()
+    d_valid = torch.empty(n, dtype=torch.uint8, device="cuda")
+    h_poses = torch.from_numpy(poses).pin_memory()
+    h_valid = torch.empty(n, dtype=torch.uint8).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    gather_cnt = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(world)]
+    gather_idx = torch.empty(world * n, dtype=torch.int64, device="cuda") if world > 1 else None
+
+    def step_device():
+        chk.isValidBatch(d_poses, out=d_valid)
+        if world > 1:   # ordered valid-sample indices -> one padded all-gather (+ counts)
+            idx, cnt = chk.compactValid(d_valid, base=rank * n)
+            dist.all_gather(gather_cnt, cnt)
+            dist.all_gather_into_tensor(gather_idx, idx)
+
+    def step_e2e():
+        chk.isValidHostPtr(h_poses.data_ptr(), n, h_valid.data_ptr())
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    step_e2e()
+    torch.cuda.synchronize()
+
+    # ---- timed region: device-resident inputs --------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = chk.stats()["kernel_launches"]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    k1_ms, k2_ms = [], []
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)               # evict L2 (untimed)
+        ev[i][0].record()
+        step_device()
+        ev[i][1].record()
+        a, b = chk.lastKernelTimesMs()      # waits for this step's kernels (events on the same stream)
+        k1_ms.append(a); k2_ms.append(b)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+    launches = chk.stats()["kernel_launches"] - launches0
+    deferred = chk.stats()["last_deferred"]
+
+    # ---- timed region: end to end through the host-buffer C-ABI call ---------------------------
+    e2e_steps = args.steps
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    valid_ref = None
+
+    if rank == 0:
+        value = world * n * args.steps / (dev_ms * 1e-3)
+        e2e_value = world * n * e2e_steps / (e2e_ms * 1e-3)
+        # ---- CPU baseline + algorithmic bytes from the oracle on a bounded sample ---------------
+        o, kind = cpu_oracle(synth.PARAMS_YAML)
+        o.set_map(m)
+        cores = os.cpu_count() or 1
+        n1 = 20_000
+        t0 = time.perf_counter(); v1 = o.check_poses(poses[:n1]); t_single = time.perf_counter() - t0
+        n_mt = 400_000
+        o.check_poses_mt(poses[:cores * 64], cores)   # builds the per-thread ODE worlds (one-time per map, untimed)
+        t0 = time.perf_counter(); v_mt = o.check_poses_mt(poses[:n_mt], cores); t_mt = time.perf_counter() - t0
+        got = d_valid.cpu().numpy()
+        parity_ok = bool(np.array_equal(got[:n_mt], v_mt) and np.array_equal(got[:n1], v1))
+        from oracle import orc
+        orc.build("port")
+        port = orc.Oracle(synth.PARAMS_YAML, "port")
+        port.set_map(m)
+        _, zv = port.check_poses(poses[:50_000], want_zone=True)
+        bytes_per_pose = 56.0 + 1.0 + 4.0 * float(zv.mean())
+        peak, peak_src = load_peaks()
+        k1 = float(np.mean(k1_ms))
+        achieved = bytes_per_pose * n / (k1 * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("check_items_warp_kernel_dram_bytes_per_launch")
+        out = {
+            "metric": "pose-validity checks/s", "value": value, "unit": "poses/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "poses_per_gpu": n, "map": f"{MAP_N}x{MAP_N}@{MAP_RES}",
+                       "map_seed": MAP_SEED, "pose_seed": POSE_SEED, "l2": "flushed between timed steps (256 MiB write)",
+                       "parallelism": f"pose shards x{world}, replicated map" + (", NCCL all-gather of valid indices" if world > 1 else "")},
+            "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": n * 56, "d2h_bytes_per_step": n,
+                    "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "check_items_warp_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_pose": bytes_per_pose, "kernel_ms": k1,
+                         "group_kernel_ms": float(np.mean(k2_ms)), "deferred_items": int(deferred)},
+            "cpu_baseline": {"value": n_mt / t_mt, "unit": "poses/s", "cores": cores, "kind": kind,
+                             "sample": f"first {n_mt} poses of the workload, {cores} threads; single-thread on first {n1}",
+                             "single_thread_value": n1 / t_single, "mask_equals_gpu": parity_ok},
+            "clocks": clocks, "wall_s_timed_region": wall,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -64,7 +64,7 @@ typedef struct artp_handle artp_handle;
 
 typedef struct artp_stats {
   uint64_t poses_checked;      /* pose checks executed since creation */
-  uint64_t poses_deferred;     /* of those, resolved by the exact plane-grouping kernel */
+  uint64_t poses_deferred;     /* deferred items summed over the calls whose stats were read (one read per call) */
   uint64_t kernel_launches;    /* kernels launched by this handle since creation */
   uint32_t last_deferred;      /* deferred count of the most recent check call */
   uint32_t last_launches;      /* kernels launched by the most recent call */
@@ -101,6 +101,12 @@ int artp_compact_valid_device(artp_handle* h, const uint8_t* d_valid, size_t n, 
                               int64_t* d_indices, uint32_t* d_count, void* stream);
 
 int artp_get_stats(artp_handle* h, artp_stats* out);
+
+/* Kernel timing for roofline reporting: when enabled, CUDA events are recorded on the launch stream around the
+ * warp kernel and the plane-grouping kernel of every check call; artp_get_last_timing waits for the last call's
+ * kernels and returns their durations in milliseconds. */
+int artp_set_timing(artp_handle* h, int enable);
+int artp_get_last_timing(artp_handle* h, float* warp_kernel_ms, float* group_kernel_ms);
 
 /* Test hook: 0 = normal (warp kernel + exact grouping kernel for deferred poses),
  *            1 = send every pose through the exact grouping kernel. */

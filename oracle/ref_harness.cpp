@@ -109,7 +109,13 @@ struct orc_handle {
   orc_geom g;
   LayerCopy map;
   CheckerPair* pair;
+  std::vector<CheckerPair*> mt_pairs;   // one ODE world + heightfield pair per worker thread (built lazily)
 };
+
+static void drop_mt_pairs(orc_handle* h) {
+  for (auto* p : h->mt_pairs) delete p;
+  h->mt_pairs.clear();
+}
 
 extern "C" {
 
@@ -125,6 +131,7 @@ orc_handle* orc_create(const orc_params* p) {
 
 void orc_destroy(orc_handle* h) {
   if (!h) return;
+  drop_mt_pairs(h);
   delete h->pair;
   delete h;
 }
@@ -136,6 +143,7 @@ int orc_set_map(orc_handle* h, const float* elevation, const float* elevation_ma
   h->map.masked.assign(elevation_masked, elevation_masked + (size_t)rows * cols);
   h->map.rows = rows; h->map.cols = cols; h->map.res = res; h->map.cx = cx; h->map.cy = cy;
   h->pair->setMap(h->map);
+  drop_mt_pairs(h);
   h->g.Lx = rows * res; h->g.Ly = cols * res; h->g.cx = cx; h->g.cy = cy; h->g.has_map = 1;
   return 0;
 }
@@ -185,8 +193,13 @@ int orc_path_length_cost(orc_handle* h, const double* s1, const double* s2, size
 int orc_check_poses_mt(orc_handle* h, const double* states, size_t n, uint8_t* valid, int n_threads) {
   if (!h || !h->g.has_map) return 1;
   if (n_threads < 1) n_threads = 1;
-  std::vector<CheckerPair*> pairs(n_threads);
-  for (int t = 0; t < n_threads; ++t) { pairs[t] = new CheckerPair(h->p); pairs[t]->setMap(h->map); }
+  // worker checkers persist across calls (the per-thread world/heightfield setup is a one-time cost per map)
+  while ((int)h->mt_pairs.size() < n_threads) {
+    CheckerPair* cp = new CheckerPair(h->p);
+    cp->setMap(h->map);
+    h->mt_pairs.push_back(cp);
+  }
+  std::vector<CheckerPair*>& pairs = h->mt_pairs;
   std::vector<std::thread> th;
   for (int t = 0; t < n_threads; ++t) {
     th.emplace_back([=, &pairs] {
@@ -196,7 +209,6 @@ int orc_check_poses_mt(orc_handle* h, const double* states, size_t n, uint8_t* v
     });
   }
   for (auto& x : th) x.join();
-  for (auto* p : pairs) delete p;
   return 0;
 }
 
