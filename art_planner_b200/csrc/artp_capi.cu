@@ -25,6 +25,9 @@ struct Handle {
   int sm_count = 0;
   artp::Checker chk;
   float* d_H[2] = {nullptr, nullptr};
+  float2* d_T[2][artp::kMaxLevel + 1] = {};
+  unsigned char* d_NF[2][artp::kMaxLevel + 1] = {};
+  int pitch = 0;
   int rows = 0, cols = 0;
   bool has_map = false;
   uint32_t* d_ctr = nullptr;        // [0] work counter, [1] defer count, [2] K2 overflow, [3] compaction total
@@ -57,11 +60,41 @@ struct Handle {
 
 // H[x + z*nx] = layer[x + (nz-1-z)*nx] (+0.0f canonicalises -0 like GetHeight's (h*scale)+offset,
 // ode/ode/src/heightfield.cpp:383).
-__global__ void reverse_columns_kernel(const float* __restrict__ layer, float* __restrict__ H, int nx, int nz) {
-  const size_t total = (size_t)nx * nz;
+__global__ void reverse_columns_kernel(const float* __restrict__ layer, float* __restrict__ H, int nx, int nz, int pitch) {
+  const size_t total = (size_t)pitch * nz;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int z = (int)(i / nx), x = (int)(i - (size_t)z * nx);
-    H[i] = layer[x + (size_t)(nz - 1 - z) * nx] * 1.0f + 0.0f;
+    const int z = (int)(i / pitch), x = (int)(i - (size_t)z * pitch);
+    H[i] = (x < nx) ? layer[x + (size_t)(nz - 1 - z) * nx] * 1.0f + 0.0f : 0.0f;   // pad columns are never read
+  }
+}
+
+// Range-table level k from level k-1 (level 0 = the heights themselves): reduction over the 2^k x 2^k window
+// starting at (x,z) = op of the four 2^(k-1) windows at offsets {0,half} (clamped at the border; clamped windows
+// are never queried). (max over all h, min over finite h or +inf, any non-finite).
+__global__ void build_level_kernel(const float* __restrict__ H, const float2* __restrict__ prevT,
+                                   const unsigned char* __restrict__ prevNF, float2* __restrict__ T,
+                                   unsigned char* __restrict__ NF, int nx, int nz, int pitch, int half) {
+  const size_t total = (size_t)pitch * nz;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int z = (int)(i / pitch), x = (int)(i - (size_t)z * pitch);
+    if (x >= nx) { T[i] = make_float2(0.f, 0.f); NF[i] = 0; continue; }
+    const int x2 = min(x + half, nx - 1), z2 = min(z + half, nz - 1);
+    const size_t id[4] = {(size_t)z * pitch + x, (size_t)z * pitch + x2, (size_t)z2 * pitch + x, (size_t)z2 * pitch + x2};
+    float mx = -CUDART_INF_F, mn = CUDART_INF_F;
+    unsigned char nf = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (prevT) {
+        const float2 v = prevT[id[q]];
+        mx = fmaxf(mx, v.x); mn = fminf(mn, v.y); nf |= prevNF[id[q]];
+      } else {
+        const float h = H[id[q]];
+        mx = fmaxf(mx, h);
+        if (fabsf(h) < CUDART_INF_F) mn = fminf(mn, h); else nf = 1;
+      }
+    }
+    T[i] = make_float2(mx, mn);
+    NF[i] = nf;
   }
 }
 
@@ -263,6 +296,7 @@ void artp_destroy(artp_handle* hh) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   cudaSetDevice(h->device);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  for (int k = 0; k < 2; ++k) for (int l = 0; l <= artp::kMaxLevel; ++l) { cudaFree(h->d_T[k][l]); cudaFree(h->d_NF[k][l]); }
   cudaFree(h->d_H[0]); cudaFree(h->d_H[1]); cudaFree(h->d_ctr); cudaFree(h->d_defer); cudaFree(h->d_stage);
   cudaFree(h->d_block_counts);
   for (int i = 0; i < 3; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -334,13 +368,16 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
   f.iW = 1.0f / f.sW;
   f.iD = 1.0f / f.sD;
   f.px = (float)cx; f.py = (float)cy;
-  // K2 shared-memory plane store: bound the zone of either box by its half-diagonal
-  int tcap = 0;
+  // K2 shared-memory plane store: bound the zone of either box by its half-diagonal; same bound -> table levels
+  int tcap = 0, kmax[2] = {0, 0};
   for (int k = 0; k < 2; ++k) {
     const float* sd = h->chk.side[k];
     const double r = 0.5 * std::sqrt((double)sd[0] * sd[0] + (double)sd[1] * sd[1] + (double)sd[2] * sd[2]);
     const int nxm = std::min(rows, (int)std::ceil(2.0 * r * f.iW) + 4), nzm = std::min(cols, (int)std::ceil(2.0 * r * f.iD) + 4);
     tcap = std::max(tcap, 2 * (nxm - 1) * (nzm - 1));
+    int kk = 0;
+    while ((2 << kk) <= std::min(nxm, nzm) && kk < artp::kMaxLevel) ++kk;   // floor(log2(min dim bound))
+    kmax[k] = kk;
   }
   tcap = (tcap + 3) & ~3;
   const int smem = tcap * 21 + 64;
@@ -354,25 +391,46 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
   h->k2_smem = smem; h->k2_tcap = tcap; h->k2_grid = h->sm_count * std::max(per_sm, 1);
   // upload
   CU_TRY(h, cudaStreamSynchronize(h->stream));
+  const int pitch = (rows + 3) & ~3;
+  const size_t npad = (size_t)pitch * cols;
   if (h->rows != rows || h->cols != cols) {
-    cudaFree(h->d_H[0]); cudaFree(h->d_H[1]);
-    h->d_H[0] = h->d_H[1] = nullptr;
-    CU_TRY(h, cudaMalloc(&h->d_H[0], ncell * sizeof(float)));
-    CU_TRY(h, cudaMalloc(&h->d_H[1], ncell * sizeof(float)));
+    for (int k = 0; k < 2; ++k) {
+      cudaFree(h->d_H[k]); h->d_H[k] = nullptr;
+      for (int l = 0; l <= artp::kMaxLevel; ++l) { cudaFree(h->d_T[k][l]); cudaFree(h->d_NF[k][l]); h->d_T[k][l] = nullptr; h->d_NF[k][l] = nullptr; }
+      CU_TRY(h, cudaMalloc(&h->d_H[k], npad * sizeof(float)));
+    }
   }
+  for (int k = 0; k < 2; ++k)
+    for (int l = 1; l <= kmax[k]; ++l)
+      if (!h->d_T[k][l]) {
+        CU_TRY(h, cudaMalloc(&h->d_T[k][l], npad * sizeof(float2)));
+        CU_TRY(h, cudaMalloc(&h->d_NF[k][l], npad));
+      }
   int rc = ensure_stage(h, ncell * sizeof(float));
   if (rc) return rc;
   const float* src[2] = {elevation, elevation_masked};
   for (int k = 0; k < 2; ++k) {
     CU_TRY(h, cudaMemcpyAsync(h->d_stage, src[k], ncell * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    reverse_columns_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>((const float*)h->d_stage, h->d_H[k], rows, cols);
+    reverse_columns_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>((const float*)h->d_stage, h->d_H[k], rows, cols, pitch);
     CU_TRY(h, cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    for (int l = 1; l <= kmax[k]; ++l) {
+      build_level_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_H[k], l > 1 ? h->d_T[k][l - 1] : nullptr,
+                                                                  l > 1 ? h->d_NF[k][l - 1] : nullptr, h->d_T[k][l],
+                                                                  h->d_NF[k][l], rows, cols, pitch, 1 << (l - 1));
+      CU_TRY(h, cudaGetLastError());
+      h->stats.kernel_launches += 1;
+    }
   }
   CU_TRY(h, cudaStreamSynchronize(h->stream));
-  h->stats.kernel_launches += 2;
-  h->rows = rows; h->cols = cols;
-  f.H = h->d_H[0]; h->chk.f[0] = f;
-  f.H = h->d_H[1]; h->chk.f[1] = f;
+  h->rows = rows; h->cols = cols; h->pitch = pitch;
+  f.pitch = pitch;
+  for (int k = 0; k < 2; ++k) {
+    f.H = h->d_H[k];
+    f.kmax = kmax[k];
+    for (int l = 0; l <= artp::kMaxLevel; ++l) { f.T[l] = (l >= 1 && l <= kmax[k]) ? h->d_T[k][l] : nullptr; f.NF[l] = (l >= 1 && l <= kmax[k]) ? h->d_NF[k][l] : nullptr; }
+    h->chk.f[k] = f;
+  }
   h->chk.Lx = Lx; h->chk.Ly = Ly; h->chk.cx = cx; h->chk.cy = cy;
   h->chk.cell_margin = 0.02f + 2e-6f * (float)std::max(rows, cols);
   h->has_map = true;

@@ -15,9 +15,18 @@
 namespace artp {
 
 // One heightfield layer as ODE sees it (dxHeightfieldData::SetData, ode/ode/src/heightfield.cpp:130-169).
+constexpr int kMaxLevel = 6;   // range tables for windows up to 64 x 64 vertices
+
 struct Field {
-  const float* H;  // H[x + z*nx] = layer(x, nz-1-z): column-reversed copy (height_map_box_checker.cpp:44)
+  const float* H;  // H[x + z*pitch] = layer(x, nz-1-z): column-reversed copy (height_map_box_checker.cpp:44)
   int nx, nz;      // m_nWidthSamples (rows), m_nDepthSamples (cols)
+  int pitch;       // row stride in floats (multiple of 4 -> 16 B aligned rows)
+  // Range tables (exact, idempotent reductions): level k holds, for every (x,z), the reduction over the
+  // 2^k x 2^k vertex window starting there: T[k][x + z*pitch] = (max h, min over finite h or +inf),
+  // NF[k][x + z*pitch] = 1 if the window holds a non-finite height. Built at artp_set_map for k = 1..kmax.
+  const float2* T[kMaxLevel + 1];
+  const unsigned char* NF[kMaxLevel + 1];
+  int kmax;
   float W, D, hW, hD, sW, sD, asp, iW, iD;
   float px, py;    // heightfield body position (float casts of the map centre)
 };
@@ -40,6 +49,16 @@ struct BoxCtx {
   float minB, maxB;
   int x0, x1, z0, z1;
 };
+
+// nextafterf(x, -inf) / nextafterf(x, +inf) for finite x (dNextAfter, ode/include/ode/common.h:296), as integer ops.
+__device__ __forceinline__ float next_down(float x) {
+  if (x == 0.0f) return __int_as_float(0x80000001);
+  return __int_as_float(__float_as_int(x) + ((x > 0.0f) ? -1 : 1));
+}
+__device__ __forceinline__ float next_up(float x) {
+  if (x == 0.0f) return __int_as_float(0x00000001);
+  return __int_as_float(__float_as_int(x) + ((x > 0.0f) ? 1 : -1));
+}
 
 __device__ __forceinline__ float rsqrt_exact(float x) { return __fdiv_rn(1.0f, __fsqrt_rn(x)); }
 
@@ -143,10 +162,10 @@ __device__ __forceinline__ bool box_setup(const Field& f, const float side[3], c
   b.maxB = b.P[1] + yr;
   if (a0 > f.W || a4 > f.D) return false;
   if (a1 < 0.0f || a5 < 0.0f) return false;
-  int nMinX = (int)floorf(nextafterf(a0 * f.iW, -CUDART_INF_F));
-  int nMaxX = (int)ceilf(nextafterf(a1 * f.iW, CUDART_INF_F));
-  int nMinZ = (int)floorf(nextafterf(a4 * f.iD, -CUDART_INF_F));
-  int nMaxZ = (int)ceilf(nextafterf(a5 * f.iD, CUDART_INF_F));
+  int nMinX = (int)floorf(next_down(a0 * f.iW));
+  int nMaxX = (int)ceilf(next_up(a1 * f.iW));
+  int nMinZ = (int)floorf(next_down(a4 * f.iD));
+  int nMaxZ = (int)ceilf(next_up(a5 * f.iD));
   b.x0 = max(nMinX, 0);
   b.x1 = min(nMaxX, f.nx - 1);
   b.z0 = max(nMinZ, 0);

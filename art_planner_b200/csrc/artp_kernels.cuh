@@ -20,7 +20,7 @@ namespace artp {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kMaxCand = 64;          // 32 lanes x (Up, Down)
-constexpr int kBloomWords = 64;       // 2048-bit filter per warp
+constexpr int kBloomWords = 128;      // 4096-bit filter per warp
 constexpr unsigned kFull = 0xffffffffu;
 
 enum { R_FREE = 0, R_HIT = 1, R_DEFER = 2 };
@@ -43,7 +43,7 @@ struct Work {
 };
 
 __device__ __forceinline__ uint32_t bloom_hash(int kx, int kz) {
-  return (((uint32_t)kx * 0x9E3779B1u) ^ ((uint32_t)kz * 0x85EBCA77u)) >> 21;   // 11 bits
+  return (((uint32_t)kx * 0x9E3779B1u) ^ ((uint32_t)kz * 0x85EBCA77u)) >> 20;   // 12 bits
 }
 constexpr float kKeyScale = 16384.0f;   // bucket width 2^-14 on n0, n2 in [-1, 1]
 constexpr float kKeyMargin = 4e-6f;     // > eps + rsqrt.approx error + quantisation error
@@ -96,8 +96,8 @@ __device__ __forceinline__ uint32_t item_slot(const Work& w, uint32_t item) {
 
 // Heights of the four corners of cell (cx, cz): A(x,z) B(x+1,z) C(x,z+1) D(x+1,z+1).
 __device__ __forceinline__ void load_cell(const Field& f, int cx, int cz, float& hA, float& hB, float& hC, float& hD) {
-  const float* p = f.H + (size_t)cz * f.nx + cx;
-  hA = __ldg(p); hB = __ldg(p + 1); hC = __ldg(p + f.nx); hD = __ldg(p + f.nx + 1);
+  const float* p = f.H + (size_t)cz * f.pitch + cx;
+  hA = __ldg(p); hB = __ldg(p + 1); hC = __ldg(p + f.pitch); hD = __ldg(p + f.pitch + 1);
 }
 
 // Exact plane of the Up / Down triangle of cell (cx, cz).
@@ -111,30 +111,57 @@ __device__ __forceinline__ void cell_plane(const Field& f, bool isUp, int cx, in
 // -------------------------------------------------------------------------------------------------
 // K1: warp-level box-vs-heightfield decision. Returns R_FREE / R_HIT / R_DEFER (warp-uniform).
 // -------------------------------------------------------------------------------------------------
+
+// Zone min / max / all-finite (heightfield.cpp:1002-1026). Fast path: exact range tables -- the zone is covered
+// by <= 32 overlapping 2^k x 2^k windows (one table entry per lane; max/min/or are idempotent so overlap is
+// harmless). Fallback (tiny or very elongated zones, e.g. clipped at the map border): stride the zone itself.
+__device__ __forceinline__ void zone_reduce(const Field& f, const BoxCtx& b, int lane, float& maxY, float& minY,
+                                            bool& allFinite) {
+  const int nX = b.x1 - b.x0 + 1, nZ = b.z1 - b.z0 + 1;
+  float mx = -CUDART_INF_F, mn = CUDART_INF_F;
+  bool fin = true;
+  const int k = 31 - __clz(min(nX, nZ));
+  const int cx = (nX + (1 << k) - 1) >> k, cz = (nZ + (1 << k) - 1) >> k;
+  if (k >= 1 && k <= f.kmax && cx * cz <= 32) {
+    if (lane < cx * cz) {
+      const int iz = lane / cx, ix = lane - iz * cx, s = 1 << k;
+      const int xs = min(b.x0 + ix * s, b.x1 - s + 1), zs = min(b.z0 + iz * s, b.z1 - s + 1);
+      const size_t idx = (size_t)zs * f.pitch + xs;
+      const float2 v = __ldg(f.T[k] + idx);
+      mx = v.x; mn = v.y;
+      fin = __ldg(f.NF[k] + idx) == 0;
+    }
+  } else {
+    const int nV = nX * nZ;
+    const uint32_t magicX = (nX > 1) ? (0xFFFFFFFFu / (uint32_t)nX + 1u) : 0u;
+    const float* base = f.H + (size_t)b.z0 * f.pitch + b.x0;
+    for (int t = lane; t < nV; t += 32) {
+      const int zi = (nX > 1) ? (int)__umulhi((uint32_t)t, magicX) : t;
+      const int xi = t - zi * nX;
+      const float h = __ldg(base + (size_t)zi * f.pitch + xi);
+      mx = fmaxf(mx, h);
+      if (finitef(h)) mn = fminf(mn, h); else fin = false;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+    mn = fminf(mn, __shfl_xor_sync(kFull, mn, o));
+  }
+  allFinite = __all_sync(kFull, fin);
+  maxY = mx; minY = mn;
+}
+
 __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws, int lane, float cell_margin) {
   const int nX = b.x1 - b.x0 + 1, nZ = b.z1 - b.z0 + 1;
   const int nV = nX * nZ;
   const uint32_t magicX = (nX > 1) ? (0xFFFFFFFFu / (uint32_t)nX + 1u) : 0u;
-  const float* base = f.H + (size_t)b.z0 * f.nx + b.x0;
+  const float* base = f.H + (size_t)b.z0 * f.pitch + b.x0;
 
-  // (1) zone scan (heightfield.cpp:1002-1026)
-  float mx = -CUDART_INF_F, mn = CUDART_INF_F;
-  bool fin = true;
-  for (int t = lane; t < nV; t += 32) {
-    const int zi = (nX > 1) ? (int)__umulhi((uint32_t)t, magicX) : t;
-    const int xi = t - zi * nX;
-    const float h = __ldg(base + (size_t)zi * f.nx + xi);
-    mx = (mx > h) ? mx : h;
-    if (finitef(h)) mn = (mn > h) ? h : mn; else fin = false;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float a = __shfl_xor_sync(kFull, mx, o), c = __shfl_xor_sync(kFull, mn, o);
-    mx = (mx > a) ? mx : a;
-    mn = (mn > c) ? c : mn;
-  }
-  const bool allFinite = __all_sync(kFull, fin);
-  const float maxY = mx, minY = mn;
+  // (1) zone reductions
+  float maxY, minY;
+  bool allFinite;
+  zone_reduce(f, b, lane, maxY, minY, allFinite);
 
   // (2) early outs (heightfield.cpp:1027-1064, 1139-1160)
   if (b.minB - maxY > -ARTP_EPS) return R_FREE;                                            // above
@@ -152,21 +179,19 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
   const uint32_t magicC = (nCX > 1) ? (0xFFFFFFFFu / (uint32_t)nCX + 1u) : 0u;
   if (allFinite) {
     // every colliding vertex belongs to some kept triangle (all finite, >= 1 cell)
-    for (int t0 = 0; t0 < nV; t0 += 32) {
-      const int t = t0 + lane;
-      bool col = false;
-      float h = 0.0f;
-      int xi = 0, zi = 0;
-      if (t < nV) {
-        zi = (nX > 1) ? (int)__umulhi((uint32_t)t, magicX) : t;
-        xi = t - zi * nX;
-        h = __ldg(base + (size_t)zi * f.nx + xi);
-        col = h > b.minB;
+    for (int t0 = 0; t0 < nV; t0 += 64) {
+      bool hit = false;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int t = t0 + 32 * u + lane;
+        if (t < nV) {
+          const int zi = (nX > 1) ? (int)__umulhi((uint32_t)t, magicX) : t;
+          const int xi = t - zi * nX;
+          const float h = __ldg(base + (size_t)zi * f.pitch + xi);
+          if (h > b.minB) hit = hit || vertex_inside(b, (b.x0 + xi) * f.sW, h, (b.z0 + zi) * f.sD);
+        }
       }
-      if (__any_sync(kFull, col)) {
-        const bool hit = col && vertex_inside(b, (b.x0 + xi) * f.sW, h, (b.z0 + zi) * f.sD);
-        if (__any_sync(kFull, hit)) return R_HIT;
-      }
+      if (__any_sync(kFull, hit)) return R_HIT;
     }
   } else {
     for (int t0 = 0; t0 < nC; t0 += 32) {
@@ -196,8 +221,6 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
   // ulps), so only triangles in the cells under the 8 corners (+- cell_margin) can report one.
   {
     for (int i = lane; i < kBloomWords; i += 32) ws.bloom[i] = 0u;
-    ws.cidx[2 * lane] = -1;
-    ws.cidx[2 * lane + 1] = -1;
     __syncwarp();
     const int corner = lane >> 2, sub = lane & 3;
     float px = b.P[0], pz = b.P[2];
@@ -213,7 +236,10 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
     const int ccx = (sub & 1) ? cxh : cxl, ccz = (sub & 2) ? czh : czl;
     bool act = !((sub & 1) && cxh == cxl) && !((sub & 2) && czh == czl);
     act = act && ccx >= b.x0 && ccx < b.x1 && ccz >= b.z0 && ccz < b.z1;
-    bool live_any = false, hit_own = false;
+    bool hit_own = false;
+    bool live[2] = {false, false};
+    float lpl[2][4];
+    int lidx[2] = {-1, -1};
     if (act) {
       float hA, hB, hC, hD;
       load_cell(f, ccx, ccz, hA, hB, hC, hD);
@@ -225,7 +251,7 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
       for (int u = 0; u < 2; ++u) {
         if (!keep[u]) continue;
         const bool isUp = (u == 0);
-        float pl[4];
+        float* pl = lpl[u];
         cell_plane(f, isUp, ccx, ccz, hA, hB, hC, hD, pl);
         // Liveness: any plane within eps of this one changes the box-plane depth by far less than tau.
         const float Q1 = pl[0] * b.R1[0] + pl[1] * b.R1[3] + pl[2] * b.R1[6];
@@ -236,10 +262,8 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
         const float tau = 16.0f * ARTP_EPS * (1.0f + b.side[0] + b.side[1] + b.side[2] + fabsf(b.P[0]) +
                                               fabsf(b.P[1]) + fabsf(b.P[2]) + fabsf(pl[3]));
         if (!(depth >= -tau)) continue;   // dead: no plane of its would-be group can touch the box
-        live_any = true;
-        const int slot = 2 * lane + u;
-        ws.cpl[slot][0] = pl[0]; ws.cpl[slot][1] = pl[1]; ws.cpl[slot][2] = pl[2]; ws.cpl[slot][3] = pl[3];
-        ws.cidx[slot] = cell_idx + u;
+        live[u] = true;
+        lidx[u] = cell_idx + u;
         // bloom keys of every bucket an eps-matching normal may fall into
         const int kx0 = (int)floorf((pl[0] - kKeyMargin + 1.0f) * kKeyScale), kx1 = (int)floorf((pl[0] + kKeyMargin + 1.0f) * kKeyScale);
         const int kz0 = (int)floorf((pl[2] - kKeyMargin + 1.0f) * kKeyScale), kz1 = (int)floorf((pl[2] + kKeyMargin + 1.0f) * kKeyScale);
@@ -255,7 +279,21 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
         for (int i = 0; i < nc; ++i) hit_own = hit_own || on_tri(f, isUp, tcx, tcz, cx[i], cz[i]);
       }
     }
-    if (!__any_sync(kFull, live_any)) return R_FREE;
+    // compact the live candidates: [Up of lanes..., Down of lanes...]
+    const unsigned m0 = __ballot_sync(kFull, live[0]), m1 = __ballot_sync(kFull, live[1]);
+    const int nLive = __popc(m0) + __popc(m1);
+    if (nLive == 0) return R_FREE;
+    const unsigned below = (1u << lane) - 1u;
+    if (live[0]) {
+      const int p = __popc(m0 & below);
+      ws.cpl[p][0] = lpl[0][0]; ws.cpl[p][1] = lpl[0][1]; ws.cpl[p][2] = lpl[0][2]; ws.cpl[p][3] = lpl[0][3];
+      ws.cidx[p] = lidx[0];
+    }
+    if (live[1]) {
+      const int p = __popc(m0) + __popc(m1 & below);
+      ws.cpl[p][0] = lpl[1][0]; ws.cpl[p][1] = lpl[1][1]; ws.cpl[p][2] = lpl[1][2]; ws.cpl[p][3] = lpl[1][3];
+      ws.cidx[p] = lidx[1];
+    }
     __syncwarp();
 
     // (5) is any live candidate epsilon-mergeable with an EARLIER kept triangle? (greedy grouping,
@@ -278,7 +316,6 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             if (!keep[u]) continue;
-            // un-normalised normal, same formulas as tri_plane
             float c0, c1, c2;   // value-identical to tri_plane's cross product (zero terms dropped)
             if (u == 0) {   // Up (A,B,C): E1 = C-A = (0, hC-hA, zC-zA), E2 = B-A = (xB-xA, hB-hA, 0); c = E1 x E2
               const float e1y = hC - hA, e1z = zC - zA, e2x = xB - xA, e2y = hB - hA;
@@ -294,7 +331,7 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
               float pl[4];
               cell_plane(f, u == 0, cx, cz, hA, hB, hC, hD, pl);
               const int idx = cell_idx + u;
-              for (int s = 0; s < kMaxCand; ++s) {
+              for (int s = 0; s < nLive; ++s) {
                 if (ws.cidx[s] > idx && plane_match(pl, ws.cpl[s])) merge = true;
               }
             }
@@ -303,45 +340,87 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
       }
       if (__any_sync(kFull, merge)) return R_DEFER;
     }
-    return __any_sync(kFull, hit_own) ? R_HIT : R_FREE;
+    const int res = __any_sync(kFull, hit_own) ? R_HIT : R_FREE;
+    __syncwarp();   // scratch is reused by the next box
+    return res;
   }
 }
 
 // Full pose decision for one work item, warp-cooperative. Returns 0 invalid / 1 valid / 2 defer.
+// The five boxes (torso + 4 feet) share the orthogonalised rotation; their centres, map-inside tests, AABBs and
+// zones are set up in parallel by lanes 0..4 and broadcast when each box is processed.
 __device__ int pose_valid_warp(const Checker& c, const double s[7], WarpScratch& ws, int lane) {
-  float t[3], R[9], Rb[9], tt[3];
+  float t[3], R[9], Rb[9];
   pose3_from_se3(s, t, R);
 #pragma unroll
   for (int i = 0; i < 9; ++i) Rb[i] = R[i];
   orthogonalize_r(Rb);   // dBodySetRotation of the same matrix for all five boxes
   BoxCtx b;
-  // torso (validity_checker.cpp:41-43, validity_checker_body.cpp:27-42): valid iff NO collision
-  compose_translation(R, t, c.torso_off[0], c.torso_off[1], c.torso_off[2], tt);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { b.R1[j] = -Rb[j]; b.R1[3 + j] = Rb[6 + j]; b.R1[6 + j] = Rb[3 + j]; }
+  const Field& g = c.f[0];   // both layers share the map geometry
+  // ---- lane-parallel box setup ----
+  const int bl = (lane < 5) ? lane : 0;
+  const bool foot = bl > 0;
+  const int fk = bl - 1;
+  const float ox = foot ? ((fk & 2) ? -c.feet_ox : c.feet_ox) : c.torso_off[0];
+  const float oy = foot ? ((fk & 1) ? -c.feet_oy : c.feet_oy) : c.torso_off[1];
+  const float oz = foot ? 0.0f : c.torso_off[2];
+  const float sd0 = foot ? c.side[1][0] : c.side[0][0], sd1 = foot ? c.side[1][1] : c.side[0][1],
+              sd2 = foot ? c.side[1][2] : c.side[0][2];
+  float tt[3];
+  compose_translation(R, t, ox, oy, oz, tt);
+  int status = 0;          // 0 outside the map, 1 rejected by the AABB-vs-extent test, 2 zone ready
+  float P0 = 0.f, P1 = 0.f, P2 = 0.f, minB = 0.f, maxB = 0.f;
+  int x0 = 0, x1 = 0, z0 = 0, z1 = 0;
   if (is_inside(c, tt[0], tt[1])) {
-    if (box_setup(c.f[0], c.side[0], tt, Rb, b)) {
-      const int r = box_collide_warp(c.f[0], b, ws, lane, c.cell_margin);
-      if (r == R_DEFER) return 2;
-      if (r == R_HIT) return 0;
+    // dCollideHeightfield prologue + dxBox::computeAABB, see box_setup()
+    const float d0 = tt[0] - g.px, d1 = tt[1] - g.py, d2 = tt[2] - 0.0f;
+    P0 = -d0 + g.hW; P1 = d2; P2 = d1 + g.hD;
+    const float xr = 0.5f * (fabsf(b.R1[0] * sd0) + fabsf(b.R1[1] * sd1) + fabsf(b.R1[2] * sd2));
+    const float yr = 0.5f * (fabsf(b.R1[3] * sd0) + fabsf(b.R1[4] * sd1) + fabsf(b.R1[5] * sd2));
+    const float zr = 0.5f * (fabsf(b.R1[6] * sd0) + fabsf(b.R1[7] * sd1) + fabsf(b.R1[8] * sd2));
+    const float a0 = P0 - xr, a1 = P0 + xr, a4 = P2 - zr, a5 = P2 + zr;
+    minB = P1 - yr; maxB = P1 + yr;
+    status = 1;
+    if (!(a0 > g.W || a4 > g.D) && !(a1 < 0.0f || a5 < 0.0f)) {
+      status = 2;
+      x0 = max((int)floorf(next_down(a0 * g.iW)), 0);
+      x1 = min((int)ceilf(next_up(a1 * g.iW)), g.nx - 1);
+      z0 = max((int)floorf(next_down(a4 * g.iD)), 0);
+      z1 = min((int)ceilf(next_up(a5 * g.iD)), g.nz - 1);
     }
   }
-  // feet (validity_checker_feet.cpp:32-70): every reach box MUST collide; early break
+  // ---- boxes in the reference's order with its short-circuits ----
 #pragma unroll 1
-  for (int k = 0; k < 4; ++k) {
-    const float ox = (k & 2) ? -c.feet_ox : c.feet_ox, oy = (k & 1) ? -c.feet_oy : c.feet_oy;
-    compose_translation(R, t, ox, oy, 0.0f, tt);
-    if (!is_inside(c, tt[0], tt[1])) {
-      if (c.unknown_untraversable) return 0;
+  for (int k = 0; k < 5; ++k) {
+    const int st = __shfl_sync(kFull, status, k);
+    const bool is_foot = k > 0;
+    if (st == 0) {                       // outside the map
+      if (!is_foot) continue;            // torso: "no collision" (validity_checker_body.cpp:29-32)
+      if (c.unknown_untraversable) return 0;   // validity_checker_feet.cpp:34-37
       continue;
     }
-    if (!box_setup(c.f[1], c.side[1], tt, Rb, b)) return 0;
-    const int r = box_collide_warp(c.f[1], b, ws, lane, c.cell_margin);
+    if (st == 1) {                       // dCollide returns 0
+      if (is_foot) return 0;
+      continue;
+    }
+    b.P[0] = __shfl_sync(kFull, P0, k); b.P[1] = __shfl_sync(kFull, P1, k); b.P[2] = __shfl_sync(kFull, P2, k);
+    b.minB = __shfl_sync(kFull, minB, k); b.maxB = __shfl_sync(kFull, maxB, k);
+    b.x0 = __shfl_sync(kFull, x0, k); b.x1 = __shfl_sync(kFull, x1, k);
+    b.z0 = __shfl_sync(kFull, z0, k); b.z1 = __shfl_sync(kFull, z1, k);
+    b.side[0] = is_foot ? c.side[1][0] : c.side[0][0];
+    b.side[1] = is_foot ? c.side[1][1] : c.side[0][1];
+    b.side[2] = is_foot ? c.side[1][2] : c.side[0][2];
+    const int r = box_collide_warp(is_foot ? c.f[1] : c.f[0], b, ws, lane, c.cell_margin);
     if (r == R_DEFER) return 2;
-    if (r == R_FREE) return 0;
+    if (!is_foot) { if (r == R_HIT) return 0; }     // torso must be free
+    else { if (r == R_FREE) return 0; }              // every reach box must touch
   }
   return 1;
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
 check_items_warp_kernel(const Checker c, const Work w, uint32_t* __restrict__ work_counter,
                         uint32_t* __restrict__ defer_count, uint32_t* __restrict__ defer_list, int force_defer) {
   __shared__ WarpScratch ws_all[kWarpsPerCta];
@@ -412,12 +491,12 @@ __device__ __forceinline__ float block_reduce_max(float v, float* red, bool is_m
 __device__ int box_collide_block(const Field& f, const BoxCtx& b, const BlockShared& sh, float* red, int* s_next) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int nX = b.x1 - b.x0 + 1, nZ = b.z1 - b.z0 + 1, nV = nX * nZ;
-  const float* base = f.H + (size_t)b.z0 * f.nx + b.x0;
+  const float* base = f.H + (size_t)b.z0 * f.pitch + b.x0;
   float mx = -CUDART_INF_F, mn = CUDART_INF_F;
   int fin = 1;
   for (int t = tid; t < nV; t += nthr) {
     const int zi = t / nX, xi = t - zi * nX;
-    const float h = __ldg(base + (size_t)zi * f.nx + xi);
+    const float h = __ldg(base + (size_t)zi * f.pitch + xi);
     mx = (mx > h) ? mx : h;
     if (finitef(h)) mn = (mn > h) ? h : mn; else fin = 0;
   }
