@@ -31,7 +31,7 @@ class ArtpParams(C.Structure):
 
 class ArtpStats(C.Structure):
     _fields_ = [("poses_checked", C.c_uint64), ("poses_deferred", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("last_deferred", C.c_uint32), ("last_launches", C.c_uint32)]
+                ("last_deferred", C.c_uint32), ("last_launches", C.c_uint32), ("last_queued_boxes", C.c_uint32)]
 
 
 _lib = None
@@ -63,7 +63,7 @@ def load():
     lib.artp_get_stats.argtypes = [vp, C.POINTER(ArtpStats)]
     lib.artp_set_mode.argtypes = [vp, i32]
     lib.artp_set_timing.argtypes = [vp, i32]
-    lib.artp_get_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.artp_get_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
     lib.artp_version.restype = C.c_char_p
     _lib = lib
     return lib

@@ -141,10 +141,11 @@ class StateValidityChecker:
         self._h.check(self._h.lib.artp_set_timing(self._h.h, int(bool(enable))))
 
     def lastKernelTimesMs(self):
-        """(warp kernel ms, plane-grouping kernel ms) of the most recent check call (CUDA events on its stream)."""
-        a, b = C.c_float(), C.c_float()
-        self._h.check(self._h.lib.artp_get_last_timing(self._h.h, C.byref(a), C.byref(b)))
-        return float(a.value), float(b.value)
+        """(classify ms, box warp stage ms, plane-grouping stage ms) of the most recent check call (CUDA events
+        recorded by the library on the call's stream)."""
+        ms = (C.c_float * 3)()
+        self._h.check(self._h.lib.artp_get_last_timing(self._h.h, ms))
+        return float(ms[0]), float(ms[1]), float(ms[2])
 
     @property
     def handle(self) -> _Handle:

@@ -31,8 +31,10 @@ struct Handle {
   int rows = 0, cols = 0;
   bool has_map = false;
   uint32_t* d_ctr = nullptr;        // [0] work counter, [1] defer count, [2] K2 overflow, [3] compaction total
-  uint32_t* d_defer = nullptr;      // deferred item list
+  uint32_t* d_defer = nullptr;      // deferred record list
   size_t defer_cap = 0;
+  artp::BoxRec* d_recs = nullptr;   // stage-A -> stage-B box queue
+  size_t recs_cap = 0;
   uint32_t* d_block_counts = nullptr;
   size_t block_counts_cap = 0;
   void* d_stage = nullptr;          // device staging for the host-buffer API
@@ -41,7 +43,7 @@ struct Handle {
   int k1_grid = 0, k2_grid = 0, k2_smem = 0, k2_tcap = 0;
   int mode = 0;
   int timing = 0;
-  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
   bool deferred_unread = false;
   artp_stats stats{};
@@ -183,14 +185,19 @@ __global__ void compact_scatter_kernel(const uint8_t* __restrict__ valid, size_t
   }
 }
 
-int ensure_defer(Handle* h, size_t n_items, cudaStream_t s) {
-  if (h->defer_cap >= n_items) return ARTP_OK;
+constexpr size_t kChunkItems = 1u << 20;   // work items per internal launch round (bounds the box queue)
+
+int ensure_queues(Handle* h, size_t n_items, cudaStream_t s) {
+  const size_t need = 5 * std::min(n_items, kChunkItems);
+  if (h->recs_cap >= need) return ARTP_OK;
   CU_TRY(h, cudaStreamSynchronize(s));
   if (h->d_defer) CU_TRY(h, cudaFree(h->d_defer));
-  h->d_defer = nullptr;
-  const size_t cap = std::max<size_t>(n_items, 1u << 16);
+  if (h->d_recs) CU_TRY(h, cudaFree(h->d_recs));
+  h->d_defer = nullptr; h->d_recs = nullptr;
+  const size_t cap = std::max<size_t>(need, 1u << 16);
+  CU_TRY(h, cudaMalloc(&h->d_recs, cap * sizeof(artp::BoxRec)));
   CU_TRY(h, cudaMalloc(&h->d_defer, cap * sizeof(uint32_t)));
-  h->defer_cap = cap;
+  h->recs_cap = cap; h->defer_cap = cap;
   return ARTP_OK;
 }
 
@@ -204,22 +211,35 @@ int ensure_stage(Handle* h, size_t bytes) {
   return ARTP_OK;
 }
 
-// Launch K1 (+K2) for a prepared Work on stream s.
-int run_items(Handle* h, const artp::Work& w, cudaStream_t s) {
-  int rc = ensure_defer(h, w.n_items, s);
+// Launch stages A, B, C for a prepared Work on stream s (in rounds of kChunkItems work items).
+int run_items(Handle* h, artp::Work w, cudaStream_t s) {
+  const size_t n_total = w.n_items;
+  int rc = ensure_queues(h, n_total, s);
   if (rc) return rc;
-  CU_TRY(h, cudaMemsetAsync(h->d_ctr, 0, 3 * sizeof(uint32_t), s));
-  if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[0], s));
-  artp::check_items_warp_kernel<<<h->k1_grid, artp::kWarpsPerCta * 32, 0, s>>>(h->chk, w, h->d_ctr, h->d_ctr + 1,
-                                                                                h->d_defer, h->mode == 1);
-  CU_TRY(h, cudaGetLastError());
-  if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[1], s));
-  artp::check_items_block_kernel<<<h->k2_grid, 256, h->k2_smem, s>>>(h->chk, w, h->d_ctr + 1, h->d_defer, h->k2_tcap,
-                                                                      h->d_ctr + 2);
-  CU_TRY(h, cudaGetLastError());
-  if (h->timing) { CU_TRY(h, cudaEventRecord(h->ev[2], s)); h->ev_valid = true; }
-  h->stats.kernel_launches += 2;
-  h->stats.last_launches = 2;
+  uint32_t launches = 0;
+  for (size_t base = 0; base < n_total; base += kChunkItems) {
+    const size_t end = std::min(n_total, base + kChunkItems);
+    w.item_base = (uint32_t)base;
+    w.n_items = (uint32_t)end;
+    const bool last = end == n_total;
+    CU_TRY(h, cudaMemsetAsync(h->d_ctr, 0, 4 * sizeof(uint32_t), s));
+    if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[0], s));
+    artp::classify_items_kernel<<<(unsigned)((end - base + 127) / 128), 128, 0, s>>>(h->chk, w, h->d_recs, h->d_ctr + 3,
+                                                                                      h->mode == 1);
+    CU_TRY(h, cudaGetLastError());
+    if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[1], s));
+    artp::box_items_warp_kernel<<<h->k1_grid, artp::kWarpsPerCta * 32, 0, s>>>(h->chk, w, h->d_recs, h->d_ctr + 3, h->d_ctr,
+                                                                                h->d_ctr + 1, h->d_defer, h->mode == 1);
+    CU_TRY(h, cudaGetLastError());
+    if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[2], s));
+    artp::box_items_block_kernel<<<h->k2_grid, 256, h->k2_smem, s>>>(h->chk, w, h->d_recs, h->d_ctr + 1, h->d_defer,
+                                                                      h->k2_tcap, h->d_ctr + 2);
+    CU_TRY(h, cudaGetLastError());
+    if (h->timing && last) { CU_TRY(h, cudaEventRecord(h->ev[3], s)); h->ev_valid = true; }
+    launches += 3;
+  }
+  h->stats.kernel_launches += launches;
+  h->stats.last_launches = launches;
   h->deferred_unread = true;
   return ARTP_OK;
 }
@@ -269,12 +289,12 @@ int artp_create(const artp_params* params, artp_handle** out) {
   if ((e = cudaGetDeviceProperties(&prop, h->device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
   h->sm_count = prop.multiProcessorCount;
   cudaFuncAttributes fa;
-  if ((e = cudaFuncGetAttributes(&fa, artp::check_items_warp_kernel)) != cudaSuccess)
+  if ((e = cudaFuncGetAttributes(&fa, artp::box_items_warp_kernel)) != cudaSuccess)
     return fail("no usable kernel image (built for sm_100a)", e);
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaMalloc(&h->d_ctr, 8 * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc", e);
   int per_sm = 0;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, artp::check_items_warp_kernel,
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, artp::box_items_warp_kernel,
                                                          artp::kWarpsPerCta * 32, 0)) != cudaSuccess)
     return fail("occupancy", e);
   h->k1_grid = h->sm_count * std::max(per_sm, 1);
@@ -298,8 +318,8 @@ void artp_destroy(artp_handle* hh) {
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   for (int k = 0; k < 2; ++k) for (int l = 0; l <= artp::kMaxLevel; ++l) { cudaFree(h->d_T[k][l]); cudaFree(h->d_NF[k][l]); }
   cudaFree(h->d_H[0]); cudaFree(h->d_H[1]); cudaFree(h->d_ctr); cudaFree(h->d_defer); cudaFree(h->d_stage);
-  cudaFree(h->d_block_counts);
-  for (int i = 0; i < 3; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  cudaFree(h->d_block_counts); cudaFree(h->d_recs);
+  for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
 }
 
@@ -316,21 +336,20 @@ int artp_set_timing(artp_handle* hh, int enable) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   std::lock_guard<std::mutex> lk(h->mtx);
   CU_TRY(h, cudaSetDevice(h->device));
-  if (enable && !h->ev[0]) for (int i = 0; i < 3; ++i) CU_TRY(h, cudaEventCreate(&h->ev[i]));
+  if (enable && !h->ev[0]) for (int i = 0; i < 4; ++i) CU_TRY(h, cudaEventCreate(&h->ev[i]));
   h->timing = enable ? 1 : 0;
   h->ev_valid = false;
   return ARTP_OK;
 }
 
-int artp_get_last_timing(artp_handle* hh, float* warp_kernel_ms, float* group_kernel_ms) {
-  if (!hh || !warp_kernel_ms || !group_kernel_ms) return ARTP_E_INVALID;
+int artp_get_last_timing(artp_handle* hh, float* ms3) {
+  if (!hh || !ms3) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
   std::lock_guard<std::mutex> lk(h->mtx);
   if (!h->timing || !h->ev_valid) { h->err = "timing not enabled or no call recorded"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
-  CU_TRY(h, cudaEventSynchronize(h->ev[2]));
-  CU_TRY(h, cudaEventElapsedTime(warp_kernel_ms, h->ev[0], h->ev[1]));
-  CU_TRY(h, cudaEventElapsedTime(group_kernel_ms, h->ev[1], h->ev[2]));
+  CU_TRY(h, cudaEventSynchronize(h->ev[3]));
+  for (int i = 0; i < 3; ++i) CU_TRY(h, cudaEventElapsedTime(ms3 + i, h->ev[i], h->ev[i + 1]));
   return ARTP_OK;
 }
 
@@ -339,9 +358,10 @@ int artp_get_stats(artp_handle* hh, artp_stats* out) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   std::lock_guard<std::mutex> lk(h->mtx);
   CU_TRY(h, cudaSetDevice(h->device));
-  uint32_t ctr[3] = {0, 0, 0};
+  uint32_t ctr[4] = {0, 0, 0, 0};
   CU_TRY(h, cudaMemcpy(ctr, h->d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost));   // synchronises the device
   h->stats.last_deferred = ctr[1];
+  h->stats.last_queued_boxes = ctr[3];
   if (h->deferred_unread) { h->stats.poses_deferred += ctr[1]; h->deferred_unread = false; }
   *out = h->stats;
   if (ctr[2] != 0) { h->err = "plane-grouping kernel overflow (zone larger than its shared-memory store)"; return ARTP_E_LIMIT; }
@@ -385,9 +405,9 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
     h->err = "box/map resolution combination exceeds the plane-grouping kernel's shared-memory store";
     return ARTP_E_LIMIT;
   }
-  CU_TRY(h, cudaFuncSetAttribute(artp::check_items_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CU_TRY(h, cudaFuncSetAttribute(artp::box_items_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int per_sm = 0;
-  CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, artp::check_items_block_kernel, 256, smem));
+  CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, artp::box_items_block_kernel, 256, smem));
   h->k2_smem = smem; h->k2_tcap = tcap; h->k2_grid = h->sm_count * std::max(per_sm, 1);
   // upload
   CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -447,7 +467,7 @@ int artp_check_poses_device(artp_handle* hh, const double* d_states, size_t n, u
   if (!d_states || !d_valid) { h->err = "null buffer"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
   artp::Work w;
-  w.s1 = nullptr; w.s2 = d_states; w.valid = d_valid; w.n_items = (uint32_t)n; w.steps = 0; w.edge_mode = 0;
+  w.s1 = nullptr; w.s2 = d_states; w.valid = d_valid; w.item_base = 0; w.n_items = (uint32_t)n; w.steps = 0; w.edge_mode = 0;
   rc = run_items(h, w, (cudaStream_t)stream);
   if (rc) return rc;
   h->stats.poses_checked += n;
@@ -495,7 +515,7 @@ int artp_check_motions_device(artp_handle* hh, const double* d_s1, const double*
   fill_u8_kernel<<<std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 8), 256, 0, s>>>(d_valid, n, 1);
   CU_TRY(h, cudaGetLastError());
   artp::Work w;
-  w.s1 = d_s1; w.s2 = d_s2; w.valid = d_valid; w.n_items = (uint32_t)items; w.steps = n_steps; w.edge_mode = 1;
+  w.s1 = d_s1; w.s2 = d_s2; w.valid = d_valid; w.item_base = 0; w.n_items = (uint32_t)items; w.steps = n_steps; w.edge_mode = 1;
   rc = run_items(h, w, s);
   if (rc) return rc;
   h->stats.kernel_launches += 1;

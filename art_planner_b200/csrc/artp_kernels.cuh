@@ -1,17 +1,21 @@
 // art_planner_b200/csrc/artp_kernels.cuh
 // Pose-validity kernels (StateValidityChecker::isValid, validity_checker.cpp:39-45, on top of the ODE
-// box-vs-heightfield decision, heightfield.cpp:973-1964) for sm_100a.
+// box-vs-heightfield decision, heightfield.cpp:973-1964) for sm_100a, as a three-stage pipeline:
 //
-//   K1  check_items_warp_kernel   one warp per work item (pose / interpolated edge state). Lanes stride the
-//       heightfield zone with coalesced fp32 loads, min/max/finite by warp shuffles, vertex-in-box and
-//       plane tests decided by warp ballots. The reference's O(T^2) plane grouping is replaced by an exact
-//       shortcut: only triangles under one of the 8 box corners can ever own a plane-contact point, so only
-//       those "candidate" planes are built; a bloom filter on the (approximate) normal finds any earlier
-//       triangle that could epsilon-merge with a live candidate. If none exists every candidate is its own
-//       group base (exact); otherwise the item is deferred to K2.
-//   K2  check_items_block_kernel  one CTA per deferred item: the full decision including the reference's
-//       greedy, order-dependent epsilon grouping, with all planes staged in shared memory.
-// Both are bit-exact against oracle/ (tests/test_pose_gpu.py).
+//   A  classify_items_kernel     one THREAD per work item (pose / interpolated edge state): quaternion -> R,
+//      dxOrthogonalizeR, the five box centres / map-inside tests / AABBs / zones, the zone min/max/all-finite from
+//      exact range tables (no zone scan), and the collider's four early-outs. Items decided here (the majority)
+//      never touch the heightfield; every box that needs the vertex / plane tests becomes a BoxRec in a queue.
+//   B  box_items_warp_kernel     one WARP per queued box: lanes stride the zone with coalesced fp32 loads,
+//      vertex-in-box and plane tests by warp ballots. The reference's O(T^2) plane grouping is replaced by an
+//      exact shortcut: only triangles under one of the 8 box corners can own a plane-contact point, so only those
+//      "candidate" planes are built; a bloom filter on the (approximate) normal finds any earlier triangle that
+//      could epsilon-merge with a live candidate. None => every candidate is its own group base (exact);
+//      otherwise the box is deferred to C.
+//   C  box_items_block_kernel    one CTA per deferred box: the full decision including the reference's greedy,
+//      order-dependent epsilon grouping, with all planes staged in shared memory.
+// The pose result is a pure AND over its boxes (torso free, every reach box touching), so B and C only ever
+// clear the provisional 1 that A wrote. All three are bit-exact against oracle/ (tests/test_pose_gpu.py).
 #pragma once
 
 #include "artp_device.cuh"
@@ -37,7 +41,8 @@ struct Work {
   const double* s1;     // EDGE: start states; POSE: unused
   const double* s2;     // EDGE: end states;   POSE: the states
   uint8_t* valid;       // per pose / per edge
-  uint32_t n_items;
+  uint32_t item_base;   // first work item of this launch (chunked calls)
+  uint32_t n_items;     // one past the last work item of this launch
   int steps;            // EDGE: interior steps; POSE: 0
   int edge_mode;
 };
@@ -112,6 +117,21 @@ __device__ __forceinline__ void cell_plane(const Field& f, bool isUp, int cx, in
 // K1: warp-level box-vs-heightfield decision. Returns R_FREE / R_HIT / R_DEFER (warp-uniform).
 // -------------------------------------------------------------------------------------------------
 
+// Early outs of dCollideHeightfieldZone (heightfield.cpp:1027-1064, 1139-1160) given the zone reductions.
+// Returns R_FREE / R_HIT, or -1 if the vertex / plane stages are needed.
+__device__ __forceinline__ int zone_early_out(const BoxCtx& b, float maxY, float minY, bool allFinite) {
+  if (b.minB - maxY > -ARTP_EPS) return R_FREE;                                            // above
+  if (minY - b.maxB > -ARTP_EPS) return R_FREE;                                            // under (art_planner mod)
+  if (allFinite && minY - b.minB > -ARTP_EPS && b.maxB - maxY > -ARTP_EPS) return R_HIT;   // spans
+  if (allFinite && maxY - minY < ARTP_EPS) {                                               // single plane
+    const float pl[4] = {0.0f, 1.0f, 0.0f, minY};
+    float cx[4], cz[4];
+    return box_plane(b, pl, 1, cx, cz) > 0 ? R_HIT : R_FREE;
+  }
+  if (b.x1 - b.x0 < 1 || b.z1 - b.z0 < 1) return R_FREE;                                   // no cell, no triangle
+  return -1;
+}
+
 // Zone min / max / all-finite (heightfield.cpp:1002-1026). Fast path: exact range tables -- the zone is covered
 // by <= 32 overlapping 2^k x 2^k windows (one table entry per lane; max/min/or are idempotent so overlap is
 // harmless). Fallback (tiny or very elongated zones, e.g. clipped at the map border): stride the zone itself.
@@ -152,27 +172,21 @@ __device__ __forceinline__ void zone_reduce(const Field& f, const BoxCtx& b, int
   maxY = mx; minY = mn;
 }
 
-__device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws, int lane, float cell_margin) {
+__device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws, int lane, float cell_margin,
+                                bool needs_reduce, bool all_finite_known) {
   const int nX = b.x1 - b.x0 + 1, nZ = b.z1 - b.z0 + 1;
   const int nV = nX * nZ;
   const uint32_t magicX = (nX > 1) ? (0xFFFFFFFFu / (uint32_t)nX + 1u) : 0u;
   const float* base = f.H + (size_t)b.z0 * f.pitch + b.x0;
 
-  // (1) zone reductions
-  float maxY, minY;
-  bool allFinite;
-  zone_reduce(f, b, lane, maxY, minY, allFinite);
-
-  // (2) early outs (heightfield.cpp:1027-1064, 1139-1160)
-  if (b.minB - maxY > -ARTP_EPS) return R_FREE;                                            // above
-  if (minY - b.maxB > -ARTP_EPS) return R_FREE;                                            // under (art_planner mod)
-  if (allFinite && minY - b.minB > -ARTP_EPS && b.maxB - maxY > -ARTP_EPS) return R_HIT;   // spans
-  if (allFinite && maxY - minY < ARTP_EPS) {
-    const float pl[4] = {0.0f, 1.0f, 0.0f, minY};
-    float cx[4], cz[4];
-    return box_plane(b, pl, 1, cx, cz) > 0 ? R_HIT : R_FREE;
+  // (1)+(2) zone reductions and early outs -- normally already done by stage A
+  bool allFinite = all_finite_known;
+  if (needs_reduce) {
+    float maxY, minY;
+    zone_reduce(f, b, lane, maxY, minY, allFinite);
+    const int e = zone_early_out(b, maxY, minY, allFinite);
+    if (e >= 0) return e;
   }
-  if (nX < 2 || nZ < 2) return R_FREE;   // no cell, no triangle
 
   // (3) vertex-in-box test of every colliding vertex of a kept triangle (heightfield.cpp:1306-1441)
   const int nCX = nX - 1, nCZ = nZ - 1, nC = nCX * nCZ;
@@ -346,113 +360,194 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
   }
 }
 
-// Full pose decision for one work item, warp-cooperative. Returns 0 invalid / 1 valid / 2 defer.
-// The five boxes (torso + 4 feet) share the orthogonalised rotation; their centres, map-inside tests, AABBs and
-// zones are set up in parallel by lanes 0..4 and broadcast when each box is processed.
-__device__ int pose_valid_warp(const Checker& c, const double s[7], WarpScratch& ws, int lane) {
-  float t[3], R[9], Rb[9];
-  pose3_from_se3(s, t, R);
+// One queued box (80 bytes): everything stage B/C need, so nothing is recomputed.
+struct BoxRec {
+  float R1[9];
+  float P[3];
+  float minB, maxB;
+  int x0, x1, z0, z1;
+  uint32_t item;     // work item id
+  uint32_t flags;    // bits 0-2: box (0 torso, 1..4 feet); bit 3: zone all finite; bit 4: zone not reduced yet
+};
+enum { REC_ALLFINITE = 8, REC_NEEDS_REDUCE = 16 };
+
+__device__ __forceinline__ void rec_to_ctx(const Checker& c, const BoxRec& r, BoxCtx& b) {
 #pragma unroll
-  for (int i = 0; i < 9; ++i) Rb[i] = R[i];
-  orthogonalize_r(Rb);   // dBodySetRotation of the same matrix for all five boxes
-  BoxCtx b;
-#pragma unroll
-  for (int j = 0; j < 3; ++j) { b.R1[j] = -Rb[j]; b.R1[3 + j] = Rb[6 + j]; b.R1[6 + j] = Rb[3 + j]; }
-  const Field& g = c.f[0];   // both layers share the map geometry
-  // ---- lane-parallel box setup ----
-  const int bl = (lane < 5) ? lane : 0;
-  const bool foot = bl > 0;
-  const int fk = bl - 1;
-  const float ox = foot ? ((fk & 2) ? -c.feet_ox : c.feet_ox) : c.torso_off[0];
-  const float oy = foot ? ((fk & 1) ? -c.feet_oy : c.feet_oy) : c.torso_off[1];
-  const float oz = foot ? 0.0f : c.torso_off[2];
-  const float sd0 = foot ? c.side[1][0] : c.side[0][0], sd1 = foot ? c.side[1][1] : c.side[0][1],
-              sd2 = foot ? c.side[1][2] : c.side[0][2];
-  float tt[3];
-  compose_translation(R, t, ox, oy, oz, tt);
-  int status = 0;          // 0 outside the map, 1 rejected by the AABB-vs-extent test, 2 zone ready
-  float P0 = 0.f, P1 = 0.f, P2 = 0.f, minB = 0.f, maxB = 0.f;
-  int x0 = 0, x1 = 0, z0 = 0, z1 = 0;
-  if (is_inside(c, tt[0], tt[1])) {
-    // dCollideHeightfield prologue + dxBox::computeAABB, see box_setup()
-    const float d0 = tt[0] - g.px, d1 = tt[1] - g.py, d2 = tt[2] - 0.0f;
-    P0 = -d0 + g.hW; P1 = d2; P2 = d1 + g.hD;
-    const float xr = 0.5f * (fabsf(b.R1[0] * sd0) + fabsf(b.R1[1] * sd1) + fabsf(b.R1[2] * sd2));
-    const float yr = 0.5f * (fabsf(b.R1[3] * sd0) + fabsf(b.R1[4] * sd1) + fabsf(b.R1[5] * sd2));
-    const float zr = 0.5f * (fabsf(b.R1[6] * sd0) + fabsf(b.R1[7] * sd1) + fabsf(b.R1[8] * sd2));
-    const float a0 = P0 - xr, a1 = P0 + xr, a4 = P2 - zr, a5 = P2 + zr;
-    minB = P1 - yr; maxB = P1 + yr;
-    status = 1;
-    if (!(a0 > g.W || a4 > g.D) && !(a1 < 0.0f || a5 < 0.0f)) {
-      status = 2;
-      x0 = max((int)floorf(next_down(a0 * g.iW)), 0);
-      x1 = min((int)ceilf(next_up(a1 * g.iW)), g.nx - 1);
-      z0 = max((int)floorf(next_down(a4 * g.iD)), 0);
-      z1 = min((int)ceilf(next_up(a5 * g.iD)), g.nz - 1);
-    }
-  }
-  // ---- boxes in the reference's order with its short-circuits ----
-#pragma unroll 1
-  for (int k = 0; k < 5; ++k) {
-    const int st = __shfl_sync(kFull, status, k);
-    const bool is_foot = k > 0;
-    if (st == 0) {                       // outside the map
-      if (!is_foot) continue;            // torso: "no collision" (validity_checker_body.cpp:29-32)
-      if (c.unknown_untraversable) return 0;   // validity_checker_feet.cpp:34-37
-      continue;
-    }
-    if (st == 1) {                       // dCollide returns 0
-      if (is_foot) return 0;
-      continue;
-    }
-    b.P[0] = __shfl_sync(kFull, P0, k); b.P[1] = __shfl_sync(kFull, P1, k); b.P[2] = __shfl_sync(kFull, P2, k);
-    b.minB = __shfl_sync(kFull, minB, k); b.maxB = __shfl_sync(kFull, maxB, k);
-    b.x0 = __shfl_sync(kFull, x0, k); b.x1 = __shfl_sync(kFull, x1, k);
-    b.z0 = __shfl_sync(kFull, z0, k); b.z1 = __shfl_sync(kFull, z1, k);
-    b.side[0] = is_foot ? c.side[1][0] : c.side[0][0];
-    b.side[1] = is_foot ? c.side[1][1] : c.side[0][1];
-    b.side[2] = is_foot ? c.side[1][2] : c.side[0][2];
-    const int r = box_collide_warp(is_foot ? c.f[1] : c.f[0], b, ws, lane, c.cell_margin);
-    if (r == R_DEFER) return 2;
-    if (!is_foot) { if (r == R_HIT) return 0; }     // torso must be free
-    else { if (r == R_FREE) return 0; }              // every reach box must touch
-  }
-  return 1;
+  for (int i = 0; i < 9; ++i) b.R1[i] = r.R1[i];
+  b.P[0] = r.P[0]; b.P[1] = r.P[1]; b.P[2] = r.P[2];
+  b.minB = r.minB; b.maxB = r.maxB;
+  b.x0 = r.x0; b.x1 = r.x1; b.z0 = r.z0; b.z1 = r.z1;
+  const int w = (r.flags & 7) ? 1 : 0;
+  b.side[0] = c.side[w][0]; b.side[1] = c.side[w][1]; b.side[2] = c.side[w][2];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stage A: one thread per work item.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs, uint32_t* __restrict__ rec_count,
+                      int force_all) {
+  const uint32_t item = w.item_base + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = item < w.n_items;
+  const int lane = threadIdx.x & 31;
+  int result = 1;                 // 1 valid so far, 0 invalid
+  int n_und = 0;                  // undecided boxes of this item
+  BoxCtx ub[5];                   // their contexts (R1 shared -> stored once below)
+  uint32_t uflags[5];
+  float R1[9];
+  uint32_t slot = 0;
+  if (in_range) {
+    slot = item_slot(w, item);
+    double s[7];
+    load_item_state(w, item, s);
+    float t[3], R[9], Rb[9];
+    pose3_from_se3(s, t, R);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rb[i] = R[i];
+    orthogonalize_r(Rb);          // dBodySetRotation of the same matrix for all five boxes
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { R1[j] = -Rb[j]; R1[3 + j] = Rb[6 + j]; R1[6 + j] = Rb[3 + j]; }
+    const Field& g = c.f[0];      // both layers share the map geometry
+#pragma unroll 1
+    for (int k = 0; k < 5 && result; ++k) {
+      const bool foot = k > 0;
+      const int fk = k - 1;
+      const float ox = foot ? ((fk & 2) ? -c.feet_ox : c.feet_ox) : c.torso_off[0];
+      const float oy = foot ? ((fk & 1) ? -c.feet_oy : c.feet_oy) : c.torso_off[1];
+      const float oz = foot ? 0.0f : c.torso_off[2];
+      const float sd0 = foot ? c.side[1][0] : c.side[0][0], sd1 = foot ? c.side[1][1] : c.side[0][1],
+                  sd2 = foot ? c.side[1][2] : c.side[0][2];
+      float tt[3];
+      compose_translation(R, t, ox, oy, oz, tt);
+      if (!is_inside(c, tt[0], tt[1])) {       // validity_checker_body.cpp:29-32, validity_checker_feet.cpp:34-37
+        if (foot && c.unknown_untraversable) result = 0;
+        continue;
+      }
+      // dCollideHeightfield prologue + dxBox::computeAABB (see box_setup())
+      BoxCtx b;
+      const float d0 = tt[0] - g.px, d1 = tt[1] - g.py, d2 = tt[2] - 0.0f;
+      b.P[0] = -d0 + g.hW; b.P[1] = d2; b.P[2] = d1 + g.hD;
+      const float xr = 0.5f * (fabsf(R1[0] * sd0) + fabsf(R1[1] * sd1) + fabsf(R1[2] * sd2));
+      const float yr = 0.5f * (fabsf(R1[3] * sd0) + fabsf(R1[4] * sd1) + fabsf(R1[5] * sd2));
+      const float zr = 0.5f * (fabsf(R1[6] * sd0) + fabsf(R1[7] * sd1) + fabsf(R1[8] * sd2));
+      const float a0 = b.P[0] - xr, a1 = b.P[0] + xr, a4 = b.P[2] - zr, a5 = b.P[2] + zr;
+      b.minB = b.P[1] - yr; b.maxB = b.P[1] + yr;
+      int r;                        // R_FREE / R_HIT / -1 undecided
+      uint32_t fl = (uint32_t)k;
+      if ((a0 > g.W || a4 > g.D) || (a1 < 0.0f || a5 < 0.0f)) {
+        r = R_FREE;                 // dCollide returns 0 (heightfield.cpp:1870-1876)
+      } else {
+        b.x0 = max((int)floorf(next_down(a0 * g.iW)), 0);
+        b.x1 = min((int)ceilf(next_up(a1 * g.iW)), g.nx - 1);
+        b.z0 = max((int)floorf(next_down(a4 * g.iD)), 0);
+        b.z1 = min((int)ceilf(next_up(a5 * g.iD)), g.nz - 1);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) b.R1[i] = R1[i];
+        b.side[0] = sd0; b.side[1] = sd1; b.side[2] = sd2;
+        // zone reductions from the range tables (exact: max/min/or are idempotent, windows may overlap)
+        const Field& f = foot ? c.f[1] : c.f[0];
+        const int nX = b.x1 - b.x0 + 1, nZ = b.z1 - b.z0 + 1;
+        const int kk = 31 - __clz(min(nX, nZ));
+        const int cx = (nX + (1 << kk) - 1) >> kk, cz = (nZ + (1 << kk) - 1) >> kk;
+        if (force_all || kk < 1 || kk > f.kmax || cx * cz > 32) {
+          r = -1; fl |= REC_NEEDS_REDUCE;
+        } else {
+          const float2* __restrict__ T = f.T[kk];
+          const unsigned char* __restrict__ NF = f.NF[kk];
+          const int sW = 1 << kk;
+          float mx = -CUDART_INF_F, mn = CUDART_INF_F;
+          int nf = 0;
+          for (int iz = 0; iz < cz; ++iz) {
+            const int zs = min(b.z0 + iz * sW, b.z1 - sW + 1);
+            for (int ix = 0; ix < cx; ++ix) {
+              const int xs = min(b.x0 + ix * sW, b.x1 - sW + 1);
+              const size_t idx = (size_t)zs * f.pitch + xs;
+              const float2 v = __ldg(T + idx);
+              mx = fmaxf(mx, v.x); mn = fminf(mn, v.y);
+              nf |= __ldg(NF + idx);
+            }
+          }
+          const bool allFinite = nf == 0;
+          r = zone_early_out(b, mx, mn, allFinite);
+          if (allFinite) fl |= REC_ALLFINITE;
+        }
+      }
+      if (r == -1) { ub[n_und] = b; uflags[n_und] = fl; ++n_und; }
+      else if (!foot) { if (r == R_HIT) result = 0; }      // torso must be free
+      else { if (r == R_FREE) result = 0; }                // every reach box must touch
+    }
+    if (!result) n_und = 0;
+    // provisional result; stages B/C clear it if an undecided box fails
+    if (w.edge_mode) { if (!result) w.valid[slot] = 0; }
+    else w.valid[slot] = (uint8_t)result;
+  }
+  // queue the undecided boxes: one warp-aggregated atomic per round
+#pragma unroll 1
+  for (int q = 0; q < 5; ++q) {
+    const bool have = q < n_und;
+    const unsigned m = __ballot_sync(kFull, have);
+    if (m == 0) break;
+    uint32_t basei = 0;
+    const int leader = __ffs(m) - 1;
+    if (lane == leader) basei = atomicAdd(rec_count, (uint32_t)__popc(m));
+    basei = __shfl_sync(kFull, basei, leader);
+    if (have) {
+      BoxRec& o = recs[basei + __popc(m & ((1u << lane) - 1u))];
+      const BoxCtx& b = ub[q];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) o.R1[i] = R1[i];
+      o.P[0] = b.P[0]; o.P[1] = b.P[1]; o.P[2] = b.P[2];
+      o.minB = b.minB; o.maxB = b.maxB;
+      o.x0 = b.x0; o.x1 = b.x1; o.z0 = b.z0; o.z1 = b.z1;
+      o.item = item; o.flags = uflags[q];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage B: one warp per queued box.
+// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
-check_items_warp_kernel(const Checker c, const Work w, uint32_t* __restrict__ work_counter,
-                        uint32_t* __restrict__ defer_count, uint32_t* __restrict__ defer_list, int force_defer) {
+box_items_warp_kernel(const Checker c, const Work w, const BoxRec* __restrict__ recs,
+                      const uint32_t* __restrict__ rec_count, uint32_t* __restrict__ work_counter,
+                      uint32_t* __restrict__ defer_count, uint32_t* __restrict__ defer_list, int force_defer) {
   __shared__ WarpScratch ws_all[kWarpsPerCta];
   const int lane = threadIdx.x & 31;
   WarpScratch& ws = ws_all[threadIdx.x >> 5];
+  const uint32_t total = *rec_count;
   for (;;) {
-    uint32_t item = 0;
-    if (lane == 0) item = atomicAdd(work_counter, 1u);
-    item = __shfl_sync(kFull, item, 0);
-    if (item >= w.n_items) break;
-    const uint32_t slot = item_slot(w, item);
-    if (w.edge_mode) {   // edge already invalid: nothing can change it (perf only; result is order-free)
+    uint32_t ri = 0;
+    if (lane == 0) ri = atomicAdd(work_counter, 1u);
+    ri = __shfl_sync(kFull, ri, 0);
+    if (ri >= total) break;
+    // load the 20-word record with lanes 0..19 and broadcast
+    const uint32_t* rp = reinterpret_cast<const uint32_t*>(recs + ri);
+    const uint32_t word = (lane < 20) ? __ldg(rp + lane) : 0u;
+    BoxRec r;
+    {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+      for (int i = 0; i < 20; ++i) dst[i] = __shfl_sync(kFull, word, i);
+    }
+    const uint32_t slot = item_slot(w, r.item);
+    {   // the item already failed on another box: nothing can change it (perf only; the result is order-free)
       int dead = 0;
       if (lane == 0) dead = (*(volatile uint8_t*)(w.valid + slot) == 0);
       if (__shfl_sync(kFull, dead, 0)) continue;
     }
-    int r;
+    const bool foot = (r.flags & 7) != 0;
+    int res;
     if (force_defer) {
-      r = 2;
+      res = R_DEFER;
     } else {
-      double s[7];
-      load_item_state(w, item, s);
-      r = pose_valid_warp(c, s, ws, lane);
+      BoxCtx b;
+      rec_to_ctx(c, r, b);
+      res = box_collide_warp(foot ? c.f[1] : c.f[0], b, ws, lane, c.cell_margin, (r.flags & REC_NEEDS_REDUCE) != 0,
+                             (r.flags & REC_ALLFINITE) != 0);
     }
     if (lane == 0) {
-      if (r == 2) {
-        defer_list[atomicAdd(defer_count, 1u)] = item;
-      } else if (w.edge_mode) {
-        if (r == 0) w.valid[slot] = 0;
-      } else {
-        w.valid[slot] = (uint8_t)r;
-      }
+      if (res == R_DEFER) defer_list[atomicAdd(defer_count, 1u)] = ri;
+      else if ((!foot && res == R_HIT) || (foot && res == R_FREE)) w.valid[slot] = 0;
     }
   }
 }
@@ -579,40 +674,10 @@ __device__ int box_collide_block(const Field& f, const BoxCtx& b, const BlockSha
   return __syncthreads_or(hit) ? R_HIT : R_FREE;
 }
 
-__device__ int pose_valid_block(const Checker& c, const double s[7], const BlockShared& sh, float* red, int* s_next) {
-  float t[3], R[9], Rb[9], tt[3];
-  pose3_from_se3(s, t, R);
-#pragma unroll
-  for (int i = 0; i < 9; ++i) Rb[i] = R[i];
-  orthogonalize_r(Rb);
-  BoxCtx b;
-  compose_translation(R, t, c.torso_off[0], c.torso_off[1], c.torso_off[2], tt);
-  if (is_inside(c, tt[0], tt[1])) {
-    if (box_setup(c.f[0], c.side[0], tt, Rb, b)) {
-      const int r = box_collide_block(c.f[0], b, sh, red, s_next);
-      if (r == R_DEFER) return 2;
-      if (r == R_HIT) return 0;
-    }
-  }
-#pragma unroll 1
-  for (int k = 0; k < 4; ++k) {
-    const float ox = (k & 2) ? -c.feet_ox : c.feet_ox, oy = (k & 1) ? -c.feet_oy : c.feet_oy;
-    compose_translation(R, t, ox, oy, 0.0f, tt);
-    if (!is_inside(c, tt[0], tt[1])) {
-      if (c.unknown_untraversable) return 0;
-      continue;
-    }
-    if (!box_setup(c.f[1], c.side[1], tt, Rb, b)) return 0;
-    const int r = box_collide_block(c.f[1], b, sh, red, s_next);
-    if (r == R_DEFER) return 2;
-    if (r == R_FREE) return 0;
-  }
-  return 1;
-}
-
 __global__ void __launch_bounds__(256)
-check_items_block_kernel(const Checker c, const Work w, const uint32_t* __restrict__ defer_count,
-                         const uint32_t* __restrict__ defer_list, int T_cap, uint32_t* __restrict__ overflow) {
+box_items_block_kernel(const Checker c, const Work w, const BoxRec* __restrict__ recs,
+                       const uint32_t* __restrict__ defer_count, const uint32_t* __restrict__ defer_list, int T_cap,
+                       uint32_t* __restrict__ overflow) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float red[8];
   __shared__ int s_next;
@@ -623,15 +688,15 @@ check_items_block_kernel(const Checker c, const Work w, const uint32_t* __restri
   sh.state = reinterpret_cast<uint8_t*>(smem_raw + (size_t)T_cap * 20);
   const uint32_t count = *defer_count;
   for (uint32_t q = blockIdx.x; q < count; q += gridDim.x) {
-    const uint32_t item = defer_list[q];
-    const uint32_t slot = item_slot(w, item);
-    double s[7];
-    load_item_state(w, item, s);
-    const int r = pose_valid_block(c, s, sh, red, &s_next);
+    const BoxRec r = recs[defer_list[q]];
+    const uint32_t slot = item_slot(w, r.item);
+    const bool foot = (r.flags & 7) != 0;
+    BoxCtx b;
+    rec_to_ctx(c, r, b);
+    const int res = box_collide_block(foot ? c.f[1] : c.f[0], b, sh, red, &s_next);
     if (threadIdx.x == 0) {
-      if (r == 2) { atomicAdd(overflow, 1u); }
-      else if (w.edge_mode) { if (r == 0) w.valid[slot] = 0; }
-      else w.valid[slot] = (uint8_t)r;
+      if (res == R_DEFER) atomicAdd(overflow, 1u);
+      else if ((!foot && res == R_HIT) || (foot && res == R_FREE)) w.valid[slot] = 0;
     }
     __syncthreads();
   }

@@ -68,6 +68,7 @@ typedef struct artp_stats {
   uint64_t kernel_launches;    /* kernels launched by this handle since creation */
   uint32_t last_deferred;      /* deferred count of the most recent check call */
   uint32_t last_launches;      /* kernels launched by the most recent call */
+  uint32_t last_queued_boxes;  /* boxes the classify stage queued for the warp stage in the most recent call's last round */
 } artp_stats;
 
 int  artp_create(const artp_params* params, artp_handle** out);
@@ -102,14 +103,14 @@ int artp_compact_valid_device(artp_handle* h, const uint8_t* d_valid, size_t n, 
 
 int artp_get_stats(artp_handle* h, artp_stats* out);
 
-/* Kernel timing for roofline reporting: when enabled, CUDA events are recorded on the launch stream around the
- * warp kernel and the plane-grouping kernel of every check call; artp_get_last_timing waits for the last call's
- * kernels and returns their durations in milliseconds. */
+/* Kernel timing for roofline reporting: when enabled, CUDA events are recorded on the launch stream around the three
+ * stages of every check call; artp_get_last_timing waits for the last call's kernels and returns
+ * ms3[0..2] = classify (thread/item), box warp stage, plane-grouping block stage, in milliseconds. */
 int artp_set_timing(artp_handle* h, int enable);
-int artp_get_last_timing(artp_handle* h, float* warp_kernel_ms, float* group_kernel_ms);
+int artp_get_last_timing(artp_handle* h, float* ms3);
 
-/* Test hook: 0 = normal (warp kernel + exact grouping kernel for deferred poses),
- *            1 = send every pose through the exact grouping kernel. */
+/* Test hook: 0 = normal (classify -> warp stage -> grouping stage for deferred boxes),
+ *            1 = send every in-map box through the exact block-level grouping kernel. */
 int artp_set_mode(artp_handle* h, int mode);
 
 /* Version string of the library / kernel image ("artp <ver> sm_100a"). */
