@@ -7,21 +7,20 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libartp.so")
-SOURCES = ["artp_capi.cu"]
-HEADERS = ["artp_device.cuh", "artp_kernels.cuh", os.path.join("..", "..", "include", "artp.h")]
+# (source, extra flags): the geometric kernels need bit-exact fp32 (no FMA contraction);
+# the motion-cost network does not.
+SOURCES = [("artp_capi.cu", ["-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off"]),
+           ("artp_cnn.cu", ["-Xcompiler", "-fPIC"])]
+HEADERS = ["artp_device.cuh", "artp_kernels.cuh", "artp_cnn.h", os.path.join("..", "..", "include", "artp.h")]
 
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-fmad=false",                       # bit-exact fp32: no FMA contraction
-    "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",
-]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17"]
 
 
 def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, s) for s in [x[0] for x in SOURCES] + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
@@ -29,8 +28,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    subprocess.run(cmd, check=True)
+    objs = []
+    for src, extra in SOURCES:
+        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        subprocess.run(cmd, check=True)
+        objs.append(obj)
+    subprocess.run([nvcc, "-shared", "-o", LIB] + objs, check=True)
     return LIB
 
 

@@ -65,6 +65,15 @@ def load():
     lib.artp_set_timing.argtypes = [vp, i32]
     lib.artp_get_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
     lib.artp_version.restype = C.c_char_p
+    lib.artp_cost_weights_size.restype = C.c_size_t
+    lib.artp_set_cost_weights.argtypes = [vp, vp, sz]
+    lib.artp_update_features.argtypes = [vp]
+    lib.artp_motion_cost.argtypes = [vp, vp, sz, vp]
+    lib.artp_motion_cost_device.argtypes = [vp, vp, sz, vp, vp]
+    lib.artp_combine_cost.argtypes = [vp, vp, sz, vp, vp]
+    lib.artp_get_features.argtypes = [vp, vp, sz, C.POINTER(i32), C.POINTER(i32)]
+    lib.artp_set_cnn_mode.argtypes = [vp, i32]
+    lib.artp_get_cnn_timing.argtypes = [vp, C.POINTER(C.c_float)]
     _lib = lib
     return lib
 

@@ -213,3 +213,73 @@ class PathLengthObjective:
             out = np.empty(n, dtype=np.float64)
         h.check(lib.artp_path_length_cost(h.h, a.ctypes.data, b.ctypes.data, n, out.ctypes.data))
         return out
+
+
+class MotionCostObjective:
+    """art_planner::MotionCostObjective's batch cost functor (objectives/motion_cost_objective.h:22-66,
+    motion_cost_objective.cpp:28-33) backed by the on-device network instead of the ROS cost server
+    (art_planner_ros/src/planner_ros.cpp:283-308)."""
+
+    def __init__(self, checker: StateValidityChecker):
+        self._c = checker
+
+    def setWeights(self, state_dict) -> None:
+        """Parameters keyed like the reference module's state_dict (numpy arrays or torch tensors)."""
+        from . import costnet
+        sd = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in state_dict.items()}
+        blob = costnet.pack_blob(sd)
+        h = self._c.handle
+        assert blob.size == h.lib.artp_cost_weights_size()
+        h.check(h.lib.artp_set_cost_weights(h.h, blob.ctypes.data, blob.size))
+
+    def updateFeatures(self) -> None:
+        """CostPredictor.updateFeatures over the checker's current map (predictor.py:28-36)."""
+        h = self._c.handle
+        h.check(h.lib.artp_update_features(h.h))
+
+    def costQuery(self, edge_matrix, out=None):
+        """edge_matrix [n, 6] float32 = [tx, ty, tyaw, sx, sy, syaw] -> [n, 3] float32 (energy, time, risk)."""
+        h, lib = self._c.handle, self._c.handle.lib
+        if _is_torch_cuda(edge_matrix):
+            import torch
+            assert edge_matrix.dtype == torch.float32 and edge_matrix.is_contiguous()
+            n = edge_matrix.shape[0]
+            if out is None:
+                out = torch.empty((n, 3), dtype=torch.float32, device=edge_matrix.device)
+            h.check(lib.artp_motion_cost_device(h.h, C.c_void_p(edge_matrix.data_ptr()), n, C.c_void_p(out.data_ptr()),
+                                                _stream_ptr()))
+            return out
+        e = np.ascontiguousarray(edge_matrix, dtype=np.float32)
+        n = e.shape[0]
+        if out is None:
+            out = np.empty((n, 3), dtype=np.float32)
+        h.check(lib.artp_motion_cost(h.h, e.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def getCost(self, cost3):
+        """(cost, feasible) per edge: w_e*E + w_t*T + w_r*R and R <= risk_threshold (motion_cost_objective.h:54-66)."""
+        h = self._c.handle
+        c = np.ascontiguousarray(cost3, dtype=np.float32)
+        n = c.shape[0]
+        cost = np.empty(n, dtype=np.float64)
+        feas = np.empty(n, dtype=np.uint8)
+        h.check(h.lib.artp_combine_cost(h.h, c.ctypes.data, n, cost.ctypes.data, feas.ctypes.data))
+        return cost, feas
+
+    def features(self):
+        """[Hf, Wf, 48] float32 feature map (test hook)."""
+        h = self._c.handle
+        hf, wf = C.c_int(), C.c_int()
+        h.check(h.lib.artp_get_features(h.h, None, 0, C.byref(hf), C.byref(wf)))
+        out = np.empty((hf.value, wf.value, 48), dtype=np.float32)
+        h.check(h.lib.artp_get_features(h.h, out.ctypes.data, out.size, C.byref(hf), C.byref(wf)))
+        return out
+
+    def setMode(self, mode: int) -> None:
+        h = self._c.handle
+        h.check(h.lib.artp_set_cnn_mode(h.h, int(mode)))
+
+    def lastTrunkTimesMs(self):
+        ms = (C.c_float * 3)()
+        self._c.handle.check(self._c.handle.lib.artp_get_cnn_timing(self._c.handle.h, ms))
+        return float(ms[0]), float(ms[1]), float(ms[2])

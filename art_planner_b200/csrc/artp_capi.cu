@@ -13,11 +13,13 @@
 #include <string>
 
 #include "../../include/artp.h"
+#include "artp_cnn.h"
 #include "artp_kernels.cuh"
 
 namespace {
 
 thread_local std::string g_create_error;
+constexpr int kCopyEvents = 16;
 
 struct Handle {
   artp_params p;
@@ -39,9 +41,13 @@ struct Handle {
   size_t block_counts_cap = 0;
   void* d_stage = nullptr;          // device staging for the host-buffer API
   size_t stage_cap = 0;
-  cudaStream_t stream = nullptr;    // internal stream for the host-buffer API
+  cudaStream_t stream = nullptr;    // internal compute stream for the host-buffer API
+  cudaStream_t copy_stream = nullptr;   // H2D slices of the host-buffer API
+  cudaEvent_t copy_ev[16] = {};
   int k1_grid = 0, k2_grid = 0, k2_smem = 0, k2_tcap = 0;
   int mode = 0;
+  artp_cnn::State* cnn = nullptr;
+  int cnn_mode = 0;
   int timing = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
@@ -292,12 +298,16 @@ int artp_create(const artp_params* params, artp_handle** out) {
   if ((e = cudaFuncGetAttributes(&fa, artp::box_items_warp_kernel)) != cudaSuccess)
     return fail("no usable kernel image (built for sm_100a)", e);
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  for (int i = 0; i < kCopyEvents; ++i)
+    if ((e = cudaEventCreateWithFlags(&h->copy_ev[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaMalloc(&h->d_ctr, 8 * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc", e);
   int per_sm = 0;
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, artp::box_items_warp_kernel,
                                                          artp::kWarpsPerCta * 32, 0)) != cudaSuccess)
     return fail("occupancy", e);
   h->k1_grid = h->sm_count * std::max(per_sm, 1);
+  h->cnn = artp_cnn::create(h->device, h->sm_count);
   // checker constants (float casts as the reference's ctor/Pose3FromXYZ arguments make them)
   artp::Checker& c = h->chk;
   std::memset(&c, 0, sizeof(c));
@@ -316,9 +326,12 @@ void artp_destroy(artp_handle* hh) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   cudaSetDevice(h->device);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  for (int i = 0; i < kCopyEvents; ++i) if (h->copy_ev[i]) cudaEventDestroy(h->copy_ev[i]);
   for (int k = 0; k < 2; ++k) for (int l = 0; l <= artp::kMaxLevel; ++l) { cudaFree(h->d_T[k][l]); cudaFree(h->d_NF[k][l]); }
   cudaFree(h->d_H[0]); cudaFree(h->d_H[1]); cudaFree(h->d_ctr); cudaFree(h->d_defer); cudaFree(h->d_stage);
   cudaFree(h->d_block_counts); cudaFree(h->d_recs);
+  artp_cnn::destroy(h->cnn);
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
 }
@@ -477,25 +490,40 @@ int artp_check_poses_device(artp_handle* hh, const double* d_states, size_t n, u
 int artp_check_poses(artp_handle* hh, const double* states, size_t n, uint8_t* valid) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  {
-    std::lock_guard<std::mutex> lk(h->mtx);
-    int rc = check_common(h, n);
-    if (rc) return rc;
-    if (n == 0) return ARTP_OK;
-    if (!states || !valid) { h->err = "null buffer"; return ARTP_E_INVALID; }
-    CU_TRY(h, cudaSetDevice(h->device));
-    const size_t in_bytes = n * 7 * sizeof(double), out_off = (in_bytes + 255) & ~(size_t)255;
-    rc = ensure_stage(h, out_off + n);
-    if (rc) return rc;
-    CU_TRY(h, cudaMemcpyAsync(h->d_stage, states, in_bytes, cudaMemcpyHostToDevice, h->stream));
-  }
-  double* d_states = (double*)h->d_stage;
-  uint8_t* d_valid = (uint8_t*)h->d_stage + ((n * 7 * sizeof(double) + 255) & ~(size_t)255);
-  int rc = artp_check_poses_device(hh, d_states, n, d_valid, h->stream);
-  if (rc) return rc;
   std::lock_guard<std::mutex> lk(h->mtx);
-  CU_TRY(h, cudaMemcpyAsync(valid, d_valid, n, cudaMemcpyDeviceToHost, h->stream));
+  int rc = check_common(h, n);
+  if (rc) return rc;
+  if (n == 0) return ARTP_OK;
+  if (!states || !valid) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  const size_t in_bytes = n * 7 * sizeof(double), out_off = (in_bytes + 255) & ~(size_t)255;
+  rc = ensure_stage(h, out_off + n);
+  if (rc) return rc;
+  double* d_states = (double*)h->d_stage;
+  uint8_t* d_valid = (uint8_t*)h->d_stage + out_off;
+  // Pipeline: the H2D copy of slice i+1 (copy stream) overlaps the kernels of slice i (compute stream); the
+  // 1 B/pose results go back on the compute stream. Small batches take the single-slice path.
+  const size_t slice = 128 * 1024;
+  const size_t n_slices = (n + slice - 1) / slice;
+  for (size_t i = 0; i < n_slices; ++i) {
+    const size_t lo = i * slice, cnt = std::min(slice, n - lo);
+    cudaEvent_t ev = h->copy_ev[i % kCopyEvents];
+    CU_TRY(h, cudaMemcpyAsync(d_states + 7 * lo, states + 7 * lo, cnt * 7 * sizeof(double), cudaMemcpyHostToDevice,
+                              n_slices > 1 ? h->copy_stream : h->stream));
+    if (n_slices > 1) {
+      CU_TRY(h, cudaEventRecord(ev, h->copy_stream));
+      CU_TRY(h, cudaStreamWaitEvent(h->stream, ev, 0));
+    }
+    artp::Work w;
+    w.s1 = nullptr; w.s2 = d_states + 7 * lo; w.valid = d_valid + lo; w.item_base = 0; w.n_items = (uint32_t)cnt;
+    w.steps = 0; w.edge_mode = 0;
+    rc = run_items(h, w, h->stream);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(valid + lo, d_valid + lo, cnt, cudaMemcpyDeviceToHost, h->stream));
+  }
   CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->stats.poses_checked += n;
+  h->stats.last_launches = (uint32_t)(3 * n_slices);
   return ARTP_OK;
 }
 
@@ -612,6 +640,90 @@ int artp_compact_valid_device(artp_handle* hh, const uint8_t* d_valid, size_t n,
   CU_TRY(h, cudaGetLastError());
   h->stats.kernel_launches += 3;
   h->stats.last_launches = 3;
+  return ARTP_OK;
+}
+
+size_t artp_cost_weights_size(void) { return artp_cnn::blob_floats(); }
+
+int artp_set_cost_weights(artp_handle* hh, const float* blob, size_t n_floats) {
+  if (!hh || !blob) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  return artp_cnn::set_weights(h->cnn, blob, n_floats, h->stream, h->err);
+}
+
+int artp_update_features(artp_handle* hh) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
+  artp_cnn::set_base_offset_mode(h->cnn, (h->cnn_mode & 2) ? 1 : 0);
+  return artp_cnn::update_features(h->cnn, h->d_H[0], h->rows, h->cols, h->pitch, h->chk.Lx / h->rows, h->chk.cx, h->chk.cy,
+                                   h->stream, h->cnn_mode & 1, h->err);
+}
+
+int artp_motion_cost_device(artp_handle* hh, const float* d_edges, size_t n, float* d_cost3, void* stream) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (n && (!d_edges || !d_cost3)) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  int rc = artp_cnn::motion_cost(h->cnn, d_edges, n, d_cost3, (cudaStream_t)stream, h->err);
+  if (rc == 0 && n) { h->stats.kernel_launches += 1; h->stats.last_launches = 1; }
+  return rc;
+}
+
+int artp_motion_cost(artp_handle* hh, const float* edges, size_t n, float* cost3) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (n == 0) return ARTP_OK;
+  const size_t in_b = n * 6 * sizeof(float), in_al = (in_b + 255) & ~(size_t)255;
+  {
+    std::lock_guard<std::mutex> lk(h->mtx);
+    if (!edges || !cost3) { h->err = "null buffer"; return ARTP_E_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_stage(h, in_al + n * 3 * sizeof(float));
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(h->d_stage, edges, in_b, cudaMemcpyHostToDevice, h->stream));
+  }
+  float* d_cost = (float*)((char*)h->d_stage + in_al);
+  int rc = artp_motion_cost_device(hh, (const float*)h->d_stage, n, d_cost, h->stream);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(h->mtx);
+  CU_TRY(h, cudaMemcpyAsync(cost3, d_cost, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return ARTP_OK;
+}
+
+int artp_combine_cost(artp_handle* hh, const float* cost3, size_t n, double* cost, uint8_t* feasible) {
+  if (!hh || (n && (!cost3 || !cost || !feasible))) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  const float we = h->p.cost_w_energy, wt = h->p.cost_w_time, wr = h->p.cost_w_risk;
+  for (size_t i = 0; i < n; ++i) {
+    const float ce = cost3[3 * i], ct = cost3[3 * i + 1], cr = cost3[3 * i + 2];
+    cost[i] = (double)(ce * we + ct * wt + cr * wr);                 // getCost: float arithmetic, returned as double
+    feasible[i] = (double)cr <= (double)h->p.risk_threshold ? 1 : 0;   // isFeasible (getRisk returns double)
+  }
+  return ARTP_OK;
+}
+
+int artp_get_features(artp_handle* hh, float* out, size_t n_floats, int* hf, int* wf) {
+  if (!hh || !hf || !wf) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  artp_cnn::feature_shape(h->cnn, hf, wf);
+  if (!out) return ARTP_OK;
+  return artp_cnn::copy_features(h->cnn, out, n_floats, h->err);
+}
+
+int artp_set_cnn_mode(artp_handle* hh, int mode) {
+  if (!hh) return ARTP_E_INVALID;
+  reinterpret_cast<Handle*>(hh)->cnn_mode = mode;
+  return ARTP_OK;
+}
+
+int artp_get_cnn_timing(artp_handle* hh, float* ms3) {
+  if (!hh || !ms3) return ARTP_E_INVALID;
+  artp_cnn::last_times(reinterpret_cast<Handle*>(hh)->cnn, ms3);
   return ARTP_OK;
 }
 

@@ -1,0 +1,729 @@
+// art_planner_b200/csrc/artp_cnn.cu -- the learned motion-cost network on sm_100a.
+//
+// Reference: art_planner_motion_cost/src/art_planner_motion_cost/predictor/network_light.py
+//   CNNpart :78-110  conv3x3(1->24)+BN, conv3x3(24->24)+BN+LReLU(0.3), maxpool 2/2, conv3x3(24->48)+BN+LReLU,
+//                    conv3x3(48->48)+BN+LReLU, maxpool 3/1, conv3x3(48->48)+BN+LReLU, conv15x15(48->48)+BN+LReLU
+//   FCpart  :113-165 and CostQuery.__call__ (cost_query.py:39-69), server centring (cost_query_server.py:160-161)
+//
+// Numerics: the reference evaluates in fp16; parity here is against the fp32 evaluation of the same module to 1e-4
+// relative, so everything accumulates in fp32 and the 15x15 convolution -- 83.6 % of the FLOPs, implicit GEMM
+// M = output pixels, N = 48, K = 225 taps x 48 channels -- runs on the 5th-gen tensor cores with an error-compensated
+// fp16 split (a = a_hi + a_lo, w = w_hi + w_lo; D += a_hi*w_hi + a_hi*w_lo + a_lo*w_hi, fp32 accumulate in TMEM),
+// which keeps ~22 mantissa bits per product.
+//
+// 15x15 kernel (conv15_tcgen05_kernel): one CTA per 16(y) x 8(x) output tile (UMMA M = 128, N = 48).
+//   * The whole input halo brick [30 y][24 x][64 ch] (hi and lo, 92 KB each) is TMA-loaded ONCE into 128B-swizzled
+//     shared memory; pixels are 128-byte rows, image rows are 24 pixels = 3072 B = 3 swizzle atoms apart, so every one
+//     of the 225 taps is just a shifted view of the same brick: start address += (ky*24 + kx)*128 B, stride between
+//     8-pixel groups (SBO) = 3072 B. Measured on B200: the 128B swizzle XOR is applied on absolute shared-memory
+//     address bits, so the shifted (128 B-aligned, not 1024 B-aligned) start needs descriptor base_offset = 0
+//     (setting it to (shift & 7) double-swizzles; profiles/debug_conv15.py). No per-tap activation traffic.
+//   * Weights [tap][48][64] fp16 hi/lo stream through a 3-stage TMA ring (12 KB per tap).
+//   * Warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected lane), warps 2..5 = epilogue
+//     (tcgen05.ld -> +bias -> LeakyReLU -> fp32 NHWC feature map).
+// The five 3x3 layers (16.4 % of the FLOPs) are fp32 CUDA-core direct convolutions in round 1.
+// This translation unit is compiled WITHOUT -fmad=false (no bit-exactness requirement here).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "artp_cnn.h"
+
+namespace artp_cnn {
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+#define CNN_TRY(expr)                                                              \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(_e); return -3; } \
+  } while (0)
+
+struct LayerDef { int cout, cin, k; bool bn; };
+static const LayerDef kLayers[14] = {
+    {24, 1, 3, true},  {24, 24, 3, true}, {48, 24, 3, true}, {48, 48, 3, true}, {48, 48, 3, true}, {48, 48, 15, true},
+    {16, 10, 1, true}, {48, 64, 1, true}, {24, 48, 1, true}, {24, 48, 1, true}, {36, 48, 1, true},
+    {1, 24, 1, false}, {1, 24, 1, false}, {1, 36, 1, false}};
+static const float kBnEps = 1e-5f;
+__device__ constexpr float kWScale = 1024.0f;   // undone exactly in the 15x15 epilogue
+
+size_t blob_floats() {
+  size_t n = 0;
+  for (const auto& l : kLayers) n += (size_t)l.cout * l.cin * l.k * l.k + (l.bn ? 4 * l.cout : l.cout);
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 direct 3x3 convolution, NHWC, BN folded, optional LeakyReLU(0.3). One thread per output pixel, all COUT
+// accumulators in registers; input tile and weight slice staged in shared memory per chunk of CK input channels.
+// SRC_MAP: the input is the heightfield layer as artp_set_map stores it (H[x + z*pitch] = layer(x, nz-1-z));
+// the network input E[r][c] = layer(rows-1-r, cols-1-c) = H[(rows-1-r) + c*pitch] (cost_query_server.py:74).
+// ------------------------------------------------------------------------------------------------
+template <int CIN, int COUT, int CK, bool ACT, bool SRC_MAP>
+__global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ in, int H, int W, int in_pitch,
+                                                      const float* __restrict__ wf /*[9][CIN][COUT]*/,
+                                                      const float* __restrict__ bias, float* __restrict__ out) {
+  constexpr int T = 16;
+  __shared__ float tile[(T + 2) * (T + 2) * CK];
+  __shared__ __align__(16) float wsm[9 * CK * COUT];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int ox0 = blockIdx.x * T, oy0 = blockIdx.y * T;
+  const int OH = H - 2, OW = W - 2;
+  float acc[COUT];
+#pragma unroll
+  for (int i = 0; i < COUT; ++i) acc[i] = 0.0f;
+  for (int c0 = 0; c0 < CIN; c0 += CK) {
+    for (int i = threadIdx.x; i < (T + 2) * (T + 2) * CK; i += 256) {
+      const int ci = i % CK, p = i / CK, px = p % (T + 2), py = p / (T + 2);
+      const int iy = oy0 + py, ix = ox0 + px;
+      float v = 0.0f;
+      if (iy < H && ix < W) {
+        if (SRC_MAP) v = __ldg(in + (size_t)ix * in_pitch + (H - 1 - iy));   // E[iy][ix], rows = H (x), cols = W (y)
+        else v = __ldg(in + ((size_t)iy * W + ix) * CIN + c0 + ci);
+      }
+      tile[i] = v;
+    }
+    for (int i = threadIdx.x; i < 9 * CK * COUT; i += 256) {
+      const int co = i % COUT, r = i / COUT, ci = r % CK, tap = r / CK;
+      wsm[i] = __ldg(wf + ((size_t)tap * CIN + c0 + ci) * COUT + co);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap % 3;
+      const float* tp = tile + ((ty + ky) * (T + 2) + tx + kx) * CK;
+#pragma unroll
+      for (int ci = 0; ci < CK; ++ci) {
+        const float v = tp[ci];
+        const float4* wp = reinterpret_cast<const float4*>(wsm + (tap * CK + ci) * COUT);
+#pragma unroll
+        for (int q = 0; q < COUT / 4; ++q) {
+          const float4 w4 = wp[q];
+          acc[4 * q + 0] = fmaf(v, w4.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  if (oy < OH && ox < OW) {
+    float* op = out + ((size_t)oy * OW + ox) * COUT;
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+      float v = acc[co] + __ldg(bias + co);
+      if (ACT) v = v > 0.0f ? v : 0.3f * v;
+      op[co] = v;
+    }
+  }
+}
+
+// max pooling, NHWC fp32: K x K window, stride S (2/2 and 3/1 in the reference).
+__global__ void maxpool_kernel(const float* __restrict__ in, int H, int W, int C, int K, int S, float* __restrict__ out,
+                               int OH, int OW) {
+  const size_t total = (size_t)OH * OW * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const size_t p = i / C;
+    const int ox = (int)(p % OW), oy = (int)(p / OW);
+    float m = -INFINITY;
+    for (int dy = 0; dy < K; ++dy)
+      for (int dx = 0; dx < K; ++dx) m = fmaxf(m, in[((size_t)(oy * S + dy) * W + ox * S + dx) * C + c]);
+    out[i] = m;
+  }
+}
+
+// fp32 NHWC [H][W][48] -> fp16 hi / lo NHWC [H][W][64] (channels 48..63 zero): the TMA source of the 15x15 layer.
+__global__ void split_pad_kernel(const float* __restrict__ in, size_t npix, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const size_t total = npix * 64;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 63);
+    const size_t p = i >> 6;
+    float v = c < 48 ? in[p * 48 + c] : 0.0f;
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+// Fold BN into conv weights: wf[tap][cin][cout] = w[cout][cin][tap] * gamma/sqrt(var+eps); bias = beta - mean*scale.
+__global__ void fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ bn /*gamma,beta,mean,var*/, int cout,
+                                 int cin, int kk, float* __restrict__ wf, float* __restrict__ bias) {
+  const int total = cout * cin * kk;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % cout, r = i / cout, ci = r % cin, tap = r / cin;
+    const float s = bn[co] / sqrtf(bn[3 * cout + co] + kBnEps);
+    wf[i] = w[((size_t)co * cin + ci) * kk + tap] * s;
+  }
+  for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < cout; co += gridDim.x * blockDim.x) {
+    const float s = bn[co] / sqrtf(bn[3 * cout + co] + kBnEps);
+    bias[co] = bn[cout + co] - bn[2 * cout + co] * s;
+  }
+}
+
+// 15x15 layer weights -> fp16 hi/lo [tap][48 n][64 c] (K-major rows of 128 B; c >= 48 zero), BN scale folded.
+__global__ void fold_flatten_kernel(const float* __restrict__ w /*[48][48][225]*/, const float* __restrict__ bn,
+                                    __half* __restrict__ whi, __half* __restrict__ wlo, float* __restrict__ bias) {
+  const int total = 225 * 48 * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i & 63, r = i >> 6, n = r % 48, tap = r / 48;
+    float v = 0.0f;
+    if (c < 48) {
+      const float s = bn[n] / sqrtf(bn[3 * 48 + n] + kBnEps);
+      v = w[((size_t)n * 48 + c) * 225 + tap] * s * kWScale;   // power-of-two scale keeps w_lo out of fp16 subnormals
+    }
+    const __half h = __float2half_rn(v);
+    whi[i] = h;
+    wlo[i] = __float2half_rn(v - __half2float(h));
+  }
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < 48; n += gridDim.x * blockDim.x) {
+    const float s = bn[n] / sqrtf(bn[3 * 48 + n] + kBnEps);
+    bias[n] = bn[48 + n] - bn[2 * 48 + n] * s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 / TMA / mbarrier primitives (inline PTX, sm_100a)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);             // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                              // leading byte offset (unused for swizzled K-major), bits [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;    // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                              // descriptor version 1 (sm_100), bits [46,48)
+  d |= (uint64_t)(base_offset & 7) << 49;              // matrix base offset, bits [49,52)
+  d |= (uint64_t)2 << 61;                              // layout type SWIZZLE_128B, bits [61,64)
+  return d;
+}
+
+constexpr int kTileY = 16, kTileX = 8;           // output tile (UMMA M = 128 = 16 groups of 8 pixels along x)
+constexpr int kBrickY = kTileY + 14, kBrickX = 24;   // halo brick, x padded 22 -> 24 so the row pitch is 3 swizzle atoms
+constexpr int kBrickBytes = kBrickY * kBrickX * 128;  // per split term
+constexpr int kWStageBytes = 2 * 48 * 128;            // hi + lo weight tile of one tap
+constexpr int kWStages = 3;
+constexpr int kConv15Smem = 2 * kBrickBytes + kWStages * kWStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+// instruction descriptor: D = f32 (bits [4,6) = 1), A = B = f16 (0), K-major both, N = 48 (>>3 at [17,23)), M = 128 (>>4 at [24,29))
+constexpr uint32_t kIdesc = (1u << 4) | ((48u >> 3) << 17) | ((128u >> 4) << 24);
+
+__global__ void __launch_bounds__(192, 1)
+conv15_tcgen05_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+                      const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
+                      const float* __restrict__ bias, float* __restrict__ out, int OH, int OW, int use_base_offset) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* a_hi = smem;
+  unsigned char* a_lo = smem + kBrickBytes;
+  unsigned char* w_st = smem + 2 * kBrickBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_st + kWStages * kWStageBytes);
+  uint64_t* bar_brick = bars;                 // TMA -> MMA: activations landed
+  uint64_t* bar_full = bars + 1;              // [kWStages] TMA -> MMA: weight tap landed
+  uint64_t* bar_empty = bars + 1 + kWStages;  // [kWStages] MMA -> TMA: stage consumed
+  uint64_t* bar_done = bars + 1 + 2 * kWStages;   // MMA -> epilogue: accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * kWStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * kTileX, y0 = blockIdx.y * kTileY;
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(bar_brick, 1);
+    for (int s = 0; s < kWStages; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM allocation: 8 accumulators x 64 columns (N = 48 used of each), one warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // activations: one box [64 ch][24 x][30 y] per split term (out-of-range pixels are zero-filled by TMA)
+      mbar_expect_tx(bar_brick, 2 * kBrickBytes);
+      tma_load_3d(a_hi, &map_ahi, bar_brick, 0, x0, y0);
+      tma_load_3d(a_lo, &map_alo, bar_brick, 0, x0, y0);
+      // weights: ring over the 225 taps
+      for (int t = 0; t < 225; ++t) {
+        const int s = t % kWStages, round = t / kWStages;
+        if (round > 0) mbar_wait(bar_empty + s, (round - 1) & 1);
+        mbar_expect_tx(bar_full + s, kWStageBytes);
+        tma_load_2d(w_st + s * kWStageBytes, &map_whi, bar_full + s, 0, t * 48);
+        tma_load_2d(w_st + s * kWStageBytes + 48 * 128, &map_wlo, bar_full + s, 0, t * 48);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(bar_brick, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t ahi = smem_u32(a_hi), alo = smem_u32(a_lo);
+      for (int t = 0; t < 225; ++t) {
+        const int s = t % kWStages, round = t / kWStages;
+        mbar_wait(bar_full + s, round & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int ky = t / 15, kx = t % 15;
+        const uint32_t shift = (uint32_t)(ky * kBrickX + kx);           // in pixels = 128-byte rows
+        const uint32_t bo = use_base_offset ? (shift & 7u) : 0u;
+        const uint32_t whi = smem_u32(w_st + s * kWStageBytes), wlo = whi + 48 * 128;
+        // The tensor core truncates when it adds into the fp32 accumulator, so a single accumulator would take
+        // 2025 biased roundings (measured 4e-5 relative). Spread them: the a_hi*w_hi products of tap t go to
+        // accumulator t % 7, both small correction terms to an eighth one; the epilogue sums the eight in fp32 RN.
+        const uint32_t d_main = tmem_base + (uint32_t)((t % 7) * 64), d_corr = tmem_base + 7u * 64u;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {   // K = 48 channels = 3 x UMMA_K(16); the 16 pad channels are never multiplied
+          const uint64_t dah = make_desc(ahi + shift * 128 + j * 32, kBrickX * 128, bo);
+          const uint64_t dal = make_desc(alo + shift * 128 + j * 32, kBrickX * 128, bo);
+          const uint64_t dwh = make_desc(whi + j * 32, 1024, 0);
+          const uint64_t dwl = make_desc(wlo + j * 32, 1024, 0);
+          umma_f16(d_main, dah, dwh, kIdesc, (t >= 7 || j != 0));
+          umma_f16(d_corr, dah, dwl, kIdesc, (t | j) != 0);
+          umma_f16(d_corr, dal, dwh, kIdesc, 1);
+        }
+        umma_commit(bar_empty + s);   // frees the weight stage once these MMAs have read it
+      }
+      umma_commit(bar_done);
+    }
+  } else {
+    // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 = output pixels m = lane index; m = yl*8 + xl
+    mbar_wait(bar_done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
+    float acc[48];
+#pragma unroll
+    for (int n = 0; n < 48; ++n) acc[n] = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        uint32_t v[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64 + c * 16);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[16 * c + i] += __uint_as_float(v[i]);
+      }
+    }
+    if (oy < OH && ox < OW) {
+      float* op = out + ((size_t)oy * OW + ox) * 48;
+#pragma unroll
+      for (int n = 0; n < 48; ++n) {
+        float f = acc[n] * (1.0f / kWScale) + __ldg(bias + n);
+        op[n] = f > 0.0f ? f : 0.3f * f;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// Reference implementation of the 15x15 layer on CUDA cores (fp32), used by the self-check entry point only.
+__global__ void conv15_reference_kernel(const float* __restrict__ in /*[H][W][48]*/, int H, int W,
+                                        const float* __restrict__ wf /*[225][48][48]*/, const float* __restrict__ bias,
+                                        float* __restrict__ out) {
+  const int OH = H - 14, OW = W - 14;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= OH * OW * 48) return;
+  const int n = i % 48, p = i / 48, ox = p % OW, oy = p / OW;
+  float acc = 0.0f;
+  for (int ky = 0; ky < 15; ++ky)
+    for (int kx = 0; kx < 15; ++kx) {
+      const float* ip = in + ((size_t)(oy + ky) * W + ox + kx) * 48;
+      const float* wp = wf + (size_t)(ky * 15 + kx) * 48 * 48 + n;
+      for (int c = 0; c < 48; ++c) acc = fmaf(ip[c], wp[c * 48], acc);
+    }
+  const float f = acc + bias[n];
+  out[i] = f > 0.0f ? f : 0.3f * f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Query head: CostQuery.__call__ + FCpart, one thread per query, folded weights in shared memory.
+// ------------------------------------------------------------------------------------------------
+struct HeadParams {
+  const float* w;   // folded: tar0 [10][16]+b[16], out0 [64][48]+b[48], o11 [48][24]+b, o12 [48][24]+b, o13 [48][36]+b,
+                    // o21 [24]+b[1], o22 [24]+b[1], o23 [36]+b[1]
+  int n_floats;
+};
+constexpr int kHeadFloats = 10 * 16 + 16 + 64 * 48 + 48 + 48 * 24 + 24 + 48 * 24 + 24 + 48 * 36 + 36 + 24 + 1 + 24 + 1 + 36 + 1;
+
+__global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ feats /*[Hf][Wf][48]*/, int Hf, int Wf,
+                                                    const float* __restrict__ hw, const float* __restrict__ edges, size_t n,
+                                                    float* __restrict__ cost3, double res, double Lx, double Ly, double cx,
+                                                    double cy) {
+  extern __shared__ float sw[];
+  for (int i = threadIdx.x; i < kHeadFloats; i += blockDim.x) sw[i] = hw[i];
+  __syncthreads();
+  const size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const float* e = edges + 6 * q;
+  // float64 arithmetic on the float32 request values, like the numpy/torch float64 path of the server
+  double tx = (double)e[0] - cx, ty = (double)e[1] - cy, tyaw = (double)e[2];
+  const double sx = (double)e[3] - cx, sy = (double)e[4] - cy, syaw = (double)e[5];
+  tx -= sx; ty -= sy; tyaw -= syaw;
+  const double feat_res = res * 2.0;
+  const int row_bias = (int)((Lx / res - 48.0) / 2.0 * 0.5), col_bias = (int)((Ly / res - 48.0) / 2.0 * 0.5);
+  double rr = sx / feat_res + row_bias, cc = sy / feat_res + col_bias;
+  rr = fmin(fmax(rr, 1.0), (double)(Hf - 2));
+  cc = fmin(fmax(cc, 1.0), (double)(Wf - 2));
+  const int row = (int)rr, col = (int)cc;   // .long() truncation
+  float x[64];
+  {
+    const float4* fp = reinterpret_cast<const float4*>(feats + ((size_t)row * Wf + col) * 48);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { const float4 v = __ldg(fp + i); x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w; }
+  }
+  const float dx = (float)tx, dy = (float)ty;
+  float ang = (float)tyaw;
+  const float PI = 3.14159265358979323846f;
+  if (ang > PI) ang -= 2.0f * PI;
+  if (ang < -PI) ang += 2.0f * PI;
+  const float sya = (float)syaw;
+  const float info[10] = {dx, dy, sqrtf(dx * dx + dy * dy), atan2f(dy, dx), ang, cosf(ang), sinf(ang), sya, cosf(sya), sinf(sya)};
+  const float* w = sw;
+  // tar0: 10 -> 16 (BN folded, no activation)
+#pragma unroll
+  for (int o = 0; o < 16; ++o) {
+    float a = w[160 + o];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) a = fmaf(info[i], w[i * 16 + o], a);
+    x[48 + o] = a;
+  }
+  w += 176;
+  float h[48];
+#pragma unroll
+  for (int o = 0; o < 48; ++o) h[o] = w[64 * 48 + o];
+  for (int i = 0; i < 64; ++i) {
+    const float v = x[i];
+#pragma unroll
+    for (int o = 0; o < 48; ++o) h[o] = fmaf(v, w[i * 48 + o], h[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < 48; ++o) h[o] = h[o] > 0.0f ? h[o] : 0.3f * h[o];
+  w += 64 * 48 + 48;
+  float outv[3];
+  const int widths[3] = {24, 24, 36};
+  const float* w2 = w + (48 * 24 + 24) * 2 + 48 * 36 + 36;
+  for (int b = 0; b < 3; ++b) {
+    const int nb = widths[b];
+    float acc2 = 0.0f;
+    for (int o = 0; o < nb; ++o) {
+      float a = w[48 * nb + o];
+      for (int i = 0; i < 48; ++i) a = fmaf(h[i], w[i * nb + o], a);
+      a = a > 0.0f ? a : 0.3f * a;
+      acc2 = fmaf(a, w2[o], acc2);
+    }
+    acc2 += w2[nb];
+    outv[b] = acc2;
+    w += 48 * nb + nb;
+    w2 += nb + 1;
+  }
+  cost3[3 * q + 0] = fmaxf(outv[0], 0.0f);                        // power  (ReLU)
+  cost3[3 * q + 1] = fmaxf(outv[1], 0.0f);                        // time   (ReLU)
+  cost3[3 * q + 2] = 1.0f - 1.0f / (1.0f + expf(-outv[2]));       // 1 - sigmoid
+}
+
+// Fold the head's 1x1 convs (+BN) into [Cin][Cout] matrices + bias, in head_kernel's order.
+__global__ void fold_head_kernel(const float* __restrict__ blob, const size_t* __restrict__ offs, float* __restrict__ hw) {
+  // offs[l] = offset of layer l (6..13) in the blob; single block
+  const int cin[8] = {10, 64, 48, 48, 48, 24, 24, 36}, cout[8] = {16, 48, 24, 24, 36, 1, 1, 1};
+  int o = 0;
+  for (int l = 0; l < 8; ++l) {
+    const float* w = blob + offs[l];
+    const float* bn = w + (size_t)cout[l] * cin[l];
+    const bool has_bn = l < 5;
+    for (int i = threadIdx.x; i < cin[l] * cout[l]; i += blockDim.x) {
+      const int co = i % cout[l], ci = i / cout[l];
+      const float s = has_bn ? bn[co] / sqrtf(bn[3 * cout[l] + co] + kBnEps) : 1.0f;
+      hw[o + i] = w[(size_t)co * cin[l] + ci] * s;
+    }
+    for (int co = threadIdx.x; co < cout[l]; co += blockDim.x) {
+      float b;
+      if (has_bn) { const float s = bn[co] / sqrtf(bn[3 * cout[l] + co] + kBnEps); b = bn[cout[l] + co] - bn[2 * cout[l] + co] * s; }
+      else b = bn[co];   // conv bias
+      hw[o + cin[l] * cout[l] + co] = b;
+    }
+    o += cin[l] * cout[l] + cout[l];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host state
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct State {
+  int device = 0, sm_count = 0;
+  bool has_weights = false, has_features = false;
+  float* d_blob = nullptr;
+  size_t layer_off[14];
+  float* d_wf[5] = {};     // folded 3x3 weights [9][cin][cout]
+  float* d_bias[6] = {};   // folded biases (layers 0..5)
+  float* d_wf6 = nullptr;  // folded fp32 15x15 weights [225][48][48] (self-check only)
+  __half *d_whi = nullptr, *d_wlo = nullptr;
+  float* d_head = nullptr;
+  size_t* d_offs = nullptr;
+  // activations (sized for the current map)
+  int rows = 0, cols = 0;
+  float *a1 = nullptr, *a2 = nullptr, *p2 = nullptr, *a3 = nullptr, *a4 = nullptr, *p4 = nullptr, *a5 = nullptr, *feat = nullptr;
+  __half *a5hi = nullptr, *a5lo = nullptr;
+  int Hf = 0, Wf = 0;
+  double res = 0, Lx = 0, Ly = 0, cx = 0, cy = 0;
+  EncodeTiledFn encode = nullptr;
+  int use_base_offset = 0;
+  float last_ms[3] = {0, 0, 0};
+  cudaEvent_t ev[4] = {};
+};
+
+State* create(int device, int sm_count) {
+  State* s = new State();
+  s->device = device;
+  s->sm_count = sm_count;
+  return s;
+}
+
+static void free_acts(State* s) {
+  cudaFree(s->a1); cudaFree(s->a2); cudaFree(s->p2); cudaFree(s->a3); cudaFree(s->a4); cudaFree(s->p4); cudaFree(s->a5);
+  cudaFree(s->feat); cudaFree(s->a5hi); cudaFree(s->a5lo);
+  s->a1 = s->a2 = s->p2 = s->a3 = s->a4 = s->p4 = s->a5 = s->feat = nullptr;
+  s->a5hi = s->a5lo = nullptr;
+}
+
+void destroy(State* s) {
+  if (!s) return;
+  free_acts(s);
+  cudaFree(s->d_blob);
+  for (auto p : s->d_wf) cudaFree(p);
+  for (auto p : s->d_bias) cudaFree(p);
+  cudaFree(s->d_wf6); cudaFree(s->d_whi); cudaFree(s->d_wlo); cudaFree(s->d_head); cudaFree(s->d_offs);
+  for (auto e : s->ev) if (e) cudaEventDestroy(e);
+  delete s;
+}
+
+void set_base_offset_mode(State* s, int on) { s->use_base_offset = on ? 1 : 0; }
+bool has_features(const State* s) { return s->has_features; }
+bool has_weights(const State* s) { return s->has_weights; }
+void last_times(const State* s, float* ms3) { ms3[0] = s->last_ms[0]; ms3[1] = s->last_ms[1]; ms3[2] = s->last_ms[2]; }
+
+int set_weights(State* s, const float* blob, size_t n, cudaStream_t st, std::string& err) {
+  if (n != blob_floats()) { err = "weight blob has the wrong number of floats"; return -1; }
+  CNN_TRY(cudaSetDevice(s->device));
+  if (!s->d_blob) {
+    CNN_TRY(cudaMalloc(&s->d_blob, n * sizeof(float)));
+    for (int l = 0; l < 5; ++l) CNN_TRY(cudaMalloc(&s->d_wf[l], (size_t)9 * kLayers[l].cin * kLayers[l].cout * sizeof(float)));
+    for (int l = 0; l < 6; ++l) CNN_TRY(cudaMalloc(&s->d_bias[l], kLayers[l].cout * sizeof(float)));
+    CNN_TRY(cudaMalloc(&s->d_wf6, (size_t)225 * 48 * 48 * sizeof(float)));
+    CNN_TRY(cudaMalloc(&s->d_whi, (size_t)225 * 48 * 64 * sizeof(__half)));
+    CNN_TRY(cudaMalloc(&s->d_wlo, (size_t)225 * 48 * 64 * sizeof(__half)));
+    CNN_TRY(cudaMalloc(&s->d_head, kHeadFloats * sizeof(float)));
+    CNN_TRY(cudaMalloc(&s->d_offs, 8 * sizeof(size_t)));
+  }
+  size_t off = 0;
+  for (int l = 0; l < 14; ++l) {
+    s->layer_off[l] = off;
+    off += (size_t)kLayers[l].cout * kLayers[l].cin * kLayers[l].k * kLayers[l].k + (kLayers[l].bn ? 4 * kLayers[l].cout : kLayers[l].cout);
+  }
+  CNN_TRY(cudaMemcpyAsync(s->d_blob, blob, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  CNN_TRY(cudaMemcpyAsync(s->d_offs, s->layer_off + 6, 8 * sizeof(size_t), cudaMemcpyHostToDevice, st));
+  for (int l = 0; l < 5; ++l) {
+    const float* w = s->d_blob + s->layer_off[l];
+    fold_conv_kernel<<<64, 256, 0, st>>>(w, w + (size_t)kLayers[l].cout * kLayers[l].cin * 9, kLayers[l].cout, kLayers[l].cin, 9,
+                                         s->d_wf[l], s->d_bias[l]);
+  }
+  {
+    const float* w = s->d_blob + s->layer_off[5];
+    fold_flatten_kernel<<<256, 256, 0, st>>>(w, w + (size_t)48 * 48 * 225, s->d_whi, s->d_wlo, s->d_bias[5]);
+    fold_conv_kernel<<<256, 256, 0, st>>>(w, w + (size_t)48 * 48 * 225, 48, 48, 225, s->d_wf6, s->d_bias[5]);
+  }
+  fold_head_kernel<<<1, 256, 0, st>>>(s->d_blob, s->d_offs, s->d_head);
+  CNN_TRY(cudaGetLastError());
+  CNN_TRY(cudaStreamSynchronize(st));
+  s->has_weights = true;
+  s->has_features = false;
+  return 0;
+}
+
+static int encode_maps(State* s, CUtensorMap* maps, int H5, int W5, std::string& err) {
+  if (!s->encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      err = "cuTensorMapEncodeTiled not available from the driver";
+      return -3;
+    }
+    s->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  // activations [H5][W5][64] fp16: dims (c, x, y)
+  const cuuint64_t adim[3] = {64, (cuuint64_t)W5, (cuuint64_t)H5};
+  const cuuint64_t astr[2] = {128, (cuuint64_t)W5 * 128};
+  const cuuint32_t abox[3] = {64, kBrickX, kBrickY};
+  const cuuint32_t one3[3] = {1, 1, 1};
+  const cuuint64_t wdim[2] = {64, 225 * 48};
+  const cuuint64_t wstr[1] = {128};
+  const cuuint32_t wbox[2] = {64, 48};
+  void* ptrs[4] = {s->a5hi, s->a5lo, s->d_whi, s->d_wlo};
+  for (int i = 0; i < 4; ++i) {
+    CUresult r;
+    if (i < 2)
+      r = s->encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, ptrs[i], adim, astr, abox, one3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    else
+      r = s->encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptrs[i], wdim, wstr, wbox, one3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return -3; }
+  }
+  return 0;
+}
+
+// CostPredictor.updateFeatures (predictor.py:28-36): the CNN trunk over the `elevation` layer currently uploaded.
+int update_features(State* s, const float* d_layer, int rows, int cols, int pitch, double res, double cx, double cy,
+                    cudaStream_t st, int use_reference_conv15, std::string& err) {
+  if (!s->has_weights) { err = "motion-cost weights not set"; return -5; }
+  if (rows < 64 || cols < 64) { err = "map too small for the motion-cost network (needs >= 64 x 64 cells)"; return -1; }
+  CNN_TRY(cudaSetDevice(s->device));
+  const int H0 = rows, W0 = cols;
+  const int H1 = H0 - 2, W1 = W0 - 2, H2 = H1 - 2, W2 = W1 - 2, HP2 = H2 / 2, WP2 = W2 / 2;
+  const int H3 = HP2 - 2, W3 = WP2 - 2, H4 = H3 - 2, W4 = W3 - 2, HP4 = H4 - 2, WP4 = W4 - 2;
+  const int H5 = HP4 - 2, W5 = WP4 - 2, H6 = H5 - 14, W6 = W5 - 14;
+  if (rows != s->rows || cols != s->cols) {
+    free_acts(s);
+    CNN_TRY(cudaMalloc(&s->a1, (size_t)H1 * W1 * 24 * 4));
+    CNN_TRY(cudaMalloc(&s->a2, (size_t)H2 * W2 * 24 * 4));
+    CNN_TRY(cudaMalloc(&s->p2, (size_t)HP2 * WP2 * 24 * 4));
+    CNN_TRY(cudaMalloc(&s->a3, (size_t)H3 * W3 * 48 * 4));
+    CNN_TRY(cudaMalloc(&s->a4, (size_t)H4 * W4 * 48 * 4));
+    CNN_TRY(cudaMalloc(&s->p4, (size_t)HP4 * WP4 * 48 * 4));
+    CNN_TRY(cudaMalloc(&s->a5, (size_t)H5 * W5 * 48 * 4));
+    CNN_TRY(cudaMalloc(&s->a5hi, (size_t)H5 * W5 * 64 * 2));
+    CNN_TRY(cudaMalloc(&s->a5lo, (size_t)H5 * W5 * 64 * 2));
+    CNN_TRY(cudaMalloc(&s->feat, (size_t)H6 * W6 * 48 * 4));
+    s->rows = rows; s->cols = cols;
+  }
+  if (!s->ev[0]) for (auto& e : s->ev) CNN_TRY(cudaEventCreate(&e));
+  auto grid2 = [](int oh, int ow) { return dim3((ow + 15) / 16, (oh + 15) / 16); };
+  CNN_TRY(cudaEventRecord(s->ev[0], st));
+  conv3x3_kernel<1, 24, 1, false, true><<<grid2(H1, W1), 256, 0, st>>>(d_layer, H0, W0, pitch, s->d_wf[0], s->d_bias[0], s->a1);
+  conv3x3_kernel<24, 24, 8, true, false><<<grid2(H2, W2), 256, 0, st>>>(s->a1, H1, W1, 0, s->d_wf[1], s->d_bias[1], s->a2);
+  maxpool_kernel<<<s->sm_count * 8, 256, 0, st>>>(s->a2, H2, W2, 24, 2, 2, s->p2, HP2, WP2);
+  conv3x3_kernel<24, 48, 8, true, false><<<grid2(H3, W3), 256, 0, st>>>(s->p2, HP2, WP2, 0, s->d_wf[2], s->d_bias[2], s->a3);
+  conv3x3_kernel<48, 48, 8, true, false><<<grid2(H4, W4), 256, 0, st>>>(s->a3, H3, W3, 0, s->d_wf[3], s->d_bias[3], s->a4);
+  maxpool_kernel<<<s->sm_count * 8, 256, 0, st>>>(s->a4, H4, W4, 48, 3, 1, s->p4, HP4, WP4);
+  conv3x3_kernel<48, 48, 8, true, false><<<grid2(H5, W5), 256, 0, st>>>(s->p4, HP4, WP4, 0, s->d_wf[4], s->d_bias[4], s->a5);
+  CNN_TRY(cudaGetLastError());
+  CNN_TRY(cudaEventRecord(s->ev[1], st));
+  if (use_reference_conv15) {
+    conv15_reference_kernel<<<(H6 * W6 * 48 + 255) / 256, 256, 0, st>>>(s->a5, H5, W5, s->d_wf6, s->d_bias[5], s->feat);
+    CNN_TRY(cudaGetLastError());
+    CNN_TRY(cudaEventRecord(s->ev[2], st));
+  } else {
+    split_pad_kernel<<<s->sm_count * 8, 256, 0, st>>>(s->a5, (size_t)H5 * W5, s->a5hi, s->a5lo);
+    CUtensorMap maps[4];
+    int rc = encode_maps(s, maps, H5, W5, err);
+    if (rc) return rc;
+    CNN_TRY(cudaFuncSetAttribute(conv15_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv15Smem));
+    CNN_TRY(cudaEventRecord(s->ev[2], st));
+    dim3 grid((W6 + kTileX - 1) / kTileX, (H6 + kTileY - 1) / kTileY);
+    conv15_tcgen05_kernel<<<grid, 192, kConv15Smem, st>>>(maps[0], maps[1], maps[2], maps[3], s->d_bias[5], s->feat, H6, W6,
+                                                          s->use_base_offset);
+    CNN_TRY(cudaGetLastError());
+  }
+  CNN_TRY(cudaEventRecord(s->ev[3], st));
+  CNN_TRY(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&s->last_ms[0], s->ev[0], s->ev[1]);   // 3x3 stack
+  cudaEventElapsedTime(&s->last_ms[1], s->ev[2], s->ev[3]);   // 15x15 layer
+  cudaEventElapsedTime(&s->last_ms[2], s->ev[0], s->ev[3]);   // whole trunk
+  s->Hf = H6; s->Wf = W6;
+  s->res = res; s->Lx = rows * res; s->Ly = cols * res; s->cx = cx; s->cy = cy;
+  s->has_features = true;
+  return 0;
+}
+
+int motion_cost(State* s, const float* d_edges, size_t n, float* d_cost3, cudaStream_t st, std::string& err) {
+  if (!s->has_weights) { err = "motion-cost weights not set"; return -5; }
+  if (!s->has_features) { err = "features not computed (call artp_update_features after artp_set_map)"; return -5; }
+  if (n == 0) return 0;
+  CNN_TRY(cudaSetDevice(s->device));
+  head_kernel<<<(unsigned)((n + 127) / 128), 128, kHeadFloats * sizeof(float), st>>>(s->feat, s->Hf, s->Wf, s->d_head, d_edges, n,
+                                                                                      d_cost3, s->res, s->Lx, s->Ly, s->cx, s->cy);
+  CNN_TRY(cudaGetLastError());
+  return 0;
+}
+
+int copy_features(State* s, float* host_out, size_t n_floats, std::string& err) {
+  if (!s->has_features) { err = "features not computed"; return -5; }
+  if (n_floats != (size_t)s->Hf * s->Wf * 48) { err = "feature buffer size mismatch"; return -1; }
+  CNN_TRY(cudaMemcpy(host_out, s->feat, n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+void feature_shape(const State* s, int* hf, int* wf) { *hf = s->Hf; *wf = s->Wf; }
+
+}  // namespace artp_cnn

@@ -22,7 +22,7 @@
  *                                   PRMMotionCost::addValidMilestone (prm_motion_cost.cpp:341-372)
  *   artp_path_length_cost[_device]  ompl::base::OptimizationObjective::motionCost ->
  *                                   PathLengthObjective::motionCost (objectives/path_length_objective.cpp:26-70)
- *   artp_set_cost_weights, artp_update_features, artp_motion_cost
+ *   artp_set_cost_weights, artp_update_features, artp_motion_cost[_device]
  *                                   the MotionCostFunc batch functor (objectives/motion_cost_objective.h:22-23)
  *                                   = ROS service cost_query (art_planner_ros/src/planner_ros.cpp:283-308,
  *                                   art_planner_motion_cost/scripts/cost_query_server.py:145-169,
@@ -112,6 +112,31 @@ int artp_get_last_timing(artp_handle* h, float* ms3);
 /* Test hook: 0 = normal (classify -> warp stage -> grouping stage for deferred boxes),
  *            1 = send every in-map box through the exact block-level grouping kernel. */
 int artp_set_mode(artp_handle* h, int mode);
+
+/* ---- learned motion cost (MotionCostFunc, objectives/motion_cost_objective.h:22-23) ------------------------------
+ * Weights: ONE flat fp32 blob in the layer order of the reference's `network` module (network_light.py:9-63):
+ * init_conv1..5, init_flatten, tar0_conv1, out0_conv1, out1_conv1..3 -- each conv.weight [Cout][Cin][kh][kw] followed by
+ * its BatchNorm weight, bias, running_mean, running_var -- then out2_conv1..3 as conv.weight followed by conv.bias.
+ * artp_cost_weights_size() floats in total (583 767 parameters + BN buffers). */
+size_t artp_cost_weights_size(void);
+int artp_set_cost_weights(artp_handle* h, const float* blob, size_t n_floats);
+/* CostPredictor.updateFeatures (predictor.py:28-36): run the CNN trunk over the `elevation` layer of the current map
+ * (orientation as cost_query_server.py:74). Call after artp_set_map whenever the map changed. */
+int artp_update_features(artp_handle* h);
+/* GPUCostQueryServer.handle_cost_query_no_update (cost_query_server.py:120-141) = CostQuery.__call__: edges n x 6 floats
+ * [target_x, target_y, target_yaw, start_x, start_y, start_yaw] in the map frame -> cost3 n x 3 floats
+ * (energy, time, risk = 1 - p_success). HOST buffers. */
+int artp_motion_cost(artp_handle* h, const float* edges, size_t n, float* cost3);
+int artp_motion_cost_device(artp_handle* h, const float* d_edges, size_t n, float* d_cost3, void* stream);
+/* MotionCostObjective::getCost / isFeasible (motion_cost_objective.h:54-66) on host arrays:
+ * cost[i] = w_e*E + w_t*T + w_r*R, feasible[i] = R <= risk_threshold (weights / threshold from artp_params). */
+int artp_combine_cost(artp_handle* h, const float* cost3, size_t n, double* cost, uint8_t* feasible);
+/* Test hooks: feature map copy-out ([Hf][Wf][48] fp32, channels last), kernel selection (bit 0: CUDA-core fp32
+ * reference for the 15x15 layer instead of tcgen05; bit 1: set the smem-descriptor base_offset, a known-wrong variant kept for the record), trunk timings
+ * ms3 = (3x3 stack, 15x15 layer, whole trunk) of the last artp_update_features. */
+int artp_get_features(artp_handle* h, float* out, size_t n_floats, int* hf, int* wf);
+int artp_set_cnn_mode(artp_handle* h, int mode);
+int artp_get_cnn_timing(artp_handle* h, float* ms3);
 
 /* Version string of the library / kernel image ("artp <ver> sm_100a"). */
 const char* artp_version(void);

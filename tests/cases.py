@@ -43,6 +43,11 @@ def ramp():
     return m
 
 
+def c4_map():
+    """BASELINE configs[3]: 256x256 crop of the C2 fBm elevation (fp32), same generator, own extent."""
+    return synth.make_fbm_map(256, 256, 0.04, seed=2, amp=0.6)
+
+
 MAPS = {
     "flat": lambda: synth.make_flat_map(),
     "flat_holes_terrace": flat_holes_terrace,
