@@ -174,12 +174,13 @@ def main():
     gather_cnt = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(world)]
     gather_idx = torch.empty(world * n, dtype=torch.int64, device="cuda") if world > 1 else None
 
+    from art_planner_b200 import sharding
+
     def step_device():
         chk.isValidBatch(d_poses, out=d_valid)
         if world > 1:   # ordered valid-sample indices -> one padded all-gather (+ counts)
             idx, cnt = chk.compactValid(d_valid, base=rank * n)
-            dist.all_gather(gather_cnt, cnt)
-            dist.all_gather_into_tensor(gather_idx, idx)
+            sharding.gather_valid_indices(idx, cnt, world, out_idx=gather_idx, out_cnt=gather_cnt)
 
     def step_e2e():
         chk.isValidHostPtr(h_poses.data_ptr(), n, h_valid.data_ptr())
@@ -227,6 +228,61 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- secondary workloads of the same hot path (BASELINE configs[2] and [3]); N = 1 only, short -------------
+    secondary = None
+    if world == 1:
+        secondary = {}
+        s1, s2 = synth.make_edges(m, 100_000, seed=4)
+        d1, d2 = torch.from_numpy(s1).cuda(), torch.from_numpy(s2).cuda()
+        mv = apb.MotionValidator(chk, 20)
+        ev_out = torch.empty(100_000, dtype=torch.uint8, device="cuda")
+        for _ in range(3):
+            mv.checkMotionBatch(d1, d2, out=ev_out)
+        torch.cuda.synchronize()
+        a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            mv.checkMotionBatch(d1, d2, out=ev_out)
+        bb.record(); torch.cuda.synchronize()
+        ms = a.elapsed_time(bb) / 20
+        secondary["edge_validity"] = {"workload": "configs[2]: 100k edges x 20 interpolation steps (+ end state), same map",
+                                      "edges_per_s": 100_000 / (ms * 1e-3), "state_checks_per_s_upper": 2_100_000 / (ms * 1e-3),
+                                      "ms_per_batch": ms, "valid_fraction": float(ev_out.float().mean())}
+        plo = apb.PathLengthObjective(chk)
+        c_out = torch.empty(100_000, dtype=torch.float64, device="cuda")
+        plo.motionCostBatch(d1, d2, out=c_out); torch.cuda.synchronize(); a.record()
+        for _ in range(50):
+            plo.motionCostBatch(d1, d2, out=c_out)
+        bb.record(); torch.cuda.synchronize()
+        secondary["path_length_cost"] = {"evals_per_s": 100_000 * 50 / (a.elapsed_time(bb) * 1e-3)}
+        try:
+            from art_planner_b200 import costnet
+            m4 = synth.make_fbm_map(256, 256, MAP_RES, seed=MAP_SEED, amp=0.6)
+            chk4 = apb.StateValidityChecker(synth.PARAMS_YAML, device=local)
+            chk4.setMap(m4); chk4.updateHeightField()
+            mco = apb.MotionCostObjective(chk4)
+            mco.setWeights(costnet.make_state_dict(seed=5))
+            tms = []
+            for _ in range(8):
+                mco.updateFeatures(); tms.append(mco.lastTrunkTimesMs())
+            tms = np.array(tms[3:]).mean(0)
+            qd = torch.from_numpy(costnet.make_queries(m4, 4096, seed=6)).cuda()
+            qo = torch.empty((4096, 3), dtype=torch.float32, device="cuda")
+            for _ in range(3):
+                mco.costQuery(qd, out=qo)
+            torch.cuda.synchronize(); a.record()
+            for _ in range(100):
+                mco.costQuery(qd, out=qo)
+            bb.record(); torch.cuda.synchronize()
+            hms = a.elapsed_time(bb) / 100
+            secondary["motion_cost_cnn"] = {
+                "workload": "configs[3]: 256x256 elevation patch -> cost CNN trunk, 4096-query batch, seeded random weights",
+                "trunk_ms": float(tms[2]), "conv3x3_stack_ms": float(tms[0]), "conv15x15_tcgen05_ms": float(tms[1]),
+                "trunk_tflops": 13.41e9 / (float(tms[2]) * 1e-3) / 1e12, "conv15_tflops": 11.21e9 / (float(tms[1]) * 1e-3) / 1e12,
+                "head_ms_4096_queries": hms, "edge_cost_evals_per_s": 4096 / (hms * 1e-3)}
+        except Exception as ex:   # never let a secondary workload take the headline line down
+            secondary["motion_cost_cnn"] = {"error": repr(ex)}
 
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -286,7 +342,7 @@ def main():
             "cpu_baseline": {"value": n_mt / t_mt, "unit": "poses/s", "cores": cores, "kind": kind,
                              "sample": f"first {n_mt} poses of the workload, {cores} threads; single-thread on first {n1}",
                              "single_thread_value": n1 / t_single, "mask_equals_gpu": parity_ok},
-            "clocks": clocks, "wall_s_timed_region": wall,
+            "clocks": clocks, "wall_s_timed_region": wall, "secondary": secondary,
         }
         print(json.dumps(out))
     if world > 1:

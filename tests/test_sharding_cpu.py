@@ -1,0 +1,74 @@
+"""CPU-only, world_size 2 over gloo: the N>1 host logic -- shard assignment, ordered index exchange, merge."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_total, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import cases
+        from art_planner_b200 import sharding, synth
+        from oracle import orc
+        m = cases.MAPS["fixture"]()
+        lo, hi = sharding.shard_range(n_total, rank, world)
+        poses = synth.make_terrain_poses(m, hi - lo, seed=9, start=lo)       # pure function of (seed, index)
+        o = orc.Oracle(cases.PARAMS["yaml"], "port")                         # the checker stands in for the GPU kernel
+        o.set_map(m)
+        valid = o.check_poses(poses)
+        cap = (n_total + world - 1) // world
+        idx = torch.zeros(cap, dtype=torch.int64)
+        nz = np.nonzero(valid)[0] + lo
+        idx[: len(nz)] = torch.from_numpy(nz)
+        cnt = torch.tensor([len(nz)], dtype=torch.int32)
+        all_idx, counts = sharding.gather_valid_indices(idx, cnt, world)
+        merged = sharding.merge_gathered(all_idx, counts, cap)
+        if rank == 0:
+            full = o.check_poses(synth.make_terrain_poses(m, n_total, seed=9))
+            q.put((merged.numpy().tolist() == np.nonzero(full)[0].tolist(), int(full.sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_ranges_partition_the_stream():
+    from art_planner_b200 import sharding
+    for n in (0, 1, 7, 1000, 1_000_003):
+        for w in (1, 2, 3, 8):
+            r = [sharding.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[k][1] == r[k + 1][0] for k in range(w - 1))
+            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def test_two_rank_index_exchange_over_gloo(port_lib):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 4001, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    ok, n_valid = q.get(timeout=10)
+    assert ok and n_valid > 0
