@@ -11,7 +11,8 @@
 // fp16 split (a = a_hi + a_lo, w = w_hi + w_lo; D += a_hi*w_hi + a_hi*w_lo + a_lo*w_hi, fp32 accumulate in TMEM),
 // which keeps ~22 mantissa bits per product.
 //
-// 15x15 kernel (conv15_tcgen05_kernel): one CTA per 16(y) x 8(x) output tile (UMMA M = 128, N = 48).
+// Tensor-core kernel (conv_tc_kernel<KS,...>, described for the 15x15 layer): one CTA per 16(y) x 8(x) output tile
+// (UMMA M = 128, N = 48).
 //   * The whole input halo brick [30 y][24 x][64 ch] (hi and lo, 92 KB each) is TMA-loaded ONCE into 128B-swizzled
 //     shared memory; pixels are 128-byte rows, image rows are 24 pixels = 3072 B = 3 swizzle atoms apart, so every one
 //     of the 225 taps is just a shifted view of the same brick: start address += (ky*24 + kx)*128 B, stride between
@@ -21,7 +22,9 @@
 //   * Weights [tap][48][64] fp16 hi/lo stream through a 3-stage TMA ring (12 KB per tap).
 //   * Warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected lane), warps 2..5 = epilogue
 //     (tcgen05.ld -> +bias -> LeakyReLU -> fp32 NHWC feature map).
-// The five 3x3 layers (16.4 % of the FLOPs) are fp32 CUDA-core direct convolutions in round 1.
+// Layers 2..5 (3x3) use the same kernel with an 18 x 16-pixel brick and 9 taps, writing either fp32 NHWC (before a
+// max-pool) or directly the next layer's fp16 hi/lo NHWC-64 input; layer 1 (Cin = 1) stays on CUDA cores.
+// A complete fp32 CUDA-core path (conv3x3_kernel, conv15_reference_kernel) is kept as the in-library cross-check.
 // This translation unit is compiled WITHOUT -fmad=false (no bit-exactness requirement here).
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -170,27 +173,6 @@ __global__ void fold_conv_kernel(const float* __restrict__ w, const float* __res
   }
 }
 
-// 15x15 layer weights -> fp16 hi/lo [tap][48 n][64 c] (K-major rows of 128 B; c >= 48 zero), BN scale folded.
-__global__ void fold_flatten_kernel(const float* __restrict__ w /*[48][48][225]*/, const float* __restrict__ bn,
-                                    __half* __restrict__ whi, __half* __restrict__ wlo, float* __restrict__ bias) {
-  const int total = 225 * 48 * 64;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c = i & 63, r = i >> 6, n = r % 48, tap = r / 48;
-    float v = 0.0f;
-    if (c < 48) {
-      const float s = bn[n] / sqrtf(bn[3 * 48 + n] + kBnEps);
-      v = w[((size_t)n * 48 + c) * 225 + tap] * s * kWScale;   // power-of-two scale keeps w_lo out of fp16 subnormals
-    }
-    const __half h = __float2half_rn(v);
-    whi[i] = h;
-    wlo[i] = __float2half_rn(v - __half2float(h));
-  }
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < 48; n += gridDim.x * blockDim.x) {
-    const float s = bn[n] / sqrtf(bn[3 * 48 + n] + kBnEps);
-    bias[n] = bn[48 + n] - bn[2 * 48 + n] * s;
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // tcgen05 / TMA / mbarrier primitives (inline PTX, sm_100a)
 // ------------------------------------------------------------------------------------------------
@@ -254,28 +236,44 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
 }
 
 constexpr int kTileY = 16, kTileX = 8;           // output tile (UMMA M = 128 = 16 groups of 8 pixels along x)
-constexpr int kBrickY = kTileY + 14, kBrickX = 24;   // halo brick, x padded 22 -> 24 so the row pitch is 3 swizzle atoms
-constexpr int kBrickBytes = kBrickY * kBrickX * 128;  // per split term
-constexpr int kWStageBytes = 2 * 48 * 128;            // hi + lo weight tile of one tap
 constexpr int kWStages = 3;
-constexpr int kConv15Smem = 2 * kBrickBytes + kWStages * kWStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-// instruction descriptor: D = f32 (bits [4,6) = 1), A = B = f16 (0), K-major both, N = 48 (>>3 at [17,23)), M = 128 (>>4 at [24,29))
-constexpr uint32_t kIdesc = (1u << 4) | ((48u >> 3) << 17) | ((128u >> 4) << 24);
 
-__global__ void __launch_bounds__(192, 1)
-conv15_tcgen05_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
-                      const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
-                      const float* __restrict__ bias, float* __restrict__ out, int OH, int OW, int use_base_offset) {
+template <int KS, int NOUT>
+struct ConvCfg {
+  static constexpr int kBrickY = kTileY + KS - 1;
+  static constexpr int kBrickX = ((kTileX + KS - 1) + 7) & ~7;   // row pitch = whole swizzle atoms (8 pixels = 1024 B)
+  static constexpr int kBrickBytes = kBrickY * kBrickX * 128;    // per split term
+  static constexpr int kWStageBytes = 2 * NOUT * 128;            // hi + lo weight tile of one tap
+  static constexpr int kSmem = 2 * kBrickBytes + kWStages * kWStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // instruction descriptor: D = f32 (bits [4,6) = 1), A = B = f16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+  static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(NOUT >> 3) << 17) | ((128u >> 4) << 24);
+};
+
+// Implicit-GEMM convolution on tcgen05 (see the file header). KS x KS taps, KSTEPS x 16 input channels multiplied
+// per tap (channels are stored padded to 64 = one 128-byte swizzle row per pixel), NOUT = UMMA N (multiple of 16),
+// NMAIN fp32 accumulators for the a_hi*w_hi products (tap t -> t % NMAIN) + 1 for the two correction terms.
+// SPLIT_OUT: write the activation as fp16 hi/lo NHWC-64 (the next layer's TMA source) instead of fp32 NHWC.
+template <int KS, int KSTEPS, int NOUT, int NMAIN, bool SPLIT_OUT>
+__global__ void __launch_bounds__(192)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+               const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
+               const float* __restrict__ bias, float* __restrict__ out, __half* __restrict__ out_hi,
+               __half* __restrict__ out_lo, int OH, int OW, int cout, int use_base_offset) {
+  using Cfg = ConvCfg<KS, NOUT>;
+  constexpr int kTaps = KS * KS;
+  constexpr int kAcc = NMAIN + 1;
+  constexpr int kTmemCols = kAcc * 64 <= 64 ? 64 : (kAcc * 64 <= 128 ? 128 : (kAcc * 64 <= 256 ? 256 : 512));
+  static_assert(kAcc * 64 <= 512, "too many accumulators");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* a_hi = smem;
-  unsigned char* a_lo = smem + kBrickBytes;
-  unsigned char* w_st = smem + 2 * kBrickBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_st + kWStages * kWStageBytes);
+  unsigned char* a_lo = smem + Cfg::kBrickBytes;
+  unsigned char* w_st = smem + 2 * Cfg::kBrickBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_st + kWStages * Cfg::kWStageBytes);
   uint64_t* bar_brick = bars;                 // TMA -> MMA: activations landed
   uint64_t* bar_full = bars + 1;              // [kWStages] TMA -> MMA: weight tap landed
   uint64_t* bar_empty = bars + 1 + kWStages;  // [kWStages] MMA -> TMA: stage consumed
-  uint64_t* bar_done = bars + 1 + 2 * kWStages;   // MMA -> epilogue: accumulator complete
+  uint64_t* bar_done = bars + 1 + 2 * kWStages;   // MMA -> epilogue: accumulators complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * kWStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -287,8 +285,8 @@ conv15_tcgen05_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_
     mbar_init(bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM allocation: 8 accumulators x 64 columns (N = 48 used of each), one warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+  if (warp == 1) {   // TMEM allocation: kAcc accumulators x 64 columns (NOUT used of each), one warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -298,17 +296,17 @@ conv15_tcgen05_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_
 
   if (warp == 0) {
     if (lane == 0) {
-      // activations: one box [64 ch][24 x][30 y] per split term (out-of-range pixels are zero-filled by TMA)
-      mbar_expect_tx(bar_brick, 2 * kBrickBytes);
+      // activations: one box [64 ch][kBrickX x][kBrickY y] per split term (out-of-range pixels are zero-filled by TMA)
+      mbar_expect_tx(bar_brick, 2 * Cfg::kBrickBytes);
       tma_load_3d(a_hi, &map_ahi, bar_brick, 0, x0, y0);
       tma_load_3d(a_lo, &map_alo, bar_brick, 0, x0, y0);
-      // weights: ring over the 225 taps
-      for (int t = 0; t < 225; ++t) {
+      // weights: ring over the taps
+      for (int t = 0; t < kTaps; ++t) {
         const int s = t % kWStages, round = t / kWStages;
         if (round > 0) mbar_wait(bar_empty + s, (round - 1) & 1);
-        mbar_expect_tx(bar_full + s, kWStageBytes);
-        tma_load_2d(w_st + s * kWStageBytes, &map_whi, bar_full + s, 0, t * 48);
-        tma_load_2d(w_st + s * kWStageBytes + 48 * 128, &map_wlo, bar_full + s, 0, t * 48);
+        mbar_expect_tx(bar_full + s, Cfg::kWStageBytes);
+        tma_load_2d(w_st + s * Cfg::kWStageBytes, &map_whi, bar_full + s, 0, t * NOUT);
+        tma_load_2d(w_st + s * Cfg::kWStageBytes + NOUT * 128, &map_wlo, bar_full + s, 0, t * NOUT);
       }
     }
   } else if (warp == 1) {
@@ -316,27 +314,28 @@ conv15_tcgen05_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_
       mbar_wait(bar_brick, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t ahi = smem_u32(a_hi), alo = smem_u32(a_lo);
-      for (int t = 0; t < 225; ++t) {
+      for (int t = 0; t < kTaps; ++t) {
         const int s = t % kWStages, round = t / kWStages;
         mbar_wait(bar_full + s, round & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int ky = t / 15, kx = t % 15;
-        const uint32_t shift = (uint32_t)(ky * kBrickX + kx);           // in pixels = 128-byte rows
+        const int ky = t / KS, kx = t % KS;
+        const uint32_t shift = (uint32_t)(ky * Cfg::kBrickX + kx);           // in pixels = 128-byte rows
         const uint32_t bo = use_base_offset ? (shift & 7u) : 0u;
-        const uint32_t whi = smem_u32(w_st + s * kWStageBytes), wlo = whi + 48 * 128;
+        const uint32_t whi = smem_u32(w_st + s * Cfg::kWStageBytes), wlo = whi + NOUT * 128;
         // The tensor core truncates when it adds into the fp32 accumulator, so a single accumulator would take
-        // 2025 biased roundings (measured 4e-5 relative). Spread them: the a_hi*w_hi products of tap t go to
-        // accumulator t % 7, both small correction terms to an eighth one; the epilogue sums the eight in fp32 RN.
-        const uint32_t d_main = tmem_base + (uint32_t)((t % 7) * 64), d_corr = tmem_base + 7u * 64u;
+        // thousands of biased roundings in the 15x15 layer (measured 4e-5 relative). Spread them: the a_hi*w_hi
+        // products of tap t go to accumulator t % NMAIN, both small correction terms to one more; the epilogue sums
+        // them in fp32 round-to-nearest.
+        const uint32_t d_main = tmem_base + (uint32_t)((t % NMAIN) * 64), d_corr = tmem_base + (uint32_t)(NMAIN * 64);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {   // K = 48 channels = 3 x UMMA_K(16); the 16 pad channels are never multiplied
-          const uint64_t dah = make_desc(ahi + shift * 128 + j * 32, kBrickX * 128, bo);
-          const uint64_t dal = make_desc(alo + shift * 128 + j * 32, kBrickX * 128, bo);
+        for (int j = 0; j < KSTEPS; ++j) {   // KSTEPS x UMMA_K(16) channels; pad channels beyond are never multiplied
+          const uint64_t dah = make_desc(ahi + shift * 128 + j * 32, Cfg::kBrickX * 128, bo);
+          const uint64_t dal = make_desc(alo + shift * 128 + j * 32, Cfg::kBrickX * 128, bo);
           const uint64_t dwh = make_desc(whi + j * 32, 1024, 0);
           const uint64_t dwl = make_desc(wlo + j * 32, 1024, 0);
-          umma_f16(d_main, dah, dwh, kIdesc, (t >= 7 || j != 0));
-          umma_f16(d_corr, dah, dwl, kIdesc, (t | j) != 0);
-          umma_f16(d_corr, dal, dwh, kIdesc, 1);
+          umma_f16(d_main, dah, dwh, Cfg::kIdesc, (t >= NMAIN || j != 0));
+          umma_f16(d_corr, dah, dwl, Cfg::kIdesc, (t | j) != 0);
+          umma_f16(d_corr, dal, dwh, Cfg::kIdesc, 1);
         }
         umma_commit(bar_empty + s);   // frees the weight stage once these MMAs have read it
       }
@@ -349,13 +348,14 @@ conv15_tcgen05_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
-    float acc[48];
+    float acc[NOUT];
 #pragma unroll
-    for (int n = 0; n < 48; ++n) acc[n] = 0.0f;
+    for (int n = 0; n < NOUT; ++n) acc[n] = 0.0f;
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
+    for (int a = 0; a < kAcc; ++a) {
+      if (a < NMAIN && a >= kTaps) continue;   // accumulator never written
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
+      for (int c = 0; c < NOUT / 16; ++c) {
         uint32_t v[16];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64 + c * 16);
         asm volatile(
@@ -369,18 +369,115 @@ conv15_tcgen05_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_
       }
     }
     if (oy < OH && ox < OW) {
-      float* op = out + ((size_t)oy * OW + ox) * 48;
+      const size_t pix = (size_t)oy * OW + ox;
+      if (SPLIT_OUT) {
+        __half2* ph = reinterpret_cast<__half2*>(out_hi + pix * 64);
+        __half2* pl = reinterpret_cast<__half2*>(out_lo + pix * 64);
 #pragma unroll
-      for (int n = 0; n < 48; ++n) {
-        float f = acc[n] * (1.0f / kWScale) + __ldg(bias + n);
-        op[n] = f > 0.0f ? f : 0.3f * f;
+        for (int n2 = 0; n2 < 32; ++n2) {
+          float f[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int n = 2 * n2 + e;
+            float v = 0.0f;
+            if (n < NOUT && n < cout) { v = acc[n < NOUT ? n : 0] * (1.0f / kWScale) + __ldg(bias + n); v = v > 0.0f ? v : 0.3f * v; }
+            f[e] = v;
+          }
+          const __half h0 = __float2half_rn(f[0]), h1 = __float2half_rn(f[1]);
+          ph[n2] = __halves2half2(h0, h1);
+          pl[n2] = __halves2half2(__float2half_rn(f[0] - __half2float(h0)), __float2half_rn(f[1] - __half2float(h1)));
+        }
+      } else {
+        float* op = out + pix * cout;
+#pragma unroll
+        for (int n = 0; n < NOUT; ++n) {
+          if (n < cout) {
+            float f = acc[n] * (1.0f / kWScale) + __ldg(bias + n);
+            op[n] = f > 0.0f ? f : 0.3f * f;
+          }
+        }
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
+// First layer (Cin = 1, no activation after its BN) on CUDA cores, reading the map layer directly and writing the
+// fp16 hi/lo NHWC-64 input of the second layer.
+__global__ void conv1_split_kernel(const float* __restrict__ layer, int H, int W, int pitch, const float* __restrict__ wf /*[9][1][24]*/,
+                                   const float* __restrict__ bias, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int OH = H - 2, OW = W - 2;
+  const size_t total = (size_t)OH * OW;
+  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(p % OW), oy = (int)(p / OW);
+    float in[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) in[t] = __ldg(layer + (size_t)(ox + t % 3) * pitch + (H - 1 - (oy + t / 3)));   // E[r][c]
+    __half2* ph = reinterpret_cast<__half2*>(hi + p * 64);
+    __half2* pl = reinterpret_cast<__half2*>(lo + p * 64);
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) {
+      float f[2] = {0.0f, 0.0f};
+      if (n2 < 12) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int n = 2 * n2 + e;
+          float a = __ldg(bias + n);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) a = fmaf(in[t], __ldg(wf + t * 24 + n), a);
+          f[e] = a;
+        }
+      }
+      const __half h0 = __float2half_rn(f[0]), h1 = __float2half_rn(f[1]);
+      ph[n2] = __halves2half2(h0, h1);
+      pl[n2] = __halves2half2(__float2half_rn(f[0] - __half2float(h0)), __float2half_rn(f[1] - __half2float(h1)));
+    }
+  }
+}
+
+// max pooling (K x K, stride S) of an fp32 NHWC [H][W][C] activation into fp16 hi/lo NHWC-64.
+__global__ void maxpool_split_kernel(const float* __restrict__ in, int H, int W, int C, int K, int S, __half* __restrict__ hi,
+                                     __half* __restrict__ lo, int OH, int OW) {
+  const size_t total = (size_t)OH * OW * 64;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 63);
+    const size_t p = i >> 6;
+    const int ox = (int)(p % OW), oy = (int)(p / OW);
+    float m = 0.0f;
+    if (c < C) {
+      m = -INFINITY;
+      for (int dy = 0; dy < K; ++dy)
+        for (int dx = 0; dx < K; ++dx) m = fmaxf(m, in[((size_t)(oy * S + dy) * W + ox * S + dx) * C + c]);
+    }
+    const __half h = __float2half_rn(m);
+    hi[i] = h;
+    lo[i] = __float2half_rn(m - __half2float(h));
+  }
+}
+
+// Tensor-core weights of one layer: [taps][NOUT][64] fp16 hi/lo (K-major rows of 128 B; pad rows / channels zero),
+// BN scale and kWScale folded; bias = beta - mean*scale.
+__global__ void fold_tc_kernel(const float* __restrict__ w /*[cout][cin][taps]*/, const float* __restrict__ bn, int cout, int cin,
+                               int taps, int nout, __half* __restrict__ whi, __half* __restrict__ wlo, float* __restrict__ bias) {
+  const int total = taps * nout * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i & 63, r = i >> 6, n = r % nout, tap = r / nout;
+    float v = 0.0f;
+    if (c < cin && n < cout) {
+      const float s = bn[n] / sqrtf(bn[3 * cout + n] + kBnEps);
+      v = w[((size_t)n * cin + c) * taps + tap] * s * kWScale;   // power-of-two scale keeps w_lo out of fp16 subnormals
+    }
+    const __half h = __float2half_rn(v);
+    whi[i] = h;
+    wlo[i] = __float2half_rn(v - __half2float(h));
+  }
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < cout; n += gridDim.x * blockDim.x) {
+    const float s = bn[n] / sqrtf(bn[3 * cout + n] + kBnEps);
+    bias[n] = bn[cout + n] - bn[2 * cout + n] * s;
   }
 }
 
@@ -520,24 +617,31 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// One tensor-core layer: weights (hi/lo), bias, and its launch geometry.
+struct TcLayer { __half *whi = nullptr, *wlo = nullptr; int nout = 0; };
+
 struct State {
   int device = 0, sm_count = 0;
   bool has_weights = false, has_features = false;
   float* d_blob = nullptr;
   size_t layer_off[14];
-  float* d_wf[5] = {};     // folded 3x3 weights [9][cin][cout]
+  float* d_wf[5] = {};     // folded fp32 3x3 weights [9][cin][cout] (layer 0 always; 1..4 for the CUDA-core check path)
   float* d_bias[6] = {};   // folded biases (layers 0..5)
-  float* d_wf6 = nullptr;  // folded fp32 15x15 weights [225][48][48] (self-check only)
-  __half *d_whi = nullptr, *d_wlo = nullptr;
+  float* d_wf6 = nullptr;  // folded fp32 15x15 weights [225][48][48] (CUDA-core check path only)
+  TcLayer tc[6];           // tensor-core weights of layers 1..5 (index = layer)
   float* d_head = nullptr;
   size_t* d_offs = nullptr;
-  // activations (sized for the current map)
+  // activations (sized for the current map); h* / l* = fp16 hi / lo NHWC-64, f* = fp32 NHWC
   int rows = 0, cols = 0;
-  float *a1 = nullptr, *a2 = nullptr, *p2 = nullptr, *a3 = nullptr, *a4 = nullptr, *p4 = nullptr, *a5 = nullptr, *feat = nullptr;
-  __half *a5hi = nullptr, *a5lo = nullptr;
+  __half *h1 = nullptr, *l1 = nullptr, *hp2 = nullptr, *lp2 = nullptr, *h3 = nullptr, *l3 = nullptr, *hp4 = nullptr,
+         *lp4 = nullptr, *h5 = nullptr, *l5 = nullptr;
+  float *f1 = nullptr, *f2 = nullptr, *fp2 = nullptr, *f3 = nullptr, *f4 = nullptr, *fp4 = nullptr, *f5 = nullptr, *feat = nullptr;
   int Hf = 0, Wf = 0;
   double res = 0, Lx = 0, Ly = 0, cx = 0, cy = 0;
   EncodeTiledFn encode = nullptr;
+  CUtensorMap maps[6][4];      // per tensor-core layer: activation hi/lo, weight hi/lo (rebuilt when buffers change)
+  bool maps_valid = false;
+  bool attrs_set = false;
   int use_base_offset = 0;
   float last_ms[3] = {0, 0, 0};
   cudaEvent_t ev[4] = {};
@@ -551,10 +655,11 @@ State* create(int device, int sm_count) {
 }
 
 static void free_acts(State* s) {
-  cudaFree(s->a1); cudaFree(s->a2); cudaFree(s->p2); cudaFree(s->a3); cudaFree(s->a4); cudaFree(s->p4); cudaFree(s->a5);
-  cudaFree(s->feat); cudaFree(s->a5hi); cudaFree(s->a5lo);
-  s->a1 = s->a2 = s->p2 = s->a3 = s->a4 = s->p4 = s->a5 = s->feat = nullptr;
-  s->a5hi = s->a5lo = nullptr;
+  void* ptrs[] = {s->h1, s->l1, s->hp2, s->lp2, s->h3, s->l3, s->hp4, s->lp4, s->h5, s->l5,
+                  s->f1, s->f2, s->fp2, s->f3, s->f4, s->fp4, s->f5, s->feat};
+  for (void* p : ptrs) cudaFree(p);
+  s->h1 = s->l1 = s->hp2 = s->lp2 = s->h3 = s->l3 = s->hp4 = s->lp4 = s->h5 = s->l5 = nullptr;
+  s->f1 = s->f2 = s->fp2 = s->f3 = s->f4 = s->fp4 = s->f5 = s->feat = nullptr;
 }
 
 void destroy(State* s) {
@@ -563,7 +668,8 @@ void destroy(State* s) {
   cudaFree(s->d_blob);
   for (auto p : s->d_wf) cudaFree(p);
   for (auto p : s->d_bias) cudaFree(p);
-  cudaFree(s->d_wf6); cudaFree(s->d_whi); cudaFree(s->d_wlo); cudaFree(s->d_head); cudaFree(s->d_offs);
+  for (auto& t : s->tc) { cudaFree(t.whi); cudaFree(t.wlo); }
+  cudaFree(s->d_wf6); cudaFree(s->d_head); cudaFree(s->d_offs);
   for (auto e : s->ev) if (e) cudaEventDestroy(e);
   delete s;
 }
@@ -573,6 +679,8 @@ bool has_features(const State* s) { return s->has_features; }
 bool has_weights(const State* s) { return s->has_weights; }
 void last_times(const State* s, float* ms3) { ms3[0] = s->last_ms[0]; ms3[1] = s->last_ms[1]; ms3[2] = s->last_ms[2]; }
 
+static const int kTcNout[6] = {0, 32, 48, 48, 48, 48};   // UMMA N per layer (Cout 24 padded to 32)
+
 int set_weights(State* s, const float* blob, size_t n, cudaStream_t st, std::string& err) {
   if (n != blob_floats()) { err = "weight blob has the wrong number of floats"; return -1; }
   CNN_TRY(cudaSetDevice(s->device));
@@ -581,8 +689,12 @@ int set_weights(State* s, const float* blob, size_t n, cudaStream_t st, std::str
     for (int l = 0; l < 5; ++l) CNN_TRY(cudaMalloc(&s->d_wf[l], (size_t)9 * kLayers[l].cin * kLayers[l].cout * sizeof(float)));
     for (int l = 0; l < 6; ++l) CNN_TRY(cudaMalloc(&s->d_bias[l], kLayers[l].cout * sizeof(float)));
     CNN_TRY(cudaMalloc(&s->d_wf6, (size_t)225 * 48 * 48 * sizeof(float)));
-    CNN_TRY(cudaMalloc(&s->d_whi, (size_t)225 * 48 * 64 * sizeof(__half)));
-    CNN_TRY(cudaMalloc(&s->d_wlo, (size_t)225 * 48 * 64 * sizeof(__half)));
+    for (int l = 1; l < 6; ++l) {
+      const size_t cnt = (size_t)kLayers[l].k * kLayers[l].k * kTcNout[l] * 64;
+      s->tc[l].nout = kTcNout[l];
+      CNN_TRY(cudaMalloc(&s->tc[l].whi, cnt * sizeof(__half)));
+      CNN_TRY(cudaMalloc(&s->tc[l].wlo, cnt * sizeof(__half)));
+    }
     CNN_TRY(cudaMalloc(&s->d_head, kHeadFloats * sizeof(float)));
     CNN_TRY(cudaMalloc(&s->d_offs, 8 * sizeof(size_t)));
   }
@@ -593,15 +705,15 @@ int set_weights(State* s, const float* blob, size_t n, cudaStream_t st, std::str
   }
   CNN_TRY(cudaMemcpyAsync(s->d_blob, blob, n * sizeof(float), cudaMemcpyHostToDevice, st));
   CNN_TRY(cudaMemcpyAsync(s->d_offs, s->layer_off + 6, 8 * sizeof(size_t), cudaMemcpyHostToDevice, st));
-  for (int l = 0; l < 5; ++l) {
+  for (int l = 0; l < 6; ++l) {
+    const int kk = kLayers[l].k * kLayers[l].k;
     const float* w = s->d_blob + s->layer_off[l];
-    fold_conv_kernel<<<64, 256, 0, st>>>(w, w + (size_t)kLayers[l].cout * kLayers[l].cin * 9, kLayers[l].cout, kLayers[l].cin, 9,
-                                         s->d_wf[l], s->d_bias[l]);
-  }
-  {
-    const float* w = s->d_blob + s->layer_off[5];
-    fold_flatten_kernel<<<256, 256, 0, st>>>(w, w + (size_t)48 * 48 * 225, s->d_whi, s->d_wlo, s->d_bias[5]);
-    fold_conv_kernel<<<256, 256, 0, st>>>(w, w + (size_t)48 * 48 * 225, 48, 48, 225, s->d_wf6, s->d_bias[5]);
+    const float* bn = w + (size_t)kLayers[l].cout * kLayers[l].cin * kk;
+    // fp32 folded weights (first layer + the CUDA-core check path) and biases
+    fold_conv_kernel<<<256, 256, 0, st>>>(w, bn, kLayers[l].cout, kLayers[l].cin, kk, l < 5 ? s->d_wf[l] : s->d_wf6, s->d_bias[l]);
+    if (l >= 1)
+      fold_tc_kernel<<<256, 256, 0, st>>>(w, bn, kLayers[l].cout, kLayers[l].cin, kk, kTcNout[l], s->tc[l].whi, s->tc[l].wlo,
+                                          s->d_bias[l]);
   }
   fold_head_kernel<<<1, 256, 0, st>>>(s->d_blob, s->d_offs, s->d_head);
   CNN_TRY(cudaGetLastError());
@@ -611,25 +723,31 @@ int set_weights(State* s, const float* blob, size_t n, cudaStream_t st, std::str
   return 0;
 }
 
-static int encode_maps(State* s, CUtensorMap* maps, int H5, int W5, std::string& err) {
-  if (!s->encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
-      err = "cuTensorMapEncodeTiled not available from the driver";
-      return -3;
-    }
-    s->encode = reinterpret_cast<EncodeTiledFn>(fn);
+static int get_encoder(State* s, std::string& err) {
+  if (s->encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+    err = "cuTensorMapEncodeTiled not available from the driver";
+    return -3;
   }
-  // activations [H5][W5][64] fp16: dims (c, x, y)
-  const cuuint64_t adim[3] = {64, (cuuint64_t)W5, (cuuint64_t)H5};
-  const cuuint64_t astr[2] = {128, (cuuint64_t)W5 * 128};
-  const cuuint32_t abox[3] = {64, kBrickX, kBrickY};
+  s->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+// maps[0..1]: activations hi/lo [H][W][64] fp16, box (64, brick_x, brick_y); maps[2..3]: weights [taps*nout][64], box (64, nout)
+static int encode_layer_maps(State* s, CUtensorMap* maps, __half* ahi, __half* alo, int H, int W, int brick_x, int brick_y,
+                             __half* whi, __half* wlo, int taps, int nout, std::string& err) {
+  int rc = get_encoder(s, err);
+  if (rc) return rc;
+  const cuuint64_t adim[3] = {64, (cuuint64_t)W, (cuuint64_t)H};
+  const cuuint64_t astr[2] = {128, (cuuint64_t)W * 128};
+  const cuuint32_t abox[3] = {64, (cuuint32_t)brick_x, (cuuint32_t)brick_y};
   const cuuint32_t one3[3] = {1, 1, 1};
-  const cuuint64_t wdim[2] = {64, 225 * 48};
+  const cuuint64_t wdim[2] = {64, (cuuint64_t)taps * nout};
   const cuuint64_t wstr[1] = {128};
-  const cuuint32_t wbox[2] = {64, 48};
-  void* ptrs[4] = {s->a5hi, s->a5lo, s->d_whi, s->d_wlo};
+  const cuuint32_t wbox[2] = {64, (cuuint32_t)nout};
+  void* ptrs[4] = {ahi, alo, whi, wlo};
   for (int i = 0; i < 4; ++i) {
     CUresult r;
     if (i < 2)
@@ -643,9 +761,29 @@ static int encode_maps(State* s, CUtensorMap* maps, int H5, int W5, std::string&
   return 0;
 }
 
+template <int KS, int KSTEPS, int NOUT, int NMAIN, bool SPLIT>
+static int launch_tc(State* s, int layer, __half* ahi, __half* alo, int H, int W, float* out, __half* ohi, __half* olo,
+                     cudaStream_t st, std::string& err) {
+  using Cfg = ConvCfg<KS, NOUT>;
+  CUtensorMap* maps = s->maps[layer];
+  if (!s->maps_valid) {
+    int rc = encode_layer_maps(s, maps, ahi, alo, H, W, Cfg::kBrickX, Cfg::kBrickY, s->tc[layer].whi, s->tc[layer].wlo, KS * KS, NOUT, err);
+    if (rc) return rc;
+  }
+  auto kern = conv_tc_kernel<KS, KSTEPS, NOUT, NMAIN, SPLIT>;
+  if (!s->attrs_set) CNN_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+  const int OH = H - KS + 1, OW = W - KS + 1;
+  dim3 grid((OW + kTileX - 1) / kTileX, (OH + kTileY - 1) / kTileY);
+  kern<<<grid, 192, Cfg::kSmem, st>>>(maps[0], maps[1], maps[2], maps[3], s->d_bias[layer], out, ohi, olo, OH, OW,
+                                      kLayers[layer].cout, s->use_base_offset);
+  CNN_TRY(cudaGetLastError());
+  return 0;
+}
+
 // CostPredictor.updateFeatures (predictor.py:28-36): the CNN trunk over the `elevation` layer currently uploaded.
+// use_cuda_core_path: fp32 CUDA-core direct convolutions for every layer (the in-library cross-check of the tensor path).
 int update_features(State* s, const float* d_layer, int rows, int cols, int pitch, double res, double cx, double cy,
-                    cudaStream_t st, int use_reference_conv15, std::string& err) {
+                    cudaStream_t st, int use_cuda_core_path, std::string& err) {
   if (!s->has_weights) { err = "motion-cost weights not set"; return -5; }
   if (rows < 64 || cols < 64) { err = "map too small for the motion-cost network (needs >= 64 x 64 cells)"; return -1; }
   CNN_TRY(cudaSetDevice(s->device));
@@ -655,49 +793,62 @@ int update_features(State* s, const float* d_layer, int rows, int cols, int pitc
   const int H5 = HP4 - 2, W5 = WP4 - 2, H6 = H5 - 14, W6 = W5 - 14;
   if (rows != s->rows || cols != s->cols) {
     free_acts(s);
-    CNN_TRY(cudaMalloc(&s->a1, (size_t)H1 * W1 * 24 * 4));
-    CNN_TRY(cudaMalloc(&s->a2, (size_t)H2 * W2 * 24 * 4));
-    CNN_TRY(cudaMalloc(&s->p2, (size_t)HP2 * WP2 * 24 * 4));
-    CNN_TRY(cudaMalloc(&s->a3, (size_t)H3 * W3 * 48 * 4));
-    CNN_TRY(cudaMalloc(&s->a4, (size_t)H4 * W4 * 48 * 4));
-    CNN_TRY(cudaMalloc(&s->p4, (size_t)HP4 * WP4 * 48 * 4));
-    CNN_TRY(cudaMalloc(&s->a5, (size_t)H5 * W5 * 48 * 4));
-    CNN_TRY(cudaMalloc(&s->a5hi, (size_t)H5 * W5 * 64 * 2));
-    CNN_TRY(cudaMalloc(&s->a5lo, (size_t)H5 * W5 * 64 * 2));
+    auto hl = [&](__half** h, __half** l, int hh, int ww) -> cudaError_t {
+      cudaError_t e = cudaMalloc(h, (size_t)hh * ww * 64 * 2);
+      return e != cudaSuccess ? e : cudaMalloc(l, (size_t)hh * ww * 64 * 2);
+    };
+    CNN_TRY(hl(&s->h1, &s->l1, H1, W1));
+    CNN_TRY(hl(&s->hp2, &s->lp2, HP2, WP2));
+    CNN_TRY(hl(&s->h3, &s->l3, H3, W3));
+    CNN_TRY(hl(&s->hp4, &s->lp4, HP4, WP4));
+    CNN_TRY(hl(&s->h5, &s->l5, H5, W5));
+    CNN_TRY(cudaMalloc(&s->f1, (size_t)H1 * W1 * 24 * 4));
+    CNN_TRY(cudaMalloc(&s->f2, (size_t)H2 * W2 * 24 * 4));
+    CNN_TRY(cudaMalloc(&s->fp2, (size_t)HP2 * WP2 * 24 * 4));
+    CNN_TRY(cudaMalloc(&s->f3, (size_t)H3 * W3 * 48 * 4));
+    CNN_TRY(cudaMalloc(&s->f4, (size_t)H4 * W4 * 48 * 4));
+    CNN_TRY(cudaMalloc(&s->fp4, (size_t)HP4 * WP4 * 48 * 4));
+    CNN_TRY(cudaMalloc(&s->f5, (size_t)H5 * W5 * 48 * 4));
     CNN_TRY(cudaMalloc(&s->feat, (size_t)H6 * W6 * 48 * 4));
     s->rows = rows; s->cols = cols;
+    s->maps_valid = false;
   }
   if (!s->ev[0]) for (auto& e : s->ev) CNN_TRY(cudaEventCreate(&e));
   auto grid2 = [](int oh, int ow) { return dim3((ow + 15) / 16, (oh + 15) / 16); };
+  const int g1 = s->sm_count * 8;
   CNN_TRY(cudaEventRecord(s->ev[0], st));
-  conv3x3_kernel<1, 24, 1, false, true><<<grid2(H1, W1), 256, 0, st>>>(d_layer, H0, W0, pitch, s->d_wf[0], s->d_bias[0], s->a1);
-  conv3x3_kernel<24, 24, 8, true, false><<<grid2(H2, W2), 256, 0, st>>>(s->a1, H1, W1, 0, s->d_wf[1], s->d_bias[1], s->a2);
-  maxpool_kernel<<<s->sm_count * 8, 256, 0, st>>>(s->a2, H2, W2, 24, 2, 2, s->p2, HP2, WP2);
-  conv3x3_kernel<24, 48, 8, true, false><<<grid2(H3, W3), 256, 0, st>>>(s->p2, HP2, WP2, 0, s->d_wf[2], s->d_bias[2], s->a3);
-  conv3x3_kernel<48, 48, 8, true, false><<<grid2(H4, W4), 256, 0, st>>>(s->a3, H3, W3, 0, s->d_wf[3], s->d_bias[3], s->a4);
-  maxpool_kernel<<<s->sm_count * 8, 256, 0, st>>>(s->a4, H4, W4, 48, 3, 1, s->p4, HP4, WP4);
-  conv3x3_kernel<48, 48, 8, true, false><<<grid2(H5, W5), 256, 0, st>>>(s->p4, HP4, WP4, 0, s->d_wf[4], s->d_bias[4], s->a5);
-  CNN_TRY(cudaGetLastError());
-  CNN_TRY(cudaEventRecord(s->ev[1], st));
-  if (use_reference_conv15) {
-    conv15_reference_kernel<<<(H6 * W6 * 48 + 255) / 256, 256, 0, st>>>(s->a5, H5, W5, s->d_wf6, s->d_bias[5], s->feat);
+  if (use_cuda_core_path) {
+    conv3x3_kernel<1, 24, 1, false, true><<<grid2(H1, W1), 256, 0, st>>>(d_layer, H0, W0, pitch, s->d_wf[0], s->d_bias[0], s->f1);
+    conv3x3_kernel<24, 24, 8, true, false><<<grid2(H2, W2), 256, 0, st>>>(s->f1, H1, W1, 0, s->d_wf[1], s->d_bias[1], s->f2);
+    maxpool_kernel<<<g1, 256, 0, st>>>(s->f2, H2, W2, 24, 2, 2, s->fp2, HP2, WP2);
+    conv3x3_kernel<24, 48, 8, true, false><<<grid2(H3, W3), 256, 0, st>>>(s->fp2, HP2, WP2, 0, s->d_wf[2], s->d_bias[2], s->f3);
+    conv3x3_kernel<48, 48, 8, true, false><<<grid2(H4, W4), 256, 0, st>>>(s->f3, H3, W3, 0, s->d_wf[3], s->d_bias[3], s->f4);
+    maxpool_kernel<<<g1, 256, 0, st>>>(s->f4, H4, W4, 48, 3, 1, s->fp4, HP4, WP4);
+    conv3x3_kernel<48, 48, 8, true, false><<<grid2(H5, W5), 256, 0, st>>>(s->fp4, HP4, WP4, 0, s->d_wf[4], s->d_bias[4], s->f5);
     CNN_TRY(cudaGetLastError());
+    CNN_TRY(cudaEventRecord(s->ev[1], st));
     CNN_TRY(cudaEventRecord(s->ev[2], st));
+    conv15_reference_kernel<<<(H6 * W6 * 48 + 255) / 256, 256, 0, st>>>(s->f5, H5, W5, s->d_wf6, s->d_bias[5], s->feat);
+    CNN_TRY(cudaGetLastError());
   } else {
-    split_pad_kernel<<<s->sm_count * 8, 256, 0, st>>>(s->a5, (size_t)H5 * W5, s->a5hi, s->a5lo);
-    CUtensorMap maps[4];
-    int rc = encode_maps(s, maps, H5, W5, err);
-    if (rc) return rc;
-    CNN_TRY(cudaFuncSetAttribute(conv15_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv15Smem));
-    CNN_TRY(cudaEventRecord(s->ev[2], st));
-    dim3 grid((W6 + kTileX - 1) / kTileX, (H6 + kTileY - 1) / kTileY);
-    conv15_tcgen05_kernel<<<grid, 192, kConv15Smem, st>>>(maps[0], maps[1], maps[2], maps[3], s->d_bias[5], s->feat, H6, W6,
-                                                          s->use_base_offset);
+    int rc;
+    conv1_split_kernel<<<g1, 256, 0, st>>>(d_layer, H0, W0, pitch, s->d_wf[0], s->d_bias[0], s->h1, s->l1);
+    if ((rc = launch_tc<3, 2, 32, 1, false>(s, 1, s->h1, s->l1, H1, W1, s->f2, nullptr, nullptr, st, err))) return rc;
+    maxpool_split_kernel<<<g1, 256, 0, st>>>(s->f2, H2, W2, 24, 2, 2, s->hp2, s->lp2, HP2, WP2);
+    if ((rc = launch_tc<3, 2, 48, 1, true>(s, 2, s->hp2, s->lp2, HP2, WP2, nullptr, s->h3, s->l3, st, err))) return rc;
+    if ((rc = launch_tc<3, 3, 48, 1, false>(s, 3, s->h3, s->l3, H3, W3, s->f4, nullptr, nullptr, st, err))) return rc;
+    maxpool_split_kernel<<<g1, 256, 0, st>>>(s->f4, H4, W4, 48, 3, 1, s->hp4, s->lp4, HP4, WP4);
+    if ((rc = launch_tc<3, 3, 48, 1, true>(s, 4, s->hp4, s->lp4, HP4, WP4, nullptr, s->h5, s->l5, st, err))) return rc;
     CNN_TRY(cudaGetLastError());
+    CNN_TRY(cudaEventRecord(s->ev[1], st));
+    CNN_TRY(cudaEventRecord(s->ev[2], st));
+    if ((rc = launch_tc<15, 3, 48, 7, false>(s, 5, s->h5, s->l5, H5, W5, s->feat, nullptr, nullptr, st, err))) return rc;
+    s->maps_valid = true;
+    s->attrs_set = true;
   }
   CNN_TRY(cudaEventRecord(s->ev[3], st));
   CNN_TRY(cudaStreamSynchronize(st));
-  cudaEventElapsedTime(&s->last_ms[0], s->ev[0], s->ev[1]);   // 3x3 stack
+  cudaEventElapsedTime(&s->last_ms[0], s->ev[0], s->ev[1]);   // layers 1..5
   cudaEventElapsedTime(&s->last_ms[1], s->ev[2], s->ev[3]);   // 15x15 layer
   cudaEventElapsedTime(&s->last_ms[2], s->ev[0], s->ev[3]);   // whole trunk
   s->Hf = H6; s->Wf = W6;
