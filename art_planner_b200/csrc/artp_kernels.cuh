@@ -50,6 +50,18 @@ struct Work {
 __device__ __forceinline__ uint32_t bloom_hash(int kx, int kz) {
   return (((uint32_t)kx * 0x9E3779B1u) ^ ((uint32_t)kz * 0x85EBCA77u)) >> 20;   // 12 bits
 }
+// ceil(2^32 / n) for the flattened-index division t / n = umulhi(t, magic) (exact while t * n < 2^32).
+struct MagicTab {
+  uint32_t v[129];
+  constexpr MagicTab() : v() {
+    for (int i = 2; i < 129; ++i) v[i] = 0xFFFFFFFFu / (uint32_t)i + 1u;
+  }
+};
+__constant__ MagicTab kMagicTab = MagicTab();
+__device__ __forceinline__ uint32_t magic_for(int n) {
+  return n <= 1 ? 0u : (n <= 128 ? kMagicTab.v[n] : 0xFFFFFFFFu / (uint32_t)n + 1u);
+}
+
 constexpr float kKeyScale = 16384.0f;   // bucket width 2^-14 on n0, n2 in [-1, 1]
 constexpr float kKeyMargin = 4e-6f;     // > eps + rsqrt.approx error + quantisation error
 
@@ -176,7 +188,7 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
                                 bool needs_reduce, bool all_finite_known) {
   const int nX = b.x1 - b.x0 + 1, nZ = b.z1 - b.z0 + 1;
   const int nV = nX * nZ;
-  const uint32_t magicX = (nX > 1) ? (0xFFFFFFFFu / (uint32_t)nX + 1u) : 0u;
+  const uint32_t magicX = magic_for(nX);
   const float* base = f.H + (size_t)b.z0 * f.pitch + b.x0;
 
   // (1)+(2) zone reductions and early outs -- normally already done by stage A
@@ -190,7 +202,7 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
 
   // (3) vertex-in-box test of every colliding vertex of a kept triangle (heightfield.cpp:1306-1441)
   const int nCX = nX - 1, nCZ = nZ - 1, nC = nCX * nCZ;
-  const uint32_t magicC = (nCX > 1) ? (0xFFFFFFFFu / (uint32_t)nCX + 1u) : 0u;
+  const uint32_t magicC = magic_for(nCX);
   if (allFinite) {
     // every colliding vertex belongs to some kept triangle (all finite, >= 1 cell)
     for (int t0 = 0; t0 < nV; t0 += 64) {
@@ -312,44 +324,65 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
 
     // (5) is any live candidate epsilon-mergeable with an EARLIER kept triangle? (greedy grouping,
     // heightfield.cpp:1511-1556: a triangle is absorbed only by an earlier base that matches it.)
+    int max_live = max(lidx[0], lidx[1]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) max_live = max(max_live, __shfl_xor_sync(kFull, max_live, o));
     bool merge = false;
     for (int t0 = 0; t0 < nC; t0 += 32) {
       const int t = t0 + lane;
+      bool flag[2] = {false, false};
+      float fpl[2][4];
+      int fidx[2] = {0, 0};
       if (t < nC) {
         const int czi = (nCX > 1) ? (int)__umulhi((uint32_t)t, magicC) : t;
         const int cxi = t - czi * nCX;
-        const int cx = b.x0 + cxi, cz = b.z0 + czi;
-        float hA, hB, hC, hD;
-        load_cell(f, cx, cz, hA, hB, hC, hD);
-        const bool fA = finitef(hA), fB = finitef(hB), fC = finitef(hC), fD = finitef(hD);
-        const bool cA = fA && hA > b.minB, cB = fB && hB > b.minB, cC = fC && hC > b.minB, cD = fD && hD > b.minB;
-        const bool keep[2] = {(cA || cB || cC) && (fA && fB && fC), (cB || cC || cD) && (fB && fC && fD)};
-        if (keep[0] || keep[1]) {
-          const float xA = cx * f.sW, xB = (cx + 1) * f.sW, zA = cz * f.sD, zC = (cz + 1) * f.sD;
-          const int cell_idx = (cxi * nCZ + czi) * 2;
+        const int cell_idx = (cxi * nCZ + czi) * 2;
+        if (cell_idx < max_live) {   // only triangles emitted before the last live candidate can absorb one
+          const int cx = b.x0 + cxi, cz = b.z0 + czi;
+          float hA, hB, hC, hD;
+          load_cell(f, cx, cz, hA, hB, hC, hD);
+          const bool fA = finitef(hA), fB = finitef(hB), fC = finitef(hC), fD = finitef(hD);
+          const bool cA = fA && hA > b.minB, cB = fB && hB > b.minB, cC = fC && hC > b.minB, cD = fD && hD > b.minB;
+          const bool keep[2] = {(cA || cB || cC) && (fA && fB && fC), (cB || cC || cD) && (fB && fC && fD)};
+          if (keep[0] || keep[1]) {
+            const float xA = cx * f.sW, xB = (cx + 1) * f.sW, zA = cz * f.sD, zC = (cz + 1) * f.sD;
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            if (!keep[u]) continue;
-            float c0, c1, c2;   // value-identical to tri_plane's cross product (zero terms dropped)
-            if (u == 0) {   // Up (A,B,C): E1 = C-A = (0, hC-hA, zC-zA), E2 = B-A = (xB-xA, hB-hA, 0); c = E1 x E2
-              const float e1y = hC - hA, e1z = zC - zA, e2x = xB - xA, e2y = hB - hA;
-              c0 = -(e1z * e2y); c1 = e1z * e2x; c2 = -(e1y * e2x);
-            } else {        // Down (D,B,C): E1 = C-D = (xA-xB, hC-hD, 0), E2 = B-D = (0, hB-hD, zA-zC); c = E2 x E1
-              const float e1x = xA - xB, e1y = hC - hD, e2y = hB - hD, e2z = zA - zC;
-              c0 = -(e2z * e1y); c1 = e2z * e1x; c2 = -(e2y * e1x);
-            }
-            const float r = rsqrtf(c0 * c0 + c1 * c1 + c2 * c2);
-            const int kx = (int)floorf((c0 * r + 1.0f) * kKeyScale), kz = (int)floorf((c2 * r + 1.0f) * kKeyScale);
-            const uint32_t hsh = bloom_hash(kx, kz);
-            if (ws.bloom[hsh >> 5] & (1u << (hsh & 31))) {
-              float pl[4];
-              cell_plane(f, u == 0, cx, cz, hA, hB, hC, hD, pl);
-              const int idx = cell_idx + u;
-              for (int s = 0; s < nLive; ++s) {
-                if (ws.cidx[s] > idx && plane_match(pl, ws.cpl[s])) merge = true;
+            for (int u = 0; u < 2; ++u) {
+              if (!keep[u] || cell_idx + u >= max_live) continue;
+              float c0, c1, c2;   // value-identical to tri_plane's cross product (zero terms dropped)
+              if (u == 0) {   // Up (A,B,C): E1 = C-A = (0, hC-hA, zC-zA), E2 = B-A = (xB-xA, hB-hA, 0); c = E1 x E2
+                const float e1y = hC - hA, e1z = zC - zA, e2x = xB - xA, e2y = hB - hA;
+                c0 = -(e1z * e2y); c1 = e1z * e2x; c2 = -(e1y * e2x);
+              } else {        // Down (D,B,C): E1 = C-D = (xA-xB, hC-hD, 0), E2 = B-D = (0, hB-hD, zA-zC); c = E2 x E1
+                const float e1x = xA - xB, e1y = hC - hD, e2y = hB - hD, e2z = zA - zC;
+                c0 = -(e2z * e1y); c1 = e2z * e1x; c2 = -(e2y * e1x);
+              }
+              const float r = rsqrtf(c0 * c0 + c1 * c1 + c2 * c2);
+              const int kx = (int)floorf((c0 * r + 1.0f) * kKeyScale), kz = (int)floorf((c2 * r + 1.0f) * kKeyScale);
+              const uint32_t hsh = bloom_hash(kx, kz);
+              if (ws.bloom[hsh >> 5] & (1u << (hsh & 31))) {
+                flag[u] = true;
+                fidx[u] = cell_idx + u;
+                cell_plane(f, u == 0, cx, cz, hA, hB, hC, hD, fpl[u]);
               }
             }
           }
+        }
+      }
+      // flagged triangles are compared warp-cooperatively: one flagged plane is broadcast, lane s (and s + 32)
+      // checks it against live candidate s
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        unsigned fm = __ballot_sync(kFull, flag[u]);
+        while (fm) {
+          const int src = __ffs(fm) - 1;
+          fm &= fm - 1;
+          float pl[4];
+          pl[0] = __shfl_sync(kFull, fpl[u][0], src); pl[1] = __shfl_sync(kFull, fpl[u][1], src);
+          pl[2] = __shfl_sync(kFull, fpl[u][2], src); pl[3] = __shfl_sync(kFull, fpl[u][3], src);
+          const int idx = __shfl_sync(kFull, fidx[u], src);
+          for (int sidx = lane; sidx < nLive; sidx += 32)
+            if (ws.cidx[sidx] > idx && plane_match(pl, ws.cpl[sidx])) merge = true;
         }
       }
       if (__any_sync(kFull, merge)) return R_DEFER;
@@ -515,11 +548,14 @@ box_items_warp_kernel(const Checker c, const Work w, const BoxRec* __restrict__ 
   const int lane = threadIdx.x & 31;
   WarpScratch& ws = ws_all[threadIdx.x >> 5];
   const uint32_t total = *rec_count;
+  constexpr uint32_t kChunk = 4;   // records claimed per atomic
   for (;;) {
-    uint32_t ri = 0;
-    if (lane == 0) ri = atomicAdd(work_counter, 1u);
-    ri = __shfl_sync(kFull, ri, 0);
-    if (ri >= total) break;
+    uint32_t r0 = 0;
+    if (lane == 0) r0 = atomicAdd(work_counter, kChunk);
+    r0 = __shfl_sync(kFull, r0, 0);
+    if (r0 >= total) break;
+    const uint32_t r1 = min(r0 + kChunk, total);
+    for (uint32_t ri = r0; ri < r1; ++ri) {
     // load the 20-word record with lanes 0..19 and broadcast
     const uint32_t* rp = reinterpret_cast<const uint32_t*>(recs + ri);
     const uint32_t word = (lane < 20) ? __ldg(rp + lane) : 0u;
@@ -530,7 +566,7 @@ box_items_warp_kernel(const Checker c, const Work w, const BoxRec* __restrict__ 
       for (int i = 0; i < 20; ++i) dst[i] = __shfl_sync(kFull, word, i);
     }
     const uint32_t slot = item_slot(w, r.item);
-    {   // the item already failed on another box: nothing can change it (perf only; the result is order-free)
+    if (w.edge_mode) {   // the edge already failed on another state/box: nothing can change it (perf only; order-free)
       int dead = 0;
       if (lane == 0) dead = (*(volatile uint8_t*)(w.valid + slot) == 0);
       if (__shfl_sync(kFull, dead, 0)) continue;
@@ -548,6 +584,7 @@ box_items_warp_kernel(const Checker c, const Work w, const BoxRec* __restrict__ 
     if (lane == 0) {
       if (res == R_DEFER) defer_list[atomicAdd(defer_count, 1u)] = ri;
       else if ((!foot && res == R_HIT) || (foot && res == R_FREE)) w.valid[slot] = 0;
+    }
     }
   }
 }
