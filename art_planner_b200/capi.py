@@ -55,6 +55,8 @@ def load():
     lib.artp_has_map.argtypes = [vp]
     lib.artp_check_poses.argtypes = [vp, vp, sz, vp]
     lib.artp_check_poses_device.argtypes = [vp, vp, sz, vp, vp]
+    lib.artp_check_poses_f32.argtypes = [vp, vp, sz, vp]
+    lib.artp_check_poses_f32_device.argtypes = [vp, vp, sz, vp, vp]
     lib.artp_check_motions.argtypes = [vp, vp, vp, sz, i32, vp]
     lib.artp_check_motions_device.argtypes = [vp, vp, vp, sz, i32, vp, vp]
     lib.artp_path_length_cost.argtypes = [vp, vp, vp, sz, vp]

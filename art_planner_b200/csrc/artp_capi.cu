@@ -217,32 +217,66 @@ int ensure_stage(Handle* h, size_t bytes) {
   return ARTP_OK;
 }
 
-// Launch stages A, B, C for a prepared Work on stream s (in rounds of kChunkItems work items).
-int run_items(Handle* h, artp::Work w, cudaStream_t s) {
+// Optional host feed of a call: the states are copied H2D in slices on the copy stream while the kernels of the
+// previous slice run on the compute stream.
+struct HostFeed {
+  const char* host;        // host states
+  char* dev;               // device destination (same layout)
+  size_t bytes_per_item;
+  size_t slice_items;
+};
+
+// Launch the pipeline for a prepared Work (items 0 .. w.n_items = the whole call) on stream s, in rounds of
+// kChunkItems work items (bounds the box queue). Within a round the classify (A) and warp (B) stages run slice by slice
+// -- the record queue and B's claim counter simply keep growing -- and the plane-grouping stage (C) runs ONCE over all
+// boxes deferred in the round (its sequential greedy has a fixed latency of tens of microseconds per launch).
+int run_items(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed = nullptr) {
   const size_t n_total = w.n_items;
   int rc = ensure_queues(h, n_total, s);
   if (rc) return rc;
   uint32_t launches = 0;
+  size_t ev_i = 0;
   for (size_t base = 0; base < n_total; base += kChunkItems) {
     const size_t end = std::min(n_total, base + kChunkItems);
+    const bool last_round = end == n_total;
+    CU_TRY(h, cudaMemsetAsync(h->d_ctr, 0, 4 * sizeof(uint32_t), s));
+    const size_t slice = (feed && feed->slice_items < end - base) ? feed->slice_items : (end - base);
+    for (size_t lo = base; lo < end; lo += slice) {
+      const size_t hi = std::min(end, lo + slice);
+      const bool last = last_round && hi == end;
+      if (feed) {
+        const bool piped = slice < end - base;
+        cudaStream_t cs = piped ? h->copy_stream : s;
+        CU_TRY(h, cudaMemcpyAsync(feed->dev + lo * feed->bytes_per_item, feed->host + lo * feed->bytes_per_item,
+                                  (hi - lo) * feed->bytes_per_item, cudaMemcpyHostToDevice, cs));
+        if (piped) {
+          cudaEvent_t ev = h->copy_ev[ev_i++ % kCopyEvents];
+          CU_TRY(h, cudaEventRecord(ev, h->copy_stream));
+          CU_TRY(h, cudaStreamWaitEvent(s, ev, 0));
+        }
+      }
+      w.item_base = (uint32_t)lo;
+      w.n_items = (uint32_t)hi;
+      // B's claim counter restarts exactly at the records this slice's A will append (the previous B overshoots it)
+      if (lo != base) CU_TRY(h, cudaMemcpyAsync(h->d_ctr, h->d_ctr + 3, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+      if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[0], s));
+      artp::classify_items_kernel<<<(unsigned)((hi - lo + 127) / 128), 128, 0, s>>>(h->chk, w, h->d_recs, h->d_ctr + 3,
+                                                                                      h->mode == 1);
+      CU_TRY(h, cudaGetLastError());
+      if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[1], s));
+      artp::box_items_warp_kernel<<<h->k1_grid, artp::kWarpsPerCta * 32, 0, s>>>(h->chk, w, h->d_recs, h->d_ctr + 3, h->d_ctr,
+                                                                                  h->d_ctr + 1, h->d_defer, h->mode == 1);
+      CU_TRY(h, cudaGetLastError());
+      if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[2], s));
+      launches += 2;
+    }
     w.item_base = (uint32_t)base;
     w.n_items = (uint32_t)end;
-    const bool last = end == n_total;
-    CU_TRY(h, cudaMemsetAsync(h->d_ctr, 0, 4 * sizeof(uint32_t), s));
-    if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[0], s));
-    artp::classify_items_kernel<<<(unsigned)((end - base + 127) / 128), 128, 0, s>>>(h->chk, w, h->d_recs, h->d_ctr + 3,
-                                                                                      h->mode == 1);
-    CU_TRY(h, cudaGetLastError());
-    if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[1], s));
-    artp::box_items_warp_kernel<<<h->k1_grid, artp::kWarpsPerCta * 32, 0, s>>>(h->chk, w, h->d_recs, h->d_ctr + 3, h->d_ctr,
-                                                                                h->d_ctr + 1, h->d_defer, h->mode == 1);
-    CU_TRY(h, cudaGetLastError());
-    if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[2], s));
     artp::box_items_block_kernel<<<h->k2_grid, 256, h->k2_smem, s>>>(h->chk, w, h->d_recs, h->d_ctr + 1, h->d_defer,
                                                                       h->k2_tcap, h->d_ctr + 2);
     CU_TRY(h, cudaGetLastError());
-    if (h->timing && last) { CU_TRY(h, cudaEventRecord(h->ev[3], s)); h->ev_valid = true; }
-    launches += 3;
+    if (h->timing && last_round) { CU_TRY(h, cudaEventRecord(h->ev[3], s)); h->ev_valid = true; }
+    launches += 1;
   }
   h->stats.kernel_launches += launches;
   h->stats.last_launches = launches;
@@ -480,7 +514,7 @@ int artp_check_poses_device(artp_handle* hh, const double* d_states, size_t n, u
   if (!d_states || !d_valid) { h->err = "null buffer"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
   artp::Work w;
-  w.s1 = nullptr; w.s2 = d_states; w.valid = d_valid; w.item_base = 0; w.n_items = (uint32_t)n; w.steps = 0; w.edge_mode = 0;
+  w.s1 = nullptr; w.s2 = d_states; w.s2f = nullptr; w.valid = d_valid; w.item_base = 0; w.n_items = (uint32_t)n; w.steps = 0; w.edge_mode = 0;
   rc = run_items(h, w, (cudaStream_t)stream);
   if (rc) return rc;
   h->stats.poses_checked += n;
@@ -501,29 +535,62 @@ int artp_check_poses(artp_handle* hh, const double* states, size_t n, uint8_t* v
   if (rc) return rc;
   double* d_states = (double*)h->d_stage;
   uint8_t* d_valid = (uint8_t*)h->d_stage + out_off;
-  // Pipeline: the H2D copy of slice i+1 (copy stream) overlaps the kernels of slice i (compute stream); the
-  // 1 B/pose results go back on the compute stream. Small batches take the single-slice path.
-  const size_t slice = 128 * 1024;
-  const size_t n_slices = (n + slice - 1) / slice;
-  for (size_t i = 0; i < n_slices; ++i) {
-    const size_t lo = i * slice, cnt = std::min(slice, n - lo);
-    cudaEvent_t ev = h->copy_ev[i % kCopyEvents];
-    CU_TRY(h, cudaMemcpyAsync(d_states + 7 * lo, states + 7 * lo, cnt * 7 * sizeof(double), cudaMemcpyHostToDevice,
-                              n_slices > 1 ? h->copy_stream : h->stream));
-    if (n_slices > 1) {
-      CU_TRY(h, cudaEventRecord(ev, h->copy_stream));
-      CU_TRY(h, cudaStreamWaitEvent(h->stream, ev, 0));
-    }
-    artp::Work w;
-    w.s1 = nullptr; w.s2 = d_states + 7 * lo; w.valid = d_valid + lo; w.item_base = 0; w.n_items = (uint32_t)cnt;
-    w.steps = 0; w.edge_mode = 0;
-    rc = run_items(h, w, h->stream);
-    if (rc) return rc;
-    CU_TRY(h, cudaMemcpyAsync(valid + lo, d_valid + lo, cnt, cudaMemcpyDeviceToHost, h->stream));
-  }
+  // the H2D copy of slice i+1 (copy stream) overlaps the kernels of slice i (compute stream); results return once
+  artp::Work w;
+  w.s1 = nullptr; w.s2 = d_states; w.s2f = nullptr; w.valid = d_valid; w.item_base = 0; w.n_items = (uint32_t)n;
+  w.steps = 0; w.edge_mode = 0;
+  HostFeed feed{(const char*)states, (char*)d_states, 7 * sizeof(double), 128 * 1024};
+  rc = run_items(h, w, h->stream, &feed);
+  if (rc) return rc;
+  CU_TRY(h, cudaMemcpyAsync(valid, d_valid, n, cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   h->stats.poses_checked += n;
-  h->stats.last_launches = (uint32_t)(3 * n_slices);
+  return ARTP_OK;
+}
+
+// float32 states: the caller has already applied the double -> float cast that Pose3FromSE3 (utils.h:25-38) performs
+// first, so the result is identical to the double entry point while the H2D stream is 28 B/pose instead of 56.
+int artp_check_poses_f32_device(artp_handle* hh, const float* d_states, size_t n, uint8_t* d_valid, void* stream) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  int rc = check_common(h, n);
+  if (rc) return rc;
+  if (n == 0) return ARTP_OK;
+  if (!d_states || !d_valid) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  artp::Work w;
+  w.s1 = nullptr; w.s2 = nullptr; w.s2f = d_states; w.valid = d_valid; w.item_base = 0; w.n_items = (uint32_t)n; w.steps = 0;
+  w.edge_mode = 0;
+  rc = run_items(h, w, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->stats.poses_checked += n;
+  return ARTP_OK;
+}
+
+int artp_check_poses_f32(artp_handle* hh, const float* states, size_t n, uint8_t* valid) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  int rc = check_common(h, n);
+  if (rc) return rc;
+  if (n == 0) return ARTP_OK;
+  if (!states || !valid) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  const size_t in_bytes = n * 7 * sizeof(float), out_off = (in_bytes + 255) & ~(size_t)255;
+  rc = ensure_stage(h, out_off + n);
+  if (rc) return rc;
+  float* d_states = (float*)h->d_stage;
+  uint8_t* d_valid = (uint8_t*)h->d_stage + out_off;
+  artp::Work w;
+  w.s1 = nullptr; w.s2 = nullptr; w.s2f = d_states; w.valid = d_valid; w.item_base = 0; w.n_items = (uint32_t)n;
+  w.steps = 0; w.edge_mode = 0;
+  HostFeed feed{(const char*)states, (char*)d_states, 7 * sizeof(float), 256 * 1024};
+  rc = run_items(h, w, h->stream, &feed);
+  if (rc) return rc;
+  CU_TRY(h, cudaMemcpyAsync(valid, d_valid, n, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->stats.poses_checked += n;
   return ARTP_OK;
 }
 
@@ -543,7 +610,7 @@ int artp_check_motions_device(artp_handle* hh, const double* d_s1, const double*
   fill_u8_kernel<<<std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 8), 256, 0, s>>>(d_valid, n, 1);
   CU_TRY(h, cudaGetLastError());
   artp::Work w;
-  w.s1 = d_s1; w.s2 = d_s2; w.valid = d_valid; w.item_base = 0; w.n_items = (uint32_t)items; w.steps = n_steps; w.edge_mode = 1;
+  w.s1 = d_s1; w.s2 = d_s2; w.s2f = nullptr; w.valid = d_valid; w.item_base = 0; w.n_items = (uint32_t)items; w.steps = n_steps; w.edge_mode = 1;
   rc = run_items(h, w, s);
   if (rc) return rc;
   h->stats.kernel_launches += 1;

@@ -40,6 +40,7 @@ struct WarpScratch {
 struct Work {
   const double* s1;     // EDGE: start states; POSE: unused
   const double* s2;     // EDGE: end states;   POSE: the states
+  const float* s2f;     // POSE only: states already cast to float (exactly what Pose3FromSE3 does first); else null
   uint8_t* valid;       // per pose / per edge
   uint32_t item_base;   // first work item of this launch (chunked calls)
   uint32_t n_items;     // one past the last work item of this launch
@@ -87,8 +88,13 @@ __device__ __forceinline__ void se3_interpolate(const double* a, const double* b
 
 __device__ __forceinline__ void load_item_state(const Work& w, uint32_t item, double s[7]) {
   if (!w.edge_mode) {
+    if (w.s2f) {
 #pragma unroll
-    for (int k = 0; k < 7; ++k) s[k] = w.s2[(size_t)item * 7 + k];
+      for (int k = 0; k < 7; ++k) s[k] = (double)w.s2f[(size_t)item * 7 + k];   // exact; cast back to float downstream
+    } else {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) s[k] = w.s2[(size_t)item * 7 + k];
+    }
     return;
   }
   const uint32_t per = (uint32_t)w.steps + 1u;

@@ -169,6 +169,7 @@ def main():
     d_poses = torch.from_numpy(poses).cuda()
     d_valid = torch.empty(n, dtype=torch.uint8, device="cuda")
     h_poses = torch.from_numpy(poses).pin_memory()
+    h_poses32 = torch.from_numpy(poses.astype(np.float32)).pin_memory()   # the cast Pose3FromSE3 does first, done by the adapter
     h_valid = torch.empty(n, dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
     gather_cnt = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(world)]
@@ -182,7 +183,10 @@ def main():
             idx, cnt = chk.compactValid(d_valid, base=rank * n)
             sharding.gather_valid_indices(idx, cnt, world, out_idx=gather_idx, out_cnt=gather_cnt)
 
-    def step_e2e():
+    def step_e2e():      # what INTEGRATION.md's adapter calls: float32 states (exact), pinned host buffers
+        chk.isValidHostPtr(h_poses32.data_ptr(), n, h_valid.data_ptr(), f32=True)
+
+    def step_e2e_f64():  # the same through the double entry point (56 B/pose on the wire)
         chk.isValidHostPtr(h_poses.data_ptr(), n, h_valid.data_ptr())
 
     for _ in range(max(args.warmup, 3)):
@@ -227,6 +231,12 @@ def main():
         step_e2e()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    step_e2e_f64(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e_f64()
+    torch.cuda.synchronize()
+    e2e64_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- secondary workloads of the same hot path (BASELINE configs[2] and [3]); N = 1 only, short -------------
@@ -330,8 +340,9 @@ def main():
             "config": {"workload": WORKLOAD, "poses_per_gpu": n, "map": f"{MAP_N}x{MAP_N}@{MAP_RES}",
                        "map_seed": MAP_SEED, "pose_seed": POSE_SEED, "l2": "flushed between timed steps (256 MiB write)",
                        "parallelism": f"pose shards x{world}, replicated map" + (", NCCL all-gather of valid indices" if world > 1 else "")},
-            "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": n * 56, "d2h_bytes_per_step": n,
-                    "ms_per_step": e2e_ms / e2e_steps},
+            "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": n,
+                    "ms_per_step": e2e_ms / e2e_steps, "api": "artp_check_poses_f32 (states cast to float by the adapter, exact)",
+                    "f64_api_value": world * n * e2e_steps / e2e64_s, "f64_api_h2d_bytes_per_step": n * 56},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "box_items_warp_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

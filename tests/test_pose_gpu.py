@@ -63,11 +63,17 @@ def test_device_buffers_and_host_buffers_agree(maps, checkers):
     m = maps("fbm_rough")
     chk = checkers("yaml")
     set_map(chk, m)
-    poses = synth.make_terrain_poses(m, 30000, seed=99)
+    poses = synth.make_terrain_poses(m, 300000, seed=99)     # > one H2D slice: exercises the copy/compute pipeline
     host = chk.isValidBatch(poses)
     dev = chk.isValidBatch(torch.from_numpy(poses).cuda())
     torch.cuda.synchronize()
     assert np.array_equal(host, dev.cpu().numpy())
+    # float32 states (the cast Pose3FromSE3 performs first, done by the caller): identical flags
+    p32 = poses.astype(np.float32)
+    assert np.array_equal(chk.isValidBatch(p32), host)
+    d32 = chk.isValidBatch(torch.from_numpy(p32).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(d32.cpu().numpy(), host)
 
 
 def test_single_state_latency_path_and_edge_cases(maps, port_lib, checkers):
