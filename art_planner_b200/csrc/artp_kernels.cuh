@@ -252,6 +252,7 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
   // (4) plane stage (heightfield.cpp:1474-1617). A plane contact point is always a box corner (up to a few
   // ulps), so only triangles in the cells under the 8 corners (+- cell_margin) can report one.
   {
+    __syncwarp();   // the previous box's reads of this warp's scratch are done (no WAR across boxes)
     for (int i = lane; i < kBloomWords; i += 32) ws.bloom[i] = 0u;
     __syncwarp();
     const int corner = lane >> 2, sub = lane & 3;

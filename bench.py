@@ -86,8 +86,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_inputs(rank: int, n: int):
+def make_inputs(rank: int, n: int, workload: str = "c2", world: int = 1):
+    """c2: BASELINE configs[1] (1000x1000 map; rank r takes samples [r*n, (r+1)*n) of the seeded stream).
+    c5: BASELINE configs[4] (4000x4000 map; rank r's samples lie in its spatial slab along x, seed 7)."""
     from art_planner_b200 import synth
+    if workload == "c5":
+        m = synth.make_fbm_map(4000, 4000, MAP_RES, seed=MAP_SEED, amp=0.6, n_walls=96)
+        k = np.arange(rank * n, (rank + 1) * n)
+        lx, ly = m.length
+        slab = lx * 0.999 / world
+        x = m.cx - 0.4995 * lx + (rank + synth.hash_uniform(7, 1, k)) * slab
+        y = m.cy + (synth.hash_uniform(7, 2, k) - 0.5) * ly * 0.999
+        return m, synth.make_terrain_poses(m, n, seed=7, start=rank * n, xy=(x, y))
     m = synth.make_fbm_map(MAP_N, MAP_N, MAP_RES, seed=MAP_SEED, amp=0.6)
     poses = synth.make_terrain_poses(m, n, seed=POSE_SEED, start=rank * n)
     return m, poses
@@ -101,25 +111,40 @@ def cpu_oracle(params):
     return orc.Oracle(params, kind), kind
 
 
+def best_thread_count(o, poses, cores, big_map=False):
+    """The compiled reference stops scaling well before all hardware threads on this host (memory-bound ODE worlds):
+    pick the thread count with the highest throughput on a short probe, so the baseline is the reference at its best."""
+    cands = sorted({c for c in (8, 16, 32, 64, 128, cores) if c <= cores and (not big_map or c <= 16)})
+    best, best_rate = cands[0], 0.0
+    probe = poses[:60_000]
+    for c in cands:
+        o.check_poses_mt(poses[:c * 64], c)          # builds the per-thread ODE worlds (one-time per map, untimed)
+        t0 = time.perf_counter(); o.check_poses_mt(probe, c); dt = time.perf_counter() - t0
+        if len(probe) / dt > best_rate:
+            best, best_rate = c, len(probe) / dt
+    return best
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path on all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from art_planner_b200 import synth
-    cores = os.cpu_count() or 1
     sample_n = 200_000
-    m, poses = make_inputs(0, sample_n)
+    m, poses = make_inputs(0, sample_n, getattr(args, "workload", "c2"), 1)
     o, kind = cpu_oracle(synth.PARAMS_YAML)
     o.set_map(m)
+    cores = best_thread_count(o, poses, os.cpu_count() or 1, m.rows * m.cols > 4_000_000)
     for _ in range(max(args.warmup, 1)):
-        o.check_poses_mt(poses[:20000], cores)      # also builds the per-thread ODE worlds (one-time per map)
+        o.check_poses_mt(poses[:20000], cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         o.check_poses_mt(poses, cores)
     dt = time.perf_counter() - t0
     value = sample_n * args.steps / dt
-    sample = f"first {sample_n} poses of the 1M-pose workload per step, {cores} threads, one ODE world per thread"
+    sample = (f"first {sample_n} poses of the 1M-pose workload per step, {cores} threads (best of a probe over "
+              f"8..{os.cpu_count()} threads), one ODE world per thread")
     print(json.dumps({
         "impl": "reference", "metric": "pose-validity checks/s", "value": value, "unit": "poses/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -137,6 +162,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2 = BASELINE configs[1] (default, the metric's config); c5 = configs[4], 4000x4000 map, spatial slabs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -160,7 +187,7 @@ def main():
         dist.barrier()
 
     n = POSES_PER_GPU
-    m, poses = make_inputs(rank, n)
+    m, poses = make_inputs(rank, n, args.workload, world)
     chk = apb.StateValidityChecker(synth.PARAMS_YAML, device=local)
     chk.setMap(m)
     chk.updateHeightField()
@@ -241,7 +268,7 @@ def main():
 
     # ---- secondary workloads of the same hot path (BASELINE configs[2] and [3]); N = 1 only, short -------------
     secondary = None
-    if world == 1:
+    if world == 1 and args.workload == "c2":
         secondary = {}
         s1, s2 = synth.make_edges(m, 100_000, seed=4)
         d1, d2 = torch.from_numpy(s1).cuda(), torch.from_numpy(s2).cuda()
@@ -306,7 +333,8 @@ def main():
         # ---- CPU baseline + algorithmic bytes from the oracle on a bounded sample ---------------
         o, kind = cpu_oracle(synth.PARAMS_YAML)
         o.set_map(m)
-        cores = os.cpu_count() or 1
+        # one ODE world + two layer copies per thread: the probe bounds host memory on big maps
+        cores = best_thread_count(o, poses, os.cpu_count() or 1, m.rows * m.cols > 4_000_000)
         n1 = 20_000
         t0 = time.perf_counter(); v1 = o.check_poses(poses[:n1]); t_single = time.perf_counter() - t0
         n_mt = 400_000
@@ -337,7 +365,9 @@ def main():
             "metric": "pose-validity checks/s", "value": value, "unit": "poses/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "poses_per_gpu": n, "map": f"{MAP_N}x{MAP_N}@{MAP_RES}",
+            "config": {"workload": WORKLOAD if args.workload == "c2" else
+                       "configs[4]: fBm 4000x4000@0.04m map, 1M samples per GPU inside the GPU's spatial slab, yaml robot geometry",
+                       "poses_per_gpu": n, "map": f"{m.rows}x{m.cols}@{MAP_RES}",
                        "map_seed": MAP_SEED, "pose_seed": POSE_SEED, "l2": "flushed between timed steps (256 MiB write)",
                        "parallelism": f"pose shards x{world}, replicated map" + (", NCCL all-gather of valid indices" if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": n,
@@ -351,7 +381,7 @@ def main():
                          "achieved_dominant_kernel_alone": achieved_dom,
                          "queued_boxes": int(queued), "deferred_boxes": int(deferred)},
             "cpu_baseline": {"value": n_mt / t_mt, "unit": "poses/s", "cores": cores, "kind": kind,
-                             "sample": f"first {n_mt} poses of the workload, {cores} threads; single-thread on first {n1}",
+                             "sample": f"first {n_mt} poses of the workload, {cores} threads (best of a probe over 8..{os.cpu_count()}); single-thread on first {n1}",
                              "single_thread_value": n1 / t_single, "mask_equals_gpu": parity_ok},
             "clocks": clocks, "wall_s_timed_region": wall, "secondary": secondary,
         }
