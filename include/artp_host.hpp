@@ -1,0 +1,345 @@
+// include/artp_host.hpp -- C++ host side of the B200-native art_planner hot path, above the C ABI (artp.h).
+//
+// Header-only mirror of the reference's plugin classes for this path -- same class and method names, argument meaning
+// and error behaviour -- so that art_planner's planners and facade keep calling what they call today:
+//   art_planner::StateValidityChecker   include/art_planner/validity_checker/validity_checker.h:21-39
+//   ompl::base::MotionValidator         (OMPL DiscreteMotionValidator; call sites prm_motion_cost.cpp:652,
+//                                        lazy_prm_star_min_update.cpp:725)
+//   art_planner::PathLengthObjective    include/art_planner/objectives/path_length_objective.h, .cpp:26-70
+//   art_planner::MotionCostObjective    include/art_planner/objectives/motion_cost_objective.h:19-78, .cpp:28-95
+// OMPL / Eigen / grid_map are not available in this build image, so the classes are written against three tiny
+// stand-ins (State = the seven doubles utils.h:25-38 reads from an SE3StateSpace::StateType, Map = two column-major
+// float layers + geometry as grid_map stores them, EdgeMatrix = row-major float matrix). With -DARTP_WITH_OMPL the
+// OMPL adapters at the bottom derive from the real ompl::base classes and forward to the same objects.
+// There is no CPU fallback: construction throws std::runtime_error if the CUDA library cannot create a handle.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <functional>
+#include <limits>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "artp.h"
+
+namespace artp_host {
+
+// art_planner::Params, the fields this path reads, with the reference's nesting (params.h:14-123).
+struct Params {
+  struct {
+    bool unknown_space_untraversable{true};
+    struct {
+      float max_query_edge_length{0.5f};
+      float risk_threshold{0.1f};
+      struct { float energy{0.0f}; float time{1.0f}; float risk{5.0f}; } cost_weights;
+    } prm_motion_cost;
+  } planner;
+  struct {
+    struct { bool use_directional_cost{false}; double max_lon_vel{0.5}; double max_lat_vel{0.1}; double max_ang_vel{0.5}; } custom_path_length;
+  } objectives;
+  struct {
+    struct { double length{1.05}; double width{0.55}; double height{0.2}; struct { double x{0}, y{0}, z{0}; } offset; } torso;
+    struct { struct { double x{0.362}, y{0.225}, z{-0.525}; } offset; struct { double x{0.25}, y{0.1}, z{0.15}; } reach; } feet;
+  } robot;
+  int device{0};   // not in the reference: CUDA device ordinal
+};
+using ParamsConstPtr = std::shared_ptr<const Params>;
+
+// The SE3StateSpace::StateType fields the reference reads (utils.h:25-38): position + quaternion, doubles.
+struct State { double x{0}, y{0}, z{0}, qx{0}, qy{0}, qz{0}, qw{1}; };
+
+// Stand-in for art_planner::Map / grid_map::GridMap: layers are column-major rows x cols (index (i,j) at i + j*rows).
+struct Map {
+  int rows{0}, cols{0};
+  double resolution{0}, position_x{0}, position_y{0};
+  std::vector<float> elevation, elevation_masked;
+};
+
+inline artp_params toArtp(const Params& p) {
+  artp_params a{};
+  a.torso_length = p.robot.torso.length; a.torso_width = p.robot.torso.width; a.torso_height = p.robot.torso.height;
+  a.torso_off_x = p.robot.torso.offset.x; a.torso_off_y = p.robot.torso.offset.y; a.torso_off_z = p.robot.torso.offset.z;
+  a.feet_off_x = p.robot.feet.offset.x; a.feet_off_y = p.robot.feet.offset.y; a.feet_off_z = p.robot.feet.offset.z;
+  a.reach_x = p.robot.feet.reach.x; a.reach_y = p.robot.feet.reach.y; a.reach_z = p.robot.feet.reach.z;
+  a.unknown_space_untraversable = p.planner.unknown_space_untraversable ? 1 : 0;
+  a.use_directional_cost = p.objectives.custom_path_length.use_directional_cost ? 1 : 0;
+  a.max_lon_vel = p.objectives.custom_path_length.max_lon_vel;
+  a.max_lat_vel = p.objectives.custom_path_length.max_lat_vel;
+  a.max_ang_vel = p.objectives.custom_path_length.max_ang_vel;
+  a.cost_w_energy = p.planner.prm_motion_cost.cost_weights.energy;
+  a.cost_w_time = p.planner.prm_motion_cost.cost_weights.time;
+  a.cost_w_risk = p.planner.prm_motion_cost.cost_weights.risk;
+  a.risk_threshold = p.planner.prm_motion_cost.risk_threshold;
+  a.device = p.device;
+  return a;
+}
+
+// Owns the artp_handle; shared by the plugin objects below (the reference shares its checker the same way,
+// path_length_objective.cpp:20: checker_(si->getStateValidityChecker())).
+class Handle {
+ public:
+  explicit Handle(const ParamsConstPtr& params) : params_(params) {
+    const artp_params a = toArtp(*params);
+    if (artp_create(&a, &h_) != ARTP_OK) throw std::runtime_error(std::string("artp_create: ") + artp_last_error(nullptr));
+  }
+  ~Handle() { artp_destroy(h_); }
+  Handle(const Handle&) = delete;
+  Handle& operator=(const Handle&) = delete;
+  artp_handle* get() const { return h_; }
+  const Params& params() const { return *params_; }
+  void check(int rc, const char* what) const {
+    if (rc != ARTP_OK) throw std::runtime_error(std::string(what) + ": " + artp_last_error(h_));
+  }
+ private:
+  ParamsConstPtr params_;
+  artp_handle* h_{nullptr};
+};
+using HandlePtr = std::shared_ptr<Handle>;
+
+// art_planner::StateValidityChecker (validity_checker.cpp:9-45).
+class StateValidityChecker {
+ public:
+  explicit StateValidityChecker(const ParamsConstPtr& params) : handle_(std::make_shared<Handle>(params)) {}
+  explicit StateValidityChecker(const HandlePtr& handle) : handle_(handle) {}
+
+  void setMap(const std::shared_ptr<Map>& map) { map_ = map; }                 // validity_checker.cpp:20-23
+
+  void updateHeightField() {                                                    // validity_checker.cpp:27-31
+    if (!map_) throw std::runtime_error("updateHeightField: no map");
+    handle_->check(artp_set_map(handle_->get(), map_->elevation.data(), map_->elevation_masked.data(), map_->rows, map_->cols,
+                                map_->resolution, map_->position_x, map_->position_y), "artp_set_map");
+  }
+
+  bool hasMap() const { return artp_has_map(handle_->get()) != 0; }             // validity_checker.cpp:33-35
+
+  bool isValid(const State* state) const {                                      // validity_checker.cpp:39-45
+    uint8_t v = 0;
+    handle_->check(artp_check_poses(handle_->get(), &state->x, 1, &v), "artp_check_poses");
+    return v != 0;
+  }
+
+  // Batch form for the rejection-sampling loops (prm_motion_cost.cpp:171-194, lazy_prm_star_min_update.cpp:549-556).
+  // Pose3FromSE3 casts every field to float first (utils.h:25-38); doing that cast here halves the PCIe traffic and
+  // gives identical flags.
+  void isValidBatch(const std::vector<State>& states, std::vector<uint8_t>* valid) const {
+    std::vector<float> buf(7 * states.size());
+    for (size_t i = 0; i < states.size(); ++i) {
+      const double* s = &states[i].x;
+      for (int k = 0; k < 7; ++k) buf[7 * i + k] = static_cast<float>(s[k]);
+    }
+    valid->resize(states.size());
+    handle_->check(artp_check_poses_f32(handle_->get(), buf.data(), states.size(), valid->data()), "artp_check_poses_f32");
+  }
+
+  const HandlePtr& handle() const { return handle_; }
+
+ private:
+  HandlePtr handle_;
+  std::shared_ptr<Map> map_;
+};
+using StateValidityCheckerPtr = std::shared_ptr<StateValidityChecker>;
+
+// ompl::base::MotionValidator as the reference uses it: discrete validation over isValid with nd segments.
+class MotionValidator {
+ public:
+  MotionValidator(const StateValidityCheckerPtr& checker, int n_segments) : checker_(checker), nd_(n_segments) {}
+  // valid(s2) && valid(interpolate(s1, s2, j/nd)) for j = 1..nd-1 (OMPL DiscreteMotionValidator::checkMotion)
+  bool checkMotion(const State* s1, const State* s2) const {
+    uint8_t v = 0;
+    const auto& h = checker_->handle();
+    h->check(artp_check_motions(h->get(), &s1->x, &s2->x, 1, nd_ - 1, &v), "artp_check_motions");
+    return v != 0;
+  }
+  void checkMotionBatch(const std::vector<State>& s1, const std::vector<State>& s2, std::vector<uint8_t>* valid) const {
+    if (s1.size() != s2.size()) throw std::invalid_argument("checkMotionBatch: size mismatch");
+    valid->resize(s1.size());
+    if (s1.empty()) return;
+    const auto& h = checker_->handle();
+    h->check(artp_check_motions(h->get(), &s1[0].x, &s2[0].x, s1.size(), nd_ - 1, valid->data()), "artp_check_motions");
+  }
+ private:
+  StateValidityCheckerPtr checker_;
+  int nd_;
+};
+
+// art_planner::PathLengthObjective (path_length_objective.cpp:26-70).
+class PathLengthObjective {
+ public:
+  explicit PathLengthObjective(const StateValidityCheckerPtr& checker) : checker_(checker) {}
+  double motionCost(const State* s1, const State* s2) const {
+    double c = 0;
+    const auto& h = checker_->handle();
+    h->check(artp_path_length_cost(h->get(), &s1->x, &s2->x, 1, &c), "artp_path_length_cost");
+    return c;
+  }
+  double motionCostHeuristic(const State* s1, const State* s2) const {           // path_length_objective.cpp:58-70
+    const double dx = s2->x - s1->x, dy = s2->y - s1->y, dz = s2->z - s1->z;
+    return std::sqrt(dx * dx + dy * dy + dz * dz) / checker_->handle()->params().objectives.custom_path_length.max_lon_vel;
+  }
+  void motionCostBatch(const std::vector<State>& s1, const std::vector<State>& s2, std::vector<double>* cost) const {
+    cost->resize(s1.size());
+    if (s1.empty()) return;
+    const auto& h = checker_->handle();
+    h->check(artp_path_length_cost(h->get(), &s1[0].x, &s2[0].x, s1.size(), cost->data()), "artp_path_length_cost");
+  }
+ private:
+  StateValidityCheckerPtr checker_;
+};
+
+// Row-major dynamic float matrix, the shape of MotionCostObjective::EdgeMatrix (motion_cost_objective.h:22).
+struct EdgeMatrix {
+  size_t n_rows{0}, n_cols{0};
+  std::vector<float> v;
+  void resize(size_t r, size_t c) { n_rows = r; n_cols = c; v.assign(r * c, 0.0f); }
+  size_t rows() const { return n_rows; }
+  float& operator()(size_t r, size_t c) { return v[r * n_cols + c]; }
+  float operator()(size_t r, size_t c) const { return v[r * n_cols + c]; }
+  const float* data() const { return v.data(); }
+  float* data() { return v.data(); }
+};
+
+// art_planner::MotionCostObjective (motion_cost_objective.h:19-78, motion_cost_objective.cpp:28-95). The batch functor
+// defaults to the in-process network (artp_motion_cost) instead of the ROS cost-server call of planner_ros.cpp:283-308.
+class MotionCostObjective {
+ public:
+  using MotionCostFunc = std::function<bool(const EdgeMatrix&, EdgeMatrix*)>;
+
+  explicit MotionCostObjective(const StateValidityCheckerPtr& checker, std::unique_ptr<MotionCostFunc> func = nullptr)
+      : checker_(checker), motion_cost_func_(std::move(func)) {
+    if (!motion_cost_func_) {
+      HandlePtr h = checker_->handle();
+      motion_cost_func_.reset(new MotionCostFunc([h](const EdgeMatrix& edges, EdgeMatrix* costs) {
+        costs->resize(edges.rows(), 3);
+        return artp_motion_cost(h->get(), edges.data(), edges.rows(), costs->data()) == ARTP_OK;
+      }));
+    }
+  }
+  void setWeights(const std::vector<float>& blob) {
+    checker_->handle()->check(artp_set_cost_weights(checker_->handle()->get(), blob.data(), blob.size()), "artp_set_cost_weights");
+  }
+  void updateFeatures() { checker_->handle()->check(artp_update_features(checker_->handle()->get()), "artp_update_features"); }
+
+  double getCost(const float* e3) const {                                        // motion_cost_objective.h:54-61
+    const auto& w = checker_->handle()->params().planner.prm_motion_cost.cost_weights;
+    return e3[0] * w.energy + e3[1] * w.time + e3[2] * w.risk;
+  }
+  bool isFeasible(const float* e3) const {                                       // motion_cost_objective.h:63-65
+    return static_cast<double>(e3[2]) <= checker_->handle()->params().planner.prm_motion_cost.risk_threshold;
+  }
+  bool costQuery(const EdgeMatrix& edge_matrix, EdgeMatrix* edge_cost) const {   // motion_cost_objective.cpp:28-33
+    edge_cost->resize(edge_matrix.rows(), 3);
+    return (*motion_cost_func_)(edge_matrix, edge_cost);
+  }
+
+  // motion_cost_objective.cpp:36-95: split the edge at max_query_edge_length, query every piece, sum; +inf if any piece
+  // is too risky; throws "Motion cost call failed" if the functor fails.
+  double motionCost(const State* s1, const State* s2) const {
+    const double dx = s2->x - s1->x, dy = s2->y - s1->y;
+    const double dist = std::sqrt(dx * dx + dy * dy);                            // lateralDistance, utils.h:52-61
+    const auto& pm = checker_->handle()->params().planner.prm_motion_cost;
+    const unsigned n_interp = static_cast<unsigned>(dist / pm.max_query_edge_length);
+    const double n_interp_div = 1.0 / (n_interp + 1);
+    EdgeMatrix em, ec;
+    em.resize(n_interp + 1, 6);
+    em(0, 3) = static_cast<float>(s1->x); em(0, 4) = static_cast<float>(s1->y); em(0, 5) = yaw(*s1);
+    em(n_interp, 0) = static_cast<float>(s2->x); em(n_interp, 1) = static_cast<float>(s2->y); em(n_interp, 2) = yaw(*s2);
+    for (unsigned step = 1; step < n_interp + 1; ++step) {
+      const State cur = interpolate(*s1, *s2, step * n_interp_div);
+      em(step - 1, 0) = static_cast<float>(cur.x); em(step - 1, 1) = static_cast<float>(cur.y); em(step - 1, 2) = yaw(cur);
+      em(step, 3) = static_cast<float>(cur.x); em(step, 4) = static_cast<float>(cur.y); em(step, 5) = yaw(cur);
+    }
+    if (!costQuery(em, &ec)) throw std::runtime_error("Motion cost call failed");
+    double cost = 0;
+    for (unsigned i = 0; i < n_interp + 1; ++i) {
+      const float* e3 = ec.data() + 3 * i;
+      if (static_cast<double>(e3[2]) > pm.risk_threshold) return std::numeric_limits<double>::infinity();
+      cost += getCost(e3);
+    }
+    return cost;
+  }
+  double motionCostHeuristic(const State*, const State*) const { return 0.0; }   // motion_cost_objective.cpp:99-103
+
+  // getYawFromSO3 (utils.h:80-88): double atan2 returned through float
+  static float yaw(const State& s) {
+    return static_cast<float>(std::atan2(2 * (s.qw * s.qz + s.qx * s.qy), 1 - 2 * (s.qy * s.qy + s.qz * s.qz)));
+  }
+  // OMPL 1.4.2 SE3StateSpace::interpolate = RealVector lerp + SO3 slerp
+  static State interpolate(const State& a, const State& b, double t) {
+    State o;
+    o.x = a.x + (b.x - a.x) * t; o.y = a.y + (b.y - a.y) * t; o.z = a.z + (b.z - a.z) * t;
+    const double dq = a.qx * b.qx + a.qy * b.qy + a.qz * b.qz + a.qw * b.qw;
+    const double dqa = std::fabs(dq);
+    const double theta = (dqa > 1.0 - 1e-9) ? 0.0 : std::acos(dqa);
+    if (theta > std::numeric_limits<double>::epsilon()) {
+      const double d = 1.0 / std::sin(theta), s0 = std::sin((1.0 - t) * theta);
+      double s1 = std::sin(t * theta);
+      if (dq < 0) s1 = -s1;
+      o.qx = (a.qx * s0 + b.qx * s1) * d; o.qy = (a.qy * s0 + b.qy * s1) * d;
+      o.qz = (a.qz * s0 + b.qz * s1) * d; o.qw = (a.qw * s0 + b.qw * s1) * d;
+    } else {
+      o.qx = a.qx; o.qy = a.qy; o.qz = a.qz; o.qw = a.qw;
+    }
+    return o;
+  }
+
+ private:
+  StateValidityCheckerPtr checker_;
+  std::unique_ptr<MotionCostFunc> motion_cost_func_;
+};
+
+}  // namespace artp_host
+
+#ifdef ARTP_WITH_OMPL
+// OMPL adapters (compiled only where OMPL >= 1.4.2 is installed): the exact plugin surface of planner.cpp:125-130.
+#include <ompl/base/MotionValidator.h>
+#include <ompl/base/SpaceInformation.h>
+#include <ompl/base/StateValidityChecker.h>
+#include <ompl/base/objectives/PathLengthOptimizationObjective.h>
+#include <ompl/base/spaces/SE3StateSpace.h>
+namespace artp_host {
+namespace ob = ompl::base;
+inline State fromOmpl(const ob::State* s) {
+  const auto* se3 = s->as<ob::SE3StateSpace::StateType>();
+  State o;
+  o.x = se3->getX(); o.y = se3->getY(); o.z = se3->getZ();
+  o.qx = se3->rotation().x; o.qy = se3->rotation().y; o.qz = se3->rotation().z; o.qw = se3->rotation().w;
+  return o;
+}
+class OmplStateValidityChecker : public ob::StateValidityChecker {
+ public:
+  OmplStateValidityChecker(const ob::SpaceInformationPtr& si, const StateValidityCheckerPtr& c) : ob::StateValidityChecker(si), c_(c) {}
+  bool isValid(const ob::State* state) const override { const State s = fromOmpl(state); return c_->isValid(&s); }
+ private:
+  StateValidityCheckerPtr c_;
+};
+class OmplMotionValidator : public ob::MotionValidator {
+ public:
+  OmplMotionValidator(const ob::SpaceInformationPtr& si, const StateValidityCheckerPtr& c) : ob::MotionValidator(si), c_(c) {}
+  bool checkMotion(const ob::State* s1, const ob::State* s2) const override {
+    const State a = fromOmpl(s1), b = fromOmpl(s2);
+    return MotionValidator(c_, si_->getStateSpace()->validSegmentCount(s1, s2)).checkMotion(&a, &b);
+  }
+  bool checkMotion(const ob::State* s1, const ob::State* s2, std::pair<ob::State*, double>& lastValid) const override {
+    lastValid.second = 0.0;
+    if (lastValid.first) si_->copyState(lastValid.first, s1);
+    return checkMotion(s1, s2);
+  }
+ private:
+  StateValidityCheckerPtr c_;
+};
+class OmplPathLengthObjective : public ob::PathLengthOptimizationObjective {
+ public:
+  OmplPathLengthObjective(const ob::SpaceInformationPtr& si, const StateValidityCheckerPtr& c)
+      : ob::PathLengthOptimizationObjective(si), o_(c) {}
+  ob::Cost motionCost(const ob::State* s1, const ob::State* s2) const override {
+    const State a = fromOmpl(s1), b = fromOmpl(s2);
+    return ob::Cost(o_.motionCost(&a, &b));
+  }
+ private:
+  PathLengthObjective o_;
+};
+}  // namespace artp_host
+#endif

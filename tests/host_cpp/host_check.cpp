@@ -1,0 +1,67 @@
+// tests/host_cpp/host_check.cpp -- drives the C++ host mirror (include/artp_host.hpp) the way art_planner's facade
+// drives its plugins: construct the checker from Params, setMap + updateHeightField, isValid / checkMotion / motionCost.
+//   host_check --expect-no-gpu            : construction must fail loudly (no CPU fallback)
+//   host_check <in.bin> <out.bin>         : run the cases in in.bin, write the results (see tests/test_host_cpp.py)
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+#include "artp_host.hpp"
+
+using namespace artp_host;
+
+template <class T> static void rd(std::ifstream& f, T* p, size_t n) { f.read(reinterpret_cast<char*>(p), sizeof(T) * n); }
+template <class T> static void wr(std::ofstream& f, const T* p, size_t n) { f.write(reinterpret_cast<const char*>(p), sizeof(T) * n); }
+
+int main(int argc, char** argv) {
+  auto params = std::make_shared<Params>();
+  if (argc == 2 && !std::strcmp(argv[1], "--expect-no-gpu")) {
+    try {
+      StateValidityChecker c(params);
+    } catch (const std::runtime_error& e) {
+      std::cout << "failed loudly: " << e.what() << "\n";
+      return 0;
+    }
+    std::cout << "a handle was created: a CUDA device is present\n";
+    return 3;
+  }
+  if (argc != 3) { std::cerr << "usage\n"; return 2; }
+  std::ifstream in(argv[1], std::ios::binary);
+  int32_t hdr[6];   // rows, cols, n_poses, n_edges, n_segments, preset (0 yaml, 1 header defaults)
+  double geo[3];    // res, cx, cy
+  rd(in, hdr, 6); rd(in, geo, 3);
+  auto map = std::make_shared<Map>();
+  map->rows = hdr[0]; map->cols = hdr[1]; map->resolution = geo[0]; map->position_x = geo[1]; map->position_y = geo[2];
+  map->elevation.resize((size_t)hdr[0] * hdr[1]); map->elevation_masked.resize(map->elevation.size());
+  rd(in, map->elevation.data(), map->elevation.size()); rd(in, map->elevation_masked.data(), map->elevation_masked.size());
+  std::vector<State> poses(hdr[2]), s1(hdr[3]), s2(hdr[3]);
+  rd(in, poses.data(), poses.size()); rd(in, s1.data(), s1.size()); rd(in, s2.data(), s2.size());
+  if (hdr[5] == 0) {   // art_planner_ros/config/params.yaml:55-71
+    params->robot.torso.length = 1.31; params->robot.torso.width = 0.65; params->robot.torso.height = 0.30;
+    params->robot.torso.offset.z = 0.04;
+    params->robot.feet.offset.x = 0.51; params->robot.feet.offset.y = 0.20; params->robot.feet.offset.z = -0.475;
+    params->robot.feet.reach.x = 0.2; params->robot.feet.reach.y = 0.2; params->robot.feet.reach.z = 0.2;
+    params->objectives.custom_path_length.use_directional_cost = true;
+    params->planner.prm_motion_cost.risk_threshold = 0.5f;
+  }
+  auto checker = std::make_shared<StateValidityChecker>(params);
+  if (checker->hasMap()) return 4;
+  checker->setMap(map);
+  checker->updateHeightField();
+  if (!checker->hasMap()) return 5;
+  std::vector<uint8_t> valid, single(std::min<size_t>(poses.size(), 16)), motion, motion1(std::min<size_t>(s1.size(), 8));
+  checker->isValidBatch(poses, &valid);
+  for (size_t i = 0; i < single.size(); ++i) single[i] = checker->isValid(&poses[i]);
+  MotionValidator mv(checker, hdr[4]);
+  mv.checkMotionBatch(s1, s2, &motion);
+  for (size_t i = 0; i < motion1.size(); ++i) motion1[i] = mv.checkMotion(&s1[i], &s2[i]);
+  PathLengthObjective plo(checker);
+  std::vector<double> cost;
+  plo.motionCostBatch(s1, s2, &cost);
+  std::ofstream out(argv[2], std::ios::binary);
+  wr(out, valid.data(), valid.size()); wr(out, single.data(), single.size());
+  wr(out, motion.data(), motion.size()); wr(out, motion1.data(), motion1.size()); wr(out, cost.data(), cost.size());
+  std::cout << "ok " << valid.size() << " poses, " << motion.size() << " edges\n";
+  return 0;
+}

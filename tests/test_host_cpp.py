@@ -1,0 +1,73 @@
+"""The C++ host mirror (include/artp_host.hpp) over the C ABI: compiles with plain g++ (CPU suite), fails loudly
+without a GPU, and -- on the GPU box -- gives the oracle's answers when driven the way the reference's facade drives
+its plugins (tests/host_cpp/host_check.cpp)."""
+import os
+import shutil
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+from art_planner_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "host_cpp", "host_check")
+
+
+@pytest.fixture(scope="module")
+def exe():
+    from art_planner_b200 import build, capi
+    if not os.path.exists(capi.LIB_PATH):
+        if shutil.which("nvcc") is None:
+            pytest.skip("libartp.so not built and nvcc absent")
+        build.build()
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.run(["g++", "-std=c++14", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "host_cpp", "host_check.cpp"), "-o", EXE,
+                    "-L", libdir, "-l:libartp.so", f"-Wl,-rpath,{libdir}"], check=True)
+    return EXE
+
+
+def test_host_mirror_compiles_and_fails_loudly_without_gpu(exe):
+    import torch
+    r = subprocess.run([exe, "--expect-no-gpu"], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 3
+    else:
+        assert r.returncode == 0 and "failed loudly" in r.stdout and "CUDA" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset,mk", [(0, "fixture"), (1, "fbm_rough")], ids=["yaml-fixture", "header-fbm"])
+def test_host_mirror_matches_oracle(exe, preset, mk, maps, port_lib, tmp_path):
+    m = maps(mk)
+    params = synth.PARAMS_YAML if preset == 0 else synth.PARAMS_HEADER
+    poses = synth.make_terrain_poses(m, 5000, seed=61)
+    s1, s2 = synth.make_edges(m, 800, seed=62)
+    nseg = 6
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("6i", m.rows, m.cols, len(poses), len(s1), nseg, preset))
+        f.write(struct.pack("3d", m.res, m.cx, m.cy))
+        f.write(np.asfortranarray(m.elevation).tobytes(order="F"))
+        f.write(np.asfortranarray(m.elevation_masked).tobytes(order="F"))
+        f.write(poses.tobytes()); f.write(s1.tobytes()); f.write(s2.tobytes())
+    r = subprocess.run([exe, fin, fout], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = open(fout, "rb").read()
+    o = 0
+    valid = np.frombuffer(raw, np.uint8, len(poses), o); o += len(poses)
+    single = np.frombuffer(raw, np.uint8, 16, o); o += 16
+    motion = np.frombuffer(raw, np.uint8, len(s1), o); o += len(s1)
+    motion1 = np.frombuffer(raw, np.uint8, 8, o); o += 8
+    cost = np.frombuffer(raw, np.float64, len(s1), o)
+    orc = port_lib.Oracle(params, "port")
+    orc.set_map(m)
+    ref = orc.check_poses(poses)
+    assert np.array_equal(valid, ref) and np.array_equal(single, ref[:16])
+    refm = orc.check_motions(s1, s2, nseg - 1)
+    assert np.array_equal(motion, refm) and np.array_equal(motion1, refm[:8])
+    refc = orc.path_length_cost(s1, s2)
+    assert np.allclose(cost, refc, rtol=1e-12, atol=0)
