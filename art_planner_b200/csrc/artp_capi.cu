@@ -725,6 +725,7 @@ int artp_update_features(artp_handle* hh) {
   std::lock_guard<std::mutex> lk(h->mtx);
   if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
   artp_cnn::set_base_offset_mode(h->cnn, (h->cnn_mode & 2) ? 1 : 0);
+  artp_cnn::set_conv15_mode(h->cnn, (h->cnn_mode >> 2) & 3);
   return artp_cnn::update_features(h->cnn, h->d_H[0], h->rows, h->cols, h->pitch, h->chk.Lx / h->rows, h->chk.cx, h->chk.cy,
                                    h->stream, h->cnn_mode & 1, h->err);
 }

@@ -219,6 +219,27 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -253,15 +274,15 @@ struct ConvCfg {
 // per tap (channels are stored padded to 64 = one 128-byte swizzle row per pixel), NOUT = UMMA N (multiple of 16),
 // NMAIN fp32 accumulators for the a_hi*w_hi products (tap t -> t % NMAIN) + 1 for the two correction terms.
 // SPLIT_OUT: write the activation as fp16 hi/lo NHWC-64 (the next layer's TMA source) instead of fp32 NHWC.
-template <int KS, int KSTEPS, int NOUT, int NMAIN, bool SPLIT_OUT>
-__global__ void __launch_bounds__(192)
+template <int KS, int KSTEPS, int NOUT, int NMAIN, bool SPLIT_OUT, int CLUSTER, int ISSUERS>
+__global__ void __launch_bounds__(192 + 32 * (ISSUERS - 1))
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
                const float* __restrict__ bias, float* __restrict__ out, __half* __restrict__ out_hi,
                __half* __restrict__ out_lo, int OH, int OW, int cout, int use_base_offset) {
   using Cfg = ConvCfg<KS, NOUT>;
   constexpr int kTaps = KS * KS;
-  constexpr int kAcc = NMAIN + 1;
+  constexpr int kAcc = NMAIN + ISSUERS;   // ISSUERS correction accumulators (one per MMA-issuing warp)
   constexpr int kTmemCols = kAcc * 64 <= 64 ? 64 : (kAcc * 64 <= 128 ? 128 : (kAcc * 64 <= 256 ? 256 : 512));
   static_assert(kAcc * 64 <= 512, "too many accumulators");
   extern __shared__ unsigned char smem_raw[];
@@ -281,8 +302,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     mbar_init(bar_brick, 1);
-    for (int s = 0; s < kWStages; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
-    mbar_init(bar_done, 1);
+    // CLUSTER = 2: the two CTAs of a pair each fetch half of every weight tile and multicast it to both, so a stage is
+    // free only when BOTH issuers have consumed it (two arrivals on each CTA's empty barrier).
+    for (int s = 0; s < kWStages; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, CLUSTER); }
+    mbar_init(bar_done, ISSUERS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation: kAcc accumulators x 64 columns (NOUT used of each), one warp
@@ -291,8 +314,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to it
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = CLUSTER > 1 ? cluster_ctarank() : 0u;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -305,16 +330,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         const int s = t % kWStages, round = t / kWStages;
         if (round > 0) mbar_wait(bar_empty + s, (round - 1) & 1);
         mbar_expect_tx(bar_full + s, Cfg::kWStageBytes);
-        tma_load_2d(w_st + s * Cfg::kWStageBytes, &map_whi, bar_full + s, 0, t * NOUT);
-        tma_load_2d(w_st + s * Cfg::kWStageBytes + NOUT * 128, &map_wlo, bar_full + s, 0, t * NOUT);
+        if (CLUSTER == 1) {
+          tma_load_2d(w_st + s * Cfg::kWStageBytes, &map_whi, bar_full + s, 0, t * NOUT);
+          tma_load_2d(w_st + s * Cfg::kWStageBytes + NOUT * 128, &map_wlo, bar_full + s, 0, t * NOUT);
+        } else if (crank == 0) {   // rank 0 brings w_hi, rank 1 brings w_lo; each lands in both CTAs
+          tma_load_2d_mc(w_st + s * Cfg::kWStageBytes, &map_whi, bar_full + s, 0, t * NOUT, (uint16_t)3);
+        } else {
+          tma_load_2d_mc(w_st + s * Cfg::kWStageBytes + NOUT * 128, &map_wlo, bar_full + s, 0, t * NOUT, (uint16_t)3);
+        }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (ISSUERS == 2 && warp == 6)) {
+    // MMA issuer(s). With ISSUERS == 2 the taps alternate between two issuing warps (own accumulators each), which
+    // overlaps the per-instruction issue latency of the small N = 48 MMAs.
     if (lane == 0) {
+      const int me = (warp == 1) ? 0 : 1;
       mbar_wait(bar_brick, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t ahi = smem_u32(a_hi), alo = smem_u32(a_lo);
-      for (int t = 0; t < kTaps; ++t) {
+      constexpr int kMainPer = NMAIN / ISSUERS;            // main accumulators per issuer
+      const uint32_t d_corr = tmem_base + (uint32_t)((NMAIN + me) * 64);
+      int mine = 0;
+      for (int t = me; t < kTaps; t += ISSUERS, ++mine) {
         const int s = t % kWStages, round = t / kWStages;
         mbar_wait(bar_full + s, round & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -324,22 +361,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         const uint32_t whi = smem_u32(w_st + s * Cfg::kWStageBytes), wlo = whi + NOUT * 128;
         // The tensor core truncates when it adds into the fp32 accumulator, so a single accumulator would take
         // thousands of biased roundings in the 15x15 layer (measured 4e-5 relative). Spread them: the a_hi*w_hi
-        // products of tap t go to accumulator t % NMAIN, both small correction terms to one more; the epilogue sums
-        // them in fp32 round-to-nearest.
-        const uint32_t d_main = tmem_base + (uint32_t)((t % NMAIN) * 64), d_corr = tmem_base + (uint32_t)(NMAIN * 64);
+        // products go round-robin to NMAIN accumulators, both small correction terms to one more per issuer; the
+        // epilogue sums them in fp32 round-to-nearest.
+        const uint32_t d_main = tmem_base + (uint32_t)((me * kMainPer + (mine % kMainPer)) * 64);
 #pragma unroll
         for (int j = 0; j < KSTEPS; ++j) {   // KSTEPS x UMMA_K(16) channels; pad channels beyond are never multiplied
           const uint64_t dah = make_desc(ahi + shift * 128 + j * 32, Cfg::kBrickX * 128, bo);
           const uint64_t dal = make_desc(alo + shift * 128 + j * 32, Cfg::kBrickX * 128, bo);
           const uint64_t dwh = make_desc(whi + j * 32, 1024, 0);
           const uint64_t dwl = make_desc(wlo + j * 32, 1024, 0);
-          umma_f16(d_main, dah, dwh, Cfg::kIdesc, (t >= NMAIN || j != 0));
-          umma_f16(d_corr, dah, dwl, Cfg::kIdesc, (t | j) != 0);
+          umma_f16(d_main, dah, dwh, Cfg::kIdesc, (mine >= kMainPer || j != 0));
+          umma_f16(d_corr, dah, dwl, Cfg::kIdesc, (mine | j) != 0);
           umma_f16(d_corr, dal, dwh, Cfg::kIdesc, 1);
         }
-        umma_commit(bar_empty + s);   // frees the weight stage once these MMAs have read it
+        if (CLUSTER == 1) umma_commit(bar_empty + s);   // frees the weight stage once these MMAs have read it
+        else umma_commit_mc(bar_empty + s, (uint16_t)3);
       }
-      umma_commit(bar_done);
+      umma_commit(bar_done);   // bar_done counts ISSUERS arrivals
     }
   } else {
     // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 = output pixels m = lane index; m = yl*8 + xl
@@ -353,7 +391,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     for (int n = 0; n < NOUT; ++n) acc[n] = 0.0f;
 #pragma unroll
     for (int a = 0; a < kAcc; ++a) {
-      if (a < NMAIN && a >= kTaps) continue;   // accumulator never written
+      if (a < NMAIN && a >= kTaps) continue;   // accumulator never written (fewer taps than accumulators)
 #pragma unroll
       for (int c = 0; c < NOUT / 16; ++c) {
         uint32_t v[16];
@@ -401,9 +439,175 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();   // no CTA exits while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
   }
+}
+
+// 15x15 layer, two-phase variant. The single-phase kernel keeps both activation bricks (a_hi, a_lo: 184 KB) resident,
+// which leaves room for only 3 weight stages: 36 KB in flight per SM against ~1.5 us of L2 latency = 24 GB/s per SM,
+// i.e. the 2.7 MB weight stream takes ~110 us while the MMAs need ~26 us (measured: 113 us; TMA multicast across a CTA
+// pair did not help -- the limit is in-flight bytes, not L2 bandwidth). Here only ONE brick is resident at a time:
+//   phase 1: a_hi brick; per tap a_hi*w_hi -> main accumulators, a_hi*w_lo -> correction accumulator (12 KB/tap)
+//   phase 2: the a_lo brick replaces it; per tap a_lo*w_hi -> correction accumulator (6 KB/tap, two taps per stage)
+// and the freed 92 KB become 8 more weight stages (11 x 12 KB in flight).
+constexpr int kW2Stages = 11;
+struct Conv15Cfg {
+  using B = ConvCfg<15, 48>;
+  static constexpr int kSmem = B::kBrickBytes + kW2Stages * B::kWStageBytes + 1024 + 256;
+};
+
+// NI MMA-issuing warps share the stages round-robin (stage g belongs to issuer g % NI): a single thread issues one
+// small (N = 48) tcgen05.mma about every 100 cycles regardless of the ring depth (measured: 113 us for 2025 MMAs with 1
+// issuer, 78 us with 2), so several issuers are needed to approach the 26 us the tensor pipe itself needs.
+template <int NI>
+__global__ void __launch_bounds__(192 + 32 * (NI - 1), 1)
+conv15_two_phase_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+                        const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
+                        const float* __restrict__ bias, float* __restrict__ out, int OH, int OW) {
+  using Cfg = ConvCfg<15, 48>;
+  static_assert(2 * NI <= 8, "two TMEM accumulators (main + correction) of 64 columns per issuer");
+  constexpr int KS = 15, NOUT = 48, KSTEPS = 3, kTaps = 225, kAcc = 2 * NI;
+  constexpr int kTmemCols = kAcc * 64 <= 128 ? 128 : (kAcc * 64 <= 256 ? 256 : 512);
+  constexpr int kPairs = (kTaps + 1) / 2;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* a_br = smem;
+  unsigned char* w_st = smem + Cfg::kBrickBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_st + kW2Stages * Cfg::kWStageBytes);
+  uint64_t* bar_brick = bars;                   // TMA -> MMA: brick landed (phase 0: a_hi, phase 1: a_lo)
+  uint64_t* bar_phase = bars + 1;               // MMA -> TMA: every issuer's phase-1 MMAs finished reading the a_hi brick
+  uint64_t* bar_done = bars + 2;                // MMA -> epilogue (NI arrivals)
+  uint64_t* bar_full = bars + 3;                // [kW2Stages]
+  uint64_t* bar_empty = bars + 3 + kW2Stages;   // [kW2Stages]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + 2 * kW2Stages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * kTileX, y0 = blockIdx.y * kTileY;
+  if (warp == 0 && lane == 0) {
+    mbar_init(bar_brick, 1); mbar_init(bar_phase, NI); mbar_init(bar_done, NI);
+    for (int s = 0; s < kW2Stages; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int issuer = (warp == 1) ? 0 : (warp >= 6 ? warp - 5 : -1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_brick, Cfg::kBrickBytes);
+      tma_load_3d(a_br, &map_ahi, bar_brick, 0, x0, y0);
+      int g = 0;
+      for (int t = 0; t < kTaps; ++t, ++g) {                       // phase 1: w_hi + w_lo of one tap per stage
+        const int s = g % kW2Stages, round = g / kW2Stages;
+        if (round > 0) mbar_wait(bar_empty + s, (round - 1) & 1);
+        mbar_expect_tx(bar_full + s, Cfg::kWStageBytes);
+        tma_load_2d(w_st + s * Cfg::kWStageBytes, &map_whi, bar_full + s, 0, t * NOUT);
+        tma_load_2d(w_st + s * Cfg::kWStageBytes + NOUT * 128, &map_wlo, bar_full + s, 0, t * NOUT);
+      }
+      mbar_wait(bar_phase, 0);                                     // a_hi brick no longer read
+      mbar_expect_tx(bar_brick, Cfg::kBrickBytes);
+      tma_load_3d(a_br, &map_alo, bar_brick, 0, x0, y0);
+      for (int u = 0; u < kPairs; ++u, ++g) {                      // phase 2: w_hi of two taps per stage
+        const int s = g % kW2Stages, round = g / kW2Stages;
+        if (round > 0) mbar_wait(bar_empty + s, (round - 1) & 1);
+        const int t0 = 2 * u, t1 = 2 * u + 1;
+        mbar_expect_tx(bar_full + s, (t1 < kTaps ? 2 : 1) * NOUT * 128);
+        tma_load_2d(w_st + s * Cfg::kWStageBytes, &map_whi, bar_full + s, 0, t0 * NOUT);
+        if (t1 < kTaps) tma_load_2d(w_st + s * Cfg::kWStageBytes + NOUT * 128, &map_whi, bar_full + s, 0, t1 * NOUT);
+      }
+    }
+  } else if (issuer >= 0) {
+    if (lane == 0) {
+      const uint32_t abr = smem_u32(a_br);
+      const uint32_t d_main = tmem_base + (uint32_t)(issuer * 128), d_corr = d_main + 64u;
+      mbar_wait(bar_brick, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      bool first = true;
+      for (int g = issuer; g < kTaps; g += NI) {                   // phase 1: g == tap
+        const int s = g % kW2Stages, round = g / kW2Stages, t = g;
+        mbar_wait(bar_full + s, round & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t shift = (uint32_t)((t / KS) * Cfg::kBrickX + (t % KS));
+        const uint32_t whi = smem_u32(w_st + s * Cfg::kWStageBytes), wlo = whi + NOUT * 128;
+#pragma unroll
+        for (int j = 0; j < KSTEPS; ++j) {
+          const uint64_t da = make_desc(abr + shift * 128 + j * 32, Cfg::kBrickX * 128, 0);
+          umma_f16(d_main, da, make_desc(whi + j * 32, 1024, 0), Cfg::kIdesc, !(first && j == 0));
+          umma_f16(d_corr, da, make_desc(wlo + j * 32, 1024, 0), Cfg::kIdesc, !(first && j == 0));
+        }
+        first = false;
+        umma_commit(bar_empty + s);
+      }
+      umma_commit(bar_phase);
+      mbar_wait(bar_brick, 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // phase-2 stages continue the global stage count: g2 = kTaps + u; the issuer of a stage is g2 % NI
+      int u0 = ((issuer - (kTaps % NI)) % NI + NI) % NI;
+      for (int u = u0; u < kPairs; u += NI) {
+        const int g = kTaps + u, s = g % kW2Stages, round = g / kW2Stages;
+        mbar_wait(bar_full + s, round & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int t = 2 * u + e;
+          if (t < kTaps) {
+            const uint32_t shift = (uint32_t)((t / KS) * Cfg::kBrickX + (t % KS));
+            const uint32_t whi = smem_u32(w_st + s * Cfg::kWStageBytes) + e * NOUT * 128;
+#pragma unroll
+            for (int j = 0; j < KSTEPS; ++j)
+              umma_f16(d_corr, make_desc(abr + shift * 128 + j * 32, Cfg::kBrickX * 128, 0), make_desc(whi + j * 32, 1024, 0),
+                       Cfg::kIdesc, 1);
+          }
+        }
+        umma_commit(bar_empty + s);
+      }
+      umma_commit(bar_done);
+    }
+  } else {
+    mbar_wait(bar_done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
+    float acc[NOUT];
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) acc[n] = 0.0f;
+#pragma unroll
+    for (int a = 0; a < kAcc; ++a) {
+#pragma unroll
+      for (int c = 0; c < NOUT / 16; ++c) {
+        uint32_t v[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64 + c * 16);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[16 * c + i] += __uint_as_float(v[i]);
+      }
+    }
+    if (oy < OH && ox < OW) {
+      float* op = out + ((size_t)oy * OW + ox) * 48;
+#pragma unroll
+      for (int n = 0; n < NOUT; ++n) {
+        const float f = acc[n] * (1.0f / kWScale) + __ldg(bias + n);
+        op[n] = f > 0.0f ? f : 0.3f * f;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
 }
 
 // First layer (Cin = 1, no activation after its BN) on CUDA cores, reading the map layer directly and writing the
@@ -643,6 +847,7 @@ struct State {
   bool maps_valid = false;
   bool attrs_set = false;
   int use_base_offset = 0;
+  int conv15_mode = 0;         // 15x15 layer: 0 two-phase (default), 1 single phase, 2 single phase + CTA-pair multicast
   float last_ms[3] = {0, 0, 0};
   cudaEvent_t ev[4] = {};
 };
@@ -675,6 +880,7 @@ void destroy(State* s) {
 }
 
 void set_base_offset_mode(State* s, int on) { s->use_base_offset = on ? 1 : 0; }
+void set_conv15_mode(State* s, int mode) { if (s->conv15_mode != mode) { s->conv15_mode = mode; s->attrs_set = false; } }
 bool has_features(const State* s) { return s->has_features; }
 bool has_weights(const State* s) { return s->has_weights; }
 void last_times(const State* s, float* ms3) { ms3[0] = s->last_ms[0]; ms3[1] = s->last_ms[1]; ms3[2] = s->last_ms[2]; }
@@ -761,7 +967,7 @@ static int encode_layer_maps(State* s, CUtensorMap* maps, __half* ahi, __half* a
   return 0;
 }
 
-template <int KS, int KSTEPS, int NOUT, int NMAIN, bool SPLIT>
+template <int KS, int KSTEPS, int NOUT, int NMAIN, bool SPLIT, int CLUSTER, int ISSUERS = 1>
 static int launch_tc(State* s, int layer, __half* ahi, __half* alo, int H, int W, float* out, __half* ohi, __half* olo,
                      cudaStream_t st, std::string& err) {
   using Cfg = ConvCfg<KS, NOUT>;
@@ -770,13 +976,23 @@ static int launch_tc(State* s, int layer, __half* ahi, __half* alo, int H, int W
     int rc = encode_layer_maps(s, maps, ahi, alo, H, W, Cfg::kBrickX, Cfg::kBrickY, s->tc[layer].whi, s->tc[layer].wlo, KS * KS, NOUT, err);
     if (rc) return rc;
   }
-  auto kern = conv_tc_kernel<KS, KSTEPS, NOUT, NMAIN, SPLIT>;
+  auto kern = conv_tc_kernel<KS, KSTEPS, NOUT, NMAIN, SPLIT, CLUSTER, ISSUERS>;
   if (!s->attrs_set) CNN_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
   const int OH = H - KS + 1, OW = W - KS + 1;
-  dim3 grid((OW + kTileX - 1) / kTileX, (OH + kTileY - 1) / kTileY);
-  kern<<<grid, 192, Cfg::kSmem, st>>>(maps[0], maps[1], maps[2], maps[3], s->d_bias[layer], out, ohi, olo, OH, OW,
-                                      kLayers[layer].cout, s->use_base_offset);
-  CNN_TRY(cudaGetLastError());
+  const int gx = (OW + kTileX - 1) / kTileX, gy = (OH + kTileY - 1) / kTileY;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(((gx + CLUSTER - 1) / CLUSTER) * CLUSTER, gy);   // padded CTAs compute an out-of-range tile (stores masked)
+  cfg.blockDim = dim3(192 + 32 * (ISSUERS - 1));
+  cfg.dynamicSmemBytes = Cfg::kSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CLUSTER > 1 ? 1 : 0;
+  const int cout = kLayers[layer].cout, ubo = s->use_base_offset;
+  const float* bias = s->d_bias[layer];
+  CNN_TRY(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], bias, out, ohi, olo, OH, OW, cout, ubo));
   return 0;
 }
 
@@ -833,16 +1049,39 @@ int update_features(State* s, const float* d_layer, int rows, int cols, int pitc
   } else {
     int rc;
     conv1_split_kernel<<<g1, 256, 0, st>>>(d_layer, H0, W0, pitch, s->d_wf[0], s->d_bias[0], s->h1, s->l1);
-    if ((rc = launch_tc<3, 2, 32, 1, false>(s, 1, s->h1, s->l1, H1, W1, s->f2, nullptr, nullptr, st, err))) return rc;
+    if ((rc = launch_tc<3, 2, 32, 1, false, 1>(s, 1, s->h1, s->l1, H1, W1, s->f2, nullptr, nullptr, st, err))) return rc;
     maxpool_split_kernel<<<g1, 256, 0, st>>>(s->f2, H2, W2, 24, 2, 2, s->hp2, s->lp2, HP2, WP2);
-    if ((rc = launch_tc<3, 2, 48, 1, true>(s, 2, s->hp2, s->lp2, HP2, WP2, nullptr, s->h3, s->l3, st, err))) return rc;
-    if ((rc = launch_tc<3, 3, 48, 1, false>(s, 3, s->h3, s->l3, H3, W3, s->f4, nullptr, nullptr, st, err))) return rc;
+    if ((rc = launch_tc<3, 2, 48, 1, true, 1>(s, 2, s->hp2, s->lp2, HP2, WP2, nullptr, s->h3, s->l3, st, err))) return rc;
+    if ((rc = launch_tc<3, 3, 48, 1, false, 1>(s, 3, s->h3, s->l3, H3, W3, s->f4, nullptr, nullptr, st, err))) return rc;
     maxpool_split_kernel<<<g1, 256, 0, st>>>(s->f4, H4, W4, 48, 3, 1, s->hp4, s->lp4, HP4, WP4);
-    if ((rc = launch_tc<3, 3, 48, 1, true>(s, 4, s->hp4, s->lp4, HP4, WP4, nullptr, s->h5, s->l5, st, err))) return rc;
+    if ((rc = launch_tc<3, 3, 48, 1, true, 1>(s, 4, s->hp4, s->lp4, HP4, WP4, nullptr, s->h5, s->l5, st, err))) return rc;
     CNN_TRY(cudaGetLastError());
     CNN_TRY(cudaEventRecord(s->ev[1], st));
     CNN_TRY(cudaEventRecord(s->ev[2], st));
-    if ((rc = launch_tc<15, 3, 48, 7, false>(s, 5, s->h5, s->l5, H5, W5, s->feat, nullptr, nullptr, st, err))) return rc;
+    if (s->conv15_mode == 0) {          // two-phase (default)
+      using Cfg = ConvCfg<15, 48>;
+      CUtensorMap* maps = s->maps[5];
+      if (!s->maps_valid) {
+        rc = encode_layer_maps(s, maps, s->h5, s->l5, H5, W5, Cfg::kBrickX, Cfg::kBrickY, s->tc[5].whi, s->tc[5].wlo, 225, 48, err);
+        if (rc) return rc;
+      }
+      constexpr int kIssuers = 4;
+      if (!s->attrs_set)
+        CNN_TRY(cudaFuncSetAttribute(conv15_two_phase_kernel<kIssuers>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv15Cfg::kSmem));
+      dim3 grid((W6 + kTileX - 1) / kTileX, (H6 + kTileY - 1) / kTileY);
+      conv15_two_phase_kernel<kIssuers><<<grid, 192 + 32 * (kIssuers - 1), Conv15Cfg::kSmem, st>>>(maps[0], maps[1], maps[2], maps[3],
+                                                                                                   s->d_bias[5], s->feat, H6, W6);
+      CNN_TRY(cudaGetLastError());
+    } else if (s->conv15_mode == 2) {   // single phase, CTA pairs with weight multicast
+      rc = launch_tc<15, 3, 48, 7, false, 2>(s, 5, s->h5, s->l5, H5, W5, s->feat, nullptr, nullptr, st, err);
+      if (rc) return rc;
+    } else if (s->conv15_mode == 3) {   // single phase, two MMA-issuing warps
+      rc = launch_tc<15, 3, 48, 6, false, 1, 2>(s, 5, s->h5, s->l5, H5, W5, s->feat, nullptr, nullptr, st, err);
+      if (rc) return rc;
+    } else {                            // single phase, one CTA per tile
+      rc = launch_tc<15, 3, 48, 7, false, 1>(s, 5, s->h5, s->l5, H5, W5, s->feat, nullptr, nullptr, st, err);
+      if (rc) return rc;
+    }
     s->maps_valid = true;
     s->attrs_set = true;
   }

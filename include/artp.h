@@ -137,7 +137,7 @@ int artp_motion_cost_device(artp_handle* h, const float* d_edges, size_t n, floa
  * cost[i] = w_e*E + w_t*T + w_r*R, feasible[i] = R <= risk_threshold (weights / threshold from artp_params). */
 int artp_combine_cost(artp_handle* h, const float* cost3, size_t n, double* cost, uint8_t* feasible);
 /* Test hooks: feature map copy-out ([Hf][Wf][48] fp32, channels last), kernel selection (bit 0: CUDA-core fp32
- * reference for the 15x15 layer instead of tcgen05; bit 1: set the smem-descriptor base_offset, a known-wrong variant kept for the record), trunk timings
+ * reference for the 15x15 layer instead of tcgen05; bit 1: set the smem-descriptor base_offset, a known-wrong variant kept for the record; bits 2-3: 15x15 layer variant, 0 = two-phase (default), 1 = single phase, 2 = single phase with CTA-pair weight multicast), trunk timings
  * ms3 = (3x3 stack, 15x15 layer, whole trunk) of the last artp_update_features. */
 int artp_get_features(artp_handle* h, float* out, size_t n_floats, int* hf, int* wf);
 int artp_set_cnn_mode(artp_handle* h, int mode);

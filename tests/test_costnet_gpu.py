@@ -35,7 +35,7 @@ def setup():
     return m, obj, orc, feat, golden
 
 
-@pytest.mark.parametrize("mode", [1, 0], ids=["cuda-core-15x15", "tcgen05"])
+@pytest.mark.parametrize("mode", [1, 0, 4, 8, 12], ids=["cuda-core", "tcgen05-two-phase", "tcgen05-single-phase", "tcgen05-multicast-pairs", "tcgen05-two-issuers"])
 def test_feature_map(setup, mode):
     m, obj, orc, feat, golden = setup
     obj.setMode(mode)
