@@ -612,33 +612,45 @@ conv15_two_phase_kernel(const __grid_constant__ CUtensorMap map_ahi, const __gri
 
 // First layer (Cin = 1, no activation after its BN) on CUDA cores, reading the map layer directly and writing the
 // fp16 hi/lo NHWC-64 input of the second layer.
-__global__ void conv1_split_kernel(const float* __restrict__ layer, int H, int W, int pitch, const float* __restrict__ wf /*[9][1][24]*/,
-                                   const float* __restrict__ bias, __half* __restrict__ hi, __half* __restrict__ lo) {
+__global__ void __launch_bounds__(256) conv1_split_kernel(const float* __restrict__ layer, int H, int W, int pitch,
+                                                          const float* __restrict__ wf /*[9][1][24]*/, const float* __restrict__ bias,
+                                                          __half* __restrict__ hi, __half* __restrict__ lo) {
+  __shared__ float sw[9 * 24 + 24];
+  for (int i = threadIdx.x; i < 9 * 24 + 24; i += blockDim.x) sw[i] = i < 216 ? wf[i] : bias[i - 216];
+  __syncthreads();
   const int OH = H - 2, OW = W - 2;
   const size_t total = (size_t)OH * OW;
+  // consecutive threads take consecutive image rows (oy): the map layer is contiguous along that axis
   for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
-    const int ox = (int)(p % OW), oy = (int)(p / OW);
+    const int oy = (int)(p % OH), ox = (int)(p / OH);
     float in[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) in[t] = __ldg(layer + (size_t)(ox + t % 3) * pitch + (H - 1 - (oy + t / 3)));   // E[r][c]
-    __half2* ph = reinterpret_cast<__half2*>(hi + p * 64);
-    __half2* pl = reinterpret_cast<__half2*>(lo + p * 64);
+    const size_t pix = (size_t)oy * OW + ox;
+    uint4* ph = reinterpret_cast<uint4*>(hi + pix * 64);
+    uint4* pl = reinterpret_cast<uint4*>(lo + pix * 64);
 #pragma unroll
-    for (int n2 = 0; n2 < 32; ++n2) {
-      float f[2] = {0.0f, 0.0f};
-      if (n2 < 12) {
+    for (int v4 = 0; v4 < 8; ++v4) {          // 8 channels (one 16-byte store) at a time; channels 24..63 are zero
+      __half2 hh[4], ll[4];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int n = 2 * n2 + e;
-          float a = __ldg(bias + n);
+      for (int e2 = 0; e2 < 4; ++e2) {
+        float f[2] = {0.0f, 0.0f};
+        if (v4 < 3) {
 #pragma unroll
-          for (int t = 0; t < 9; ++t) a = fmaf(in[t], __ldg(wf + t * 24 + n), a);
-          f[e] = a;
+          for (int e = 0; e < 2; ++e) {
+            const int n = 8 * v4 + 2 * e2 + e;
+            float a = sw[216 + n];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) a = fmaf(in[t], sw[t * 24 + n], a);
+            f[e] = a;
+          }
         }
+        const __half h0 = __float2half_rn(f[0]), h1 = __float2half_rn(f[1]);
+        hh[e2] = __halves2half2(h0, h1);
+        ll[e2] = __halves2half2(__float2half_rn(f[0] - __half2float(h0)), __float2half_rn(f[1] - __half2float(h1)));
       }
-      const __half h0 = __float2half_rn(f[0]), h1 = __float2half_rn(f[1]);
-      ph[n2] = __halves2half2(h0, h1);
-      pl[n2] = __halves2half2(__float2half_rn(f[0] - __half2float(h0)), __float2half_rn(f[1] - __half2float(h1)));
+      ph[v4] = *reinterpret_cast<uint4*>(hh);
+      pl[v4] = *reinterpret_cast<uint4*>(ll);
     }
   }
 }
