@@ -145,19 +145,6 @@ __global__ void maxpool_kernel(const float* __restrict__ in, int H, int W, int C
   }
 }
 
-// fp32 NHWC [H][W][48] -> fp16 hi / lo NHWC [H][W][64] (channels 48..63 zero): the TMA source of the 15x15 layer.
-__global__ void split_pad_kernel(const float* __restrict__ in, size_t npix, __half* __restrict__ hi, __half* __restrict__ lo) {
-  const size_t total = npix * 64;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i & 63);
-    const size_t p = i >> 6;
-    float v = c < 48 ? in[p * 48 + c] : 0.0f;
-    const __half h = __float2half_rn(v);
-    hi[i] = h;
-    lo[i] = __float2half_rn(v - __half2float(h));
-  }
-}
-
 // Fold BN into conv weights: wf[tap][cin][cout] = w[cout][cin][tap] * gamma/sqrt(var+eps); bias = beta - mean*scale.
 __global__ void fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ bn /*gamma,beta,mean,var*/, int cout,
                                  int cin, int kk, float* __restrict__ wf, float* __restrict__ bias) {
@@ -719,11 +706,8 @@ __global__ void conv15_reference_kernel(const float* __restrict__ in /*[H][W][48
 // ------------------------------------------------------------------------------------------------
 // Query head: CostQuery.__call__ + FCpart, one thread per query, folded weights in shared memory.
 // ------------------------------------------------------------------------------------------------
-struct HeadParams {
-  const float* w;   // folded: tar0 [10][16]+b[16], out0 [64][48]+b[48], o11 [48][24]+b, o12 [48][24]+b, o13 [48][36]+b,
-                    // o21 [24]+b[1], o22 [24]+b[1], o23 [36]+b[1]
-  int n_floats;
-};
+// folded head weights: tar0 [10][16]+b[16], out0 [64][48]+b[48], o11 [48][24]+b, o12 [48][24]+b, o13 [48][36]+b,
+// o21 [24]+b[1], o22 [24]+b[1], o23 [36]+b[1]
 constexpr int kHeadFloats = 10 * 16 + 16 + 64 * 48 + 48 + 48 * 24 + 24 + 48 * 24 + 24 + 48 * 36 + 36 + 24 + 1 + 24 + 1 + 36 + 1;
 
 __global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ feats /*[Hf][Wf][48]*/, int Hf, int Wf,
