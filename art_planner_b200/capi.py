@@ -59,6 +59,8 @@ def load():
     lib.artp_check_poses_f32_device.argtypes = [vp, vp, sz, vp, vp]
     lib.artp_check_motions.argtypes = [vp, vp, vp, sz, i32, vp]
     lib.artp_check_motions_device.argtypes = [vp, vp, vp, sz, i32, vp, vp]
+    lib.artp_check_edge_interiors.argtypes = [vp, vp, vp, sz, vp, C.c_double, vp]
+    lib.artp_check_edge_interiors_device.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, vp]
     lib.artp_path_length_cost.argtypes = [vp, vp, vp, sz, vp]
     lib.artp_path_length_cost_device.argtypes = [vp, vp, vp, sz, vp, vp]
     lib.artp_compact_valid_device.argtypes = [vp, vp, sz, C.c_int64, vp, vp, vp]

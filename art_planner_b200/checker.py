@@ -117,6 +117,20 @@ class StateValidityChecker:
         h.check(fn(h.h, s.ctypes.data, n, out.ctypes.data))
         return out
 
+    def sampleValidBatch(self, sampler, n_wanted: int, batch: int = 65536, max_draws: int = 1 << 24):
+        """The rejection-sampling loop `do sampleUniform(s) while (!isValid(s))` (prm_motion_cost.cpp:171-194,
+        lazy_prm_star_min_update.cpp:549-556) in batches: sampler(m) -> [m, 7] candidates; valid ones are kept in draw
+        order until n_wanted states are collected or max_draws candidates were drawn. Returns (states, drawn)."""
+        kept, have, drawn = [], 0, 0
+        while have < n_wanted and drawn < max_draws:
+            m = min(batch, max_draws - drawn)
+            cand = np.ascontiguousarray(sampler(m))
+            drawn += m
+            ok = cand[self.isValidBatch(cand) != 0][: n_wanted - have]
+            kept.append(ok)
+            have += len(ok)
+        return (np.concatenate(kept) if kept else np.zeros((0, 7))), drawn
+
     def isValidHostPtr(self, states_ptr: int, n: int, valid_ptr: int, f32: bool = False) -> None:
         """Raw host pointers (e.g. pinned torch tensors): the exact call an OMPL adapter makes. f32: the states were
         already cast to float (what Pose3FromSE3 does first) -- identical results, half the H2D bytes."""
@@ -187,6 +201,45 @@ class MotionValidator:
             out = np.empty(n, dtype=np.uint8)
         h.check(lib.artp_check_motions(h.h, a.ctypes.data, b.ctypes.data, n, self.n_steps, out.ctypes.data))
         return out
+
+    def checkEdgeInteriors(self, s1, s2, n_interp=None, max_lateral: float = 0.5):
+        """PRMMotionCost::addValidMilestone's connection loop (prm_motion_cost.cpp:341-372) over a batch of candidate
+        edges: per edge the number of leading valid interior states (== n_interp[e] iff the connection is valid).
+        Returns (valid_prefix, n_interp). Host arrays, or CUDA float64 tensors (then n_interp must be given as an
+        int tensor / array and the prefix sums are built with torch)."""
+        h, lib = self._c.handle, self._c.handle.lib
+        if _is_torch_cuda(s1):
+            import torch
+            assert s1.dtype == torch.float64 and s2.dtype == torch.float64 and s1.is_contiguous() and s2.is_contiguous()
+            n = s1.shape[0]
+            if n_interp is None:
+                d = torch.sqrt((s2[:, 0] - s1[:, 0]) ** 2 + (s2[:, 1] - s1[:, 1]) ** 2)
+                n_interp = (d / max_lateral).to(torch.int64)
+            ni = torch.as_tensor(n_interp, device=s1.device).to(torch.int64)
+            off = torch.zeros(n + 1, dtype=torch.int64, device=s1.device)
+            off[1:] = torch.cumsum(ni, 0)
+            total = int(off[-1].item())
+            off32 = off.to(torch.int32).contiguous()      # same bits as uint32 below 2^31
+            assert total < 2 ** 31
+            flags = torch.empty(max(total, 1), dtype=torch.uint8, device=s1.device)
+            out = torch.empty(n, dtype=torch.int32, device=s1.device)
+            h.check(lib.artp_check_edge_interiors_device(
+                h.h, C.c_void_p(s1.data_ptr()), C.c_void_p(s2.data_ptr()), n, C.c_void_p(off32.data_ptr()), total,
+                C.c_void_p(flags.data_ptr()), C.c_void_p(out.data_ptr()), _stream_ptr()))
+            return out, ni.to(torch.int32)
+        a = np.ascontiguousarray(s1, dtype=np.float64)
+        b = np.ascontiguousarray(s2, dtype=np.float64)
+        n = a.shape[0]
+        out = np.empty(n, dtype=np.int32)
+        if n_interp is None:
+            d = np.sqrt((b[:, 0] - a[:, 0]) ** 2 + (b[:, 1] - a[:, 1]) ** 2)
+            ni = (d / max_lateral).astype(np.uint32).astype(np.int32)
+        else:
+            ni = np.ascontiguousarray(n_interp, dtype=np.int32)
+        h.check(lib.artp_check_edge_interiors(h.h, a.ctypes.data, b.ctypes.data, n,
+                                              None if n_interp is None else ni.ctypes.data, float(max_lateral),
+                                              out.ctypes.data))
+        return out, ni
 
 
 class PathLengthObjective:

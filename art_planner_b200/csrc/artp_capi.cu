@@ -11,6 +11,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/artp.h"
 #include "artp_cnn.h"
@@ -641,6 +642,100 @@ int artp_check_motions(artp_handle* hh, const double* s1, const double* s2, size
   std::lock_guard<std::mutex> lk(h->mtx);
   CU_TRY(h, cudaMemcpyAsync(valid, d_valid, n, cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return ARTP_OK;
+}
+
+// valid_prefix[e] = number of leading 1s in item_valid[item_off[e] .. item_off[e+1])
+__global__ void edge_prefix_kernel(const uint8_t* __restrict__ item_valid, const uint32_t* __restrict__ item_off, size_t n,
+                                   int32_t* __restrict__ valid_prefix) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t o0 = item_off[e], o1 = item_off[e + 1];
+    uint32_t k = o0;
+    while (k < o1 && item_valid[k]) ++k;
+    valid_prefix[e] = (int32_t)(k - o0);
+  }
+}
+
+int artp_check_edge_interiors_device(artp_handle* hh, const double* d_s1, const double* d_s2, size_t n,
+                                     const uint32_t* d_item_off, size_t total_items, uint8_t* d_item_valid,
+                                     int32_t* d_valid_prefix, void* stream) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  int rc = check_common(h, total_items);
+  if (rc) return rc;
+  if (n == 0) return ARTP_OK;
+  if (!d_s1 || !d_s2 || !d_item_off || !d_valid_prefix || (total_items && !d_item_valid)) {
+    h->err = "null buffer"; return ARTP_E_INVALID;
+  }
+  if (n >= 0xFFFFFFFFull) { h->err = "too many edges"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  h->stats.last_launches = 0;
+  if (total_items) {
+    artp::Work w;
+    w.s1 = d_s1; w.s2 = d_s2; w.s2f = nullptr; w.valid = d_item_valid; w.item_base = 0; w.n_items = (uint32_t)total_items;
+    w.steps = 0; w.edge_mode = 0; w.item_off = d_item_off; w.n_edges = (uint32_t)n;
+    rc = run_items(h, w, s);
+    if (rc) return rc;
+  }
+  edge_prefix_kernel<<<std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 8), 256, 0, s>>>(d_item_valid, d_item_off, n,
+                                                                                                  d_valid_prefix);
+  CU_TRY(h, cudaGetLastError());
+  h->stats.kernel_launches += 1;
+  h->stats.last_launches += 1;
+  h->stats.poses_checked += total_items;
+  return ARTP_OK;
+}
+
+int artp_check_edge_interiors(artp_handle* hh, const double* s1, const double* s2, size_t n, const int32_t* n_interp,
+                              double max_lateral, int32_t* valid_prefix) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::vector<uint32_t> off;
+  size_t total = 0, sb_al = 0, ob_al = 0, pb_al = 0;
+  {
+    std::lock_guard<std::mutex> lk(h->mtx);
+    if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
+    if (n == 0) return ARTP_OK;
+    if (!s1 || !s2 || !valid_prefix) { h->err = "null buffer"; return ARTP_E_INVALID; }
+    if (!n_interp && !(max_lateral > 0.0)) { h->err = "n_interp == NULL needs max_lateral > 0"; return ARTP_E_INVALID; }
+    off.resize(n + 1);
+    for (size_t e = 0; e < n; ++e) {
+      off[e] = (uint32_t)total;
+      long long ne;
+      if (n_interp) {
+        ne = n_interp[e];
+      } else {   // lateralDistance (utils.h:52-61) / max_lateral truncated like prm_motion_cost.cpp:341-343
+        const double dx = s2[7 * e] - s1[7 * e], dy = s2[7 * e + 1] - s1[7 * e + 1];
+        ne = (long long)(unsigned int)(std::sqrt(dx * dx + dy * dy) / max_lateral);
+      }
+      if (ne < 0) { h->err = "n_interp < 0"; return ARTP_E_INVALID; }
+      total += (size_t)ne;
+      if (total >= 0xFFFFFFFFull) { h->err = "too many interior states (>= 2^32)"; return ARTP_E_INVALID; }
+    }
+    off[n] = (uint32_t)total;
+    const size_t sb = n * 7 * sizeof(double);
+    sb_al = (sb + 255) & ~(size_t)255;
+    ob_al = ((n + 1) * sizeof(uint32_t) + 255) & ~(size_t)255;
+    pb_al = (n * sizeof(int32_t) + 255) & ~(size_t)255;
+    CU_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_stage(h, 2 * sb_al + ob_al + pb_al + total + 256);
+    if (rc) return rc;
+    char* base = (char*)h->d_stage;
+    CU_TRY(h, cudaMemcpyAsync(base, s1, sb, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(base + sb_al, s2, sb, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(base + 2 * sb_al, off.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  }
+  char* base = (char*)h->d_stage;
+  int32_t* d_prefix = (int32_t*)(base + 2 * sb_al + ob_al);
+  int rc = artp_check_edge_interiors_device(hh, (const double*)base, (const double*)(base + sb_al), n,
+                                            (const uint32_t*)(base + 2 * sb_al), total,
+                                            (uint8_t*)(base + 2 * sb_al + ob_al + pb_al), d_prefix, h->stream);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(h->mtx);
+  CU_TRY(h, cudaMemcpyAsync(valid_prefix, d_prefix, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));   // `off` must outlive its H2D copy: it does, we synchronise here
   return ARTP_OK;
 }
 

@@ -46,6 +46,10 @@ struct Work {
   uint32_t n_items;     // one past the last work item of this launch
   int steps;            // EDGE: interior steps; POSE: 0
   int edge_mode;
+  // INTERIOR mode (edge_mode == 0, item_off != null): item i is interior state j = i - item_off[e] + 1 of edge e at
+  // t = j * (1.0 / (n_e + 1)), n_e = item_off[e+1] - item_off[e]  (prm_motion_cost.cpp:345-353); valid[] is per item.
+  const uint32_t* item_off = nullptr;   // n_edges + 1 exclusive prefix sums of the per-edge interior-state counts
+  uint32_t n_edges = 0;
 };
 
 __device__ __forceinline__ uint32_t bloom_hash(int kx, int kz) {
@@ -87,6 +91,21 @@ __device__ __forceinline__ void se3_interpolate(const double* a, const double* b
 }
 
 __device__ __forceinline__ void load_item_state(const Work& w, uint32_t item, double s[7]) {
+  if (w.item_off) {
+    uint32_t lo = 0, hi = w.n_edges;          // largest e with item_off[e] <= item
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(w.item_off + mid) <= item) lo = mid; else hi = mid;
+    }
+    const uint32_t o0 = __ldg(w.item_off + lo), o1 = __ldg(w.item_off + lo + 1);
+    const int n_e = (int)(o1 - o0), step = (int)(item - o0) + 1;
+    const double n_interp_div = 1.0 / (double)(n_e + 1);
+    double a[7], b[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { a[k] = w.s1[(size_t)lo * 7 + k]; b[k] = w.s2[(size_t)lo * 7 + k]; }
+    se3_interpolate(a, b, (double)step * n_interp_div, s);
+    return;
+  }
   if (!w.edge_mode) {
     if (w.s2f) {
 #pragma unroll

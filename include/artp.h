@@ -20,6 +20,8 @@
  *                                   DiscreteMotionValidator over isValid (call sites prm_motion_cost.cpp:652,
  *                                   lazy_prm_star_min_update.cpp:725) and the in-tree interpolation loop
  *                                   PRMMotionCost::addValidMilestone (prm_motion_cost.cpp:341-372)
+ *   artp_check_edge_interiors[_device]  that same addValidMilestone loop with its exact semantics: per-edge
+ *                                   interior-state counts, no endpoint check, stop at the first invalid state
  *   artp_path_length_cost[_device]  ompl::base::OptimizationObjective::motionCost ->
  *                                   PathLengthObjective::motionCost (objectives/path_length_objective.cpp:26-70)
  *   artp_set_cost_weights, artp_update_features, artp_motion_cost[_device]
@@ -95,6 +97,21 @@ int artp_check_poses_f32_device(artp_handle* h, const float* d_states, size_t n,
 int artp_check_motions(artp_handle* h, const double* s1, const double* s2, size_t n, int n_steps, uint8_t* valid);
 int artp_check_motions_device(artp_handle* h, const double* d_s1, const double* d_s2, size_t n, int n_steps,
                               uint8_t* d_valid, void* stream);
+
+/* PRMMotionCost::addValidMilestone's connection test (prm_motion_cost.cpp:341-372), batched over the n candidate
+ * edges of new milestones: edge e has n_interp[e] interior states at t = step * (1.0 / (n_interp[e] + 1)),
+ * step = 1..n_interp[e] (endpoints are NOT checked there), and the reference loop stops at the first invalid one.
+ * valid_prefix[e] = number of leading valid interior states; the connection is valid iff it equals n_interp[e], and
+ * the caller inserts the first valid_prefix[e] states as intermediate milestones exactly like :356-366.
+ * n_interp == NULL: computed per edge as (unsigned)(lateralDistance(s1, s2) / max_lateral) like :341-343
+ * (the reference's max_lateral is 0.5). Total interior states must be < 2^32. */
+int artp_check_edge_interiors(artp_handle* h, const double* s1, const double* s2, size_t n, const int32_t* n_interp,
+                              double max_lateral, int32_t* valid_prefix);
+/* DEVICE buffers: d_item_off = n + 1 exclusive prefix sums (uint32) of the per-edge interior-state counts,
+ * total_items = d_item_off[n], d_item_valid = scratch of total_items bytes that receives the per-state flags. */
+int artp_check_edge_interiors_device(artp_handle* h, const double* d_s1, const double* d_s2, size_t n,
+                                     const uint32_t* d_item_off, size_t total_items, uint8_t* d_item_valid,
+                                     int32_t* d_valid_prefix, void* stream);
 
 /* PathLengthObjective::motionCost for n edges -> cost[n] (double). */
 int artp_path_length_cost(artp_handle* h, const double* s1, const double* s2, size_t n, double* cost);

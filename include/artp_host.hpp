@@ -134,6 +134,28 @@ class StateValidityChecker {
     handle_->check(artp_check_poses_f32(handle_->get(), buf.data(), states.size(), valid->data()), "artp_check_poses_f32");
   }
 
+  // The rejection-sampling loop `do { sampleUniform(s) } while (!isValid(s))` (prm_motion_cost.cpp:171-194,
+  // lazy_prm_star_min_update.cpp:549-556) in batches: draw `batch` candidates with the caller's sampler, check them in
+  // one call, keep the valid ones in draw order; repeat until n_wanted states are collected or max_draws candidates
+  // were drawn (the reference bounds the same loop by time). Returns the number of candidates drawn.
+  template <class Sampler>   // void sampler(State* out)
+  size_t sampleValidBatch(Sampler&& sampler, size_t n_wanted, size_t batch, size_t max_draws, std::vector<State>* out) const {
+    out->clear();
+    size_t drawn = 0;
+    std::vector<State> cand;
+    std::vector<uint8_t> valid;
+    while (out->size() < n_wanted && drawn < max_draws) {
+      const size_t m = std::min(batch, max_draws - drawn);
+      cand.resize(m);
+      for (size_t i = 0; i < m; ++i) sampler(&cand[i]);
+      drawn += m;
+      isValidBatch(cand, &valid);
+      for (size_t i = 0; i < m && out->size() < n_wanted; ++i)
+        if (valid[i]) out->push_back(cand[i]);
+    }
+    return drawn;
+  }
+
   const HandlePtr& handle() const { return handle_; }
 
  private:
@@ -159,6 +181,23 @@ class MotionValidator {
     if (s1.empty()) return;
     const auto& h = checker_->handle();
     h->check(artp_check_motions(h->get(), &s1[0].x, &s2[0].x, s1.size(), nd_ - 1, valid->data()), "artp_check_motions");
+  }
+  // PRMMotionCost::addValidMilestone's connection loop (prm_motion_cost.cpp:341-372) for a batch of candidate edges:
+  // n_interp[e] = (unsigned)(lateralDistance / max_lateral) interior states, valid_prefix[e] = how many leading ones are
+  // valid; the connection holds iff valid_prefix[e] == n_interp[e].
+  void checkEdgeInteriors(const std::vector<State>& s1, const std::vector<State>& s2, double max_lateral,
+                          std::vector<int32_t>* n_interp, std::vector<int32_t>* valid_prefix) const {
+    if (s1.size() != s2.size()) throw std::invalid_argument("checkEdgeInteriors: size mismatch");
+    n_interp->resize(s1.size());
+    valid_prefix->resize(s1.size());
+    if (s1.empty()) return;
+    for (size_t e = 0; e < s1.size(); ++e) {
+      const double dx = s2[e].x - s1[e].x, dy = s2[e].y - s1[e].y;             // lateralDistance, utils.h:52-61
+      (*n_interp)[e] = static_cast<int32_t>(static_cast<unsigned int>(std::sqrt(dx * dx + dy * dy) / max_lateral));
+    }
+    const auto& h = checker_->handle();
+    h->check(artp_check_edge_interiors(h->get(), &s1[0].x, &s2[0].x, s1.size(), n_interp->data(), max_lateral,
+                                       valid_prefix->data()), "artp_check_edge_interiors");
   }
  private:
   StateValidityCheckerPtr checker_;

@@ -532,6 +532,114 @@ int orc_check_motions(orc_handle* h, const double* s1, const double* s2, size_t 
   return 0;
 }
 
+int orc_check_edge_interiors(orc_handle* h, const double* s1, const double* s2, size_t n, const int32_t* n_interp,
+                             double max_lateral, int32_t* valid_prefix) {
+  if (!h || !h->g.has_map) return 1;
+  port_ctx c = {h, {0, 0, 0, 0, 0, 0, 0}};
+  for (size_t i = 0; i < n; ++i) {
+    const int32_t ni = n_interp ? n_interp[i] : orc_n_interp(s1 + 7 * i, s2 + 7 * i, max_lateral);
+    valid_prefix[i] = orc_edge_interior_prefix(&h->p, &h->g, port_collide, &c, s1 + 7 * i, s2 + 7 * i, ni);
+  }
+  free(c.sc.tri); free(c.sc.group);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * SE3FromSE2Sampler::sampleUniform, art_planner/src/sampler.cpp:40-131 (uniform variates are inputs)
+ * ---------------------------------------------------------------------------------------------- */
+/* grid_map::getPositionFromIndex (GridMapMath.cpp): position = mapPosition + (0.5*length - 0.5*res) + res * (-index) */
+static void gm_position_of_index(const orc_sampler_map* m, int row, int col, double pos[2]) {
+  const double offx = 0.5 * (m->rows * m->res) - 0.5 * m->res, offy = 0.5 * (m->cols * m->res) - 0.5 * m->res;
+  pos[0] = (m->cx + offx) + m->res * (-(double)row);
+  pos[1] = (m->cy + offy) + m->res * (-(double)col);
+}
+
+/* grid_map::getIndexFromPosition: indexVector = (position - 0.5*length - mapPosition) / res; index = (int)(-indexVector);
+ * valid iff checkIfPositionWithinMap && index in range. */
+static int gm_index_of_position(const orc_sampler_map* m, const double pos[2], int* row, int* col) {
+  const double Lx = m->rows * m->res, Ly = m->cols * m->res;
+  const double vx = ((pos[0] - 0.5 * Lx) - m->cx) / m->res, vy = ((pos[1] - 0.5 * Ly) - m->cy) / m->res;
+  *row = (int)(-vx);
+  *col = (int)(-vy);
+  orc_geom g = {Lx, Ly, m->cx, m->cy, 1};
+  const double tx = -((pos[0] - g.cx) - 0.5 * Lx), ty = -((pos[1] - g.cy) - 0.5 * Ly);
+  const int inside = tx >= 0.0 && ty >= 0.0 && tx < Lx && ty < Ly;
+  return inside && *row >= 0 && *col >= 0 && *row < m->rows && *col < m->cols;
+}
+
+static void cross3d(const double a[3], const double b[3], double o[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+static void sample_one(const orc_sampler_map* m, const orc_sampler_params* p, const double u[6], double s[7], int32_t rc[2]) {
+  double pos[2];
+  if (p->sample_from_distribution) {
+    /* samplePositionInMapFromDist, sampler.cpp:54-77: linear scans, float CDF against double variate */
+    const double samp_col = u[0], samp_row = u[1];
+    int row, col;
+    for (row = 0; row < m->rows - 1; ++row)
+      if ((double)m->cum_prob_rowwise[row] > samp_row) break;
+    for (col = 0; col < m->cols - 1; ++col)
+      if ((double)m->cum_prob[row + (size_t)col * m->rows] > samp_col) break;
+    gm_position_of_index(m, row, col, pos);
+  } else {
+    /* samplePositionInMap, sampler.cpp:40-50: one attempt; uniformReal(a,b) = (b-a)*u + a */
+    pos[0] = (p->high[0] - p->low[0]) * u[0] + p->low[0];
+    pos[1] = (p->high[1] - p->low[1]) * u[1] + p->low[1];
+  }
+  int row, col;
+  if (!gm_index_of_position(m, pos, &row, &col)) {      /* :91 getIndexOfPosition throws / :50 loop repeats */
+    for (int k = 0; k < 7; ++k) s[k] = NAN;
+    rc[0] = rc[1] = -1;
+    return;
+  }
+  rc[0] = row; rc[1] = col;
+  const size_t at = row + (size_t)col * m->rows;
+  double x = pos[0], y = pos[1], z = (double)m->elevation[at];                 /* :93-95 */
+  const double nw[3] = {(double)m->normal_x[at], (double)m->normal_y[at], (double)m->normal_z[at]};   /* :98 */
+  const float sd = m->plane_fit_std_dev[at];                                    /* :100 */
+  const double pert = ((2.0 * u[2] + -1.0) * (double)(sd < 0.5f ? sd : 0.5f)) * p->reach_z;   /* :103 */
+  x += nw[0] * pert; y += nw[1] * pert; z += nw[2] * pert;                      /* :105-107 */
+  /* RNG::eulerRPY (OMPL 1.4.2 RandomNumbers.cpp) */
+  const double pi = 3.14159265358979323846;
+  double v0 = pi * (-2.0 * u[3] + 1.0);
+  double v1 = acos(1.0 - 2.0 * u[4]) - pi / 2.0;
+  const double v2 = pi * (-2.0 * u[5] + 1.0);
+  /* Quaterniond(AngleAxisd(yaw, UnitZ)).inverse() * normal_w   (:118-121; Eigen Quaternion.h) */
+  const double ha = 0.5 * v2, sn = sin(ha), cs = cos(ha);
+  const double q[4] = {sn * 0.0, sn * 0.0, sn * 1.0, cs};                       /* x y z w */
+  const double n2 = (q[0] * q[0] + q[2] * q[2]) + (q[1] * q[1] + q[3] * q[3]);  /* squaredNorm, 2-wide packets */
+  const double qi[3] = {-q[0] / n2, -q[1] / n2, -q[2] / n2}, qw = q[3] / n2;
+  double uv[3], t2[3], nb[3];
+  cross3d(qi, nw, uv);
+  uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+  cross3d(qi, uv, t2);
+  for (int k = 0; k < 3; ++k) nb[k] = (nw[k] + qw * uv[k]) + t2[k];
+  v0 = -atan2(nb[1], nb[2]) + v0 * p->max_roll_pert / M_PI_2;                   /* :123-124 */
+  v1 = atan2(nb[0], nb[2]) + v1 * p->max_pitch_pert / M_PI_4;                   /* :125-126 */
+  /* setSO3FromRPY, utils.h:101-115 */
+  const double r2 = v0 * 0.5, p2 = v1 * 0.5, y2 = v2 * 0.5;
+  const double cr = cos(r2), cp = cos(p2), cy = cos(y2), sr = sin(r2), sp = sin(p2), sy = sin(y2);
+  s[0] = x; s[1] = y; s[2] = z;
+  s[6] = cy * cp * cr + sy * sp * sr;
+  s[3] = cy * cp * sr - sy * sp * cr;
+  s[4] = sy * cp * sr + cy * sp * cr;
+  s[5] = sy * cp * cr - cy * sp * sr;
+}
+
+int orc_sample_states(const orc_sampler_map* m, const orc_sampler_params* p, const double* u, size_t n, double* states,
+                      int32_t* rowcol) {
+  if (!m || !p || (p->sample_from_distribution && (!m->cum_prob || !m->cum_prob_rowwise))) return 1;
+  for (size_t i = 0; i < n; ++i) {
+    int32_t rc[2];
+    sample_one(m, p, u + 6 * i, states + 7 * i, rc);
+    if (rowcol) { rowcol[2 * i] = rc[0]; rowcol[2 * i + 1] = rc[1]; }
+  }
+  return 0;
+}
+
 int orc_path_length_cost(orc_handle* h, const double* s1, const double* s2, size_t n, double* cost) {
   if (!h) return 1;
   for (size_t i = 0; i < n; ++i) cost[i] = orc_path_length(&h->p, s1 + 7 * i, s2 + 7 * i);

@@ -63,6 +63,43 @@ int orc_check_poses(orc_handle* h, const double* states, size_t n, uint8_t* vali
 int orc_check_motions(orc_handle* h, const double* s1, const double* s2, size_t n, int n_steps,
                       uint8_t* valid, uint32_t* zone_verts);
 
+/* PRMMotionCost::addValidMilestone's edge interpolation (prm_motion_cost.cpp:341-372): edge e has n_interp[e] interior
+ * states at t = step * (1.0 / (n_interp[e] + 1)), step = 1..n_interp[e]; valid_prefix[e] = number of leading interior
+ * states that are valid (the loop stops at the first invalid one). n_interp == NULL: computed as
+ * (unsigned)(lateralDistance(s1, s2) / max_lateral) like :341-343. */
+int orc_check_edge_interiors(orc_handle* h, const double* s1, const double* s2, size_t n, const int32_t* n_interp,
+                             double max_lateral, int32_t* valid_prefix);
+
+/* ---- SE3FromSE2Sampler::sampleUniform (art_planner/src/sampler.cpp:40-131), liborc_port.so only ------------------
+ * A deterministic restatement: the reference draws its uniforms from OMPL's RNG (std::mt19937, not in the tree); here
+ * the six uniform01 variates one sample consumes are INPUTS, in the order the reference draws them:
+ *   sample_from_distribution:  u0 = samp_col, u1 = samp_row (sampler.cpp:56-57), u2 -> uniformReal(-1,1) (:103),
+ *                              u3,u4,u5 -> RNG::eulerRPY roll, pitch, yaw (:114; OMPL 1.4.2 RandomNumbers.cpp)
+ *   otherwise:                 u0 -> x, u1 -> y in [low, high] (RealVectorStateSampler::sampleUniform; its z draw is
+ *                              overwritten at :97 and is not an input), one attempt of the :46-50 loop; a position
+ *                              outside the map makes the sample "rejected" (rowcol = -1, state = NaN) -- the reference
+ *                              simply draws again, which leaves the distribution of accepted samples unchanged.
+ * Layers are grid_map matrices (column-major rows x cols). grid_map / Eigen / OMPL are not in the reference tree:
+ * parity unpinned at this level (restated from their published sources). */
+typedef struct orc_sampler_map {
+  const float *elevation, *normal_x, *normal_y, *normal_z, *plane_fit_std_dev;
+  const float *cum_prob;           /* "cum_prob" layer (probability_distribution.cpp:20-46); NULL in uniform mode */
+  const float *cum_prob_rowwise;   /* column 0 of "cum_prob_rowwise_hack": rows floats */
+  int rows, cols;
+  double res, cx, cy;
+} orc_sampler_map;
+
+typedef struct orc_sampler_params {
+  double max_roll_pert, max_pitch_pert;   /* params.h:79-80 (radians) */
+  int sample_from_distribution;           /* params.h:81 */
+  double low[2], high[2];                 /* SE3 position bounds x, y (planner.cpp:148-160) */
+  double reach_z;                         /* robot.feet.reach.z (sampler.cpp:103) */
+} orc_sampler_params;
+
+/* u: n x 6 doubles in [0,1); states: n x 7 doubles; rowcol (nullable): n x 2 ints (sampled cell, -1 if rejected). */
+int orc_sample_states(const orc_sampler_map* m, const orc_sampler_params* p, const double* u, size_t n, double* states,
+                      int32_t* rowcol);
+
 /* PathLengthObjective::motionCost (path_length_objective.cpp:26-70). */
 int orc_path_length_cost(orc_handle* h, const double* s1, const double* s2, size_t n, double* cost);
 

@@ -135,6 +135,26 @@ static inline void orc_se3_interpolate(const double a[7], const double b[7], dou
   }
 }
 
+/* lateralDistance (utils.h:52-61) and the interior-state count of addValidMilestone (prm_motion_cost.cpp:341-343). */
+static inline int32_t orc_n_interp(const double a[7], const double b[7], double max_lateral) {
+  const double dx = b[0] - a[0], dy = b[1] - a[1];
+  return (int32_t)(unsigned int)(sqrt(dx * dx + dy * dy) / max_lateral);
+}
+
+/* prm_motion_cost.cpp:345-372: leading valid interior states of one edge. */
+static inline int32_t orc_edge_interior_prefix(const orc_params* p, const orc_geom* g, orc_collide_fn collide, void* ctx,
+                                               const double a[7], const double b[7], int32_t n_interp) {
+  const double n_interp_div = 1.0 / (n_interp + 1);
+  int32_t k = 0;
+  for (int32_t step = 1; step < n_interp + 1; ++step) {
+    double st[7];
+    orc_se3_interpolate(a, b, step * n_interp_div, st);
+    if (!orc_state_valid(p, g, collide, ctx, st, NULL)) break;
+    ++k;
+  }
+  return k;
+}
+
 /* getYawFromSO3 (utils.h:80-88): atan2 in double, returned through `Scalar` = float. */
 static inline double orc_yaw_from_quat(const double s[7]) {
   const double x = s[3], y = s[4], z = s[5], w = s[6];

@@ -64,6 +64,15 @@ def main() -> None:
         out[name + "/cost"] = c
         out[name + "/sha"] = np.array(digest(m.elevation, m.elevation_masked, s1, s2))
         print(f"{name}: valid={int(v.sum())}/{n}")
+    for name, mk, pk, n, seed, dmin, dmax in cases.INTERIOR_CASES:
+        m = maps[mk]
+        o = Oracle(cases.PARAMS[pk], "reference")
+        o.set_map(m)
+        s1, s2 = synth.make_edges(m, n, seed, dmin=dmin, dmax=dmax)
+        k = o.check_edge_interiors(s1, s2, None, 0.5)
+        out[name + "/prefix"] = k.astype(np.int8)
+        out[name + "/sha"] = np.array(digest(m.elevation, m.elevation_masked, s1, s2))
+        print(f"{name}: prefix histogram {np.bincount(k).tolist()}")
     path = os.path.join(ROOT, "tests", "golden", "reference_masks.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -63,6 +63,7 @@ class Oracle:
         lib.orc_check_motions.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                                           C.c_void_p, C.c_void_p]
         lib.orc_path_length_cost.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.orc_check_edge_interiors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_double, C.c_void_p]
         lib.orc_check_poses_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
         lib.orc_kind.restype = C.c_char_p
         p = OrcParams()
@@ -128,6 +129,16 @@ class Oracle:
                                         valid.ctypes.data, zv.ctypes.data)
         assert rc == 0
         return (valid, zv) if want_zone else valid
+
+    def check_edge_interiors(self, s1, s2, n_interp=None, max_lateral=0.5):
+        a, b = _f64(s1), _f64(s2)
+        n = a.shape[0]
+        out = np.zeros(n, np.int32)
+        ni = None if n_interp is None else np.ascontiguousarray(n_interp, dtype=np.int32)
+        rc = self.lib.orc_check_edge_interiors(self.h, a.ctypes.data, b.ctypes.data, n,
+                                               None if ni is None else ni.ctypes.data, float(max_lateral), out.ctypes.data)
+        assert rc == 0
+        return out
 
     def path_length_cost(self, s1, s2):
         a, b = _f64(s1), _f64(s2)

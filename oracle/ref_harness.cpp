@@ -183,6 +183,16 @@ int orc_check_motions(orc_handle* h, const double* s1, const double* s2, size_t 
   return 0;
 }
 
+int orc_check_edge_interiors(orc_handle* h, const double* s1, const double* s2, size_t n, const int32_t* n_interp,
+                             double max_lateral, int32_t* valid_prefix) {
+  if (!h || !h->g.has_map) return 1;
+  for (size_t i = 0; i < n; ++i) {
+    const int32_t ni = n_interp ? n_interp[i] : orc_n_interp(s1 + 7 * i, s2 + 7 * i, max_lateral);
+    valid_prefix[i] = orc_edge_interior_prefix(&h->p, &h->g, ref_collide, h->pair, s1 + 7 * i, s2 + 7 * i, ni);
+  }
+  return 0;
+}
+
 int orc_path_length_cost(orc_handle* h, const double* s1, const double* s2, size_t n, double* cost) {
   if (!h) return 1;
   for (size_t i = 0; i < n; ++i) cost[i] = orc_path_length(&h->p, s1 + 7 * i, s2 + 7 * i);

@@ -107,6 +107,13 @@ BOX_CASES = [
 BOX_N = 20000
 
 # (name, map, params, n_edges, n_steps, seed)
+# addValidMilestone connection batches (prm_motion_cost.cpp:341-372): (name, map, params, n, seed, dmin, dmax);
+# n_interp = (unsigned)(lateralDistance / 0.5) per edge -> 0..6 interior states here
+INTERIOR_CASES = [
+    ("interior_fbm_rough_yaml", "fbm_rough", "yaml", 4000, 21, 0.05, 3.4),
+    ("interior_fixture_header", "fixture", "header", 3000, 22, 0.05, 2.0),
+]
+
 EDGE_CASES = [
     ("edges_fbm_rough_yaml", "fbm_rough", "yaml", 3000, 20, 4),
     ("edges_fixture_header", "fixture", "header", 3000, 7, 5),

@@ -59,9 +59,19 @@ int main(int argc, char** argv) {
   PathLengthObjective plo(checker);
   std::vector<double> cost;
   plo.motionCostBatch(s1, s2, &cost);
+  std::vector<int32_t> n_interp, prefix;
+  mv.checkEdgeInteriors(s1, s2, 0.5, &n_interp, &prefix);                    // prm_motion_cost.cpp:341-372
+  size_t cursor = 0;                                                          // "sampler": replays the pose file in order
+  std::vector<State> sampled;
+  const uint64_t drawn = checker->sampleValidBatch([&](State* st) { *st = poses[cursor++ % poses.size()]; },
+                                                   /*n_wanted=*/100, /*batch=*/64, /*max_draws=*/poses.size(), &sampled);
+  const uint64_t n_sampled = sampled.size();
   std::ofstream out(argv[2], std::ios::binary);
   wr(out, valid.data(), valid.size()); wr(out, single.data(), single.size());
   wr(out, motion.data(), motion.size()); wr(out, motion1.data(), motion1.size()); wr(out, cost.data(), cost.size());
+  wr(out, n_interp.data(), n_interp.size()); wr(out, prefix.data(), prefix.size());
+  wr(out, &drawn, 1); wr(out, &n_sampled, 1);
+  if (n_sampled) wr(out, &sampled[0].x, 7 * n_sampled);
   std::cout << "ok " << valid.size() << " poses, " << motion.size() << " edges\n";
   return 0;
 }

@@ -62,7 +62,11 @@ def test_host_mirror_matches_oracle(exe, preset, mk, maps, port_lib, tmp_path):
     single = np.frombuffer(raw, np.uint8, 16, o); o += 16
     motion = np.frombuffer(raw, np.uint8, len(s1), o); o += len(s1)
     motion1 = np.frombuffer(raw, np.uint8, 8, o); o += 8
-    cost = np.frombuffer(raw, np.float64, len(s1), o)
+    cost = np.frombuffer(raw, np.float64, len(s1), o); o += 8 * len(s1)
+    n_interp = np.frombuffer(raw, np.int32, len(s1), o); o += 4 * len(s1)
+    prefix = np.frombuffer(raw, np.int32, len(s1), o); o += 4 * len(s1)
+    drawn, n_sampled = np.frombuffer(raw, np.uint64, 2, o); o += 16
+    sampled = np.frombuffer(raw, np.float64, 7 * int(n_sampled), o).reshape(-1, 7)
     orc = port_lib.Oracle(params, "port")
     orc.set_map(m)
     ref = orc.check_poses(poses)
@@ -71,3 +75,12 @@ def test_host_mirror_matches_oracle(exe, preset, mk, maps, port_lib, tmp_path):
     assert np.array_equal(motion, refm) and np.array_equal(motion1, refm[:8])
     refc = orc.path_length_cost(s1, s2)
     assert np.allclose(cost, refc, rtol=1e-12, atol=0)
+    # addValidMilestone connection loop and the batched rejection-sampling helper
+    d = np.sqrt((s2[:, 0] - s1[:, 0]) ** 2 + (s2[:, 1] - s1[:, 1]) ** 2)
+    assert np.array_equal(n_interp, (d / 0.5).astype(np.int32))
+    assert np.array_equal(prefix, orc.check_edge_interiors(s1, s2, None, 0.5))
+    want = poses[ref != 0][:100]
+    assert int(n_sampled) == len(want) and np.array_equal(sampled, want)
+    if len(want) == 100:
+        last = np.nonzero(ref)[0][99]
+        assert int(drawn) == min(len(poses), (last // 64 + 1) * 64)

@@ -78,3 +78,61 @@ def test_edges_device_buffers(maps, make_checker):
     dev = mv.checkMotionBatch(torch.from_numpy(s1).cuda(), torch.from_numpy(s2).cuda())
     torch.cuda.synchronize()
     assert np.array_equal(host, dev.cpu().numpy())
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["warp+group", "group-only"])
+@pytest.mark.parametrize("case", cases.INTERIOR_CASES, ids=[c[0] for c in cases.INTERIOR_CASES])
+def test_edge_interiors_bit_exact(case, mode, golden, maps, make_checker):
+    """addValidMilestone's connection loop (prm_motion_cost.cpp:341-372): leading valid interior states per edge."""
+    import torch
+    import art_planner_b200 as ap
+    name, mk, pk, n, seed, dmin, dmax = case
+    m = maps(mk)
+    chk = make_checker(pk, m)
+    chk.setMode(mode)
+    s1, s2 = synth.make_edges(m, n, seed, dmin=dmin, dmax=dmax)
+    ref = golden[name + "/prefix"].astype(np.int32)
+    mv = ap.MotionValidator(chk)
+    got, ni = mv.checkEdgeInteriors(s1, s2)                 # counts derived inside the library (n_interp == NULL)
+    assert np.array_equal(got, ref)
+    got2, _ = mv.checkEdgeInteriors(s1, s2, n_interp=ni)    # caller-provided counts
+    assert np.array_equal(got2, ref)
+    dev, ni_d = mv.checkEdgeInteriors(torch.from_numpy(s1).cuda(), torch.from_numpy(s2).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(ni_d.cpu().numpy(), ni)
+    assert np.array_equal(dev.cpu().numpy(), ref)
+    chk.setMode(0)
+
+
+def test_edge_interiors_against_per_state_checks(maps, make_checker, port_lib):
+    """Size-independent property: the prefix equals what isValidBatch says about the interpolated states (oracle
+    interpolation), on a batch larger than one 2^20-item round."""
+    import art_planner_b200 as ap
+    m = maps("fbm_rough")
+    chk = make_checker("yaml", m)
+    n = 400_000
+    s1, s2 = synth.make_edges(m, n, 5, dmin=0.05, dmax=3.4)
+    got, ni = ap.MotionValidator(chk).checkEdgeInteriors(s1, s2)
+    assert int(ni.sum()) > (1 << 20)
+    assert (got <= ni).all()
+    # edges with zero interior states are trivially valid connections
+    assert (got[ni == 0] == 0).all()
+    # cross-check a slice against the CPU oracle
+    o = port_lib.Oracle(cases.PARAMS["yaml"], "port")
+    o.set_map(m)
+    sl = slice(n - 3000, n)
+    assert np.array_equal(got[sl], o.check_edge_interiors(s1[sl], s2[sl], None, 0.5))
+
+
+def test_edge_interiors_empty_and_errors(maps, make_checker):
+    import art_planner_b200 as ap
+    m = maps("flat")
+    chk = make_checker("yaml", m)
+    mv = ap.MotionValidator(chk)
+    got, ni = mv.checkEdgeInteriors(np.zeros((0, 7)), np.zeros((0, 7)))
+    assert got.shape == (0,)
+    s1, s2 = synth.make_edges(m, 10, 3)
+    got, _ = mv.checkEdgeInteriors(s1, s2, n_interp=np.zeros(10, np.int32))
+    assert (got == 0).all()
+    with pytest.raises(RuntimeError):
+        mv.checkEdgeInteriors(s1, s2, n_interp=np.full(10, -1, np.int32))

@@ -61,6 +61,23 @@ def test_port_edges_match_reference_golden(case, golden, maps, port_lib):
     assert np.array_equal(o.path_length_cost(s1, s2), golden[name + "/cost"])
 
 
+@pytest.mark.parametrize("case", cases.INTERIOR_CASES, ids=[c[0] for c in cases.INTERIOR_CASES])
+def test_port_edge_interiors_match_reference_golden(case, golden, maps, port_lib):
+    name, mk, pk, n, seed, dmin, dmax = case
+    m = maps(mk)
+    o = port_lib.Oracle(cases.PARAMS[pk], "port")
+    o.set_map(m)
+    s1, s2 = synth.make_edges(m, n, seed, dmin=dmin, dmax=dmax)
+    assert digest(m.elevation, m.elevation_masked, s1, s2) == str(golden[name + "/sha"])
+    ref = golden[name + "/prefix"].astype(np.int32)
+    assert np.array_equal(o.check_edge_interiors(s1, s2, None, 0.5), ref)
+    # explicit counts give the same answer, and the prefix is consistent with per-state validity
+    d = np.sqrt((s2[:, 0] - s1[:, 0]) ** 2 + (s2[:, 1] - s1[:, 1]) ** 2)
+    ni = (d / 0.5).astype(np.int32)
+    assert np.array_equal(o.check_edge_interiors(s1, s2, ni, 0.5), ref)
+    assert (ref <= ni).all() and (ref < ni).any() and (ref == ni).any()
+
+
 def test_edge_with_zero_steps_is_endpoint_check(maps, port_lib):
     m = maps("fixture")
     o = port_lib.Oracle(cases.PARAMS["yaml"], "port")

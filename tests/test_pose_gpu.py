@@ -142,3 +142,24 @@ def test_full_size_properties_c2(checkers):
     sel = np.arange(0, n, 50)
     assert np.array_equal(a.cpu().numpy()[sel], o.check_poses(poses[sel]))
     assert 0.05 < float(a.float().mean()) < 0.95
+
+
+def test_batched_rejection_sampling(maps, checkers, port_lib):
+    """sampleValidBatch keeps exactly the valid candidates, in draw order (rejection loop, prm_motion_cost.cpp:171-194)."""
+    m = maps("fbm_rough")
+    chk = checkers("yaml")
+    set_map(chk, m)
+    pool = synth.make_terrain_poses(m, 6000, seed=99)
+    cur = [0]
+
+    def sampler(k):
+        out = pool[cur[0]:cur[0] + k]
+        cur[0] += k
+        return out
+    got, drawn = chk.sampleValidBatch(sampler, 500, batch=512, max_draws=len(pool))
+    o = port_lib.Oracle(cases.PARAMS["yaml"], "port")
+    o.set_map(m)
+    ref = o.check_poses(pool)
+    want = pool[ref != 0][:500]
+    assert np.array_equal(got, want)
+    assert drawn % 512 == 0 or drawn == len(pool)
