@@ -29,6 +29,11 @@ class ArtpParams(C.Structure):
         ("risk_threshold", C.c_float), ("device", C.c_int)]
 
 
+class ArtpSamplerParams(C.Structure):
+    _fields_ = [("max_roll_pert", C.c_double), ("max_pitch_pert", C.c_double), ("sample_from_distribution", C.c_int),
+                ("low", C.c_double * 2), ("high", C.c_double * 2)]
+
+
 class ArtpStats(C.Structure):
     _fields_ = [("poses_checked", C.c_uint64), ("poses_deferred", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("last_deferred", C.c_uint32), ("last_launches", C.c_uint32), ("last_queued_boxes", C.c_uint32)]
@@ -61,6 +66,13 @@ def load():
     lib.artp_check_motions_device.argtypes = [vp, vp, vp, sz, i32, vp, vp]
     lib.artp_check_edge_interiors.argtypes = [vp, vp, vp, sz, vp, C.c_double, vp]
     lib.artp_check_edge_interiors_device.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, vp]
+    u64 = C.c_uint64
+    lib.artp_set_sampler.argtypes = [vp, C.POINTER(ArtpSamplerParams), vp, vp, vp, vp, vp, vp]
+    lib.artp_sampler_uniforms.argtypes = [vp, u64, u64, sz, vp]
+    lib.artp_sample_states.argtypes = [vp, vp, u64, u64, sz, vp, vp]
+    lib.artp_sample_states_device.argtypes = [vp, vp, u64, u64, sz, vp, vp, vp]
+    lib.artp_sample_valid.argtypes = [vp, u64, u64, sz, vp, sz, C.POINTER(C.c_size_t)]
+    lib.artp_sample_valid_device.argtypes = [vp, u64, u64, sz, vp, sz, vp, vp]
     lib.artp_path_length_cost.argtypes = [vp, vp, vp, sz, vp]
     lib.artp_path_length_cost_device.argtypes = [vp, vp, vp, sz, vp, vp]
     lib.artp_compact_valid_device.argtypes = [vp, vp, sz, C.c_int64, vp, vp, vp]

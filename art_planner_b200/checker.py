@@ -170,6 +170,81 @@ class StateValidityChecker:
         return self._h
 
 
+class SE3FromSE2Sampler:
+    """art_planner::SE3FromSE2Sampler::sampleUniform (src/sampler.cpp:82-131) on the device, plus the fused
+    sample -> isValid -> compact form of the rejection loops around it (prm_motion_cost.cpp:171-194).
+
+    `layers` carries normal_x/y/z, plane_fit_std_dev, cum_prob, cum_prob_rowwise (grid_map matrices);
+    `sp` the sampler parameters (max_roll_pert, max_pitch_pert, sample_from_distribution, low, high).
+    Must be re-created / setLayers() again after every setMap on the checker."""
+
+    def __init__(self, checker: StateValidityChecker, layers, sp, seed: int = 0):
+        self._c = checker
+        self.seed = int(seed)
+        self._next = 0
+        self.setLayers(layers, sp)
+
+    def setLayers(self, layers, sp) -> None:
+        h, lib = self._c.handle, self._c.handle.lib
+        f = lambda a: None if a is None else np.asfortranarray(a, dtype=np.float32)
+        keep = [f(layers.normal_x), f(layers.normal_y), f(layers.normal_z), f(layers.plane_fit_std_dev),
+                f(getattr(layers, "cum_prob", None)),
+                None if getattr(layers, "cum_prob_rowwise", None) is None
+                else np.ascontiguousarray(layers.cum_prob_rowwise, dtype=np.float32)]
+        p = capi.ArtpSamplerParams(float(sp.max_roll_pert), float(sp.max_pitch_pert), int(sp.sample_from_distribution),
+                                   (C.c_double * 2)(*sp.low), (C.c_double * 2)(*sp.high))
+        h.check(lib.artp_set_sampler(h.h, C.byref(p), *[None if a is None else a.ctypes.data for a in keep]))
+
+    def uniforms(self, first: int, n: int) -> np.ndarray:
+        """The [n, 6] uniform01 variates of samples first..first+n-1 of this sampler's Philox stream."""
+        h, lib = self._c.handle, self._c.handle.lib
+        u = np.empty((n, 6), np.float64)
+        h.check(lib.artp_sampler_uniforms(h.h, self.seed, int(first), n, u.ctypes.data))
+        return u
+
+    def sampleUniformBatch(self, n: int, u=None, first=None, want_cells: bool = False):
+        """n candidates [n, 7]. u: optional [n, 6] variates (else the Philox stream from `first`, default: continue)."""
+        h, lib = self._c.handle, self._c.handle.lib
+        if first is None:
+            first = self._next
+            if u is None:
+                self._next += n
+        states = np.empty((n, 7), np.float64)
+        rc = np.empty((n, 2), np.int32) if want_cells else None
+        uu = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
+        assert uu is None or uu.shape == (n, 6)
+        h.check(lib.artp_sample_states(h.h, None if uu is None else uu.ctypes.data, self.seed, int(first), n,
+                                       states.ctypes.data, None if rc is None else rc.ctypes.data))
+        return (states, rc) if want_cells else states
+
+    def sampleUniform(self) -> np.ndarray:
+        return self.sampleUniformBatch(1)[0]
+
+    def sampleValidBatch(self, n_draw: int, first=None, capacity=None, out=None):
+        """Draw n_draw candidates on the device, check them, return (valid states in draw order, n_valid).
+        out: optional reusable [cap, 7] float64 host buffer (numpy array or pinned CPU torch tensor); a fresh
+        58 MB numpy array per 2^20 draws costs more in page faults than the whole GPU pass."""
+        h, lib = self._c.handle, self._c.handle.lib
+        if first is None:
+            first = self._next
+            self._next += n_draw
+        if out is None:
+            cap = n_draw if capacity is None else int(capacity)
+            out = np.empty((cap, 7), np.float64)
+        else:
+            cap = out.shape[0] if capacity is None else min(int(capacity), out.shape[0])
+        ptr = out.ctypes.data if isinstance(out, np.ndarray) else out.data_ptr()
+        nv = C.c_size_t(0)
+        h.check(lib.artp_sample_valid(h.h, self.seed, int(first), n_draw, C.c_void_p(ptr), cap, C.byref(nv)))
+        return out[: min(nv.value, cap)], nv.value
+
+    def sampleValidDevice(self, n_draw: int, first: int, out, count):
+        """Device buffers: out = CUDA float64 [cap, 7], count = CUDA int32 [1]; asynchronous on the current stream."""
+        h, lib = self._c.handle, self._c.handle.lib
+        h.check(lib.artp_sample_valid_device(h.h, self.seed, int(first), n_draw, C.c_void_p(out.data_ptr()), out.shape[0],
+                                             C.c_void_p(count.data_ptr()), _stream_ptr()))
+
+
 class MotionValidator:
     """Discrete motion validation over StateValidityChecker (OMPL DiscreteMotionValidator semantics with a fixed
     segment count): valid(s2) and valid(interpolate(s1, s2, j/(n_steps+1))) for j = 1..n_steps."""

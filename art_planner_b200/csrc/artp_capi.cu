@@ -16,6 +16,7 @@
 #include "../../include/artp.h"
 #include "artp_cnn.h"
 #include "artp_kernels.cuh"
+#include "artp_sampler.cuh"
 
 namespace {
 
@@ -49,6 +50,13 @@ struct Handle {
   int mode = 0;
   artp_cnn::State* cnn = nullptr;
   int cnn_mode = 0;
+  // sampler (artp_set_sampler): device copies of the per-cell layers, scratch of the fused sample->check->compact path
+  artp::SamplerDev samp{};
+  float* d_samp_layers = nullptr;   // normal_x | normal_y | normal_z | std_dev | cum_prob | cum_row
+  size_t samp_layers_cap = 0;
+  bool has_sampler = false;
+  void* d_samp_scratch = nullptr;
+  size_t samp_scratch_cap = 0;
   int timing = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
@@ -365,7 +373,7 @@ void artp_destroy(artp_handle* hh) {
   for (int i = 0; i < kCopyEvents; ++i) if (h->copy_ev[i]) cudaEventDestroy(h->copy_ev[i]);
   for (int k = 0; k < 2; ++k) for (int l = 0; l <= artp::kMaxLevel; ++l) { cudaFree(h->d_T[k][l]); cudaFree(h->d_NF[k][l]); }
   cudaFree(h->d_H[0]); cudaFree(h->d_H[1]); cudaFree(h->d_ctr); cudaFree(h->d_defer); cudaFree(h->d_stage);
-  cudaFree(h->d_block_counts); cudaFree(h->d_recs);
+  cudaFree(h->d_block_counts); cudaFree(h->d_recs); cudaFree(h->d_samp_layers); cudaFree(h->d_samp_scratch);
   artp_cnn::destroy(h->cnn);
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
@@ -502,6 +510,7 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
   h->chk.Lx = Lx; h->chk.Ly = Ly; h->chk.cx = cx; h->chk.cy = cy;
   h->chk.cell_margin = 0.02f + 2e-6f * (float)std::max(rows, cols);
   h->has_map = true;
+  h->has_sampler = false;      // its layers belong to the previous map
   return ARTP_OK;
 }
 
@@ -779,14 +788,8 @@ int artp_path_length_cost(artp_handle* hh, const double* s1, const double* s2, s
   return ARTP_OK;
 }
 
-int artp_compact_valid_device(artp_handle* hh, const uint8_t* d_valid, size_t n, int64_t base, int64_t* d_indices,
-                              uint32_t* d_count, void* stream) {
-  if (!hh) return ARTP_E_INVALID;
-  Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
-  if (!d_valid || !d_indices || !d_count) { h->err = "null buffer"; return ARTP_E_INVALID; }
-  CU_TRY(h, cudaSetDevice(h->device));
-  cudaStream_t s = (cudaStream_t)stream;
+static int compact_valid_impl(Handle* h, const uint8_t* d_valid, size_t n, int64_t base, int64_t* d_indices,
+                              uint32_t* d_count, cudaStream_t s) {
   if (n == 0) { CU_TRY(h, cudaMemsetAsync(d_count, 0, sizeof(uint32_t), s)); return ARTP_OK; }
   const size_t nb = (n + kCompactBlock - 1) / kCompactBlock;
   if (h->block_counts_cap < nb) {
@@ -802,6 +805,260 @@ int artp_compact_valid_device(artp_handle* hh, const uint8_t* d_valid, size_t n,
   CU_TRY(h, cudaGetLastError());
   h->stats.kernel_launches += 3;
   h->stats.last_launches = 3;
+  return ARTP_OK;
+}
+
+int artp_compact_valid_device(artp_handle* hh, const uint8_t* d_valid, size_t n, int64_t base, int64_t* d_indices,
+                              uint32_t* d_count, void* stream) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (!d_valid || !d_indices || !d_count) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  return compact_valid_impl(h, d_valid, n, base, d_indices, d_count, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sampler: SE3FromSE2Sampler::sampleUniform on the device (artp_sampler.cuh)
+// ---------------------------------------------------------------------------------------------------------------
+int artp_set_sampler(artp_handle* hh, const artp_sampler_params* sp, const float* normal_x, const float* normal_y,
+                     const float* normal_z, const float* plane_fit_std_dev, const float* cum_prob,
+                     const float* cum_prob_rowwise) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
+  if (!sp || !normal_x || !normal_y || !normal_z || !plane_fit_std_dev) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  if (sp->sample_from_distribution && (!cum_prob || !cum_prob_rowwise)) {
+    h->err = "sample_from_distribution needs the cum_prob layers"; return ARTP_E_INVALID;
+  }
+  if (!sp->sample_from_distribution && !(sp->high[0] > sp->low[0] && sp->high[1] > sp->low[1])) {
+    h->err = "empty sampling bounds"; return ARTP_E_INVALID;
+  }
+  CU_TRY(h, cudaSetDevice(h->device));
+  const size_t ncell = (size_t)h->rows * h->cols;
+  const size_t need = (5 * ncell + (size_t)h->rows + 64) * sizeof(float);
+  if (h->samp_layers_cap < need) {
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_samp_layers);
+    h->d_samp_layers = nullptr; h->samp_layers_cap = 0;
+    CU_TRY(h, cudaMalloc(&h->d_samp_layers, need));
+    h->samp_layers_cap = need;
+  }
+  float* base = h->d_samp_layers;
+  const float* src[4] = {normal_x, normal_y, normal_z, plane_fit_std_dev};
+  for (int k = 0; k < 4; ++k)
+    CU_TRY(h, cudaMemcpyAsync(base + k * ncell, src[k], ncell * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  artp::SamplerDev& m = h->samp;
+  m.elevation_rev = h->d_H[0]; m.pitch = h->pitch;
+  m.normal_x = base; m.normal_y = base + ncell; m.normal_z = base + 2 * ncell; m.std_dev = base + 3 * ncell;
+  m.cum_prob = nullptr; m.cum_row = nullptr;
+  m.rows = h->rows; m.cols = h->cols;
+  m.res = h->chk.Lx / h->rows; m.cx = h->chk.cx; m.cy = h->chk.cy;
+  m.max_roll_pert = sp->max_roll_pert; m.max_pitch_pert = sp->max_pitch_pert;
+  m.from_distribution = sp->sample_from_distribution ? 1 : 0;
+  m.low[0] = sp->low[0]; m.low[1] = sp->low[1]; m.high[0] = sp->high[0]; m.high[1] = sp->high[1];
+  m.reach_z = h->p.reach_z;
+  if (m.from_distribution) {
+    CU_TRY(h, cudaMemcpyAsync(base + 4 * ncell, cum_prob, ncell * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(base + 5 * ncell, cum_prob_rowwise, (size_t)h->rows * sizeof(float), cudaMemcpyHostToDevice,
+                              h->stream));
+    m.cum_prob = base + 4 * ncell; m.cum_row = base + 5 * ncell;
+    // the binary searches need monotone (or all-NaN) CDF rows: refuse anything else
+    CU_TRY(h, cudaMemsetAsync(h->d_ctr + 3, 0, sizeof(uint32_t), h->stream));
+    artp::validate_cdf_kernel<<<(h->rows + 127) / 128, 128, 0, h->stream>>>(m.cum_prob, h->rows, h->cols, (size_t)h->rows, 1,
+                                                                             h->d_ctr + 3);
+    artp::validate_cdf_kernel<<<1, 32, 0, h->stream>>>(m.cum_row, 1, h->rows, 1, 0, h->d_ctr + 3);
+    CU_TRY(h, cudaGetLastError());
+    uint32_t bad = 0;
+    CU_TRY(h, cudaMemcpyAsync(&bad, h->d_ctr + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->stats.kernel_launches += 2;
+    if (bad) { h->err = "cum_prob layers are not cumulative distributions (rows must be non-decreasing or all NaN)"; return ARTP_E_INVALID; }
+  } else {
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  h->has_sampler = true;
+  return ARTP_OK;
+}
+
+static int sampler_ready(Handle* h) {
+  if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
+  if (!h->has_sampler) { h->err = "no sampler layers set (artp_set_sampler after artp_set_map)"; return ARTP_E_NOMAP; }
+  return ARTP_OK;
+}
+
+static inline unsigned grid_for(Handle* h, size_t n, int block) {
+  return (unsigned)std::min<size_t>((n + block - 1) / block, (size_t)h->sm_count * 16);
+}
+
+int artp_sampler_uniforms(artp_handle* hh, uint64_t seed, uint64_t first_sample, size_t n, double* u) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (n == 0) return ARTP_OK;
+  if (!u) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  int rc = ensure_stage(h, n * 6 * sizeof(double));
+  if (rc) return rc;
+  artp::sampler_uniforms_kernel<<<grid_for(h, n, 256), 256, 0, h->stream>>>(seed, first_sample, n, (double*)h->d_stage);
+  CU_TRY(h, cudaGetLastError());
+  CU_TRY(h, cudaMemcpyAsync(u, h->d_stage, n * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->stats.kernel_launches += 1;
+  return ARTP_OK;
+}
+
+int artp_sample_states_device(artp_handle* hh, const double* d_u, uint64_t seed, uint64_t first_sample, size_t n,
+                              double* d_states, int32_t* d_rowcol, void* stream) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  int rc = sampler_ready(h);
+  if (rc) return rc;
+  if (n == 0) return ARTP_OK;
+  if (!d_states) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  artp::sample_states_kernel<<<grid_for(h, n, 128), 128, 0, (cudaStream_t)stream>>>(h->samp, d_u, seed, first_sample, n, d_states,
+                                                                                   nullptr, d_rowcol);
+  CU_TRY(h, cudaGetLastError());
+  h->stats.kernel_launches += 1;
+  h->stats.last_launches = 1;
+  return ARTP_OK;
+}
+
+int artp_sample_states(artp_handle* hh, const double* u, uint64_t seed, uint64_t first_sample, size_t n, double* states,
+                       int32_t* rowcol) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  const size_t ub = (n * 6 * sizeof(double) + 255) & ~(size_t)255, sb = (n * 7 * sizeof(double) + 255) & ~(size_t)255;
+  {
+    std::lock_guard<std::mutex> lk(h->mtx);
+    int rc = sampler_ready(h);
+    if (rc) return rc;
+    if (n == 0) return ARTP_OK;
+    if (!states) { h->err = "null buffer"; return ARTP_E_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->device));
+    rc = ensure_stage(h, ub + sb + n * 2 * sizeof(int32_t));
+    if (rc) return rc;
+    if (u) CU_TRY(h, cudaMemcpyAsync(h->d_stage, u, n * 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  char* base = (char*)h->d_stage;
+  int rc = artp_sample_states_device(hh, u ? (const double*)base : nullptr, seed, first_sample, n, (double*)(base + ub),
+                                     rowcol ? (int32_t*)(base + ub + sb) : nullptr, h->stream);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(h->mtx);
+  CU_TRY(h, cudaMemcpyAsync(states, base + ub, n * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (rowcol) CU_TRY(h, cudaMemcpyAsync(rowcol, base + ub + sb, n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return ARTP_OK;
+}
+
+// running total += chunk count (device-side, stream ordered)
+__global__ void add_count_kernel(uint32_t* total, const uint32_t* chunk) { *total += *chunk; }
+
+// out + 7 * (*total) .. : ordered gather of this chunk's valid candidates behind the previous chunks'
+__global__ void gather_chunk_kernel(const double* __restrict__ states, const int64_t* __restrict__ idx,
+                                    const uint32_t* __restrict__ chunk_count, const uint32_t* __restrict__ total_before,
+                                    size_t capacity, double* __restrict__ out) {
+  const size_t before = *total_before;
+  const size_t room = capacity > before ? capacity - before : 0;
+  const size_t cc = *chunk_count;
+  const size_t keep = cc < room ? cc : room;
+  const size_t n = keep * 7;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t k = i / 7, c = i - k * 7;
+    out[before * 7 + i] = states[(size_t)idx[k] * 7 + c];
+  }
+}
+
+static constexpr size_t kSampleChunk = (size_t)1 << 21;
+
+int artp_sample_valid_device(artp_handle* hh, uint64_t seed, uint64_t first_sample, size_t n_draw, double* d_states_out,
+                             size_t capacity, uint32_t* d_count, void* stream) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  int rc = sampler_ready(h);
+  if (rc) return rc;
+  if (!d_count || (capacity && !d_states_out)) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CU_TRY(h, cudaMemsetAsync(d_count, 0, sizeof(uint32_t), s));
+  if (n_draw == 0) return ARTP_OK;
+  const size_t chunk = std::min(n_draw, kSampleChunk);
+  // scratch: states f64 | states f32 | indices | valid | chunk count
+  const size_t o_f32 = chunk * 7 * sizeof(double), o_idx = o_f32 + ((chunk * 7 * sizeof(float) + 255) & ~(size_t)255),
+               o_val = o_idx + chunk * sizeof(int64_t), o_cnt = o_val + ((chunk + 255) & ~(size_t)255), total = o_cnt + 256;
+  if (h->samp_scratch_cap < total) {
+    CU_TRY(h, cudaStreamSynchronize(s));
+    cudaFree(h->d_samp_scratch);
+    h->d_samp_scratch = nullptr; h->samp_scratch_cap = 0;
+    CU_TRY(h, cudaMalloc(&h->d_samp_scratch, total));
+    h->samp_scratch_cap = total;
+  }
+  char* sc = (char*)h->d_samp_scratch;
+  double* d_st = (double*)sc;
+  float* d_sf = (float*)(sc + o_f32);
+  int64_t* d_idx = (int64_t*)(sc + o_idx);
+  uint8_t* d_val = (uint8_t*)(sc + o_val);
+  uint32_t* d_cnt = (uint32_t*)(sc + o_cnt);
+  uint32_t launches = 0;
+  for (size_t done = 0; done < n_draw; done += chunk) {
+    const size_t m = std::min(chunk, n_draw - done);
+    artp::sample_states_kernel<<<grid_for(h, m, 128), 128, 0, s>>>(h->samp, nullptr, seed, first_sample + done, m, d_st, d_sf,
+                                                                   nullptr);
+    CU_TRY(h, cudaGetLastError());
+    artp::Work w;
+    w.s1 = nullptr; w.s2 = nullptr; w.s2f = d_sf; w.valid = d_val; w.item_base = 0; w.n_items = (uint32_t)m; w.steps = 0;
+    w.edge_mode = 0;
+    rc = run_items(h, w, s);
+    if (rc) return rc;
+    launches += h->stats.last_launches + 1;
+    if (!h->samp.from_distribution) {   // rejected (outside-map) candidates carry NaN states
+      artp::reject_nan_kernel<<<grid_for(h, m, 256), 256, 0, s>>>(d_st, m, d_val);
+      launches += 1;
+    }
+    rc = compact_valid_impl(h, d_val, m, 0, d_idx, d_cnt, s);
+    if (rc) return rc;
+    gather_chunk_kernel<<<grid_for(h, m * 7, 256), 256, 0, s>>>(d_st, d_idx, d_cnt, d_count, capacity, d_states_out);
+    add_count_kernel<<<1, 1, 0, s>>>(d_count, d_cnt);
+    CU_TRY(h, cudaGetLastError());
+    launches += 5;
+    h->stats.kernel_launches += 3 + (h->samp.from_distribution ? 0 : 1);
+    h->stats.poses_checked += m;
+  }
+  h->stats.last_launches = launches;
+  return ARTP_OK;
+}
+
+int artp_sample_valid(artp_handle* hh, uint64_t seed, uint64_t first_sample, size_t n_draw, double* states, size_t capacity,
+                      size_t* n_valid) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  const size_t cap = std::min(capacity, n_draw);
+  {
+    std::lock_guard<std::mutex> lk(h->mtx);
+    int rc = sampler_ready(h);
+    if (rc) return rc;
+    if (!n_valid || (cap && !states)) { h->err = "null buffer"; return ARTP_E_INVALID; }
+    CU_TRY(h, cudaSetDevice(h->device));
+    rc = ensure_stage(h, cap * 7 * sizeof(double) + 256);
+    if (rc) return rc;
+  }
+  uint32_t* d_count = (uint32_t*)((char*)h->d_stage + cap * 7 * sizeof(double));
+  int rc = artp_sample_valid_device(hh, seed, first_sample, n_draw, (double*)h->d_stage, cap, d_count, h->stream);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(h->mtx);
+  uint32_t cnt = 0;
+  CU_TRY(h, cudaMemcpyAsync(&cnt, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  const size_t keep = std::min<size_t>(cnt, cap);
+  if (keep) {
+    CU_TRY(h, cudaMemcpyAsync(states, h->d_stage, keep * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  *n_valid = cnt;      // > capacity means the output was truncated to `capacity` states
   return ARTP_OK;
 }
 

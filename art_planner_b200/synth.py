@@ -288,3 +288,71 @@ def make_edges(m: SynthMap, n: int, seed: int = 4, start: int = 0, dmin: float =
     y2 = np.clip(s1[:, 1] + d * np.sin(hd), m.cy - 0.4995 * ly, m.cy + 0.4995 * ly)
     s2 = make_terrain_poses(m, n, seed + 7919, start, xy=(x2, y2))
     return s1, s2
+
+
+# ---------------------------------------------------------------------------------------------
+# sampler inputs: the per-cell layers SE3FromSE2Sampler reads (sampler.cpp:54-131)
+# ---------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class SamplerLayers:
+    """grid_map layers (float32 [rows, cols], Fortran order) the reference's map pre-processing produces
+    (processors::Basic normals / plane-fit std-dev, probability_distribution.cpp:20-46 CDFs). Synthetic stand-ins."""
+    normal_x: np.ndarray
+    normal_y: np.ndarray
+    normal_z: np.ndarray
+    plane_fit_std_dev: np.ndarray
+    sample_probability: np.ndarray
+    cum_prob: np.ndarray
+    cum_prob_rowwise: np.ndarray        # column 0 of "cum_prob_rowwise_hack", [rows]
+
+
+def cumulative_distribution(prob: np.ndarray):
+    """computeCumulativeProbabilityDistribution (probability_distribution.cpp:20-46) on a float32 matrix: returns
+    (cum_prob [rows, cols] Fortran order, cum_prob_rowwise [rows]). Rows without probability mass become NaN rows,
+    exactly like the reference's 0/0 division."""
+    prob = np.asarray(prob, dtype=np.float32)
+    row_sum = prob.sum(axis=1, dtype=np.float32)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        rowwise = (row_sum / row_sum.sum(dtype=np.float32)).astype(np.float32)
+        cum = (prob / row_sum[:, None]).astype(np.float32)
+    return np.asfortranarray(np.cumsum(cum, axis=1, dtype=np.float32)), np.cumsum(rowwise, dtype=np.float32)
+
+
+def make_sampler_layers(m: SynthMap, seed: int = 7, empty_rows: bool = True) -> SamplerLayers:
+    """Normals from central differences of the elevation layer, a hashed plane-fit error in [0, 0.8] (so that the
+    min(std, 0.5) clamp of sampler.cpp:103 is exercised) and a blocky sample probability with dead regions."""
+    e = np.where(np.isfinite(m.elevation), m.elevation, 0.0).astype(np.float64)
+    # grid_map axes: row index grows towards -x, column index towards -y
+    gx = -np.gradient(e, m.res, axis=0)
+    gy = -np.gradient(e, m.res, axis=1)
+    nrm = np.sqrt(gx * gx + gy * gy + 1.0)
+    rows, cols = m.rows, m.cols
+    k = np.arange(rows * cols).reshape(rows, cols)
+    std = (0.8 * hash_uniform(seed, 31, k) ** 2).astype(np.float32)
+    blk = (np.arange(rows)[:, None] // 16) * 1024 + (np.arange(cols)[None, :] // 16)
+    prob = hash_uniform(seed, 32, blk)
+    prob = np.where(prob < 0.25, 0.0, prob) * (0.5 + 0.5 * hash_uniform(seed, 33, k))
+    if empty_rows:
+        prob[rows // 3: rows // 3 + 3, :] = 0.0          # rows without mass -> NaN CDF rows
+        prob[0, :] = 0.0
+        prob[rows - 1, :] = 0.0
+    prob = prob.astype(np.float32)
+    cum, cum_row = cumulative_distribution(prob)
+    f = lambda a: np.asfortranarray(a.astype(np.float32))
+    return SamplerLayers(f(-gx / nrm), f(-gy / nrm), f(1.0 / nrm), np.asfortranarray(std), np.asfortranarray(prob),
+                         cum, cum_row)
+
+
+@dataclasses.dataclass(frozen=True)
+class SamplerParams:
+    """params.h:79-81 plus the SE3 position bounds Planner::setMap installs (planner.cpp:148-160)."""
+    max_roll_pert: float = 3.33 / 180 * math.pi
+    max_pitch_pert: float = 10.0 / 180 * math.pi
+    sample_from_distribution: bool = True
+    low: tuple = (-1.0, -1.0)
+    high: tuple = (1.0, 1.0)
+
+
+def sampler_params_for(m: SynthMap, from_distribution: bool = True) -> SamplerParams:
+    lx, ly = m.length
+    return SamplerParams(sample_from_distribution=from_distribution, low=(m.cx - lx, m.cy - ly), high=(m.cx + lx, m.cy + ly))

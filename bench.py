@@ -293,6 +293,31 @@ def main():
             plo.motionCostBatch(d1, d2, out=c_out)
         bb.record(); torch.cuda.synchronize()
         secondary["path_length_cost"] = {"evals_per_s": 100_000 * 50 / (a.elapsed_time(bb) * 1e-3)}
+        try:   # device sampler + fused sample -> isValid -> compact (no host pose stream)
+            L = synth.make_sampler_layers(m, seed=7)
+            smp = apb.SE3FromSE2Sampler(chk, L, synth.sampler_params_for(m), seed=1)
+            nd = 1 << 20
+            s_out = torch.empty((nd, 7), dtype=torch.float64, device="cuda")
+            s_cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+            for _ in range(3):
+                smp.sampleValidDevice(nd, 0, s_out, s_cnt)
+            torch.cuda.synchronize(); a.record()
+            for it in range(20):
+                smp.sampleValidDevice(nd, it * nd, s_out, s_cnt)
+            bb.record(); torch.cuda.synchronize()
+            ms = a.elapsed_time(bb) / 20
+            h_out = torch.empty((nd, 7), dtype=torch.float64).pin_memory()
+            smp.sampleValidBatch(nd, first=0, out=h_out)
+            t0 = time.perf_counter()
+            for it in range(10):
+                hs, nv = smp.sampleValidBatch(nd, first=it * nd, out=h_out)
+            host_s = (time.perf_counter() - t0) / 10
+            secondary["fused_sample_check_compact"] = {
+                "workload": "2^20 candidates drawn from the map's sampling CDF on the device (Philox stream), checked, valid ones compacted in draw order",
+                "candidates_per_s_device": nd / (ms * 1e-3), "ms_per_batch": ms, "valid_fraction": nv / nd,
+                "candidates_per_s_host_api": nd / host_s, "d2h_bytes_per_batch": int(nv) * 56, "h2d_bytes_per_batch": 0}
+        except Exception as ex:
+            secondary["fused_sample_check_compact"] = {"error": repr(ex)}
         try:
             from art_planner_b200 import costnet
             m4 = synth.make_fbm_map(256, 256, MAP_RES, seed=MAP_SEED, amp=0.6)

@@ -22,6 +22,10 @@
  *                                   PRMMotionCost::addValidMilestone (prm_motion_cost.cpp:341-372)
  *   artp_check_edge_interiors[_device]  that same addValidMilestone loop with its exact semantics: per-edge
  *                                   interior-state counts, no endpoint check, stop at the first invalid state
+ *   artp_set_sampler, artp_sample_states[_device], artp_sample_valid[_device], artp_sampler_uniforms
+ *                                   ompl::base::StateSampler::sampleUniform -> SE3FromSE2Sampler::sampleUniform
+ *                                   (src/sampler.cpp:82-131, positions :40-77) and the rejection loops around it
+ *                                   (prm_motion_cost.cpp:171-194, lazy_prm_star_min_update.cpp:549-556)
  *   artp_path_length_cost[_device]  ompl::base::OptimizationObjective::motionCost ->
  *                                   PathLengthObjective::motionCost (objectives/path_length_objective.cpp:26-70)
  *   artp_set_cost_weights, artp_update_features, artp_motion_cost[_device]
@@ -112,6 +116,45 @@ int artp_check_edge_interiors(artp_handle* h, const double* s1, const double* s2
 int artp_check_edge_interiors_device(artp_handle* h, const double* d_s1, const double* d_s2, size_t n,
                                      const uint32_t* d_item_off, size_t total_items, uint8_t* d_item_valid,
                                      int32_t* d_valid_prefix, void* stream);
+
+/* ---- SE3FromSE2Sampler::sampleUniform (art_planner/src/sampler.cpp:40-131) on the device ------------------------
+ * candidates are generated where they are checked, so the rejection loops
+ * (prm_motion_cost.cpp:171-194, lazy_prm_star_min_update.cpp:549-556) need no host->device pose stream.
+ * One candidate consumes six uniform01 variates in the order the reference draws them:
+ *   sample_from_distribution:  u0 = samp_col, u1 = samp_row (:56-57), u2 -> uniformReal(-1,1) (:103),
+ *                              u3,u4,u5 -> RNG::eulerRPY roll, pitch, yaw (:114)
+ *   otherwise:                 u0 -> x, u1 -> y in [low, high]; a position outside the map is a rejected candidate
+ *                              (NaN state, rowcol -1, never valid) where the reference loop (:46-50) draws again.
+ * The variates are either caller-provided (u != NULL) or produced by the documented counter-based stream
+ * Philox4x32-10(key = seed, counter = (sample index, block 0..2, "ARTP")), see artp_sampler_uniforms(). */
+typedef struct artp_sampler_params {
+  double max_roll_pert, max_pitch_pert;   /* params.h:79-80, radians */
+  int    sample_from_distribution;        /* params.h:81 */
+  double low[2], high[2];                 /* SE3 position bounds x,y (planner.cpp:148-160); uniform mode only */
+} artp_sampler_params;
+
+/* Per-cell layers the sampler reads, HOST pointers in grid_map layout (like artp_set_map, which must come first and
+ * provides "elevation" and the geometry): normal_x/y/z, plane_fit_std_dev (Map::getNormal / getPlaneFitStdDev,
+ * map.h:94-116), "cum_prob" and column 0 of "cum_prob_rowwise_hack" (probability_distribution.cpp:20-46; may be NULL
+ * when !sample_from_distribution). CDF rows must be non-decreasing or all NaN (else ARTP_E_INVALID).
+ * artp_set_map invalidates the sampler layers. */
+int artp_set_sampler(artp_handle* h, const artp_sampler_params* sp, const float* normal_x, const float* normal_y,
+                     const float* normal_z, const float* plane_fit_std_dev, const float* cum_prob,
+                     const float* cum_prob_rowwise);
+/* The variates of samples first_sample .. first_sample+n-1 under `seed`: u[n][6] (host). */
+int artp_sampler_uniforms(artp_handle* h, uint64_t seed, uint64_t first_sample, size_t n, double* u);
+/* n candidates -> states[n][7] (x y z qx qy qz qw), rowcol[n][2] (sampled cell; nullable). u == NULL: Philox stream. */
+int artp_sample_states(artp_handle* h, const double* u, uint64_t seed, uint64_t first_sample, size_t n, double* states,
+                       int32_t* rowcol);
+int artp_sample_states_device(artp_handle* h, const double* d_u, uint64_t seed, uint64_t first_sample, size_t n,
+                              double* d_states, int32_t* d_rowcol, void* stream);
+/* Fused sample -> isValid -> ordered compaction: draws candidates first_sample .. first_sample+n_draw-1 of the Philox
+ * stream and writes the valid ones, in draw order, to states (at most `capacity`); *n_valid / *d_count = number of
+ * valid candidates (> capacity: output truncated). */
+int artp_sample_valid(artp_handle* h, uint64_t seed, uint64_t first_sample, size_t n_draw, double* states,
+                      size_t capacity, size_t* n_valid);
+int artp_sample_valid_device(artp_handle* h, uint64_t seed, uint64_t first_sample, size_t n_draw, double* d_states_out,
+                             size_t capacity, uint32_t* d_count, void* stream);
 
 /* PathLengthObjective::motionCost for n edges -> cost[n] (double). */
 int artp_path_length_cost(artp_handle* h, const double* s1, const double* s2, size_t n, double* cost);

@@ -44,6 +44,11 @@ struct Params {
     struct { double length{1.05}; double width{0.55}; double height{0.2}; struct { double x{0}, y{0}, z{0}; } offset; } torso;
     struct { struct { double x{0.362}, y{0.225}, z{-0.525}; } offset; struct { double x{0.25}, y{0.1}, z{0.15}; } reach; } feet;
   } robot;
+  struct {
+    double max_pitch_pert{10.0 / 180 * 3.14159265358979323846};   // params.h:79
+    double max_roll_pert{3.33 / 180 * 3.14159265358979323846};    // params.h:80
+    bool sample_from_distribution{true};                            // params.h:81
+  } sampler;
   int device{0};   // not in the reference: CUDA device ordinal
 };
 using ParamsConstPtr = std::shared_ptr<const Params>;
@@ -56,6 +61,9 @@ struct Map {
   int rows{0}, cols{0};
   double resolution{0}, position_x{0}, position_y{0};
   std::vector<float> elevation, elevation_masked;
+  // layers the sampler reads (Map::getNormal / getPlaneFitStdDev map.h:94-116, probability_distribution.cpp:20-46);
+  // cum_prob_rowwise = column 0 of "cum_prob_rowwise_hack". Empty when no sampler is used.
+  std::vector<float> normal_x, normal_y, normal_z, plane_fit_std_dev, cum_prob, cum_prob_rowwise;
 };
 
 inline artp_params toArtp(const Params& p) {
@@ -163,6 +171,54 @@ class StateValidityChecker {
   std::shared_ptr<Map> map_;
 };
 using StateValidityCheckerPtr = std::shared_ptr<StateValidityChecker>;
+
+// art_planner::SE3FromSE2Sampler (sampler.cpp:13-131): sampleUniform on the device, one candidate per Philox counter,
+// and the rejection loop around it (prm_motion_cost.cpp:171-194) as one fused sample -> isValid -> compact call.
+class SE3FromSE2Sampler {
+ public:
+  // bounds: SE3 position bounds x,y (planner.cpp:148-160); only read when !sample_from_distribution.
+  SE3FromSE2Sampler(const StateValidityCheckerPtr& checker, const std::shared_ptr<Map>& map, uint64_t seed,
+                    const double low[2], const double high[2])
+      : checker_(checker), seed_(seed) {
+    const auto& h = checker_->handle();
+    const Params& p = h->params();
+    artp_sampler_params sp{};
+    sp.max_roll_pert = p.sampler.max_roll_pert; sp.max_pitch_pert = p.sampler.max_pitch_pert;
+    sp.sample_from_distribution = p.sampler.sample_from_distribution ? 1 : 0;
+    sp.low[0] = low[0]; sp.low[1] = low[1]; sp.high[0] = high[0]; sp.high[1] = high[1];
+    h->check(artp_set_sampler(h->get(), &sp, map->normal_x.data(), map->normal_y.data(), map->normal_z.data(),
+                              map->plane_fit_std_dev.data(), map->cum_prob.empty() ? nullptr : map->cum_prob.data(),
+                              map->cum_prob_rowwise.empty() ? nullptr : map->cum_prob_rowwise.data()), "artp_set_sampler");
+  }
+  void sampleUniform(State* state) {                                             // sampler.cpp:82-131
+    const auto& h = checker_->handle();
+    h->check(artp_sample_states(h->get(), nullptr, seed_, next_, 1, &state->x, nullptr), "artp_sample_states");
+    ++next_;
+  }
+  void sampleUniformBatch(size_t n, std::vector<State>* states) {
+    states->resize(n);
+    if (!n) return;
+    const auto& h = checker_->handle();
+    h->check(artp_sample_states(h->get(), nullptr, seed_, next_, n, &(*states)[0].x, nullptr), "artp_sample_states");
+    next_ += n;
+  }
+  // Draws n_draw candidates, returns the valid ones in draw order (what n_draw iterations of
+  // `do sampleUniform(s) while (!isValid(s))` would have accepted).
+  void sampleValidBatch(size_t n_draw, std::vector<State>* valid) {
+    valid->resize(n_draw);
+    size_t n_valid = 0;
+    const auto& h = checker_->handle();
+    if (n_draw)
+      h->check(artp_sample_valid(h->get(), seed_, next_, n_draw, &(*valid)[0].x, n_draw, &n_valid), "artp_sample_valid");
+    next_ += n_draw;
+    valid->resize(n_valid);
+  }
+  uint64_t nextIndex() const { return next_; }
+ private:
+  StateValidityCheckerPtr checker_;
+  uint64_t seed_;
+  uint64_t next_{0};
+};
 
 // ompl::base::MotionValidator as the reference uses it: discrete validation over isValid with nd segments.
 class MotionValidator {

@@ -26,6 +26,39 @@ class OrcParams(C.Structure):
         ("max_lon_vel", C.c_double), ("max_lat_vel", C.c_double), ("max_ang_vel", C.c_double)]
 
 
+class OrcSamplerMap(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("elevation", "normal_x", "normal_y", "normal_z", "plane_fit_std_dev",
+                                          "cum_prob", "cum_prob_rowwise")] + [
+        ("rows", C.c_int), ("cols", C.c_int), ("res", C.c_double), ("cx", C.c_double), ("cy", C.c_double)]
+
+
+class OrcSamplerParams(C.Structure):
+    _fields_ = [("max_roll_pert", C.c_double), ("max_pitch_pert", C.c_double), ("sample_from_distribution", C.c_int),
+                ("low", C.c_double * 2), ("high", C.c_double * 2), ("reach_z", C.c_double)]
+
+
+def sample_states(m, layers, sp, reach_z: float, u):
+    """SE3FromSE2Sampler::sampleUniform restated (artp_oracle.c, port library only): u [n, 6] uniforms ->
+    (states [n, 7], rowcol [n, 2])."""
+    if not os.path.exists(PORT_SO):
+        build("port")
+    lib = C.CDLL(PORT_SO)
+    lib.orc_sample_states.argtypes = [C.POINTER(OrcSamplerMap), C.POINTER(OrcSamplerParams), C.c_void_p, C.c_size_t,
+                                      C.c_void_p, C.c_void_p]
+    keep = [np.asfortranarray(a, dtype=np.float32) for a in (
+        m.elevation, layers.normal_x, layers.normal_y, layers.normal_z, layers.plane_fit_std_dev, layers.cum_prob)]
+    keep.append(np.ascontiguousarray(layers.cum_prob_rowwise, dtype=np.float32))
+    sm = OrcSamplerMap(*[a.ctypes.data for a in keep], m.rows, m.cols, float(m.res), float(m.cx), float(m.cy))
+    pp = OrcSamplerParams(float(sp.max_roll_pert), float(sp.max_pitch_pert), int(sp.sample_from_distribution),
+                          (C.c_double * 2)(*sp.low), (C.c_double * 2)(*sp.high), float(reach_z))
+    uu = np.ascontiguousarray(u, dtype=np.float64)
+    n = uu.shape[0]
+    states = np.zeros((n, 7), np.float64)
+    rc = np.zeros((n, 2), np.int32)
+    assert lib.orc_sample_states(C.byref(sm), C.byref(pp), uu.ctypes.data, n, states.ctypes.data, rc.ctypes.data) == 0
+    return states, rc
+
+
 def build(kind: str = "port", quiet: bool = True) -> None:
     """Compile the oracle library with oracle/Makefile (building the checker is not using it)."""
     target = "port" if kind == "port" else "ref"

@@ -37,6 +37,11 @@ int main(int argc, char** argv) {
   rd(in, map->elevation.data(), map->elevation.size()); rd(in, map->elevation_masked.data(), map->elevation_masked.size());
   std::vector<State> poses(hdr[2]), s1(hdr[3]), s2(hdr[3]);
   rd(in, poses.data(), poses.size()); rd(in, s1.data(), s1.size()); rd(in, s2.data(), s2.size());
+  const size_t ncell = map->elevation.size();
+  for (auto* layer : {&map->normal_x, &map->normal_y, &map->normal_z, &map->plane_fit_std_dev, &map->cum_prob}) {
+    layer->resize(ncell); rd(in, layer->data(), ncell);
+  }
+  map->cum_prob_rowwise.resize(hdr[0]); rd(in, map->cum_prob_rowwise.data(), map->cum_prob_rowwise.size());
   if (hdr[5] == 0) {   // art_planner_ros/config/params.yaml:55-71
     params->robot.torso.length = 1.31; params->robot.torso.width = 0.65; params->robot.torso.height = 0.30;
     params->robot.torso.offset.z = 0.04;
@@ -66,12 +71,23 @@ int main(int argc, char** argv) {
   const uint64_t drawn = checker->sampleValidBatch([&](State* st) { *st = poses[cursor++ % poses.size()]; },
                                                    /*n_wanted=*/100, /*batch=*/64, /*max_draws=*/poses.size(), &sampled);
   const uint64_t n_sampled = sampled.size();
+  // SE3FromSE2Sampler: 63 + 1 candidates of the stream, then a fused sample -> check -> compact batch
+  const double Lx = map->rows * map->resolution, Ly = map->cols * map->resolution;
+  const double low[2] = {map->position_x - Lx, map->position_y - Ly}, high[2] = {map->position_x + Lx, map->position_y + Ly};
+  SE3FromSE2Sampler smp(checker, map, /*seed=*/99, low, high);
+  std::vector<State> drawn64, accepted;
+  smp.sampleUniformBatch(63, &drawn64);
+  drawn64.emplace_back(); smp.sampleUniform(&drawn64.back());
+  smp.sampleValidBatch(2000, &accepted);
+  const uint64_t n_accepted = accepted.size(), next_index = smp.nextIndex();
   std::ofstream out(argv[2], std::ios::binary);
   wr(out, valid.data(), valid.size()); wr(out, single.data(), single.size());
   wr(out, motion.data(), motion.size()); wr(out, motion1.data(), motion1.size()); wr(out, cost.data(), cost.size());
   wr(out, n_interp.data(), n_interp.size()); wr(out, prefix.data(), prefix.size());
   wr(out, &drawn, 1); wr(out, &n_sampled, 1);
   if (n_sampled) wr(out, &sampled[0].x, 7 * n_sampled);
+  wr(out, &drawn64[0].x, 7 * drawn64.size()); wr(out, &n_accepted, 1); wr(out, &next_index, 1);
+  if (n_accepted) wr(out, &accepted[0].x, 7 * n_accepted);
   std::cout << "ok " << valid.size() << " poses, " << motion.size() << " edges\n";
   return 0;
 }

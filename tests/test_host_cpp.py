@@ -54,6 +54,10 @@ def test_host_mirror_matches_oracle(exe, preset, mk, maps, port_lib, tmp_path):
         f.write(np.asfortranarray(m.elevation).tobytes(order="F"))
         f.write(np.asfortranarray(m.elevation_masked).tobytes(order="F"))
         f.write(poses.tobytes()); f.write(s1.tobytes()); f.write(s2.tobytes())
+        L = synth.make_sampler_layers(m, seed=7)
+        for a in (L.normal_x, L.normal_y, L.normal_z, L.plane_fit_std_dev, L.cum_prob):
+            f.write(np.asfortranarray(a, dtype=np.float32).tobytes(order="F"))
+        f.write(np.ascontiguousarray(L.cum_prob_rowwise, dtype=np.float32).tobytes())
     r = subprocess.run([exe, fin, fout], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     raw = open(fout, "rb").read()
@@ -66,7 +70,10 @@ def test_host_mirror_matches_oracle(exe, preset, mk, maps, port_lib, tmp_path):
     n_interp = np.frombuffer(raw, np.int32, len(s1), o); o += 4 * len(s1)
     prefix = np.frombuffer(raw, np.int32, len(s1), o); o += 4 * len(s1)
     drawn, n_sampled = np.frombuffer(raw, np.uint64, 2, o); o += 16
-    sampled = np.frombuffer(raw, np.float64, 7 * int(n_sampled), o).reshape(-1, 7)
+    sampled = np.frombuffer(raw, np.float64, 7 * int(n_sampled), o).reshape(-1, 7); o += 56 * int(n_sampled)
+    drawn64 = np.frombuffer(raw, np.float64, 7 * 64, o).reshape(-1, 7); o += 56 * 64
+    n_accepted, next_index = np.frombuffer(raw, np.uint64, 2, o); o += 16
+    accepted = np.frombuffer(raw, np.float64, 7 * int(n_accepted), o).reshape(-1, 7)
     orc = port_lib.Oracle(params, "port")
     orc.set_map(m)
     ref = orc.check_poses(poses)
@@ -84,3 +91,17 @@ def test_host_mirror_matches_oracle(exe, preset, mk, maps, port_lib, tmp_path):
     if len(want) == 100:
         last = np.nonzero(ref)[0][99]
         assert int(drawn) == min(len(poses), (last // 64 + 1) * 64)
+    # SE3FromSE2Sampler mirror: stream positions 0..63, then the fused batch over 64..2063
+    import philox_ref
+    sp = synth.sampler_params_for(m)
+    ref64, _ = port_lib.sample_states(m, L, sp, params.reach_z, philox_ref.sampler_uniforms(99, 0, 64))
+    assert np.abs(drawn64 - ref64).max() < 1e-12
+    cand, _ = port_lib.sample_states(m, L, sp, params.reach_z, philox_ref.sampler_uniforms(99, 64, 2000))
+    assert int(next_index) == 2064
+    # validity is decided on the device's own candidates (ulp-level differences to `cand`): compare with a tolerance
+    # on the states and exactly on the count unless a candidate sits on a decision boundary
+    flags = orc.check_poses(cand)
+    if int(n_accepted) == int(flags.sum()):
+        assert np.abs(accepted - cand[flags != 0]).max() < 1e-12
+    else:
+        assert abs(int(n_accepted) - int(flags.sum())) <= 2
