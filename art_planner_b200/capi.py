@@ -76,6 +76,8 @@ def load():
     lib.artp_path_length_cost.argtypes = [vp, vp, vp, sz, vp]
     lib.artp_path_length_cost_device.argtypes = [vp, vp, vp, sz, vp, vp]
     lib.artp_compact_valid_device.argtypes = [vp, vp, sz, C.c_int64, vp, vp, vp]
+    lib.artp_pack_valid_bits_device.argtypes = [vp, vp, sz, vp, vp]
+    lib.artp_compact_bits_device.argtypes = [vp, vp, sz, C.c_int64, vp, vp, vp]
     lib.artp_get_stats.argtypes = [vp, C.POINTER(ArtpStats)]
     lib.artp_set_mode.argtypes = [vp, i32]
     lib.artp_set_timing.argtypes = [vp, i32]

@@ -149,6 +149,28 @@ class StateValidityChecker:
                                                             _stream_ptr()))
         return idx, cnt
 
+    def packValidBits(self, valid, out=None):
+        """CUDA uint8 mask [n] -> bit-packed int32 words [(n+31)//32] (item i = bit i&31 of word i>>5)."""
+        import torch
+        n = valid.shape[0]
+        if out is None:
+            out = torch.empty((n + 31) // 32, dtype=torch.int32, device=valid.device)
+        self._h.check(self._h.lib.artp_pack_valid_bits_device(self._h.h, C.c_void_p(valid.data_ptr()), n,
+                                                              C.c_void_p(out.data_ptr()), _stream_ptr()))
+        return out
+
+    def compactBits(self, bits, n: int, base: int = 0, out_idx=None, out_cnt=None):
+        """Ordered indices of the set bits among the first n of a bit-packed CUDA mask -> (indices int64 [n], count)."""
+        import torch
+        if out_idx is None:
+            out_idx = torch.empty(n, dtype=torch.int64, device=bits.device)
+        if out_cnt is None:
+            out_cnt = torch.empty(1, dtype=torch.int32, device=bits.device)
+        self._h.check(self._h.lib.artp_compact_bits_device(self._h.h, C.c_void_p(bits.data_ptr()), n, int(base),
+                                                           C.c_void_p(out_idx.data_ptr()), C.c_void_p(out_cnt.data_ptr()),
+                                                           _stream_ptr()))
+        return out_idx, out_cnt
+
     def setMode(self, mode: int) -> None:
         self._h.check(self._h.lib.artp_set_mode(self._h.h, int(mode)))
 

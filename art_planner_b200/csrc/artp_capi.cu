@@ -146,9 +146,16 @@ __global__ void path_length_kernel(const double* __restrict__ s1, const double* 
 
 // Ordered compaction: (A) per-block counts, (B) single-block exclusive scan, (C) scatter.
 constexpr int kCompactBlock = 1024;
+// BITS: the mask is bit-packed (item i = bit i&31 of word i>>5, artp_pack_valid_bits_device), else one byte per item.
+template <bool BITS>
+__device__ __forceinline__ int mask_at(const uint8_t* __restrict__ valid, size_t i) {
+  if (BITS) return (int)((reinterpret_cast<const uint32_t*>(valid)[i >> 5] >> (i & 31)) & 1u);
+  return valid[i] != 0;
+}
+template <bool BITS>
 __global__ void compact_count_kernel(const uint8_t* __restrict__ valid, size_t n, uint32_t* __restrict__ counts) {
   const size_t i = (size_t)blockIdx.x * kCompactBlock + threadIdx.x;
-  const int v = (i < n) && valid[i] != 0;
+  const int v = (i < n) && mask_at<BITS>(valid, i);
   const int c = __syncthreads_count(v);
   if (threadIdx.x == 0) counts[blockIdx.x] = (uint32_t)c;
 }
@@ -179,11 +186,12 @@ __global__ void compact_scan_kernel(uint32_t* counts, size_t nb, uint32_t* total
   }
   if (threadIdx.x == 0) *total = carry;
 }
+template <bool BITS>
 __global__ void compact_scatter_kernel(const uint8_t* __restrict__ valid, size_t n, int64_t base,
                                        const uint32_t* __restrict__ offsets, int64_t* __restrict__ out) {
   __shared__ uint32_t wsum[32];
   const size_t i = (size_t)blockIdx.x * kCompactBlock + threadIdx.x;
-  const int v = (i < n) && valid[i] != 0;
+  const int v = (i < n) && mask_at<BITS>(valid, i);
   const unsigned bal = __ballot_sync(0xffffffffu, v);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 0) wsum[wid] = __popc(bal);
@@ -197,6 +205,18 @@ __global__ void compact_scatter_kernel(const uint8_t* __restrict__ valid, size_t
   if (v) {
     const uint32_t pos = offsets[blockIdx.x] + (wid ? wsum[wid - 1] : 0u) + __popc(bal & ((1u << lane) - 1u));
     out[pos] = base + (int64_t)i;
+  }
+}
+
+// bits[w] bit b = valid[32*w + b] != 0; one warp ballot per word, tail bits zero.
+__global__ void pack_bits_kernel(const uint8_t* __restrict__ valid, size_t n, uint32_t* __restrict__ bits) {
+  const size_t words = (n + 31) / 32;
+  const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5, wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (size_t w = wid; w < words; w += warps) {
+    const size_t i = w * 32 + lane;
+    const unsigned bal = __ballot_sync(0xffffffffu, i < n && valid[i] != 0);
+    if (lane == 0) bits[w] = bal;
   }
 }
 
@@ -789,7 +809,7 @@ int artp_path_length_cost(artp_handle* hh, const double* s1, const double* s2, s
 }
 
 static int compact_valid_impl(Handle* h, const uint8_t* d_valid, size_t n, int64_t base, int64_t* d_indices,
-                              uint32_t* d_count, cudaStream_t s) {
+                              uint32_t* d_count, cudaStream_t s, bool bits = false) {
   if (n == 0) { CU_TRY(h, cudaMemsetAsync(d_count, 0, sizeof(uint32_t), s)); return ARTP_OK; }
   const size_t nb = (n + kCompactBlock - 1) / kCompactBlock;
   if (h->block_counts_cap < nb) {
@@ -799,9 +819,11 @@ static int compact_valid_impl(Handle* h, const uint8_t* d_valid, size_t n, int64
     CU_TRY(h, cudaMalloc(&h->d_block_counts, nb * sizeof(uint32_t)));
     h->block_counts_cap = nb;
   }
-  compact_count_kernel<<<(unsigned)nb, kCompactBlock, 0, s>>>(d_valid, n, h->d_block_counts);
+  if (bits) compact_count_kernel<true><<<(unsigned)nb, kCompactBlock, 0, s>>>(d_valid, n, h->d_block_counts);
+  else compact_count_kernel<false><<<(unsigned)nb, kCompactBlock, 0, s>>>(d_valid, n, h->d_block_counts);
   compact_scan_kernel<<<1, 1024, 0, s>>>(h->d_block_counts, nb, d_count);
-  compact_scatter_kernel<<<(unsigned)nb, kCompactBlock, 0, s>>>(d_valid, n, base, h->d_block_counts, d_indices);
+  if (bits) compact_scatter_kernel<true><<<(unsigned)nb, kCompactBlock, 0, s>>>(d_valid, n, base, h->d_block_counts, d_indices);
+  else compact_scatter_kernel<false><<<(unsigned)nb, kCompactBlock, 0, s>>>(d_valid, n, base, h->d_block_counts, d_indices);
   CU_TRY(h, cudaGetLastError());
   h->stats.kernel_launches += 3;
   h->stats.last_launches = 3;
@@ -816,6 +838,32 @@ int artp_compact_valid_device(artp_handle* hh, const uint8_t* d_valid, size_t n,
   if (!d_valid || !d_indices || !d_count) { h->err = "null buffer"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
   return compact_valid_impl(h, d_valid, n, base, d_indices, d_count, (cudaStream_t)stream);
+}
+
+int artp_pack_valid_bits_device(artp_handle* hh, const uint8_t* d_valid, size_t n, uint32_t* d_bits, void* stream) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (n == 0) return ARTP_OK;
+  if (!d_valid || !d_bits) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  const size_t words = (n + 31) / 32;
+  pack_bits_kernel<<<(unsigned)std::min<size_t>((words * 32 + 255) / 256, (size_t)h->sm_count * 8), 256, 0,
+                     (cudaStream_t)stream>>>(d_valid, n, d_bits);
+  CU_TRY(h, cudaGetLastError());
+  h->stats.kernel_launches += 1;
+  h->stats.last_launches = 1;
+  return ARTP_OK;
+}
+
+int artp_compact_bits_device(artp_handle* hh, const uint32_t* d_bits, size_t n, int64_t base, int64_t* d_indices,
+                             uint32_t* d_count, void* stream) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (!d_bits || !d_indices || !d_count) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  return compact_valid_impl(h, reinterpret_cast<const uint8_t*>(d_bits), n, base, d_indices, d_count, (cudaStream_t)stream, true);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

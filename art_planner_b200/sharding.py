@@ -34,3 +34,49 @@ def merge_gathered(all_idx, counts, cap: int):
     import torch
     parts = [all_idx[r * cap: r * cap + int(c.item())] for r, c in enumerate(counts)]
     return torch.cat(parts) if parts else all_idx[:0]
+
+
+def gather_valid_bits(bits, world: int, group=None, out=None):
+    """All-gather the per-rank bit-packed validity masks (one collective, no padding, no count exchange).
+
+    bits: int32 tensor [words] (same length on every rank: shards are padded to a multiple of 32 samples by the
+    caller, see words_per_shard). Returns int32 [world * words]: rank r's samples are bits [r*words*32, ...)."""
+    import torch
+    import torch.distributed as dist
+    if out is None:
+        out = torch.empty(world * bits.numel(), dtype=bits.dtype, device=bits.device)
+    dist.all_gather_into_tensor(out, bits, group=group)
+    return out
+
+
+def words_per_shard(n_per_rank: int) -> int:
+    return (n_per_rank + 31) // 32
+
+
+def indices_from_bits(all_bits, n_total: int, world: int):
+    """Reference (torch) decoding of a gathered bit mask into ordered global sample indices: rank r owns
+    shard_range(n_total, r, world), its words start at r * words_per_shard(cap), cap = ceil(n_total / world).
+    The CUDA path does the same with artp_compact_bits_device per rank slice; the gloo tests check this form."""
+    import torch
+    cap = (n_total + world - 1) // world
+    w = words_per_shard(cap)
+    out = []
+    for r in range(world):
+        lo, hi = shard_range(n_total, r, world)
+        words = all_bits[r * w:(r + 1) * w].to(torch.int64) & 0xFFFFFFFF
+        bit = (words[:, None] >> torch.arange(32, device=all_bits.device)[None, :]) & 1
+        local = torch.nonzero(bit.reshape(-1)[: hi - lo]).reshape(-1)
+        out.append(local + lo)
+    return torch.cat(out) if out else torch.zeros(0, dtype=torch.int64)
+
+
+def pack_bits_reference(valid, cap=None):
+    """torch restatement of artp_pack_valid_bits_device (CPU tensors; used by the gloo tests); cap pads the shard."""
+    import torch
+    n = valid.numel()
+    w = words_per_shard(n if cap is None else cap)
+    pad = torch.zeros(w * 32, dtype=torch.int64)
+    pad[:n] = (valid != 0).to(torch.int64)
+    words = (pad.reshape(w, 32) << torch.arange(32)[None, :]).sum(dim=1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words)
+    return words.to(torch.int32)

@@ -199,16 +199,22 @@ def main():
     h_poses32 = torch.from_numpy(poses.astype(np.float32)).pin_memory()   # the cast Pose3FromSE3 does first, done by the adapter
     h_valid = torch.empty(n, dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
-    gather_cnt = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(world)]
+    # N > 1 exchange: bit-packed masks (n/32 words per rank) all-gathered in one NCCL call, then every rank compacts
+    # the gathered mask into the global ordered valid-index list
+    assert n % 32 == 0
+    my_bits = torch.empty(n // 32, dtype=torch.int32, device="cuda")
+    all_bits = torch.empty(world * (n // 32), dtype=torch.int32, device="cuda") if world > 1 else None
     gather_idx = torch.empty(world * n, dtype=torch.int64, device="cuda") if world > 1 else None
+    gather_cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
 
     from art_planner_b200 import sharding
 
     def step_device():
         chk.isValidBatch(d_poses, out=d_valid)
-        if world > 1:   # ordered valid-sample indices -> one padded all-gather (+ counts)
-            idx, cnt = chk.compactValid(d_valid, base=rank * n)
-            sharding.gather_valid_indices(idx, cnt, world, out_idx=gather_idx, out_cnt=gather_cnt)
+        if world > 1:   # 125 KB of mask bits per rank on the wire, then the global ordered index list on every rank
+            chk.packValidBits(d_valid, out=my_bits)
+            sharding.gather_valid_bits(my_bits, world, out=all_bits)
+            chk.compactBits(all_bits, world * n, base=0, out_idx=gather_idx, out_cnt=gather_cnt)
 
     def step_e2e():      # what INTEGRATION.md's adapter calls: float32 states (exact), pinned host buffers
         chk.isValidHostPtr(h_poses32.data_ptr(), n, h_valid.data_ptr(), f32=True)
@@ -394,7 +400,7 @@ def main():
                        "configs[4]: fBm 4000x4000@0.04m map, 1M samples per GPU inside the GPU's spatial slab, yaml robot geometry",
                        "poses_per_gpu": n, "map": f"{m.rows}x{m.cols}@{MAP_RES}",
                        "map_seed": MAP_SEED, "pose_seed": POSE_SEED, "l2": "flushed between timed steps (256 MiB write)",
-                       "parallelism": f"pose shards x{world}, replicated map" + (", NCCL all-gather of valid indices" if world > 1 else "")},
+                       "parallelism": f"pose shards x{world}, replicated map" + (", NCCL all-gather of bit-packed masks + global ordered compaction on every rank" if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": n,
                     "ms_per_step": e2e_ms / e2e_steps, "api": "artp_check_poses_f32 (states cast to float by the adapter, exact)",
                     "f64_api_value": world * n * e2e_steps / e2e64_s, "f64_api_h2d_bytes_per_step": n * 56},

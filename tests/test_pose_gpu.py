@@ -163,3 +163,20 @@ def test_batched_rejection_sampling(maps, checkers, port_lib):
     want = pool[ref != 0][:500]
     assert np.array_equal(got, want)
     assert drawn % 512 == 0 or drawn == len(pool)
+
+
+def test_bit_packed_mask_and_compaction(maps, checkers):
+    """artp_pack_valid_bits_device / artp_compact_bits_device == the torch restatements (multi-GPU exchange format)."""
+    import torch
+    from art_planner_b200 import sharding
+    chk = checkers("yaml")
+    g = torch.Generator().manual_seed(5)
+    for n in (1, 31, 32, 33, 4097, 1_000_003):
+        v = (torch.rand(n, generator=g) < 0.37).to(torch.uint8)
+        bits = chk.packValidBits(v.cuda())
+        torch.cuda.synchronize()
+        assert torch.equal(bits.cpu(), sharding.pack_bits_reference(v))
+        idx, cnt = chk.compactBits(bits, n, base=1000)
+        torch.cuda.synchronize()
+        want = torch.nonzero(v).reshape(-1) + 1000
+        assert int(cnt.item()) == want.numel() and torch.equal(idx[: want.numel()].cpu(), want)

@@ -43,9 +43,14 @@ def _worker(rank, world, port, n_total, q):
         cnt = torch.tensor([len(nz)], dtype=torch.int32)
         all_idx, counts = sharding.gather_valid_indices(idx, cnt, world)
         merged = sharding.merge_gathered(all_idx, counts, cap)
+        # the bit-packed exchange (what bench.py --gpus N uses): one all-gather of cap/32 words per rank
+        bits = sharding.pack_bits_reference(torch.from_numpy(valid), cap)
+        all_bits = sharding.gather_valid_bits(bits, world)
+        from_bits = sharding.indices_from_bits(all_bits, n_total, world)
         if rank == 0:
             full = o.check_poses(synth.make_terrain_poses(m, n_total, seed=9))
-            q.put((merged.numpy().tolist() == np.nonzero(full)[0].tolist(), int(full.sum())))
+            want = np.nonzero(full)[0].tolist()
+            q.put((merged.numpy().tolist() == want and from_bits.numpy().tolist() == want, int(full.sum())))
     finally:
         dist.destroy_process_group()
 
@@ -72,3 +77,13 @@ def test_two_rank_index_exchange_over_gloo(port_lib):
         assert p.exitcode == 0
     ok, n_valid = q.get(timeout=10)
     assert ok and n_valid > 0
+
+
+def test_bit_packing_reference_roundtrip():
+    from art_planner_b200 import sharding
+    g = torch.Generator().manual_seed(3)
+    for n in (1, 31, 32, 33, 1000, 4097):
+        v = (torch.rand(n, generator=g) < 0.4).to(torch.uint8)
+        bits = sharding.pack_bits_reference(v)
+        assert bits.numel() == (n + 31) // 32 and bits.dtype == torch.int32
+        assert sharding.indices_from_bits(bits, n, 1).tolist() == torch.nonzero(v).reshape(-1).tolist()
