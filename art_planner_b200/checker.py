@@ -149,6 +149,16 @@ class StateValidityChecker:
                                                             _stream_ptr()))
         return idx, cnt
 
+    def estimateNormals(self, estimation_radius: float, want_host: bool = True):
+        """art_planner::estimateNormals (utils.cpp:213-324) for the current elevation layer, on the device; the layers
+        stay resident as the sampler's inputs. Returns (normal_x, normal_y, normal_z, plane_fit_std_dev) float32
+        Fortran-order arrays, or None when want_host is False."""
+        rows, cols = self._map.elevation.shape
+        outs = [np.empty((rows, cols), np.float32, order="F") for _ in range(4)] if want_host else [None] * 4
+        self._h.check(self._h.lib.artp_estimate_normals(self._h.h, float(estimation_radius),
+                                                        *[None if a is None else a.ctypes.data for a in outs]))
+        return tuple(outs) if want_host else None
+
     def packValidBits(self, valid, out=None):
         """CUDA uint8 mask [n] -> bit-packed int32 words [(n+31)//32] (item i = bit i&31 of word i>>5)."""
         import torch
@@ -209,7 +219,8 @@ class SE3FromSE2Sampler:
     def setLayers(self, layers, sp) -> None:
         h, lib = self._c.handle, self._c.handle.lib
         f = lambda a: None if a is None else np.asfortranarray(a, dtype=np.float32)
-        keep = [f(layers.normal_x), f(layers.normal_y), f(layers.normal_z), f(layers.plane_fit_std_dev),
+        keep = [f(getattr(layers, "normal_x", None)), f(getattr(layers, "normal_y", None)),
+                f(getattr(layers, "normal_z", None)), f(getattr(layers, "plane_fit_std_dev", None)),
                 f(getattr(layers, "cum_prob", None)),
                 None if getattr(layers, "cum_prob_rowwise", None) is None
                 else np.ascontiguousarray(layers.cum_prob_rowwise, dtype=np.float32)]

@@ -55,6 +55,7 @@ struct Handle {
   float* d_samp_layers = nullptr;   // normal_x | normal_y | normal_z | std_dev | cum_prob | cum_row
   size_t samp_layers_cap = 0;
   bool has_sampler = false;
+  bool has_device_normals = false;  // artp_estimate_normals filled normal_x/y/z/std_dev of d_samp_layers for this map
   void* d_samp_scratch = nullptr;
   size_t samp_scratch_cap = 0;
   int timing = 0;
@@ -531,6 +532,7 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
   h->chk.cell_margin = 0.02f + 2e-6f * (float)std::max(rows, cols);
   h->has_map = true;
   h->has_sampler = false;      // its layers belong to the previous map
+  h->has_device_normals = false;
   return ARTP_OK;
 }
 
@@ -869,6 +871,48 @@ int artp_compact_bits_device(artp_handle* hh, const uint32_t* d_bits, size_t n, 
 // ---------------------------------------------------------------------------------------------------------------
 // Sampler: SE3FromSE2Sampler::sampleUniform on the device (artp_sampler.cuh)
 // ---------------------------------------------------------------------------------------------------------------
+static int ensure_sampler_layers(Handle* h) {
+  const size_t ncell = (size_t)h->rows * h->cols;
+  const size_t need = (5 * ncell + (size_t)h->rows + 64) * sizeof(float);
+  if (h->samp_layers_cap >= need) return ARTP_OK;
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  cudaFree(h->d_samp_layers);
+  h->d_samp_layers = nullptr; h->samp_layers_cap = 0;
+  h->has_device_normals = false;
+  CU_TRY(h, cudaMalloc(&h->d_samp_layers, need));
+  h->samp_layers_cap = need;
+  return ARTP_OK;
+}
+
+int artp_estimate_normals(artp_handle* hh, double estimation_radius, float* normal_x, float* normal_y, float* normal_z,
+                          float* plane_fit_std_dev) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
+  if (!(estimation_radius >= 0.0)) { h->err = "estimation_radius < 0"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  int rc = ensure_sampler_layers(h);
+  if (rc) return rc;
+  const size_t ncell = (size_t)h->rows * h->cols;
+  const double res = h->chk.Lx / h->rows;
+  float* base = h->d_samp_layers;
+  const int r_cells = (int)(estimation_radius / res), r_diag = (int)(estimation_radius * 0.70710678118 / res);   // utils.cpp:226-227
+  artp::estimate_normals_kernel<<<(unsigned)std::min<size_t>((ncell + 127) / 128, (size_t)h->sm_count * 32), 128, 0, h->stream>>>(
+      h->d_H[0], h->pitch, h->rows, h->cols, res, h->chk.cx, h->chk.cy, r_cells, r_diag, base, base + ncell, base + 2 * ncell,
+      base + 3 * ncell);
+  CU_TRY(h, cudaGetLastError());
+  float* dst[4] = {normal_x, normal_y, normal_z, plane_fit_std_dev};
+  for (int k = 0; k < 4; ++k)
+    if (dst[k]) CU_TRY(h, cudaMemcpyAsync(dst[k], base + k * ncell, ncell * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->has_device_normals = true;
+  h->has_sampler = false;          // the sampler must be (re)armed with artp_set_sampler
+  h->stats.kernel_launches += 1;
+  h->stats.last_launches = 1;
+  return ARTP_OK;
+}
+
 int artp_set_sampler(artp_handle* hh, const artp_sampler_params* sp, const float* normal_x, const float* normal_y,
                      const float* normal_z, const float* plane_fit_std_dev, const float* cum_prob,
                      const float* cum_prob_rowwise) {
@@ -876,7 +920,14 @@ int artp_set_sampler(artp_handle* hh, const artp_sampler_params* sp, const float
   Handle* h = reinterpret_cast<Handle*>(hh);
   std::lock_guard<std::mutex> lk(h->mtx);
   if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
-  if (!sp || !normal_x || !normal_y || !normal_z || !plane_fit_std_dev) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  const bool host_normals = normal_x && normal_y && normal_z && plane_fit_std_dev;
+  if (!sp) { h->err = "null sampler params"; return ARTP_E_INVALID; }
+  if (!host_normals && (normal_x || normal_y || normal_z || plane_fit_std_dev)) {
+    h->err = "pass all four normal / plane-fit layers or none"; return ARTP_E_INVALID;
+  }
+  if (!host_normals && !h->has_device_normals) {
+    h->err = "no normal layers: pass them or call artp_estimate_normals after artp_set_map"; return ARTP_E_INVALID;
+  }
   if (sp->sample_from_distribution && (!cum_prob || !cum_prob_rowwise)) {
     h->err = "sample_from_distribution needs the cum_prob layers"; return ARTP_E_INVALID;
   }
@@ -885,18 +936,17 @@ int artp_set_sampler(artp_handle* hh, const artp_sampler_params* sp, const float
   }
   CU_TRY(h, cudaSetDevice(h->device));
   const size_t ncell = (size_t)h->rows * h->cols;
-  const size_t need = (5 * ncell + (size_t)h->rows + 64) * sizeof(float);
-  if (h->samp_layers_cap < need) {
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
-    cudaFree(h->d_samp_layers);
-    h->d_samp_layers = nullptr; h->samp_layers_cap = 0;
-    CU_TRY(h, cudaMalloc(&h->d_samp_layers, need));
-    h->samp_layers_cap = need;
+  {
+    int rc = ensure_sampler_layers(h);
+    if (rc) return rc;
   }
   float* base = h->d_samp_layers;
-  const float* src[4] = {normal_x, normal_y, normal_z, plane_fit_std_dev};
-  for (int k = 0; k < 4; ++k)
-    CU_TRY(h, cudaMemcpyAsync(base + k * ncell, src[k], ncell * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  if (host_normals) {
+    const float* src[4] = {normal_x, normal_y, normal_z, plane_fit_std_dev};
+    for (int k = 0; k < 4; ++k)
+      CU_TRY(h, cudaMemcpyAsync(base + k * ncell, src[k], ncell * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    h->has_device_normals = false;   // overwritten by the caller's layers
+  }
   artp::SamplerDev& m = h->samp;
   m.elevation_rev = h->d_H[0]; m.pitch = h->pitch;
   m.normal_x = base; m.normal_y = base + ncell; m.normal_z = base + 2 * ncell; m.std_dev = base + 3 * ncell;

@@ -184,6 +184,73 @@ __global__ void reject_nan_kernel(const double* __restrict__ states, size_t n, u
     if (states[i * 7] != states[i * 7]) valid[i] = 0;
 }
 
+// ---- art_planner::estimateNormals (art_planner/src/utils.cpp:213-324) ------------------------------------------
+// One thread per cell (row index fastest -> coalesced in the column-major layers). float arithmetic exactly as Eigen
+// evaluates the reference's expressions on 3-vectors (not vectorised): cross = (a1*b2 - a2*b1, ...), squaredNorm =
+// x*x + (y*y + z*z), normalized() divides by sqrtf when the squared norm is > 0. Built with -fmad=false; sqrtf and
+// the divisions are IEEE (nvcc defaults), so the result is bit-identical to the CPU restatement.
+struct F3 { float x, y, z; };
+
+__device__ __forceinline__ void en_accumulate(const F3& a, const F3& b, F3& sum) {
+  float c0 = a.y * b.z - a.z * b.y;
+  float c1 = a.z * b.x - a.x * b.z;
+  float c2 = a.x * b.y - a.y * b.x;
+  const float z = c0 * c0 + (c1 * c1 + c2 * c2);
+  if (z > 0.0f) { const float n = sqrtf(z); c0 /= n; c1 /= n; c2 /= n; }
+  sum.x += c0; sum.y += c1; sum.z += c2;
+}
+
+__global__ void estimate_normals_kernel(const float* __restrict__ H_rev, int pitch, int rows, int cols, double res, double cx,
+                                        double cy, int r_cells, int r_diag, float* __restrict__ nx, float* __restrict__ ny,
+                                        float* __restrict__ nz, float* __restrict__ sd) {
+  const size_t total = (size_t)rows * cols;
+  const double offx = 0.5 * (rows * res) - 0.5 * res, offy = 0.5 * (cols * res) - 0.5 * res;
+  for (size_t at = blockIdx.x * (size_t)blockDim.x + threadIdx.x; at < total; at += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(at / rows), i = (int)(at - (size_t)j * rows);
+    // map_3d (:236-249): grid_map::getPosition cast to float, elevation as stored
+    auto P = [&](int ii, int jj) {
+      F3 p;
+      p.x = (float)((cx + offx) + res * (-(double)ii));
+      p.y = (float)((cy + offy) + res * (-(double)jj));
+      p.z = __ldg(H_rev + (size_t)ii + (size_t)(cols - 1 - jj) * pitch);
+      return p;
+    };
+    const F3 c = P(i, j);
+    F3 sum = {0.0f, 0.0f, 0.0f};
+    unsigned int n_vec = 0;
+    float max_z_diff = 0.0f;
+    auto pair = [&](int i1, int j1, int i2, int j2) {
+      const F3 p1 = P(i1, j1), p2 = P(i2, j2);
+      const F3 vx = {p1.x - c.x, p1.y - c.y, p1.z - c.z}, vy = {p2.x - c.x, p2.y - c.y, p2.z - c.z};
+      if (fabsf(vx.z) > max_z_diff) max_z_diff = fabsf(vx.z);
+      if (fabsf(vy.z) > max_z_diff) max_z_diff = fabsf(vy.z);
+      en_accumulate(vx, vy, sum);
+      ++n_vec;
+    };
+    for (int o = 1; o < r_cells; ++o) {                                  // :260-271
+      if (i + o >= rows || j + o >= cols) continue;
+      pair(i + o, j, i, j + o);
+    }
+    for (int o = 1; o < r_cells; ++o) {                                  // :272-282
+      if (i - o < 0 || j - o < 0) continue;
+      pair(i - o, j, i, j - o);
+    }
+    for (int o = 1; o < r_diag; ++o) {                                   // :283-297
+      if (i + o >= rows || j + o >= cols || i - o < 0) continue;
+      pair(i + o, j + o, i - o, j + o);
+    }
+    for (int o = 1; o < r_diag; ++o) {                                   // :298-312
+      if (i - o < 0 || j - o < 0 || i + o >= rows) continue;
+      pair(i - o, j - o, i + o, j - o);
+    }
+    if (n_vec > 0) { const float d = (float)n_vec; sum.x /= d; sum.y /= d; sum.z /= d; }   // :315-317
+    sd[at] = max_z_diff;
+    const float z = sum.x * sum.x + (sum.y * sum.y + sum.z * sum.z);     // normalize(), :320
+    if (z > 0.0f) { const float n = sqrtf(z); sum.x /= n; sum.y /= n; sum.z /= n; }
+    nx[at] = sum.x; ny[at] = sum.y; nz[at] = sum.z;
+  }
+}
+
 // Every CDF row must be non-decreasing and finite, or entirely NaN (a row without probability mass:
 // probability_distribution.cpp:28 divides 0 by 0). bad[0] counts violations. One thread per row / for the row CDF.
 __global__ void validate_cdf_kernel(const float* __restrict__ c, int rows, int cols, size_t stride_in_row, size_t stride_row,

@@ -136,8 +136,16 @@ typedef struct artp_sampler_params {
 /* Per-cell layers the sampler reads, HOST pointers in grid_map layout (like artp_set_map, which must come first and
  * provides "elevation" and the geometry): normal_x/y/z, plane_fit_std_dev (Map::getNormal / getPlaneFitStdDev,
  * map.h:94-116), "cum_prob" and column 0 of "cum_prob_rowwise_hack" (probability_distribution.cpp:20-46; may be NULL
- * when !sample_from_distribution). CDF rows must be non-decreasing or all NaN (else ARTP_E_INVALID).
+ * when !sample_from_distribution). The four normal / plane-fit pointers may all be NULL after artp_estimate_normals.
+ * CDF rows must be non-decreasing or all NaN (else ARTP_E_INVALID).
  * artp_set_map invalidates the sampler layers. */
+/* art_planner::estimateNormals (art_planner/src/utils.cpp:213-324; called from processors::Basic, basic.cpp:47, with
+ * estimation_radius = (torso.length + torso.width) * 0.25) for the elevation layer of the current map, on the device.
+ * The four layers stay on the device as the sampler's normal / plane-fit layers (then artp_set_sampler may be called
+ * with the four pointers NULL) and are copied to the non-NULL HOST outputs (grid_map layout). Bit-identical to the
+ * reference's float arithmetic (the elevation layer's -0 is stored as +0, see artp_set_map). */
+int artp_estimate_normals(artp_handle* h, double estimation_radius, float* normal_x, float* normal_y, float* normal_z,
+                          float* plane_fit_std_dev);
 int artp_set_sampler(artp_handle* h, const artp_sampler_params* sp, const float* normal_x, const float* normal_y,
                      const float* normal_z, const float* plane_fit_std_dev, const float* cum_prob,
                      const float* cum_prob_rowwise);

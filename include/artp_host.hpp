@@ -123,6 +123,19 @@ class StateValidityChecker {
 
   bool hasMap() const { return artp_has_map(handle_->get()) != 0; }             // validity_checker.cpp:33-35
 
+  // art_planner::estimateNormals (utils.cpp:213-324) as processors::Basic calls it (basic.cpp:47), on the device; fills
+  // the map's normal_x/y/z and plane_fit_std_dev layers and keeps them resident for SE3FromSE2Sampler.
+  void estimateNormals() {
+    if (!map_) throw std::runtime_error("estimateNormals: no map");
+    const Params& p = handle_->params();
+    const size_t ncell = static_cast<size_t>(map_->rows) * map_->cols;
+    map_->normal_x.resize(ncell); map_->normal_y.resize(ncell); map_->normal_z.resize(ncell);
+    map_->plane_fit_std_dev.resize(ncell);
+    handle_->check(artp_estimate_normals(handle_->get(), (p.robot.torso.length + p.robot.torso.width) * 0.25,
+                                         map_->normal_x.data(), map_->normal_y.data(), map_->normal_z.data(),
+                                         map_->plane_fit_std_dev.data()), "artp_estimate_normals");
+  }
+
   bool isValid(const State* state) const {                                      // validity_checker.cpp:39-45
     uint8_t v = 0;
     handle_->check(artp_check_poses(handle_->get(), &state->x, 1, &v), "artp_check_poses");

@@ -640,6 +640,82 @@ int orc_sample_states(const orc_sampler_map* m, const orc_sampler_params* p, con
   return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * art_planner::estimateNormals, art_planner/src/utils.cpp:213-324
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { float v[3]; } f3;
+
+static f3 en_sub(f3 a, f3 b) { f3 r = {{a.v[0] - b.v[0], a.v[1] - b.v[1], a.v[2] - b.v[2]}}; return r; }
+
+/* vec_x.cross(vec_y).normalized() added into sum (utils.cpp:268 etc.) */
+static void en_accumulate(f3 vx, f3 vy, f3* sum) {
+  f3 c;
+  c.v[0] = vx.v[1] * vy.v[2] - vx.v[2] * vy.v[1];
+  c.v[1] = vx.v[2] * vy.v[0] - vx.v[0] * vy.v[2];
+  c.v[2] = vx.v[0] * vy.v[1] - vx.v[1] * vy.v[0];
+  const float z = c.v[0] * c.v[0] + (c.v[1] * c.v[1] + c.v[2] * c.v[2]);
+  if (z > 0.0f) { const float n = sqrtf(z); c.v[0] /= n; c.v[1] /= n; c.v[2] /= n; }
+  sum->v[0] += c.v[0]; sum->v[1] += c.v[1]; sum->v[2] += c.v[2];
+}
+
+int orc_estimate_normals(const float* elevation, int rows, int cols, double res, double cx, double cy,
+                         double estimation_radius, float* normal_x, float* normal_y, float* normal_z,
+                         float* plane_fit_std_dev) {
+  const int r_cells = (int)(estimation_radius / res);                         /* :226 */
+  const int r_diag = (int)(estimation_radius * 0.70710678118 / res);          /* :227 */
+  /* map_3d (:236-249): cell positions cast to float (grid_map::getPosition, see gm_position_of_index) */
+  float* px = (float*)malloc(sizeof(float) * rows);
+  float* py = (float*)malloc(sizeof(float) * cols);
+  if (!px || !py) { free(px); free(py); return 1; }
+  const double offx = 0.5 * (rows * res) - 0.5 * res, offy = 0.5 * (cols * res) - 0.5 * res;
+  for (int i = 0; i < rows; ++i) px[i] = (float)((cx + offx) + res * (-(double)i));
+  for (int j = 0; j < cols; ++j) py[j] = (float)((cy + offy) + res * (-(double)j));
+#define EN_P(i, j) ((f3){{px[i], py[j], elevation[(i) + (size_t)(j) * rows]}})
+#define EN_DZ(q_) do { const float a_ = fabsf((q_).v[2]); if (a_ > max_z_diff) max_z_diff = a_; } while (0)
+  for (int i = 0; i < rows; ++i) {
+    for (int j = 0; j < cols; ++j) {
+      f3 sum = {{0.0f, 0.0f, 0.0f}};
+      unsigned int n_vec = 0;
+      float max_z_diff = 0.0f;
+      const f3 center = EN_P(i, j);
+      for (int o = 1; o < r_cells; ++o) {                                      /* :260-271 */
+        if (i + o >= rows || j + o >= cols) continue;
+        const f3 vx = en_sub(EN_P(i + o, j), center), vy = en_sub(EN_P(i, j + o), center);
+        EN_DZ(vx); EN_DZ(vy);
+        en_accumulate(vx, vy, &sum); ++n_vec;
+      }
+      for (int o = 1; o < r_cells; ++o) {                                      /* :272-282 */
+        if (i - o < 0 || j - o < 0) continue;
+        const f3 vx = en_sub(EN_P(i - o, j), center), vy = en_sub(EN_P(i, j - o), center);
+        EN_DZ(vx); EN_DZ(vy);
+        en_accumulate(vx, vy, &sum); ++n_vec;
+      }
+      for (int o = 1; o < r_diag; ++o) {                                       /* :283-297 */
+        if (i + o >= rows || j + o >= cols || i - o < 0) continue;            /* j_offset_2 = j + o: same bound */
+        const f3 vx = en_sub(EN_P(i + o, j + o), center), vy = en_sub(EN_P(i - o, j + o), center);
+        EN_DZ(vx); EN_DZ(vy);
+        en_accumulate(vx, vy, &sum); ++n_vec;
+      }
+      for (int o = 1; o < r_diag; ++o) {                                       /* :298-312 */
+        if (i - o < 0 || j - o < 0 || i + o >= rows) continue;
+        const f3 vx = en_sub(EN_P(i - o, j - o), center), vy = en_sub(EN_P(i + o, j - o), center);
+        EN_DZ(vx); EN_DZ(vy);
+        en_accumulate(vx, vy, &sum); ++n_vec;
+      }
+      if (n_vec > 0) { const float d = (float)n_vec; sum.v[0] /= d; sum.v[1] /= d; sum.v[2] /= d; }   /* :315-317 */
+      const size_t at = i + (size_t)j * rows;
+      plane_fit_std_dev[at] = max_z_diff;                                      /* :318 */
+      const float z = sum.v[0] * sum.v[0] + (sum.v[1] * sum.v[1] + sum.v[2] * sum.v[2]);   /* normalize(), :320 */
+      if (z > 0.0f) { const float n = sqrtf(z); sum.v[0] /= n; sum.v[1] /= n; sum.v[2] /= n; }
+      normal_x[at] = sum.v[0]; normal_y[at] = sum.v[1]; normal_z[at] = sum.v[2];
+    }
+  }
+#undef EN_P
+#undef EN_DZ
+  free(px); free(py);
+  return 0;
+}
+
 int orc_path_length_cost(orc_handle* h, const double* s1, const double* s2, size_t n, double* cost) {
   if (!h) return 1;
   for (size_t i = 0; i < n; ++i) cost[i] = orc_path_length(&h->p, s1 + 7 * i, s2 + 7 * i);

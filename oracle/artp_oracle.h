@@ -100,6 +100,15 @@ typedef struct orc_sampler_params {
 int orc_sample_states(const orc_sampler_map* m, const orc_sampler_params* p, const double* u, size_t n, double* states,
                       int32_t* rowcol);
 
+/* art_planner::estimateNormals (art_planner/src/utils.cpp:213-324), liborc_port.so only: per-cell surface normal
+ * (average of normalised cross products of axis / diagonal neighbour pairs within estimation_radius) and the
+ * "plane_fit_std_dev" layer (largest |dz| seen). All float arithmetic as Eigen evaluates it (3-vectors are not
+ * vectorised: cross = a1*b2-a2*b1,..; squaredNorm = x*x + (y*y + z*z); normalized() divides by sqrt when > 0).
+ * Layers column-major rows x cols. */
+int orc_estimate_normals(const float* elevation, int rows, int cols, double res, double cx, double cy,
+                         double estimation_radius, float* normal_x, float* normal_y, float* normal_z,
+                         float* plane_fit_std_dev);
+
 /* PathLengthObjective::motionCost (path_length_objective.cpp:26-70). */
 int orc_path_length_cost(orc_handle* h, const double* s1, const double* s2, size_t n, double* cost);
 

@@ -59,6 +59,22 @@ def sample_states(m, layers, sp, reach_z: float, u):
     return states, rc
 
 
+def estimate_normals(m, estimation_radius: float):
+    """art_planner::estimateNormals restated (artp_oracle.c): returns (normal_x, normal_y, normal_z, plane_fit_std_dev),
+    float32 Fortran-order [rows, cols]."""
+    if not os.path.exists(PORT_SO):
+        build("port")
+    lib = C.CDLL(PORT_SO)
+    lib.orc_estimate_normals.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    e = np.asfortranarray(m.elevation, dtype=np.float32)
+    outs = [np.zeros(e.shape, np.float32, order="F") for _ in range(4)]
+    rc = lib.orc_estimate_normals(e.ctypes.data, e.shape[0], e.shape[1], float(m.res), float(m.cx), float(m.cy),
+                                  float(estimation_radius), *[a.ctypes.data for a in outs])
+    assert rc == 0
+    return tuple(outs)
+
+
 def build(kind: str = "port", quiet: bool = True) -> None:
     """Compile the oracle library with oracle/Makefile (building the checker is not using it)."""
     target = "port" if kind == "port" else "ref"

@@ -92,3 +92,35 @@ def test_oracle_uniform_mode_rejects_outside(setup, port_lib):
     xs = sp.low[0] + (sp.high[0] - sp.low[0]) * u[:, 0]
     inside = np.abs(xs - m.cx) < 0.5 * lx - 1e-9
     assert not (rej & inside & (np.abs(sp.low[1] + (sp.high[1] - sp.low[1]) * u[:, 1] - m.cy) < 0.5 * ly - 1e-9)).any()
+
+
+def test_oracle_estimate_normals(maps, port_lib):
+    """utils.cpp:213-324 restated: unit normals tilted against the slope, zero vector where no neighbour pair fits,
+    plane_fit_std_dev = largest |dz| over the visited neighbours."""
+    m = maps("ramp")
+    nx, ny, nz, sd = port_lib.estimate_normals(m, 0.49)
+    n2 = nx.astype(np.float64) ** 2 + ny.astype(np.float64) ** 2 + nz.astype(np.float64) ** 2
+    zero = n2 == 0
+    assert np.allclose(n2[~zero], 1.0, atol=1e-6)
+    # the only cells without any neighbour pair are the two corners (rows-1, 0) and (0, cols-1)... and their like:
+    # every loop needs either (i+o, j+o) or (i-o, j-o) style room
+    assert zero.sum() <= 4 and zero[m.rows - 1, 0] and zero[0, m.cols - 1]
+    assert (nz[~zero] > 0).all()
+    inner = (slice(16, -16), slice(16, -16))
+    e = m.elevation.astype(np.float64)
+    r = int(0.49 / m.res)
+    # std layer == max |dz| along the axis / diagonal offsets actually visited (interior cells see all of them)
+    want = np.zeros_like(e[inner])
+    for o in range(1, r):
+        for di, dj in ((o, 0), (0, o), (-o, 0), (0, -o)):
+            want = np.maximum(want, np.abs(np.roll(e, (-di, -dj), (0, 1))[inner] - e[inner]))
+    rd = int(0.49 * 0.70710678118 / m.res)
+    for o in range(1, rd):
+        for di, dj in ((o, o), (-o, o), (-o, -o), (o, -o)):
+            want = np.maximum(want, np.abs(np.roll(e, (-di, -dj), (0, 1))[inner] - e[inner]))
+    assert np.allclose(sd[inner], want, atol=1e-6)
+    # flat map: every defined normal is exactly +z
+    f = maps("flat")
+    fx, fy, fz, fs = port_lib.estimate_normals(f, 0.49)
+    ok = fz != 0
+    assert (fz[ok] == 1.0).all() and (fx[ok] == 0).all() and (fy[ok] == 0).all() and (fs == 0).all()

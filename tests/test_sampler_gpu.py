@@ -112,3 +112,48 @@ def test_sampler_errors(rig):
     chk2.updateHeightField()                     # a new map invalidates the sampler layers
     with pytest.raises(RuntimeError):
         smp.sampleUniformBatch(4)
+
+
+@pytest.mark.parametrize("mk", ["fbm_rough", "ramp", "fixture", "flat_holes_terrace"])
+def test_estimate_normals_bit_exact(maps, port_lib, mk):
+    """artp_estimate_normals == the CPU restatement of utils.cpp:213-324, bit for bit (float32 layers)."""
+    import art_planner_b200 as ap
+    m = maps(mk)
+    chk = ap.StateValidityChecker(cases.PARAMS["yaml"], device=0)
+    chk.setMap(m)
+    chk.updateHeightField()
+    p = cases.PARAMS["yaml"]
+    radius = (p.torso_length + p.torso_width) * 0.25            # basic.cpp:47
+    got = chk.estimateNormals(radius)
+    ref = port_lib.estimate_normals(m, radius)
+    for g, r, name in zip(got, ref, ("normal_x", "normal_y", "normal_z", "plane_fit_std_dev")):
+        fin = np.isfinite(r)
+        assert np.array_equal(np.isfinite(g), fin), name
+        assert np.array_equal(g[fin].view(np.uint32), r[fin].view(np.uint32)), name
+
+
+def test_sampler_on_device_normals(rig, port_lib):
+    """set_map -> estimate_normals (device) -> sampler without host normal layers == oracle fed the oracle's normals."""
+    ap, m, chk0, L = rig
+    chk = ap.StateValidityChecker(cases.PARAMS["yaml"], device=0)
+    chk.setMap(m)
+    chk.updateHeightField()
+    sp = synth.sampler_params_for(m)
+
+    class OnlyCdf:
+        cum_prob, cum_prob_rowwise = L.cum_prob, L.cum_prob_rowwise
+    with pytest.raises(RuntimeError):                      # no normals yet
+        ap.SE3FromSE2Sampler(chk, OnlyCdf, sp, seed=3)
+    chk.estimateNormals(0.49, want_host=False)
+    smp = ap.SE3FromSE2Sampler(chk, OnlyCdf, sp, seed=3)
+    nx, ny, nz, sd = port_lib.estimate_normals(m, 0.49)
+    import copy
+    L2 = copy.copy(L)
+    L2.normal_x, L2.normal_y, L2.normal_z, L2.plane_fit_std_dev = nx, ny, nz, sd
+    u = philox_ref.sampler_uniforms(3, 0, 20000)
+    ref, ref_rc = port_lib.sample_states(m, L2, sp, cases.PARAMS["yaml"].reach_z, u)
+    got, rc = smp.sampleUniformBatch(20000, first=0, want_cells=True)
+    assert np.array_equal(rc, ref_rc)
+    ok = ~np.isnan(ref).any(axis=1)
+    assert np.array_equal(np.isnan(got).any(axis=1), ~ok)
+    assert np.abs(got[ok] - ref[ok]).max() < STATE_TOL
