@@ -499,6 +499,32 @@ int orc_port_box_stats(orc_handle* h, int which, const float* origins, const flo
   return 0;
 }
 
+/* Port-only diagnostics: all five boxes of every pose WITHOUT the reference's short-circuits (what the GPU's
+ * classify stage sees): exit stage, hit flag and zone vertex count per box; box 0 = torso, 1..4 = feet.
+ * stage 255 = box centre outside the map (no collider call). */
+int orc_port_pose_box_stats(orc_handle* h, const double* states, size_t n, uint8_t* stage, uint8_t* hit, uint32_t* zv_out) {
+  if (!h || !h->g.has_map) return 1;
+  port_ctx c = {h, {0, 0, 0, 0, 0, 0, 0}};
+  for (size_t i = 0; i < n; ++i) {
+    float t[3], R[9], rot[12], o[3], tt[3];
+    orc_pose3_from_se3(states + 7 * i, t, R);
+    orc_fill_rot12(R, rot);
+    const float fx = (float)h->p.feet_off_x, fy = (float)h->p.feet_off_y;
+    for (int k = 0; k < 5; ++k) {
+      if (k == 0) { o[0] = (float)h->p.torso_off_x; o[1] = (float)h->p.torso_off_y; o[2] = (float)(h->p.torso_off_z - h->p.feet_off_z); }
+      else { o[0] = ((k - 1) & 2) ? -fx : fx; o[1] = ((k - 1) & 1) ? -fy : fy; o[2] = 0.0f; }
+      orc_compose_translation(R, t, o, tt);
+      uint32_t zv = 0;
+      if (!orc_is_inside(&h->g, tt[0], tt[1])) { stage[5 * i + k] = 255; hit[5 * i + k] = 0; zv_out[5 * i + k] = 0; continue; }
+      hit[5 * i + k] = (uint8_t)(port_collide(&c, k ? 1 : 0, tt, rot, &zv) ? 1 : 0);
+      stage[5 * i + k] = (uint8_t)c.sc.stage;
+      zv_out[5 * i + k] = zv;
+    }
+  }
+  free(c.sc.tri); free(c.sc.group);
+  return 0;
+}
+
 int orc_check_poses(orc_handle* h, const double* states, size_t n, uint8_t* valid, uint32_t* zone_verts) {
   if (!h || !h->g.has_map) return 1;
   port_ctx c = {h, {0, 0, 0, 0, 0, 0, 0}};
