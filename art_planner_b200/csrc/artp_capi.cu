@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -47,6 +48,7 @@ struct Handle {
   cudaStream_t copy_stream = nullptr;   // H2D slices of the host-buffer API
   cudaEvent_t copy_ev[16] = {};
   int k1_grid = 0, k2_grid = 0, k2_smem = 0, k2_tcap = 0;
+  int k0_flags = 0;                 // tuning switch of the classify stage (env ARTP_K0_FLAGS: 2 = no vertex probes)
   int mode = 0;
   artp_cnn::State* cnn = nullptr;
   int cnn_mode = 0;
@@ -291,7 +293,7 @@ int run_items(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed = nu
       if (lo != base) CU_TRY(h, cudaMemcpyAsync(h->d_ctr, h->d_ctr + 3, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
       if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[0], s));
       artp::classify_items_kernel<<<(unsigned)((hi - lo + 127) / 128), 128, 0, s>>>(h->chk, w, h->d_recs, h->d_ctr + 3,
-                                                                                      h->mode == 1);
+                                                                                      (h->mode == 1 ? 1 : 0) | h->k0_flags);
       CU_TRY(h, cudaGetLastError());
       if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[1], s));
       artp::box_items_warp_kernel<<<h->k1_grid, artp::kWarpsPerCta * 32, 0, s>>>(h->chk, w, h->d_recs, h->d_ctr + 3, h->d_ctr,
@@ -371,6 +373,7 @@ int artp_create(const artp_params* params, artp_handle** out) {
                                                          artp::kWarpsPerCta * 32, 0)) != cudaSuccess)
     return fail("occupancy", e);
   h->k1_grid = h->sm_count * std::max(per_sm, 1);
+  if (const char* kf = std::getenv("ARTP_K0_FLAGS")) h->k0_flags = std::atoi(kf) & 2;
   h->cnn = artp_cnn::create(h->device, h->sm_count);
   // checker constants (float casts as the reference's ctor/Pose3FromXYZ arguments make them)
   artp::Checker& c = h->chk;

@@ -445,7 +445,9 @@ __device__ __forceinline__ void rec_to_ctx(const Checker& c, const BoxRec& r, Bo
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs, uint32_t* __restrict__ rec_count,
-                      int force_all) {
+                      int flags) {
+  const int force_all = flags & 1;      // every in-map box goes to the later stages (artp_set_mode 1)
+  const bool probe = !(flags & 2);      // vertex probes (tuning switch ARTP_K0_FLAGS=2 turns them off)
   const uint32_t item = w.item_base + blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = item < w.n_items;
   const int lane = threadIdx.x & 31;
@@ -516,19 +518,54 @@ classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs, 
           const int sW = 1 << kk;
           float mx = -CUDART_INF_F, mn = CUDART_INF_F;
           int nf = 0;
-          for (int iz = 0; iz < cz; ++iz) {
-            const int zs = min(b.z0 + iz * sW, b.z1 - sW + 1);
-            for (int ix = 0; ix < cx; ++ix) {
-              const int xs = min(b.x0 + ix * sW, b.x1 - sW + 1);
-              const size_t idx = (size_t)zs * f.pitch + xs;
-              const float2 v = __ldg(T + idx);
-              mx = fmaxf(mx, v.x); mn = fminf(mn, v.y);
-              nf |= __ldg(NF + idx);
+          if (cx <= 2 && cz <= 2) {
+            // the common case (window edge > half the zone edge): all four windows are requested before any is used
+            const int xs0 = b.x0, xs1 = b.x1 - sW + 1, zs0 = b.z0, zs1 = b.z1 - sW + 1;
+            const size_t i00 = (size_t)zs0 * f.pitch + xs0, i01 = (size_t)zs0 * f.pitch + xs1,
+                         i10 = (size_t)zs1 * f.pitch + xs0, i11 = (size_t)zs1 * f.pitch + xs1;
+            const float2 v0 = __ldg(T + i00), v1 = __ldg(T + i01), v2 = __ldg(T + i10), v3 = __ldg(T + i11);
+            const int n0 = __ldg(NF + i00), n1 = __ldg(NF + i01), n2 = __ldg(NF + i10), n3 = __ldg(NF + i11);
+            mx = fmaxf(fmaxf(v0.x, v1.x), fmaxf(v2.x, v3.x));
+            mn = fminf(fminf(v0.y, v1.y), fminf(v2.y, v3.y));
+            nf = n0 | n1 | n2 | n3;
+          } else {
+            for (int iz = 0; iz < cz; ++iz) {
+              const int zs = min(b.z0 + iz * sW, b.z1 - sW + 1);
+              for (int ix = 0; ix < cx; ++ix) {
+                const int xs = min(b.x0 + ix * sW, b.x1 - sW + 1);
+                const size_t idx = (size_t)zs * f.pitch + xs;
+                const float2 v = __ldg(T + idx);
+                mx = fmaxf(mx, v.x); mn = fminf(mn, v.y);
+                nf |= __ldg(NF + idx);
+              }
             }
           }
           const bool allFinite = nf == 0;
           r = zone_early_out(b, mx, mn, allFinite);
           if (allFinite) fl |= REC_ALLFINITE;
+          if (r == -1 && allFinite && nX >= 2 && nZ >= 2 && probe) {
+            // Vertex probes. In an all-finite zone every vertex with h > minB belongs to a kept triangle, and the
+            // collider returns 1 as soon as ANY such vertex lies inside the box (heightfield.cpp:1344-1441), so a
+            // hit found here is exactly the reference's answer; a miss decides nothing and the box is queued.
+            // Reach box: the cell under the box centre; torso: a 3x3 pattern across the footprint.
+            // (measured: 3x3 / 5x5 reach-box patterns remove another 25 % of the queue but cost the classify stage
+            // twice what the warp stage saves -- one thread walks them serially)
+            const int np = foot ? 1 : 9;
+            const float h0 = 0.5f * sd0, h1 = 0.5f * sd1;
+            for (int pi = 0; pi < np && r == -1; ++pi) {
+              const float u0 = foot ? 0.0f : 0.7f * (float)(pi % 3 - 1), u1 = foot ? 0.0f : 0.7f * (float)(pi / 3 - 1);
+              const float qx = b.P[0] + (u0 * h0) * R1[0] + (u1 * h1) * R1[1];
+              const float qz = b.P[2] + (u0 * h0) * R1[6] + (u1 * h1) * R1[7];
+              const int pcx = min(max((int)floorf(qx * g.iW), b.x0), b.x1 - 1);
+              const int pcz = min(max((int)floorf(qz * g.iD), b.z0), b.z1 - 1);
+              float hA, hB, hC, hD;
+              load_cell(f, pcx, pcz, hA, hB, hC, hD);
+              const float xA = pcx * f.sW, xB = (pcx + 1) * f.sW, zA = pcz * f.sD, zC = (pcz + 1) * f.sD;
+              if ((hA > b.minB && vertex_inside(b, xA, hA, zA)) || (hB > b.minB && vertex_inside(b, xB, hB, zA)) ||
+                  (hC > b.minB && vertex_inside(b, xA, hC, zC)) || (hD > b.minB && vertex_inside(b, xB, hD, zC)))
+                r = R_HIT;
+            }
+          }
         }
       }
       if (r == -1) { ub[n_und] = b; uflags[n_und] = fl; ++n_und; }
