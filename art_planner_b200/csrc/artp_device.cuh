@@ -266,27 +266,14 @@ __device__ __forceinline__ int box_plane(const BoxCtx& b, const float n[4], int 
 // dxHeightfieldData::IsOnHeightfield2 (ode/ode/src/heightfield.cpp:264-321). (cx,cz): integer coords of the
 // triangle's first vertex (A for Up, D for Down).
 __device__ __forceinline__ bool on_tri(const Field& f, bool isUp, int cx, int cz, float X, float Z) {
-  if (isUp) {
-    const float MinX = cx * f.sW;
-    if (X < MinX) return false;
-    const float MaxX = (cx + 1) * f.sW;
-    if (X >= MaxX) return false;
-    const float MinZ = cz * f.sD;
-    if (Z < MinZ) return false;
-    const float MaxZ = (cz + 1) * f.sD;
-    if (Z >= MaxZ) return false;
-    return (MaxZ - Z) > (X - MinX) * f.asp;
-  } else {
-    const float MaxX = cx * f.sW;
-    if (X >= MaxX) return false;
-    const float MinX = (cx - 1) * f.sW;
-    if (X < MinX) return false;
-    const float MaxZ = cz * f.sD;
-    if (Z >= MaxZ) return false;
-    const float MinZ = (cz - 1) * f.sD;
-    if (Z < MinZ) return false;
-    return (MaxZ - Z) <= (X - MinX) * f.asp;
-  }
+  // Up:   MinX = cx*sW,     MaxX = (cx+1)*sW, ... inside && (MaxZ - Z) >  (X - MinX) * asp
+  // Down: MinX = (cx-1)*sW, MaxX = cx*sW,     ... inside && (MaxZ - Z) <= (X - MinX) * asp
+  // written without an isUp branch (same products, same comparisons) so mixed warps do not diverge.
+  const int lx = isUp ? cx : cx - 1, lz = isUp ? cz : cz - 1;
+  const float MinX = lx * f.sW, MaxX = (lx + 1) * f.sW, MinZ = lz * f.sD, MaxZ = (lz + 1) * f.sD;
+  const bool inside = (X >= MinX) && (X < MaxX) && (Z >= MinZ) && (Z < MaxZ);
+  const bool above = (MaxZ - Z) > (X - MinX) * f.asp;
+  return inside && (isUp ? above : !above);
 }
 
 __device__ __forceinline__ bool finitef(float h) { return fabsf(h) < CUDART_INF_F; }   // no NaN by contract

@@ -146,8 +146,8 @@ __device__ __forceinline__ void load_cell(const Field& f, int cx, int cz, float&
 __device__ __forceinline__ void cell_plane(const Field& f, bool isUp, int cx, int cz, float hA, float hB, float hC,
                                            float hD, float pl[4]) {
   const float xA = cx * f.sW, xB = (cx + 1) * f.sW, zA = cz * f.sD, zC = (cz + 1) * f.sD;
-  if (isUp) tri_plane(true, xA, hA, zA, xB, hB, zA, xA, hC, zC, pl);     // (A, B, C)
-  else      tri_plane(false, xB, hD, zC, xB, hB, zA, xA, hC, zC, pl);    // (D, B, C)
+  // (A, B, C) or (D, B, C): one instruction stream for both (lanes holding an Up and a Down triangle do not diverge)
+  tri_plane(isUp, isUp ? xA : xB, isUp ? hA : hD, isUp ? zA : zC, xB, hB, zA, xA, hC, zC, pl);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -274,7 +274,11 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
     __syncwarp();   // the previous box's reads of this warp's scratch are done (no WAR across boxes)
     for (int i = lane; i < kBloomWords; i += 32) ws.bloom[i] = 0u;
     __syncwarp();
-    const int corner = lane >> 2, sub = lane & 3;
+    // Task mapping: lane = (half, corner, triangle): lanes 0..15 take sub-cell `2*pass` of corner (lane >> 1) & 7,
+    // lanes 16..31 sub-cell `2*pass + 1`; the Up / Down triangles of a cell go to neighbouring lanes. A corner has a
+    // second / third / fourth candidate cell only when it lies within cell_margin of a cell boundary, so pass 0 is
+    // normally 16 busy lanes and pass 1 is skipped by the whole warp.
+    const int corner = (lane >> 1) & 7, u = lane & 1;
     float px = b.P[0], pz = b.P[2];
     {
       const float h0 = 0.5f * b.side[0], h1 = 0.5f * b.side[1], h2 = 0.5f * b.side[2];
@@ -285,53 +289,57 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
     const float gx = px * f.iW, gz = pz * f.iD;
     const int cxl = (int)floorf(gx - cell_margin), cxh = (int)floorf(gx + cell_margin);
     const int czl = (int)floorf(gz - cell_margin), czh = (int)floorf(gz + cell_margin);
-    const int ccx = (sub & 1) ? cxh : cxl, ccz = (sub & 2) ? czh : czl;
-    bool act = !((sub & 1) && cxh == cxl) && !((sub & 2) && czh == czl);
-    act = act && ccx >= b.x0 && ccx < b.x1 && ccz >= b.z0 && ccz < b.z1;
     bool hit_own = false;
     bool live[2] = {false, false};
     float lpl[2][4];
     int lidx[2] = {-1, -1};
-    if (act) {
-      float hA, hB, hC, hD;
-      load_cell(f, ccx, ccz, hA, hB, hC, hD);
-      const bool fA = finitef(hA), fB = finitef(hB), fC = finitef(hC), fD = finitef(hD);
-      const bool cA = fA && hA > b.minB, cB = fB && hB > b.minB, cC = fC && hC > b.minB, cD = fD && hD > b.minB;
-      const bool keep[2] = {(cA || cB || cC) && (fA && fB && fC), (cB || cC || cD) && (fB && fC && fD)};
-      const int cell_idx = ((ccx - b.x0) * nCZ + (ccz - b.z0)) * 2;   // emission order: x outer, z inner, Up, Down
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (!keep[u]) continue;
+    for (int pass = 0; pass < 2; ++pass) {
+      const int sub = 2 * pass + (lane >> 4);
+      const int ccx = (sub & 1) ? cxh : cxl, ccz = (sub & 2) ? czh : czl;
+      bool act = !((sub & 1) && cxh == cxl) && !((sub & 2) && czh == czl);
+      act = act && ccx >= b.x0 && ccx < b.x1 && ccz >= b.z0 && ccz < b.z1;
+      if (!__any_sync(kFull, act)) continue;
+      if (act) {
+        float hA, hB, hC, hD;
+        load_cell(f, ccx, ccz, hA, hB, hC, hD);
+        const bool fA = finitef(hA), fB = finitef(hB), fC = finitef(hC), fD = finitef(hD);
+        const bool cA = fA && hA > b.minB, cB = fB && hB > b.minB, cC = fC && hC > b.minB, cD = fD && hD > b.minB;
         const bool isUp = (u == 0);
-        float* pl = lpl[u];
-        cell_plane(f, isUp, ccx, ccz, hA, hB, hC, hD, pl);
-        // Liveness: any plane within eps of this one changes the box-plane depth by far less than tau.
-        const float Q1 = pl[0] * b.R1[0] + pl[1] * b.R1[3] + pl[2] * b.R1[6];
-        const float Q2 = pl[0] * b.R1[1] + pl[1] * b.R1[4] + pl[2] * b.R1[7];
-        const float Q3 = pl[0] * b.R1[2] + pl[1] * b.R1[5] + pl[2] * b.R1[8];
-        const float B1 = fabsf(b.side[0] * Q1), B2 = fabsf(b.side[1] * Q2), B3 = fabsf(b.side[2] * Q3);
-        const float depth = pl[3] + 0.5f * (B1 + B2 + B3) - (pl[0] * b.P[0] + pl[1] * b.P[1] + pl[2] * b.P[2]);
-        const float tau = 16.0f * ARTP_EPS * (1.0f + b.side[0] + b.side[1] + b.side[2] + fabsf(b.P[0]) +
-                                              fabsf(b.P[1]) + fabsf(b.P[2]) + fabsf(pl[3]));
-        if (!(depth >= -tau)) continue;   // dead: no plane of its would-be group can touch the box
-        live[u] = true;
-        lidx[u] = cell_idx + u;
-        // bloom keys of every bucket an eps-matching normal may fall into
-        const int kx0 = (int)floorf((pl[0] - kKeyMargin + 1.0f) * kKeyScale), kx1 = (int)floorf((pl[0] + kKeyMargin + 1.0f) * kKeyScale);
-        const int kz0 = (int)floorf((pl[2] - kKeyMargin + 1.0f) * kKeyScale), kz1 = (int)floorf((pl[2] + kKeyMargin + 1.0f) * kKeyScale);
-        for (int kx = kx0; kx <= kx1; ++kx)
-          for (int kz = kz0; kz <= kz1; ++kz) {
-            const uint32_t hsh = bloom_hash(kx, kz);
-            atomicOr(&ws.bloom[hsh >> 5], 1u << (hsh & 31));
+        const bool keep = isUp ? ((cA || cB || cC) && (fA && fB && fC)) : ((cB || cC || cD) && (fB && fC && fD));
+        const int cell_idx = ((ccx - b.x0) * nCZ + (ccz - b.z0)) * 2;   // emission order: x outer, z inner, Up, Down
+        if (keep) {
+          float* pl = lpl[pass];
+          cell_plane(f, isUp, ccx, ccz, hA, hB, hC, hD, pl);
+          // Liveness: any plane within eps of this one changes the box-plane depth by far less than tau.
+          const float Q1 = pl[0] * b.R1[0] + pl[1] * b.R1[3] + pl[2] * b.R1[6];
+          const float Q2 = pl[0] * b.R1[1] + pl[1] * b.R1[4] + pl[2] * b.R1[7];
+          const float Q3 = pl[0] * b.R1[2] + pl[1] * b.R1[5] + pl[2] * b.R1[8];
+          const float B1 = fabsf(b.side[0] * Q1), B2 = fabsf(b.side[1] * Q2), B3 = fabsf(b.side[2] * Q3);
+          const float depth = pl[3] + 0.5f * (B1 + B2 + B3) - (pl[0] * b.P[0] + pl[1] * b.P[1] + pl[2] * b.P[2]);
+          const float tau = 16.0f * ARTP_EPS * (1.0f + b.side[0] + b.side[1] + b.side[2] + fabsf(b.P[0]) +
+                                                fabsf(b.P[1]) + fabsf(b.P[2]) + fabsf(pl[3]));
+          if (depth >= -tau) {   // else dead: no plane of its would-be group can touch the box
+            live[pass] = true;
+            lidx[pass] = cell_idx + u;
+            // bloom keys of every bucket an eps-matching normal may fall into
+            const int kx0 = (int)floorf((pl[0] - kKeyMargin + 1.0f) * kKeyScale), kx1 = (int)floorf((pl[0] + kKeyMargin + 1.0f) * kKeyScale);
+            const int kz0 = (int)floorf((pl[2] - kKeyMargin + 1.0f) * kKeyScale), kz1 = (int)floorf((pl[2] + kKeyMargin + 1.0f) * kKeyScale);
+            for (int kx = kx0; kx <= kx1; ++kx)
+              for (int kz = kz0; kz <= kz1; ++kz) {
+                const uint32_t hsh = bloom_hash(kx, kz);
+                atomicOr(&ws.bloom[hsh >> 5], 1u << (hsh & 31));
+              }
+            // contact points with the triangle's OWN plane (valid if it turns out to be its group base)
+            float cx[4], cz[4];
+            const int nc = box_plane(b, pl, 4, cx, cz);
+            const int tcx = isUp ? ccx : ccx + 1, tcz = isUp ? ccz : ccz + 1;
+            for (int i = 0; i < nc; ++i) hit_own = hit_own || on_tri(f, isUp, tcx, tcz, cx[i], cz[i]);
           }
-        // contact points with the triangle's OWN plane (valid if it turns out to be its group base)
-        float cx[4], cz[4];
-        const int nc = box_plane(b, pl, 4, cx, cz);
-        const int tcx = isUp ? ccx : ccx + 1, tcz = isUp ? ccz : ccz + 1;
-        for (int i = 0; i < nc; ++i) hit_own = hit_own || on_tri(f, isUp, tcx, tcz, cx[i], cz[i]);
+        }
       }
     }
-    // compact the live candidates: [Up of lanes..., Down of lanes...]
+    // compact the live candidates: [pass 0 of lanes..., pass 1 of lanes...]
     const unsigned m0 = __ballot_sync(kFull, live[0]), m1 = __ballot_sync(kFull, live[1]);
     const int nLive = __popc(m0) + __popc(m1);
     if (nLive == 0) return R_FREE;
