@@ -740,7 +740,45 @@ __device__ int box_collide_block(const Field& f, const BoxCtx& b, const BlockSha
     if (keepDn) { cell_plane(f, false, cx, cz, hA, hB, hC, hD, sh.planes + 4 * (i0 + 1)); sh.group[i0 + 1] = i0 + 1; }
   }
   if (__syncthreads_or(hit)) return R_HIT;
+  // Singleton screen. The greedy grouping below is sequential in the number of groups (~T when nothing merges:
+  // 2000 block-wide steps, 60 us for a torso zone). A triangle can absorb or be absorbed only if some OTHER kept
+  // triangle epsilon-matches it, and matching planes have normals within eps, i.e. the other's (n0, n2) bucket lies in
+  // this one's +-kKeyMargin neighbourhood. Two bit tables over the hashed buckets (occupied, occupied twice) find the
+  // triangles that cannot have a partner: they are their own group, marked assigned up front; the sequential loop only
+  // walks the rest (normally none).
+  {
+    __shared__ uint32_t occ1[kBloomWords], occ2[kBloomWords];
+    for (int i = tid; i < kBloomWords; i += nthr) { occ1[i] = 0u; occ2[i] = 0u; }
+    __syncthreads();
+    for (int m = tid; m < T; m += nthr) {
+      if (sh.group[m] < 0) continue;
+      const float* pm = sh.planes + 4 * m;
+      const uint32_t hsh = bloom_hash((int)floorf((pm[0] + 1.0f) * kKeyScale), (int)floorf((pm[2] + 1.0f) * kKeyScale));
+      const uint32_t bit = 1u << (hsh & 31);
+      if (atomicOr(&occ1[hsh >> 5], bit) & bit) atomicOr(&occ2[hsh >> 5], bit);
+    }
+    __syncthreads();
+    int any_pot = 0;
+    for (int m = tid; m < T; m += nthr) {
+      if (sh.group[m] < 0) continue;
+      const float* pm = sh.planes + 4 * m;
+      const int kxc = (int)floorf((pm[0] + 1.0f) * kKeyScale), kzc = (int)floorf((pm[2] + 1.0f) * kKeyScale);
+      const int kx0 = (int)floorf((pm[0] - kKeyMargin + 1.0f) * kKeyScale), kx1 = (int)floorf((pm[0] + kKeyMargin + 1.0f) * kKeyScale);
+      const int kz0 = (int)floorf((pm[2] - kKeyMargin + 1.0f) * kKeyScale), kz1 = (int)floorf((pm[2] + kKeyMargin + 1.0f) * kKeyScale);
+      bool pot = false;
+      for (int kx = kx0; kx <= kx1; ++kx)
+        for (int kz = kz0; kz <= kz1; ++kz) {
+          const uint32_t hsh = bloom_hash(kx, kz);
+          const uint32_t* tab = (kx == kxc && kz == kzc) ? occ2 : occ1;   // own bucket: someone else must be there too
+          pot = pot || ((tab[hsh >> 5] >> (hsh & 31)) & 1u);
+        }
+      if (pot) any_pot = 1; else sh.state[m] = 1;
+    }
+    any_pot = __syncthreads_or(any_pot);
+    if (!any_pot) goto groups_done;
+  }
   // greedy grouping (heightfield.cpp:1511-1556)
+  {
   int k = -1;
   for (;;) {
     if (tid == 0) {
@@ -765,6 +803,8 @@ __device__ int box_collide_block(const Field& f, const BoxCtx& b, const BlockSha
     if (tid == 0) sh.state[k] = 1;
     __syncthreads();
   }
+  }
+groups_done:
   // per-group plane contacts vs member triangles (heightfield.cpp:1573-1617), evaluated per member
   hit = 0;
   for (int m = tid; m < T; m += nthr) {
