@@ -585,26 +585,28 @@ classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs, 
     if (w.edge_mode) { if (!result) w.valid[slot] = 0; }
     else w.valid[slot] = (uint8_t)result;
   }
-  // queue the undecided boxes: one warp-aggregated atomic per round
-#pragma unroll 1
-  for (int q = 0; q < 5; ++q) {
-    const bool have = q < n_und;
-    const unsigned m = __ballot_sync(kFull, have);
-    if (m == 0) break;
-    uint32_t basei = 0;
-    const int leader = __ffs(m) - 1;
-    if (lane == leader) basei = atomicAdd(rec_count, (uint32_t)__popc(m));
-    basei = __shfl_sync(kFull, basei, leader);
-    if (have) {
-      BoxRec& o = recs[basei + __popc(m & ((1u << lane) - 1u))];
-      const BoxCtx& b = ub[q];
+  // queue the undecided boxes: one atomic per warp (inclusive scan of the per-lane counts)
+  int incl = n_und;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) o.R1[i] = R1[i];
-      o.P[0] = b.P[0]; o.P[1] = b.P[1]; o.P[2] = b.P[2];
-      o.minB = b.minB; o.maxB = b.maxB;
-      o.x0 = b.x0; o.x1 = b.x1; o.z0 = b.z0; o.z1 = b.z1;
-      o.item = item; o.flags = uflags[q];
-    }
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += y;
+  }
+  const int total = __shfl_sync(kFull, incl, 31);
+  if (total == 0) return;
+  uint32_t basei = 0;
+  if (lane == 31) basei = atomicAdd(rec_count, (uint32_t)total);
+  basei = __shfl_sync(kFull, basei, 31) + (uint32_t)(incl - n_und);
+#pragma unroll 1
+  for (int q = 0; q < n_und; ++q) {
+    BoxRec& o = recs[basei + q];
+    const BoxCtx& b = ub[q];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o.R1[i] = R1[i];
+    o.P[0] = b.P[0]; o.P[1] = b.P[1]; o.P[2] = b.P[2];
+    o.minB = b.minB; o.maxB = b.maxB;
+    o.x0 = b.x0; o.x1 = b.x1; o.z0 = b.z0; o.z1 = b.z1;
+    o.item = item; o.flags = uflags[q];
   }
 }
 
