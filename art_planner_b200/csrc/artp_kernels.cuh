@@ -451,7 +451,7 @@ __device__ __forceinline__ void rec_to_ctx(const Checker& c, const BoxRec& r, Bo
 // ---------------------------------------------------------------------------------------------
 // Stage A: one thread per work item.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs, uint32_t* __restrict__ rec_count,
                       int flags) {
   const int force_all = flags & 1;      // every in-map box goes to the later stages (artp_set_mode 1)

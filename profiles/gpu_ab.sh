@@ -1,2 +1,1 @@
-timeout 800 python -m pytest tests/test_pose_gpu.py tests/test_motion_gpu.py -x -q -m gpu 2>&1 | tail -3
-for F in 0 8; do echo "ARTP_K0_FLAGS=$F"; ARTP_K0_FLAGS=$F bash profiles/gpu_quick.sh; done
+for V in lb8 lb10; do cp variants_tmp/libartp_$V.so art_planner_b200/libartp.so; echo "variant $V"; ARTP_SKIP_BUILD=1 bash profiles/gpu_quick.sh; done
