@@ -23,7 +23,7 @@
 namespace artp {
 
 constexpr int kWarpsPerCta = 8;
-constexpr int kMaxCand = 64;          // 32 lanes x (Up, Down)
+constexpr int kMaxCand = 32;          // live candidates kept per box (more -> the box goes to the grouping stage)
 constexpr int kBloomWords = 128;      // 4096-bit filter per warp
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -343,6 +343,7 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
     const unsigned m0 = __ballot_sync(kFull, live[0]), m1 = __ballot_sync(kFull, live[1]);
     const int nLive = __popc(m0) + __popc(m1);
     if (nLive == 0) return R_FREE;
+    if (nLive > kMaxCand) return R_DEFER;   // exact fallback; needs > 32 live corner candidates (not seen in practice)
     const unsigned below = (1u << lane) - 1u;
     if (live[0]) {
       const int p = __popc(m0 & below);
