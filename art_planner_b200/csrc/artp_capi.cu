@@ -60,6 +60,7 @@ struct Handle {
   bool has_device_normals = false;  // artp_estimate_normals filled normal_x/y/z/std_dev of d_samp_layers for this map
   void* d_samp_scratch = nullptr;
   size_t samp_scratch_cap = 0;
+  uint8_t* h_small_out = nullptr;   // mapped pinned host bytes the latency-path kernel writes its verdicts to
   int timing = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
@@ -296,7 +297,9 @@ int run_items(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed = nu
                                                                                       (h->mode == 1 ? 1 : 0) | h->k0_flags);
       CU_TRY(h, cudaGetLastError());
       if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[1], s));
-      artp::box_items_warp_kernel<<<h->k1_grid, artp::kWarpsPerCta * 32, 0, s>>>(h->chk, w, h->d_recs, h->d_ctr + 3, h->d_ctr,
+      // small batches (the planner's one-state isValid calls): no more CTAs than there can be boxes
+      const unsigned grid_b = (unsigned)std::min<size_t>((size_t)h->k1_grid, (5 * (hi - lo) + artp::kWarpsPerCta - 1) / artp::kWarpsPerCta);
+      artp::box_items_warp_kernel<<<grid_b, artp::kWarpsPerCta * 32, 0, s>>>(h->chk, w, h->d_recs, h->d_ctr + 3, h->d_ctr,
                                                                                   h->d_ctr + 1, h->d_defer, h->mode == 1);
       CU_TRY(h, cudaGetLastError());
       if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[2], s));
@@ -304,7 +307,8 @@ int run_items(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed = nu
     }
     w.item_base = (uint32_t)base;
     w.n_items = (uint32_t)end;
-    artp::box_items_block_kernel<<<h->k2_grid, 256, h->k2_smem, s>>>(h->chk, w, h->d_recs, h->d_ctr + 1, h->d_defer,
+    const unsigned grid_c = (unsigned)std::min<size_t>((size_t)h->k2_grid, 5 * (end - base));
+    artp::box_items_block_kernel<<<grid_c, 256, h->k2_smem, s>>>(h->chk, w, h->d_recs, h->d_ctr + 1, h->d_defer,
                                                                       h->k2_tcap, h->d_ctr + 2);
     CU_TRY(h, cudaGetLastError());
     if (h->timing && last_round) { CU_TRY(h, cudaEventRecord(h->ev[3], s)); h->ev_valid = true; }
@@ -398,6 +402,7 @@ void artp_destroy(artp_handle* hh) {
   for (int k = 0; k < 2; ++k) for (int l = 0; l <= artp::kMaxLevel; ++l) { cudaFree(h->d_T[k][l]); cudaFree(h->d_NF[k][l]); }
   cudaFree(h->d_H[0]); cudaFree(h->d_H[1]); cudaFree(h->d_ctr); cudaFree(h->d_defer); cudaFree(h->d_stage);
   cudaFree(h->d_block_counts); cudaFree(h->d_recs); cudaFree(h->d_samp_layers); cudaFree(h->d_samp_scratch);
+  if (h->h_small_out) cudaFreeHost(h->h_small_out);
   artp_cnn::destroy(h->cnn);
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
@@ -556,6 +561,26 @@ int artp_check_poses_device(artp_handle* hh, const double* d_states, size_t n, u
   return ARTP_OK;
 }
 
+// Latency path for n <= kSmallBatch host states (doubles): one launch, verdicts through mapped host memory.
+static int check_poses_small(Handle* h, const artp::SmallBatch& sb, size_t n, uint8_t* valid) {
+  if (!h->h_small_out) {
+    CU_TRY(h, cudaHostAlloc((void**)&h->h_small_out, 64, cudaHostAllocMapped));
+    CU_TRY(h, cudaFuncSetAttribute(artp::pose_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
+  uint8_t* d_out = nullptr;
+  CU_TRY(h, cudaHostGetDevicePointer((void**)&d_out, h->h_small_out, 0));
+  artp::pose_small_kernel<<<(unsigned)n, 256, h->k2_smem, h->stream>>>(h->chk, sb, d_out, h->k2_tcap, h->d_ctr + 2,
+                                                                        h->mode == 1);
+  CU_TRY(h, cudaGetLastError());
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  std::memcpy(valid, h->h_small_out, n);
+  h->stats.kernel_launches += 1;
+  h->stats.last_launches = 1;
+  h->stats.poses_checked += n;
+  h->ev_valid = false;
+  return ARTP_OK;
+}
+
 int artp_check_poses(artp_handle* hh, const double* states, size_t n, uint8_t* valid) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
@@ -565,6 +590,11 @@ int artp_check_poses(artp_handle* hh, const double* states, size_t n, uint8_t* v
   if (n == 0) return ARTP_OK;
   if (!states || !valid) { h->err = "null buffer"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
+  if (n <= (size_t)artp::kSmallBatch && !h->timing) {
+    artp::SmallBatch sb;
+    std::memcpy(sb.s, states, n * 7 * sizeof(double));
+    return check_poses_small(h, sb, n, valid);
+  }
   const size_t in_bytes = n * 7 * sizeof(double), out_off = (in_bytes + 255) & ~(size_t)255;
   rc = ensure_stage(h, out_off + n);
   if (rc) return rc;
@@ -612,6 +642,11 @@ int artp_check_poses_f32(artp_handle* hh, const float* states, size_t n, uint8_t
   if (n == 0) return ARTP_OK;
   if (!states || !valid) { h->err = "null buffer"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
+  if (n <= (size_t)artp::kSmallBatch && !h->timing) {
+    artp::SmallBatch sb;
+    for (size_t i = 0; i < n * 7; ++i) (&sb.s[0][0])[i] = (double)states[i];   // exact; cast back to float in the kernel
+    return check_poses_small(h, sb, n, valid);
+  }
   const size_t in_bytes = n * 7 * sizeof(float), out_off = (in_bytes + 255) & ~(size_t)255;
   rc = ensure_stage(h, out_off + n);
   if (rc) return rc;

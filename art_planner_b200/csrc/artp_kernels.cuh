@@ -449,6 +449,109 @@ __device__ __forceinline__ void rec_to_ctx(const Checker& c, const BoxRec& r, Bo
   b.side[0] = c.side[w][0]; b.side[1] = c.side[w][1]; b.side[2] = c.side[w][2];
 }
 
+// One box of one item in the classify stage: box pose, zone, range-table reductions, the collider's early outs and the
+// vertex probes. Returns R_FREE / R_HIT when decided, -1 when the box needs the vertex / plane stages (b and fl are
+// then complete), kBoxOutside when the box centre is outside the map (the caller applies the outside-map rule).
+constexpr int kBoxOutside = -2;
+__device__ __forceinline__ int classify_box(const Checker& c, const float R[9], const float R1[9], const float t[3], int k,
+                                            int force_all, bool probe, BoxCtx& b, uint32_t& fl) {
+  const Field& g = c.f[0];      // both layers share the map geometry
+  const bool foot = k > 0;
+  const int fk = k - 1;
+  const float ox = foot ? ((fk & 2) ? -c.feet_ox : c.feet_ox) : c.torso_off[0];
+  const float oy = foot ? ((fk & 1) ? -c.feet_oy : c.feet_oy) : c.torso_off[1];
+  const float oz = foot ? 0.0f : c.torso_off[2];
+  const float sd0 = foot ? c.side[1][0] : c.side[0][0], sd1 = foot ? c.side[1][1] : c.side[0][1],
+              sd2 = foot ? c.side[1][2] : c.side[0][2];
+  float tt[3];
+  compose_translation(R, t, ox, oy, oz, tt);
+  if (!is_inside(c, tt[0], tt[1])) return kBoxOutside;   // validity_checker_body.cpp:29-32, validity_checker_feet.cpp:34-37
+  // dCollideHeightfield prologue + dxBox::computeAABB (see box_setup())
+  const float d0 = tt[0] - g.px, d1 = tt[1] - g.py, d2 = tt[2] - 0.0f;
+  b.P[0] = -d0 + g.hW; b.P[1] = d2; b.P[2] = d1 + g.hD;
+  const float xr = 0.5f * (fabsf(R1[0] * sd0) + fabsf(R1[1] * sd1) + fabsf(R1[2] * sd2));
+  const float yr = 0.5f * (fabsf(R1[3] * sd0) + fabsf(R1[4] * sd1) + fabsf(R1[5] * sd2));
+  const float zr = 0.5f * (fabsf(R1[6] * sd0) + fabsf(R1[7] * sd1) + fabsf(R1[8] * sd2));
+  const float a0 = b.P[0] - xr, a1 = b.P[0] + xr, a4 = b.P[2] - zr, a5 = b.P[2] + zr;
+  b.minB = b.P[1] - yr; b.maxB = b.P[1] + yr;
+  int r;                        // R_FREE / R_HIT / -1 undecided
+  fl = (uint32_t)k;
+  if ((a0 > g.W || a4 > g.D) || (a1 < 0.0f || a5 < 0.0f)) {
+    r = R_FREE;                 // dCollide returns 0 (heightfield.cpp:1870-1876)
+  } else {
+    b.x0 = max((int)floorf(next_down(a0 * g.iW)), 0);
+    b.x1 = min((int)ceilf(next_up(a1 * g.iW)), g.nx - 1);
+    b.z0 = max((int)floorf(next_down(a4 * g.iD)), 0);
+    b.z1 = min((int)ceilf(next_up(a5 * g.iD)), g.nz - 1);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) b.R1[i] = R1[i];
+    b.side[0] = sd0; b.side[1] = sd1; b.side[2] = sd2;
+    // zone reductions from the range tables (exact: max/min/or are idempotent, windows may overlap)
+    const Field& f = foot ? c.f[1] : c.f[0];
+    const int nX = b.x1 - b.x0 + 1, nZ = b.z1 - b.z0 + 1;
+    const int kk = 31 - __clz(min(nX, nZ));
+    const int cx = (nX + (1 << kk) - 1) >> kk, cz = (nZ + (1 << kk) - 1) >> kk;
+    if (force_all || kk < 1 || kk > f.kmax || cx * cz > 32) {
+      r = -1; fl |= REC_NEEDS_REDUCE;
+    } else {
+      const float2* __restrict__ T = f.T[kk];
+      const unsigned char* __restrict__ NF = f.NF[kk];
+      const int sW = 1 << kk;
+      float mx = -CUDART_INF_F, mn = CUDART_INF_F;
+      int nf = 0;
+      if (cx <= 2 && cz <= 2) {
+        // the common case (window edge > half the zone edge): all four windows are requested before any is used
+        const int xs0 = b.x0, xs1 = b.x1 - sW + 1, zs0 = b.z0, zs1 = b.z1 - sW + 1;
+        const size_t i00 = (size_t)zs0 * f.pitch + xs0, i01 = (size_t)zs0 * f.pitch + xs1,
+                     i10 = (size_t)zs1 * f.pitch + xs0, i11 = (size_t)zs1 * f.pitch + xs1;
+        const float2 v0 = __ldg(T + i00), v1 = __ldg(T + i01), v2 = __ldg(T + i10), v3 = __ldg(T + i11);
+        const int n0 = __ldg(NF + i00), n1 = __ldg(NF + i01), n2 = __ldg(NF + i10), n3 = __ldg(NF + i11);
+        mx = fmaxf(fmaxf(v0.x, v1.x), fmaxf(v2.x, v3.x));
+        mn = fminf(fminf(v0.y, v1.y), fminf(v2.y, v3.y));
+        nf = n0 | n1 | n2 | n3;
+      } else {
+        for (int iz = 0; iz < cz; ++iz) {
+          const int zs = min(b.z0 + iz * sW, b.z1 - sW + 1);
+          for (int ix = 0; ix < cx; ++ix) {
+            const int xs = min(b.x0 + ix * sW, b.x1 - sW + 1);
+            const size_t idx = (size_t)zs * f.pitch + xs;
+            const float2 v = __ldg(T + idx);
+            mx = fmaxf(mx, v.x); mn = fminf(mn, v.y);
+            nf |= __ldg(NF + idx);
+          }
+        }
+      }
+      const bool allFinite = nf == 0;
+      r = zone_early_out(b, mx, mn, allFinite);
+      if (allFinite) fl |= REC_ALLFINITE;
+      if (r == -1 && allFinite && nX >= 2 && nZ >= 2 && probe) {
+        // Vertex probes. In an all-finite zone every vertex with h > minB belongs to a kept triangle, and the
+        // collider returns 1 as soon as ANY such vertex lies inside the box (heightfield.cpp:1344-1441), so a
+        // hit found here is exactly the reference's answer; a miss decides nothing and the box is queued.
+        // Reach box: the cell under the box centre; torso: a 3x3 pattern across the footprint.
+        // (measured: 3x3 / 5x5 reach-box patterns remove another 25 % of the queue but cost the classify stage
+        // twice what the warp stage saves -- one thread walks them serially)
+        const int np = foot ? 1 : 9;
+        const float h0 = 0.5f * sd0, h1 = 0.5f * sd1;
+        for (int pi = 0; pi < np && r == -1; ++pi) {
+          const float u0 = foot ? 0.0f : 0.7f * (float)(pi % 3 - 1), u1 = foot ? 0.0f : 0.7f * (float)(pi / 3 - 1);
+          const float qx = b.P[0] + (u0 * h0) * R1[0] + (u1 * h1) * R1[1];
+          const float qz = b.P[2] + (u0 * h0) * R1[6] + (u1 * h1) * R1[7];
+          const int pcx = min(max((int)floorf(qx * g.iW), b.x0), b.x1 - 1);
+          const int pcz = min(max((int)floorf(qz * g.iD), b.z0), b.z1 - 1);
+          float hA, hB, hC, hD;
+          load_cell(f, pcx, pcz, hA, hB, hC, hD);
+          const float xA = pcx * f.sW, xB = (pcx + 1) * f.sW, zA = pcz * f.sD, zC = (pcz + 1) * f.sD;
+          if ((hA > b.minB && vertex_inside(b, xA, hA, zA)) || (hB > b.minB && vertex_inside(b, xB, hB, zA)) ||
+              (hC > b.minB && vertex_inside(b, xA, hC, zC)) || (hD > b.minB && vertex_inside(b, xB, hD, zC)))
+            r = R_HIT;
+        }
+      }
+    }
+  }
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Stage A: one thread per work item.
 // ---------------------------------------------------------------------------------------------
@@ -477,105 +580,15 @@ classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs, 
     orthogonalize_r(Rb);          // dBodySetRotation of the same matrix for all five boxes
 #pragma unroll
     for (int j = 0; j < 3; ++j) { R1[j] = -Rb[j]; R1[3 + j] = Rb[6 + j]; R1[6 + j] = Rb[3 + j]; }
-    const Field& g = c.f[0];      // both layers share the map geometry
 #pragma unroll 1
     for (int k = 0; k < 5 && result; ++k) {
+      BoxCtx b;
+      uint32_t fl;
       const bool foot = k > 0;
-      const int fk = k - 1;
-      const float ox = foot ? ((fk & 2) ? -c.feet_ox : c.feet_ox) : c.torso_off[0];
-      const float oy = foot ? ((fk & 1) ? -c.feet_oy : c.feet_oy) : c.torso_off[1];
-      const float oz = foot ? 0.0f : c.torso_off[2];
-      const float sd0 = foot ? c.side[1][0] : c.side[0][0], sd1 = foot ? c.side[1][1] : c.side[0][1],
-                  sd2 = foot ? c.side[1][2] : c.side[0][2];
-      float tt[3];
-      compose_translation(R, t, ox, oy, oz, tt);
-      if (!is_inside(c, tt[0], tt[1])) {       // validity_checker_body.cpp:29-32, validity_checker_feet.cpp:34-37
+      const int r = classify_box(c, R, R1, t, k, force_all, probe, b, fl);
+      if (r == kBoxOutside) {
         if (foot && c.unknown_untraversable) result = 0;
         continue;
-      }
-      // dCollideHeightfield prologue + dxBox::computeAABB (see box_setup())
-      BoxCtx b;
-      const float d0 = tt[0] - g.px, d1 = tt[1] - g.py, d2 = tt[2] - 0.0f;
-      b.P[0] = -d0 + g.hW; b.P[1] = d2; b.P[2] = d1 + g.hD;
-      const float xr = 0.5f * (fabsf(R1[0] * sd0) + fabsf(R1[1] * sd1) + fabsf(R1[2] * sd2));
-      const float yr = 0.5f * (fabsf(R1[3] * sd0) + fabsf(R1[4] * sd1) + fabsf(R1[5] * sd2));
-      const float zr = 0.5f * (fabsf(R1[6] * sd0) + fabsf(R1[7] * sd1) + fabsf(R1[8] * sd2));
-      const float a0 = b.P[0] - xr, a1 = b.P[0] + xr, a4 = b.P[2] - zr, a5 = b.P[2] + zr;
-      b.minB = b.P[1] - yr; b.maxB = b.P[1] + yr;
-      int r;                        // R_FREE / R_HIT / -1 undecided
-      uint32_t fl = (uint32_t)k;
-      if ((a0 > g.W || a4 > g.D) || (a1 < 0.0f || a5 < 0.0f)) {
-        r = R_FREE;                 // dCollide returns 0 (heightfield.cpp:1870-1876)
-      } else {
-        b.x0 = max((int)floorf(next_down(a0 * g.iW)), 0);
-        b.x1 = min((int)ceilf(next_up(a1 * g.iW)), g.nx - 1);
-        b.z0 = max((int)floorf(next_down(a4 * g.iD)), 0);
-        b.z1 = min((int)ceilf(next_up(a5 * g.iD)), g.nz - 1);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) b.R1[i] = R1[i];
-        b.side[0] = sd0; b.side[1] = sd1; b.side[2] = sd2;
-        // zone reductions from the range tables (exact: max/min/or are idempotent, windows may overlap)
-        const Field& f = foot ? c.f[1] : c.f[0];
-        const int nX = b.x1 - b.x0 + 1, nZ = b.z1 - b.z0 + 1;
-        const int kk = 31 - __clz(min(nX, nZ));
-        const int cx = (nX + (1 << kk) - 1) >> kk, cz = (nZ + (1 << kk) - 1) >> kk;
-        if (force_all || kk < 1 || kk > f.kmax || cx * cz > 32) {
-          r = -1; fl |= REC_NEEDS_REDUCE;
-        } else {
-          const float2* __restrict__ T = f.T[kk];
-          const unsigned char* __restrict__ NF = f.NF[kk];
-          const int sW = 1 << kk;
-          float mx = -CUDART_INF_F, mn = CUDART_INF_F;
-          int nf = 0;
-          if (cx <= 2 && cz <= 2) {
-            // the common case (window edge > half the zone edge): all four windows are requested before any is used
-            const int xs0 = b.x0, xs1 = b.x1 - sW + 1, zs0 = b.z0, zs1 = b.z1 - sW + 1;
-            const size_t i00 = (size_t)zs0 * f.pitch + xs0, i01 = (size_t)zs0 * f.pitch + xs1,
-                         i10 = (size_t)zs1 * f.pitch + xs0, i11 = (size_t)zs1 * f.pitch + xs1;
-            const float2 v0 = __ldg(T + i00), v1 = __ldg(T + i01), v2 = __ldg(T + i10), v3 = __ldg(T + i11);
-            const int n0 = __ldg(NF + i00), n1 = __ldg(NF + i01), n2 = __ldg(NF + i10), n3 = __ldg(NF + i11);
-            mx = fmaxf(fmaxf(v0.x, v1.x), fmaxf(v2.x, v3.x));
-            mn = fminf(fminf(v0.y, v1.y), fminf(v2.y, v3.y));
-            nf = n0 | n1 | n2 | n3;
-          } else {
-            for (int iz = 0; iz < cz; ++iz) {
-              const int zs = min(b.z0 + iz * sW, b.z1 - sW + 1);
-              for (int ix = 0; ix < cx; ++ix) {
-                const int xs = min(b.x0 + ix * sW, b.x1 - sW + 1);
-                const size_t idx = (size_t)zs * f.pitch + xs;
-                const float2 v = __ldg(T + idx);
-                mx = fmaxf(mx, v.x); mn = fminf(mn, v.y);
-                nf |= __ldg(NF + idx);
-              }
-            }
-          }
-          const bool allFinite = nf == 0;
-          r = zone_early_out(b, mx, mn, allFinite);
-          if (allFinite) fl |= REC_ALLFINITE;
-          if (r == -1 && allFinite && nX >= 2 && nZ >= 2 && probe) {
-            // Vertex probes. In an all-finite zone every vertex with h > minB belongs to a kept triangle, and the
-            // collider returns 1 as soon as ANY such vertex lies inside the box (heightfield.cpp:1344-1441), so a
-            // hit found here is exactly the reference's answer; a miss decides nothing and the box is queued.
-            // Reach box: the cell under the box centre; torso: a 3x3 pattern across the footprint.
-            // (measured: 3x3 / 5x5 reach-box patterns remove another 25 % of the queue but cost the classify stage
-            // twice what the warp stage saves -- one thread walks them serially)
-            const int np = foot ? 1 : 9;
-            const float h0 = 0.5f * sd0, h1 = 0.5f * sd1;
-            for (int pi = 0; pi < np && r == -1; ++pi) {
-              const float u0 = foot ? 0.0f : 0.7f * (float)(pi % 3 - 1), u1 = foot ? 0.0f : 0.7f * (float)(pi / 3 - 1);
-              const float qx = b.P[0] + (u0 * h0) * R1[0] + (u1 * h1) * R1[1];
-              const float qz = b.P[2] + (u0 * h0) * R1[6] + (u1 * h1) * R1[7];
-              const int pcx = min(max((int)floorf(qx * g.iW), b.x0), b.x1 - 1);
-              const int pcz = min(max((int)floorf(qz * g.iD), b.z0), b.z1 - 1);
-              float hA, hB, hC, hD;
-              load_cell(f, pcx, pcz, hA, hB, hC, hD);
-              const float xA = pcx * f.sW, xB = (pcx + 1) * f.sW, zA = pcz * f.sD, zC = (pcz + 1) * f.sD;
-              if ((hA > b.minB && vertex_inside(b, xA, hA, zA)) || (hB > b.minB && vertex_inside(b, xB, hB, zA)) ||
-                  (hC > b.minB && vertex_inside(b, xA, hC, zC)) || (hD > b.minB && vertex_inside(b, xB, hD, zC)))
-                r = R_HIT;
-            }
-          }
-        }
       }
       if (r == -1) { ub[n_und] = b; uflags[n_und] = fl; ++n_und; }
       else if (!foot) { if (r == R_HIT) result = 0; }      // torso must be free
@@ -851,6 +864,85 @@ box_items_block_kernel(const Checker c, const Work w, const BoxRec* __restrict__
     }
     __syncthreads();
   }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Latency path: the planner's one-state-at-a-time isValid calls (ompl::base::StateValidityChecker::isValid). One launch
+// does everything for up to kSmallBatch poses -- the states travel in the kernel parameter block and the verdicts are
+// written straight to mapped host memory, so a call is one launch + one stream synchronise instead of memset, H2D,
+// three launches and D2H. One CTA per pose: threads 0..4 classify the five boxes, warps 0..4 run the warp-stage
+// decision of the undecided ones, the whole CTA handles a deferred box with the grouping-stage code.
+// -------------------------------------------------------------------------------------------------
+constexpr int kSmallBatch = 64;
+struct SmallBatch {
+  double s[kSmallBatch][7];
+};
+
+__global__ void __launch_bounds__(256)
+pose_small_kernel(const Checker c, const SmallBatch sb, uint8_t* __restrict__ out, int T_cap, uint32_t* __restrict__ overflow,
+                  int force_all) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float red[8];
+  __shared__ int s_next;
+  __shared__ BoxCtx s_box[5];
+  __shared__ uint32_t s_fl[5];
+  __shared__ int s_res[5];          // per box: -1 undecided, R_FREE / R_HIT decided, R_DEFER, kBoxOutside
+  __shared__ WarpScratch s_ws[5];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid < 5) {
+    double st[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) st[i] = sb.s[blockIdx.x][i];
+    float t[3], R[9], Rb[9], R1[9];
+    pose3_from_se3(st, t, R);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rb[i] = R[i];
+    orthogonalize_r(Rb);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { R1[j] = -Rb[j]; R1[3 + j] = Rb[6 + j]; R1[6 + j] = Rb[3 + j]; }
+    BoxCtx b;
+    uint32_t fl = 0;
+    const int r = classify_box(c, R, R1, t, tid, force_all, true, b, fl);
+    s_res[tid] = r;
+    if (r == -1) { s_box[tid] = b; s_fl[tid] = fl; }
+  }
+  __syncthreads();
+  // item verdict from the decided boxes (validity_checker.cpp:39-45 and the outside-map rules)
+  bool valid = true;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int r = s_res[k];
+    if (r == kBoxOutside) { if (k > 0 && c.unknown_untraversable) valid = false; }
+    else if (k == 0) { if (r == R_HIT) valid = false; }
+    else if (r == R_FREE) valid = false;
+  }
+  if (valid && !force_all && wid < 5 && s_res[wid] == -1) {
+    const bool foot = wid > 0;
+    const int res = box_collide_warp(foot ? c.f[1] : c.f[0], s_box[wid], s_ws[wid], lane, c.cell_margin,
+                                     (s_fl[wid] & REC_NEEDS_REDUCE) != 0, (s_fl[wid] & REC_ALLFINITE) != 0);
+    if (lane == 0) s_res[wid] = res;
+  }
+  __syncthreads();
+  if (valid) {
+    BlockShared sh;
+    sh.T_cap = T_cap;
+    sh.planes = reinterpret_cast<float*>(smem_raw);
+    sh.group = reinterpret_cast<int*>(smem_raw + (size_t)T_cap * 16);
+    sh.state = reinterpret_cast<uint8_t*>(smem_raw + (size_t)T_cap * 20);
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) {
+      int r = s_res[k];                       // block-uniform
+      if (r == -1 || r == R_DEFER) {          // -1 only in force_all mode
+        const bool foot = k > 0;
+        r = box_collide_block(foot ? c.f[1] : c.f[0], s_box[k], sh, red, &s_next);
+        if (r == R_DEFER && tid == 0) atomicAdd(overflow, 1u);
+        __syncthreads();
+      }
+      if (r == kBoxOutside) continue;
+      if ((k == 0 && r == R_HIT) || (k > 0 && r == R_FREE)) valid = false;
+    }
+  }
+  if (tid == 0) out[blockIdx.x] = valid ? 1 : 0;
 }
 
 }  // namespace artp

@@ -299,6 +299,22 @@ def main():
             plo.motionCostBatch(d1, d2, out=c_out)
         bb.record(); torch.cuda.synchronize()
         secondary["path_length_cost"] = {"evals_per_s": 100_000 * 50 / (a.elapsed_time(bb) * 1e-3)}
+        try:   # latency of small batches through the host-buffer API (what a one-state isValid call pays)
+            lat = {}
+            chk.setTiming(False)   # the one-launch latency path (n <= 16) is bypassed while kernel timing is on
+            for nb in (1, 16, 64, 65, 4096, 65536):
+                hp = h_poses32[:nb]
+                for _ in range(20):
+                    chk.isValidHostPtr(hp.data_ptr(), nb, h_valid.data_ptr(), f32=True)
+                reps = 200 if nb <= 4096 else 50
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    chk.isValidHostPtr(hp.data_ptr(), nb, h_valid.data_ptr(), f32=True)
+                lat[str(nb)] = (time.perf_counter() - t0) / reps * 1e6
+            chk.setTiming(True)
+            secondary["host_api_latency_us_by_batch"] = lat
+        except Exception as ex:
+            secondary["host_api_latency_us_by_batch"] = {"error": repr(ex)}
         try:   # device sampler + fused sample -> isValid -> compact (no host pose stream)
             L = synth.make_sampler_layers(m, seed=7)
             smp = apb.SE3FromSE2Sampler(chk, L, synth.sampler_params_for(m), seed=1)

@@ -180,3 +180,28 @@ def test_bit_packed_mask_and_compaction(maps, checkers):
         torch.cuda.synchronize()
         want = torch.nonzero(v).reshape(-1) + 1000
         assert int(cnt.item()) == want.numel() and torch.equal(idx[: want.numel()].cpu(), want)
+
+
+@pytest.mark.parametrize("mk", ["fbm_rough", "flat_holes_terrace", "fixture"])
+def test_latency_path_small_batches(maps, checkers, port_lib, mk):
+    """n <= 16 host states take the one-launch latency path (pose_small_kernel): same verdicts as the oracle, in both
+    grouping modes, through the double and the float entry points."""
+    m = maps(mk)
+    chk = checkers("yaml")
+    set_map(chk, m)
+    o = port_lib.Oracle(cases.PARAMS["yaml"], "port")
+    o.set_map(m)
+    poses = synth.make_terrain_poses(m, 600, seed=123)
+    ref = o.check_poses(poses)
+    assert 0 < ref.sum() < len(ref)
+    for mode in (0, 1):
+        chk.setMode(mode)
+        pos = 0
+        for n in list(range(1, 17)) * 2 + [17, 33, 63, 64, 64]:
+            chunk = poses[pos:pos + n]
+            assert np.array_equal(chk.isValidBatch(chunk), ref[pos:pos + n]), (mode, n, pos)
+            assert np.array_equal(chk.isValidBatch(chunk.astype(np.float32)), ref[pos:pos + n]), (mode, n, pos)
+            pos += n
+    chk.setMode(0)
+    far = np.array([[1e3, -1e3, 0.0, 0, 0, 0, 1.0]])           # outside the map: the outside-map rules
+    assert np.array_equal(chk.isValidBatch(far), o.check_poses(far))
