@@ -562,7 +562,7 @@ int artp_check_poses_device(artp_handle* hh, const double* d_states, size_t n, u
 }
 
 // Latency path for n <= kSmallBatch host states (doubles): one launch, verdicts through mapped host memory.
-static int check_poses_small(Handle* h, const artp::SmallBatch& sb, size_t n, uint8_t* valid) {
+static int check_poses_small(Handle* h, const artp::SmallBatch& sb, size_t n, uint8_t* valid, int steps = -1) {
   if (!h->h_small_out) {
     CU_TRY(h, cudaHostAlloc((void**)&h->h_small_out, 64, cudaHostAllocMapped));
     CU_TRY(h, cudaFuncSetAttribute(artp::pose_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -570,10 +570,19 @@ static int check_poses_small(Handle* h, const artp::SmallBatch& sb, size_t n, ui
   uint8_t* d_out = nullptr;
   CU_TRY(h, cudaHostGetDevicePointer((void**)&d_out, h->h_small_out, 0));
   artp::pose_small_kernel<<<(unsigned)n, 256, h->k2_smem, h->stream>>>(h->chk, sb, d_out, h->k2_tcap, h->d_ctr + 2,
-                                                                        h->mode == 1);
+                                                                        h->mode == 1, steps);
   CU_TRY(h, cudaGetLastError());
   CU_TRY(h, cudaStreamSynchronize(h->stream));
-  std::memcpy(valid, h->h_small_out, n);
+  if (steps < 0) {
+    std::memcpy(valid, h->h_small_out, n);
+  } else {   // n = edges * (steps + 1) state verdicts -> one flag per edge
+    const size_t per = (size_t)steps + 1;
+    for (size_t e = 0; e < n / per; ++e) {
+      uint8_t ok = 1;
+      for (size_t j = 0; j < per; ++j) ok &= h->h_small_out[e * per + j];
+      valid[e] = ok;
+    }
+  }
   h->stats.kernel_launches += 1;
   h->stats.last_launches = 1;
   h->stats.poses_checked += n;
@@ -692,6 +701,20 @@ int artp_check_motions_device(artp_handle* hh, const double* d_s1, const double*
 int artp_check_motions(artp_handle* hh, const double* s1, const double* s2, size_t n, int n_steps, uint8_t* valid) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
+  if (n > 0 && n_steps >= 0 && n * ((size_t)n_steps + 1) <= (size_t)artp::kSmallBatch && 2 * n <= (size_t)artp::kSmallBatch &&
+      s1 && s2 && valid) {
+    // latency path (a single checkMotion call): one fused launch, interpolation on the device as in the pipeline
+    std::lock_guard<std::mutex> lk(h->mtx);
+    if (h->has_map && !h->timing) {
+      CU_TRY(h, cudaSetDevice(h->device));
+      artp::SmallBatch sb;
+      for (size_t e = 0; e < n; ++e) {
+        std::memcpy(sb.s[2 * e], s1 + 7 * e, 7 * sizeof(double));
+        std::memcpy(sb.s[2 * e + 1], s2 + 7 * e, 7 * sizeof(double));
+      }
+      return check_poses_small(h, sb, n * ((size_t)n_steps + 1), valid, n_steps);
+    }
+  }
   const size_t sb = n * 7 * sizeof(double), sb_al = (sb + 255) & ~(size_t)255;
   {
     std::lock_guard<std::mutex> lk(h->mtx);

@@ -880,7 +880,7 @@ struct SmallBatch {
 
 __global__ void __launch_bounds__(256)
 pose_small_kernel(const Checker c, const SmallBatch sb, uint8_t* __restrict__ out, int T_cap, uint32_t* __restrict__ overflow,
-                  int force_all) {
+                  int force_all, int steps) {   // steps < 0: CTA b checks sb.s[b]; else edges: see below
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float red[8];
   __shared__ int s_next;
@@ -891,8 +891,22 @@ pose_small_kernel(const Checker c, const SmallBatch sb, uint8_t* __restrict__ ou
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid < 5) {
     double st[7];
+    if (steps < 0) {
 #pragma unroll
-    for (int i = 0; i < 7; ++i) st[i] = sb.s[blockIdx.x][i];
+      for (int i = 0; i < 7; ++i) st[i] = sb.s[blockIdx.x][i];
+    } else {
+      // edge e = (s1 = sb.s[2e], s2 = sb.s[2e+1]); CTA e*(steps+1)+j checks s2 (j == 0) or interpolate(s1, s2, j/(steps+1))
+      const uint32_t per = (uint32_t)steps + 1u, e = blockIdx.x / per, j = blockIdx.x - e * per;
+      double a[7], bb[7];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) { a[i] = sb.s[2 * e][i]; bb[i] = sb.s[2 * e + 1][i]; }
+      if (j == 0) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) st[i] = bb[i];
+      } else {
+        se3_interpolate(a, bb, (double)j / (double)per, st);
+      }
+    }
     float t[3], R[9], Rb[9], R1[9];
     pose3_from_se3(st, t, R);
 #pragma unroll

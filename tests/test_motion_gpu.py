@@ -136,3 +136,21 @@ def test_edge_interiors_empty_and_errors(maps, make_checker):
     assert (got == 0).all()
     with pytest.raises(RuntimeError):
         mv.checkEdgeInteriors(s1, s2, n_interp=np.full(10, -1, np.int32))
+
+
+def test_single_edge_latency_path(maps, make_checker, port_lib):
+    """One checkMotion call at a time (<= 64 states) takes the fused one-launch path: same flags as the oracle."""
+    import art_planner_b200 as ap
+    m = maps("fbm_rough")
+    chk = make_checker("yaml", m)
+    o = port_lib.Oracle(cases.PARAMS["yaml"], "port")
+    o.set_map(m)
+    s1, s2 = synth.make_edges(m, 300, 77)
+    for steps in (0, 7, 20, 63):
+        ref = o.check_motions(s1, s2, steps)
+        mv = ap.MotionValidator(chk, steps)
+        got = np.array([mv.checkMotion(s1[i], s2[i]) for i in range(len(s1))], dtype=np.uint8)
+        assert np.array_equal(got, ref), steps
+    ref = o.check_motions(s1, s2, 20)
+    mv = ap.MotionValidator(chk, 20)
+    assert np.array_equal(np.concatenate([mv.checkMotionBatch(s1[i:i + 3], s2[i:i + 3]) for i in range(0, 300, 3)]), ref)
