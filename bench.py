@@ -202,19 +202,33 @@ def main():
     # N > 1 exchange: bit-packed masks (n/32 words per rank) all-gathered in one NCCL call, then every rank compacts
     # the gathered mask into the global ordered valid-index list
     assert n % 32 == 0
-    my_bits = torch.empty(n // 32, dtype=torch.int32, device="cuda")
+    my_bits = [torch.empty(n // 32, dtype=torch.int32, device="cuda") for _ in range(2)]
     all_bits = torch.empty(world * (n // 32), dtype=torch.int32, device="cuda") if world > 1 else None
     gather_idx = torch.empty(world * n, dtype=torch.int64, device="cuda") if world > 1 else None
     gather_cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    side = torch.cuda.Stream() if world > 1 else None
+    ev_done = torch.cuda.Event() if world > 1 else None
 
     from art_planner_b200 import sharding
 
-    def step_device():
+    def exchange(b, after_event):
+        """The verdict exchange of the step that packed my_bits[b]: runs on the side stream, strictly after
+        `after_event` (the START event of the timed window it is accounted to), concurrently with that window's checks."""
+        with torch.cuda.stream(side):
+            side.wait_event(after_event)
+            sharding.gather_valid_bits(my_bits[b], world, out=all_bits)     # 125 KB of mask bits per rank on the wire
+            chk.compactBits(all_bits, world * n, base=0, out_idx=gather_idx, out_cnt=gather_cnt)   # global ordered list
+            ev_done.record(side)
+
+    def step_device(i, start_event):
+        """Window i = checks of step i  ||  exchange of step i-1; the window ends when both are done."""
+        if world > 1 and i > 0:
+            exchange((i - 1) & 1, start_event)
         chk.isValidBatch(d_poses, out=d_valid)
-        if world > 1:   # 125 KB of mask bits per rank on the wire, then the global ordered index list on every rank
-            chk.packValidBits(d_valid, out=my_bits)
-            sharding.gather_valid_bits(my_bits, world, out=all_bits)
-            chk.compactBits(all_bits, world * n, base=0, out_idx=gather_idx, out_cnt=gather_cnt)
+        if world > 1:
+            chk.packValidBits(d_valid, out=my_bits[i & 1])
+            if i > 0:
+                torch.cuda.current_stream().wait_event(ev_done)
 
     def step_e2e():      # what INTEGRATION.md's adapter calls: float32 states (exact), pinned host buffers
         chk.isValidHostPtr(h_poses32.data_ptr(), n, h_valid.data_ptr(), f32=True)
@@ -222,8 +236,13 @@ def main():
     def step_e2e_f64():  # the same through the double entry point (56 B/pose on the wire)
         chk.isValidHostPtr(h_poses.data_ptr(), n, h_valid.data_ptr())
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
+    warm_ev = torch.cuda.Event()
+    for i in range(max(args.warmup, 3)):
+        warm_ev.record()
+        step_device(i, warm_ev)
+    if world > 1:
+        warm_ev.record()
+        exchange((max(args.warmup, 3) - 1) & 1, warm_ev)
     step_e2e()
     torch.cuda.synchronize()
 
@@ -232,7 +251,8 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = chk.stats()["kernel_launches"]
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # one extra window at the end (N > 1): the exchange of the last step
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
     k0_ms, k1_ms, k2_ms = [], [], []
     if world > 1:
         dist.barrier()
@@ -241,15 +261,26 @@ def main():
     for i in range(args.steps):
         flush.fill_(i & 0xFF)               # evict L2 (untimed)
         ev[i][0].record()
-        step_device()
+        step_device(i, ev[i][0])
         ev[i][1].record()
         ka, kb, kc = chk.lastKernelTimesMs()   # waits for this step's kernels (events on the same stream)
         k0_ms.append(ka); k1_ms.append(kb); k2_ms.append(kc)
+    ev[args.steps][0].record()
+    if world > 1:
+        exchange((args.steps - 1) & 1, ev[args.steps][0])
+        torch.cuda.current_stream().wait_event(ev_done)
+    ev[args.steps][1].record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - wall0
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+    exchange_ok = None
+    if world > 1:   # the gathered global index list must hold exactly the valid samples of all ranks
+        tot = d_valid.to(torch.int64).sum().reshape(1)
+        dist.all_reduce(tot)
+        first = int(gather_idx[0].item()) if int(gather_cnt.item()) else -1
+        exchange_ok = bool(int(gather_cnt.item()) == int(tot.item()) and first >= 0)
     launches = chk.stats()["kernel_launches"] - launches0
     deferred = chk.stats()["last_deferred"]
     queued = chk.stats()["last_queued_boxes"]
@@ -416,7 +447,7 @@ def main():
                        "configs[4]: fBm 4000x4000@0.04m map, 1M samples per GPU inside the GPU's spatial slab, yaml robot geometry",
                        "poses_per_gpu": n, "map": f"{m.rows}x{m.cols}@{MAP_RES}",
                        "map_seed": MAP_SEED, "pose_seed": POSE_SEED, "l2": "flushed between timed steps (256 MiB write)",
-                       "parallelism": f"pose shards x{world}, replicated map" + (", NCCL all-gather of bit-packed masks + global ordered compaction on every rank" if world > 1 else "")},
+                       "parallelism": f"pose shards x{world}, replicated map" + (", NCCL all-gather of bit-packed masks + global ordered compaction on every rank, pipelined: the exchange of step i runs on a side stream inside the timed window of step i+1 (+ one closing window)" if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": n,
                     "ms_per_step": e2e_ms / e2e_steps, "api": "artp_check_poses_f32 (states cast to float by the adapter, exact)",
                     "f64_api_value": world * n * e2e_steps / e2e64_s, "f64_api_h2d_bytes_per_step": n * 56},
@@ -435,7 +466,7 @@ def main():
             "cpu_baseline": {"value": n_mt / t_mt, "unit": "poses/s", "cores": cores, "kind": kind,
                              "sample": f"first {n_mt} poses of the workload, {cores} threads (best of a probe over 8..{os.cpu_count()}); single-thread on first {n1}",
                              "single_thread_value": n1 / t_single, "mask_equals_gpu": parity_ok},
-            "clocks": clocks, "wall_s_timed_region": wall, "secondary": secondary,
+            "clocks": clocks, "wall_s_timed_region": wall, "secondary": secondary, "exchange_ok": exchange_ok,
         }
         print(json.dumps(out))
     if world > 1:
