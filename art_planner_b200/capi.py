@@ -69,6 +69,7 @@ def load():
     u64 = C.c_uint64
     lib.artp_set_sampler.argtypes = [vp, C.POINTER(ArtpSamplerParams), vp, vp, vp, vp, vp, vp]
     lib.artp_estimate_normals.argtypes = [vp, C.c_double, vp, vp, vp, vp]
+    lib.artp_compute_sample_cdf.argtypes = [vp, vp, vp, vp]
     lib.artp_sampler_uniforms.argtypes = [vp, u64, u64, sz, vp]
     lib.artp_sample_states.argtypes = [vp, vp, u64, u64, sz, vp, vp]
     lib.artp_sample_states_device.argtypes = [vp, vp, u64, u64, sz, vp, vp, vp]

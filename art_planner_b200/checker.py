@@ -159,6 +159,16 @@ class StateValidityChecker:
                                                         *[None if a is None else a.ctypes.data for a in outs]))
         return tuple(outs) if want_host else None
 
+    def computeSampleCdf(self, sample_probability, want_host: bool = True):
+        """computeCumulativeProbabilityDistribution (probability_distribution.cpp:20-46) on the device; the CDF layers stay
+        resident for SE3FromSE2Sampler. Returns (cum_prob [rows, cols] F-order, cum_prob_rowwise [rows]) or None."""
+        p = np.asfortranarray(sample_probability, dtype=np.float32)
+        cum = np.empty(p.shape, np.float32, order="F") if want_host else None
+        row = np.empty(p.shape[0], np.float32) if want_host else None
+        self._h.check(self._h.lib.artp_compute_sample_cdf(self._h.h, p.ctypes.data, None if cum is None else cum.ctypes.data,
+                                                          None if row is None else row.ctypes.data))
+        return (cum, row) if want_host else None
+
     def packValidBits(self, valid, out=None):
         """CUDA uint8 mask [n] -> bit-packed int32 words [(n+31)//32] (item i = bit i&31 of word i>>5)."""
         import torch

@@ -58,6 +58,7 @@ struct Handle {
   size_t samp_layers_cap = 0;
   bool has_sampler = false;
   bool has_device_normals = false;  // artp_estimate_normals filled normal_x/y/z/std_dev of d_samp_layers for this map
+  bool has_device_cdf = false;      // artp_compute_sample_cdf filled cum_prob / cum_row of d_samp_layers for this map
   void* d_samp_scratch = nullptr;
   size_t samp_scratch_cap = 0;
   uint8_t* h_small_out = nullptr;   // mapped pinned host bytes the latency-path kernel writes its verdicts to
@@ -541,6 +542,7 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
   h->has_map = true;
   h->has_sampler = false;      // its layers belong to the previous map
   h->has_device_normals = false;
+  h->has_device_cdf = false;
   return ARTP_OK;
 }
 
@@ -940,6 +942,7 @@ static int ensure_sampler_layers(Handle* h) {
   cudaFree(h->d_samp_layers);
   h->d_samp_layers = nullptr; h->samp_layers_cap = 0;
   h->has_device_normals = false;
+  h->has_device_cdf = false;
   CU_TRY(h, cudaMalloc(&h->d_samp_layers, need));
   h->samp_layers_cap = need;
   return ARTP_OK;
@@ -974,6 +977,35 @@ int artp_estimate_normals(artp_handle* hh, double estimation_radius, float* norm
   return ARTP_OK;
 }
 
+int artp_compute_sample_cdf(artp_handle* hh, const float* sample_probability, float* cum_prob, float* cum_prob_rowwise) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
+  if (!sample_probability) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  int rc = ensure_sampler_layers(h);
+  if (rc) return rc;
+  const size_t ncell = (size_t)h->rows * h->cols;
+  rc = ensure_stage(h, ncell * sizeof(float));
+  if (rc) return rc;
+  float* d_cum = h->d_samp_layers + 4 * ncell;
+  float* d_row = h->d_samp_layers + 5 * ncell;
+  CU_TRY(h, cudaMemcpyAsync(h->d_stage, sample_probability, ncell * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  artp::cdf_rows_kernel<<<(h->rows + 63) / 64, 64, 0, h->stream>>>((const float*)h->d_stage, h->rows, h->cols, d_cum, d_row);
+  artp::cdf_rowwise_kernel<<<1, 32, 0, h->stream>>>(d_row, h->rows);
+  CU_TRY(h, cudaGetLastError());
+  if (cum_prob) CU_TRY(h, cudaMemcpyAsync(cum_prob, d_cum, ncell * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (cum_prob_rowwise)
+    CU_TRY(h, cudaMemcpyAsync(cum_prob_rowwise, d_row, (size_t)h->rows * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->has_device_cdf = true;
+  h->has_sampler = false;          // the sampler must be (re)armed with artp_set_sampler
+  h->stats.kernel_launches += 2;
+  h->stats.last_launches = 2;
+  return ARTP_OK;
+}
+
 int artp_set_sampler(artp_handle* hh, const artp_sampler_params* sp, const float* normal_x, const float* normal_y,
                      const float* normal_z, const float* plane_fit_std_dev, const float* cum_prob,
                      const float* cum_prob_rowwise) {
@@ -989,8 +1021,10 @@ int artp_set_sampler(artp_handle* hh, const artp_sampler_params* sp, const float
   if (!host_normals && !h->has_device_normals) {
     h->err = "no normal layers: pass them or call artp_estimate_normals after artp_set_map"; return ARTP_E_INVALID;
   }
-  if (sp->sample_from_distribution && (!cum_prob || !cum_prob_rowwise)) {
-    h->err = "sample_from_distribution needs the cum_prob layers"; return ARTP_E_INVALID;
+  const bool host_cdf = cum_prob && cum_prob_rowwise;
+  if (sp->sample_from_distribution && !host_cdf && !(h->has_device_cdf && !cum_prob && !cum_prob_rowwise)) {
+    h->err = "sample_from_distribution needs the cum_prob layers (pass both, or call artp_compute_sample_cdf first)";
+    return ARTP_E_INVALID;
   }
   if (!sp->sample_from_distribution && !(sp->high[0] > sp->low[0] && sp->high[1] > sp->low[1])) {
     h->err = "empty sampling bounds"; return ARTP_E_INVALID;
@@ -1019,9 +1053,12 @@ int artp_set_sampler(artp_handle* hh, const artp_sampler_params* sp, const float
   m.low[0] = sp->low[0]; m.low[1] = sp->low[1]; m.high[0] = sp->high[0]; m.high[1] = sp->high[1];
   m.reach_z = h->p.reach_z;
   if (m.from_distribution) {
-    CU_TRY(h, cudaMemcpyAsync(base + 4 * ncell, cum_prob, ncell * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(base + 5 * ncell, cum_prob_rowwise, (size_t)h->rows * sizeof(float), cudaMemcpyHostToDevice,
-                              h->stream));
+    if (host_cdf) {
+      CU_TRY(h, cudaMemcpyAsync(base + 4 * ncell, cum_prob, ncell * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+      CU_TRY(h, cudaMemcpyAsync(base + 5 * ncell, cum_prob_rowwise, (size_t)h->rows * sizeof(float), cudaMemcpyHostToDevice,
+                                h->stream));
+      h->has_device_cdf = false;   // overwritten by the caller's layers
+    }
     m.cum_prob = base + 4 * ncell; m.cum_row = base + 5 * ncell;
     // the binary searches need monotone (or all-NaN) CDF rows: refuse anything else
     CU_TRY(h, cudaMemsetAsync(h->d_ctr + 3, 0, sizeof(uint32_t), h->stream));

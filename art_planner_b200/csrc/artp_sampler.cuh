@@ -251,6 +251,35 @@ __global__ void estimate_normals_kernel(const float* __restrict__ H_rev, int pit
   }
 }
 
+// ---- computeCumulativeProbabilityDistribution (probability_distribution.cpp:20-46) ---------------------------
+// One thread per row walks its columns left to right (the order of the reference's rowwise sum and of its column-by-
+// column cumulation); neighbouring threads touch neighbouring rows of the column-major layer, so every step is one
+// coalesced access. row_sum[i] receives the row's probability mass.
+__global__ void cdf_rows_kernel(const float* __restrict__ prob, int rows, int cols, float* __restrict__ cum_prob,
+                                float* __restrict__ row_sum) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += gridDim.x * blockDim.x) {
+    float s = prob[i];
+    for (int j = 1; j < cols; ++j) s = s + prob[i + (size_t)j * rows];
+    row_sum[i] = s;
+    float run = prob[i] / s;
+    cum_prob[i] = run;
+    for (int j = 1; j < cols; ++j) {
+      run = prob[i + (size_t)j * rows] / s + run;
+      cum_prob[i + (size_t)j * rows] = run;
+    }
+  }
+}
+
+// Row distribution: sums / total, cumulated (sequential by definition; rows <= a few thousand). One thread.
+__global__ void cdf_rowwise_kernel(float* __restrict__ row, int rows) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  float total = row[0];
+  for (int i = 1; i < rows; ++i) total = total + row[i];
+  float run = row[0] / total;
+  row[0] = run;
+  for (int i = 1; i < rows; ++i) { run = row[i] / total + run; row[i] = run; }
+}
+
 // Every CDF row must be non-decreasing and finite, or entirely NaN (a row without probability mass:
 // probability_distribution.cpp:28 divides 0 by 0). bad[0] counts violations. One thread per row / for the row CDF.
 __global__ void validate_cdf_kernel(const float* __restrict__ c, int rows, int cols, size_t stride_in_row, size_t stride_row,

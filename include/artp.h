@@ -146,6 +146,11 @@ typedef struct artp_sampler_params {
  * reference's float arithmetic (the elevation layer's -0 is stored as +0, see artp_set_map). */
 int artp_estimate_normals(artp_handle* h, double estimation_radius, float* normal_x, float* normal_y, float* normal_z,
                           float* plane_fit_std_dev);
+/* computeCumulativeProbabilityDistribution (src/map/processors/probability_distribution.cpp:20-46) on the device:
+ * "sample_probability" (HOST, grid_map layout) -> "cum_prob" and column 0 of "cum_prob_rowwise_hack", kept on the device
+ * as the sampler's CDF layers (artp_set_sampler may then get NULL for both) and copied to the non-NULL HOST outputs.
+ * Sums run left to right per row; rows without mass become NaN rows exactly like the reference's 0/0. */
+int artp_compute_sample_cdf(artp_handle* h, const float* sample_probability, float* cum_prob, float* cum_prob_rowwise);
 int artp_set_sampler(artp_handle* h, const artp_sampler_params* sp, const float* normal_x, const float* normal_y,
                      const float* normal_z, const float* plane_fit_std_dev, const float* cum_prob,
                      const float* cum_prob_rowwise);

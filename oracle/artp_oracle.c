@@ -742,6 +742,35 @@ int orc_estimate_normals(const float* elevation, int rows, int cols, double res,
   return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * computeCumulativeProbabilityDistribution, probability_distribution.cpp:20-46
+ * ---------------------------------------------------------------------------------------------- */
+int orc_compute_cdf(const float* prob, int rows, int cols, float* cum_prob, float* cum_row) {
+  float total = 0.0f;
+  for (int i = 0; i < rows; ++i) {                       /* :23 prob.rowwise().sum() */
+    float s = prob[i];
+    for (int j = 1; j < cols; ++j) s = s + prob[i + (size_t)j * rows];
+    cum_row[i] = s;
+  }
+  total = cum_row[0];
+  for (int i = 1; i < rows; ++i) total = total + cum_row[i];   /* :26 prob_rowwise.sum() */
+  for (int i = 0; i < rows; ++i) {
+    const float rs = cum_row[i];
+    /* :28 cum_prob.array().colwise() /= rowwise sums ; :37-39 cumulate along the columns */
+    float run = prob[i] / rs;
+    cum_prob[i] = run;
+    for (int j = 1; j < cols; ++j) {
+      run = prob[i + (size_t)j * rows] / rs + run;
+      cum_prob[i + (size_t)j * rows] = run;
+    }
+  }
+  /* :26 normalise, :32-35 cumulate the row distribution */
+  float run = cum_row[0] / total;
+  cum_row[0] = run;
+  for (int i = 1; i < rows; ++i) { run = cum_row[i] / total + run; cum_row[i] = run; }
+  return 0;
+}
+
 int orc_path_length_cost(orc_handle* h, const double* s1, const double* s2, size_t n, double* cost) {
   if (!h) return 1;
   for (size_t i = 0; i < n; ++i) cost[i] = orc_path_length(&h->p, s1 + 7 * i, s2 + 7 * i);

@@ -109,6 +109,14 @@ int orc_estimate_normals(const float* elevation, int rows, int cols, double res,
                          double estimation_radius, float* normal_x, float* normal_y, float* normal_z,
                          float* plane_fit_std_dev);
 
+/* computeCumulativeProbabilityDistribution (art_planner/src/map/processors/probability_distribution.cpp:20-46),
+ * liborc_port.so only: "sample_probability" (rows x cols, column-major) -> "cum_prob" (each row divided by its sum, then
+ * cumulated along the columns) and column 0 of "cum_prob_rowwise_hack" (row sums divided by their total, cumulated).
+ * Sums are taken left to right (Eigen's rowwise partial reduction on a column-major matrix does the same per row; the
+ * grand total uses Eigen's packet reduction in the reference, whose order depends on its build flags -- restated here
+ * as the plain sequential sum: parity unpinned at this level). Rows without mass become NaN rows (0/0), as there. */
+int orc_compute_cdf(const float* sample_probability, int rows, int cols, float* cum_prob, float* cum_prob_rowwise);
+
 /* PathLengthObjective::motionCost (path_length_objective.cpp:26-70). */
 int orc_path_length_cost(orc_handle* h, const double* s1, const double* s2, size_t n, double* cost);
 

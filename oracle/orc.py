@@ -75,6 +75,20 @@ def estimate_normals(m, estimation_radius: float):
     return tuple(outs)
 
 
+def compute_cdf(prob):
+    """computeCumulativeProbabilityDistribution restated (artp_oracle.c): (cum_prob [rows, cols] F-order, cum_row [rows])."""
+    if not os.path.exists(PORT_SO):
+        build("port")
+    lib = C.CDLL(PORT_SO)
+    lib.orc_compute_cdf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    p = np.asfortranarray(prob, dtype=np.float32)
+    cum = np.zeros(p.shape, np.float32, order="F")
+    row = np.zeros(p.shape[0], np.float32)
+    with np.errstate(all="ignore"):
+        assert lib.orc_compute_cdf(p.ctypes.data, p.shape[0], p.shape[1], cum.ctypes.data, row.ctypes.data) == 0
+    return cum, row
+
+
 def build(kind: str = "port", quiet: bool = True) -> None:
     """Compile the oracle library with oracle/Makefile (building the checker is not using it)."""
     target = "port" if kind == "port" else "ref"

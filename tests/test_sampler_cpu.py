@@ -124,3 +124,19 @@ def test_oracle_estimate_normals(maps, port_lib):
     fx, fy, fz, fs = port_lib.estimate_normals(f, 0.49)
     ok = fz != 0
     assert (fz[ok] == 1.0).all() and (fx[ok] == 0).all() and (fy[ok] == 0).all() and (fs == 0).all()
+
+
+def test_oracle_cdf_layers(setup, port_lib):
+    """probability_distribution.cpp:20-46 restated: row-normalised column cumulation, row distribution, NaN rows."""
+    m, L = setup
+    cum, row = port_lib.compute_cdf(L.sample_probability)
+    p = L.sample_probability.astype(np.float64)
+    mass = p.sum(axis=1)
+    dead = mass == 0
+    assert dead.any() and np.isnan(cum[dead]).all() and not np.isnan(cum[~dead]).any()
+    want = np.cumsum(p[~dead] / mass[~dead, None], axis=1)
+    assert np.abs(cum[~dead] - want).max() < 5e-6
+    assert np.abs(row - np.cumsum(mass / mass.sum())).max() < 5e-6
+    assert (np.diff(cum[~dead], axis=1) >= 0).all() and (np.diff(row) >= 0).all()
+    # numpy stand-in used by synth.make_sampler_layers agrees to summation-order noise
+    assert np.nanmax(np.abs(cum - L.cum_prob)) < 5e-6

@@ -157,3 +157,34 @@ def test_sampler_on_device_normals(rig, port_lib):
     ok = ~np.isnan(ref).any(axis=1)
     assert np.array_equal(np.isnan(got).any(axis=1), ~ok)
     assert np.abs(got[ok] - ref[ok]).max() < STATE_TOL
+
+
+def test_sample_cdf_on_device_and_full_device_chain(rig, port_lib):
+    """artp_compute_sample_cdf == the CPU restatement of probability_distribution.cpp:20-46 bit for bit, and the chain
+    set_map -> estimate_normals -> compute_sample_cdf -> sampler (no host layers at all) samples like the oracle."""
+    ap, m, chk0, L = rig
+    chk = ap.StateValidityChecker(cases.PARAMS["yaml"], device=0)
+    chk.setMap(m)
+    chk.updateHeightField()
+    cum, row = chk.computeSampleCdf(L.sample_probability)
+    rcum, rrow = port_lib.compute_cdf(L.sample_probability)
+    nan = np.isnan(rcum)
+    assert nan.any() and np.array_equal(np.isnan(cum), nan)
+    assert np.array_equal(cum[~nan].view(np.uint32), rcum[~nan].view(np.uint32))
+    assert np.array_equal(row.view(np.uint32), rrow.view(np.uint32))
+    chk.estimateNormals(0.49, want_host=False)
+    sp = synth.sampler_params_for(m)
+
+    class Nothing:
+        pass
+    smp = ap.SE3FromSE2Sampler(chk, Nothing, sp, seed=8)
+    import copy
+    L2 = copy.copy(L)
+    L2.normal_x, L2.normal_y, L2.normal_z, L2.plane_fit_std_dev = port_lib.estimate_normals(m, 0.49)
+    L2.cum_prob, L2.cum_prob_rowwise = rcum, rrow
+    u = philox_ref.sampler_uniforms(8, 0, 20000)
+    ref, ref_rc = port_lib.sample_states(m, L2, sp, cases.PARAMS["yaml"].reach_z, u)
+    got, rc = smp.sampleUniformBatch(20000, first=0, want_cells=True)
+    assert np.array_equal(rc, ref_rc)
+    ok = ~np.isnan(ref).any(axis=1)
+    assert np.abs(got[ok] - ref[ok]).max() < STATE_TOL
