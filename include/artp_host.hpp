@@ -155,6 +155,18 @@ class StateValidityChecker {
     handle_->check(artp_check_poses_f32(handle_->get(), buf.data(), states.size(), valid->data()), "artp_check_poses_f32");
   }
 
+  // computeCumulativeProbabilityDistribution (probability_distribution.cpp:20-46) on the device: fills the map's cum_prob /
+  // cum_prob_rowwise layers from `sample_probability` (rows x cols, column-major) and keeps them resident for the sampler.
+  void computeSampleCdf(const std::vector<float>& sample_probability) {
+    if (!map_) throw std::runtime_error("computeSampleCdf: no map");
+    const size_t ncell = static_cast<size_t>(map_->rows) * map_->cols;
+    if (sample_probability.size() != ncell) throw std::invalid_argument("computeSampleCdf: layer size mismatch");
+    map_->cum_prob.resize(ncell);
+    map_->cum_prob_rowwise.resize(map_->rows);
+    handle_->check(artp_compute_sample_cdf(handle_->get(), sample_probability.data(), map_->cum_prob.data(),
+                                           map_->cum_prob_rowwise.data()), "artp_compute_sample_cdf");
+  }
+
   // The rejection-sampling loop `do { sampleUniform(s) } while (!isValid(s))` (prm_motion_cost.cpp:171-194,
   // lazy_prm_star_min_update.cpp:549-556) in batches: draw `batch` candidates with the caller's sampler, check them in
   // one call, keep the valid ones in draw order; repeat until n_wanted states are collected or max_draws candidates
