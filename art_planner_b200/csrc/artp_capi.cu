@@ -309,7 +309,7 @@ int run_items(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed = nu
     w.item_base = (uint32_t)base;
     w.n_items = (uint32_t)end;
     const unsigned grid_c = (unsigned)std::min<size_t>((size_t)h->k2_grid, 5 * (end - base));
-    artp::box_items_block_kernel<<<grid_c, 256, h->k2_smem, s>>>(h->chk, w, h->d_recs, h->d_ctr + 1, h->d_defer,
+    artp::box_items_block_kernel<<<grid_c, artp::kBlockStageThreads, h->k2_smem, s>>>(h->chk, w, h->d_recs, h->d_ctr + 1, h->d_defer,
                                                                       h->k2_tcap, h->d_ctr + 2);
     CU_TRY(h, cudaGetLastError());
     if (h->timing && last_round) { CU_TRY(h, cudaEventRecord(h->ev[3], s)); h->ev_valid = true; }
@@ -493,7 +493,7 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
   }
   CU_TRY(h, cudaFuncSetAttribute(artp::box_items_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int per_sm = 0;
-  CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, artp::box_items_block_kernel, 256, smem));
+  CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, artp::box_items_block_kernel, artp::kBlockStageThreads, smem));
   h->k2_smem = smem; h->k2_tcap = tcap; h->k2_grid = h->sm_count * std::max(per_sm, 1);
   // upload
   CU_TRY(h, cudaStreamSynchronize(h->stream));

@@ -838,12 +838,13 @@ groups_done:
   return __syncthreads_or(hit) ? R_HIT : R_FREE;
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kBlockStageThreads = 256;   // threads per deferred box in the grouping stage
+__global__ void __launch_bounds__(kBlockStageThreads)
 box_items_block_kernel(const Checker c, const Work w, const BoxRec* __restrict__ recs,
                        const uint32_t* __restrict__ defer_count, const uint32_t* __restrict__ defer_list, int T_cap,
                        uint32_t* __restrict__ overflow) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float red[8];
+  __shared__ float red[kBlockStageThreads / 32];
   __shared__ int s_next;
   BlockShared sh;
   sh.T_cap = T_cap;

@@ -323,6 +323,22 @@ def main():
         secondary["edge_validity"] = {"workload": "configs[2]: 100k edges x 20 interpolation steps (+ end state), same map",
                                       "edges_per_s": 100_000 / (ms * 1e-3), "state_checks_per_s_upper": 2_100_000 / (ms * 1e-3),
                                       "ms_per_batch": ms, "valid_fraction": float(ev_out.float().mean())}
+        try:   # addValidMilestone connection batches (prm_motion_cost.cpp:341-372): per-edge interior-state counts
+            e1, e2 = synth.make_edges(m, 200_000, seed=9, dmin=0.05, dmax=3.4)
+            g1, g2 = torch.from_numpy(e1).cuda(), torch.from_numpy(e2).cuda()
+            mvi = apb.MotionValidator(chk)
+            pref, ni = mvi.checkEdgeInteriors(g1, g2)
+            torch.cuda.synchronize(); a.record()
+            for _ in range(10):
+                pref, ni = mvi.checkEdgeInteriors(g1, g2, n_interp=ni)
+            bb.record(); torch.cuda.synchronize()
+            ms_i = a.elapsed_time(bb) / 10
+            secondary["edge_interiors"] = {"workload": "200k candidate connections, n_interp = lateralDistance/0.5 interior states each",
+                                           "edges_per_s": 200_000 / (ms_i * 1e-3), "interior_states": int(ni.sum()),
+                                           "state_checks_per_s_upper": float(ni.sum()) / (ms_i * 1e-3), "ms_per_batch": ms_i,
+                                           "fully_valid_fraction": float((pref == ni).float().mean())}
+        except Exception as ex:
+            secondary["edge_interiors"] = {"error": repr(ex)}
         plo = apb.PathLengthObjective(chk)
         c_out = torch.empty(100_000, dtype=torch.float64, device="cuda")
         plo.motionCostBatch(d1, d2, out=c_out); torch.cuda.synchronize(); a.record()

@@ -1,1 +1,4 @@
-for F in 0 4 8; do echo "ARTP_K0_FLAGS=$F"; ARTP_K0_FLAGS=$F bash profiles/gpu_quick.sh; done
+timeout 800 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+bash profiles/gpu_quick.sh
+python -c "
+import json; d=json.load(open('gpurun_out/bench_latest.json')); print(d['secondary']['edge_interiors'])"
