@@ -1,4 +1,2 @@
 timeout 800 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 bash profiles/gpu_quick.sh
-python -c "
-import json; d=json.load(open('gpurun_out/bench_latest.json')); print(d['secondary']['edge_interiors'])"
