@@ -26,6 +26,11 @@
  *                                   ompl::base::StateSampler::sampleUniform -> SE3FromSE2Sampler::sampleUniform
  *                                   (src/sampler.cpp:82-131, positions :40-77) and the rejection loops around it
  *                                   (prm_motion_cost.cpp:171-194, lazy_prm_star_min_update.cpp:549-556)
+ *   artp_estimate_normals           art_planner::estimateNormals (src/utils.cpp:213-324; processors::Basic, basic.cpp:47)
+ *   artp_compute_sample_cdf         computeCumulativeProbabilityDistribution
+ *                                   (src/map/processors/probability_distribution.cpp:20-46)
+ *   artp_compact_valid_device, artp_pack_valid_bits_device, artp_compact_bits_device
+ *                                   no reference counterpart: the multi-GPU verdict exchange
  *   artp_path_length_cost[_device]  ompl::base::OptimizationObjective::motionCost ->
  *                                   PathLengthObjective::motionCost (objectives/path_length_objective.cpp:26-70)
  *   artp_set_cost_weights, artp_update_features, artp_motion_cost[_device]
