@@ -887,7 +887,8 @@ pose_small_kernel(const Checker c, const SmallBatch sb, uint8_t* __restrict__ ou
   __shared__ int s_next;
   __shared__ BoxCtx s_box[5];
   __shared__ uint32_t s_fl[5];
-  __shared__ int s_res[5];          // per box: -1 undecided, R_FREE / R_HIT decided, R_DEFER, kBoxOutside
+  __shared__ int s_res[5];          // per box after classify: -1 undecided, R_FREE / R_HIT decided, kBoxOutside
+  __shared__ int s_res2[5];         // warp-stage result of an undecided box (separate: other warps may still read s_res)
   __shared__ WarpScratch s_ws[5];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid < 5) {
@@ -935,7 +936,7 @@ pose_small_kernel(const Checker c, const SmallBatch sb, uint8_t* __restrict__ ou
     const bool foot = wid > 0;
     const int res = box_collide_warp(foot ? c.f[1] : c.f[0], s_box[wid], s_ws[wid], lane, c.cell_margin,
                                      (s_fl[wid] & REC_NEEDS_REDUCE) != 0, (s_fl[wid] & REC_ALLFINITE) != 0);
-    if (lane == 0) s_res[wid] = res;
+    if (lane == 0) s_res2[wid] = res;
   }
   __syncthreads();
   if (valid) {
@@ -947,6 +948,7 @@ pose_small_kernel(const Checker c, const SmallBatch sb, uint8_t* __restrict__ ou
 #pragma unroll 1
     for (int k = 0; k < 5; ++k) {
       int r = s_res[k];                       // block-uniform
+      if (r == -1 && !force_all) r = s_res2[k];
       if (r == -1 || r == R_DEFER) {          // -1 only in force_all mode
         const bool foot = k > 0;
         r = box_collide_block(foot ? c.f[1] : c.f[0], s_box[k], sh, red, &s_next);
