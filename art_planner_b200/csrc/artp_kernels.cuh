@@ -429,7 +429,7 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
 }
 
 // One queued box (80 bytes): everything stage B/C need, so nothing is recomputed.
-struct BoxRec {
+struct alignas(16) BoxRec {
   float R1[9];
   float P[3];
   float minB, maxB;
@@ -437,6 +437,7 @@ struct BoxRec {
   uint32_t item;     // work item id
   uint32_t flags;    // bits 0-2: box (0 torso, 1..4 feet); bit 3: zone all finite; bit 4: zone not reduced yet
 };
+static_assert(sizeof(BoxRec) == 80, "BoxRec is read as five 16-byte words");
 enum { REC_ALLFINITE = 8, REC_NEEDS_REDUCE = 16 };
 
 __device__ __forceinline__ void rec_to_ctx(const Checker& c, const BoxRec& r, BoxCtx& b) {
@@ -643,14 +644,14 @@ box_items_warp_kernel(const Checker c, const Work w, const BoxRec* __restrict__ 
     if (r0 >= total) break;
     const uint32_t r1 = min(r0 + kChunk, total);
     for (uint32_t ri = r0; ri < r1; ++ri) {
-    // load the 20-word record with lanes 0..19 and broadcast
-    const uint32_t* rp = reinterpret_cast<const uint32_t*>(recs + ri);
-    const uint32_t word = (lane < 20) ? __ldg(rp + lane) : 0u;
+    // every lane reads the whole 80-byte record itself: five 16-byte loads from one address per warp (a broadcast
+    // transaction each) instead of one load + 20 shuffles
     BoxRec r;
     {
-      uint32_t* dst = reinterpret_cast<uint32_t*>(&r);
+      const uint4* rp = reinterpret_cast<const uint4*>(recs + ri);
+      uint4* dst = reinterpret_cast<uint4*>(&r);
 #pragma unroll
-      for (int i = 0; i < 20; ++i) dst[i] = __shfl_sync(kFull, word, i);
+      for (int i = 0; i < 5; ++i) dst[i] = __ldg(rp + i);
     }
     const uint32_t slot = item_slot(w, r.item);
     if (w.edge_mode) {   // the edge already failed on another state/box: nothing can change it (perf only; order-free)

@@ -1,2 +1,2 @@
-timeout 800 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 300 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
 bash profiles/gpu_quick.sh
