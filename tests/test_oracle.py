@@ -108,3 +108,44 @@ def test_port_equals_compiled_reference_on_fresh_seeds(maps, port_lib):
         for which in (0, 1):
             org, rot = cases.box_samples(m, 5000, 4321, which, 0.8, 0.4)
             assert np.array_equal(P.box_collide(which, org, rot), R.box_collide(which, org, rot))
+
+
+def _terraces():
+    """Piecewise-constant steps: large coplanar triangle sets, the worst case for the greedy eps-grouping."""
+    import dataclasses
+    m = synth.make_flat_map()
+    e = np.array(m.elevation, dtype=np.float32, order="F")
+    r, c = np.indices(e.shape)
+    e[:] = (0.07 * ((r // 9) % 4) + 0.05 * ((c // 13) % 3)).astype(np.float32)
+    return dataclasses.replace(m, elevation=e, elevation_masked=np.asfortranarray(e.copy()), desc="terraces")
+
+
+def _spikes():
+    """Gentle fBm with 1 % isolated 0.4 m spikes: single-vertex contacts and very steep triangles."""
+    import dataclasses
+    m = synth.make_fbm_map(200, 200, amp=0.2)
+    e = np.array(m.elevation, dtype=np.float32, order="F")
+    k = np.arange(e.size).reshape(e.shape)
+    e[synth.hash_uniform(77, 1, k) < 0.01] += 0.4
+    mk = np.array(m.elevation_masked, dtype=np.float32, order="F")
+    fin = np.isfinite(mk)
+    mk[fin] = e[fin]
+    return dataclasses.replace(m, elevation=e, elevation_masked=mk, desc="spikes")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/ode"), reason="reference tree not present on this box")
+@pytest.mark.parametrize("mk", [_terraces, _spikes], ids=["terraces", "spikes"])
+def test_port_equals_compiled_reference_on_adversarial_maps(mk, port_lib):
+    port_lib.build("ref")
+    m = mk()
+    P = port_lib.Oracle(cases.PARAMS["yaml"], "port")
+    R = port_lib.Oracle(cases.PARAMS["yaml"], "reference")
+    P.set_map(m)
+    R.set_map(m)
+    poses = synth.make_terrain_poses(m, 20000, seed=31)
+    a = P.check_poses(poses)
+    assert 0 < a.sum() < len(a)
+    assert np.array_equal(a, R.check_poses(poses))
+    for which in (0, 1):
+        org, rot = cases.box_samples(m, 20000, 99, which, 0.9, 0.35)
+        assert np.array_equal(P.box_collide(which, org, rot), R.box_collide(which, org, rot))
