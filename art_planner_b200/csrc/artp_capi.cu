@@ -66,9 +66,21 @@ struct Handle {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
   bool deferred_unread = false;
+  // Cross-stream ordering of the per-handle scratch: calls may come on different streams; every call that
+  // uses a scratch group first makes its stream wait for the previous user of that group, and records an event after.
+  // group 0: d_ctr / d_recs / d_defer / d_stage / d_samp_scratch (check, sampler);  group 1: d_block_counts (compaction)
+  cudaEvent_t chain_ev[2] = {nullptr, nullptr};
+  cudaStream_t chain_stream[2] = {nullptr, nullptr};
+  bool chain_busy[2] = {false, false};
+  // Sticky error word in mapped pinned host memory: the plane-grouping stage sets it when a zone does not fit its
+  // shared-memory store (the item is then marked INVALID -- fail closed). Host-buffer calls return ARTP_E_LIMIT from the
+  // call that caused it; device-buffer (asynchronous) calls surface it through artp_poll_error().
+  uint32_t* h_err = nullptr;        // host view
+  uint32_t* d_err = nullptr;        // device view of the same word
+  int tcap_override = 0;            // test hook (artp_debug_set_group_capacity)
   artp_stats stats{};
   std::string err;
-  std::mutex mtx;
+  std::recursive_mutex mtx;   // recursive: host-buffer entry points hold it across their nested *_device call
 };
 
 #define CU_TRY(h, expr)                                                                          \
@@ -251,6 +263,33 @@ int ensure_stage(Handle* h, size_t bytes) {
   return ARTP_OK;
 }
 
+// Scratch-group ordering across streams (see Handle::chain_ev).
+int chain_begin(Handle* h, int g, cudaStream_t s) {
+  if (h->chain_busy[g] && h->chain_stream[g] != s) CU_TRY(h, cudaStreamWaitEvent(s, h->chain_ev[g], 0));
+  return ARTP_OK;
+}
+int chain_end(Handle* h, int g, cudaStream_t s) {
+  CU_TRY(h, cudaEventRecord(h->chain_ev[g], s));
+  h->chain_stream[g] = s;
+  h->chain_busy[g] = true;
+  return ARTP_OK;
+}
+struct ChainScope {   // begin on construction, end on destruction (every return path)
+  Handle* h; int g; cudaStream_t s; int rc;
+  ChainScope(Handle* h_, int g_, cudaStream_t s_) : h(h_), g(g_), s(s_), rc(chain_begin(h_, g_, s_)) {}
+  ~ChainScope() { if (rc == ARTP_OK) chain_end(h, g, s); }
+};
+
+// Sticky plane-grouping overflow (set by the device, see Handle::h_err): read and clear.
+int take_sticky_error(Handle* h) {
+  if (h->h_err && *(volatile uint32_t*)h->h_err) {
+    *(volatile uint32_t*)h->h_err = 0;
+    h->err = "plane-grouping stage overflow: a zone exceeded its shared-memory store; affected poses were marked invalid";
+    return ARTP_E_LIMIT;
+  }
+  return ARTP_OK;
+}
+
 // Optional host feed of a call: the states are copied H2D in slices on the copy stream while the kernels of the
 // previous slice run on the compute stream.
 struct HostFeed {
@@ -310,7 +349,7 @@ int run_items(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed = nu
     w.n_items = (uint32_t)end;
     const unsigned grid_c = (unsigned)std::min<size_t>((size_t)h->k2_grid, 5 * (end - base));
     artp::box_items_block_kernel<<<grid_c, artp::kBlockStageThreads, h->k2_smem, s>>>(h->chk, w, h->d_recs, h->d_ctr + 1, h->d_defer,
-                                                                      h->k2_tcap, h->d_ctr + 2);
+                                                                      h->k2_tcap, h->d_err);
     CU_TRY(h, cudaGetLastError());
     if (h->timing && last_round) { CU_TRY(h, cudaEventRecord(h->ev[3], s)); h->ev_valid = true; }
     launches += 1;
@@ -373,6 +412,11 @@ int artp_create(const artp_params* params, artp_handle** out) {
   for (int i = 0; i < kCopyEvents; ++i)
     if ((e = cudaEventCreateWithFlags(&h->copy_ev[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaMalloc(&h->d_ctr, 8 * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc", e);
+  for (int g = 0; g < 2; ++g)
+    if ((e = cudaEventCreateWithFlags(&h->chain_ev[g], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaHostAlloc((void**)&h->h_err, 64, cudaHostAllocMapped)) != cudaSuccess) return fail("cudaHostAlloc", e);
+  *h->h_err = 0;
+  if ((e = cudaHostGetDevicePointer((void**)&h->d_err, h->h_err, 0)) != cudaSuccess) return fail("cudaHostGetDevicePointer", e);
   int per_sm = 0;
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, artp::box_items_warp_kernel,
                                                          artp::kWarpsPerCta * 32, 0)) != cudaSuccess)
@@ -404,6 +448,8 @@ void artp_destroy(artp_handle* hh) {
   cudaFree(h->d_H[0]); cudaFree(h->d_H[1]); cudaFree(h->d_ctr); cudaFree(h->d_defer); cudaFree(h->d_stage);
   cudaFree(h->d_block_counts); cudaFree(h->d_recs); cudaFree(h->d_samp_layers); cudaFree(h->d_samp_scratch);
   if (h->h_small_out) cudaFreeHost(h->h_small_out);
+  if (h->h_err) cudaFreeHost(h->h_err);
+  for (int g = 0; g < 2; ++g) if (h->chain_ev[g]) cudaEventDestroy(h->chain_ev[g]);
   artp_cnn::destroy(h->cnn);
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
@@ -420,7 +466,7 @@ int artp_set_mode(artp_handle* hh, int mode) {
 int artp_set_timing(artp_handle* hh, int enable) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   CU_TRY(h, cudaSetDevice(h->device));
   if (enable && !h->ev[0]) for (int i = 0; i < 4; ++i) CU_TRY(h, cudaEventCreate(&h->ev[i]));
   h->timing = enable ? 1 : 0;
@@ -431,7 +477,7 @@ int artp_set_timing(artp_handle* hh, int enable) {
 int artp_get_last_timing(artp_handle* hh, float* ms3) {
   if (!hh || !ms3) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (!h->timing || !h->ev_valid) { h->err = "timing not enabled or no call recorded"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
   CU_TRY(h, cudaEventSynchronize(h->ev[3]));
@@ -442,7 +488,7 @@ int artp_get_last_timing(artp_handle* hh, float* ms3) {
 int artp_get_stats(artp_handle* hh, artp_stats* out) {
   if (!hh || !out) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   CU_TRY(h, cudaSetDevice(h->device));
   uint32_t ctr[4] = {0, 0, 0, 0};
   CU_TRY(h, cudaMemcpy(ctr, h->d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost));   // synchronises the device
@@ -450,15 +496,14 @@ int artp_get_stats(artp_handle* hh, artp_stats* out) {
   h->stats.last_queued_boxes = ctr[3];
   if (h->deferred_unread) { h->stats.poses_deferred += ctr[1]; h->deferred_unread = false; }
   *out = h->stats;
-  if (ctr[2] != 0) { h->err = "plane-grouping kernel overflow (zone larger than its shared-memory store)"; return ARTP_E_LIMIT; }
-  return ARTP_OK;
+  return take_sticky_error(h);
 }
 
 int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation_masked, int rows, int cols, double res,
                  double cx, double cy) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (!elevation || !elevation_masked || rows < 2 || cols < 2 || !(res > 0)) { h->err = "bad map arguments"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
   const size_t ncell = (size_t)rows * cols;
@@ -485,6 +530,7 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
     while ((2 << kk) <= std::min(nxm, nzm) && kk < artp::kMaxLevel) ++kk;   // floor(log2(min dim bound))
     kmax[k] = kk;
   }
+  if (h->tcap_override > 0) tcap = std::min(tcap, h->tcap_override);   // test hook: force the overflow path
   tcap = (tcap + 3) & ~3;
   const int smem = tcap * 21 + 64;
   if (smem > 200 * 1024) {
@@ -495,8 +541,9 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
   int per_sm = 0;
   CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, artp::box_items_block_kernel, artp::kBlockStageThreads, smem));
   h->k2_smem = smem; h->k2_tcap = tcap; h->k2_grid = h->sm_count * std::max(per_sm, 1);
-  // upload
-  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  // upload (the previous map may still be in use by asynchronous calls on the caller's streams)
+  CU_TRY(h, cudaDeviceSynchronize());
+  h->chain_busy[0] = h->chain_busy[1] = false;
   const int pitch = (rows + 3) & ~3;
   const size_t npad = (size_t)pitch * cols;
   if (h->rows != rows || h->cols != cols) {
@@ -549,7 +596,7 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
 int artp_check_poses_device(artp_handle* hh, const double* d_states, size_t n, uint8_t* d_valid, void* stream) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   int rc = check_common(h, n);
   if (rc) return rc;
   if (n == 0) return ARTP_OK;
@@ -557,6 +604,8 @@ int artp_check_poses_device(artp_handle* hh, const double* d_states, size_t n, u
   CU_TRY(h, cudaSetDevice(h->device));
   artp::Work w;
   w.s1 = nullptr; w.s2 = d_states; w.s2f = nullptr; w.valid = d_valid; w.item_base = 0; w.n_items = (uint32_t)n; w.steps = 0; w.edge_mode = 0;
+  ChainScope cs(h, 0, (cudaStream_t)stream);
+  if (cs.rc) return cs.rc;
   rc = run_items(h, w, (cudaStream_t)stream);
   if (rc) return rc;
   h->stats.poses_checked += n;
@@ -571,7 +620,8 @@ static int check_poses_small(Handle* h, const artp::SmallBatch& sb, size_t n, ui
   }
   uint8_t* d_out = nullptr;
   CU_TRY(h, cudaHostGetDevicePointer((void**)&d_out, h->h_small_out, 0));
-  artp::pose_small_kernel<<<(unsigned)n, 256, h->k2_smem, h->stream>>>(h->chk, sb, d_out, h->k2_tcap, h->d_ctr + 2,
+  { int rc0 = chain_begin(h, 0, h->stream); if (rc0) return rc0; }
+  artp::pose_small_kernel<<<(unsigned)n, 256, h->k2_smem, h->stream>>>(h->chk, sb, d_out, h->k2_tcap, h->d_err,
                                                                         h->mode == 1, steps);
   CU_TRY(h, cudaGetLastError());
   CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -589,13 +639,14 @@ static int check_poses_small(Handle* h, const artp::SmallBatch& sb, size_t n, ui
   h->stats.last_launches = 1;
   h->stats.poses_checked += n;
   h->ev_valid = false;
-  return ARTP_OK;
+  if (h->chain_stream[0] == h->stream || !h->chain_busy[0]) h->chain_busy[0] = false;   // everything of this group has completed
+  return take_sticky_error(h);
 }
 
 int artp_check_poses(artp_handle* hh, const double* states, size_t n, uint8_t* valid) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   int rc = check_common(h, n);
   if (rc) return rc;
   if (n == 0) return ARTP_OK;
@@ -616,12 +667,15 @@ int artp_check_poses(artp_handle* hh, const double* states, size_t n, uint8_t* v
   w.s1 = nullptr; w.s2 = d_states; w.s2f = nullptr; w.valid = d_valid; w.item_base = 0; w.n_items = (uint32_t)n;
   w.steps = 0; w.edge_mode = 0;
   HostFeed feed{(const char*)states, (char*)d_states, 7 * sizeof(double), 128 * 1024};
+  rc = chain_begin(h, 0, h->stream);
+  if (rc) return rc;
   rc = run_items(h, w, h->stream, &feed);
   if (rc) return rc;
   CU_TRY(h, cudaMemcpyAsync(valid, d_valid, n, cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->chain_busy[0] = false;
   h->stats.poses_checked += n;
-  return ARTP_OK;
+  return take_sticky_error(h);
 }
 
 // float32 states: the caller has already applied the double -> float cast that Pose3FromSE3 (utils.h:25-38) performs
@@ -629,7 +683,7 @@ int artp_check_poses(artp_handle* hh, const double* states, size_t n, uint8_t* v
 int artp_check_poses_f32_device(artp_handle* hh, const float* d_states, size_t n, uint8_t* d_valid, void* stream) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   int rc = check_common(h, n);
   if (rc) return rc;
   if (n == 0) return ARTP_OK;
@@ -638,6 +692,8 @@ int artp_check_poses_f32_device(artp_handle* hh, const float* d_states, size_t n
   artp::Work w;
   w.s1 = nullptr; w.s2 = nullptr; w.s2f = d_states; w.valid = d_valid; w.item_base = 0; w.n_items = (uint32_t)n; w.steps = 0;
   w.edge_mode = 0;
+  ChainScope cs(h, 0, (cudaStream_t)stream);
+  if (cs.rc) return cs.rc;
   rc = run_items(h, w, (cudaStream_t)stream);
   if (rc) return rc;
   h->stats.poses_checked += n;
@@ -647,7 +703,7 @@ int artp_check_poses_f32_device(artp_handle* hh, const float* d_states, size_t n
 int artp_check_poses_f32(artp_handle* hh, const float* states, size_t n, uint8_t* valid) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   int rc = check_common(h, n);
   if (rc) return rc;
   if (n == 0) return ARTP_OK;
@@ -667,19 +723,22 @@ int artp_check_poses_f32(artp_handle* hh, const float* states, size_t n, uint8_t
   w.s1 = nullptr; w.s2 = nullptr; w.s2f = d_states; w.valid = d_valid; w.item_base = 0; w.n_items = (uint32_t)n;
   w.steps = 0; w.edge_mode = 0;
   HostFeed feed{(const char*)states, (char*)d_states, 7 * sizeof(float), 256 * 1024};
+  rc = chain_begin(h, 0, h->stream);
+  if (rc) return rc;
   rc = run_items(h, w, h->stream, &feed);
   if (rc) return rc;
   CU_TRY(h, cudaMemcpyAsync(valid, d_valid, n, cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->chain_busy[0] = false;
   h->stats.poses_checked += n;
-  return ARTP_OK;
+  return take_sticky_error(h);
 }
 
 int artp_check_motions_device(artp_handle* hh, const double* d_s1, const double* d_s2, size_t n, int n_steps,
                               uint8_t* d_valid, void* stream) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (n_steps < 0) { h->err = "n_steps < 0"; return ARTP_E_INVALID; }
   const size_t items = n * ((size_t)n_steps + 1);
   int rc = check_common(h, items);
@@ -688,6 +747,8 @@ int artp_check_motions_device(artp_handle* hh, const double* d_s1, const double*
   if (!d_s1 || !d_s2 || !d_valid) { h->err = "null buffer"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
+  ChainScope cs(h, 0, s);
+  if (cs.rc) return cs.rc;
   fill_u8_kernel<<<std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 8), 256, 0, s>>>(d_valid, n, 1);
   CU_TRY(h, cudaGetLastError());
   artp::Work w;
@@ -706,7 +767,7 @@ int artp_check_motions(artp_handle* hh, const double* s1, const double* s2, size
   if (n > 0 && n_steps >= 0 && n * ((size_t)n_steps + 1) <= (size_t)artp::kSmallBatch && 2 * n <= (size_t)artp::kSmallBatch &&
       s1 && s2 && valid) {
     // latency path (a single checkMotion call): one fused launch, interpolation on the device as in the pipeline
-    std::lock_guard<std::mutex> lk(h->mtx);
+    std::lock_guard<std::recursive_mutex> lk(h->mtx);
     if (h->has_map && !h->timing) {
       CU_TRY(h, cudaSetDevice(h->device));
       artp::SmallBatch sb;
@@ -718,25 +779,25 @@ int artp_check_motions(artp_handle* hh, const double* s1, const double* s2, size
     }
   }
   const size_t sb = n * 7 * sizeof(double), sb_al = (sb + 255) & ~(size_t)255;
-  {
-    std::lock_guard<std::mutex> lk(h->mtx);
-    if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
-    if (n == 0) return ARTP_OK;
-    if (!s1 || !s2 || !valid) { h->err = "null buffer"; return ARTP_E_INVALID; }
-    CU_TRY(h, cudaSetDevice(h->device));
-    int rc = ensure_stage(h, 2 * sb_al + n);
-    if (rc) return rc;
-    CU_TRY(h, cudaMemcpyAsync(h->d_stage, s1, sb, cudaMemcpyHostToDevice, h->stream));
-    CU_TRY(h, cudaMemcpyAsync((char*)h->d_stage + sb_al, s2, sb, cudaMemcpyHostToDevice, h->stream));
-  }
-  uint8_t* d_valid = (uint8_t*)h->d_stage + 2 * sb_al;
-  int rc = artp_check_motions_device(hh, (const double*)h->d_stage, (const double*)((char*)h->d_stage + sb_al), n, n_steps,
-                                     d_valid, h->stream);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);   // held across stage -> launch -> D2H: d_stage is per handle
+  if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
+  if (n == 0) return ARTP_OK;
+  if (!s1 || !s2 || !valid) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  int rc = chain_begin(h, 0, h->stream);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(h->mtx);
+  rc = ensure_stage(h, 2 * sb_al + n);
+  if (rc) return rc;
+  CU_TRY(h, cudaMemcpyAsync(h->d_stage, s1, sb, cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, cudaMemcpyAsync((char*)h->d_stage + sb_al, s2, sb, cudaMemcpyHostToDevice, h->stream));
+  uint8_t* d_valid = (uint8_t*)h->d_stage + 2 * sb_al;
+  rc = artp_check_motions_device(hh, (const double*)h->d_stage, (const double*)((char*)h->d_stage + sb_al), n, n_steps,
+                                 d_valid, h->stream);
+  if (rc) return rc;
   CU_TRY(h, cudaMemcpyAsync(valid, d_valid, n, cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
-  return ARTP_OK;
+  h->chain_busy[0] = false;
+  return take_sticky_error(h);
 }
 
 // valid_prefix[e] = number of leading 1s in item_valid[item_off[e] .. item_off[e+1])
@@ -755,7 +816,7 @@ int artp_check_edge_interiors_device(artp_handle* hh, const double* d_s1, const 
                                      int32_t* d_valid_prefix, void* stream) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   int rc = check_common(h, total_items);
   if (rc) return rc;
   if (n == 0) return ARTP_OK;
@@ -765,6 +826,8 @@ int artp_check_edge_interiors_device(artp_handle* hh, const double* d_s1, const 
   if (n >= 0xFFFFFFFFull) { h->err = "too many edges"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
+  ChainScope cs(h, 0, s);
+  if (cs.rc) return cs.rc;
   h->stats.last_launches = 0;
   if (total_items) {
     artp::Work w;
@@ -789,7 +852,7 @@ int artp_check_edge_interiors(artp_handle* hh, const double* s1, const double* s
   std::vector<uint32_t> off;
   size_t total = 0, sb_al = 0, ob_al = 0, pb_al = 0;
   {
-    std::lock_guard<std::mutex> lk(h->mtx);
+    std::lock_guard<std::recursive_mutex> lk(h->mtx);
     if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
     if (n == 0) return ARTP_OK;
     if (!s1 || !s2 || !valid_prefix) { h->err = "null buffer"; return ARTP_E_INVALID; }
@@ -827,7 +890,7 @@ int artp_check_edge_interiors(artp_handle* hh, const double* s1, const double* s
                                             (const uint32_t*)(base + 2 * sb_al), total,
                                             (uint8_t*)(base + 2 * sb_al + ob_al + pb_al), d_prefix, h->stream);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   CU_TRY(h, cudaMemcpyAsync(valid_prefix, d_prefix, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));   // `off` must outlive its H2D copy: it does, we synchronise here
   return ARTP_OK;
@@ -837,7 +900,7 @@ int artp_path_length_cost_device(artp_handle* hh, const double* d_s1, const doub
                                  void* stream) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (n == 0) return ARTP_OK;
   if (!d_s1 || !d_s2 || !d_cost) { h->err = "null buffer"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
@@ -854,7 +917,7 @@ int artp_path_length_cost(artp_handle* hh, const double* s1, const double* s2, s
   Handle* h = reinterpret_cast<Handle*>(hh);
   const size_t sb = n * 7 * sizeof(double), sb_al = (sb + 255) & ~(size_t)255;
   {
-    std::lock_guard<std::mutex> lk(h->mtx);
+    std::lock_guard<std::recursive_mutex> lk(h->mtx);
     if (n == 0) return ARTP_OK;
     if (!s1 || !s2 || !cost) { h->err = "null buffer"; return ARTP_E_INVALID; }
     CU_TRY(h, cudaSetDevice(h->device));
@@ -867,7 +930,7 @@ int artp_path_length_cost(artp_handle* hh, const double* s1, const double* s2, s
   int rc = artp_path_length_cost_device(hh, (const double*)h->d_stage, (const double*)((char*)h->d_stage + sb_al), n, d_cost,
                                         h->stream);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   CU_TRY(h, cudaMemcpyAsync(cost, d_cost, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   return ARTP_OK;
@@ -899,7 +962,7 @@ int artp_compact_valid_device(artp_handle* hh, const uint8_t* d_valid, size_t n,
                               uint32_t* d_count, void* stream) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (!d_valid || !d_indices || !d_count) { h->err = "null buffer"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
   return compact_valid_impl(h, d_valid, n, base, d_indices, d_count, (cudaStream_t)stream);
@@ -908,7 +971,7 @@ int artp_compact_valid_device(artp_handle* hh, const uint8_t* d_valid, size_t n,
 int artp_pack_valid_bits_device(artp_handle* hh, const uint8_t* d_valid, size_t n, uint32_t* d_bits, void* stream) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (n == 0) return ARTP_OK;
   if (!d_valid || !d_bits) { h->err = "null buffer"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
@@ -925,7 +988,7 @@ int artp_compact_bits_device(artp_handle* hh, const uint32_t* d_bits, size_t n, 
                              uint32_t* d_count, void* stream) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (!d_bits || !d_indices || !d_count) { h->err = "null buffer"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
   return compact_valid_impl(h, reinterpret_cast<const uint8_t*>(d_bits), n, base, d_indices, d_count, (cudaStream_t)stream, true);
@@ -952,7 +1015,7 @@ int artp_estimate_normals(artp_handle* hh, double estimation_radius, float* norm
                           float* plane_fit_std_dev) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
   if (!(estimation_radius >= 0.0)) { h->err = "estimation_radius < 0"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
@@ -980,7 +1043,7 @@ int artp_estimate_normals(artp_handle* hh, double estimation_radius, float* norm
 int artp_compute_sample_cdf(artp_handle* hh, const float* sample_probability, float* cum_prob, float* cum_prob_rowwise) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
   if (!sample_probability) { h->err = "null buffer"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
@@ -1011,7 +1074,7 @@ int artp_set_sampler(artp_handle* hh, const artp_sampler_params* sp, const float
                      const float* cum_prob_rowwise) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
   const bool host_normals = normal_x && normal_y && normal_z && plane_fit_std_dev;
   if (!sp) { h->err = "null sampler params"; return ARTP_E_INVALID; }
@@ -1091,7 +1154,7 @@ static inline unsigned grid_for(Handle* h, size_t n, int block) {
 int artp_sampler_uniforms(artp_handle* hh, uint64_t seed, uint64_t first_sample, size_t n, double* u) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (n == 0) return ARTP_OK;
   if (!u) { h->err = "null buffer"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
@@ -1109,7 +1172,7 @@ int artp_sample_states_device(artp_handle* hh, const double* d_u, uint64_t seed,
                               double* d_states, int32_t* d_rowcol, void* stream) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   int rc = sampler_ready(h);
   if (rc) return rc;
   if (n == 0) return ARTP_OK;
@@ -1129,7 +1192,7 @@ int artp_sample_states(artp_handle* hh, const double* u, uint64_t seed, uint64_t
   Handle* h = reinterpret_cast<Handle*>(hh);
   const size_t ub = (n * 6 * sizeof(double) + 255) & ~(size_t)255, sb = (n * 7 * sizeof(double) + 255) & ~(size_t)255;
   {
-    std::lock_guard<std::mutex> lk(h->mtx);
+    std::lock_guard<std::recursive_mutex> lk(h->mtx);
     int rc = sampler_ready(h);
     if (rc) return rc;
     if (n == 0) return ARTP_OK;
@@ -1143,7 +1206,7 @@ int artp_sample_states(artp_handle* hh, const double* u, uint64_t seed, uint64_t
   int rc = artp_sample_states_device(hh, u ? (const double*)base : nullptr, seed, first_sample, n, (double*)(base + ub),
                                      rowcol ? (int32_t*)(base + ub + sb) : nullptr, h->stream);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   CU_TRY(h, cudaMemcpyAsync(states, base + ub, n * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (rowcol) CU_TRY(h, cudaMemcpyAsync(rowcol, base + ub + sb, n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1174,7 +1237,7 @@ int artp_sample_valid_device(artp_handle* hh, uint64_t seed, uint64_t first_samp
                              size_t capacity, uint32_t* d_count, void* stream) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   int rc = sampler_ready(h);
   if (rc) return rc;
   if (!d_count || (capacity && !d_states_out)) { h->err = "null buffer"; return ARTP_E_INVALID; }
@@ -1234,7 +1297,7 @@ int artp_sample_valid(artp_handle* hh, uint64_t seed, uint64_t first_sample, siz
   Handle* h = reinterpret_cast<Handle*>(hh);
   const size_t cap = std::min(capacity, n_draw);
   {
-    std::lock_guard<std::mutex> lk(h->mtx);
+    std::lock_guard<std::recursive_mutex> lk(h->mtx);
     int rc = sampler_ready(h);
     if (rc) return rc;
     if (!n_valid || (cap && !states)) { h->err = "null buffer"; return ARTP_E_INVALID; }
@@ -1245,7 +1308,7 @@ int artp_sample_valid(artp_handle* hh, uint64_t seed, uint64_t first_sample, siz
   uint32_t* d_count = (uint32_t*)((char*)h->d_stage + cap * 7 * sizeof(double));
   int rc = artp_sample_valid_device(hh, seed, first_sample, n_draw, (double*)h->d_stage, cap, d_count, h->stream);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   uint32_t cnt = 0;
   CU_TRY(h, cudaMemcpyAsync(&cnt, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1263,14 +1326,14 @@ size_t artp_cost_weights_size(void) { return artp_cnn::blob_floats(); }
 int artp_set_cost_weights(artp_handle* hh, const float* blob, size_t n_floats) {
   if (!hh || !blob) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   return artp_cnn::set_weights(h->cnn, blob, n_floats, h->stream, h->err);
 }
 
 int artp_update_features(artp_handle* hh) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
   artp_cnn::set_base_offset_mode(h->cnn, (h->cnn_mode & 2) ? 1 : 0);
   artp_cnn::set_conv15_mode(h->cnn, (h->cnn_mode >> 2) & 3);
@@ -1281,7 +1344,7 @@ int artp_update_features(artp_handle* hh) {
 int artp_motion_cost_device(artp_handle* hh, const float* d_edges, size_t n, float* d_cost3, void* stream) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (n && (!d_edges || !d_cost3)) { h->err = "null buffer"; return ARTP_E_INVALID; }
   int rc = artp_cnn::motion_cost(h->cnn, d_edges, n, d_cost3, (cudaStream_t)stream, h->err);
   if (rc == 0 && n) { h->stats.kernel_launches += 1; h->stats.last_launches = 1; }
@@ -1294,7 +1357,7 @@ int artp_motion_cost(artp_handle* hh, const float* edges, size_t n, float* cost3
   if (n == 0) return ARTP_OK;
   const size_t in_b = n * 6 * sizeof(float), in_al = (in_b + 255) & ~(size_t)255;
   {
-    std::lock_guard<std::mutex> lk(h->mtx);
+    std::lock_guard<std::recursive_mutex> lk(h->mtx);
     if (!edges || !cost3) { h->err = "null buffer"; return ARTP_E_INVALID; }
     CU_TRY(h, cudaSetDevice(h->device));
     int rc = ensure_stage(h, in_al + n * 3 * sizeof(float));
@@ -1304,7 +1367,7 @@ int artp_motion_cost(artp_handle* hh, const float* edges, size_t n, float* cost3
   float* d_cost = (float*)((char*)h->d_stage + in_al);
   int rc = artp_motion_cost_device(hh, (const float*)h->d_stage, n, d_cost, h->stream);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   CU_TRY(h, cudaMemcpyAsync(cost3, d_cost, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   return ARTP_OK;
@@ -1325,7 +1388,7 @@ int artp_combine_cost(artp_handle* hh, const float* cost3, size_t n, double* cos
 int artp_get_features(artp_handle* hh, float* out, size_t n_floats, int* hf, int* wf) {
   if (!hh || !hf || !wf) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
-  std::lock_guard<std::mutex> lk(h->mtx);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   artp_cnn::feature_shape(h->cnn, hf, wf);
   if (!out) return ARTP_OK;
   return artp_cnn::copy_features(h->cnn, out, n_floats, h->err);

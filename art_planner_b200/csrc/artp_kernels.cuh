@@ -861,7 +861,9 @@ box_items_block_kernel(const Checker c, const Work w, const BoxRec* __restrict__
     rec_to_ctx(c, r, b);
     const int res = box_collide_block(foot ? c.f[1] : c.f[0], b, sh, red, &s_next);
     if (threadIdx.x == 0) {
-      if (res == R_DEFER) atomicAdd(overflow, 1u);
+      // a zone that does not fit the plane store cannot be decided: fail closed (item invalid) and raise the sticky
+      // error word (mapped host memory; the host returns ARTP_E_LIMIT from the call / artp_poll_error)
+      if (res == R_DEFER) { *(volatile uint32_t*)overflow = 1u; w.valid[slot] = 0; }
       else if ((!foot && res == R_HIT) || (foot && res == R_FREE)) w.valid[slot] = 0;
     }
     __syncthreads();
@@ -953,10 +955,10 @@ pose_small_kernel(const Checker c, const SmallBatch sb, uint8_t* __restrict__ ou
       if (r == -1 || r == R_DEFER) {          // -1 only in force_all mode
         const bool foot = k > 0;
         r = box_collide_block(foot ? c.f[1] : c.f[0], s_box[k], sh, red, &s_next);
-        if (r == R_DEFER && tid == 0) atomicAdd(overflow, 1u);
+        if (r == R_DEFER) { if (tid == 0) *(volatile uint32_t*)overflow = 1u; valid = false; }   // fail closed
         __syncthreads();
       }
-      if (r == kBoxOutside) continue;
+      if (r == kBoxOutside || r == R_DEFER) continue;
       if ((k == 0 && r == R_HIT) || (k > 0 && r == R_FREE)) valid = false;
     }
   }

@@ -141,14 +141,15 @@ def _gradient_noise(seed: int, octave: int, u: np.ndarray, v: np.ndarray) -> np.
 
 
 def fbm_height(seed: int, x: np.ndarray, y: np.ndarray, amp: float, wavelength: float = 8.0,
-               octaves: int = 5) -> np.ndarray:
-    """fBm of gradient noise: `octaves` octaves, base wavelength in metres, peak amplitude ~amp."""
+               octaves: int = 5, persistence: float = 0.5) -> np.ndarray:
+    """fBm of gradient noise: `octaves` octaves, base wavelength in metres, peak amplitude ~amp; every octave has
+    `persistence` times the amplitude of the previous one (0.5 = the classic 1/f spectrum)."""
     h = np.zeros(np.broadcast(x, y).shape, dtype=np.float64)
     a, f, norm = 1.0, 1.0 / wavelength, 0.0
     for o in range(octaves):
         h += a * _gradient_noise(seed, o, x * f + 0.37 * (o + 1), y * f + 0.61 * (o + 1))
         norm += a
-        a *= 0.5
+        a *= persistence
         f *= 2.0
     return h * (amp * 1.4142135623730951 / norm)
 
@@ -160,13 +161,13 @@ def make_flat_map(rows=200, cols=200, res=0.04, height=0.0, cx=0.0, cy=0.0) -> S
 
 
 def make_fbm_map(rows=1000, cols=1000, res=0.04, seed=2, amp=0.6, wavelength=8.0, octaves=5,
-                 blob_frac=0.02, n_walls=6, wall_height=0.5, cx=0.0, cy=0.0) -> SynthMap:
+                 blob_frac=0.02, n_walls=6, wall_height=0.5, cx=0.0, cy=0.0, persistence=0.5) -> SynthMap:
     """C2/C5: fBm terrain + a few step walls; ~blob_frac of the cells in 0.3-1 m square blobs are
     untraversable (-inf in `elevation_masked`)."""
     m = SynthMap(np.zeros((rows, cols), np.float32, order="F"), np.zeros((1, 1), np.float32), res, cx, cy, "")
     x, y = m.cell_xy()
     lx, ly = m.length
-    e = fbm_height(seed, x[:, None], y[None, :], amp, wavelength, octaves)
+    e = fbm_height(seed, x[:, None], y[None, :], amp, wavelength, octaves, persistence)
     # step walls: axis-aligned slabs raised by wall_height
     for w in range(n_walls):
         u = hash_uniform(seed, 2000 + w, np.arange(5))
@@ -193,7 +194,7 @@ def make_fbm_map(rows=1000, cols=1000, res=0.04, seed=2, amp=0.6, wavelength=8.0
         for a in range(n_blobs):
             masked[i0[a]:i1[a] + 1, j0[a]:j1[a] + 1] = -np.inf
     desc = (f"fBm gradient noise {rows}x{cols}@{res} seed={seed} amp={amp} wavelength={wavelength} "
-            f"octaves={octaves} walls={n_walls}x{wall_height}m blobs={blob_frac}")
+            f"octaves={octaves} persistence={persistence} walls={n_walls}x{wall_height}m blobs={blob_frac}")
     return SynthMap(e32, masked, res, cx, cy, desc)
 
 
@@ -245,10 +246,12 @@ def make_flat_poses(m: SynthMap, n: int, seed: int = 1, start: int = 0, margin: 
 
 def make_terrain_poses(m: SynthMap, n: int, seed: int = 3, start: int = 0, z_range: float = 0.12,
                        roll_pert: float = math.radians(3.33), pitch_pert: float = math.radians(10.0),
-                       xy: tuple | None = None) -> np.ndarray:
+                       xy: tuple | None = None, normal_cells: int = 1) -> np.ndarray:
     """C2/C5 samples: x,y uniform inside the map, yaw uniform, z = cell height + U(+-z_range),
     roll/pitch = terrain-normal aligned + U(+-pert), like SE3FromSE2Sampler::sampleUniform
-    (art_planner/src/sampler.cpp:82-131). Returns [n, 7] float64."""
+    (art_planner/src/sampler.cpp:82-131). The normal is the central difference over +-normal_cells cells
+    (the reference's estimateNormals averages over estimation_radius = (torso length + width)/4, utils.cpp:213-324;
+    normal_cells = 12 is that radius at 0.04 m). Returns [n, 7] float64."""
     k = np.arange(start, start + n)
     lx, ly = m.length
     if xy is None:
@@ -261,8 +264,9 @@ def make_terrain_poses(m: SynthMap, n: int, seed: int = 3, start: int = 0, z_ran
     z = e[i, j].astype(np.float64) + (hash_uniform(seed, 3, k) * 2 - 1) * z_range
     yaw = (hash_uniform(seed, 4, k) * 2 - 1) * math.pi
     # finite-difference normal (x decreases with i, y decreases with j)
-    ip, im = np.clip(i + 1, 0, m.rows - 1), np.clip(i - 1, 0, m.rows - 1)
-    jp, jm = np.clip(j + 1, 0, m.cols - 1), np.clip(j - 1, 0, m.cols - 1)
+    nc = int(normal_cells)
+    ip, im = np.clip(i + nc, 0, m.rows - 1), np.clip(i - nc, 0, m.rows - 1)
+    jp, jm = np.clip(j + nc, 0, m.cols - 1), np.clip(j - nc, 0, m.cols - 1)
     dzdx = (e[im, j].astype(np.float64) - e[ip, j]) / ((ip - im) * m.res)
     dzdy = (e[i, jm].astype(np.float64) - e[i, jp]) / ((jp - jm) * m.res)
     nrm = np.sqrt(dzdx * dzdx + dzdy * dzdy + 1.0)

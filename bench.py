@@ -125,6 +125,60 @@ def best_thread_count(o, poses, cores, big_map=False):
     return best
 
 
+STAGE_NAMES = ("aabb", "above", "under", "span", "single_plane", "vertex", "plane_hit", "fall_through")
+#: the "rough" level of SURVEY 8(d): fBm with more high-frequency energy; poses aligned to the normal over +-12 cells
+#: (= the reference's estimateNormals radius at 0.04 m) so that most torso boxes reach the triangle / plane pass
+ROUGH_MAP = dict(amp=1.2, wavelength=3.0, persistence=0.7)
+ROUGH_POSES = dict(normal_cells=12)
+
+
+def exit_mix(port, poses):
+    """Per-box exit stage of the reference collider (port statistics, no pose-level short-circuit): torso and feet."""
+    st, _, _ = port.pose_box_stats(poses)
+    t = np.bincount(st[:, 0], minlength=256)
+    f = np.bincount(st[:, 1:].ravel(), minlength=256)
+    return {"torso": {k: round(float(t[i]) / len(st), 4) for i, k in enumerate(STAGE_NAMES)},
+            "feet": {k: round(float(f[i]) / (4 * len(st)), 4) for i, k in enumerate(STAGE_NAMES)},
+            "sample": len(st)}
+
+
+def pose_workload(torch, chk, flush, m, poses, steps, ref, kind, port, n_mt=400_000, n1=20_000):
+    """One 1M-pose validity batch on map m, device-resident: per-stage times, queue sizes, exit mix, and the compiled
+    reference (single thread + all threads) on a prefix with the mask compared."""
+    n = len(poses)
+    chk.setMap(m); chk.updateHeightField(); chk.setTiming(True)
+    d = torch.from_numpy(poses).cuda()
+    out = torch.empty(n, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        chk.isValidBatch(d, out=out)
+    torch.cuda.synchronize()
+    ks, tot = [], 0.0
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(steps):
+        flush.fill_(i & 0xFF)
+        a.record(); chk.isValidBatch(d, out=out); b.record()
+        ks.append(chk.lastKernelTimesMs())
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    st = chk.stats()
+    got = out.cpu().numpy()
+    k = np.mean(np.array(ks), 0)
+    ref.set_map(m); port.set_map(m)
+    cores = best_thread_count(ref, poses, os.cpu_count() or 1)
+    t0 = time.perf_counter(); v1 = ref.check_poses(poses[:n1]); t1 = time.perf_counter() - t0
+    ref.check_poses_mt(poses[:cores * 64], cores)
+    t0 = time.perf_counter(); vm = ref.check_poses_mt(poses[:n_mt], cores); tm = time.perf_counter() - t0
+    _, zv = port.check_poses(poses[:50_000], want_zone=True)
+    return {"map": m.desc, "poses": n, "poses_per_s": n * steps / (tot * 1e-3), "ms_per_step": tot / steps,
+            "classify_ms": float(k[0]), "warp_stage_ms": float(k[1]), "group_stage_ms": float(k[2]),
+            "queued_boxes": st["last_queued_boxes"], "deferred_boxes": st["last_deferred"],
+            "valid_fraction": float(got.mean()), "exit_mix": exit_mix(port, poses[:20_000]),
+            "algorithmic_bytes_per_pose": 57.0 + 4.0 * float(zv.mean()),
+            "cpu": {"kind": kind, "single_thread_poses_per_s": n1 / t1, "all_threads_poses_per_s": n_mt / tm, "cores": cores,
+                    "sample": f"first {n_mt} poses ({cores} threads), first {n1} (1 thread)",
+                    "mask_equals_gpu": bool(np.array_equal(got[:n_mt], vm) and np.array_equal(got[:n1], v1))}}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path on all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -320,9 +374,30 @@ def main():
             mv.checkMotionBatch(d1, d2, out=ev_out)
         bb.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(bb) / 20
+        o_e, kind_e = cpu_oracle(synth.PARAMS_YAML)      # mask of the FULL batch against the compiled reference
+        o_e.set_map(m)
+        cores_e = min(os.cpu_count() or 1, 32)
+        t0 = time.perf_counter(); ev_ref = o_e.check_motions_mt(s1, s2, 20, cores_e); t_e = time.perf_counter() - t0
         secondary["edge_validity"] = {"workload": "configs[2]: 100k edges x 20 interpolation steps (+ end state), same map",
                                       "edges_per_s": 100_000 / (ms * 1e-3), "state_checks_per_s_upper": 2_100_000 / (ms * 1e-3),
-                                      "ms_per_batch": ms, "valid_fraction": float(ev_out.float().mean())}
+                                      "ms_per_batch": ms, "valid_fraction": float(ev_out.float().mean()),
+                                      "mask_equals_reference": bool(np.array_equal(ev_out.cpu().numpy(), ev_ref)),
+                                      "cpu": {"kind": kind_e, "cores": cores_e, "edges_per_s": 100_000 / t_e,
+                                              "sample": "all 100k edges (early exit at the first invalid state)"}}
+        del o_e
+        try:   # C2 at a second roughness level -- the regime where most torso boxes reach the plane pass
+            from oracle import orc
+            m_r = synth.make_fbm_map(MAP_N, MAP_N, MAP_RES, seed=MAP_SEED, **ROUGH_MAP)
+            p_r = synth.make_terrain_poses(m_r, n, seed=POSE_SEED, **ROUGH_POSES)
+            o_r, kind_r = cpu_oracle(synth.PARAMS_YAML)
+            orc.build("port")
+            chk_r = apb.StateValidityChecker(synth.PARAMS_YAML, device=local)
+            secondary["c2_rough"] = pose_workload(torch, chk_r, flush, m_r, p_r, 20, o_r, kind_r,
+                                                  orc.Oracle(synth.PARAMS_YAML, "port"))
+            secondary["c2_rough"]["generator"] = {"map": ROUGH_MAP, "poses": ROUGH_POSES, "map_seed": MAP_SEED, "pose_seed": POSE_SEED}
+            del chk_r, o_r
+        except Exception as ex:
+            secondary["c2_rough"] = {"error": repr(ex)}
         try:   # addValidMilestone connection batches (prm_motion_cost.cpp:341-372): per-edge interior-state counts
             e1, e2 = synth.make_edges(m, 200_000, seed=9, dmin=0.05, dmax=3.4)
             g1, g2 = torch.from_numpy(e1).cuda(), torch.from_numpy(e2).cuda()

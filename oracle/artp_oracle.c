@@ -802,3 +802,38 @@ int orc_check_poses_mt(orc_handle* h, const double* states, size_t n, uint8_t* v
   free(th); free(jobs);
   return 0;
 }
+
+typedef struct mt_edge_job { orc_handle* h; const double *s1, *s2; size_t lo, hi; int n_steps; uint8_t* valid; } mt_edge_job;
+
+static void* mt_edge_worker(void* v) {
+  mt_edge_job* j = (mt_edge_job*)v;
+  port_ctx c = {j->h, {0, 0, 0, 0, 0, 0, 0}};
+  for (size_t i = j->lo; i < j->hi; ++i) {
+    int ok = orc_state_valid(&j->h->p, &j->h->g, port_collide, &c, j->s2 + 7 * i, NULL);
+    for (int k = 1; k <= j->n_steps && ok; ++k) {
+      double st[7];
+      orc_se3_interpolate(j->s1 + 7 * i, j->s2 + 7 * i, (double)k / (double)(j->n_steps + 1), st);
+      ok = orc_state_valid(&j->h->p, &j->h->g, port_collide, &c, st, NULL);
+    }
+    j->valid[i] = (uint8_t)ok;
+  }
+  free(c.sc.tri); free(c.sc.group);
+  return NULL;
+}
+
+/* orc_check_motions on n_threads workers. */
+int orc_check_motions_mt(orc_handle* h, const double* s1, const double* s2, size_t n, int n_steps, uint8_t* valid,
+                         int n_threads) {
+  if (!h || !h->g.has_map) return 1;
+  if (n_threads < 1) n_threads = 1;
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * n_threads);
+  mt_edge_job* jobs = (mt_edge_job*)malloc(sizeof(mt_edge_job) * n_threads);
+  for (int t = 0; t < n_threads; ++t) {
+    jobs[t].h = h; jobs[t].s1 = s1; jobs[t].s2 = s2; jobs[t].valid = valid; jobs[t].n_steps = n_steps;
+    jobs[t].lo = n * (size_t)t / n_threads; jobs[t].hi = n * (size_t)(t + 1) / n_threads;
+    pthread_create(&th[t], NULL, mt_edge_worker, &jobs[t]);
+  }
+  for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+  free(th); free(jobs);
+  return 0;
+}

@@ -124,6 +124,10 @@ int orc_path_length_cost(orc_handle* h, const double* s1, const double* s2, size
  * ("all cores" CPU baseline). */
 int orc_check_poses_mt(orc_handle* h, const double* states, size_t n, uint8_t* valid, int n_threads);
 
+/* orc_check_motions with T worker threads (bench.py: mask check of the full configs[2] batch). */
+int orc_check_motions_mt(orc_handle* h, const double* s1, const double* s2, size_t n, int n_steps, uint8_t* valid,
+                         int n_threads);
+
 /* Identifies the implementation: "port" or "reference". */
 const char* orc_kind(void);
 

@@ -128,6 +128,7 @@ class Oracle:
         lib.orc_path_length_cost.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         lib.orc_check_edge_interiors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_double, C.c_void_p]
         lib.orc_check_poses_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+        lib.orc_check_motions_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_int]
         lib.orc_kind.restype = C.c_char_p
         p = OrcParams()
         for name, _ in OrcParams._fields_:
@@ -192,6 +193,28 @@ class Oracle:
                                         valid.ctypes.data, zv.ctypes.data)
         assert rc == 0
         return (valid, zv) if want_zone else valid
+
+    def check_motions_mt(self, s1, s2, n_steps: int, n_threads: int):
+        a, b = _f64(s1), _f64(s2)
+        n = a.shape[0]
+        valid = np.zeros(n, np.uint8)
+        rc = self.lib.orc_check_motions_mt(self.h, a.ctypes.data, b.ctypes.data, n, int(n_steps), valid.ctypes.data,
+                                           int(n_threads))
+        assert rc == 0
+        return valid
+
+    def pose_box_stats(self, states):
+        """Port library only: per (pose, box) exit stage of the collider WITHOUT the pose-level short-circuits
+        (ORC_ST_*: 0 aabb, 1 above, 2 under, 3 span, 4 single plane, 5 vertex, 6 plane hit, 7 fall-through, 255 outside
+        the map), hit flag and zone vertex count; arrays of shape [n, 5] (box 0 = torso, 1..4 = feet)."""
+        assert self.kind == "port"
+        s = _f64(states)
+        n = s.shape[0]
+        st = np.zeros((n, 5), np.uint8); hit = np.zeros((n, 5), np.uint8); zv = np.zeros((n, 5), np.uint32)
+        f = self.lib.orc_port_pose_box_stats
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        assert f(self.h, s.ctypes.data, n, st.ctypes.data, hit.ctypes.data, zv.ctypes.data) == 0
+        return st, hit, zv
 
     def check_edge_interiors(self, s1, s2, n_interp=None, max_lateral=0.5):
         a, b = _f64(s1), _f64(s2)

@@ -222,6 +222,36 @@ int orc_check_poses_mt(orc_handle* h, const double* states, size_t n, uint8_t* v
   return 0;
 }
 
+// orc_check_motions on n_threads workers (same per-thread worlds as orc_check_poses_mt).
+int orc_check_motions_mt(orc_handle* h, const double* s1, const double* s2, size_t n, int n_steps, uint8_t* valid,
+                         int n_threads) {
+  if (!h || !h->g.has_map) return 1;
+  if (n_threads < 1) n_threads = 1;
+  while ((int)h->mt_pairs.size() < n_threads) {
+    CheckerPair* cp = new CheckerPair(h->p);
+    cp->setMap(h->map);
+    h->mt_pairs.push_back(cp);
+  }
+  std::vector<CheckerPair*>& pairs = h->mt_pairs;
+  std::vector<std::thread> th;
+  for (int t = 0; t < n_threads; ++t) {
+    th.emplace_back([=, &pairs] {
+      const size_t lo = n * (size_t)t / n_threads, hi = n * (size_t)(t + 1) / n_threads;
+      for (size_t i = lo; i < hi; ++i) {
+        int ok = orc_state_valid(&h->p, &h->g, ref_collide, pairs[t], s2 + 7 * i, nullptr);
+        for (int j = 1; j <= n_steps && ok; ++j) {
+          double st[7];
+          orc_se3_interpolate(s1 + 7 * i, s2 + 7 * i, (double)j / (double)(n_steps + 1), st);
+          ok = orc_state_valid(&h->p, &h->g, ref_collide, pairs[t], st, nullptr);
+        }
+        valid[i] = (uint8_t)ok;
+      }
+    });
+  }
+  for (auto& x : th) x.join();
+  return 0;
+}
+
 // Extra (reference library only): the heightfield body's rotation after dBodySetRotation, so the test
 // can pin the constant matrix the port hard-codes.
 void orc_ref_field_rotation(orc_handle* h, float out[12]) { h->pair->torso.fieldRotation(out); }

@@ -48,7 +48,52 @@ def c4_map():
     return synth.make_fbm_map(256, 256, 0.04, seed=2, amp=0.6)
 
 
+def terraces():
+    """Piecewise-constant steps: large coplanar triangle sets, the worst case for the greedy eps-grouping
+    (heightfield.cpp:1511-1556)."""
+    import dataclasses
+    m = synth.make_flat_map()
+    e = np.array(m.elevation, dtype=np.float32, order="F")
+    r, c = np.indices(e.shape)
+    e[:] = (0.07 * ((r // 9) % 4) + 0.05 * ((c // 13) % 3)).astype(np.float32)
+    return dataclasses.replace(m, elevation=e, elevation_masked=np.asfortranarray(e.copy()), desc="terraces")
+
+
+def spikes():
+    """Gentle fBm with 1 % isolated 0.4 m spikes: single-vertex contacts and very steep triangles."""
+    import dataclasses
+    m = synth.make_fbm_map(200, 200, amp=0.2)
+    e = np.array(m.elevation, dtype=np.float32, order="F")
+    k = np.arange(e.size).reshape(e.shape)
+    e[synth.hash_uniform(77, 1, k) < 0.01] += 0.4
+    mk = np.array(m.elevation_masked, dtype=np.float32, order="F")
+    fin = np.isfinite(mk)
+    mk[fin] = e[fin]
+    return dataclasses.replace(m, elevation=e, elevation_masked=mk, desc="spikes")
+
+
+def terraces_tilted():
+    """The terraces sheared by a small planar ramp: every terrace is a large set of triangles whose planes are equal only
+    up to rounding -- epsilon-grouping near its threshold instead of exactly coplanar."""
+    import dataclasses
+    m = terraces()
+    xs, ys = m.cell_xy()
+    e = (m.elevation.astype(np.float64) + 0.013 * xs[:, None] - 0.007 * ys[None, :]).astype(np.float32)
+    e = np.asfortranarray(e)
+    return dataclasses.replace(m, elevation=e, elevation_masked=e.copy(order="F"), desc="terraces + planar shear")
+
+
+#: "rough" regime of SURVEY 8(a10) / 8(d): most torso boxes get past the collider's early outs (port statistics on this
+#: map with HARD_POSES: above 26 %, vertex 22 %, plane 1 %, fall-through 49 %)
+HARD = dict(amp=1.2, wavelength=3.0, persistence=0.7)
+HARD_POSES = dict(normal_cells=12)
+
+
 MAPS = {
+    "terraces": terraces,
+    "terraces_tilted": terraces_tilted,
+    "spikes": spikes,
+    "fbm_hard": lambda: synth.make_fbm_map(400, 400, **HARD),
     "flat": lambda: synth.make_flat_map(),
     "flat_holes_terrace": flat_holes_terrace,
     "ramp": ramp,
@@ -75,6 +120,18 @@ POSE_CASES = [
      lambda m: synth.make_terrain_poses(m, 20000, seed=31, z_range=0.4, roll_pert=0.7, pitch_pert=0.7)),
     ("ramp_tilt_header", "ramp", "header",
      lambda m: synth.make_terrain_poses(m, 10000, seed=32, z_range=0.3, roll_pert=0.5, pitch_pert=0.5)),
+    # the hard regime: epsilon-grouping worst cases and terrain where most torso boxes reach the triangle / plane pass
+    ("terraces_yaml", "terraces", "yaml", lambda m: synth.make_terrain_poses(m, 20000, seed=31)),
+    ("terraces_header", "terraces", "header", lambda m: synth.make_terrain_poses(m, 20000, seed=33)),
+    ("terraces_low_yaml", "terraces", "yaml",
+     lambda m: synth.make_terrain_poses(m, 20000, seed=34, z_range=0.25, roll_pert=0.15, pitch_pert=0.2)),
+    ("terraces_tilted_yaml", "terraces_tilted", "yaml", lambda m: synth.make_terrain_poses(m, 20000, seed=35, z_range=0.2)),
+    ("spikes_yaml", "spikes", "yaml", lambda m: synth.make_terrain_poses(m, 20000, seed=31)),
+    ("spikes_header", "spikes", "header", lambda m: synth.make_terrain_poses(m, 20000, seed=36, z_range=0.2)),
+    ("fbm_hard_yaml", "fbm_hard", "yaml", lambda m: synth.make_terrain_poses(m, 20000, seed=3, **HARD_POSES)),
+    ("fbm_hard_header", "fbm_hard", "header", lambda m: synth.make_terrain_poses(m, 20000, seed=37, **HARD_POSES)),
+    ("fbm_hard_low_yaml", "fbm_hard", "yaml",
+     lambda m: synth.make_terrain_poses(m, 20000, seed=38, z_range=0.3, roll_pert=0.3, pitch_pert=0.3, **HARD_POSES)),
 ]
 
 
@@ -103,6 +160,10 @@ BOX_CASES = [
     ("box_ramp", "ramp", 4, 0.3, 0.3),
     ("box_fbm_rough", "fbm_rough", 5, 0.3, 0.3),
     ("box_fbm_tilt", "fbm_rough", 7, 1.2, 0.6),
+    ("box_terraces", "terraces", 99, 0.9, 0.35),
+    ("box_terraces_tilted", "terraces_tilted", 98, 0.4, 0.3),
+    ("box_spikes", "spikes", 99, 0.9, 0.35),
+    ("box_fbm_hard", "fbm_hard", 97, 0.5, 0.4),
 ]
 BOX_N = 20000
 
@@ -117,6 +178,8 @@ INTERIOR_CASES = [
 EDGE_CASES = [
     ("edges_fbm_rough_yaml", "fbm_rough", "yaml", 3000, 20, 4),
     ("edges_fixture_header", "fixture", "header", 3000, 7, 5),
+    ("edges_fbm_hard_yaml", "fbm_hard", "yaml", 4000, 3, 41),
+    ("edges_terraces_yaml", "terraces", "yaml", 4000, 4, 42),
 ]
 
 

@@ -110,31 +110,8 @@ def test_port_equals_compiled_reference_on_fresh_seeds(maps, port_lib):
             assert np.array_equal(P.box_collide(which, org, rot), R.box_collide(which, org, rot))
 
 
-def _terraces():
-    """Piecewise-constant steps: large coplanar triangle sets, the worst case for the greedy eps-grouping."""
-    import dataclasses
-    m = synth.make_flat_map()
-    e = np.array(m.elevation, dtype=np.float32, order="F")
-    r, c = np.indices(e.shape)
-    e[:] = (0.07 * ((r // 9) % 4) + 0.05 * ((c // 13) % 3)).astype(np.float32)
-    return dataclasses.replace(m, elevation=e, elevation_masked=np.asfortranarray(e.copy()), desc="terraces")
-
-
-def _spikes():
-    """Gentle fBm with 1 % isolated 0.4 m spikes: single-vertex contacts and very steep triangles."""
-    import dataclasses
-    m = synth.make_fbm_map(200, 200, amp=0.2)
-    e = np.array(m.elevation, dtype=np.float32, order="F")
-    k = np.arange(e.size).reshape(e.shape)
-    e[synth.hash_uniform(77, 1, k) < 0.01] += 0.4
-    mk = np.array(m.elevation_masked, dtype=np.float32, order="F")
-    fin = np.isfinite(mk)
-    mk[fin] = e[fin]
-    return dataclasses.replace(m, elevation=e, elevation_masked=mk, desc="spikes")
-
-
 @pytest.mark.skipif(not os.path.isdir("/root/reference/ode"), reason="reference tree not present on this box")
-@pytest.mark.parametrize("mk", [_terraces, _spikes], ids=["terraces", "spikes"])
+@pytest.mark.parametrize("mk", [cases.terraces, cases.spikes, cases.terraces_tilted], ids=["terraces", "spikes", "terraces_tilted"])
 def test_port_equals_compiled_reference_on_adversarial_maps(mk, port_lib):
     port_lib.build("ref")
     m = mk()
@@ -149,3 +126,19 @@ def test_port_equals_compiled_reference_on_adversarial_maps(mk, port_lib):
     for which in (0, 1):
         org, rot = cases.box_samples(m, 20000, 99, which, 0.9, 0.35)
         assert np.array_equal(P.box_collide(which, org, rot), R.box_collide(which, org, rot))
+
+
+def test_hard_regime_exit_mix(maps, port_lib):
+    """The 'fbm_hard' map really is the hard regime (SURVEY 8(a10) 'rough'): most torso boxes get past the early outs."""
+    import ctypes as C
+    m = maps("fbm_hard")
+    o = port_lib.Oracle(cases.PARAMS["yaml"], "port")
+    o.set_map(m)
+    poses = synth.make_terrain_poses(m, 4000, seed=3, **cases.HARD_POSES)
+    n = len(poses)
+    st = np.zeros(5 * n, np.uint8); hit = np.zeros(5 * n, np.uint8); zv = np.zeros(5 * n, np.uint32)
+    f = o.lib.orc_port_pose_box_stats
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert f(o.h, poses.ctypes.data, n, st.ctypes.data, hit.ctypes.data, zv.ctypes.data) == 0
+    torso = np.bincount(st.reshape(n, 5)[:, 0], minlength=8)[:8] / n     # ORC_ST_*: 5 vertex, 6 plane, 7 fall-through
+    assert torso[5] + torso[6] + torso[7] >= 0.5 and torso[7] >= 0.4, torso

@@ -205,3 +205,18 @@ def test_latency_path_small_batches(maps, checkers, port_lib, mk):
     chk.setMode(0)
     far = np.array([[1e3, -1e3, 0.0, 0, 0, 0, 1.0]])           # outside the map: the outside-map rules
     assert np.array_equal(chk.isValidBatch(far), o.check_poses(far))
+
+
+def test_terraces_exercise_the_deferral_path(maps, golden, checkers):
+    """Normal mode on piecewise-constant terrain: the corner-candidate shortcut of the warp stage must hand boxes with an
+    epsilon-mergeable earlier plane to the exact grouping stage (heightfield.cpp:1511-1556) -- assert that path runs."""
+    m = maps("terraces")
+    chk = checkers("yaml")
+    set_map(chk, m)
+    chk.setMode(0)
+    name, _, _, gen = [c for c in cases.POSE_CASES if c[0] == "terraces_low_yaml"][0]
+    poses = gen(m)
+    got = chk.isValidBatch(poses)
+    st = chk.stats()
+    assert st["last_queued_boxes"] > 0 and st["last_deferred"] > 0, st
+    assert np.array_equal(got, unpack(golden, name + "/mask", len(got)))
