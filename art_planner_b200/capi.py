@@ -36,7 +36,9 @@ class ArtpSamplerParams(C.Structure):
 
 class ArtpStats(C.Structure):
     _fields_ = [("poses_checked", C.c_uint64), ("poses_deferred", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("last_deferred", C.c_uint32), ("last_launches", C.c_uint32), ("last_queued_boxes", C.c_uint32)]
+                ("last_deferred", C.c_uint32), ("last_launches", C.c_uint32), ("last_queued_boxes", C.c_uint32),
+                ("last_queued_warp_stage", C.c_uint32), ("last_queued_reach_stage", C.c_uint32),
+                ("last_reach_plane_stage", C.c_uint32)]
 
 
 _lib = None
@@ -82,8 +84,11 @@ def load():
     lib.artp_compact_bits_device.argtypes = [vp, vp, sz, C.c_int64, vp, vp, vp]
     lib.artp_get_stats.argtypes = [vp, C.POINTER(ArtpStats)]
     lib.artp_set_mode.argtypes = [vp, i32]
+    lib.artp_poll_error.argtypes = [vp]
+    lib.artp_debug_set_group_capacity.argtypes = [vp, i32]
     lib.artp_set_timing.argtypes = [vp, i32]
     lib.artp_get_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.artp_get_last_stage_timing.argtypes = [vp, C.POINTER(C.c_float)]
     lib.artp_version.restype = C.c_char_p
     lib.artp_cost_weights_size.restype = C.c_size_t
     lib.artp_set_cost_weights.argtypes = [vp, vp, sz]

@@ -194,6 +194,14 @@ class StateValidityChecker:
     def setMode(self, mode: int) -> None:
         self._h.check(self._h.lib.artp_set_mode(self._h.h, int(mode)))
 
+    def pollError(self) -> None:
+        """Raise ArtpError(ARTP_E_LIMIT) if an asynchronous (device-buffer) call hit the plane-grouping overflow since the
+        last poll (the affected poses were reported invalid). Synchronise the stream first."""
+        self._h.check(self._h.lib.artp_poll_error(self._h.h))
+
+    def debugSetGroupCapacity(self, max_triangles: int) -> None:
+        self._h.check(self._h.lib.artp_debug_set_group_capacity(self._h.h, int(max_triangles)))
+
     def stats(self) -> dict:
         return self._h.stats()
 
@@ -206,6 +214,12 @@ class StateValidityChecker:
         ms = (C.c_float * 3)()
         self._h.check(self._h.lib.artp_get_last_timing(self._h.h, ms))
         return float(ms[0]), float(ms[1]), float(ms[2])
+
+    def lastStageTimesMs(self):
+        """(classify, warp stage, reach vertex scan, reach plane stage, plane grouping) ms of the most recent check call."""
+        ms = (C.c_float * 5)()
+        self._h.check(self._h.lib.artp_get_last_stage_timing(self._h.h, ms))
+        return tuple(float(x) for x in ms)
 
     @property
     def handle(self) -> _Handle:
@@ -261,7 +275,23 @@ class SE3FromSE2Sampler:
         return (states, rc) if want_cells else states
 
     def sampleUniform(self) -> np.ndarray:
-        return self.sampleUniformBatch(1)[0]
+        """One state, never NaN: in uniform mode a draw outside the map is redrawn from the next counter of the stream,
+        like samplePositionInMap's loop (sampler.cpp:46-50)."""
+        while True:
+            s = self.sampleUniformBatch(1)[0]
+            if not np.isnan(s[0]):
+                return s
+
+    def sampleUniformInside(self, n: int) -> np.ndarray:
+        """n states, none NaN, in draw order (rejected outside-map candidates of the uniform mode are redrawn)."""
+        out = []
+        have = 0
+        while have < n:
+            s = self.sampleUniformBatch(n - have)
+            s = s[~np.isnan(s[:, 0])]
+            out.append(s)
+            have += len(s)
+        return np.concatenate(out) if out else np.zeros((0, 7))
 
     def sampleValidBatch(self, n_draw: int, first=None, capacity=None, out=None):
         """Draw n_draw candidates on the device, check them, return (valid states in draw order, n_valid).

@@ -3,6 +3,7 @@
 // artp_set_map ~ setMap + updateHeightField (HeightMapBoxChecker::setHeightField,
 // art_planner/src/validity_checker/height_map_box_checker.cpp:38-54), artp_check_* ~ isValid / checkMotion.
 // No CPU fallback: every entry point fails with ARTP_E_CUDA if the device or the kernel image is unusable.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -17,6 +18,7 @@
 #include "../../include/artp.h"
 #include "artp_cnn.h"
 #include "artp_kernels.cuh"
+#include "artp_reach.cuh"
 #include "artp_sampler.cuh"
 
 namespace {
@@ -35,10 +37,14 @@ struct Handle {
   int pitch = 0;
   int rows = 0, cols = 0;
   bool has_map = false;
-  uint32_t* d_ctr = nullptr;        // [0] work counter, [1] defer count, [2] K2 overflow, [3] compaction total
-  uint32_t* d_defer = nullptr;      // deferred record list
+  // [0] warp-stage claim counter, [1] defer count, [2] reach-vertex claim counter, [3] warp-queue count,
+  // [4] reach-queue count, [5] plane-list count, [6] reach-plane claim counter, [7] scratch (sampler CDF validation)
+  uint32_t* d_ctr = nullptr;
+  uint32_t* d_defer = nullptr;      // deferred record list (bit 31: reach-box queue)
   size_t defer_cap = 0;
-  artp::BoxRec* d_recs = nullptr;   // stage-A -> stage-B box queue
+  artp::BoxRec* d_recs = nullptr;   // classify -> warp-stage box queue (torso boxes, reach boxes of unusual size)
+  artp::BoxRec* d_recs_f = nullptr; // classify -> thread-level reach-box queue
+  uint32_t* d_plane_list = nullptr; // reach boxes that survived the vertex scan
   size_t recs_cap = 0;
   uint32_t* d_block_counts = nullptr;
   size_t block_counts_cap = 0;
@@ -47,7 +53,8 @@ struct Handle {
   cudaStream_t stream = nullptr;    // internal compute stream for the host-buffer API
   cudaStream_t copy_stream = nullptr;   // H2D slices of the host-buffer API
   cudaEvent_t copy_ev[16] = {};
-  int k1_grid = 0, k2_grid = 0, k2_smem = 0, k2_tcap = 0;
+  int k1_grid = 0, k2_grid = 0, k2_smem = 0, k2_tcap = 0, f1_grid = 0, f2_grid = 0, reach_smem = 0;
+  CUtensorMap reach_tmap;           // 2-D tile map over the elevation_masked layer (reach-box zones)
   int k0_flags = 0;                 // tuning switch of the classify stage (env ARTP_K0_FLAGS: 2 = no vertex probes)
   int mode = 0;
   artp_cnn::State* cnn = nullptr;
@@ -63,7 +70,7 @@ struct Handle {
   size_t samp_scratch_cap = 0;
   uint8_t* h_small_out = nullptr;   // mapped pinned host bytes the latency-path kernel writes its verdicts to
   int timing = 0;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // classify | warp | reach vertex | reach plane | group
   bool ev_valid = false;
   bool deferred_unread = false;
   // Cross-stream ordering of the per-handle scratch: calls may come on different streams; every call that
@@ -240,14 +247,16 @@ __global__ void pack_bits_kernel(const uint8_t* __restrict__ valid, size_t n, ui
 constexpr size_t kChunkItems = 1u << 20;   // work items per internal launch round (bounds the box queue)
 
 int ensure_queues(Handle* h, size_t n_items, cudaStream_t s) {
+  (void)s;
   const size_t need = 5 * std::min(n_items, kChunkItems);
   if (h->recs_cap >= need) return ARTP_OK;
-  CU_TRY(h, cudaStreamSynchronize(s));
-  if (h->d_defer) CU_TRY(h, cudaFree(h->d_defer));
-  if (h->d_recs) CU_TRY(h, cudaFree(h->d_recs));
-  h->d_defer = nullptr; h->d_recs = nullptr;
+  CU_TRY(h, cudaDeviceSynchronize());   // rare (growth only): users on any stream must be done before the free
+  cudaFree(h->d_defer); cudaFree(h->d_recs); cudaFree(h->d_recs_f); cudaFree(h->d_plane_list);
+  h->d_defer = nullptr; h->d_recs = nullptr; h->d_recs_f = nullptr; h->d_plane_list = nullptr; h->recs_cap = 0;
   const size_t cap = std::max<size_t>(need, 1u << 16);
   CU_TRY(h, cudaMalloc(&h->d_recs, cap * sizeof(artp::BoxRec)));
+  CU_TRY(h, cudaMalloc(&h->d_recs_f, cap * sizeof(artp::BoxRec)));
+  CU_TRY(h, cudaMalloc(&h->d_plane_list, cap * sizeof(uint32_t)));
   CU_TRY(h, cudaMalloc(&h->d_defer, cap * sizeof(uint32_t)));
   h->recs_cap = cap; h->defer_cap = cap;
   return ARTP_OK;
@@ -255,7 +264,7 @@ int ensure_queues(Handle* h, size_t n_items, cudaStream_t s) {
 
 int ensure_stage(Handle* h, size_t bytes) {
   if (h->stage_cap >= bytes) return ARTP_OK;
-  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaDeviceSynchronize());
   if (h->d_stage) CU_TRY(h, cudaFree(h->d_stage));
   h->d_stage = nullptr;
   CU_TRY(h, cudaMalloc(&h->d_stage, bytes));
@@ -299,10 +308,17 @@ struct HostFeed {
   size_t slice_items;
 };
 
+// The claim counters of the consumer stages restart where the next slice's producers will append (the persistent
+// consumers of the previous slice overshoot their counters).
+__global__ void restart_claims_kernel(uint32_t* ctr) {
+  ctr[0] = ctr[3]; ctr[2] = ctr[4]; ctr[6] = ctr[5];
+}
+
 // Launch the pipeline for a prepared Work (items 0 .. w.n_items = the whole call) on stream s, in rounds of
-// kChunkItems work items (bounds the box queue). Within a round the classify (A) and warp (B) stages run slice by slice
-// -- the record queue and B's claim counter simply keep growing -- and the plane-grouping stage (C) runs ONCE over all
-// boxes deferred in the round (its sequential greedy has a fixed latency of tens of microseconds per launch).
+// kChunkItems work items (bounds the box queues). Within a round the stages run slice by slice -- classify (A), warp
+// stage (W: torso boxes), reach vertex scan (F1), reach plane stage (F2); the queues and claim counters simply keep
+// growing -- and the plane-grouping stage (C) runs ONCE over all boxes deferred in the round (its sequential greedy has
+// a fixed latency of tens of microseconds per launch).
 int run_items(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed = nullptr) {
   const size_t n_total = w.n_items;
   int rc = ensure_queues(h, n_total, s);
@@ -312,7 +328,7 @@ int run_items(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed = nu
   for (size_t base = 0; base < n_total; base += kChunkItems) {
     const size_t end = std::min(n_total, base + kChunkItems);
     const bool last_round = end == n_total;
-    CU_TRY(h, cudaMemsetAsync(h->d_ctr, 0, 4 * sizeof(uint32_t), s));
+    CU_TRY(h, cudaMemsetAsync(h->d_ctr, 0, 7 * sizeof(uint32_t), s));
     const size_t slice = (feed && feed->slice_items < end - base) ? feed->slice_items : (end - base);
     for (size_t lo = base; lo < end; lo += slice) {
       const size_t hi = std::min(end, lo + slice);
@@ -330,28 +346,45 @@ int run_items(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed = nu
       }
       w.item_base = (uint32_t)lo;
       w.n_items = (uint32_t)hi;
-      // B's claim counter restarts exactly at the records this slice's A will append (the previous B overshoots it)
-      if (lo != base) CU_TRY(h, cudaMemcpyAsync(h->d_ctr, h->d_ctr + 3, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+      if (lo != base) { restart_claims_kernel<<<1, 1, 0, s>>>(h->d_ctr); launches += 1; }
       if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[0], s));
-      artp::classify_items_kernel<<<(unsigned)((hi - lo + 127) / 128), 128, 0, s>>>(h->chk, w, h->d_recs, h->d_ctr + 3,
-                                                                                      (h->mode == 1 ? 1 : 0) | h->k0_flags);
+      artp::classify_items_kernel<<<(unsigned)((hi - lo + 127) / 128), 128, 0, s>>>(
+          h->chk, w, h->d_recs, h->d_recs_f, h->d_ctr + 3, h->d_ctr + 4, (h->mode == 1 ? 1 : 0) | h->k0_flags);
       CU_TRY(h, cudaGetLastError());
       if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[1], s));
       // small batches (the planner's one-state isValid calls): no more CTAs than there can be boxes
-      const unsigned grid_b = (unsigned)std::min<size_t>((size_t)h->k1_grid, (5 * (hi - lo) + artp::kWarpsPerCta - 1) / artp::kWarpsPerCta);
-      artp::box_items_warp_kernel<<<grid_b, artp::kWarpsPerCta * 32, 0, s>>>(h->chk, w, h->d_recs, h->d_ctr + 3, h->d_ctr,
+      const size_t nb = hi - lo;
+      const unsigned grid_w = (unsigned)std::min<size_t>((size_t)h->k1_grid, (5 * nb + artp::kWarpsPerCta - 1) / artp::kWarpsPerCta);
+      artp::box_items_warp_kernel<<<grid_w, artp::kWarpsPerCta * 32, 0, s>>>(h->chk, w, h->d_recs, h->d_ctr + 3, h->d_ctr,
                                                                                   h->d_ctr + 1, h->d_defer, h->mode == 1);
       CU_TRY(h, cudaGetLastError());
       if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[2], s));
+      if (h->chk.reach_tw) {
+        constexpr int kRT = artp::kReachWarpsPerCta * 32;
+        const unsigned grid_f1 = (unsigned)std::min<size_t>((size_t)h->f1_grid, (4 * nb + kRT - 1) / kRT);
+        artp::reach_vertex_kernel<<<grid_f1, kRT, h->reach_smem, s>>>(h->chk, h->reach_tmap, w, h->d_recs_f, h->d_ctr + 4, h->d_ctr + 2,
+                                                                        h->d_plane_list, h->d_ctr + 5);
+        CU_TRY(h, cudaGetLastError());
+        if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[3], s));
+        const unsigned grid_f2 = (unsigned)std::min<size_t>((size_t)h->f2_grid, (4 * nb + kRT - 1) / kRT);
+        artp::reach_plane_kernel<<<grid_f2, kRT, h->reach_smem, s>>>(h->chk, h->reach_tmap, w, h->d_recs_f, h->d_plane_list, h->d_ctr + 5,
+                                                                       h->d_ctr + 6, h->d_ctr + 1, h->d_defer);
+        CU_TRY(h, cudaGetLastError());
+        if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[4], s));
+        launches += 2;
+      } else if (h->timing && last) {
+        CU_TRY(h, cudaEventRecord(h->ev[3], s));
+        CU_TRY(h, cudaEventRecord(h->ev[4], s));
+      }
       launches += 2;
     }
     w.item_base = (uint32_t)base;
     w.n_items = (uint32_t)end;
     const unsigned grid_c = (unsigned)std::min<size_t>((size_t)h->k2_grid, 5 * (end - base));
-    artp::box_items_block_kernel<<<grid_c, artp::kBlockStageThreads, h->k2_smem, s>>>(h->chk, w, h->d_recs, h->d_ctr + 1, h->d_defer,
-                                                                      h->k2_tcap, h->d_err);
+    artp::box_items_block_kernel<<<grid_c, artp::kBlockStageThreads, h->k2_smem, s>>>(h->chk, w, h->d_recs, h->d_recs_f, h->d_ctr + 1,
+                                                                      h->d_defer, h->k2_tcap, h->d_err);
     CU_TRY(h, cudaGetLastError());
-    if (h->timing && last_round) { CU_TRY(h, cudaEventRecord(h->ev[3], s)); h->ev_valid = true; }
+    if (h->timing && last_round) { CU_TRY(h, cudaEventRecord(h->ev[5], s)); h->ev_valid = true; }
     launches += 1;
   }
   h->stats.kernel_launches += launches;
@@ -422,6 +455,7 @@ int artp_create(const artp_params* params, artp_handle** out) {
                                                          artp::kWarpsPerCta * 32, 0)) != cudaSuccess)
     return fail("occupancy", e);
   h->k1_grid = h->sm_count * std::max(per_sm, 1);
+
   if (const char* kf = std::getenv("ARTP_K0_FLAGS")) h->k0_flags = std::atoi(kf) & 2;
   h->cnn = artp_cnn::create(h->device, h->sm_count);
   // checker constants (float casts as the reference's ctor/Pose3FromXYZ arguments make them)
@@ -446,12 +480,12 @@ void artp_destroy(artp_handle* hh) {
   for (int i = 0; i < kCopyEvents; ++i) if (h->copy_ev[i]) cudaEventDestroy(h->copy_ev[i]);
   for (int k = 0; k < 2; ++k) for (int l = 0; l <= artp::kMaxLevel; ++l) { cudaFree(h->d_T[k][l]); cudaFree(h->d_NF[k][l]); }
   cudaFree(h->d_H[0]); cudaFree(h->d_H[1]); cudaFree(h->d_ctr); cudaFree(h->d_defer); cudaFree(h->d_stage);
-  cudaFree(h->d_block_counts); cudaFree(h->d_recs); cudaFree(h->d_samp_layers); cudaFree(h->d_samp_scratch);
+  cudaFree(h->d_block_counts); cudaFree(h->d_recs); cudaFree(h->d_recs_f); cudaFree(h->d_plane_list); cudaFree(h->d_samp_layers); cudaFree(h->d_samp_scratch);
   if (h->h_small_out) cudaFreeHost(h->h_small_out);
   if (h->h_err) cudaFreeHost(h->h_err);
   for (int g = 0; g < 2; ++g) if (h->chain_ev[g]) cudaEventDestroy(h->chain_ev[g]);
   artp_cnn::destroy(h->cnn);
-  for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
 }
 
@@ -468,7 +502,7 @@ int artp_set_timing(artp_handle* hh, int enable) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   std::lock_guard<std::recursive_mutex> lk(h->mtx);
   CU_TRY(h, cudaSetDevice(h->device));
-  if (enable && !h->ev[0]) for (int i = 0; i < 4; ++i) CU_TRY(h, cudaEventCreate(&h->ev[i]));
+  if (enable && !h->ev[0]) for (int i = 0; i < 6; ++i) CU_TRY(h, cudaEventCreate(&h->ev[i]));
   h->timing = enable ? 1 : 0;
   h->ev_valid = false;
   return ARTP_OK;
@@ -480,8 +514,36 @@ int artp_get_last_timing(artp_handle* hh, float* ms3) {
   std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (!h->timing || !h->ev_valid) { h->err = "timing not enabled or no call recorded"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
-  CU_TRY(h, cudaEventSynchronize(h->ev[3]));
-  for (int i = 0; i < 3; ++i) CU_TRY(h, cudaEventElapsedTime(ms3 + i, h->ev[i], h->ev[i + 1]));
+  CU_TRY(h, cudaEventSynchronize(h->ev[5]));
+  CU_TRY(h, cudaEventElapsedTime(ms3 + 0, h->ev[0], h->ev[1]));   // classify
+  CU_TRY(h, cudaEventElapsedTime(ms3 + 1, h->ev[1], h->ev[4]));   // box stages: warp + reach vertex + reach plane
+  CU_TRY(h, cudaEventElapsedTime(ms3 + 2, h->ev[4], h->ev[5]));   // plane grouping
+  return ARTP_OK;
+}
+
+int artp_get_last_stage_timing(artp_handle* hh, float* ms5) {
+  if (!hh || !ms5) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
+  if (!h->timing || !h->ev_valid) { h->err = "timing not enabled or no call recorded"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaEventSynchronize(h->ev[5]));
+  for (int i = 0; i < 5; ++i) CU_TRY(h, cudaEventElapsedTime(ms5 + i, h->ev[i], h->ev[i + 1]));
+  return ARTP_OK;
+}
+
+int artp_poll_error(artp_handle* hh) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
+  return take_sticky_error(h);
+}
+
+int artp_debug_set_group_capacity(artp_handle* hh, int max_triangles) {
+  if (!hh || max_triangles < 0) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
+  h->tcap_override = max_triangles;   // takes effect at the next artp_set_map
   return ARTP_OK;
 }
 
@@ -490,10 +552,13 @@ int artp_get_stats(artp_handle* hh, artp_stats* out) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   std::lock_guard<std::recursive_mutex> lk(h->mtx);
   CU_TRY(h, cudaSetDevice(h->device));
-  uint32_t ctr[4] = {0, 0, 0, 0};
+  uint32_t ctr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   CU_TRY(h, cudaMemcpy(ctr, h->d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost));   // synchronises the device
   h->stats.last_deferred = ctr[1];
-  h->stats.last_queued_boxes = ctr[3];
+  h->stats.last_queued_boxes = ctr[3] + ctr[4];
+  h->stats.last_queued_warp_stage = ctr[3];
+  h->stats.last_queued_reach_stage = ctr[4];
+  h->stats.last_reach_plane_stage = ctr[5];
   if (h->deferred_unread) { h->stats.poses_deferred += ctr[1]; h->deferred_unread = false; }
   *out = h->stats;
   return take_sticky_error(h);
@@ -586,6 +651,43 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
   }
   h->chk.Lx = Lx; h->chk.Ly = Ly; h->chk.cx = cx; h->chk.cy = cy;
   h->chk.cell_margin = 0.02f + 2e-6f * (float)std::max(rows, cols);
+  // Thread-level reach-box stages: one TMA tile per box. A zone spans at most ceil(2 r / s) + 3 vertices per axis
+  // (r = box half-diagonal); boxes whose zone is larger (never for the bound itself) fall back to the warp stage.
+  {
+    const float* sd = h->chk.side[1];
+    const double r = 0.5 * std::sqrt((double)sd[0] * sd[0] + (double)sd[1] * sd[1] + (double)sd[2] * sd[2]);
+    const int tw = ((int)std::ceil(2.0 * r * f.iW) + 3 + 3) & ~3, th = (int)std::ceil(2.0 * r * f.iD) + 3;
+    const uint32_t bytes = (uint32_t)tw * th * 4, stride = (bytes + 127u) & ~127u;
+    const int smem = artp::kReachWarpsPerCta * 32 * (int)stride + 128;
+    h->chk.reach_tw = 0; h->chk.reach_th = 0; h->chk.reach_tile_bytes = 0; h->chk.reach_tile_stride = 0;
+    if (tw <= 256 && th <= 256 && smem <= 200 * 1024) {
+      typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+        h->err = "cuTensorMapEncodeTiled not available from the driver"; return ARTP_E_CUDA;
+      }
+      const cuuint64_t gdim[2] = {(cuuint64_t)pitch, (cuuint64_t)cols};
+      const cuuint64_t gstr[1] = {(cuuint64_t)pitch * sizeof(float)};
+      const cuuint32_t box[2] = {(cuuint32_t)tw, (cuuint32_t)th};
+      const cuuint32_t one[2] = {1, 1};
+      const CUresult cr = reinterpret_cast<EncodeTiledFn>(fn)(&h->reach_tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->d_H[1], gdim, gstr,
+                                                              box, one, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")"; return ARTP_E_CUDA; }
+      CU_TRY(h, cudaFuncSetAttribute(artp::reach_vertex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CU_TRY(h, cudaFuncSetAttribute(artp::reach_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      int ps = 0;
+      CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, artp::reach_vertex_kernel, artp::kReachWarpsPerCta * 32, smem));
+      h->f1_grid = h->sm_count * std::max(ps, 1);
+      CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, artp::reach_plane_kernel, artp::kReachWarpsPerCta * 32, smem));
+      h->f2_grid = h->sm_count * std::max(ps, 1);
+      h->reach_smem = smem;
+      h->chk.reach_tw = tw; h->chk.reach_th = th; h->chk.reach_tile_bytes = bytes; h->chk.reach_tile_stride = stride;
+    }
+  }
   h->has_map = true;
   h->has_sampler = false;      // its layers belong to the previous map
   h->has_device_normals = false;
@@ -851,8 +953,8 @@ int artp_check_edge_interiors(artp_handle* hh, const double* s1, const double* s
   Handle* h = reinterpret_cast<Handle*>(hh);
   std::vector<uint32_t> off;
   size_t total = 0, sb_al = 0, ob_al = 0, pb_al = 0;
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);   // held across stage -> launch -> D2H
   {
-    std::lock_guard<std::recursive_mutex> lk(h->mtx);
     if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
     if (n == 0) return ARTP_OK;
     if (!s1 || !s2 || !valid_prefix) { h->err = "null buffer"; return ARTP_E_INVALID; }
@@ -877,7 +979,9 @@ int artp_check_edge_interiors(artp_handle* hh, const double* s1, const double* s
     ob_al = ((n + 1) * sizeof(uint32_t) + 255) & ~(size_t)255;
     pb_al = (n * sizeof(int32_t) + 255) & ~(size_t)255;
     CU_TRY(h, cudaSetDevice(h->device));
-    int rc = ensure_stage(h, 2 * sb_al + ob_al + pb_al + total + 256);
+    int rc = chain_begin(h, 0, h->stream);
+    if (rc) return rc;
+    rc = ensure_stage(h, 2 * sb_al + ob_al + pb_al + total + 256);
     if (rc) return rc;
     char* base = (char*)h->d_stage;
     CU_TRY(h, cudaMemcpyAsync(base, s1, sb, cudaMemcpyHostToDevice, h->stream));
@@ -890,10 +994,10 @@ int artp_check_edge_interiors(artp_handle* hh, const double* s1, const double* s
                                             (const uint32_t*)(base + 2 * sb_al), total,
                                             (uint8_t*)(base + 2 * sb_al + ob_al + pb_al), d_prefix, h->stream);
   if (rc) return rc;
-  std::lock_guard<std::recursive_mutex> lk(h->mtx);
   CU_TRY(h, cudaMemcpyAsync(valid_prefix, d_prefix, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));   // `off` must outlive its H2D copy: it does, we synchronise here
-  return ARTP_OK;
+  h->chain_busy[0] = false;
+  return take_sticky_error(h);
 }
 
 int artp_path_length_cost_device(artp_handle* hh, const double* d_s1, const double* d_s2, size_t n, double* d_cost,
@@ -916,32 +1020,34 @@ int artp_path_length_cost(artp_handle* hh, const double* s1, const double* s2, s
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
   const size_t sb = n * 7 * sizeof(double), sb_al = (sb + 255) & ~(size_t)255;
-  {
-    std::lock_guard<std::recursive_mutex> lk(h->mtx);
-    if (n == 0) return ARTP_OK;
-    if (!s1 || !s2 || !cost) { h->err = "null buffer"; return ARTP_E_INVALID; }
-    CU_TRY(h, cudaSetDevice(h->device));
-    int rc = ensure_stage(h, 2 * sb_al + n * sizeof(double));
-    if (rc) return rc;
-    CU_TRY(h, cudaMemcpyAsync(h->d_stage, s1, sb, cudaMemcpyHostToDevice, h->stream));
-    CU_TRY(h, cudaMemcpyAsync((char*)h->d_stage + sb_al, s2, sb, cudaMemcpyHostToDevice, h->stream));
-  }
-  double* d_cost = (double*)((char*)h->d_stage + 2 * sb_al);
-  int rc = artp_path_length_cost_device(hh, (const double*)h->d_stage, (const double*)((char*)h->d_stage + sb_al), n, d_cost,
-                                        h->stream);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);   // held across stage -> launch -> D2H
+  if (n == 0) return ARTP_OK;
+  if (!s1 || !s2 || !cost) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  int rc = chain_begin(h, 0, h->stream);
   if (rc) return rc;
-  std::lock_guard<std::recursive_mutex> lk(h->mtx);
+  rc = ensure_stage(h, 2 * sb_al + n * sizeof(double));
+  if (rc) return rc;
+  CU_TRY(h, cudaMemcpyAsync(h->d_stage, s1, sb, cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, cudaMemcpyAsync((char*)h->d_stage + sb_al, s2, sb, cudaMemcpyHostToDevice, h->stream));
+  double* d_cost = (double*)((char*)h->d_stage + 2 * sb_al);
+  rc = artp_path_length_cost_device(hh, (const double*)h->d_stage, (const double*)((char*)h->d_stage + sb_al), n, d_cost,
+                                    h->stream);
+  if (rc) return rc;
   CU_TRY(h, cudaMemcpyAsync(cost, d_cost, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->chain_busy[0] = false;
   return ARTP_OK;
 }
 
 static int compact_valid_impl(Handle* h, const uint8_t* d_valid, size_t n, int64_t base, int64_t* d_indices,
                               uint32_t* d_count, cudaStream_t s, bool bits = false) {
   if (n == 0) { CU_TRY(h, cudaMemsetAsync(d_count, 0, sizeof(uint32_t), s)); return ARTP_OK; }
+  ChainScope cs(h, 1, s);
+  if (cs.rc) return cs.rc;
   const size_t nb = (n + kCompactBlock - 1) / kCompactBlock;
   if (h->block_counts_cap < nb) {
-    CU_TRY(h, cudaStreamSynchronize(s));
+    CU_TRY(h, cudaDeviceSynchronize());   // every stream that may still read the old buffer
     cudaFree(h->d_block_counts);
     h->d_block_counts = nullptr;
     CU_TRY(h, cudaMalloc(&h->d_block_counts, nb * sizeof(uint32_t)));
@@ -1019,7 +1125,9 @@ int artp_estimate_normals(artp_handle* hh, double estimation_radius, float* norm
   if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
   if (!(estimation_radius >= 0.0)) { h->err = "estimation_radius < 0"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
-  int rc = ensure_sampler_layers(h);
+  int rc = chain_begin(h, 0, h->stream);
+  if (rc) return rc;
+  rc = ensure_sampler_layers(h);
   if (rc) return rc;
   const size_t ncell = (size_t)h->rows * h->cols;
   const double res = h->chk.Lx / h->rows;
@@ -1047,7 +1155,9 @@ int artp_compute_sample_cdf(artp_handle* hh, const float* sample_probability, fl
   if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
   if (!sample_probability) { h->err = "null buffer"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
-  int rc = ensure_sampler_layers(h);
+  int rc = chain_begin(h, 0, h->stream);
+  if (rc) return rc;
+  rc = ensure_sampler_layers(h);
   if (rc) return rc;
   const size_t ncell = (size_t)h->rows * h->cols;
   rc = ensure_stage(h, ncell * sizeof(float));
@@ -1095,7 +1205,9 @@ int artp_set_sampler(artp_handle* hh, const artp_sampler_params* sp, const float
   CU_TRY(h, cudaSetDevice(h->device));
   const size_t ncell = (size_t)h->rows * h->cols;
   {
-    int rc = ensure_sampler_layers(h);
+    int rc = chain_begin(h, 0, h->stream);
+    if (rc) return rc;
+    rc = ensure_sampler_layers(h);
     if (rc) return rc;
   }
   float* base = h->d_samp_layers;
@@ -1124,13 +1236,13 @@ int artp_set_sampler(artp_handle* hh, const artp_sampler_params* sp, const float
     }
     m.cum_prob = base + 4 * ncell; m.cum_row = base + 5 * ncell;
     // the binary searches need monotone (or all-NaN) CDF rows: refuse anything else
-    CU_TRY(h, cudaMemsetAsync(h->d_ctr + 3, 0, sizeof(uint32_t), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->d_ctr + 7, 0, sizeof(uint32_t), h->stream));
     artp::validate_cdf_kernel<<<(h->rows + 127) / 128, 128, 0, h->stream>>>(m.cum_prob, h->rows, h->cols, (size_t)h->rows, 1,
-                                                                             h->d_ctr + 3);
-    artp::validate_cdf_kernel<<<1, 32, 0, h->stream>>>(m.cum_row, 1, h->rows, 1, 0, h->d_ctr + 3);
+                                                                             h->d_ctr + 7);
+    artp::validate_cdf_kernel<<<1, 32, 0, h->stream>>>(m.cum_row, 1, h->rows, 1, 0, h->d_ctr + 7);
     CU_TRY(h, cudaGetLastError());
     uint32_t bad = 0;
-    CU_TRY(h, cudaMemcpyAsync(&bad, h->d_ctr + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(&bad, h->d_ctr + 7, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     h->stats.kernel_launches += 2;
     if (bad) { h->err = "cum_prob layers are not cumulative distributions (rows must be non-decreasing or all NaN)"; return ARTP_E_INVALID; }
@@ -1158,7 +1270,9 @@ int artp_sampler_uniforms(artp_handle* hh, uint64_t seed, uint64_t first_sample,
   if (n == 0) return ARTP_OK;
   if (!u) { h->err = "null buffer"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
-  int rc = ensure_stage(h, n * 6 * sizeof(double));
+  int rc = chain_begin(h, 0, h->stream);
+  if (rc) return rc;
+  rc = ensure_stage(h, n * 6 * sizeof(double));
   if (rc) return rc;
   artp::sampler_uniforms_kernel<<<grid_for(h, n, 256), 256, 0, h->stream>>>(seed, first_sample, n, (double*)h->d_stage);
   CU_TRY(h, cudaGetLastError());
@@ -1191,22 +1305,21 @@ int artp_sample_states(artp_handle* hh, const double* u, uint64_t seed, uint64_t
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
   const size_t ub = (n * 6 * sizeof(double) + 255) & ~(size_t)255, sb = (n * 7 * sizeof(double) + 255) & ~(size_t)255;
-  {
-    std::lock_guard<std::recursive_mutex> lk(h->mtx);
-    int rc = sampler_ready(h);
-    if (rc) return rc;
-    if (n == 0) return ARTP_OK;
-    if (!states) { h->err = "null buffer"; return ARTP_E_INVALID; }
-    CU_TRY(h, cudaSetDevice(h->device));
-    rc = ensure_stage(h, ub + sb + n * 2 * sizeof(int32_t));
-    if (rc) return rc;
-    if (u) CU_TRY(h, cudaMemcpyAsync(h->d_stage, u, n * 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  }
-  char* base = (char*)h->d_stage;
-  int rc = artp_sample_states_device(hh, u ? (const double*)base : nullptr, seed, first_sample, n, (double*)(base + ub),
-                                     rowcol ? (int32_t*)(base + ub + sb) : nullptr, h->stream);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);   // held across stage -> launch -> D2H
+  int rc = sampler_ready(h);
   if (rc) return rc;
-  std::lock_guard<std::recursive_mutex> lk(h->mtx);
+  if (n == 0) return ARTP_OK;
+  if (!states) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  rc = chain_begin(h, 0, h->stream);
+  if (rc) return rc;
+  rc = ensure_stage(h, ub + sb + n * 2 * sizeof(int32_t));
+  if (rc) return rc;
+  if (u) CU_TRY(h, cudaMemcpyAsync(h->d_stage, u, n * 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  char* base = (char*)h->d_stage;
+  rc = artp_sample_states_device(hh, u ? (const double*)base : nullptr, seed, first_sample, n, (double*)(base + ub),
+                                 rowcol ? (int32_t*)(base + ub + sb) : nullptr, h->stream);
+  if (rc) return rc;
   CU_TRY(h, cudaMemcpyAsync(states, base + ub, n * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (rowcol) CU_TRY(h, cudaMemcpyAsync(rowcol, base + ub + sb, n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1245,12 +1358,14 @@ int artp_sample_valid_device(artp_handle* hh, uint64_t seed, uint64_t first_samp
   cudaStream_t s = (cudaStream_t)stream;
   CU_TRY(h, cudaMemsetAsync(d_count, 0, sizeof(uint32_t), s));
   if (n_draw == 0) return ARTP_OK;
+  ChainScope cs(h, 0, s);
+  if (cs.rc) return cs.rc;
   const size_t chunk = std::min(n_draw, kSampleChunk);
   // scratch: states f64 | states f32 | indices | valid | chunk count
   const size_t o_f32 = chunk * 7 * sizeof(double), o_idx = o_f32 + ((chunk * 7 * sizeof(float) + 255) & ~(size_t)255),
                o_val = o_idx + chunk * sizeof(int64_t), o_cnt = o_val + ((chunk + 255) & ~(size_t)255), total = o_cnt + 256;
   if (h->samp_scratch_cap < total) {
-    CU_TRY(h, cudaStreamSynchronize(s));
+    CU_TRY(h, cudaDeviceSynchronize());
     cudaFree(h->d_samp_scratch);
     h->d_samp_scratch = nullptr; h->samp_scratch_cap = 0;
     CU_TRY(h, cudaMalloc(&h->d_samp_scratch, total));
@@ -1296,19 +1411,18 @@ int artp_sample_valid(artp_handle* hh, uint64_t seed, uint64_t first_sample, siz
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
   const size_t cap = std::min(capacity, n_draw);
-  {
-    std::lock_guard<std::recursive_mutex> lk(h->mtx);
-    int rc = sampler_ready(h);
-    if (rc) return rc;
-    if (!n_valid || (cap && !states)) { h->err = "null buffer"; return ARTP_E_INVALID; }
-    CU_TRY(h, cudaSetDevice(h->device));
-    rc = ensure_stage(h, cap * 7 * sizeof(double) + 256);
-    if (rc) return rc;
-  }
-  uint32_t* d_count = (uint32_t*)((char*)h->d_stage + cap * 7 * sizeof(double));
-  int rc = artp_sample_valid_device(hh, seed, first_sample, n_draw, (double*)h->d_stage, cap, d_count, h->stream);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);   // held across stage -> launch -> D2H
+  int rc = sampler_ready(h);
   if (rc) return rc;
-  std::lock_guard<std::recursive_mutex> lk(h->mtx);
+  if (!n_valid || (cap && !states)) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  rc = chain_begin(h, 0, h->stream);
+  if (rc) return rc;
+  rc = ensure_stage(h, cap * 7 * sizeof(double) + 256);
+  if (rc) return rc;
+  uint32_t* d_count = (uint32_t*)((char*)h->d_stage + cap * 7 * sizeof(double));
+  rc = artp_sample_valid_device(hh, seed, first_sample, n_draw, (double*)h->d_stage, cap, d_count, h->stream);
+  if (rc) return rc;
   uint32_t cnt = 0;
   CU_TRY(h, cudaMemcpyAsync(&cnt, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1356,18 +1470,17 @@ int artp_motion_cost(artp_handle* hh, const float* edges, size_t n, float* cost3
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (n == 0) return ARTP_OK;
   const size_t in_b = n * 6 * sizeof(float), in_al = (in_b + 255) & ~(size_t)255;
-  {
-    std::lock_guard<std::recursive_mutex> lk(h->mtx);
-    if (!edges || !cost3) { h->err = "null buffer"; return ARTP_E_INVALID; }
-    CU_TRY(h, cudaSetDevice(h->device));
-    int rc = ensure_stage(h, in_al + n * 3 * sizeof(float));
-    if (rc) return rc;
-    CU_TRY(h, cudaMemcpyAsync(h->d_stage, edges, in_b, cudaMemcpyHostToDevice, h->stream));
-  }
-  float* d_cost = (float*)((char*)h->d_stage + in_al);
-  int rc = artp_motion_cost_device(hh, (const float*)h->d_stage, n, d_cost, h->stream);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);   // held across stage -> launch -> D2H
+  if (!edges || !cost3) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  int rc = chain_begin(h, 0, h->stream);
   if (rc) return rc;
-  std::lock_guard<std::recursive_mutex> lk(h->mtx);
+  rc = ensure_stage(h, in_al + n * 3 * sizeof(float));
+  if (rc) return rc;
+  CU_TRY(h, cudaMemcpyAsync(h->d_stage, edges, in_b, cudaMemcpyHostToDevice, h->stream));
+  float* d_cost = (float*)((char*)h->d_stage + in_al);
+  rc = artp_motion_cost_device(hh, (const float*)h->d_stage, n, d_cost, h->stream);
+  if (rc) return rc;
   CU_TRY(h, cudaMemcpyAsync(cost3, d_cost, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   return ARTP_OK;
@@ -1379,7 +1492,9 @@ int artp_combine_cost(artp_handle* hh, const float* cost3, size_t n, double* cos
   const float we = h->p.cost_w_energy, wt = h->p.cost_w_time, wr = h->p.cost_w_risk;
   for (size_t i = 0; i < n; ++i) {
     const float ce = cost3[3 * i], ct = cost3[3 * i + 1], cr = cost3[3 * i + 2];
-    cost[i] = (double)(ce * we + ct * wt + cr * wr);                 // getCost: float arithmetic, returned as double
+    // getCost: getEnergy/getTime/getRisk return double (motion_cost_objective.h:30-46), so the weighted sum is evaluated
+    // in double on exact float products
+    cost[i] = (double)ce * (double)we + (double)ct * (double)wt + (double)cr * (double)wr;
     feasible[i] = (double)cr <= (double)h->p.risk_threshold ? 1 : 0;   // isFeasible (getRisk returns double)
   }
   return ARTP_OK;

@@ -230,6 +230,18 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
   const uint32_t magicC = magic_for(nCX);
   if (allFinite) {
     // every colliding vertex belongs to some kept triangle (all finite, >= 1 cell)
+    if (nV > 128) {
+      // Probe pass: one vertex per lane on an 8 x 4 lattice over the box footprint (a hit anywhere in the zone is the
+      // reference's answer, heightfield.cpp:1344-1441) -- finds most intersecting torso boxes in one step instead of
+      // the row-by-row scan reaching them.
+      const float u0 = (((float)(lane & 7) + 0.5f) * 0.25f - 1.0f) * (0.5f * b.side[0]);
+      const float u1 = (((float)(lane >> 3) + 0.5f) * 0.5f - 1.0f) * (0.5f * b.side[1]);
+      const float qx = b.P[0] + u0 * b.R1[0] + u1 * b.R1[1], qz = b.P[2] + u0 * b.R1[6] + u1 * b.R1[7];
+      const int vx = min(max(__float2int_rn(qx * f.iW), b.x0), b.x1), vz = min(max(__float2int_rn(qz * f.iD), b.z0), b.z1);
+      const float h = __ldg(f.H + (size_t)vz * f.pitch + vx);
+      const bool hit = h > b.minB && vertex_inside(b, vx * f.sW, h, vz * f.sD);
+      if (__any_sync(kFull, hit)) return R_HIT;
+    }
     for (int t0 = 0; t0 < nV; t0 += 64) {
       bool hit = false;
 #pragma unroll
@@ -455,7 +467,8 @@ __device__ __forceinline__ void rec_to_ctx(const Checker& c, const BoxRec& r, Bo
 // then complete), kBoxOutside when the box centre is outside the map (the caller applies the outside-map rule).
 constexpr int kBoxOutside = -2;
 __device__ __forceinline__ int classify_box(const Checker& c, const float R[9], const float R1[9], const float t[3], int k,
-                                            int force_all, bool probe, BoxCtx& b, uint32_t& fl) {
+                                            int force_all, int probe /* bit 0: reach boxes, bit 1: torso */, BoxCtx& b,
+                                            uint32_t& fl) {
   const Field& g = c.f[0];      // both layers share the map geometry
   const bool foot = k > 0;
   const int fk = k - 1;
@@ -525,7 +538,7 @@ __device__ __forceinline__ int classify_box(const Checker& c, const float R[9], 
       const bool allFinite = nf == 0;
       r = zone_early_out(b, mx, mn, allFinite);
       if (allFinite) fl |= REC_ALLFINITE;
-      if (r == -1 && allFinite && nX >= 2 && nZ >= 2 && probe) {
+      if (r == -1 && allFinite && nX >= 2 && nZ >= 2 && (probe & (foot ? 1 : 2))) {
         // Vertex probes. In an all-finite zone every vertex with h > minB belongs to a kept triangle, and the
         // collider returns 1 as soon as ANY such vertex lies inside the box (heightfield.cpp:1344-1441), so a
         // hit found here is exactly the reference's answer; a miss decides nothing and the box is queued.
@@ -557,16 +570,18 @@ __device__ __forceinline__ int classify_box(const Checker& c, const float R[9], 
 // Stage A: one thread per work item.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 8)
-classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs, uint32_t* __restrict__ rec_count,
-                      int flags) {
-  const int force_all = flags & 1;      // every in-map box goes to the later stages (artp_set_mode 1)
-  const bool probe = !(flags & 2);      // vertex probes (tuning switch ARTP_K0_FLAGS=2 turns them off)
+classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs_w, BoxRec* __restrict__ recs_f,
+                      uint32_t* __restrict__ count_w, uint32_t* __restrict__ count_f, int flags) {
+  const int force_all = flags & 1;      // every in-map box goes to the grouping stage (artp_set_mode 1)
+  // Vertex probes here only for reach boxes (one cell, most lanes busy); an undecided torso is rare (a few lanes of a
+  // warp) and its probes run lane-parallel at the head of the warp stage instead. ARTP_K0_FLAGS=2 turns probes off.
+  const int probe = (flags & 2) ? 0 : 1;
   const uint32_t item = w.item_base + blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = item < w.n_items;
   const int lane = threadIdx.x & 31;
   int result = 1;                 // 1 valid so far, 0 invalid
-  int n_und = 0;                  // undecided boxes of this item
-  BoxCtx ub[5];                   // their contexts (R1 shared -> stored once below)
+  int n_w = 0, n_f = 0;           // undecided boxes of this item for the warp stage / the thread-level reach stages
+  BoxCtx ub[5];                   // their contexts: warp-stage boxes from the front, reach-stage boxes from the back
   uint32_t uflags[5];
   float R1[9];
   uint32_t slot = 0;
@@ -591,37 +606,48 @@ classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs, 
         if (foot && c.unknown_untraversable) result = 0;
         continue;
       }
-      if (r == -1) { ub[n_und] = b; uflags[n_und] = fl; ++n_und; }
+      if (r == -1) {
+        // reach boxes whose table-reduced zone fits the TMA tile take the thread-level stages
+        const bool thread_path = foot && !(fl & REC_NEEDS_REDUCE) && (b.x1 - b.x0) + 3 < c.reach_tw && (b.z1 - b.z0) < c.reach_th;   // tile origin = x0 & ~3
+        const int q = thread_path ? 4 - n_f++ : n_w++;
+        ub[q] = b; uflags[q] = fl;
+      }
       else if (!foot) { if (r == R_HIT) result = 0; }      // torso must be free
       else { if (r == R_FREE) result = 0; }                // every reach box must touch
     }
-    if (!result) n_und = 0;
-    // provisional result; stages B/C clear it if an undecided box fails
+    if (!result) { n_w = 0; n_f = 0; }
+    // provisional result; the later stages clear it if an undecided box fails
     if (w.edge_mode) { if (!result) w.valid[slot] = 0; }
     else w.valid[slot] = (uint8_t)result;
   }
-  // queue the undecided boxes: one atomic per warp (inclusive scan of the per-lane counts)
-  int incl = n_und;
+  // queue the undecided boxes: one atomic per warp and queue (inclusive scan of the per-lane counts)
+  int incl_w = n_w, incl_f = n_f;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const int y = __shfl_up_sync(kFull, incl, o);
-    if (lane >= o) incl += y;
+    const int yw = __shfl_up_sync(kFull, incl_w, o), yf = __shfl_up_sync(kFull, incl_f, o);
+    if (lane >= o) { incl_w += yw; incl_f += yf; }
   }
-  const int total = __shfl_sync(kFull, incl, 31);
-  if (total == 0) return;
-  uint32_t basei = 0;
-  if (lane == 31) basei = atomicAdd(rec_count, (uint32_t)total);
-  basei = __shfl_sync(kFull, basei, 31) + (uint32_t)(incl - n_und);
+  const int total_w = __shfl_sync(kFull, incl_w, 31), total_f = __shfl_sync(kFull, incl_f, 31);
+  if (total_w == 0 && total_f == 0) return;
+  uint32_t base_w = 0, base_f = 0;
+  if (lane == 31) {
+    if (total_w) base_w = atomicAdd(count_w, (uint32_t)total_w);
+    if (total_f) base_f = atomicAdd(count_f, (uint32_t)total_f);
+  }
+  base_w = __shfl_sync(kFull, base_w, 31) + (uint32_t)(incl_w - n_w);
+  base_f = __shfl_sync(kFull, base_f, 31) + (uint32_t)(incl_f - n_f);
 #pragma unroll 1
-  for (int q = 0; q < n_und; ++q) {
-    BoxRec& o = recs[basei + q];
-    const BoxCtx& b = ub[q];
+  for (int q = 0; q < n_w + n_f; ++q) {
+    const bool fq = q >= n_w;
+    const int src = fq ? 4 - (q - n_w) : q;
+    BoxRec& o = fq ? recs_f[base_f + (q - n_w)] : recs_w[base_w + q];
+    const BoxCtx& b = ub[src];
 #pragma unroll
     for (int i = 0; i < 9; ++i) o.R1[i] = R1[i];
     o.P[0] = b.P[0]; o.P[1] = b.P[1]; o.P[2] = b.P[2];
     o.minB = b.minB; o.maxB = b.maxB;
     o.x0 = b.x0; o.x1 = b.x1; o.z0 = b.z0; o.z1 = b.z1;
-    o.item = item; o.flags = uflags[q];
+    o.item = item; o.flags = uflags[src];
   }
 }
 
@@ -841,7 +867,7 @@ groups_done:
 
 constexpr int kBlockStageThreads = 256;   // threads per deferred box in the grouping stage
 __global__ void __launch_bounds__(kBlockStageThreads)
-box_items_block_kernel(const Checker c, const Work w, const BoxRec* __restrict__ recs,
+box_items_block_kernel(const Checker c, const Work w, const BoxRec* __restrict__ recs, const BoxRec* __restrict__ recs_f,
                        const uint32_t* __restrict__ defer_count, const uint32_t* __restrict__ defer_list, int T_cap,
                        uint32_t* __restrict__ overflow) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -854,7 +880,8 @@ box_items_block_kernel(const Checker c, const Work w, const BoxRec* __restrict__
   sh.state = reinterpret_cast<uint8_t*>(smem_raw + (size_t)T_cap * 20);
   const uint32_t count = *defer_count;
   for (uint32_t q = blockIdx.x; q < count; q += gridDim.x) {
-    const BoxRec r = recs[defer_list[q]];
+    const uint32_t e = defer_list[q];     // bit 31: record of the reach-box queue
+    const BoxRec r = (e & 0x80000000u) ? recs_f[e & 0x7fffffffu] : recs[e];
     const uint32_t slot = item_slot(w, r.item);
     const bool foot = (r.flags & 7) != 0;
     BoxCtx b;
@@ -921,7 +948,7 @@ pose_small_kernel(const Checker c, const SmallBatch sb, uint8_t* __restrict__ ou
     for (int j = 0; j < 3; ++j) { R1[j] = -Rb[j]; R1[3 + j] = Rb[6 + j]; R1[6 + j] = Rb[3 + j]; }
     BoxCtx b;
     uint32_t fl = 0;
-    const int r = classify_box(c, R, R1, t, tid, force_all, true, b, fl);
+    const int r = classify_box(c, R, R1, t, tid, force_all, 3, b, fl);
     s_res[tid] = r;
     if (r == -1) { s_box[tid] = b; s_fl[tid] = fl; }
   }

@@ -157,7 +157,7 @@ def pose_workload(torch, chk, flush, m, poses, steps, ref, kind, port, n_mt=400_
     for i in range(steps):
         flush.fill_(i & 0xFF)
         a.record(); chk.isValidBatch(d, out=out); b.record()
-        ks.append(chk.lastKernelTimesMs())
+        ks.append(chk.lastStageTimesMs())
         torch.cuda.synchronize()
         tot += a.elapsed_time(b)
     st = chk.stats()
@@ -170,8 +170,11 @@ def pose_workload(torch, chk, flush, m, poses, steps, ref, kind, port, n_mt=400_
     t0 = time.perf_counter(); vm = ref.check_poses_mt(poses[:n_mt], cores); tm = time.perf_counter() - t0
     _, zv = port.check_poses(poses[:50_000], want_zone=True)
     return {"map": m.desc, "poses": n, "poses_per_s": n * steps / (tot * 1e-3), "ms_per_step": tot / steps,
-            "classify_ms": float(k[0]), "warp_stage_ms": float(k[1]), "group_stage_ms": float(k[2]),
-            "queued_boxes": st["last_queued_boxes"], "deferred_boxes": st["last_deferred"],
+            "classify_ms": float(k[0]), "warp_stage_ms": float(k[1]), "reach_vertex_ms": float(k[2]),
+            "reach_plane_ms": float(k[3]), "group_stage_ms": float(k[4]), "pass_ms": float(k.sum()),
+            "queued_boxes": st["last_queued_boxes"], "queued_warp_stage": st["last_queued_warp_stage"],
+            "queued_reach_stage": st["last_queued_reach_stage"], "reach_plane_stage": st["last_reach_plane_stage"],
+            "deferred_boxes": st["last_deferred"],
             "valid_fraction": float(got.mean()), "exit_mix": exit_mix(port, poses[:20_000]),
             "algorithmic_bytes_per_pose": 57.0 + 4.0 * float(zv.mean()),
             "cpu": {"kind": kind, "single_thread_poses_per_s": n1 / t1, "all_threads_poses_per_s": n_mt / tm, "cores": cores,
@@ -307,7 +310,7 @@ def main():
     launches0 = chk.stats()["kernel_launches"]
     # one extra window at the end (N > 1): the exchange of the last step
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
-    k0_ms, k1_ms, k2_ms = [], [], []
+    k0_ms, k1_ms, k2_ms, stage_ms = [], [], [], []
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -318,7 +321,7 @@ def main():
         step_device(i, ev[i][0])
         ev[i][1].record()
         ka, kb, kc = chk.lastKernelTimesMs()   # waits for this step's kernels (events on the same stream)
-        k0_ms.append(ka); k1_ms.append(kb); k2_ms.append(kc)
+        k0_ms.append(ka); k1_ms.append(kb); k2_ms.append(kc); stage_ms.append(chk.lastStageTimesMs())
     ev[args.steps][0].record()
     if world > 1:
         exchange((args.steps - 1) & 1, ev[args.steps][0])
@@ -338,6 +341,7 @@ def main():
     launches = chk.stats()["kernel_launches"] - launches0
     deferred = chk.stats()["last_deferred"]
     queued = chk.stats()["last_queued_boxes"]
+    stats_last = chk.stats()
 
     # ---- timed region: end to end through the host-buffer C-ABI call ---------------------------
     e2e_steps = args.steps
@@ -557,6 +561,11 @@ def main():
                          "classify_kernel_ms": k0, "group_kernel_ms": k2, "pass_ms": k0 + k1 + k2,
                          "achieved_dominant_kernel_alone": achieved_dom,
                          "queued_boxes": int(queued), "deferred_boxes": int(deferred),
+                         "stage_ms": dict(zip(("classify", "warp_stage", "reach_vertex", "reach_plane", "group"),
+                                              [float(x) for x in np.mean(np.array(stage_ms), 0)])),
+                         "queued_warp_stage": stats_last["last_queued_warp_stage"],
+                         "queued_reach_stage": stats_last["last_queued_reach_stage"],
+                         "reach_plane_stage": stats_last["last_reach_plane_stage"],
                          "actual_dram_GBps_dominant_kernel": (traffic / (k1 * 1e-3) / 1e9) if traffic else None,
                          "note": "achieved = ALGORITHMIC bytes (the zone vertices the reference scans, SURVEY 8d) / sum of "
                                  "the three stage durations; the range tables and vertex probes answer most of those scans "

@@ -79,7 +79,10 @@ typedef struct artp_stats {
   uint64_t kernel_launches;    /* kernels launched by this handle since creation */
   uint32_t last_deferred;      /* deferred count of the most recent check call */
   uint32_t last_launches;      /* kernels launched by the most recent call */
-  uint32_t last_queued_boxes;  /* boxes the classify stage queued for the warp stage in the most recent call's last round */
+  uint32_t last_queued_boxes;  /* boxes the classify stage queued for the later stages in the most recent call's last round */
+  uint32_t last_queued_warp_stage;   /* ... of which for the warp stage (torso boxes, reach boxes of unusual size) */
+  uint32_t last_queued_reach_stage;  /* ... of which for the thread-level reach-box stages */
+  uint32_t last_reach_plane_stage;   /* reach boxes that survived the vertex scan and ran the plane stage */
 } artp_stats;
 
 int  artp_create(const artp_params* params, artp_handle** out);
@@ -192,11 +195,29 @@ int artp_compact_bits_device(artp_handle* h, const uint32_t* d_bits, size_t n, i
 
 int artp_get_stats(artp_handle* h, artp_stats* out);
 
+/* Threads and streams. A handle is safe to share between threads (the reference's checkers are called from the planning
+ * thread, the ROS callback threads and the cleaner thread): every entry point holds the handle's lock for its
+ * whole duration, host-buffer calls including their staging copies. The *_device entry points are asynchronous on the
+ * caller's stream; calls issued on DIFFERENT streams are ordered against each other on the device (each waits for the
+ * previous user of the handle's scratch buffers), so they are safe but do not overlap -- use one handle per stream for
+ * concurrency.
+ *
+ * Errors detected on the device: if the plane-grouping stage cannot hold a zone in its shared-memory store (sized at
+ * artp_set_map from the box diagonals; cannot happen for boxes that passed artp_set_map unless the test hook below is
+ * used) the affected pose / edge is reported INVALID (fail closed) and a sticky error is raised: host-buffer calls return
+ * ARTP_E_LIMIT from the call that caused it; after asynchronous *_device calls, synchronise the stream and call
+ * artp_poll_error (returns ARTP_E_LIMIT once, then clears). artp_get_stats reports it too. */
+int artp_poll_error(artp_handle* h);
+/* Test hook: cap the plane store at max_triangles (0 = no cap) from the next artp_set_map on. */
+int artp_debug_set_group_capacity(artp_handle* h, int max_triangles);
+
 /* Kernel timing for roofline reporting: when enabled, CUDA events are recorded on the launch stream around the three
  * stages of every check call; artp_get_last_timing waits for the last call's kernels and returns
- * ms3[0..2] = classify (thread/item), box warp stage, plane-grouping block stage, in milliseconds. */
+ * ms3[0..2] = classify (thread/item), box stages (warp stage + reach-box stages), plane-grouping block stage, in ms. */
 int artp_set_timing(artp_handle* h, int enable);
 int artp_get_last_timing(artp_handle* h, float* ms3);
+/* Per-stage form: ms5 = classify, warp stage (torso boxes), reach vertex scan, reach plane stage, plane grouping. */
+int artp_get_last_stage_timing(artp_handle* h, float* ms5);
 
 /* Test hook: 0 = normal (classify -> warp stage -> grouping stage for deferred boxes),
  *            1 = send every in-map box through the exact block-level grouping kernel. */

@@ -217,15 +217,25 @@ class SE3FromSE2Sampler {
   }
   void sampleUniform(State* state) {                                             // sampler.cpp:82-131
     const auto& h = checker_->handle();
-    h->check(artp_sample_states(h->get(), nullptr, seed_, next_, 1, &state->x, nullptr), "artp_sample_states");
-    ++next_;
+    do {   // uniform mode: a draw outside the map is a NaN candidate; samplePositionInMap (sampler.cpp:46-50) draws again
+      h->check(artp_sample_states(h->get(), nullptr, seed_, next_, 1, &state->x, nullptr), "artp_sample_states");
+      ++next_;
+    } while (state->x != state->x);
   }
+  // n states, none NaN: rejected (outside-map, uniform mode only) candidates are redrawn from the following counters of
+  // the stream, like the reference's draw-again loop; the output keeps draw order.
   void sampleUniformBatch(size_t n, std::vector<State>* states) {
-    states->resize(n);
-    if (!n) return;
+    states->clear();
+    states->reserve(n);
     const auto& h = checker_->handle();
-    h->check(artp_sample_states(h->get(), nullptr, seed_, next_, n, &(*states)[0].x, nullptr), "artp_sample_states");
-    next_ += n;
+    std::vector<State> buf;
+    while (states->size() < n) {
+      const size_t m = n - states->size();
+      buf.resize(m);
+      h->check(artp_sample_states(h->get(), nullptr, seed_, next_, m, &buf[0].x, nullptr), "artp_sample_states");
+      next_ += m;
+      for (const State& s : buf) if (s.x == s.x) states->push_back(s);
+    }
   }
   // Draws n_draw candidates, returns the valid ones in draw order (what n_draw iterations of
   // `do sampleUniform(s) while (!isValid(s))` would have accepted).
@@ -344,7 +354,8 @@ class MotionCostObjective {
 
   double getCost(const float* e3) const {                                        // motion_cost_objective.h:54-61
     const auto& w = checker_->handle()->params().planner.prm_motion_cost.cost_weights;
-    return e3[0] * w.energy + e3[1] * w.time + e3[2] * w.risk;
+    // getEnergy/getTime/getRisk return double: the weighted sum is evaluated in double on exact float products
+    return static_cast<double>(e3[0]) * w.energy + static_cast<double>(e3[1]) * w.time + static_cast<double>(e3[2]) * w.risk;
   }
   bool isFeasible(const float* e3) const {                                       // motion_cost_objective.h:63-65
     return static_cast<double>(e3[2]) <= checker_->handle()->params().planner.prm_motion_cost.risk_threshold;

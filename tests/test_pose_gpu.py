@@ -220,3 +220,98 @@ def test_terraces_exercise_the_deferral_path(maps, golden, checkers):
     st = chk.stats()
     assert st["last_queued_boxes"] > 0 and st["last_deferred"] > 0, st
     assert np.array_equal(got, unpack(golden, name + "/mask", len(got)))
+
+
+def test_group_stage_overflow_is_reported_by_the_call_that_caused_it(maps, golden):
+    """A zone that does not fit the plane store: the pose is reported invalid (fail closed) and the host-buffer call itself
+    returns ARTP_E_LIMIT; asynchronous calls surface it through pollError (VERDICT r1 weak #7, ADVICE)."""
+    import torch
+    import art_planner_b200 as ap
+    from art_planner_b200 import capi
+    m = maps("terraces")
+    chk = ap.StateValidityChecker(cases.PARAMS["yaml"], device=0)
+    chk.debugSetGroupCapacity(64)          # far below a torso zone's ~2000 triangles
+    set_map(chk, m)
+    chk.setMode(1)                         # every in-map box goes through the grouping stage
+    poses = synth.make_terrain_poses(m, 5000, seed=31)
+    with pytest.raises(ap.ArtpError) as ei:
+        chk.isValidBatch(poses)
+    assert ei.value.code == capi.ARTP_E_LIMIT
+    chk.pollError()                        # sticky word was consumed by the failing call
+    d = chk.isValidBatch(torch.from_numpy(poses).cuda())
+    torch.cuda.synchronize()
+    with pytest.raises(ap.ArtpError):
+        chk.pollError()
+    ref = unpack(golden, "terraces_yaml/mask", 20000)[:5000]
+    got = d.cpu().numpy()
+    assert not (got & ~ref).any()          # overflow never turns an invalid pose valid
+    # the latency path reports it too
+    with pytest.raises(ap.ArtpError):
+        for i in range(64):
+            chk.isValid(poses[i])
+    chk.debugSetGroupCapacity(0)
+    set_map(chk, m)
+    assert np.array_equal(chk.isValidBatch(poses), ref)
+    chk.pollError()
+
+
+def test_handle_is_thread_safe(maps, port_lib):
+    """Two host threads share one handle (the reference calls its checker from the planning thread and the connection /
+    cleaner threads): every call returns its own answer (ADVICE r1: staging buffer races)."""
+    import threading
+    import art_planner_b200 as ap
+    m = maps("fbm_rough")
+    chk = ap.StateValidityChecker(cases.PARAMS["yaml"], device=0)
+    set_map(chk, m)
+    o = port_lib.Oracle(cases.PARAMS["yaml"], "port")
+    o.set_map(m)
+    pa = synth.make_terrain_poses(m, 70000, seed=501)
+    s1, s2 = synth.make_edges(m, 3000, seed=502)
+    ref_p, ref_e = o.check_poses(pa), o.check_motions(s1, s2, 6)
+    ref_c = o.path_length_cost(s1, s2)
+    mv, plo = ap.MotionValidator(chk, 6), ap.PathLengthObjective(chk)
+    errs = []
+
+    def worker(kind):
+        try:
+            for it in range(6):
+                if kind == 0:
+                    assert np.array_equal(chk.isValidBatch(pa), ref_p)
+                elif kind == 1:
+                    assert np.array_equal(mv.checkMotionBatch(s1, s2), ref_e)
+                else:
+                    assert np.allclose(plo.motionCostBatch(s1, s2), ref_c, rtol=1e-12, atol=0)
+                    assert chk.isValid(pa[it]) == bool(ref_p[it])
+        except Exception as ex:      # noqa: BLE001
+            errs.append((kind, repr(ex)))
+    th = [threading.Thread(target=worker, args=(k,)) for k in (0, 1, 2, 1)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+
+
+def test_calls_on_different_streams_share_a_handle_safely(maps, port_lib):
+    """Asynchronous calls on two CUDA streams use the same per-handle queues: the library orders them (ADVICE r1)."""
+    import torch
+    m = maps("fbm_rough")
+    import art_planner_b200 as ap
+    chk = ap.StateValidityChecker(cases.PARAMS["yaml"], device=0)
+    set_map(chk, m)
+    o = port_lib.Oracle(cases.PARAMS["yaml"], "port")
+    o.set_map(m)
+    pa = synth.make_terrain_poses(m, 200000, seed=601)
+    pb = synth.make_terrain_poses(m, 200000, seed=602)
+    ra, rb = o.check_poses_mt(pa, 8), o.check_poses_mt(pb, 8)
+    da, db = torch.from_numpy(pa).cuda(), torch.from_numpy(pb).cuda()
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for it in range(4):
+        with torch.cuda.stream(sa):
+            va = chk.isValidBatch(da)
+        with torch.cuda.stream(sb):
+            vb = chk.isValidBatch(db)
+        outs.append((va, vb))
+    torch.cuda.synchronize()
+    for va, vb in outs:
+        assert np.array_equal(va.cpu().numpy(), ra) and np.array_equal(vb.cpu().numpy(), rb)
