@@ -18,7 +18,7 @@
 #include "../../include/artp.h"
 #include "artp_cnn.h"
 #include "artp_kernels.cuh"
-#include "artp_reach.cuh"
+#include "artp_tiles.cuh"
 #include "artp_sampler.cuh"
 
 namespace {
@@ -44,7 +44,6 @@ struct Handle {
   size_t defer_cap = 0;
   artp::BoxRec* d_recs = nullptr;   // classify -> warp-stage box queue (torso boxes, reach boxes of unusual size)
   artp::BoxRec* d_recs_f = nullptr; // classify -> thread-level reach-box queue
-  uint32_t* d_plane_list = nullptr; // reach boxes that survived the vertex scan
   size_t recs_cap = 0;
   uint32_t* d_block_counts = nullptr;
   size_t block_counts_cap = 0;
@@ -53,8 +52,11 @@ struct Handle {
   cudaStream_t stream = nullptr;    // internal compute stream for the host-buffer API
   cudaStream_t copy_stream = nullptr;   // H2D slices of the host-buffer API
   cudaEvent_t copy_ev[16] = {};
-  int k1_grid = 0, k2_grid = 0, k2_smem = 0, k2_tcap = 0, f1_grid = 0, f2_grid = 0, reach_smem = 0;
-  CUtensorMap reach_tmap;           // 2-D tile map over the elevation_masked layer (reach-box zones)
+  int k1_grid = 0, k2_grid = 0, k2_smem = 0, k2_tcap = 0;
+  // stage B (artp_tiles.cuh): [0] big tiles (torso queue, 4 warps per CTA), [1] small tiles (reach-box queue, 8 warps)
+  artp::TileCfg tile_cfg[2] = {};
+  int tile_grid[2] = {0, 0}, tile_smem[2] = {0, 0}, tile_warps[2] = {4, 8};
+  CUtensorMap tile_map[2][2];       // [cfg][layer]: 2-D tile maps over elevation / elevation_masked
   int k0_flags = 0;                 // tuning switch of the classify stage (env ARTP_K0_FLAGS: 2 = no vertex probes)
   int mode = 0;
   artp_cnn::State* cnn = nullptr;
@@ -251,12 +253,11 @@ int ensure_queues(Handle* h, size_t n_items, cudaStream_t s) {
   const size_t need = 5 * std::min(n_items, kChunkItems);
   if (h->recs_cap >= need) return ARTP_OK;
   CU_TRY(h, cudaDeviceSynchronize());   // rare (growth only): users on any stream must be done before the free
-  cudaFree(h->d_defer); cudaFree(h->d_recs); cudaFree(h->d_recs_f); cudaFree(h->d_plane_list);
-  h->d_defer = nullptr; h->d_recs = nullptr; h->d_recs_f = nullptr; h->d_plane_list = nullptr; h->recs_cap = 0;
+  cudaFree(h->d_defer); cudaFree(h->d_recs); cudaFree(h->d_recs_f);
+  h->d_defer = nullptr; h->d_recs = nullptr; h->d_recs_f = nullptr; h->recs_cap = 0;
   const size_t cap = std::max<size_t>(need, 1u << 16);
   CU_TRY(h, cudaMalloc(&h->d_recs, cap * sizeof(artp::BoxRec)));
   CU_TRY(h, cudaMalloc(&h->d_recs_f, cap * sizeof(artp::BoxRec)));
-  CU_TRY(h, cudaMalloc(&h->d_plane_list, cap * sizeof(uint32_t)));
   CU_TRY(h, cudaMalloc(&h->d_defer, cap * sizeof(uint32_t)));
   h->recs_cap = cap; h->defer_cap = cap;
   return ARTP_OK;
@@ -311,7 +312,7 @@ struct HostFeed {
 // The claim counters of the consumer stages restart where the next slice's producers will append (the persistent
 // consumers of the previous slice overshoot their counters).
 __global__ void restart_claims_kernel(uint32_t* ctr) {
-  ctr[0] = ctr[3]; ctr[2] = ctr[4]; ctr[6] = ctr[5];
+  ctr[0] = ctr[3]; ctr[2] = ctr[4];
 }
 
 // Launch the pipeline for a prepared Work (items 0 .. w.n_items = the whole call) on stream s, in rounds of
@@ -354,28 +355,25 @@ int run_items(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed = nu
       if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[1], s));
       // small batches (the planner's one-state isValid calls): no more CTAs than there can be boxes
       const size_t nb = hi - lo;
-      const unsigned grid_w = (unsigned)std::min<size_t>((size_t)h->k1_grid, (5 * nb + artp::kWarpsPerCta - 1) / artp::kWarpsPerCta);
-      artp::box_items_warp_kernel<<<grid_w, artp::kWarpsPerCta * 32, 0, s>>>(h->chk, w, h->d_recs, h->d_ctr + 3, h->d_ctr,
-                                                                                  h->d_ctr + 1, h->d_defer, h->mode == 1);
-      CU_TRY(h, cudaGetLastError());
+      {
+        const int wpc = h->tile_warps[0];
+        const unsigned grid_w = (unsigned)std::min<size_t>((size_t)h->tile_grid[0], (5 * nb + wpc - 1) / wpc);
+        artp::box_tiles_warp_kernel<<<grid_w, wpc * 32, h->tile_smem[0], s>>>(h->chk, h->tile_map[0][0], h->tile_map[0][1], h->tile_cfg[0],
+                                                                               w, h->d_recs, h->d_ctr + 3, h->d_ctr, h->d_ctr + 1, h->d_defer,
+                                                                               0u, h->mode == 1);
+        CU_TRY(h, cudaGetLastError());
+      }
       if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[2], s));
       if (h->chk.reach_tw) {
-        constexpr int kRT = artp::kReachWarpsPerCta * 32;
-        const unsigned grid_f1 = (unsigned)std::min<size_t>((size_t)h->f1_grid, (4 * nb + kRT - 1) / kRT);
-        artp::reach_vertex_kernel<<<grid_f1, kRT, h->reach_smem, s>>>(h->chk, h->reach_tmap, w, h->d_recs_f, h->d_ctr + 4, h->d_ctr + 2,
-                                                                        h->d_plane_list, h->d_ctr + 5);
+        const int wpc = h->tile_warps[1];
+        const unsigned grid_f = (unsigned)std::min<size_t>((size_t)h->tile_grid[1], (4 * nb + wpc - 1) / wpc);
+        artp::box_tiles_warp_kernel<<<grid_f, wpc * 32, h->tile_smem[1], s>>>(h->chk, h->tile_map[1][1], h->tile_map[1][1], h->tile_cfg[1],
+                                                                               w, h->d_recs_f, h->d_ctr + 4, h->d_ctr + 2, h->d_ctr + 1,
+                                                                               h->d_defer, artp::kDeferReachBit, h->mode == 1);
         CU_TRY(h, cudaGetLastError());
-        if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[3], s));
-        const unsigned grid_f2 = (unsigned)std::min<size_t>((size_t)h->f2_grid, (4 * nb + kRT - 1) / kRT);
-        artp::reach_plane_kernel<<<grid_f2, kRT, h->reach_smem, s>>>(h->chk, h->reach_tmap, w, h->d_recs_f, h->d_plane_list, h->d_ctr + 5,
-                                                                       h->d_ctr + 6, h->d_ctr + 1, h->d_defer);
-        CU_TRY(h, cudaGetLastError());
-        if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[4], s));
-        launches += 2;
-      } else if (h->timing && last) {
-        CU_TRY(h, cudaEventRecord(h->ev[3], s));
-        CU_TRY(h, cudaEventRecord(h->ev[4], s));
+        launches += 1;
       }
+      if (h->timing && last) { CU_TRY(h, cudaEventRecord(h->ev[3], s)); CU_TRY(h, cudaEventRecord(h->ev[4], s)); }
       launches += 2;
     }
     w.item_base = (uint32_t)base;
@@ -438,7 +436,7 @@ int artp_create(const artp_params* params, artp_handle** out) {
   if ((e = cudaGetDeviceProperties(&prop, h->device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
   h->sm_count = prop.multiProcessorCount;
   cudaFuncAttributes fa;
-  if ((e = cudaFuncGetAttributes(&fa, artp::box_items_warp_kernel)) != cudaSuccess)
+  if ((e = cudaFuncGetAttributes(&fa, artp::box_tiles_warp_kernel)) != cudaSuccess)
     return fail("no usable kernel image (built for sm_100a)", e);
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
@@ -450,12 +448,6 @@ int artp_create(const artp_params* params, artp_handle** out) {
   if ((e = cudaHostAlloc((void**)&h->h_err, 64, cudaHostAllocMapped)) != cudaSuccess) return fail("cudaHostAlloc", e);
   *h->h_err = 0;
   if ((e = cudaHostGetDevicePointer((void**)&h->d_err, h->h_err, 0)) != cudaSuccess) return fail("cudaHostGetDevicePointer", e);
-  int per_sm = 0;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, artp::box_items_warp_kernel,
-                                                         artp::kWarpsPerCta * 32, 0)) != cudaSuccess)
-    return fail("occupancy", e);
-  h->k1_grid = h->sm_count * std::max(per_sm, 1);
-
   if (const char* kf = std::getenv("ARTP_K0_FLAGS")) h->k0_flags = std::atoi(kf) & 2;
   h->cnn = artp_cnn::create(h->device, h->sm_count);
   // checker constants (float casts as the reference's ctor/Pose3FromXYZ arguments make them)
@@ -480,7 +472,7 @@ void artp_destroy(artp_handle* hh) {
   for (int i = 0; i < kCopyEvents; ++i) if (h->copy_ev[i]) cudaEventDestroy(h->copy_ev[i]);
   for (int k = 0; k < 2; ++k) for (int l = 0; l <= artp::kMaxLevel; ++l) { cudaFree(h->d_T[k][l]); cudaFree(h->d_NF[k][l]); }
   cudaFree(h->d_H[0]); cudaFree(h->d_H[1]); cudaFree(h->d_ctr); cudaFree(h->d_defer); cudaFree(h->d_stage);
-  cudaFree(h->d_block_counts); cudaFree(h->d_recs); cudaFree(h->d_recs_f); cudaFree(h->d_plane_list); cudaFree(h->d_samp_layers); cudaFree(h->d_samp_scratch);
+  cudaFree(h->d_block_counts); cudaFree(h->d_recs); cudaFree(h->d_recs_f); cudaFree(h->d_samp_layers); cudaFree(h->d_samp_scratch);
   if (h->h_small_out) cudaFreeHost(h->h_small_out);
   if (h->h_err) cudaFreeHost(h->h_err);
   for (int g = 0; g < 2; ++g) if (h->chain_ev[g]) cudaEventDestroy(h->chain_ev[g]);
@@ -558,7 +550,7 @@ int artp_get_stats(artp_handle* hh, artp_stats* out) {
   h->stats.last_queued_boxes = ctr[3] + ctr[4];
   h->stats.last_queued_warp_stage = ctr[3];
   h->stats.last_queued_reach_stage = ctr[4];
-  h->stats.last_reach_plane_stage = ctr[5];
+  h->stats.last_reach_plane_stage = 0;
   if (h->deferred_unread) { h->stats.poses_deferred += ctr[1]; h->deferred_unread = false; }
   *out = h->stats;
   return take_sticky_error(h);
@@ -651,41 +643,53 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
   }
   h->chk.Lx = Lx; h->chk.Ly = Ly; h->chk.cx = cx; h->chk.cy = cy;
   h->chk.cell_margin = 0.02f + 2e-6f * (float)std::max(rows, cols);
-  // Thread-level reach-box stages: one TMA tile per box. A zone spans at most ceil(2 r / s) + 3 vertices per axis
-  // (r = box half-diagonal); boxes whose zone is larger (never for the bound itself) fall back to the warp stage.
+  // Stage B tiles (artp_tiles.cuh): a zone spans at most ceil(2 r / s) + 3 vertices per axis (r = box half-diagonal);
+  // + 3 columns because the tile starts at x0 & ~3; width rounded up to a multiple of 4 floats (16-byte rows).
   {
-    const float* sd = h->chk.side[1];
-    const double r = 0.5 * std::sqrt((double)sd[0] * sd[0] + (double)sd[1] * sd[1] + (double)sd[2] * sd[2]);
-    const int tw = ((int)std::ceil(2.0 * r * f.iW) + 3 + 3) & ~3, th = (int)std::ceil(2.0 * r * f.iD) + 3;
-    const uint32_t bytes = (uint32_t)tw * th * 4, stride = (bytes + 127u) & ~127u;
-    const int smem = artp::kReachWarpsPerCta * 32 * (int)stride + 128;
-    h->chk.reach_tw = 0; h->chk.reach_th = 0; h->chk.reach_tile_bytes = 0; h->chk.reach_tile_stride = 0;
-    if (tw <= 256 && th <= 256 && smem <= 200 * 1024) {
-      typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-      void* fn = nullptr;
-      cudaDriverEntryPointQueryResult qres;
-      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
-        h->err = "cuTensorMapEncodeTiled not available from the driver"; return ARTP_E_CUDA;
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      h->err = "cuTensorMapEncodeTiled not available from the driver"; return ARTP_E_CUDA;
+    }
+    h->chk.reach_tw = 0; h->chk.reach_th = 0;
+    for (int q = 0; q < 2; ++q) {          // 0: big tiles (torso box bound), 1: small tiles (reach box bound)
+      const float* sd = h->chk.side[q];
+      const double r = 0.5 * std::sqrt((double)sd[0] * sd[0] + (double)sd[1] * sd[1] + (double)sd[2] * sd[2]);
+      int tw = ((int)std::ceil(2.0 * r * f.iW) + 3 + 3 + 3) & ~3, th = (int)std::ceil(2.0 * r * f.iD) + 3;
+      tw = std::min(tw, 256); th = std::min(th, 256);
+      artp::TileCfg tc;
+      tc.tw = tw; tc.th = th; tc.bytes = (uint32_t)tw * th * 4; tc.stride = (tc.bytes + 127u) & ~127u;
+      int wpc = q == 0 ? 4 : 8;
+      while (wpc > 1 && (size_t)wpc * 2 * tc.stride + 128 > 160 * 1024) wpc >>= 1;
+      const size_t smem = (size_t)wpc * 2 * tc.stride + 128;
+      if (smem > 200 * 1024) {
+        if (q == 1) continue;              // no reach-box queue: everything takes the big-tile queue
+        // boxes this large relative to the cells: tiles capped, oversized zones go to the grouping stage
+        tc.tw = 64; tc.th = 64; tc.bytes = 64 * 64 * 4; tc.stride = tc.bytes; wpc = 4;
       }
       const cuuint64_t gdim[2] = {(cuuint64_t)pitch, (cuuint64_t)cols};
       const cuuint64_t gstr[1] = {(cuuint64_t)pitch * sizeof(float)};
-      const cuuint32_t box[2] = {(cuuint32_t)tw, (cuuint32_t)th};
+      const cuuint32_t box[2] = {(cuuint32_t)tc.tw, (cuuint32_t)tc.th};
       const cuuint32_t one[2] = {1, 1};
-      const CUresult cr = reinterpret_cast<EncodeTiledFn>(fn)(&h->reach_tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->d_H[1], gdim, gstr,
-                                                              box, one, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (cr != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")"; return ARTP_E_CUDA; }
-      CU_TRY(h, cudaFuncSetAttribute(artp::reach_vertex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CU_TRY(h, cudaFuncSetAttribute(artp::reach_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      for (int layer = 0; layer < 2; ++layer) {
+        const CUresult cr = reinterpret_cast<EncodeTiledFn>(fn)(&h->tile_map[q][layer], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->d_H[layer], gdim,
+                                                                gstr, box, one, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")"; return ARTP_E_CUDA; }
+      }
+      h->tile_cfg[q] = tc; h->tile_warps[q] = wpc;
+      h->tile_smem[q] = (int)((size_t)wpc * 2 * tc.stride + 128);
+      if (q == 1) { h->chk.reach_tw = tc.tw; h->chk.reach_th = tc.th; }
+    }
+    const int smax = std::max(h->tile_smem[0], h->tile_smem[1]);
+    CU_TRY(h, cudaFuncSetAttribute(artp::box_tiles_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+    for (int q = 0; q < 2; ++q) {
       int ps = 0;
-      CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, artp::reach_vertex_kernel, artp::kReachWarpsPerCta * 32, smem));
-      h->f1_grid = h->sm_count * std::max(ps, 1);
-      CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, artp::reach_plane_kernel, artp::kReachWarpsPerCta * 32, smem));
-      h->f2_grid = h->sm_count * std::max(ps, 1);
-      h->reach_smem = smem;
-      h->chk.reach_tw = tw; h->chk.reach_th = th; h->chk.reach_tile_bytes = bytes; h->chk.reach_tile_stride = stride;
+      CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, artp::box_tiles_warp_kernel, h->tile_warps[q] * 32, h->tile_smem[q]));
+      h->tile_grid[q] = h->sm_count * std::max(ps, 1);
     }
   }
   h->has_map = true;

@@ -39,11 +39,9 @@ struct Checker {
   int unknown_untraversable;
   double Lx, Ly, cx, cy;  // grid_map length / position (doubles) for isInside
   float cell_margin;      // candidate-cell search margin in cells (plane stage)
-  // thread-level reach-box stages (artp_reach.cuh): TMA tile of reach_tw x reach_th floats per box (0: path disabled;
-  // the tile starts at column x0 & ~3, so a zone may be at most reach_tw - 3 wide),
-  // reach_tile_bytes = tw * th * 4 (what one TMA transfers), reach_tile_stride = that rounded up to 128 bytes
+  // extent of the reach-box queue's TMA tile in floats (artp_tiles.cuh; 0: no such queue). The tile starts at column
+  // x0 & ~3, so a zone may be at most reach_tw - 3 wide.
   int reach_tw, reach_th;
-  uint32_t reach_tile_bytes, reach_tile_stride;
 };
 
 // Box pose in heightfield space + AABB + zone.

@@ -6,7 +6,7 @@
 //      dxOrthogonalizeR, the five box centres / map-inside tests / AABBs / zones, the zone min/max/all-finite from
 //      exact range tables (no zone scan), and the collider's four early-outs. Items decided here (the majority)
 //      never touch the heightfield; every box that needs the vertex / plane tests becomes a BoxRec in a queue.
-//   B  box_items_warp_kernel     one WARP per queued box: lanes stride the zone with coalesced fp32 loads,
+//   B  box_tiles_warp_kernel (artp_tiles.cuh)   one WARP per queued box, the box's zone staged in shared memory by TMA:
 //      vertex-in-box and plane tests by warp ballots. The reference's O(T^2) plane grouping is replaced by an
 //      exact shortcut: only triangles under one of the 8 box corners can own a plane-contact point, so only those
 //      "candidate" planes are built; a bloom filter on the (approximate) normal finds any earlier triangle that
@@ -32,7 +32,9 @@ enum { R_FREE = 0, R_HIT = 1, R_DEFER = 2 };
 struct WarpScratch {
   float cpl[kMaxCand][4];   // candidate planes (exact)
   int cidx[kMaxCand];       // emission index of a LIVE candidate, -1 otherwise
-  uint32_t bloom[kBloomWords];
+  uint32_t bloom[kBloomWords];    // level 1: approximate (n0, n2)
+  uint32_t bloom2[kBloomWords];   // level 2: exact (n0, n2, d)
+  uint32_t cand_bits[kBloomWords];   // bit i: triangle i of the zone is a live candidate
 };
 
 // Work description shared by K1/K2. EDGE mode: item w -> edge e = w / (steps+1), j = w % (steps+1);
@@ -209,54 +211,144 @@ __device__ __forceinline__ void zone_reduce(const Field& f, const BoxCtx& b, int
   maxY = mx; minY = mn;
 }
 
-__device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws, int lane, float cell_margin,
-                                bool needs_reduce, bool all_finite_known) {
+// The zone as the warp stage reads it: element (xi, zi) -- vertex (x0 + xi, z0 + zi) -- at p[zi * stride + xi]; either the
+// heightfield itself (p = H + z0 * pitch + x0, stride = pitch) or a shared-memory tile the zone was copied into by TMA.
+struct ZoneView { const float* p; int stride; };
+template <bool SMEM>
+__device__ __forceinline__ float zload(const ZoneView& v, int xi, int zi) {
+  const float* q = v.p + zi * v.stride + xi;
+  return SMEM ? *q : __ldg(q);
+}
+template <bool SMEM>
+__device__ __forceinline__ void zcell(const ZoneView& v, int lx, int lz, float& hA, float& hB, float& hC, float& hD) {
+  const float* q = v.p + lz * v.stride + lx;
+  if (SMEM) { hA = q[0]; hB = q[1]; hC = q[v.stride]; hD = q[v.stride + 1]; }
+  else { hA = __ldg(q); hB = __ldg(q + 1); hC = __ldg(q + v.stride); hD = __ldg(q + v.stride + 1); }
+}
+
+// Bloom keys of the merge screen. Level 1 (cheap, every kept triangle): buckets of the APPROXIMATE normal (n0, n2);
+// level 2 (flagged triangles only): buckets of the EXACT plane (n0, n2, d).
+__device__ __forceinline__ uint32_t bloom_hash3(int kx, int kz, int kd) {
+  return ((((uint32_t)kx * 0x9E3779B1u) ^ ((uint32_t)kz * 0x85EBCA77u)) + (uint32_t)kd * 0xC2B2AE3Du) >> 20;   // 12 bits
+}
+constexpr float kDScale = 524288.0f;    // level-2 bucket width 2^-19 on d (> 2 eps, so |d_m - d_c| < eps spans <= 2 buckets)
+__device__ __forceinline__ int dkey(float d) { return (int)floorf(fminf(fmaxf(d, -2000.0f), 2000.0f) * kDScale); }
+
+// Warp-level decision for one box; the zone is read through `zv`. Returns R_FREE / R_HIT / R_DEFER (warp-uniform).
+//   (3) vertex stage: lane = vertex. Big all-finite zones (the torso's ~40 x 40 vertices) are walked window by window:
+//       the level-3 range table holds the maximum of every 8 x 8 vertex window, and a window whose maximum does not
+//       exceed the box bottom holds neither a colliding vertex nor a kept triangle, so it is skipped in the vertex
+//       stage AND in the merge screen -- on rough terrain most torso boxes hover over all but a few peaks.
+//   (4) plane stage: a plane contact point is always a box corner (up to a few ulps), so only the triangles in the
+//       cells under the 8 corners (+- cell_margin) can report one: <= 64 candidates, lane = candidate.
+//   (5) merge screen: does an EARLIER kept triangle epsilon-match a live candidate (greedy grouping,
+//       heightfield.cpp:1511-1556)? Two bloom levels: the approximate normal of every kept triangle against the
+//       candidates' (n0, n2) buckets; a flagged lane builds its exact plane and tests the (n0, n2, d) buckets -- matching
+//       planes need |d_m - d_c| < eps, which on non-degenerate terrain never happens, so the exact compare against the
+//       candidate list (shared memory) is reached only on flat / terraced ground. Live candidates themselves are
+//       skipped by the screen (a bitmap over the triangle indices); candidate-vs-candidate matches are caught when the
+//       level-2 keys are inserted. Any match => R_DEFER (exact stage C).
+// Code size matters here (round 2: a 5 400-instruction version stalled on instruction fetch, `no_instruction` 9 of 16
+// cycles per issue): one region loop serves both the windowed and the flat case, nothing is unrolled.
+template <bool SMEM>
+__device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView& zv, WarpScratch& ws, int lane,
+                                float cell_margin, bool needs_reduce, bool all_finite_known) {
   const int nX = b.x1 - b.x0 + 1, nZ = b.z1 - b.z0 + 1;
   const int nV = nX * nZ;
-  const uint32_t magicX = magic_for(nX);
-  const float* base = f.H + (size_t)b.z0 * f.pitch + b.x0;
 
   // (1)+(2) zone reductions and early outs -- normally already done by stage A
   bool allFinite = all_finite_known;
   if (needs_reduce) {
-    float maxY, minY;
-    zone_reduce(f, b, lane, maxY, minY, allFinite);
-    const int e = zone_early_out(b, maxY, minY, allFinite);
+    const uint32_t magicX = magic_for(nX);
+    float mx = -CUDART_INF_F, mn = CUDART_INF_F;
+    bool fin = true;
+#pragma unroll 1
+    for (int t = lane; t < nV; t += 32) {
+      const int zi = (nX > 1) ? (int)__umulhi((uint32_t)t, magicX) : t;
+      const float h = zload<SMEM>(zv, t - zi * nX, zi);
+      mx = fmaxf(mx, h);
+      if (finitef(h)) mn = fminf(mn, h); else fin = false;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+      mn = fminf(mn, __shfl_xor_sync(kFull, mn, o));
+    }
+    allFinite = __all_sync(kFull, fin);
+    const int e = zone_early_out(b, mx, mn, allFinite);
     if (e >= 0) return e;
   }
 
+  const int nCZ = nZ - 1;
+  // A vertex strictly inside the box lies within the box's vertical extent: h >= maxB + slack cannot be inside
+  // (slack = 1e-4 + 4e-6 |maxB|: > 10x the rounding of the rotated coordinates and of maxB itself).
+  const float top = b.maxB + (1e-4f + 4e-6f * fabsf(b.maxB));
+
+  // Regions: the active 8 x 8-vertex windows of a big all-finite zone (bit w of `act`), else the whole zone.
+  const int nWx = (nX + 5) / 7, nWz = (nZ + 5) / 7;       // windows advance by 7 cells
+  const bool windowed = allFinite && nV > 256 && f.kmax >= 3 && nX >= 8 && nZ >= 8 && nWx * nWz <= 64;
+  unsigned long long act = 1ull;
+  if (windowed) {
+    const float2* __restrict__ T3 = f.T[3];
+    act = 0ull;
+#pragma unroll 1
+    for (int w0 = 0; w0 < nWx * nWz; w0 += 32) {
+      const int wi = w0 + lane;
+      bool a = false;
+      if (wi < nWx * nWz) {
+        const int wz = wi / nWx, wx = wi - wz * nWx;
+        const int xs = min(b.x0 + 7 * wx, b.x1 - 7), zs = min(b.z0 + 7 * wz, b.z1 - 7);
+        a = __ldg(T3 + (size_t)zs * f.pitch + xs).x > b.minB;
+      }
+      act |= (unsigned long long)__ballot_sync(kFull, a) << w0;
+    }
+    if (act == 0ull) return R_FREE;   // no vertex above the box bottom: no colliding vertex, no kept triangle
+  }
+  // region r of the walk: origin (lx0, lz0) and extent (rw, rh) in vertices
+  auto region = [&](int wi, int& lx0, int& lz0, int& rw, int& rh) {
+    if (windowed) {
+      const int wz = wi / nWx, wx = wi - wz * nWx;
+      lx0 = min(7 * wx, nX - 8); lz0 = min(7 * wz, nZ - 8); rw = 8; rh = 8;
+    } else { lx0 = 0; lz0 = 0; rw = nX; rh = nZ; }
+  };
+
   // (3) vertex-in-box test of every colliding vertex of a kept triangle (heightfield.cpp:1306-1441)
-  const int nCX = nX - 1, nCZ = nZ - 1, nC = nCX * nCZ;
-  const uint32_t magicC = magic_for(nCX);
   if (allFinite) {
     // every colliding vertex belongs to some kept triangle (all finite, >= 1 cell)
     if (nV > 128) {
       // Probe pass: one vertex per lane on an 8 x 4 lattice over the box footprint (a hit anywhere in the zone is the
-      // reference's answer, heightfield.cpp:1344-1441) -- finds most intersecting torso boxes in one step instead of
-      // the row-by-row scan reaching them.
+      // reference's answer) -- finds most intersecting torso boxes in one step.
       const float u0 = (((float)(lane & 7) + 0.5f) * 0.25f - 1.0f) * (0.5f * b.side[0]);
       const float u1 = (((float)(lane >> 3) + 0.5f) * 0.5f - 1.0f) * (0.5f * b.side[1]);
       const float qx = b.P[0] + u0 * b.R1[0] + u1 * b.R1[1], qz = b.P[2] + u0 * b.R1[6] + u1 * b.R1[7];
       const int vx = min(max(__float2int_rn(qx * f.iW), b.x0), b.x1), vz = min(max(__float2int_rn(qz * f.iD), b.z0), b.z1);
-      const float h = __ldg(f.H + (size_t)vz * f.pitch + vx);
-      const bool hit = h > b.minB && vertex_inside(b, vx * f.sW, h, vz * f.sD);
+      const float h = zload<SMEM>(zv, vx - b.x0, vz - b.z0);
+      const bool hit = h > b.minB && h < top && vertex_inside(b, vx * f.sW, h, vz * f.sD);
       if (__any_sync(kFull, hit)) return R_HIT;
     }
-    for (int t0 = 0; t0 < nV; t0 += 64) {
-      bool hit = false;
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int t = t0 + 32 * u + lane;
-        if (t < nV) {
-          const int zi = (nX > 1) ? (int)__umulhi((uint32_t)t, magicX) : t;
-          const int xi = t - zi * nX;
-          const float h = __ldg(base + (size_t)zi * f.pitch + xi);
-          if (h > b.minB) hit = hit || vertex_inside(b, (b.x0 + xi) * f.sW, h, (b.z0 + zi) * f.sD);
+#pragma unroll 1
+    for (unsigned long long m = act; m; m &= m - 1) {
+      int lx0, lz0, rw, rh;
+      region(__ffsll((long long)m) - 1, lx0, lz0, rw, rh);
+      const uint32_t magicW = magic_for(rw);
+      const int n = rw * rh;
+#pragma unroll 1
+      for (int t0 = 0; t0 < n; t0 += 32) {
+        const int t = t0 + lane;
+        bool hit = false;
+        if (t < n) {
+          const int q = (rw > 1) ? (int)__umulhi((uint32_t)t, magicW) : t;
+          const int xi = lx0 + t - q * rw, zi = lz0 + q;
+          const float h = zload<SMEM>(zv, xi, zi);
+          hit = h > b.minB && h < top && vertex_inside(b, (b.x0 + xi) * f.sW, h, (b.z0 + zi) * f.sD);
         }
+        if (__any_sync(kFull, hit)) return R_HIT;
       }
-      if (__any_sync(kFull, hit)) return R_HIT;
     }
   } else {
+    const int nCX = nX - 1, nC = nCX * nCZ;
+    const uint32_t magicC = magic_for(nCX);
+#pragma unroll 1
     for (int t0 = 0; t0 < nC; t0 += 32) {
       const int t = t0 + lane;
       bool hit = false;
@@ -265,179 +357,201 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, WarpScratch& ws
         const int cxi = t - czi * nCX;
         const int cx = b.x0 + cxi, cz = b.z0 + czi;
         float hA, hB, hC, hD;
-        load_cell(f, cx, cz, hA, hB, hC, hD);
+        zcell<SMEM>(zv, cxi, czi, hA, hB, hC, hD);
         const bool fA = finitef(hA), fB = finitef(hB), fC = finitef(hC), fD = finitef(hD);
         const bool cA = fA && hA > b.minB, cB = fB && hB > b.minB, cC = fC && hC > b.minB, cD = fD && hD > b.minB;
         const bool keepUp = (cA || cB || cC) && (fA && fB && fC);
         const bool keepDn = (cB || cC || cD) && (fB && fC && fD);
-        const float xA = cx * f.sW, xB = (cx + 1) * f.sW, zA = cz * f.sD, zC = (cz + 1) * f.sD;
-        if (keepUp && cA) hit = hit || vertex_inside(b, xA, hA, zA);
-        if ((keepUp || keepDn) && cB) hit = hit || vertex_inside(b, xB, hB, zA);
-        if ((keepUp || keepDn) && cC) hit = hit || vertex_inside(b, xA, hC, zC);
-        if (keepDn && cD) hit = hit || vertex_inside(b, xB, hD, zC);
+        // vertex v of the cell (0 A, 1 B, 2 C, 3 D) is tested if it collides and belongs to a kept triangle
+#pragma unroll 1
+        for (int v = 0; v < 4 && !hit; ++v) {
+          const bool cv = v == 0 ? (keepUp && cA) : v == 1 ? ((keepUp || keepDn) && cB) : v == 2 ? ((keepUp || keepDn) && cC) : (keepDn && cD);
+          if (cv) hit = vertex_inside(b, (cx + (v & 1)) * f.sW, v == 0 ? hA : v == 1 ? hB : v == 2 ? hC : hD, (cz + (v >> 1)) * f.sD);
+        }
       }
       if (__any_sync(kFull, hit)) return R_HIT;
     }
   }
 
-  // (4) plane stage (heightfield.cpp:1474-1617). A plane contact point is always a box corner (up to a few
-  // ulps), so only triangles in the cells under the 8 corners (+- cell_margin) can report one.
+  // (4) plane stage (heightfield.cpp:1474-1617)
+  const int T = 2 * (nX - 1) * nCZ;                      // triangles of the zone
+  const bool use_bits = T <= 32 * kBloomWords;           // candidate bitmap over the triangle indices
+  __syncwarp();   // the previous box's reads of this warp's scratch are done (no WAR across boxes)
+#pragma unroll 1
+  for (int i = lane; i < kBloomWords; i += 32) { ws.bloom[i] = 0u; ws.bloom2[i] = 0u; ws.cand_bits[i] = 0u; }
+  __syncwarp();
+  // Task t = lane + 32 * pass: corner (t >> 1) & 7, triangle t & 1 (Up / Down of a cell on neighbouring lanes), sub-cell
+  // t >> 4. A corner has a second / third / fourth candidate cell only when it lies within cell_margin of a cell
+  // boundary, so pass 0 is normally 16 busy lanes and pass 1 is skipped by the whole warp.
+  const int corner = (lane >> 1) & 7, u = lane & 1;
+  float px = b.P[0], pz = b.P[2];
   {
-    __syncwarp();   // the previous box's reads of this warp's scratch are done (no WAR across boxes)
-    for (int i = lane; i < kBloomWords; i += 32) ws.bloom[i] = 0u;
-    __syncwarp();
-    // Task mapping: lane = (half, corner, triangle): lanes 0..15 take sub-cell `2*pass` of corner (lane >> 1) & 7,
-    // lanes 16..31 sub-cell `2*pass + 1`; the Up / Down triangles of a cell go to neighbouring lanes. A corner has a
-    // second / third / fourth candidate cell only when it lies within cell_margin of a cell boundary, so pass 0 is
-    // normally 16 busy lanes and pass 1 is skipped by the whole warp.
-    const int corner = (lane >> 1) & 7, u = lane & 1;
-    float px = b.P[0], pz = b.P[2];
+    const float h0 = 0.5f * b.side[0], h1 = 0.5f * b.side[1], h2 = 0.5f * b.side[2];
+    if (corner & 1) { px += h0 * b.R1[0]; pz += h0 * b.R1[6]; } else { px -= h0 * b.R1[0]; pz -= h0 * b.R1[6]; }
+    if (corner & 2) { px += h1 * b.R1[1]; pz += h1 * b.R1[7]; } else { px -= h1 * b.R1[1]; pz -= h1 * b.R1[7]; }
+    if (corner & 4) { px += h2 * b.R1[2]; pz += h2 * b.R1[8]; } else { px -= h2 * b.R1[2]; pz -= h2 * b.R1[8]; }
+  }
+  const float gx = px * f.iW, gz = pz * f.iD;
+  const int cxl = (int)floorf(gx - cell_margin), cxh = (int)floorf(gx + cell_margin);
+  const int czl = (int)floorf(gz - cell_margin), czh = (int)floorf(gz + cell_margin);
+  bool hit_own = false, pair_possible = false;
+  int nLive = 0, max_live = -1;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const int sub = 2 * pass + (lane >> 4);
+    const int ccx = (sub & 1) ? cxh : cxl, ccz = (sub & 2) ? czh : czl;
+    bool actc = !((sub & 1) && cxh == cxl) && !((sub & 2) && czh == czl);
+    actc = actc && ccx >= b.x0 && ccx < b.x1 && ccz >= b.z0 && ccz < b.z1;
+    if (!__any_sync(kFull, actc)) continue;
+    // an upright box projects its top corners into the cells of the bottom corners: the same triangle twice
     {
-      const float h0 = 0.5f * b.side[0], h1 = 0.5f * b.side[1], h2 = 0.5f * b.side[2];
-      if (corner & 1) { px += h0 * b.R1[0]; pz += h0 * b.R1[6]; } else { px -= h0 * b.R1[0]; pz -= h0 * b.R1[6]; }
-      if (corner & 2) { px += h1 * b.R1[1]; pz += h1 * b.R1[7]; } else { px -= h1 * b.R1[1]; pz -= h1 * b.R1[7]; }
-      if (corner & 4) { px += h2 * b.R1[2]; pz += h2 * b.R1[8]; } else { px -= h2 * b.R1[2]; pz -= h2 * b.R1[8]; }
+      const int pcx = __shfl_xor_sync(kFull, ccx, 8), pcz = __shfl_xor_sync(kFull, ccz, 8);
+      const bool pact = __shfl_xor_sync(kFull, actc, 8);
+      if ((corner & 4) && pact && pcx == ccx && pcz == ccz) actc = false;
     }
-    const float gx = px * f.iW, gz = pz * f.iD;
-    const int cxl = (int)floorf(gx - cell_margin), cxh = (int)floorf(gx + cell_margin);
-    const int czl = (int)floorf(gz - cell_margin), czh = (int)floorf(gz + cell_margin);
-    bool hit_own = false;
-    bool live[2] = {false, false};
-    float lpl[2][4];
-    int lidx[2] = {-1, -1};
-#pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-      const int sub = 2 * pass + (lane >> 4);
-      const int ccx = (sub & 1) ? cxh : cxl, ccz = (sub & 2) ? czh : czl;
-      bool act = !((sub & 1) && cxh == cxl) && !((sub & 2) && czh == czl);
-      act = act && ccx >= b.x0 && ccx < b.x1 && ccz >= b.z0 && ccz < b.z1;
-      if (!__any_sync(kFull, act)) continue;
-      if (act) {
-        float hA, hB, hC, hD;
-        load_cell(f, ccx, ccz, hA, hB, hC, hD);
-        const bool fA = finitef(hA), fB = finitef(hB), fC = finitef(hC), fD = finitef(hD);
-        const bool cA = fA && hA > b.minB, cB = fB && hB > b.minB, cC = fC && hC > b.minB, cD = fD && hD > b.minB;
-        const bool isUp = (u == 0);
-        const bool keep = isUp ? ((cA || cB || cC) && (fA && fB && fC)) : ((cB || cC || cD) && (fB && fC && fD));
-        const int cell_idx = ((ccx - b.x0) * nCZ + (ccz - b.z0)) * 2;   // emission order: x outer, z inner, Up, Down
-        if (keep) {
-          float* pl = lpl[pass];
-          cell_plane(f, isUp, ccx, ccz, hA, hB, hC, hD, pl);
-          // Liveness: any plane within eps of this one changes the box-plane depth by far less than tau.
-          const float Q1 = pl[0] * b.R1[0] + pl[1] * b.R1[3] + pl[2] * b.R1[6];
-          const float Q2 = pl[0] * b.R1[1] + pl[1] * b.R1[4] + pl[2] * b.R1[7];
-          const float Q3 = pl[0] * b.R1[2] + pl[1] * b.R1[5] + pl[2] * b.R1[8];
-          const float B1 = fabsf(b.side[0] * Q1), B2 = fabsf(b.side[1] * Q2), B3 = fabsf(b.side[2] * Q3);
-          const float depth = pl[3] + 0.5f * (B1 + B2 + B3) - (pl[0] * b.P[0] + pl[1] * b.P[1] + pl[2] * b.P[2]);
-          const float tau = 16.0f * ARTP_EPS * (1.0f + b.side[0] + b.side[1] + b.side[2] + fabsf(b.P[0]) +
-                                                fabsf(b.P[1]) + fabsf(b.P[2]) + fabsf(pl[3]));
-          if (depth >= -tau) {   // else dead: no plane of its would-be group can touch the box
-            live[pass] = true;
-            lidx[pass] = cell_idx + u;
-            // bloom keys of every bucket an eps-matching normal may fall into
-            const int kx0 = (int)floorf((pl[0] - kKeyMargin + 1.0f) * kKeyScale), kx1 = (int)floorf((pl[0] + kKeyMargin + 1.0f) * kKeyScale);
-            const int kz0 = (int)floorf((pl[2] - kKeyMargin + 1.0f) * kKeyScale), kz1 = (int)floorf((pl[2] + kKeyMargin + 1.0f) * kKeyScale);
-            for (int kx = kx0; kx <= kx1; ++kx)
-              for (int kz = kz0; kz <= kz1; ++kz) {
-                const uint32_t hsh = bloom_hash(kx, kz);
-                atomicOr(&ws.bloom[hsh >> 5], 1u << (hsh & 31));
+    bool live = false;
+    float pl[4] = {0.f, 0.f, 0.f, 0.f};
+    int idx = -1;
+    if (actc) {
+      float hA, hB, hC, hD;
+      zcell<SMEM>(zv, ccx - b.x0, ccz - b.z0, hA, hB, hC, hD);
+      const bool fA = finitef(hA), fB = finitef(hB), fC = finitef(hC), fD = finitef(hD);
+      const bool cA = fA && hA > b.minB, cB = fB && hB > b.minB, cC = fC && hC > b.minB, cD = fD && hD > b.minB;
+      const bool isUp = (u == 0);
+      const bool keep = isUp ? ((cA || cB || cC) && (fA && fB && fC)) : ((cB || cC || cD) && (fB && fC && fD));
+      if (keep) {
+        cell_plane(f, isUp, ccx, ccz, hA, hB, hC, hD, pl);
+        // Liveness: any plane within eps of this one changes the box-plane depth by far less than tau.
+        const float Q1 = pl[0] * b.R1[0] + pl[1] * b.R1[3] + pl[2] * b.R1[6];
+        const float Q2 = pl[0] * b.R1[1] + pl[1] * b.R1[4] + pl[2] * b.R1[7];
+        const float Q3 = pl[0] * b.R1[2] + pl[1] * b.R1[5] + pl[2] * b.R1[8];
+        const float B1 = fabsf(b.side[0] * Q1), B2 = fabsf(b.side[1] * Q2), B3 = fabsf(b.side[2] * Q3);
+        const float depth = pl[3] + 0.5f * (B1 + B2 + B3) - (pl[0] * b.P[0] + pl[1] * b.P[1] + pl[2] * b.P[2]);
+        const float tau = 16.0f * ARTP_EPS * (1.0f + b.side[0] + b.side[1] + b.side[2] + fabsf(b.P[0]) +
+                                              fabsf(b.P[1]) + fabsf(b.P[2]) + fabsf(pl[3]));
+        if (depth >= -tau) {   // else dead: no plane of its would-be group can touch the box
+          live = true;
+          idx = ((ccx - b.x0) * nCZ + (ccz - b.z0)) * 2 + u;   // emission order: x outer, z inner, Up, Down
+          if (use_bits) atomicOr(&ws.cand_bits[idx >> 5], 1u << (idx & 31));
+          // level-1 keys: every bucket the approximate normal of an eps-matching triangle may fall into;
+          // level-2 keys: every bucket its exact (n0, n2, d) may fall into. The candidate's own level-2 bucket goes in
+          // last (after every candidate of the pass has inserted its neighbour buckets): finding it occupied means
+          // another live candidate may match this one.
+          const int kxc = (int)floorf((pl[0] + 1.0f) * kKeyScale), kzc = (int)floorf((pl[2] + 1.0f) * kKeyScale), kdc = dkey(pl[3]);
+          const int kx0 = (int)floorf((pl[0] - kKeyMargin + 1.0f) * kKeyScale), kx1 = (int)floorf((pl[0] + kKeyMargin + 1.0f) * kKeyScale);
+          const int kz0 = (int)floorf((pl[2] - kKeyMargin + 1.0f) * kKeyScale), kz1 = (int)floorf((pl[2] + kKeyMargin + 1.0f) * kKeyScale);
+          const int kd0 = dkey(pl[3] - 2.0f * ARTP_EPS), kd1 = dkey(pl[3] + 2.0f * ARTP_EPS);
+#pragma unroll 1
+          for (int kx = kx0; kx <= kx1; ++kx)
+#pragma unroll 1
+            for (int kz = kz0; kz <= kz1; ++kz) {
+              const uint32_t hsh = bloom_hash(kx, kz);
+              atomicOr(&ws.bloom[hsh >> 5], 1u << (hsh & 31));
+#pragma unroll 1
+              for (int kd = kd0; kd <= kd1; ++kd) {
+                if (kx == kxc && kz == kzc && kd == kdc) continue;
+                const uint32_t h3 = bloom_hash3(kx, kz, kd);
+                atomicOr(&ws.bloom2[h3 >> 5], 1u << (h3 & 31));
               }
-            // contact points with the triangle's OWN plane (valid if it turns out to be its group base)
-            float cx[4], cz[4];
-            const int nc = box_plane(b, pl, 4, cx, cz);
-            const int tcx = isUp ? ccx : ccx + 1, tcz = isUp ? ccz : ccz + 1;
-            for (int i = 0; i < nc; ++i) hit_own = hit_own || on_tri(f, isUp, tcx, tcz, cx[i], cz[i]);
-          }
+            }
+          // contact points with the triangle's OWN plane (valid if it turns out to be its group base)
+          float cx[4], cz[4];
+          const int nc = box_plane(b, pl, 4, cx, cz);
+          const int tcx = isUp ? ccx : ccx + 1, tcz = isUp ? ccz : ccz + 1;
+#pragma unroll 1
+          for (int i = 0; i < nc; ++i) hit_own = hit_own || on_tri(f, isUp, tcx, tcz, cx[i], cz[i]);
         }
       }
     }
-    // compact the live candidates: [pass 0 of lanes..., pass 1 of lanes...]
-    const unsigned m0 = __ballot_sync(kFull, live[0]), m1 = __ballot_sync(kFull, live[1]);
-    const int nLive = __popc(m0) + __popc(m1);
-    if (nLive == 0) return R_FREE;
-    if (nLive > kMaxCand) return R_DEFER;   // exact fallback; needs > 32 live corner candidates (not seen in practice)
-    const unsigned below = (1u << lane) - 1u;
-    if (live[0]) {
-      const int p = __popc(m0 & below);
-      ws.cpl[p][0] = lpl[0][0]; ws.cpl[p][1] = lpl[0][1]; ws.cpl[p][2] = lpl[0][2]; ws.cpl[p][3] = lpl[0][3];
-      ws.cidx[p] = lidx[0];
-    }
-    if (live[1]) {
-      const int p = __popc(m0) + __popc(m1 & below);
-      ws.cpl[p][0] = lpl[1][0]; ws.cpl[p][1] = lpl[1][1]; ws.cpl[p][2] = lpl[1][2]; ws.cpl[p][3] = lpl[1][3];
-      ws.cidx[p] = lidx[1];
-    }
     __syncwarp();
-
-    // (5) is any live candidate epsilon-mergeable with an EARLIER kept triangle? (greedy grouping,
-    // heightfield.cpp:1511-1556: a triangle is absorbed only by an earlier base that matches it.)
-    int max_live = max(lidx[0], lidx[1]);
+    if (live) {
+      const uint32_t h3 = bloom_hash3((int)floorf((pl[0] + 1.0f) * kKeyScale), (int)floorf((pl[2] + 1.0f) * kKeyScale), dkey(pl[3]));
+      if ((atomicOr(&ws.bloom2[h3 >> 5], 1u << (h3 & 31)) >> (h3 & 31)) & 1u) pair_possible = true;
+    }
+    // append this pass's live candidates to the list
+    const unsigned lm = __ballot_sync(kFull, live);
+    if (nLive + __popc(lm) > kMaxCand) return R_DEFER;   // exact fallback (not seen in practice)
+    if (live) {
+      const int p = nLive + __popc(lm & ((1u << lane) - 1u));
+      ws.cpl[p][0] = pl[0]; ws.cpl[p][1] = pl[1]; ws.cpl[p][2] = pl[2]; ws.cpl[p][3] = pl[3];
+      ws.cidx[p] = idx;
+    }
+    nLive += __popc(lm);
+    max_live = max(max_live, idx);
+  }
+  if (nLive == 0) return R_FREE;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) max_live = max(max_live, __shfl_xor_sync(kFull, max_live, o));
+  for (int o = 16; o > 0; o >>= 1) max_live = max(max_live, __shfl_xor_sync(kFull, max_live, o));
+  __syncwarp();
+  if (!use_bits) pair_possible = true;
+  if (__any_sync(kFull, pair_possible)) {
+    // candidate against candidate, exactly: any two matching live candidates => one may absorb the other
     bool merge = false;
-    for (int t0 = 0; t0 < nC; t0 += 32) {
+    if (lane < nLive) {
+#pragma unroll 1
+      for (int j = 0; j < nLive; ++j)
+        if (ws.cidx[j] != ws.cidx[lane] && plane_match(ws.cpl[lane], ws.cpl[j])) merge = true;
+    }
+    if (__any_sync(kFull, merge)) return R_DEFER;
+  }
+
+  // (5) merge screen over the regions: one cell per lane
+#pragma unroll 1
+  for (unsigned long long m = act; m; m &= m - 1) {
+    int lx0, lz0, rw, rh;
+    region(__ffsll((long long)m) - 1, lx0, lz0, rw, rh);
+    if ((lx0 * nCZ + lz0) * 2 >= max_live) continue;       // the whole region is emitted after the last live candidate
+    const int cw = rw - 1, n = cw * (rh - 1);
+    const uint32_t magicW = magic_for(cw);
+#pragma unroll 1
+    for (int t0 = 0; t0 < n; t0 += 32) {
       const int t = t0 + lane;
-      bool flag[2] = {false, false};
-      float fpl[2][4];
-      int fidx[2] = {0, 0};
-      if (t < nC) {
-        const int czi = (nCX > 1) ? (int)__umulhi((uint32_t)t, magicC) : t;
-        const int cxi = t - czi * nCX;
+      bool merge = false;
+      if (t < n) {
+        const int q = (cw > 1) ? (int)__umulhi((uint32_t)t, magicW) : t;
+        const int cxi = lx0 + t - q * cw, czi = lz0 + q;
         const int cell_idx = (cxi * nCZ + czi) * 2;
         if (cell_idx < max_live) {   // only triangles emitted before the last live candidate can absorb one
           const int cx = b.x0 + cxi, cz = b.z0 + czi;
           float hA, hB, hC, hD;
-          load_cell(f, cx, cz, hA, hB, hC, hD);
+          zcell<SMEM>(zv, cxi, czi, hA, hB, hC, hD);
           const bool fA = finitef(hA), fB = finitef(hB), fC = finitef(hC), fD = finitef(hD);
           const bool cA = fA && hA > b.minB, cB = fB && hB > b.minB, cC = fC && hC > b.minB, cD = fD && hD > b.minB;
-          const bool keep[2] = {(cA || cB || cC) && (fA && fB && fC), (cB || cC || cD) && (fB && fC && fD)};
-          if (keep[0] || keep[1]) {
+          const bool keepUp = (cA || cB || cC) && (fA && fB && fC), keepDn = (cB || cC || cD) && (fB && fC && fD);
+          if (keepUp || keepDn) {
             const float xA = cx * f.sW, xB = (cx + 1) * f.sW, zA = cz * f.sD, zC = (cz + 1) * f.sD;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              if (!keep[u] || cell_idx + u >= max_live) continue;
-              float c0, c1, c2;   // value-identical to tri_plane's cross product (zero terms dropped)
-              if (u == 0) {   // Up (A,B,C): E1 = C-A = (0, hC-hA, zC-zA), E2 = B-A = (xB-xA, hB-hA, 0); c = E1 x E2
-                const float e1y = hC - hA, e1z = zC - zA, e2x = xB - xA, e2y = hB - hA;
-                c0 = -(e1z * e2y); c1 = e1z * e2x; c2 = -(e1y * e2x);
-              } else {        // Down (D,B,C): E1 = C-D = (xA-xB, hC-hD, 0), E2 = B-D = (0, hB-hD, zA-zC); c = E2 x E1
-                const float e1x = xA - xB, e1y = hC - hD, e2y = hB - hD, e2z = zA - zC;
-                c0 = -(e2z * e1y); c1 = e2z * e1x; c2 = -(e2y * e1x);
-              }
+#pragma unroll 1
+            for (int uu = 0; uu < 2; ++uu) {
+              const int idx = cell_idx + uu;
+              if (!(uu == 0 ? keepUp : keepDn) || idx >= max_live) continue;
+              if (use_bits && ((ws.cand_bits[idx >> 5] >> (idx & 31)) & 1u)) continue;   // live candidates: handled above
+              // approximate normal (cross product value-identical to tri_plane's, zero terms dropped):
+              // Up (A,B,C): E1 = C-A, E2 = B-A, c = E1 x E2;  Down (D,B,C): E1 = C-D, E2 = B-D, c = E2 x E1
+              const float ey = uu == 0 ? hC - hA : hB - hD, ez = uu == 0 ? zC - zA : zA - zC;
+              const float gx2 = uu == 0 ? xB - xA : xA - xB, gy = uu == 0 ? hB - hA : hC - hD;
+              const float c0 = -(ez * gy), c1 = ez * gx2, c2 = -(ey * gx2);
               const float r = rsqrtf(c0 * c0 + c1 * c1 + c2 * c2);
-              const int kx = (int)floorf((c0 * r + 1.0f) * kKeyScale), kz = (int)floorf((c2 * r + 1.0f) * kKeyScale);
-              const uint32_t hsh = bloom_hash(kx, kz);
+              const uint32_t hsh = bloom_hash((int)floorf((c0 * r + 1.0f) * kKeyScale), (int)floorf((c2 * r + 1.0f) * kKeyScale));
               if (ws.bloom[hsh >> 5] & (1u << (hsh & 31))) {
-                flag[u] = true;
-                fidx[u] = cell_idx + u;
-                cell_plane(f, u == 0, cx, cz, hA, hB, hC, hD, fpl[u]);
+                float plm[4];   // flagged: exact plane, level-2 buckets
+                cell_plane(f, uu == 0, cx, cz, hA, hB, hC, hD, plm);
+                const uint32_t h3 = bloom_hash3((int)floorf((plm[0] + 1.0f) * kKeyScale), (int)floorf((plm[2] + 1.0f) * kKeyScale), dkey(plm[3]));
+                if (ws.bloom2[h3 >> 5] & (1u << (h3 & 31))) {
+#pragma unroll 1
+                  for (int sidx = 0; sidx < nLive; ++sidx)
+                    if (ws.cidx[sidx] > idx && plane_match(plm, ws.cpl[sidx])) merge = true;
+                }
               }
             }
           }
         }
       }
-      // flagged triangles are compared warp-cooperatively: one flagged plane is broadcast, lane s (and s + 32)
-      // checks it against live candidate s
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        unsigned fm = __ballot_sync(kFull, flag[u]);
-        while (fm) {
-          const int src = __ffs(fm) - 1;
-          fm &= fm - 1;
-          float pl[4];
-          pl[0] = __shfl_sync(kFull, fpl[u][0], src); pl[1] = __shfl_sync(kFull, fpl[u][1], src);
-          pl[2] = __shfl_sync(kFull, fpl[u][2], src); pl[3] = __shfl_sync(kFull, fpl[u][3], src);
-          const int idx = __shfl_sync(kFull, fidx[u], src);
-          for (int sidx = lane; sidx < nLive; sidx += 32)
-            if (ws.cidx[sidx] > idx && plane_match(pl, ws.cpl[sidx])) merge = true;
-        }
-      }
       if (__any_sync(kFull, merge)) return R_DEFER;
     }
-    const int res = __any_sync(kFull, hit_own) ? R_HIT : R_FREE;
-    __syncwarp();   // scratch is reused by the next box
-    return res;
   }
+  const int res = __any_sync(kFull, hit_own) ? R_HIT : R_FREE;
+  __syncwarp();   // scratch is reused by the next box
+  return res;
 }
 
 // One queued box (80 bytes): everything stage B/C need, so nothing is recomputed.
@@ -580,8 +694,8 @@ classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs_w
   const bool in_range = item < w.n_items;
   const int lane = threadIdx.x & 31;
   int result = 1;                 // 1 valid so far, 0 invalid
-  int n_w = 0, n_f = 0;           // undecided boxes of this item for the warp stage / the thread-level reach stages
-  BoxCtx ub[5];                   // their contexts: warp-stage boxes from the front, reach-stage boxes from the back
+  int n_w = 0, n_f = 0;           // undecided boxes of this item for the big-tile queue / the reach-box queue
+  BoxCtx ub[5];                   // their contexts: big-tile boxes from the front, reach boxes from the back
   uint32_t uflags[5];
   float R1[9];
   uint32_t slot = 0;
@@ -607,8 +721,9 @@ classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs_w
         continue;
       }
       if (r == -1) {
-        // reach boxes whose table-reduced zone fits the TMA tile take the thread-level stages
-        const bool thread_path = foot && !(fl & REC_NEEDS_REDUCE) && (b.x1 - b.x0) + 3 < c.reach_tw && (b.z1 - b.z0) < c.reach_th;   // tile origin = x0 & ~3
+        // reach boxes go to their own queue (small TMA tiles); the torso -- and a reach box whose zone would not fit the
+        // small tile -- to the big-tile queue
+        const bool thread_path = foot && (b.x1 - b.x0) + 4 <= c.reach_tw && (b.z1 - b.z0) + 1 <= c.reach_th;
         const int q = thread_path ? 4 - n_f++ : n_w++;
         ub[q] = b; uflags[q] = fl;
       }
@@ -648,58 +763,6 @@ classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs_w
     o.minB = b.minB; o.maxB = b.maxB;
     o.x0 = b.x0; o.x1 = b.x1; o.z0 = b.z0; o.z1 = b.z1;
     o.item = item; o.flags = uflags[src];
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Stage B: one warp per queued box.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
-box_items_warp_kernel(const Checker c, const Work w, const BoxRec* __restrict__ recs,
-                      const uint32_t* __restrict__ rec_count, uint32_t* __restrict__ work_counter,
-                      uint32_t* __restrict__ defer_count, uint32_t* __restrict__ defer_list, int force_defer) {
-  __shared__ WarpScratch ws_all[kWarpsPerCta];
-  const int lane = threadIdx.x & 31;
-  WarpScratch& ws = ws_all[threadIdx.x >> 5];
-  const uint32_t total = *rec_count;
-  constexpr uint32_t kChunk = 4;   // records claimed per atomic
-  for (;;) {
-    uint32_t r0 = 0;
-    if (lane == 0) r0 = atomicAdd(work_counter, kChunk);
-    r0 = __shfl_sync(kFull, r0, 0);
-    if (r0 >= total) break;
-    const uint32_t r1 = min(r0 + kChunk, total);
-    for (uint32_t ri = r0; ri < r1; ++ri) {
-    // every lane reads the whole 80-byte record itself: five 16-byte loads from one address per warp (a broadcast
-    // transaction each) instead of one load + 20 shuffles
-    BoxRec r;
-    {
-      const uint4* rp = reinterpret_cast<const uint4*>(recs + ri);
-      uint4* dst = reinterpret_cast<uint4*>(&r);
-#pragma unroll
-      for (int i = 0; i < 5; ++i) dst[i] = __ldg(rp + i);
-    }
-    const uint32_t slot = item_slot(w, r.item);
-    if (w.edge_mode) {   // the edge already failed on another state/box: nothing can change it (perf only; order-free)
-      int dead = 0;
-      if (lane == 0) dead = (*(volatile uint8_t*)(w.valid + slot) == 0);
-      if (__shfl_sync(kFull, dead, 0)) continue;
-    }
-    const bool foot = (r.flags & 7) != 0;
-    int res;
-    if (force_defer) {
-      res = R_DEFER;
-    } else {
-      BoxCtx b;
-      rec_to_ctx(c, r, b);
-      res = box_collide_warp(foot ? c.f[1] : c.f[0], b, ws, lane, c.cell_margin, (r.flags & REC_NEEDS_REDUCE) != 0,
-                             (r.flags & REC_ALLFINITE) != 0);
-    }
-    if (lane == 0) {
-      if (res == R_DEFER) defer_list[atomicAdd(defer_count, 1u)] = ri;
-      else if ((!foot && res == R_HIT) || (foot && res == R_FREE)) w.valid[slot] = 0;
-    }
-    }
   }
 }
 
@@ -964,8 +1027,10 @@ pose_small_kernel(const Checker c, const SmallBatch sb, uint8_t* __restrict__ ou
   }
   if (valid && !force_all && wid < 5 && s_res[wid] == -1) {
     const bool foot = wid > 0;
-    const int res = box_collide_warp(foot ? c.f[1] : c.f[0], s_box[wid], s_ws[wid], lane, c.cell_margin,
-                                     (s_fl[wid] & REC_NEEDS_REDUCE) != 0, (s_fl[wid] & REC_ALLFINITE) != 0);
+    const Field& fw = foot ? c.f[1] : c.f[0];
+    const ZoneView zv{fw.H + (size_t)s_box[wid].z0 * fw.pitch + s_box[wid].x0, fw.pitch};   // straight from the heightfield
+    const int res = box_collide_warp<false>(fw, s_box[wid], zv, s_ws[wid], lane, c.cell_margin,
+                                            (s_fl[wid] & REC_NEEDS_REDUCE) != 0, (s_fl[wid] & REC_ALLFINITE) != 0);
     if (lane == 0) s_res2[wid] = res;
   }
   __syncthreads();

@@ -170,10 +170,10 @@ def pose_workload(torch, chk, flush, m, poses, steps, ref, kind, port, n_mt=400_
     t0 = time.perf_counter(); vm = ref.check_poses_mt(poses[:n_mt], cores); tm = time.perf_counter() - t0
     _, zv = port.check_poses(poses[:50_000], want_zone=True)
     return {"map": m.desc, "poses": n, "poses_per_s": n * steps / (tot * 1e-3), "ms_per_step": tot / steps,
-            "classify_ms": float(k[0]), "warp_stage_ms": float(k[1]), "reach_vertex_ms": float(k[2]),
-            "reach_plane_ms": float(k[3]), "group_stage_ms": float(k[4]), "pass_ms": float(k.sum()),
+            "classify_ms": float(k[0]), "torso_queue_ms": float(k[1]), "reach_queue_ms": float(k[2]),
+            "group_stage_ms": float(k[4]), "pass_ms": float(k.sum()),
             "queued_boxes": st["last_queued_boxes"], "queued_warp_stage": st["last_queued_warp_stage"],
-            "queued_reach_stage": st["last_queued_reach_stage"], "reach_plane_stage": st["last_reach_plane_stage"],
+            "queued_reach_stage": st["last_queued_reach_stage"],
             "deferred_boxes": st["last_deferred"],
             "valid_fraction": float(got.mean()), "exit_mix": exit_mix(port, poses[:20_000]),
             "algorithmic_bytes_per_pose": 57.0 + 4.0 * float(zv.mean()),
@@ -561,11 +561,10 @@ def main():
                          "classify_kernel_ms": k0, "group_kernel_ms": k2, "pass_ms": k0 + k1 + k2,
                          "achieved_dominant_kernel_alone": achieved_dom,
                          "queued_boxes": int(queued), "deferred_boxes": int(deferred),
-                         "stage_ms": dict(zip(("classify", "warp_stage", "reach_vertex", "reach_plane", "group"),
+                         "stage_ms": dict(zip(("classify", "torso_queue", "reach_queue", "unused", "group"),
                                               [float(x) for x in np.mean(np.array(stage_ms), 0)])),
                          "queued_warp_stage": stats_last["last_queued_warp_stage"],
                          "queued_reach_stage": stats_last["last_queued_reach_stage"],
-                         "reach_plane_stage": stats_last["last_reach_plane_stage"],
                          "actual_dram_GBps_dominant_kernel": (traffic / (k1 * 1e-3) / 1e9) if traffic else None,
                          "note": "achieved = ALGORITHMIC bytes (the zone vertices the reference scans, SURVEY 8d) / sum of "
                                  "the three stage durations; the range tables and vertex probes answer most of those scans "

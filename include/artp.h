@@ -80,9 +80,9 @@ typedef struct artp_stats {
   uint32_t last_deferred;      /* deferred count of the most recent check call */
   uint32_t last_launches;      /* kernels launched by the most recent call */
   uint32_t last_queued_boxes;  /* boxes the classify stage queued for the later stages in the most recent call's last round */
-  uint32_t last_queued_warp_stage;   /* ... of which for the warp stage (torso boxes, reach boxes of unusual size) */
-  uint32_t last_queued_reach_stage;  /* ... of which for the thread-level reach-box stages */
-  uint32_t last_reach_plane_stage;   /* reach boxes that survived the vertex scan and ran the plane stage */
+  uint32_t last_queued_warp_stage;   /* ... of which in the big-tile queue (torso boxes, reach boxes of unusual size) */
+  uint32_t last_queued_reach_stage;  /* ... of which in the reach-box queue (small tiles) */
+  uint32_t last_reach_plane_stage;   /* reserved (0) */
 } artp_stats;
 
 int  artp_create(const artp_params* params, artp_handle** out);
@@ -216,7 +216,7 @@ int artp_debug_set_group_capacity(artp_handle* h, int max_triangles);
  * ms3[0..2] = classify (thread/item), box stages (warp stage + reach-box stages), plane-grouping block stage, in ms. */
 int artp_set_timing(artp_handle* h, int enable);
 int artp_get_last_timing(artp_handle* h, float* ms3);
-/* Per-stage form: ms5 = classify, warp stage (torso boxes), reach vertex scan, reach plane stage, plane grouping. */
+/* Per-stage form: ms5 = classify, big-tile queue (torso boxes), reach-box queue, 0, plane grouping. */
 int artp_get_last_stage_timing(artp_handle* h, float* ms5);
 
 /* Test hook: 0 = normal (classify -> warp stage -> grouping stage for deferred boxes),
