@@ -55,7 +55,7 @@ struct Handle {
   int k1_grid = 0, k2_grid = 0, k2_smem = 0, k2_tcap = 0;
   // stage B (artp_tiles.cuh): [0] big tiles (torso queue, 4 warps per CTA), [1] small tiles (reach-box queue, 8 warps)
   artp::TileCfg tile_cfg[2] = {};
-  int tile_grid[2] = {0, 0}, tile_smem[2] = {0, 0}, tile_warps[2] = {4, 8};
+  int tile_grid[2] = {0, 0}, tile_smem[2] = {0, 0}, tile_warps[2] = {8, 8};
   CUtensorMap tile_map[2][2];       // [cfg][layer]: 2-D tile maps over elevation / elevation_masked
   int k0_flags = 0;                 // tuning switch of the classify stage (env ARTP_K0_FLAGS: 2 = no vertex probes)
   int mode = 0;
@@ -115,8 +115,8 @@ __global__ void reverse_columns_kernel(const float* __restrict__ layer, float* _
 // starting at (x,z) = op of the four 2^(k-1) windows at offsets {0,half} (clamped at the border; clamped windows
 // are never queried). (max over all h, min over finite h or +inf, any non-finite).
 __global__ void build_level_kernel(const float* __restrict__ H, const float2* __restrict__ prevT,
-                                   const unsigned char* __restrict__ prevNF, float2* __restrict__ T,
-                                   unsigned char* __restrict__ NF, int nx, int nz, int pitch, int half) {
+                                   const unsigned char* __restrict__ prevNF, const unsigned char* __restrict__ mergeable,
+                                   float2* __restrict__ T, unsigned char* __restrict__ NF, int nx, int nz, int pitch, int half) {
   const size_t total = (size_t)pitch * nz;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int z = (int)(i / pitch), x = (int)(i - (size_t)z * pitch);
@@ -133,11 +133,95 @@ __global__ void build_level_kernel(const float* __restrict__ H, const float2* __
       } else {
         const float h = H[id[q]];
         mx = fmaxf(mx, h);
-        if (fabsf(h) < CUDART_INF_F) mn = fminf(mn, h); else nf = 1;
+        if (fabsf(h) < CUDART_INF_F) mn = fminf(mn, h); else nf |= 1;
+        nf |= mergeable[id[q]];      // 0 or 2: the cell starting at this vertex holds a mergeable triangle
       }
     }
     T[i] = make_float2(mx, mn);
     NF[i] = nf;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Plane tables: which cells hold a triangle whose plane equals (within eps, the greedy grouping's test,
+// heightfield.cpp:1541-1546) the plane of ANOTHER triangle of the layer? A zone without such a cell cannot merge
+// anything: every kept triangle is its own plane group whatever the box, and the warp stage skips its merge screen.
+// All triangle planes (exact, the collider's arithmetic) go into a hash table keyed by their (n0, n2, d) buckets; a
+// second pass looks every triangle's +-2 eps neighbour buckets up. Natural terrain flags nothing; flat or terraced
+// maps flag almost everything and keep the screen / the exact grouping stage.
+struct PlaneSlot { unsigned long long key; uint32_t lo, hi; };
+constexpr unsigned long long kEmptyKey = ~0ull;
+__device__ __forceinline__ unsigned long long plane_key(int kx, int kz, int kd) {
+  return ((unsigned long long)(uint32_t)(kx & 0xffff) << 48) | ((unsigned long long)(uint32_t)(kz & 0xffff) << 32) | (uint32_t)kd;
+}
+__device__ __forceinline__ uint32_t plane_slot_hash(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return (uint32_t)k;
+}
+__global__ void plane_table_clear_kernel(PlaneSlot* tab, size_t cap) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
+    tab[i].key = kEmptyKey; tab[i].lo = 0xffffffffu; tab[i].hi = 0u;
+  }
+}
+// Exact plane of triangle u of cell (x, z), or false if one of its vertices is not finite (never kept).
+__device__ __forceinline__ bool cell_tri_plane(const artp::Field& f, int x, int z, int u, float pl[4]) {
+  float hA, hB, hC, hD;
+  artp::load_cell(f, x, z, hA, hB, hC, hD);
+  const bool ok = u == 0 ? (artp::finitef(hA) && artp::finitef(hB) && artp::finitef(hC))
+                         : (artp::finitef(hD) && artp::finitef(hB) && artp::finitef(hC));
+  if (!ok) return false;
+  artp::cell_plane(f, u == 0, x, z, hA, hB, hC, hD, pl);
+  return true;
+}
+__global__ void plane_table_insert_kernel(const artp::Field f, PlaneSlot* tab, uint32_t mask) {
+  const size_t ncell = (size_t)(f.nx - 1) * (f.nz - 1);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < 2 * ncell; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t c = i >> 1;
+    const int u = (int)(i & 1), z = (int)(c / (f.nx - 1)), x = (int)(c - (size_t)z * (f.nx - 1));
+    float pl[4];
+    if (!cell_tri_plane(f, x, z, u, pl)) continue;
+    const uint32_t id = (uint32_t)(((size_t)z * f.pitch + x) * 2 + u);
+    const unsigned long long key = plane_key((int)floorf((pl[0] + 1.0f) * artp::kKeyScale), (int)floorf((pl[2] + 1.0f) * artp::kKeyScale),
+                                             artp::dkey(pl[3]));
+    uint32_t s = plane_slot_hash(key) & mask;
+    for (;;) {
+      const unsigned long long old = atomicCAS(&tab[s].key, kEmptyKey, key);
+      if (old == kEmptyKey || old == key) {
+        // (lo, hi) only has to tell "one triangle" from "several": skip the atomics once id lies strictly inside
+        if (!(tab[s].lo < id && tab[s].hi > id)) { atomicMin(&tab[s].lo, id); atomicMax(&tab[s].hi, id); }
+        break;
+      }
+      s = (s + 1) & mask;
+    }
+  }
+}
+__global__ void plane_table_query_kernel(const artp::Field f, const PlaneSlot* __restrict__ tab, uint32_t mask,
+                                         unsigned char* __restrict__ mergeable) {
+  const size_t ncell = (size_t)(f.nx - 1) * (f.nz - 1);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < 2 * ncell; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t c = i >> 1;
+    const int u = (int)(i & 1), z = (int)(c / (f.nx - 1)), x = (int)(c - (size_t)z * (f.nx - 1));
+    float pl[4];
+    if (!cell_tri_plane(f, x, z, u, pl)) continue;
+    const uint32_t id = (uint32_t)(((size_t)z * f.pitch + x) * 2 + u);
+    const float e2 = 2.0f * ARTP_EPS;
+    const int kx0 = (int)floorf((pl[0] - e2 + 1.0f) * artp::kKeyScale), kx1 = (int)floorf((pl[0] + e2 + 1.0f) * artp::kKeyScale);
+    const int kz0 = (int)floorf((pl[2] - e2 + 1.0f) * artp::kKeyScale), kz1 = (int)floorf((pl[2] + e2 + 1.0f) * artp::kKeyScale);
+    const int kd0 = artp::dkey(pl[3] - e2), kd1 = artp::dkey(pl[3] + e2);
+    bool dup = false;
+    for (int kx = kx0; kx <= kx1 && !dup; ++kx)
+      for (int kz = kz0; kz <= kz1 && !dup; ++kz)
+        for (int kd = kd0; kd <= kd1 && !dup; ++kd) {
+          const unsigned long long key = plane_key(kx, kz, kd);
+          uint32_t s = plane_slot_hash(key) & mask;
+          for (;;) {
+            const unsigned long long k = tab[s].key;
+            if (k == kEmptyKey) break;
+            if (k == key) { dup = tab[s].lo != id || tab[s].hi != id; break; }
+            s = (s + 1) & mask;
+          }
+        }
+    if (dup) mergeable[(size_t)z * f.pitch + x] = 2;   // races write the same value
   }
 }
 
@@ -619,20 +703,35 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
   int rc = ensure_stage(h, ncell * sizeof(float));
   if (rc) return rc;
   const float* src[2] = {elevation, elevation_masked};
+  // plane tables (temporary): 4 slots per cell = load factor 0.5 for the 2 triangles of a cell
+  size_t cap = 1;
+  while (cap < 4 * ncell) cap <<= 1;
+  PlaneSlot* d_tab = nullptr;
+  unsigned char* d_merge = nullptr;
+  CU_TRY(h, cudaMalloc(&d_tab, cap * sizeof(PlaneSlot)));
+  if (cudaMalloc(&d_merge, npad) != cudaSuccess) { cudaFree(d_tab); h->err = "cudaMalloc (plane tables)"; return ARTP_E_CUDA; }
   for (int k = 0; k < 2; ++k) {
     CU_TRY(h, cudaMemcpyAsync(h->d_stage, src[k], ncell * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     reverse_columns_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>((const float*)h->d_stage, h->d_H[k], rows, cols, pitch);
     CU_TRY(h, cudaGetLastError());
-    h->stats.kernel_launches += 1;
+    artp::Field fk = f;
+    fk.H = h->d_H[k]; fk.pitch = pitch;
+    plane_table_clear_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(d_tab, cap);
+    CU_TRY(h, cudaMemsetAsync(d_merge, 0, npad, h->stream));
+    plane_table_insert_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(fk, d_tab, (uint32_t)(cap - 1));
+    plane_table_query_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(fk, d_tab, (uint32_t)(cap - 1), d_merge);
+    CU_TRY(h, cudaGetLastError());
+    h->stats.kernel_launches += 4;
     for (int l = 1; l <= kmax[k]; ++l) {
       build_level_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_H[k], l > 1 ? h->d_T[k][l - 1] : nullptr,
-                                                                  l > 1 ? h->d_NF[k][l - 1] : nullptr, h->d_T[k][l],
+                                                                  l > 1 ? h->d_NF[k][l - 1] : nullptr, d_merge, h->d_T[k][l],
                                                                   h->d_NF[k][l], rows, cols, pitch, 1 << (l - 1));
       CU_TRY(h, cudaGetLastError());
       h->stats.kernel_launches += 1;
     }
   }
   CU_TRY(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d_tab); cudaFree(d_merge);
   h->rows = rows; h->cols = cols; h->pitch = pitch;
   f.pitch = pitch;
   for (int k = 0; k < 2; ++k) {
@@ -662,13 +761,15 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
       tw = std::min(tw, 256); th = std::min(th, 256);
       artp::TileCfg tc;
       tc.tw = tw; tc.th = th; tc.bytes = (uint32_t)tw * th * 4; tc.stride = (tc.bytes + 127u) & ~127u;
-      int wpc = q == 0 ? 4 : 8;
-      while (wpc > 1 && (size_t)wpc * 2 * tc.stride + 128 > 160 * 1024) wpc >>= 1;
-      const size_t smem = (size_t)wpc * 2 * tc.stride + 128;
-      if (smem > 200 * 1024) {
+      // big tiles: one slot per warp (three 8-warp CTAs per SM hide the copy latency better than a second 7 KB slot);
+      // small tiles: two slots, the next box's tile is in flight while this one is decided
+      tc.slots = (tc.stride > 2048) ? 1 : 2;
+      int wpc = 8;
+      while (wpc > 1 && (size_t)wpc * tc.slots * tc.stride + 128 > 72 * 1024) wpc >>= 1;
+      if ((size_t)wpc * tc.slots * tc.stride + 128 > 200 * 1024) {
         if (q == 1) continue;              // no reach-box queue: everything takes the big-tile queue
         // boxes this large relative to the cells: tiles capped, oversized zones go to the grouping stage
-        tc.tw = 64; tc.th = 64; tc.bytes = 64 * 64 * 4; tc.stride = tc.bytes; wpc = 4;
+        tc.tw = 64; tc.th = 64; tc.bytes = 64 * 64 * 4; tc.stride = tc.bytes; tc.slots = 1; wpc = 4;
       }
       const cuuint64_t gdim[2] = {(cuuint64_t)pitch, (cuuint64_t)cols};
       const cuuint64_t gstr[1] = {(cuuint64_t)pitch * sizeof(float)};
@@ -681,7 +782,7 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
         if (cr != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")"; return ARTP_E_CUDA; }
       }
       h->tile_cfg[q] = tc; h->tile_warps[q] = wpc;
-      h->tile_smem[q] = (int)((size_t)wpc * 2 * tc.stride + 128);
+      h->tile_smem[q] = (int)((size_t)wpc * tc.slots * tc.stride + 128);
       if (q == 1) { h->chk.reach_tw = tc.tw; h->chk.reach_th = tc.th; }
     }
     const int smax = std::max(h->tile_smem[0], h->tile_smem[1]);

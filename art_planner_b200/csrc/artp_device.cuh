@@ -23,7 +23,8 @@ struct Field {
   int pitch;       // row stride in floats (multiple of 4 -> 16 B aligned rows)
   // Range tables (exact, idempotent reductions): level k holds, for every (x,z), the reduction over the
   // 2^k x 2^k vertex window starting there: T[k][x + z*pitch] = (max h, min over finite h or +inf),
-  // NF[k][x + z*pitch] = 1 if the window holds a non-finite height. Built at artp_set_map for k = 1..kmax.
+  // NF[k][x + z*pitch]: bit 0 = the window holds a non-finite height, bit 1 = a cell starting in the window has a
+  // triangle whose plane matches (within eps) the plane of another triangle of the map. Built at artp_set_map, k = 1..kmax.
   const float2* T[kMaxLevel + 1];
   const unsigned char* NF[kMaxLevel + 1];
   int kmax;

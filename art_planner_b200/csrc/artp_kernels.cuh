@@ -188,7 +188,7 @@ __device__ __forceinline__ void zone_reduce(const Field& f, const BoxCtx& b, int
       const size_t idx = (size_t)zs * f.pitch + xs;
       const float2 v = __ldg(f.T[k] + idx);
       mx = v.x; mn = v.y;
-      fin = __ldg(f.NF[k] + idx) == 0;
+      fin = (__ldg(f.NF[k] + idx) & 1) == 0;
     }
   } else {
     const int nV = nX * nZ;
@@ -252,7 +252,7 @@ __device__ __forceinline__ int dkey(float d) { return (int)floorf(fminf(fmaxf(d,
 // cycles per issue): one region loop serves both the windowed and the flat case, nothing is unrolled.
 template <bool SMEM>
 __device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView& zv, WarpScratch& ws, int lane,
-                                float cell_margin, bool needs_reduce, bool all_finite_known) {
+                                float cell_margin, bool needs_reduce, bool all_finite_known, bool merge_free) {
   const int nX = b.x1 - b.x0 + 1, nZ = b.z1 - b.z0 + 1;
   const int nV = nX * nZ;
 
@@ -304,9 +304,12 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView&
     }
     if (act == 0ull) return R_FREE;   // no vertex above the box bottom: no colliding vertex, no kept triangle
   }
+  // neighbouring windows share a row / column of vertices: when most of them are active one pass over the zone is cheaper
+  const bool by_window = windowed && 3 * __popcll(act) <= 2 * nWx * nWz;
+  if (!by_window) act = 1ull;
   // region r of the walk: origin (lx0, lz0) and extent (rw, rh) in vertices
   auto region = [&](int wi, int& lx0, int& lz0, int& rw, int& rh) {
-    if (windowed) {
+    if (by_window) {
       const int wz = wi / nWx, wx = wi - wz * nWx;
       lx0 = min(7 * wx, nX - 8); lz0 = min(7 * wz, nZ - 8); rw = 8; rh = 8;
     } else { lx0 = 0; lz0 = 0; rw = nX; rh = nZ; }
@@ -376,9 +379,13 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView&
   // (4) plane stage (heightfield.cpp:1474-1617)
   const int T = 2 * (nX - 1) * nCZ;                      // triangles of the zone
   const bool use_bits = T <= 32 * kBloomWords;           // candidate bitmap over the triangle indices
+  // merge_free: the map's plane tables (artp_set_map) say that no two triangles of this zone lie in one plane (within
+  // eps): every kept triangle is its own group, no screen is needed -- the normal case on natural terrain.
   __syncwarp();   // the previous box's reads of this warp's scratch are done (no WAR across boxes)
+  if (!merge_free) {
 #pragma unroll 1
-  for (int i = lane; i < kBloomWords; i += 32) { ws.bloom[i] = 0u; ws.bloom2[i] = 0u; ws.cand_bits[i] = 0u; }
+    for (int i = lane; i < kBloomWords; i += 32) { ws.bloom[i] = 0u; ws.bloom2[i] = 0u; ws.cand_bits[i] = 0u; }
+  }
   __syncwarp();
   // Task t = lane + 32 * pass: corner (t >> 1) & 7, triangle t & 1 (Up / Down of a cell on neighbouring lanes), sub-cell
   // t >> 4. A corner has a second / third / fourth candidate cell only when it lies within cell_margin of a cell
@@ -432,6 +439,7 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView&
         if (depth >= -tau) {   // else dead: no plane of its would-be group can touch the box
           live = true;
           idx = ((ccx - b.x0) * nCZ + (ccz - b.z0)) * 2 + u;   // emission order: x outer, z inner, Up, Down
+          if (!merge_free) {
           if (use_bits) atomicOr(&ws.cand_bits[idx >> 5], 1u << (idx & 31));
           // level-1 keys: every bucket the approximate normal of an eps-matching triangle may fall into;
           // level-2 keys: every bucket its exact (n0, n2, d) may fall into. The candidate's own level-2 bucket goes in
@@ -454,6 +462,7 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView&
                 atomicOr(&ws.bloom2[h3 >> 5], 1u << (h3 & 31));
               }
             }
+          }
           // contact points with the triangle's OWN plane (valid if it turns out to be its group base)
           float cx[4], cz[4];
           const int nc = box_plane(b, pl, 4, cx, cz);
@@ -464,7 +473,7 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView&
       }
     }
     __syncwarp();
-    if (live) {
+    if (live && !merge_free) {
       const uint32_t h3 = bloom_hash3((int)floorf((pl[0] + 1.0f) * kKeyScale), (int)floorf((pl[2] + 1.0f) * kKeyScale), dkey(pl[3]));
       if ((atomicOr(&ws.bloom2[h3 >> 5], 1u << (h3 & 31)) >> (h3 & 31)) & 1u) pair_possible = true;
     }
@@ -480,6 +489,7 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView&
     max_live = max(max_live, idx);
   }
   if (nLive == 0) return R_FREE;
+  if (merge_free) return __any_sync(kFull, hit_own) ? R_HIT : R_FREE;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) max_live = max(max_live, __shfl_xor_sync(kFull, max_live, o));
   __syncwarp();
@@ -561,10 +571,11 @@ struct alignas(16) BoxRec {
   float minB, maxB;
   int x0, x1, z0, z1;
   uint32_t item;     // work item id
-  uint32_t flags;    // bits 0-2: box (0 torso, 1..4 feet); bit 3: zone all finite; bit 4: zone not reduced yet
+  uint32_t flags;    // bits 0-2: box (0 torso, 1..4 feet); bit 3: zone all finite; bit 4: zone not reduced yet;
+                     // bit 5: no mergeable triangle pair in the zone (plane tables, artp_set_map)
 };
 static_assert(sizeof(BoxRec) == 80, "BoxRec is read as five 16-byte words");
-enum { REC_ALLFINITE = 8, REC_NEEDS_REDUCE = 16 };
+enum { REC_ALLFINITE = 8, REC_NEEDS_REDUCE = 16, REC_MERGEFREE = 32 };
 
 __device__ __forceinline__ void rec_to_ctx(const Checker& c, const BoxRec& r, BoxCtx& b) {
 #pragma unroll
@@ -649,9 +660,10 @@ __device__ __forceinline__ int classify_box(const Checker& c, const float R[9], 
           }
         }
       }
-      const bool allFinite = nf == 0;
+      const bool allFinite = (nf & 1) == 0;
       r = zone_early_out(b, mx, mn, allFinite);
       if (allFinite) fl |= REC_ALLFINITE;
+      if ((nf & 2) == 0) fl |= REC_MERGEFREE;   // no two triangles of the zone lie in one plane: greedy grouping is the identity
       if (r == -1 && allFinite && nX >= 2 && nZ >= 2 && (probe & (foot ? 1 : 2))) {
         // Vertex probes. In an all-finite zone every vertex with h > minB belongs to a kept triangle, and the
         // collider returns 1 as soon as ANY such vertex lies inside the box (heightfield.cpp:1344-1441), so a
@@ -1030,7 +1042,8 @@ pose_small_kernel(const Checker c, const SmallBatch sb, uint8_t* __restrict__ ou
     const Field& fw = foot ? c.f[1] : c.f[0];
     const ZoneView zv{fw.H + (size_t)s_box[wid].z0 * fw.pitch + s_box[wid].x0, fw.pitch};   // straight from the heightfield
     const int res = box_collide_warp<false>(fw, s_box[wid], zv, s_ws[wid], lane, c.cell_margin,
-                                            (s_fl[wid] & REC_NEEDS_REDUCE) != 0, (s_fl[wid] & REC_ALLFINITE) != 0);
+                                            (s_fl[wid] & REC_NEEDS_REDUCE) != 0, (s_fl[wid] & REC_ALLFINITE) != 0,
+                                            (s_fl[wid] & REC_MERGEFREE) != 0);
     if (lane == 0) s_res2[wid] = res;
   }
   __syncthreads();

@@ -54,6 +54,7 @@ __device__ __forceinline__ void tma_tile_2d(void* dst, const CUtensorMap* map, u
 struct TileCfg {
   int tw, th;              // tile extent in floats (tw a multiple of 4; a zone may be at most tw - 3 wide, th high)
   uint32_t bytes, stride;  // tw * th * 4, and that rounded up to 128 bytes
+  int slots;               // tile slots per warp: 2 = the next box's tile is prefetched while this one is decided, 1 = none
 };
 constexpr int kMaxTileWarps = 8;
 
@@ -69,7 +70,7 @@ box_tiles_warp_kernel(const Checker c, const __grid_constant__ CUtensorMap map0,
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   WarpScratch& ws = ws_all[wid];
   unsigned char* slots = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tile_smem) + 127) & ~(uintptr_t)127) +
-                         (size_t)wid * 2 * tc.stride;   // TMA destinations: 128-byte aligned
+                         (size_t)wid * tc.slots * tc.stride;   // TMA destinations: 128-byte aligned
   if (lane == 0) { mbar_init(&bars[wid][0], 1); mbar_init(&bars[wid][1], 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
@@ -96,10 +97,9 @@ box_tiles_warp_kernel(const Checker c, const __grid_constant__ CUtensorMap map0,
       if (lane == 0) for (uint32_t ri = r0; ri < r1; ++ri) defer_list[atomicAdd(defer_count, 1u)] = ri | queue_bit;
       continue;
     }
-    __syncwarp();                      // every lane is done with both tile slots
-    prefetch(r0, 0);
     for (uint32_t ri = r0; ri < r1; ++ri) {
-      const int slot = (int)(ri - r0) & 1;
+      const int slot = (int)(ri - r0) & (tc.slots - 1);
+      if (tc.slots == 1 || ri == r0) { __syncwarp(); prefetch(ri, slot); }   // every lane is done with the slot
       // every lane reads the whole 80-byte record itself: five 16-byte loads from one address per warp (broadcasts)
       BoxRec r;
       {
@@ -108,7 +108,7 @@ box_tiles_warp_kernel(const Checker c, const __grid_constant__ CUtensorMap map0,
 #pragma unroll
         for (int i = 0; i < 5; ++i) dst[i] = __ldg(rp + i);
       }
-      if (ri + 1 < r1) { __syncwarp(); prefetch(ri + 1, slot ^ 1); }   // the other slot's box (ri - 1) is finished
+      if (tc.slots == 2 && ri + 1 < r1) { __syncwarp(); prefetch(ri + 1, slot ^ 1); }   // the other slot's box (ri - 1) is finished
       const uint32_t slot_item = item_slot(w, r.item);
       const bool foot = (r.flags & 7) != 0;
       // another box of the item (or state of the edge) already failed: nothing can change the verdict (perf only)
@@ -126,7 +126,7 @@ box_tiles_warp_kernel(const Checker c, const __grid_constant__ CUtensorMap map0,
       } else {
         const ZoneView zv{reinterpret_cast<const float*>(slots + (size_t)slot * tc.stride) + (b.x0 & 3), tc.tw};
         res = box_collide_warp<true>(foot ? c.f[1] : c.f[0], b, zv, ws, lane, c.cell_margin, (r.flags & REC_NEEDS_REDUCE) != 0,
-                                     (r.flags & REC_ALLFINITE) != 0);
+                                     (r.flags & REC_ALLFINITE) != 0, (r.flags & REC_MERGEFREE) != 0);
       }
       if (lane == 0) {
         if (res == R_DEFER) defer_list[atomicAdd(defer_count, 1u)] = ri | queue_bit;
