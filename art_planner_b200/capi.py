@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libartp.so")
 
-ARTP_OK, ARTP_E_INVALID, ARTP_E_NOMAP, ARTP_E_CUDA, ARTP_E_LIMIT, ARTP_E_NOWEIGHTS = 0, -1, -2, -3, -4, -5
+ARTP_OK, ARTP_E_INVALID, ARTP_E_NOMAP, ARTP_E_CUDA, ARTP_E_LIMIT, ARTP_E_NOWEIGHTS, ARTP_E_WINDOW = 0, -1, -2, -3, -4, -5, -6
 
 
 class ArtpError(RuntimeError):
@@ -81,6 +81,9 @@ def load():
     lib.artp_path_length_cost_device.argtypes = [vp, vp, vp, sz, vp, vp]
     lib.artp_compact_valid_device.argtypes = [vp, vp, sz, C.c_int64, vp, vp, vp]
     lib.artp_pack_valid_bits_device.argtypes = [vp, vp, sz, vp, vp]
+    lib.artp_check_poses_bits_device.argtypes = [vp, vp, sz, vp, vp, vp]
+    lib.artp_compact_valid_u32_device.argtypes = [vp, vp, sz, C.c_uint32, vp, vp, vp]
+    lib.artp_set_map_window.argtypes = [vp, vp, vp, i32, i32, dbl, dbl, dbl, i32, i32]
     lib.artp_compact_bits_device.argtypes = [vp, vp, sz, C.c_int64, vp, vp, vp]
     lib.artp_get_stats.argtypes = [vp, C.POINTER(ArtpStats)]
     lib.artp_set_mode.argtypes = [vp, i32]

@@ -76,10 +76,19 @@ class StateValidityChecker:
     def setMap(self, synth_map) -> None:             # validity_checker.cpp:20-23
         self._map = synth_map
 
-    def updateHeightField(self) -> None:             # validity_checker.cpp:27-31 -> setHeightField
+    def updateHeightField(self, window=None) -> None:   # validity_checker.cpp:27-31 -> setHeightField
+        """window = (row0, nrows): upload only that row slab of the map (spatial shard, artp_set_map_window); geometry stays
+        that of the full map, so verdicts are identical to a checker holding everything."""
         if self._map is None:
             raise capi.ArtpError(capi.ARTP_E_NOMAP, "setMap() was not called")
         m = self._map
+        if window is not None:
+            row0, nrows = int(window[0]), int(window[1])
+            e = np.asfortranarray(m.elevation[row0:row0 + nrows, :], dtype=np.float32)
+            k = np.asfortranarray(m.elevation_masked[row0:row0 + nrows, :], dtype=np.float32)
+            self._h.check(self._h.lib.artp_set_map_window(self._h.h, e.ctypes.data, k.ctypes.data, m.elevation.shape[0],
+                                                          m.elevation.shape[1], float(m.res), float(m.cx), float(m.cy), row0, nrows))
+            return
         e = np.asfortranarray(m.elevation, dtype=np.float32)
         k = np.asfortranarray(m.elevation_masked, dtype=np.float32)
         if e.shape != k.shape:
@@ -168,6 +177,26 @@ class StateValidityChecker:
         self._h.check(self._h.lib.artp_compute_sample_cdf(self._h.h, p.ctypes.data, None if cum is None else cum.ctypes.data,
                                                           None if row is None else row.ctypes.data))
         return (cum, row) if want_host else None
+
+    def isValidBatchBits(self, states, out_valid, out_bits):
+        """One shard step of the multi-GPU path: verdict bytes + bit-packed mask (CUDA float64 states), one call."""
+        n = states.shape[0]
+        self._h.check(self._h.lib.artp_check_poses_bits_device(self._h.h, C.c_void_p(states.data_ptr()), n,
+                                                               C.c_void_p(out_valid.data_ptr()), C.c_void_p(out_bits.data_ptr()),
+                                                               _stream_ptr()))
+
+    def compactValidU32(self, valid, base: int = 0, out_idx=None, out_cnt=None):
+        """Ordered 32-bit indices (base + i) of the non-zero entries of a CUDA uint8 mask -> (indices int32 view, count)."""
+        import torch
+        n = valid.shape[0]
+        if out_idx is None:
+            out_idx = torch.empty(n, dtype=torch.int32, device=valid.device)
+        if out_cnt is None:
+            out_cnt = torch.zeros(1, dtype=torch.int32, device=valid.device)
+        self._h.check(self._h.lib.artp_compact_valid_u32_device(self._h.h, C.c_void_p(valid.data_ptr()), n, int(base),
+                                                                C.c_void_p(out_idx.data_ptr()), C.c_void_p(out_cnt.data_ptr()),
+                                                                _stream_ptr()))
+        return out_idx, out_cnt
 
     def packValidBits(self, valid, out=None):
         """CUDA uint8 mask [n] -> bit-packed int32 words [(n+31)//32] (item i = bit i&31 of word i>>5)."""

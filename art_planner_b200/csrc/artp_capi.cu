@@ -35,7 +35,8 @@ struct Handle {
   float2* d_T[2][artp::kMaxLevel + 1] = {};
   unsigned char* d_NF[2][artp::kMaxLevel + 1] = {};
   int pitch = 0;
-  int rows = 0, cols = 0;
+  int rows = 0, cols = 0;           // full map
+  int win_row0 = 0, win_rows = 0;   // rows held by this handle (artp_set_map_window); whole map: 0, rows
   bool has_map = false;
   // [0] warp-stage claim counter, [1] defer count, [2] reach-vertex claim counter, [3] warp-queue count,
   // [4] reach-queue count, [5] plane-list count, [6] reach-plane claim counter, [7] scratch (sampler CDF validation)
@@ -164,22 +165,22 @@ __global__ void plane_table_clear_kernel(PlaneSlot* tab, size_t cap) {
   }
 }
 // Exact plane of triangle u of cell (x, z), or false if one of its vertices is not finite (never kept).
-__device__ __forceinline__ bool cell_tri_plane(const artp::Field& f, int x, int z, int u, float pl[4]) {
+__device__ __forceinline__ bool cell_tri_plane(const artp::Field& f, int x, int x_off, int z, int u, float pl[4]) {
   float hA, hB, hC, hD;
   artp::load_cell(f, x, z, hA, hB, hC, hD);
   const bool ok = u == 0 ? (artp::finitef(hA) && artp::finitef(hB) && artp::finitef(hC))
                          : (artp::finitef(hD) && artp::finitef(hB) && artp::finitef(hC));
   if (!ok) return false;
-  artp::cell_plane(f, u == 0, x, z, hA, hB, hC, hD, pl);
+  artp::cell_plane(f, u == 0, x + x_off, z, hA, hB, hC, hD, pl);   // vertex coordinates are those of the full map
   return true;
 }
-__global__ void plane_table_insert_kernel(const artp::Field f, PlaneSlot* tab, uint32_t mask) {
+__global__ void plane_table_insert_kernel(const artp::Field f, int x_off, PlaneSlot* tab, uint32_t mask) {
   const size_t ncell = (size_t)(f.nx - 1) * (f.nz - 1);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < 2 * ncell; i += (size_t)gridDim.x * blockDim.x) {
     const size_t c = i >> 1;
     const int u = (int)(i & 1), z = (int)(c / (f.nx - 1)), x = (int)(c - (size_t)z * (f.nx - 1));
     float pl[4];
-    if (!cell_tri_plane(f, x, z, u, pl)) continue;
+    if (!cell_tri_plane(f, x, x_off, z, u, pl)) continue;
     const uint32_t id = (uint32_t)(((size_t)z * f.pitch + x) * 2 + u);
     const unsigned long long key = plane_key((int)floorf((pl[0] + 1.0f) * artp::kKeyScale), (int)floorf((pl[2] + 1.0f) * artp::kKeyScale),
                                              artp::dkey(pl[3]));
@@ -195,14 +196,14 @@ __global__ void plane_table_insert_kernel(const artp::Field f, PlaneSlot* tab, u
     }
   }
 }
-__global__ void plane_table_query_kernel(const artp::Field f, const PlaneSlot* __restrict__ tab, uint32_t mask,
+__global__ void plane_table_query_kernel(const artp::Field f, int x_off, const PlaneSlot* __restrict__ tab, uint32_t mask,
                                          unsigned char* __restrict__ mergeable) {
   const size_t ncell = (size_t)(f.nx - 1) * (f.nz - 1);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < 2 * ncell; i += (size_t)gridDim.x * blockDim.x) {
     const size_t c = i >> 1;
     const int u = (int)(i & 1), z = (int)(c / (f.nx - 1)), x = (int)(c - (size_t)z * (f.nx - 1));
     float pl[4];
-    if (!cell_tri_plane(f, x, z, u, pl)) continue;
+    if (!cell_tri_plane(f, x, x_off, z, u, pl)) continue;
     const uint32_t id = (uint32_t)(((size_t)z * f.pitch + x) * 2 + u);
     const float e2 = 2.0f * ARTP_EPS;
     const int kx0 = (int)floorf((pl[0] - e2 + 1.0f) * artp::kKeyScale), kx1 = (int)floorf((pl[0] + e2 + 1.0f) * artp::kKeyScale);
@@ -296,9 +297,9 @@ __global__ void compact_scan_kernel(uint32_t* counts, size_t nb, uint32_t* total
   }
   if (threadIdx.x == 0) *total = carry;
 }
-template <bool BITS>
+template <bool BITS, typename IndexT>
 __global__ void compact_scatter_kernel(const uint8_t* __restrict__ valid, size_t n, int64_t base,
-                                       const uint32_t* __restrict__ offsets, int64_t* __restrict__ out) {
+                                       const uint32_t* __restrict__ offsets, IndexT* __restrict__ out) {
   __shared__ uint32_t wsum[32];
   const size_t i = (size_t)blockIdx.x * kCompactBlock + threadIdx.x;
   const int v = (i < n) && mask_at<BITS>(valid, i);
@@ -314,7 +315,7 @@ __global__ void compact_scatter_kernel(const uint8_t* __restrict__ valid, size_t
   __syncthreads();
   if (v) {
     const uint32_t pos = offsets[blockIdx.x] + (wid ? wsum[wid - 1] : 0u) + __popc(bal & ((1u << lane) - 1u));
-    out[pos] = base + (int64_t)i;
+    out[pos] = (IndexT)(base + (int64_t)i);
   }
 }
 
@@ -377,7 +378,13 @@ struct ChainScope {   // begin on construction, end on destruction (every return
 // Sticky plane-grouping overflow (set by the device, see Handle::h_err): read and clear.
 int take_sticky_error(Handle* h) {
   if (h->h_err && *(volatile uint32_t*)h->h_err) {
+    const uint32_t e = *(volatile uint32_t*)h->h_err;
     *(volatile uint32_t*)h->h_err = 0;
+    if (e & 2u) {
+      h->err = "a box reached outside this handle's map window (artp_set_map_window: route samples to the shard that holds them, "
+               "halo >= box half-diagonal + offsets); affected poses were marked invalid";
+      return ARTP_E_WINDOW;
+    }
     h->err = "plane-grouping stage overflow: a zone exceeded its shared-memory store; affected poses were marked invalid";
     return ARTP_E_LIMIT;
   }
@@ -642,12 +649,24 @@ int artp_get_stats(artp_handle* hh, artp_stats* out) {
 
 int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation_masked, int rows, int cols, double res,
                  double cx, double cy) {
+  return artp_set_map_window(hh, elevation, elevation_masked, rows, cols, res, cx, cy, 0, rows);
+}
+
+// Spatial shard of a map: this handle holds only rows [row0, row0 + nrows) of the rows x cols layers --
+// its slab plus the halo the caller chose -- but keeps the geometry of the FULL map (sample spacing L / (N - 1), vertex
+// coordinates, isInside), so every verdict is bit-identical to a handle holding the whole map. The device pointers
+// of the layer / range tables are shifted by -row0, so the kernels keep indexing with global vertex indices.
+int artp_set_map_window(artp_handle* hh, const float* elevation, const float* elevation_masked, int rows, int cols, double res,
+                        double cx, double cy, int row0, int nrows) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
   std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (!elevation || !elevation_masked || rows < 2 || cols < 2 || !(res > 0)) { h->err = "bad map arguments"; return ARTP_E_INVALID; }
+  if (row0 < 0 || nrows < 2 || row0 + nrows > rows || (row0 & 3)) {
+    h->err = "bad map window (row0 must be a multiple of 4, 0 <= row0, row0 + nrows <= rows, nrows >= 2)"; return ARTP_E_INVALID;
+  }
   CU_TRY(h, cudaSetDevice(h->device));
-  const size_t ncell = (size_t)rows * cols;
+  const size_t ncell = (size_t)nrows * cols;
   // geometry exactly as dxHeightfieldData::SetData computes it in fp32 (heightfield.cpp:130-169)
   const double Lx = rows * res, Ly = cols * res;   // grid_map: length = size * resolution
   artp::Field f;
@@ -685,9 +704,9 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
   // upload (the previous map may still be in use by asynchronous calls on the caller's streams)
   CU_TRY(h, cudaDeviceSynchronize());
   h->chain_busy[0] = h->chain_busy[1] = false;
-  const int pitch = (rows + 3) & ~3;
+  const int pitch = (nrows + 3) & ~3;
   const size_t npad = (size_t)pitch * cols;
-  if (h->rows != rows || h->cols != cols) {
+  if (h->win_rows != nrows || h->cols != cols) {
     for (int k = 0; k < 2; ++k) {
       cudaFree(h->d_H[k]); h->d_H[k] = nullptr;
       for (int l = 0; l <= artp::kMaxLevel; ++l) { cudaFree(h->d_T[k][l]); cudaFree(h->d_NF[k][l]); h->d_T[k][l] = nullptr; h->d_NF[k][l] = nullptr; }
@@ -712,34 +731,39 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
   if (cudaMalloc(&d_merge, npad) != cudaSuccess) { cudaFree(d_tab); h->err = "cudaMalloc (plane tables)"; return ARTP_E_CUDA; }
   for (int k = 0; k < 2; ++k) {
     CU_TRY(h, cudaMemcpyAsync(h->d_stage, src[k], ncell * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    reverse_columns_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>((const float*)h->d_stage, h->d_H[k], rows, cols, pitch);
+    reverse_columns_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>((const float*)h->d_stage, h->d_H[k], nrows, cols, pitch);
     CU_TRY(h, cudaGetLastError());
-    artp::Field fk = f;
-    fk.H = h->d_H[k]; fk.pitch = pitch;
+    artp::Field fk = f;                     // local storage, global geometry: cell x of the window is global cell x + row0
+    fk.H = h->d_H[k]; fk.pitch = pitch; fk.nx = nrows;
     plane_table_clear_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(d_tab, cap);
     CU_TRY(h, cudaMemsetAsync(d_merge, 0, npad, h->stream));
-    plane_table_insert_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(fk, d_tab, (uint32_t)(cap - 1));
-    plane_table_query_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(fk, d_tab, (uint32_t)(cap - 1), d_merge);
+    plane_table_insert_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(fk, row0, d_tab, (uint32_t)(cap - 1));
+    plane_table_query_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(fk, row0, d_tab, (uint32_t)(cap - 1), d_merge);
     CU_TRY(h, cudaGetLastError());
     h->stats.kernel_launches += 4;
     for (int l = 1; l <= kmax[k]; ++l) {
       build_level_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_H[k], l > 1 ? h->d_T[k][l - 1] : nullptr,
                                                                   l > 1 ? h->d_NF[k][l - 1] : nullptr, d_merge, h->d_T[k][l],
-                                                                  h->d_NF[k][l], rows, cols, pitch, 1 << (l - 1));
+                                                                  h->d_NF[k][l], nrows, cols, pitch, 1 << (l - 1));
       CU_TRY(h, cudaGetLastError());
       h->stats.kernel_launches += 1;
     }
   }
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   cudaFree(d_tab); cudaFree(d_merge);
-  h->rows = rows; h->cols = cols; h->pitch = pitch;
+  h->rows = rows; h->cols = cols; h->pitch = pitch; h->win_row0 = row0; h->win_rows = nrows;
   f.pitch = pitch;
+  f.x_lo = row0; f.x_hi = row0 + nrows - 1;
   for (int k = 0; k < 2; ++k) {
-    f.H = h->d_H[k];
+    f.H = h->d_H[k] - row0;                 // indexed with GLOBAL vertex indices x in [x_lo, x_hi]
     f.kmax = kmax[k];
-    for (int l = 0; l <= artp::kMaxLevel; ++l) { f.T[l] = (l >= 1 && l <= kmax[k]) ? h->d_T[k][l] : nullptr; f.NF[l] = (l >= 1 && l <= kmax[k]) ? h->d_NF[k][l] : nullptr; }
+    for (int l = 0; l <= artp::kMaxLevel; ++l) {
+      f.T[l] = (l >= 1 && l <= kmax[k]) ? h->d_T[k][l] - row0 : nullptr;
+      f.NF[l] = (l >= 1 && l <= kmax[k]) ? h->d_NF[k][l] - row0 : nullptr;
+    }
     h->chk.f[k] = f;
   }
+  h->chk.err_word = h->d_err;
   h->chk.Lx = Lx; h->chk.Ly = Ly; h->chk.cx = cx; h->chk.cy = cy;
   h->chk.cell_margin = 0.02f + 2e-6f * (float)std::max(rows, cols);
   // Stage B tiles (artp_tiles.cuh): a zone spans at most ceil(2 r / s) + 3 vertices per axis (r = box half-diagonal);
@@ -781,6 +805,7 @@ int artp_set_map(artp_handle* hh, const float* elevation, const float* elevation
                                                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")"; return ARTP_E_CUDA; }
       }
+      tc.x_off = row0;
       h->tile_cfg[q] = tc; h->tile_warps[q] = wpc;
       h->tile_smem[q] = (int)((size_t)wpc * tc.slots * tc.stride + 128);
       if (q == 1) { h->chk.reach_tw = tc.tw; h->chk.reach_th = tc.th; }
@@ -1145,8 +1170,8 @@ int artp_path_length_cost(artp_handle* hh, const double* s1, const double* s2, s
   return ARTP_OK;
 }
 
-static int compact_valid_impl(Handle* h, const uint8_t* d_valid, size_t n, int64_t base, int64_t* d_indices,
-                              uint32_t* d_count, cudaStream_t s, bool bits = false) {
+static int compact_valid_impl(Handle* h, const uint8_t* d_valid, size_t n, int64_t base, void* d_indices,
+                              uint32_t* d_count, cudaStream_t s, bool bits = false, bool u32 = false) {
   if (n == 0) { CU_TRY(h, cudaMemsetAsync(d_count, 0, sizeof(uint32_t), s)); return ARTP_OK; }
   ChainScope cs(h, 1, s);
   if (cs.rc) return cs.rc;
@@ -1161,8 +1186,9 @@ static int compact_valid_impl(Handle* h, const uint8_t* d_valid, size_t n, int64
   if (bits) compact_count_kernel<true><<<(unsigned)nb, kCompactBlock, 0, s>>>(d_valid, n, h->d_block_counts);
   else compact_count_kernel<false><<<(unsigned)nb, kCompactBlock, 0, s>>>(d_valid, n, h->d_block_counts);
   compact_scan_kernel<<<1, 1024, 0, s>>>(h->d_block_counts, nb, d_count);
-  if (bits) compact_scatter_kernel<true><<<(unsigned)nb, kCompactBlock, 0, s>>>(d_valid, n, base, h->d_block_counts, d_indices);
-  else compact_scatter_kernel<false><<<(unsigned)nb, kCompactBlock, 0, s>>>(d_valid, n, base, h->d_block_counts, d_indices);
+  if (bits) compact_scatter_kernel<true, int64_t><<<(unsigned)nb, kCompactBlock, 0, s>>>(d_valid, n, base, h->d_block_counts, (int64_t*)d_indices);
+  else if (u32) compact_scatter_kernel<false, uint32_t><<<(unsigned)nb, kCompactBlock, 0, s>>>(d_valid, n, base, h->d_block_counts, (uint32_t*)d_indices);
+  else compact_scatter_kernel<false, int64_t><<<(unsigned)nb, kCompactBlock, 0, s>>>(d_valid, n, base, h->d_block_counts, (int64_t*)d_indices);
   CU_TRY(h, cudaGetLastError());
   h->stats.kernel_launches += 3;
   h->stats.last_launches = 3;
@@ -1177,6 +1203,27 @@ int artp_compact_valid_device(artp_handle* hh, const uint8_t* d_valid, size_t n,
   if (!d_valid || !d_indices || !d_count) { h->err = "null buffer"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
   return compact_valid_impl(h, d_valid, n, base, d_indices, d_count, (cudaStream_t)stream);
+}
+
+int artp_compact_valid_u32_device(artp_handle* hh, const uint8_t* d_valid, size_t n, uint32_t base, uint32_t* d_indices,
+                                  uint32_t* d_count, void* stream) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
+  if (!d_valid || !d_indices || !d_count) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  if (n + (size_t)base > 0xFFFFFFFFull) { h->err = "indices do not fit 32 bits"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  return compact_valid_impl(h, d_valid, n, (int64_t)base, d_indices, d_count, (cudaStream_t)stream, false, true);
+}
+
+// isValid for a shard + the bit-packed verdicts the multi-GPU exchange sends, in one call on one stream.
+int artp_check_poses_bits_device(artp_handle* hh, const double* d_states, size_t n, uint8_t* d_valid, uint32_t* d_bits, void* stream) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
+  int rc = artp_check_poses_device(hh, d_states, n, d_valid, stream);
+  if (rc) return rc;
+  return artp_pack_valid_bits_device(hh, d_valid, n, d_bits, stream);
 }
 
 int artp_pack_valid_bits_device(artp_handle* hh, const uint8_t* d_valid, size_t n, uint32_t* d_bits, void* stream) {
@@ -1228,6 +1275,7 @@ int artp_estimate_normals(artp_handle* hh, double estimation_radius, float* norm
   Handle* h = reinterpret_cast<Handle*>(hh);
   std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
+  if (h->win_rows != h->rows) { h->err = "not available on a map window (artp_set_map_window)"; return ARTP_E_INVALID; }
   if (!(estimation_radius >= 0.0)) { h->err = "estimation_radius < 0"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
   int rc = chain_begin(h, 0, h->stream);
@@ -1258,6 +1306,7 @@ int artp_compute_sample_cdf(artp_handle* hh, const float* sample_probability, fl
   Handle* h = reinterpret_cast<Handle*>(hh);
   std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
+  if (h->win_rows != h->rows) { h->err = "not available on a map window (artp_set_map_window)"; return ARTP_E_INVALID; }
   if (!sample_probability) { h->err = "null buffer"; return ARTP_E_INVALID; }
   CU_TRY(h, cudaSetDevice(h->device));
   int rc = chain_begin(h, 0, h->stream);
@@ -1291,6 +1340,7 @@ int artp_set_sampler(artp_handle* hh, const artp_sampler_params* sp, const float
   Handle* h = reinterpret_cast<Handle*>(hh);
   std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
+  if (h->win_rows != h->rows) { h->err = "not available on a map window (artp_set_map_window)"; return ARTP_E_INVALID; }
   const bool host_normals = normal_x && normal_y && normal_z && plane_fit_std_dev;
   if (!sp) { h->err = "null sampler params"; return ARTP_E_INVALID; }
   if (!host_normals && (normal_x || normal_y || normal_z || plane_fit_std_dev)) {
@@ -1554,6 +1604,7 @@ int artp_update_features(artp_handle* hh) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   std::lock_guard<std::recursive_mutex> lk(h->mtx);
   if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
+  if (h->win_rows != h->rows) { h->err = "not available on a map window (artp_set_map_window)"; return ARTP_E_INVALID; }
   artp_cnn::set_base_offset_mode(h->cnn, (h->cnn_mode & 2) ? 1 : 0);
   artp_cnn::set_conv15_mode(h->cnn, (h->cnn_mode >> 2) & 3);
   return artp_cnn::update_features(h->cnn, h->d_H[0], h->rows, h->cols, h->pitch, h->chk.Lx / h->rows, h->chk.cx, h->chk.cy,

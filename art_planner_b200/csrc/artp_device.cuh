@@ -30,6 +30,9 @@ struct Field {
   int kmax;
   float W, D, hW, hD, sW, sD, asp, iW, iD;
   float px, py;    // heightfield body position (float casts of the map centre)
+  // Map window (artp_set_map_window): only vertices x in [x_lo, x_hi] are stored (H, T, NF are shifted by -x_lo so that
+  // global indices keep working); nx and all geometry are those of the full map. Whole map: 0, nx - 1.
+  int x_lo, x_hi;
 };
 
 struct Checker {
@@ -40,6 +43,7 @@ struct Checker {
   int unknown_untraversable;
   double Lx, Ly, cx, cy;  // grid_map length / position (doubles) for isInside
   float cell_margin;      // candidate-cell search margin in cells (plane stage)
+  uint32_t* err_word;     // sticky error word (mapped host memory): bit 0 plane-store overflow, bit 1 box outside the map window
   // extent of the reach-box queue's TMA tile in floats (artp_tiles.cuh; 0: no such queue). The tile starts at column
   // x0 & ~3, so a zone may be at most reach_tw - 3 wide.
   int reach_tw, reach_th;

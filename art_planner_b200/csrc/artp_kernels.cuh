@@ -591,6 +591,7 @@ __device__ __forceinline__ void rec_to_ctx(const Checker& c, const BoxRec& r, Bo
 // vertex probes. Returns R_FREE / R_HIT when decided, -1 when the box needs the vertex / plane stages (b and fl are
 // then complete), kBoxOutside when the box centre is outside the map (the caller applies the outside-map rule).
 constexpr int kBoxOutside = -2;
+constexpr int kBoxOutsideWindow = -3;   // map shards (artp_set_map_window): the item is reported invalid + sticky error
 __device__ __forceinline__ int classify_box(const Checker& c, const float R[9], const float R1[9], const float t[3], int k,
                                             int force_all, int probe /* bit 0: reach boxes, bit 1: torso */, BoxCtx& b,
                                             uint32_t& fl) {
@@ -622,6 +623,7 @@ __device__ __forceinline__ int classify_box(const Checker& c, const float R[9], 
     b.x1 = min((int)ceilf(next_up(a1 * g.iW)), g.nx - 1);
     b.z0 = max((int)floorf(next_down(a4 * g.iD)), 0);
     b.z1 = min((int)ceilf(next_up(a5 * g.iD)), g.nz - 1);
+    if (b.x0 < g.x_lo || b.x1 > g.x_hi) return kBoxOutsideWindow;   // the zone leaves this handle's map window
 #pragma unroll
     for (int i = 0; i < 9; ++i) b.R1[i] = R1[i];
     b.side[0] = sd0; b.side[1] = sd1; b.side[2] = sd2;
@@ -732,6 +734,7 @@ classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs_w
         if (foot && c.unknown_untraversable) result = 0;
         continue;
       }
+      if (r == kBoxOutsideWindow) { *(volatile uint32_t*)c.err_word = 2u; result = 0; continue; }   // fail closed
       if (r == -1) {
         // reach boxes go to their own queue (small TMA tiles); the torso -- and a reach box whose zone would not fit the
         // small tile -- to the big-tile queue
@@ -1033,7 +1036,8 @@ pose_small_kernel(const Checker c, const SmallBatch sb, uint8_t* __restrict__ ou
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
     const int r = s_res[k];
-    if (r == kBoxOutside) { if (k > 0 && c.unknown_untraversable) valid = false; }
+    if (r == kBoxOutsideWindow) { if (tid == 0) *(volatile uint32_t*)c.err_word = 2u; valid = false; }
+    else if (r == kBoxOutside) { if (k > 0 && c.unknown_untraversable) valid = false; }
     else if (k == 0) { if (r == R_HIT) valid = false; }
     else if (r == R_FREE) valid = false;
   }

@@ -54,6 +54,7 @@ __device__ __forceinline__ void tma_tile_2d(void* dst, const CUtensorMap* map, u
 struct TileCfg {
   int tw, th;              // tile extent in floats (tw a multiple of 4; a zone may be at most tw - 3 wide, th high)
   uint32_t bytes, stride;  // tw * th * 4, and that rounded up to 128 bytes
+  int x_off;               // first stored vertex column of the layer (map window), a multiple of 4
   int slots;               // tile slots per warp: 2 = the next box's tile is prefetched while this one is decided, 1 = none
 };
 constexpr int kMaxTileWarps = 8;
@@ -84,7 +85,7 @@ box_tiles_warp_kernel(const Checker c, const __grid_constant__ CUtensorMap map0,
     const uint32_t fl = zr2.w;                                                    // word 19: flags
     if (lane == 0) {
       mbar_expect_tx(&bars[wid][slot], tc.bytes);
-      tma_tile_2d(slots + (size_t)slot * tc.stride, (fl & 7u) ? &map1 : &map0, &bars[wid][slot], x0 & ~3, z0);
+      tma_tile_2d(slots + (size_t)slot * tc.stride, (fl & 7u) ? &map1 : &map0, &bars[wid][slot], (x0 & ~3) - tc.x_off, z0);
     }
   };
   for (;;) {

@@ -175,11 +175,11 @@ def make_fbm_map(rows=1000, cols=1000, res=0.04, seed=2, amp=0.6, wavelength=8.0
         wy = cy - 0.5 * ly + u[1] * ly
         length = 2.0 + 6.0 * u[2]
         thick = 0.2 + 0.4 * u[3]
-        if u[4] < 0.5:
-            sel = (np.abs(x[:, None] - wx) < 0.5 * length) & (np.abs(y[None, :] - wy) < 0.5 * thick)
-        else:
-            sel = (np.abs(x[:, None] - wx) < 0.5 * thick) & (np.abs(y[None, :] - wy) < 0.5 * length)
-        e = np.where(sel, e + wall_height, e)
+        ex, ey = (length, thick) if u[4] < 0.5 else (thick, length)
+        ri = np.nonzero(np.abs(x - wx) < 0.5 * ex)[0]          # the slab is a rectangle of rows x columns
+        ci = np.nonzero(np.abs(y - wy) < 0.5 * ey)[0]
+        if ri.size and ci.size:
+            e[ri[0]:ri[-1] + 1, ci[0]:ci[-1] + 1] += wall_height
     e32 = np.asfortranarray(e.astype(np.float32))
     masked = e32.copy(order="F")
     # untraversable square blobs, 0.3-1.0 m (mean area ~0.46 m^2)

@@ -182,6 +182,83 @@ def pose_workload(torch, chk, flush, m, poses, steps, ref, kind, port, n_mt=400_
                     "mask_equals_gpu": bool(np.array_equal(got[:n_mt], vm) and np.array_equal(got[:n1], v1))}}
 
 
+def run_c5(torch, dist, apb, synth, world, rank, local, flush, steps=5):
+    """BASELINE configs[4]: the 4000x4000 map in `world` spatial row slabs (strong scaling: 8 M samples in total). Every rank
+    uploads only its slab + a 40-row halo (artp_set_map_window: full-map geometry, local tables), checks the samples that
+    fall into its slab, and the ranks all-gather the bit masks. N = 1: the whole map on one GPU."""
+    import art_planner_b200  # noqa: F401
+    N5, total, halo = 4000, 8_000_000, 40
+    n_r = total // world
+    m = synth.make_fbm_map(N5, N5, MAP_RES, seed=MAP_SEED, amp=0.6, n_walls=96)
+    rows_per = N5 // world
+    s0, s1 = rank * rows_per, (rank + 1) * rows_per
+    lo, hi = max(0, s0 - halo), min(N5, s1 + halo)
+    chk = apb.StateValidityChecker(synth.PARAMS_YAML, device=local)
+    chk.setMap(m)
+    t0 = time.perf_counter()
+    chk.updateHeightField(window=(lo, hi - lo) if world > 1 else None)
+    torch.cuda.synchronize()
+    set_map_s = time.perf_counter() - t0
+    chk.setTiming(True)
+    lx, ly = m.length
+    k = np.arange(rank * n_r, (rank + 1) * n_r)
+    x_hi, x_lo = m.cx + 0.5 * lx - s0 * MAP_RES, m.cx + 0.5 * lx - s1 * MAP_RES        # x range of the slab's rows
+    x = x_lo + (0.0005 + 0.999 * synth.hash_uniform(7, 1, k)) * (x_hi - x_lo)
+    y = m.cy + (synth.hash_uniform(7, 2, k) - 0.5) * ly * 0.999
+    poses = synth.make_terrain_poses(m, n_r, seed=7, start=rank * n_r, xy=(x, y))
+    d = torch.from_numpy(poses).cuda()
+    v = torch.empty(n_r, dtype=torch.uint8, device="cuda")
+    words = (n_r + 31) // 32
+    bits = torch.empty(words, dtype=torch.int32, device="cuda")
+    idx = torch.empty(n_r, dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    all_bits = torch.empty(world * words, dtype=torch.int32, device="cuda") if world > 1 else None
+
+    def step():
+        chk.isValidBatchBits(d, v, bits)
+        chk.compactValidU32(v, base=0, out_idx=idx, out_cnt=cnt)
+        if world > 1:
+            dist.all_gather_into_tensor(all_bits, bits)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms, stage = 0.0, []
+    for i in range(steps):
+        flush.fill_(i & 0xFF)
+        a.record(); step(); b.record(); torch.cuda.synchronize()
+        ms += a.elapsed_time(b)
+        stage.append(chk.lastStageTimesMs())
+    chk.pollError()                       # ARTP_E_WINDOW here would mean a sample was routed to the wrong shard
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    st = chk.stats()
+    out = None
+    if rank == 0:
+        o, kind = cpu_oracle(synth.PARAMS_YAML)
+        o.set_map(m)                      # the oracle always sees the WHOLE map
+        sel = np.arange(0, n_r, 50)
+        cores = min(os.cpu_count() or 1, 16)
+        t0 = time.perf_counter(); ref = o.check_poses_mt(poses[sel], cores); t_cpu = time.perf_counter() - t0
+        got = v.cpu().numpy()
+        sm = np.mean(np.array(stage), 0)
+        out = {"workload": f"configs[4]: fBm 4000x4000@0.04m map, {total} samples in {world} spatial row slab(s) (+{halo}-row halo), strong scaling",
+               "poses_per_s": total * steps / (float(t[0]) * 1e-3), "ms_per_step": float(t[0]) / steps, "steps": steps,
+               "samples_per_gpu": n_r, "map_rows_on_gpu": hi - lo if world > 1 else N5,
+               "set_map_s": set_map_s, "valid_fraction": float(got.mean()),
+               "stage_ms_last_round": dict(zip(("classify", "torso_queue", "reach_queue", "unused", "group"), [float(z) for z in sm])),
+               "queued_boxes_last_round": st["last_queued_boxes"],
+               "exchange": "one NCCL all-gather of the bit masks per step, inside the timed step (not pipelined)" if world > 1 else "none (N = 1)",
+               "mask_equals_reference": bool(np.array_equal(got[sel], ref)),
+               "cpu": {"kind": kind, "cores": cores, "poses_per_s": len(sel) / t_cpu,
+                       "sample": f"every 50th sample of rank 0's shard ({len(sel)} poses) against the whole map"}}
+    del chk
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path on all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -256,13 +333,14 @@ def main():
     h_poses32 = torch.from_numpy(poses.astype(np.float32)).pin_memory()   # the cast Pose3FromSE3 does first, done by the adapter
     h_valid = torch.empty(n, dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
-    # N > 1 exchange: bit-packed masks (n/32 words per rank) all-gathered in one NCCL call, then every rank compacts
-    # the gathered mask into the global ordered valid-index list
+    # Every step produces the verdict bytes, their bit-packed form and the ordered list of valid sample indices of this
+    # rank's shard (32-bit, global numbering). N > 1: the ranks exchange the bit masks with ONE NCCL all-gather (125 KB
+    # per rank and 10^6 samples); a consumer that wants the global index list reads the per-rank segments + counts.
     assert n % 32 == 0
     my_bits = [torch.empty(n // 32, dtype=torch.int32, device="cuda") for _ in range(2)]
+    loc_idx = torch.empty(n, dtype=torch.int32, device="cuda")
+    loc_cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
     all_bits = torch.empty(world * (n // 32), dtype=torch.int32, device="cuda") if world > 1 else None
-    gather_idx = torch.empty(world * n, dtype=torch.int64, device="cuda") if world > 1 else None
-    gather_cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
     side = torch.cuda.Stream() if world > 1 else None
     ev_done = torch.cuda.Event() if world > 1 else None
 
@@ -274,18 +352,23 @@ def main():
         with torch.cuda.stream(side):
             side.wait_event(after_event)
             sharding.gather_valid_bits(my_bits[b], world, out=all_bits)     # 125 KB of mask bits per rank on the wire
-            chk.compactBits(all_bits, world * n, base=0, out_idx=gather_idx, out_cnt=gather_cnt)   # global ordered list
             ev_done.record(side)
 
     def step_device(i, start_event):
         """Window i = checks of step i  ||  exchange of step i-1; the window ends when both are done."""
         if world > 1 and i > 0:
             exchange((i - 1) & 1, start_event)
-        chk.isValidBatch(d_poses, out=d_valid)
+        chk.isValidBatchBits(d_poses, d_valid, my_bits[i & 1])                  # check + pack, one call
+        chk.compactValidU32(d_valid, base=rank * n, out_idx=loc_idx, out_cnt=loc_cnt)   # this shard's ordered index list
+        if world > 1 and i > 0:
+            torch.cuda.current_stream().wait_event(ev_done)
+
+    def step_serial():
+        """The same step without pipelining: check -> pack -> local list -> all-gather, one stream."""
+        chk.isValidBatchBits(d_poses, d_valid, my_bits[0])
+        chk.compactValidU32(d_valid, base=rank * n, out_idx=loc_idx, out_cnt=loc_cnt)
         if world > 1:
-            chk.packValidBits(d_valid, out=my_bits[i & 1])
-            if i > 0:
-                torch.cuda.current_stream().wait_event(ev_done)
+            sharding.gather_valid_bits(my_bits[0], world, out=all_bits)
 
     def step_e2e():      # what INTEGRATION.md's adapter calls: float32 states (exact), pinned host buffers
         chk.isValidHostPtr(h_poses32.data_ptr(), n, h_valid.data_ptr(), f32=True)
@@ -332,12 +415,28 @@ def main():
         dist.barrier()
     wall = time.perf_counter() - wall0
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+    # the same step un-pipelined (check -> pack -> local list -> all-gather on one stream)
+    sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_serial(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    serial_ms = 0.0
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        sa.record(); step_serial(); sb.record(); torch.cuda.synchronize()
+        serial_ms += sa.elapsed_time(sb)
     exchange_ok = None
-    if world > 1:   # the gathered global index list must hold exactly the valid samples of all ranks
-        tot = d_valid.to(torch.int64).sum().reshape(1)
-        dist.all_reduce(tot)
-        first = int(gather_idx[0].item()) if int(gather_cnt.item()) else -1
-        exchange_ok = bool(int(gather_cnt.item()) == int(tot.item()) and first >= 0)
+    if world > 1:   # verify the WHOLE exchange: every gathered bit against every rank's verdict byte, and the local list
+        all_valid = torch.empty(world * n, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(all_valid, d_valid)
+        w64 = all_bits.to(torch.int64) & 0xFFFFFFFF
+        unpacked = ((w64[:, None] >> torch.arange(32, device="cuda")[None, :]) & 1).reshape(-1).to(torch.uint8)
+        want_idx = (torch.nonzero(d_valid).reshape(-1) + rank * n).to(torch.int32)
+        cnt = int(loc_cnt.item())
+        ok = torch.equal(unpacked, (all_valid != 0).to(torch.uint8)) and cnt == want_idx.numel() and torch.equal(loc_idx[:cnt], want_idx)
+        okt = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        exchange_ok = bool(int(okt.item()))
     launches = chk.stats()["kernel_launches"] - launches0
     deferred = chk.stats()["last_deferred"]
     queued = chk.stats()["last_queued_boxes"]
@@ -494,10 +593,15 @@ def main():
         except Exception as ex:   # never let a secondary workload take the headline line down
             secondary["motion_cost_cnn"] = {"error": repr(ex)}
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    c5 = None
+    try:
+        c5 = run_c5(torch, dist, apb, synth, world, rank, local, flush)
+    except Exception as ex:      # never let the sharded workload take the headline line down
+        c5 = {"error": repr(ex)}
+    t = torch.tensor([dev_ms, e2e_s * 1e3, serial_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, serial_ms = float(t[0]), float(t[1]), float(t[2])
     valid_ref = None
 
     if rank == 0:
@@ -550,7 +654,7 @@ def main():
                        "configs[4]: fBm 4000x4000@0.04m map, 1M samples per GPU inside the GPU's spatial slab, yaml robot geometry",
                        "poses_per_gpu": n, "map": f"{m.rows}x{m.cols}@{MAP_RES}",
                        "map_seed": MAP_SEED, "pose_seed": POSE_SEED, "l2": "flushed between timed steps (256 MiB write)",
-                       "parallelism": f"pose shards x{world}, replicated map" + (", NCCL all-gather of bit-packed masks + global ordered compaction on every rank, pipelined: the exchange of step i runs on a side stream inside the timed window of step i+1 (+ one closing window)" if world > 1 else "")},
+                       "parallelism": f"pose shards x{world}, replicated 1000x1000 map" + (", one NCCL all-gather of bit-packed masks per step, pipelined: the exchange of step i runs on a side stream inside the timed window of step i+1 (+ one closing window); see exchange.unpipelined_value and c5 (spatial shards)" if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": n,
                     "ms_per_step": e2e_ms / e2e_steps, "api": "artp_check_poses_f32 (states cast to float by the adapter, exact)",
                     "f64_api_value": world * n * e2e_steps / e2e64_s, "f64_api_h2d_bytes_per_step": n * 56},
@@ -572,6 +676,10 @@ def main():
                                  "~1-2 % of peak: the pipeline is instruction-issue bound (61 % issue slots busy, profiles/)"},
             "cpu_baseline": cpu_baseline,
             "clocks": clocks, "wall_s_timed_region": wall, "secondary": secondary, "exchange_ok": exchange_ok,
+            "exchange": {"unpipelined_value": world * n * args.steps / (serial_ms * 1e-3), "unpipelined_ms_per_step": serial_ms / args.steps,
+                         "wire_bytes_per_rank_per_step": n // 8 if world > 1 else 0,
+                         "what": "check + pack + this shard's ordered 32-bit index list" + (" + one NCCL all-gather of the bit masks" if world > 1 else "")},
+            "c5": c5,
         }
         print(json.dumps(out))
     if world > 1:

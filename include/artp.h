@@ -56,6 +56,7 @@ extern "C" {
 #define ARTP_E_CUDA       -3   /* CUDA runtime error / no device */
 #define ARTP_E_LIMIT      -4   /* box/map combination exceeds a compiled limit */
 #define ARTP_E_NOWEIGHTS  -5   /* motion-cost network weights / features not set */
+#define ARTP_E_WINDOW     -6   /* a box reached outside the handle's map window (artp_set_map_window) */
 
 /* art_planner::Params fields the hot path reads (include/art_planner/params.h). Doubles as in the reference. */
 typedef struct artp_params {
@@ -94,6 +95,15 @@ const char* artp_last_error(const artp_handle* h);   /* h may be NULL: last crea
 int artp_set_map(artp_handle* h, const float* elevation, const float* elevation_masked,
                  int rows, int cols, double res, double cx, double cy);
 int artp_has_map(const artp_handle* h);
+/* Spatial shard of a map (multi-GPU): the handle receives only rows [row0, row0 + nrows) of the rows x cols
+ * layers (HOST pointers to nrows x cols column-major matrices; row0 a multiple of 4) -- its slab plus a halo of at least
+ * the largest box half-diagonal + box offsets -- while rows, res, cx, cy describe the FULL map. Geometry (ODE sample
+ * spacing L / (N - 1), vertex coordinates, grid_map isInside) is that of the full map, so verdicts are bit-identical to a
+ * handle holding everything; device memory and the range / plane tables shrink to the window. A pose whose boxes reach
+ * outside the window is reported invalid and raises ARTP_E_WINDOW (sticky, like ARTP_E_LIMIT): route every sample to
+ * the shard that holds it. The sampler, normal estimation and the cost network need the whole map (ARTP_E_INVALID). */
+int artp_set_map_window(artp_handle* h, const float* elevation, const float* elevation_masked, int rows, int cols,
+                        double res, double cx, double cy, int row0, int nrows);
 
 /* n SE(3) states, 7 doubles each (x y z qx qy qz qw) -> valid[n] (0/1). HOST buffers; H2D/D2H inside. */
 int artp_check_poses(artp_handle* h, const double* states, size_t n, uint8_t* valid);
@@ -190,6 +200,13 @@ int artp_compact_valid_device(artp_handle* h, const uint8_t* d_valid, size_t n, 
  * 125 KB per 10^6 poses on the wire instead of 8 MB of padded indices -- and the ordered compaction of such a
  * (gathered) bit mask, which every rank runs on the all-gathered words to obtain the global valid-index list. */
 int artp_pack_valid_bits_device(artp_handle* h, const uint8_t* d_valid, size_t n, uint32_t* d_bits, void* stream);
+/* A shard's step of the multi-GPU path in one call: isValid of its n samples (d_valid, bytes) and the bit-packed mask
+ * (d_bits, (n+31)/32 words) that goes on the wire. */
+int artp_check_poses_bits_device(artp_handle* h, const double* d_states, size_t n, uint8_t* d_valid, uint32_t* d_bits, void* stream);
+/* Ordered compaction into 32-bit indices (base + i): the per-shard valid-sample list; a consumer that needs the global
+ * list reads the per-rank counts + segments. */
+int artp_compact_valid_u32_device(artp_handle* h, const uint8_t* d_valid, size_t n, uint32_t base, uint32_t* d_indices,
+                                  uint32_t* d_count, void* stream);
 int artp_compact_bits_device(artp_handle* h, const uint32_t* d_bits, size_t n, int64_t base, int64_t* d_indices,
                              uint32_t* d_count, void* stream);
 

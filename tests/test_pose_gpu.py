@@ -315,3 +315,55 @@ def test_calls_on_different_streams_share_a_handle_safely(maps, port_lib):
     torch.cuda.synchronize()
     for va, vb in outs:
         assert np.array_equal(va.cpu().numpy(), ra) and np.array_equal(vb.cpu().numpy(), rb)
+
+
+def test_map_window_shards_equal_the_whole_map(port_lib):
+    """Spatial shards (artp_set_map_window): a handle that holds only a row slab + halo answers exactly like the whole
+    map for every sample routed to it; a sample whose boxes leave the window is invalid + ARTP_E_WINDOW."""
+    import art_planner_b200 as ap
+    from art_planner_b200 import capi
+    m = synth.make_fbm_map(600, 500, seed=11, amp=0.6)
+    whole = ap.StateValidityChecker(cases.PARAMS["yaml"], device=0)
+    whole.setMap(m); whole.updateHeightField()
+    n = 120000
+    poses = synth.make_terrain_poses(m, n, seed=12)
+    ref = whole.isValidBatch(poses)
+    lx, _ = m.length
+    row = np.floor((m.cx + 0.5 * lx - poses[:, 0]) / m.res).astype(int)   # grid_map row of every sample
+    halo, got = 40, np.full(n, 255, np.uint8)
+    for s0, s1 in ((0, 200), (200, 400), (400, 600)):
+        lo, hi = max(0, s0 - halo), min(m.rows, s1 + halo)
+        shard = ap.StateValidityChecker(cases.PARAMS["yaml"], device=0)
+        shard.setMap(m); shard.updateHeightField(window=(lo, hi - lo))
+        sel = np.nonzero((row >= s0) & (row < s1))[0]
+        got[sel] = shard.isValidBatch(poses[sel])
+        shard.pollError()
+        if s0 == 200:   # samples of the neighbouring slab far from this window: loud failure, never a wrong 'valid'
+            far = np.nonzero(row < 100)[0][:500]
+            with pytest.raises(ap.ArtpError) as ei:
+                shard.isValidBatch(poses[far])
+            assert ei.value.code == capi.ARTP_E_WINDOW
+    assert np.array_equal(got, ref)
+    o = port_lib.Oracle(cases.PARAMS["yaml"], "port")
+    o.set_map(m)
+    assert np.array_equal(ref[::40], o.check_poses(poses[::40]))
+    with pytest.raises(ap.ArtpError):
+        whole.updateHeightField(window=(2, 100))      # row0 must be a multiple of 4
+
+
+def test_u32_compaction_and_fused_bits(maps, checkers):
+    import torch
+    from art_planner_b200 import sharding
+    m = maps("fbm_rough")
+    chk = checkers("yaml")
+    set_map(chk, m)
+    d = torch.from_numpy(synth.make_terrain_poses(m, 70001, seed=77)).cuda()
+    v = torch.empty(70001, dtype=torch.uint8, device="cuda")
+    bits = torch.empty((70001 + 31) // 32, dtype=torch.int32, device="cuda")
+    chk.isValidBatchBits(d, v, bits)
+    idx, cnt = chk.compactValidU32(v, base=5)
+    torch.cuda.synchronize()
+    assert torch.equal(v, chk.isValidBatch(d))
+    assert torch.equal(bits.cpu(), sharding.pack_bits_reference(v.cpu()))
+    want = torch.nonzero(v).reshape(-1).to(torch.int32) + 5
+    assert int(cnt.item()) == want.numel() and torch.equal(idx[: want.numel()], want)
