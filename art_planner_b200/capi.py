@@ -88,6 +88,9 @@ def load():
     lib.artp_get_stats.argtypes = [vp, C.POINTER(ArtpStats)]
     lib.artp_set_mode.argtypes = [vp, i32]
     lib.artp_poll_error.argtypes = [vp]
+    lib.artp_host_alloc.restype = C.c_void_p
+    lib.artp_host_alloc.argtypes = [sz]
+    lib.artp_host_free.argtypes = [vp]
     lib.artp_debug_set_group_capacity.argtypes = [vp, i32]
     lib.artp_set_timing.argtypes = [vp, i32]
     lib.artp_get_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
@@ -118,3 +121,29 @@ def make_params(rp, device: int = 0, cost_weights=(0.0, 1.0, 5.0), risk_threshol
     p.risk_threshold = float(risk_threshold)
     p.device = int(device)
     return p
+
+
+class HostBuffer:
+    """A pinned host array from artp_host_alloc (cudaHostAlloc'd: reaches the device at PCIe line rate), as numpy."""
+
+    def __init__(self, shape, dtype):
+        import numpy as np
+        self.lib = load()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = self.lib.artp_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise ArtpError(ARTP_E_CUDA, "artp_host_alloc failed")
+        buf = (C.c_char * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            self.lib.artp_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

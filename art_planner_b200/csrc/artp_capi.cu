@@ -25,6 +25,7 @@ namespace {
 
 thread_local std::string g_create_error;
 constexpr int kCopyEvents = 16;
+constexpr int kMaxSlices = 64;   // H2D pipeline slices per round of the host-buffer calls
 
 struct Handle {
   artp_params p;
@@ -52,13 +53,21 @@ struct Handle {
   size_t stage_cap = 0;
   cudaStream_t stream = nullptr;    // internal compute stream for the host-buffer API
   cudaStream_t copy_stream = nullptr;   // H2D slices of the host-buffer API
+  cudaStream_t box_stream = nullptr;    // box stages of slice i, concurrent with the copy + classify of slice i + 1
   cudaEvent_t copy_ev[16] = {};
+  cudaEvent_t slice_ev[kMaxSlices] = {};   // classify of slice i done (box_stream waits on it)
+  cudaEvent_t box_ev = nullptr;            // box stages of a round done (stream waits on it)
+  int trace = 0;                           // env ARTP_TRACE: print the timeline of host-fed rounds (debug)
+  cudaEvent_t tr_ev[6] = {};
+  uint32_t* d_slices = nullptr;            // per slice: {big-queue end, big-queue claim, reach-queue end, reach-queue claim}
   int k1_grid = 0, k2_grid = 0, k2_smem = 0, k2_tcap = 0;
   // stage B (artp_tiles.cuh): [0] big tiles (torso queue, 4 warps per CTA), [1] small tiles (reach-box queue, 8 warps)
   artp::TileCfg tile_cfg[2] = {};
   int tile_grid[2] = {0, 0}, tile_smem[2] = {0, 0}, tile_warps[2] = {8, 8};
   CUtensorMap tile_map[2][2];       // [cfg][layer]: 2-D tile maps over elevation / elevation_masked
   int k0_flags = 0;                 // tuning switch of the classify stage (env ARTP_K0_FLAGS: 2 = no vertex probes)
+  bool slice_override = false;
+  size_t slice_items_f64 = 128 * 1024, slice_items_f32 = 256 * 1024;   // H2D pipeline slices of the host-buffer calls (env ARTP_SLICE_ITEMS)
   int mode = 0;
   artp_cnn::State* cnn = nullptr;
   int cnn_mode = 0;
@@ -397,13 +406,112 @@ struct HostFeed {
   const char* host;        // host states
   char* dev;               // device destination (same layout)
   size_t bytes_per_item;
-  size_t slice_items;
+  size_t slice_items;      // classic equal slices (small calls, env override)
+  // Slice schedule of a full round as fractions (0-terminated; empty: equal slices). Copy-bound feeds (doubles) start
+  // big and end small so that little compute is left once the last byte has landed; compute-bound feeds (floats) start
+  // small so that the kernels start early, and use few slices (every slice costs ~65 us of launch tails).
+  float schedule[8];
 };
 
 // The claim counters of the consumer stages restart where the next slice's producers will append (the persistent
 // consumers of the previous slice overshoot their counters).
 __global__ void restart_claims_kernel(uint32_t* ctr) {
   ctr[0] = ctr[3]; ctr[2] = ctr[4];
+}
+
+// Slice i of a piped round is closed: its box stages consume the queue entries [end of slice i-1, current count).
+__global__ void close_slice_kernel(const uint32_t* ctr, uint32_t* slices, int i) {
+  const uint32_t w0 = i ? slices[4 * (i - 1)] : 0u, f0 = i ? slices[4 * (i - 1) + 2] : 0u;
+  slices[4 * i] = ctr[3]; slices[4 * i + 1] = w0;        // big-tile queue: end, claim counter (starts at the slice's begin)
+  slices[4 * i + 2] = ctr[4]; slices[4 * i + 3] = f0;    // reach-box queue
+}
+
+// Host-fed round (the host-buffer entry points): the states arrive in slices over PCIe. Three streams:
+//   copy_stream   H2D of slice i+1
+//   s             classify of slice i as soon as its copy has landed (appends to the two box queues)
+//   box_stream    box stages of slice i over exactly the queue entries its classify appended (own claim counters), then
+//                 the grouping stage once per round
+// so the copy, the classify stage and the box stages of three consecutive slices overlap; s waits for box_stream at the end.
+int run_round_piped(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed, size_t base, size_t end, size_t slice,
+                    uint32_t& launches, size_t& ev_i) {
+  CU_TRY(h, cudaMemsetAsync(h->d_ctr, 0, 7 * sizeof(uint32_t), s));
+  // slice boundaries
+  size_t cut[kMaxSlices + 1];
+  int ncut = 0;
+  cut[0] = base;
+  if (feed->schedule[0] > 0.0f && end - base >= (1u << 18) && !h->slice_override) {
+    double acc = 0.0;
+    for (int i = 0; i < 8 && feed->schedule[i] > 0.0f; ++i) {
+      acc += feed->schedule[i];
+      size_t c = base + (size_t)((double)(end - base) * acc);
+      c = std::min(end, (c + 127) & ~(size_t)127);
+      if (c > cut[ncut]) cut[++ncut] = c;
+    }
+    if (cut[ncut] != end) cut[++ncut] = end;
+  } else {
+    for (size_t lo = base; lo < end; lo += slice) cut[++ncut] = std::min(end, lo + slice);
+  }
+  if (h->trace) { cudaEventRecord(h->tr_ev[0], s); cudaStreamWaitEvent(h->copy_stream, h->tr_ev[0], 0); cudaEventRecord(h->tr_ev[1], h->copy_stream); }
+  for (int si = 0; si < ncut; ++si) {
+    const size_t lo = cut[si], hi = cut[si + 1];
+    CU_TRY(h, cudaMemcpyAsync(feed->dev + lo * feed->bytes_per_item, feed->host + lo * feed->bytes_per_item,
+                              (hi - lo) * feed->bytes_per_item, cudaMemcpyHostToDevice, h->copy_stream));
+    cudaEvent_t ev = h->copy_ev[ev_i++ % kCopyEvents];
+    CU_TRY(h, cudaEventRecord(ev, h->copy_stream));
+    CU_TRY(h, cudaStreamWaitEvent(s, ev, 0));
+    w.item_base = (uint32_t)lo;
+    w.n_items = (uint32_t)hi;
+    artp::classify_items_kernel<<<(unsigned)((hi - lo + 127) / 128), 128, 0, s>>>(
+        h->chk, w, h->d_recs, h->d_recs_f, h->d_ctr + 3, h->d_ctr + 4, (h->mode == 1 ? 1 : 0) | h->k0_flags);
+    close_slice_kernel<<<1, 1, 0, s>>>(h->d_ctr, h->d_slices, si);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(h->slice_ev[si], s));
+    CU_TRY(h, cudaStreamWaitEvent(h->box_stream, h->slice_ev[si], 0));
+    const size_t nb = hi - lo;
+    if (h->chk.reach_tw) {
+      const int wpc = h->tile_warps[1];
+      const unsigned grid_f = (unsigned)std::min<size_t>((size_t)h->tile_grid[1], (4 * nb + wpc - 1) / wpc);
+      artp::box_tiles_warp_kernel<<<grid_f, wpc * 32, h->tile_smem[1], h->box_stream>>>(
+          h->chk, h->tile_map[1][1], h->tile_map[1][1], h->tile_cfg[1], w, h->d_recs_f, h->d_slices + 4 * si + 2, h->d_slices + 4 * si + 3,
+          h->d_ctr + 1, h->d_defer, artp::kDeferReachBit, h->mode == 1);
+      launches += 1;
+    }
+    CU_TRY(h, cudaGetLastError());
+    launches += 2;
+  }
+  {
+    // the big-tile queue (torso boxes: few) is drained ONCE per round, on s, concurrently with the reach-box queue of the
+    // last slices on box_stream; claim counter ctr[0] starts at 0 (memset above), count = ctr[3]
+    const int wpc = h->tile_warps[0];
+    const unsigned grid_w = (unsigned)std::min<size_t>((size_t)h->tile_grid[0], (end - base + wpc - 1) / wpc);
+    artp::box_tiles_warp_kernel<<<grid_w, wpc * 32, h->tile_smem[0], s>>>(h->chk, h->tile_map[0][0], h->tile_map[0][1], h->tile_cfg[0], w,
+                                                                           h->d_recs, h->d_ctr + 3, h->d_ctr, h->d_ctr + 1, h->d_defer, 0u,
+                                                                           h->mode == 1);
+    CU_TRY(h, cudaGetLastError());
+    launches += 1;
+    // the grouping stage (box_stream) needs the deferrals of both queues
+    CU_TRY(h, cudaEventRecord(h->slice_ev[kMaxSlices - 1], s));
+    CU_TRY(h, cudaStreamWaitEvent(h->box_stream, h->slice_ev[kMaxSlices - 1], 0));
+  }
+  if (h->trace) { cudaEventRecord(h->tr_ev[2], h->copy_stream); cudaEventRecord(h->tr_ev[3], s); cudaEventRecord(h->tr_ev[4], h->box_stream); }
+  w.item_base = (uint32_t)base;
+  w.n_items = (uint32_t)end;
+  const unsigned grid_c = (unsigned)std::min<size_t>((size_t)h->k2_grid, 5 * (end - base));
+  artp::box_items_block_kernel<<<grid_c, artp::kBlockStageThreads, h->k2_smem, h->box_stream>>>(h->chk, w, h->d_recs, h->d_recs_f, h->d_ctr + 1,
+                                                                                             h->d_defer, h->k2_tcap, h->d_err);
+  CU_TRY(h, cudaGetLastError());
+  launches += 1;
+  CU_TRY(h, cudaEventRecord(h->box_ev, h->box_stream));
+  CU_TRY(h, cudaStreamWaitEvent(s, h->box_ev, 0));
+  if (h->trace) {
+    cudaEventRecord(h->tr_ev[5], s);
+    cudaEventSynchronize(h->tr_ev[5]);
+    float t[5];
+    for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], h->tr_ev[0], h->tr_ev[i + 1]);
+    std::fprintf(stderr, "[artp trace] copies start %.3f end %.3f | classify end %.3f | box stages end %.3f | grouping end %.3f ms\n", t[0], t[1],
+                 t[2], t[3], t[4]);
+  }
+  return ARTP_OK;
 }
 
 // Launch the pipeline for a prepared Work (items 0 .. w.n_items = the whole call) on stream s, in rounds of
@@ -420,6 +528,12 @@ int run_items(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed = nu
   for (size_t base = 0; base < n_total; base += kChunkItems) {
     const size_t end = std::min(n_total, base + kChunkItems);
     const bool last_round = end == n_total;
+    if (feed && feed->slice_items < end - base && (end - base + feed->slice_items - 1) / feed->slice_items < (size_t)kMaxSlices &&
+        !h->timing) {
+      rc = run_round_piped(h, w, s, feed, base, end, feed->slice_items, launches, ev_i);
+      if (rc) return rc;
+      continue;
+    }
     CU_TRY(h, cudaMemsetAsync(h->d_ctr, 0, 7 * sizeof(uint32_t), s));
     const size_t slice = (feed && feed->slice_items < end - base) ? feed->slice_items : (end - base);
     for (size_t lo = base; lo < end; lo += slice) {
@@ -531,6 +645,11 @@ int artp_create(const artp_params* params, artp_handle** out) {
     return fail("no usable kernel image (built for sm_100a)", e);
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&h->box_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  for (int i = 0; i < kMaxSlices; ++i)
+    if ((e = cudaEventCreateWithFlags(&h->slice_ev[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&h->box_ev, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaMalloc(&h->d_slices, kMaxSlices * 4 * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc", e);
   for (int i = 0; i < kCopyEvents; ++i)
     if ((e = cudaEventCreateWithFlags(&h->copy_ev[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaMalloc(&h->d_ctr, 8 * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc", e);
@@ -540,6 +659,11 @@ int artp_create(const artp_params* params, artp_handle** out) {
   *h->h_err = 0;
   if ((e = cudaHostGetDevicePointer((void**)&h->d_err, h->h_err, 0)) != cudaSuccess) return fail("cudaHostGetDevicePointer", e);
   if (const char* kf = std::getenv("ARTP_K0_FLAGS")) h->k0_flags = std::atoi(kf) & 2;
+  if (std::getenv("ARTP_TRACE")) { h->trace = 1; for (auto& te : h->tr_ev) cudaEventCreate(&te); }
+  if (const char* sl = std::getenv("ARTP_SLICE_ITEMS")) {
+    const long v = std::atol(sl);
+    if (v >= 1024) { h->slice_items_f64 = (size_t)v; h->slice_items_f32 = (size_t)v; h->slice_override = true; }
+  }
   h->cnn = artp_cnn::create(h->device, h->sm_count);
   // checker constants (float casts as the reference's ctor/Pose3FromXYZ arguments make them)
   artp::Checker& c = h->chk;
@@ -561,6 +685,10 @@ void artp_destroy(artp_handle* hh) {
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   for (int i = 0; i < kCopyEvents; ++i) if (h->copy_ev[i]) cudaEventDestroy(h->copy_ev[i]);
+  if (h->box_stream) { cudaStreamSynchronize(h->box_stream); cudaStreamDestroy(h->box_stream); }
+  for (int i = 0; i < kMaxSlices; ++i) if (h->slice_ev[i]) cudaEventDestroy(h->slice_ev[i]);
+  if (h->box_ev) cudaEventDestroy(h->box_ev);
+  cudaFree(h->d_slices);
   for (int k = 0; k < 2; ++k) for (int l = 0; l <= artp::kMaxLevel; ++l) { cudaFree(h->d_T[k][l]); cudaFree(h->d_NF[k][l]); }
   cudaFree(h->d_H[0]); cudaFree(h->d_H[1]); cudaFree(h->d_ctr); cudaFree(h->d_defer); cudaFree(h->d_stage);
   cudaFree(h->d_block_counts); cudaFree(h->d_recs); cudaFree(h->d_recs_f); cudaFree(h->d_samp_layers); cudaFree(h->d_samp_scratch);
@@ -614,6 +742,16 @@ int artp_get_last_stage_timing(artp_handle* hh, float* ms5) {
   for (int i = 0; i < 5; ++i) CU_TRY(h, cudaEventElapsedTime(ms5 + i, h->ev[i], h->ev[i + 1]));
   return ARTP_OK;
 }
+
+// Pinned host memory for the adapter's staging buffers (the contiguous n x 7 state batch it gathers the OMPL states into,
+// the verdict bytes): cudaHostAlloc'd pages reach the device at PCIe line rate (measured 55 GB/s on the B200 boxes, where
+// memory pinned after the fact -- cudaHostRegister, torch's pin_memory -- reached 17-25 GB/s; profiles/pcie_probe.cu).
+void* artp_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+  return p;
+}
+void artp_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int artp_poll_error(artp_handle* hh) {
   if (!hh) return ARTP_E_INVALID;
@@ -898,7 +1036,7 @@ int artp_check_poses(artp_handle* hh, const double* states, size_t n, uint8_t* v
   artp::Work w;
   w.s1 = nullptr; w.s2 = d_states; w.s2f = nullptr; w.valid = d_valid; w.item_base = 0; w.n_items = (uint32_t)n;
   w.steps = 0; w.edge_mode = 0;
-  HostFeed feed{(const char*)states, (char*)d_states, 7 * sizeof(double), 128 * 1024};
+  HostFeed feed{(const char*)states, (char*)d_states, 7 * sizeof(double), h->slice_items_f64, {0.30f, 0.25f, 0.20f, 0.13f, 0.08f, 0.04f, 0.f, 0.f}};
   rc = chain_begin(h, 0, h->stream);
   if (rc) return rc;
   rc = run_items(h, w, h->stream, &feed);
@@ -954,7 +1092,7 @@ int artp_check_poses_f32(artp_handle* hh, const float* states, size_t n, uint8_t
   artp::Work w;
   w.s1 = nullptr; w.s2 = nullptr; w.s2f = d_states; w.valid = d_valid; w.item_base = 0; w.n_items = (uint32_t)n;
   w.steps = 0; w.edge_mode = 0;
-  HostFeed feed{(const char*)states, (char*)d_states, 7 * sizeof(float), 256 * 1024};
+  HostFeed feed{(const char*)states, (char*)d_states, 7 * sizeof(float), h->slice_items_f32, {0.10f, 0.30f, 0.60f, 0.f, 0.f, 0.f, 0.f, 0.f}};
   rc = chain_begin(h, 0, h->stream);
   if (rc) return rc;
   rc = run_items(h, w, h->stream, &feed);

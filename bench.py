@@ -329,9 +329,12 @@ def main():
 
     d_poses = torch.from_numpy(poses).cuda()
     d_valid = torch.empty(n, dtype=torch.uint8, device="cuda")
-    h_poses = torch.from_numpy(poses).pin_memory()
-    h_poses32 = torch.from_numpy(poses.astype(np.float32)).pin_memory()   # the cast Pose3FromSE3 does first, done by the adapter
-    h_valid = torch.empty(n, dtype=torch.uint8).pin_memory()
+    # the adapter's batch buffers: pinned host memory from artp_host_alloc (cudaHostAlloc'd pages: PCIe line rate)
+    from art_planner_b200 import capi
+    hb_poses, hb_poses32, hb_valid = capi.HostBuffer((n, 7), np.float64), capi.HostBuffer((n, 7), np.float32), capi.HostBuffer((n,), np.uint8)
+    hb_poses.array[:] = poses
+    hb_poses32.array[:] = poses.astype(np.float32)        # the cast Pose3FromSE3 does first, done by the adapter
+    h_poses, h_poses32, h_valid = (torch.from_numpy(x.array) for x in (hb_poses, hb_poses32, hb_valid))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
     # Every step produces the verdict bytes, their bit-packed form and the ordered list of valid sample indices of this
     # rank's shard (32-bit, global numbering). N > 1: the ranks exchange the bit masks with ONE NCCL all-gather (125 KB

@@ -110,6 +110,11 @@ int artp_check_poses(artp_handle* h, const double* states, size_t n, uint8_t* va
 /* Same with DEVICE buffers on `stream` (a cudaStream_t cast to void*, may be NULL); asynchronous. */
 int artp_check_poses_device(artp_handle* h, const double* d_states, size_t n, uint8_t* d_valid, void* stream);
 
+/* Pinned host memory for the adapter's batch buffers (states in, verdicts out): pages from cudaHostAlloc reach the device
+ * at PCIe line rate, which memory pinned after the fact does not (profiles/pcie_probe.cu). NULL on failure. */
+void* artp_host_alloc(size_t bytes);
+void  artp_host_free(void* p);
+
 /* float32 states (n x 7 floats): the caller applies the double -> float cast Pose3FromSE3 (utils.h:25-38) performs
  * first; results are identical to the double entry points at half the host<->device traffic. */
 int artp_check_poses_f32(artp_handle* h, const float* states, size_t n, uint8_t* valid);
