@@ -34,6 +34,10 @@ class ArtpSamplerParams(C.Structure):
                 ("low", C.c_double * 2), ("high", C.c_double * 2)]
 
 
+class ArtpSe3Space(C.Structure):
+    _fields_ = [("low", C.c_double * 3), ("high", C.c_double * 3), ("longest_valid_segment_fraction", C.c_double)]
+
+
 class ArtpStats(C.Structure):
     _fields_ = [("poses_checked", C.c_uint64), ("poses_deferred", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("last_deferred", C.c_uint32), ("last_launches", C.c_uint32), ("last_queued_boxes", C.c_uint32),
@@ -66,6 +70,10 @@ def load():
     lib.artp_check_poses_f32_device.argtypes = [vp, vp, sz, vp, vp]
     lib.artp_check_motions.argtypes = [vp, vp, vp, sz, i32, vp]
     lib.artp_check_motions_device.argtypes = [vp, vp, vp, sz, i32, vp, vp]
+    lib.artp_valid_segment_count.argtypes = [C.POINTER(ArtpSe3Space), vp, vp, sz, vp]
+    lib.artp_check_motions_segments.argtypes = [vp, vp, vp, sz, vp, C.POINTER(ArtpSe3Space), vp, vp]
+    lib.artp_edge_matrix_from_states.argtypes = [vp, vp, sz, vp]
+    lib.artp_motion_cost_states.argtypes = [vp, vp, vp, sz, vp, vp, vp]
     lib.artp_check_edge_interiors.argtypes = [vp, vp, vp, sz, vp, C.c_double, vp]
     lib.artp_check_edge_interiors_device.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, vp]
     u64 = C.c_uint64

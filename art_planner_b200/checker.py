@@ -379,6 +379,35 @@ class MotionValidator:
         h.check(lib.artp_check_motions(h.h, a.ctypes.data, b.ctypes.data, n, self.n_steps, out.ctypes.data))
         return out
 
+    @staticmethod
+    def se3Space(synth_map, reach_z: float, fraction: float = 0.01):
+        """The SE3 space parameters Planner::setMap installs (planner.cpp:146-156): x, y bounds = map centre +- the FULL
+        map length, z bounds = finite elevation range -+ reach.z / 2; OMPL's default longest-valid-segment fraction."""
+        lx, ly = synth_map.length
+        e = synth_map.elevation[np.isfinite(synth_map.elevation)]
+        return capi.ArtpSe3Space((C.c_double * 3)(synth_map.cx - lx, synth_map.cy - ly, float(e.min()) - reach_z / 2),
+                                 (C.c_double * 3)(synth_map.cx + lx, synth_map.cy + ly, float(e.max()) + reach_z / 2), float(fraction))
+
+    def validSegmentCount(self, space, s1, s2):
+        """SE3StateSpace::validSegmentCount per edge (OMPL 1.4.2 rule, host arithmetic)."""
+        a = np.ascontiguousarray(s1, dtype=np.float64); b = np.ascontiguousarray(s2, dtype=np.float64)
+        nd = np.empty(a.shape[0], np.int32)
+        self._c.handle.check(self._c.handle.lib.artp_valid_segment_count(C.byref(space), a.ctypes.data, b.ctypes.data, a.shape[0],
+                                                                         nd.ctypes.data))
+        return nd
+
+    def checkMotionSegments(self, s1, s2, nd=None, space=None):
+        """DiscreteMotionValidator::checkMotion(s1, s2, lastValid) for a batch with per-edge segment counts (nd, or the OMPL
+        rule from `space`): returns (valid uint8 [n], lastValid.second float64 [n])."""
+        h, lib = self._c.handle, self._c.handle.lib
+        a = np.ascontiguousarray(s1, dtype=np.float64); b = np.ascontiguousarray(s2, dtype=np.float64)
+        n = a.shape[0]
+        seg = None if nd is None else np.ascontiguousarray(nd, dtype=np.int32)
+        valid = np.empty(n, np.uint8); t = np.empty(n, np.float64)
+        h.check(lib.artp_check_motions_segments(h.h, a.ctypes.data, b.ctypes.data, n, None if seg is None else seg.ctypes.data,
+                                                None if space is None else C.byref(space), valid.ctypes.data, t.ctypes.data))
+        return valid, t
+
     def checkEdgeInteriors(self, s1, s2, n_interp=None, max_lateral: float = 0.5):
         """PRMMotionCost::addValidMilestone's connection loop (prm_motion_cost.cpp:341-372) over a batch of candidate
         edges: per edge the number of leading valid interior states (== n_interp[e] iff the connection is valid).
@@ -489,6 +518,24 @@ class MotionCostObjective:
             out = np.empty((n, 3), dtype=np.float32)
         h.check(lib.artp_motion_cost(h.h, e.ctypes.data, n, out.ctypes.data))
         return out
+
+    def edgeMatrixFromStates(self, s_start, s_target):
+        """[n, 6] float32 rows [tx, ty, tyaw, sx, sy, syaw] as PRMMotionCostMaintainer::updateEdges fills them."""
+        a = np.ascontiguousarray(s_start, dtype=np.float64); b = np.ascontiguousarray(s_target, dtype=np.float64)
+        out = np.empty((a.shape[0], 6), np.float32)
+        self._c.handle.check(self._c.handle.lib.artp_edge_matrix_from_states(a.ctypes.data, b.ctypes.data, a.shape[0], out.ctypes.data))
+        return out
+
+    def updateEdgesBatch(self, s_start, s_target):
+        """PRMMotionCostMaintainer::updateEdges / computeCostForVertexEdges for n graph edges in one call: edge matrix ->
+        cost query -> isFeasible / getCost. Returns (cost float64 [n] with +inf for infeasible edges, feasible uint8 [n],
+        cost3 float32 [n, 3])."""
+        h = self._c.handle
+        a = np.ascontiguousarray(s_start, dtype=np.float64); b = np.ascontiguousarray(s_target, dtype=np.float64)
+        n = a.shape[0]
+        cost = np.empty(n, np.float64); feas = np.empty(n, np.uint8); c3 = np.empty((n, 3), np.float32)
+        h.check(h.lib.artp_motion_cost_states(h.h, a.ctypes.data, b.ctypes.data, n, cost.ctypes.data, feas.ctypes.data, c3.ctypes.data))
+        return cost, feas, c3
 
     def getCost(self, cost3):
         """(cost, feasible) per edge: w_e*E + w_t*T + w_r*R and R <= risk_threshold (motion_cost_objective.h:54-66)."""

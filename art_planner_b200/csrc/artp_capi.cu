@@ -1181,9 +1181,17 @@ __global__ void edge_prefix_kernel(const uint8_t* __restrict__ item_valid, const
   }
 }
 
+static int check_items_prefix(artp_handle* hh, const double* d_s1, const double* d_s2, size_t n, const uint32_t* d_item_off,
+                              size_t total_items, uint8_t* d_item_valid, int32_t* d_valid_prefix, void* stream, int quotient);
+
 int artp_check_edge_interiors_device(artp_handle* hh, const double* d_s1, const double* d_s2, size_t n,
                                      const uint32_t* d_item_off, size_t total_items, uint8_t* d_item_valid,
                                      int32_t* d_valid_prefix, void* stream) {
+  return check_items_prefix(hh, d_s1, d_s2, n, d_item_off, total_items, d_item_valid, d_valid_prefix, stream, 0);
+}
+
+static int check_items_prefix(artp_handle* hh, const double* d_s1, const double* d_s2, size_t n, const uint32_t* d_item_off,
+                              size_t total_items, uint8_t* d_item_valid, int32_t* d_valid_prefix, void* stream, int quotient) {
   if (!hh) return ARTP_E_INVALID;
   Handle* h = reinterpret_cast<Handle*>(hh);
   std::lock_guard<std::recursive_mutex> lk(h->mtx);
@@ -1202,7 +1210,7 @@ int artp_check_edge_interiors_device(artp_handle* hh, const double* d_s1, const 
   if (total_items) {
     artp::Work w;
     w.s1 = d_s1; w.s2 = d_s2; w.s2f = nullptr; w.valid = d_item_valid; w.item_base = 0; w.n_items = (uint32_t)total_items;
-    w.steps = 0; w.edge_mode = 0; w.item_off = d_item_off; w.n_edges = (uint32_t)n;
+    w.steps = 0; w.edge_mode = 0; w.item_off = d_item_off; w.n_edges = (uint32_t)n; w.quotient = quotient;
     rc = run_items(h, w, s);
     if (rc) return rc;
   }
@@ -1266,6 +1274,158 @@ int artp_check_edge_interiors(artp_handle* hh, const double* s1, const double* s
   CU_TRY(h, cudaStreamSynchronize(h->stream));   // `off` must outlive its H2D copy: it does, we synchronise here
   h->chain_busy[0] = false;
   return take_sticky_error(h);
+}
+
+// ompl::base::CompoundStateSpace::validSegmentCount for SE3 = max over the R^3 and SO(3) sub-spaces of
+// (unsigned)ceil(distance / (maximum extent * longest valid segment fraction)) (OMPL 1.4.2 StateSpace.cpp;
+// RealVectorStateSpace: Euclidean distance, extent = |high - low|; SO3StateSpace: arc length acos(|q1.q2|) with
+// the 1e-9 clamp, extent pi/2). Host arithmetic, doubles, like OMPL.
+int artp_valid_segment_count(const artp_se3_space* sp, const double* s1, const double* s2, size_t n, int32_t* nd) {
+  if (!sp || (n && (!s1 || !s2 || !nd))) return ARTP_E_INVALID;
+  const double frac = sp->longest_valid_segment_fraction > 0 ? sp->longest_valid_segment_fraction : 0.01;
+  double e2 = 0;
+  for (int i = 0; i < 3; ++i) e2 += (sp->high[i] - sp->low[i]) * (sp->high[i] - sp->low[i]);
+  const double seg_r3 = std::sqrt(e2) * frac, seg_so3 = 0.5 * 3.14159265358979323846 * frac;
+  if (!(seg_r3 > 0)) return ARTP_E_INVALID;
+  for (size_t i = 0; i < n; ++i) {
+    const double* a = s1 + 7 * i;
+    const double* b = s2 + 7 * i;
+    const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+    const double d3 = std::sqrt(dx * dx + dy * dy + dz * dz);
+    const double dq = std::fabs(a[3] * b[3] + a[4] * b[4] + a[5] * b[5] + a[6] * b[6]);
+    const double ds = (dq > 1.0 - 1e-9) ? 0.0 : std::acos(dq);
+    const unsigned n3 = (unsigned)std::ceil(d3 / seg_r3), ns = (unsigned)std::ceil(ds / seg_so3);
+    nd[i] = (int32_t)std::max(n3, ns);
+  }
+  return ARTP_OK;
+}
+
+int artp_check_motions_segments(artp_handle* hh, const double* s1, const double* s2, size_t n, const int32_t* nd,
+                                const artp_se3_space* sp, uint8_t* valid, double* last_valid_t) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);   // held across stage -> launch -> D2H
+  if (!h->has_map) { h->err = "no map set"; return ARTP_E_NOMAP; }
+  if (n == 0) return ARTP_OK;
+  if (!s1 || !s2 || !valid || (!nd && !sp)) { h->err = "null buffer (nd == NULL needs the space parameters)"; return ARTP_E_INVALID; }
+  std::vector<int32_t> seg(n);
+  if (nd) std::copy(nd, nd + n, seg.begin());
+  else { const int rc = artp_valid_segment_count(sp, s1, s2, n, seg.data()); if (rc) { h->err = "bad SE3 space parameters"; return rc; } }
+  std::vector<uint32_t> off(n + 1);
+  size_t total = 0;
+  for (size_t e = 0; e < n; ++e) {
+    if (seg[e] < 0) { h->err = "segment count < 0"; return ARTP_E_INVALID; }
+    if (seg[e] < 1) seg[e] = 1;                 // nd = 0 (identical states): only s2 is checked
+    off[e] = (uint32_t)total;
+    total += (size_t)seg[e];
+    if (total >= 0xFFFFFFFFull) { h->err = "too many states (>= 2^32)"; return ARTP_E_INVALID; }
+  }
+  off[n] = (uint32_t)total;
+  const size_t sb = n * 7 * sizeof(double), sb_al = (sb + 255) & ~(size_t)255;
+  const size_t ob_al = ((n + 1) * sizeof(uint32_t) + 255) & ~(size_t)255, pb_al = (n * sizeof(int32_t) + 255) & ~(size_t)255;
+  CU_TRY(h, cudaSetDevice(h->device));
+  int rc = chain_begin(h, 0, h->stream);
+  if (rc) return rc;
+  rc = ensure_stage(h, 2 * sb_al + ob_al + pb_al + total + 256);
+  if (rc) return rc;
+  char* base = (char*)h->d_stage;
+  CU_TRY(h, cudaMemcpyAsync(base, s1, sb, cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, cudaMemcpyAsync(base + sb_al, s2, sb, cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, cudaMemcpyAsync(base + 2 * sb_al, off.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  int32_t* d_prefix = (int32_t*)(base + 2 * sb_al + ob_al);
+  rc = check_items_prefix(hh, (const double*)base, (const double*)(base + sb_al), n, (const uint32_t*)(base + 2 * sb_al), total,
+                          (uint8_t*)(base + 2 * sb_al + ob_al + pb_al), d_prefix, h->stream, 1);
+  if (rc) return rc;
+  std::vector<int32_t> prefix(n);
+  CU_TRY(h, cudaMemcpyAsync(prefix.data(), d_prefix, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->chain_busy[0] = false;
+  for (size_t e = 0; e < n; ++e) {
+    // DiscreteMotionValidator::checkMotion(s1, s2, lastValid): the first invalid state in the order j = 1 .. nd-1, s2
+    // is state index p (0-based) => lastValid.second = p / nd  ((j-1)/nd for an interior state, (nd-1)/nd for s2)
+    valid[e] = prefix[e] == seg[e] ? 1 : 0;
+    if (last_valid_t) last_valid_t[e] = valid[e] ? 1.0 : (double)prefix[e] / (double)seg[e];
+  }
+  return take_sticky_error(h);
+}
+
+// Rows [tx, ty, tyaw, sx, sy, syaw] of the MotionCostFunc edge matrix from SE(3) states exactly as
+// PRMMotionCostMaintainer::updateEdges / computeCostForVertexEdges fill them (prm_motion_cost.cpp:27-128): x, y cast
+// double -> float by the assignment into the float matrix, yaw = getYawFromSO3 (utils.h:80-88: double atan2, float result).
+__global__ void edge_matrix_kernel(const double* __restrict__ s_start, const double* __restrict__ s_target, size_t n,
+                                   float* __restrict__ edges) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double* a = s_start + 7 * i;
+    const double* b = s_target + 7 * i;
+    float* o = edges + 6 * i;
+    o[0] = (float)b[0]; o[1] = (float)b[1];
+    o[2] = (float)atan2(2 * (b[6] * b[5] + b[3] * b[4]), 1 - 2 * (b[4] * b[4] + b[5] * b[5]));
+    o[3] = (float)a[0]; o[4] = (float)a[1];
+    o[5] = (float)atan2(2 * (a[6] * a[5] + a[3] * a[4]), 1 - 2 * (a[4] * a[4] + a[5] * a[5]));
+  }
+}
+// getCost / isFeasible per row (motion_cost_objective.h:54-66); infeasible edges get +inf like updateEdges (:56-59)
+__global__ void combine_cost_kernel(const float* __restrict__ cost3, size_t n, float we, float wt, float wr, float thr,
+                                    double* __restrict__ cost, uint8_t* __restrict__ feasible) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float ce = cost3[3 * i], ct = cost3[3 * i + 1], cr = cost3[3 * i + 2];
+    const bool ok = (double)cr <= (double)thr;
+    feasible[i] = ok ? 1 : 0;
+    cost[i] = ok ? (double)ce * (double)we + (double)ct * (double)wt + (double)cr * (double)wr : CUDART_INF;
+  }
+}
+
+int artp_edge_matrix_from_states(const double* s_start, const double* s_target, size_t n, float* edges) {
+  if (n && (!s_start || !s_target || !edges)) return ARTP_E_INVALID;
+  for (size_t i = 0; i < n; ++i) {
+    const double* a = s_start + 7 * i;
+    const double* b = s_target + 7 * i;
+    float* o = edges + 6 * i;
+    o[0] = (float)b[0]; o[1] = (float)b[1];
+    o[2] = (float)std::atan2(2 * (b[6] * b[5] + b[3] * b[4]), 1 - 2 * (b[4] * b[4] + b[5] * b[5]));
+    o[3] = (float)a[0]; o[4] = (float)a[1];
+    o[5] = (float)std::atan2(2 * (a[6] * a[5] + a[3] * a[4]), 1 - 2 * (a[4] * a[4] + a[5] * a[5]));
+  }
+  return ARTP_OK;
+}
+
+int artp_motion_cost_states(artp_handle* hh, const double* s_start, const double* s_target, size_t n, double* cost,
+                            uint8_t* feasible, float* cost3) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);   // held across stage -> launch -> D2H
+  if (n == 0) return ARTP_OK;
+  if (!s_start || !s_target || !cost || !feasible) { h->err = "null buffer"; return ARTP_E_INVALID; }
+  CU_TRY(h, cudaSetDevice(h->device));
+  const size_t sb = n * 7 * sizeof(double), sb_al = (sb + 255) & ~(size_t)255, eb_al = (n * 6 * sizeof(float) + 255) & ~(size_t)255,
+               cb_al = (n * 3 * sizeof(float) + 255) & ~(size_t)255, db_al = (n * sizeof(double) + 255) & ~(size_t)255;
+  int rc = chain_begin(h, 0, h->stream);
+  if (rc) return rc;
+  rc = ensure_stage(h, 2 * sb_al + eb_al + cb_al + db_al + n);
+  if (rc) return rc;
+  char* base = (char*)h->d_stage;
+  float* d_edges = (float*)(base + 2 * sb_al);
+  float* d_c3 = (float*)(base + 2 * sb_al + eb_al);
+  double* d_cost = (double*)(base + 2 * sb_al + eb_al + cb_al);
+  uint8_t* d_feas = (uint8_t*)(base + 2 * sb_al + eb_al + cb_al + db_al);
+  CU_TRY(h, cudaMemcpyAsync(base, s_start, sb, cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, cudaMemcpyAsync(base + sb_al, s_target, sb, cudaMemcpyHostToDevice, h->stream));
+  const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 8);
+  edge_matrix_kernel<<<grid, 256, 0, h->stream>>>((const double*)base, (const double*)(base + sb_al), n, d_edges);
+  CU_TRY(h, cudaGetLastError());
+  rc = artp_cnn::motion_cost(h->cnn, d_edges, n, d_c3, h->stream, h->err);
+  if (rc) return rc;
+  combine_cost_kernel<<<grid, 256, 0, h->stream>>>(d_c3, n, h->p.cost_w_energy, h->p.cost_w_time, h->p.cost_w_risk, h->p.risk_threshold, d_cost,
+                                                   d_feas);
+  CU_TRY(h, cudaGetLastError());
+  CU_TRY(h, cudaMemcpyAsync(cost, d_cost, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaMemcpyAsync(feasible, d_feas, n, cudaMemcpyDeviceToHost, h->stream));
+  if (cost3) CU_TRY(h, cudaMemcpyAsync(cost3, d_c3, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->chain_busy[0] = false;
+  h->stats.kernel_launches += 3;
+  h->stats.last_launches = 3;
+  return ARTP_OK;
 }
 
 int artp_path_length_cost_device(artp_handle* hh, const double* d_s1, const double* d_s2, size_t n, double* d_cost,

@@ -52,6 +52,9 @@ struct Work {
   // t = j * (1.0 / (n_e + 1)), n_e = item_off[e+1] - item_off[e]  (prm_motion_cost.cpp:345-353); valid[] is per item.
   const uint32_t* item_off = nullptr;   // n_edges + 1 exclusive prefix sums of the per-edge interior-state counts
   uint32_t n_edges = 0;
+  // SEGMENT mode (item_off != null, quotient = 1): OMPL DiscreteMotionValidator over nd_e = item_off[e+1] - item_off[e]
+  // segments: item k of edge e is interpolate(s1, s2, (k + 1) / nd_e) for k < nd_e - 1 and s2 itself for k = nd_e - 1.
+  int quotient = 0;
 };
 
 __device__ __forceinline__ uint32_t bloom_hash(int kx, int kz) {
@@ -101,10 +104,19 @@ __device__ __forceinline__ void load_item_state(const Work& w, uint32_t item, do
     }
     const uint32_t o0 = __ldg(w.item_off + lo), o1 = __ldg(w.item_off + lo + 1);
     const int n_e = (int)(o1 - o0), step = (int)(item - o0) + 1;
-    const double n_interp_div = 1.0 / (double)(n_e + 1);
     double a[7], b[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) { a[k] = w.s1[(size_t)lo * 7 + k]; b[k] = w.s2[(size_t)lo * 7 + k]; }
+    if (w.quotient) {
+      if (step == n_e) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) s[k] = b[k];
+      } else {
+        se3_interpolate(a, b, (double)step / (double)n_e, s);
+      }
+      return;
+    }
+    const double n_interp_div = 1.0 / (double)(n_e + 1);
     se3_interpolate(a, b, (double)step * n_interp_div, s);
     return;
   }
@@ -570,7 +582,7 @@ struct alignas(16) BoxRec {
   float P[3];
   float minB, maxB;
   int x0, x1, z0, z1;
-  uint32_t item;     // work item id
+  uint32_t item;     // verdict slot of the work item (pose index / edge index / interior-state index)
   uint32_t flags;    // bits 0-2: box (0 torso, 1..4 feet); bit 3: zone all finite; bit 4: zone not reduced yet;
                      // bit 5: no mergeable triangle pair in the zone (plane tables, artp_set_map)
 };
@@ -777,7 +789,7 @@ classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs_w
     o.P[0] = b.P[0]; o.P[1] = b.P[1]; o.P[2] = b.P[2];
     o.minB = b.minB; o.maxB = b.maxB;
     o.x0 = b.x0; o.x1 = b.x1; o.z0 = b.z0; o.z1 = b.z1;
-    o.item = item; o.flags = uflags[src];
+    o.item = slot; o.flags = uflags[src];      // later stages only need the verdict slot
   }
 }
 
@@ -960,7 +972,7 @@ box_items_block_kernel(const Checker c, const Work w, const BoxRec* __restrict__
   for (uint32_t q = blockIdx.x; q < count; q += gridDim.x) {
     const uint32_t e = defer_list[q];     // bit 31: record of the reach-box queue
     const BoxRec r = (e & 0x80000000u) ? recs_f[e & 0x7fffffffu] : recs[e];
-    const uint32_t slot = item_slot(w, r.item);
+    const uint32_t slot = r.item;
     const bool foot = (r.flags & 7) != 0;
     BoxCtx b;
     rec_to_ctx(c, r, b);

@@ -110,7 +110,7 @@ box_tiles_warp_kernel(const Checker c, const __grid_constant__ CUtensorMap map0,
         for (int i = 0; i < 5; ++i) dst[i] = __ldg(rp + i);
       }
       if (tc.slots == 2 && ri + 1 < r1) { __syncwarp(); prefetch(ri + 1, slot ^ 1); }   // the other slot's box (ri - 1) is finished
-      const uint32_t slot_item = item_slot(w, r.item);
+      const uint32_t slot_item = r.item;
       const bool foot = (r.flags & 7) != 0;
       // another box of the item (or state of the edge) already failed: nothing can change the verdict (perf only)
       int dead = 0;

@@ -125,6 +125,21 @@ int artp_check_motions(artp_handle* h, const double* s1, const double* s2, size_
 int artp_check_motions_device(artp_handle* h, const double* d_s1, const double* d_s2, size_t n, int n_steps,
                               uint8_t* d_valid, void* stream);
 
+/* ompl::base::DiscreteMotionValidator::checkMotion(s1, s2[, lastValid]) (OMPL 1.4.2; the reference's default motion
+ * validator, call sites prm_motion_cost.cpp:652, lazy_prm_star_min_update.cpp:725) with PER-EDGE segment counts:
+ * edge e is valid iff interpolate(s1, s2, j / nd[e]) is valid for j = 1 .. nd[e]-1 and s2 is valid. nd[e] =
+ * SE3StateSpace::validSegmentCount(s1, s2); nd == NULL: computed by artp_valid_segment_count from *sp (the space
+ * parameters Planner::setMap installs, planner.cpp:146-156). last_valid_t (nullable) receives lastValid.second: the
+ * parameter of the last valid state before the first invalid one in OMPL's order ((j-1)/nd, or (nd-1)/nd when only s2
+ * is invalid; 1.0 for valid edges) -- the caller obtains lastValid.first by interpolating at that parameter. */
+typedef struct artp_se3_space {
+  double low[3], high[3];                  /* RealVectorBounds of the SE3 space (planner.cpp:148-156) */
+  double longest_valid_segment_fraction;   /* OMPL default 0.01 (the reference never changes it); <= 0 means 0.01 */
+} artp_se3_space;
+int artp_valid_segment_count(const artp_se3_space* sp, const double* s1, const double* s2, size_t n, int32_t* nd);
+int artp_check_motions_segments(artp_handle* h, const double* s1, const double* s2, size_t n, const int32_t* nd,
+                                const artp_se3_space* sp, uint8_t* valid, double* last_valid_t);
+
 /* PRMMotionCost::addValidMilestone's connection test (prm_motion_cost.cpp:341-372), batched over the n candidate
  * edges of new milestones: edge e has n_interp[e] interior states at t = step * (1.0 / (n_interp[e] + 1)),
  * step = 1..n_interp[e] (endpoints are NOT checked there), and the reference loop stops at the first invalid one.
@@ -260,6 +275,14 @@ int artp_update_features(artp_handle* h);
  * (energy, time, risk = 1 - p_success). HOST buffers. */
 int artp_motion_cost(artp_handle* h, const float* edges, size_t n, float* cost3);
 int artp_motion_cost_device(artp_handle* h, const float* d_edges, size_t n, float* d_cost3, void* stream);
+/* PRMMotionCostMaintainer::updateEdges / computeCostForVertexEdges (prm_motion_cost.cpp:27-128) for n graph edges
+ * (source vertex state s_start = v1, target vertex state s_target = v2): the [n x 6] float edge matrix
+ * [tx, ty, tyaw, sx, sy, syaw] with getYawFromSO3 (utils.h:80-88) ... */
+int artp_edge_matrix_from_states(const double* s_start, const double* s_target, size_t n, float* edges);
+/* ... and the whole batch in one call: edge matrix -> cost query -> isFeasible / getCost per row. cost[i] = +inf for
+ * infeasible (too risky) edges exactly like updateEdges (:56-59); cost3 (nullable): the raw (energy, time, risk) rows. */
+int artp_motion_cost_states(artp_handle* h, const double* s_start, const double* s_target, size_t n, double* cost,
+                            uint8_t* feasible, float* cost3);
 /* MotionCostObjective::getCost / isFeasible (motion_cost_objective.h:54-66) on host arrays:
  * cost[i] = w_e*E + w_t*T + w_r*R, feasible[i] = R <= risk_threshold (weights / threshold from artp_params). */
 int artp_combine_cost(artp_handle* h, const float* cost3, size_t n, double* cost, uint8_t* feasible);

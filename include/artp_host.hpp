@@ -273,6 +273,54 @@ class MotionValidator {
     const auto& h = checker_->handle();
     h->check(artp_check_motions(h->get(), &s1[0].x, &s2[0].x, s1.size(), nd_ - 1, valid->data()), "artp_check_motions");
   }
+  // DiscreteMotionValidator::checkMotion(s1, s2, lastValid) with this validator's segment count: returns validity and,
+  // for an invalid motion, lastValid.second = the parameter of the last valid state before the first invalid one in
+  // OMPL's order (j = 1 .. nd-1, then s2); *last_valid (nullable) receives interpolate(s1, s2, that parameter).
+  bool checkMotion(const State* s1, const State* s2, double* last_valid_t, State* last_valid) const {
+    uint8_t v = 0;
+    double t = 1.0;
+    const int32_t nd = nd_;
+    const auto& h = checker_->handle();
+    h->check(artp_check_motions_segments(h->get(), &s1->x, &s2->x, 1, &nd, nullptr, &v, &t), "artp_check_motions_segments");
+    if (!v) {
+      if (last_valid_t) *last_valid_t = t;
+      if (last_valid) *last_valid = interpolateSE3(*s1, *s2, t);
+    }
+    return v != 0;
+  }
+  // The batch form with PER-EDGE segment counts nd[e] = SE3StateSpace::validSegmentCount(s1, s2) (OMPL 1.4.2 rule,
+  // artp_valid_segment_count) -- what si_->checkMotion does at prm_motion_cost.cpp:652 / lazy_prm_star_min_update.cpp:725.
+  void checkMotionSegments(const std::vector<State>& s1, const std::vector<State>& s2, const artp_se3_space& space,
+                           std::vector<uint8_t>* valid, std::vector<double>* last_valid_t, std::vector<int32_t>* nd = nullptr) const {
+    if (s1.size() != s2.size()) throw std::invalid_argument("checkMotionSegments: size mismatch");
+    valid->resize(s1.size());
+    last_valid_t->resize(s1.size());
+    if (s1.empty()) return;
+    std::vector<int32_t> seg(s1.size());
+    const auto& h = checker_->handle();
+    h->check(artp_valid_segment_count(&space, &s1[0].x, &s2[0].x, s1.size(), seg.data()), "artp_valid_segment_count");
+    h->check(artp_check_motions_segments(h->get(), &s1[0].x, &s2[0].x, s1.size(), seg.data(), nullptr, valid->data(),
+                                         last_valid_t->data()), "artp_check_motions_segments");
+    if (nd) *nd = seg;
+  }
+  // OMPL 1.4.2 SE3StateSpace::interpolate = RealVector lerp + SO3 slerp
+  static State interpolateSE3(const State& a, const State& b, double t) {
+    State o;
+    o.x = a.x + (b.x - a.x) * t; o.y = a.y + (b.y - a.y) * t; o.z = a.z + (b.z - a.z) * t;
+    const double dq = a.qx * b.qx + a.qy * b.qy + a.qz * b.qz + a.qw * b.qw;
+    const double dqa = std::fabs(dq);
+    const double theta = (dqa > 1.0 - 1e-9) ? 0.0 : std::acos(dqa);
+    if (theta > std::numeric_limits<double>::epsilon()) {
+      const double d = 1.0 / std::sin(theta), s0 = std::sin((1.0 - t) * theta);
+      double s1 = std::sin(t * theta);
+      if (dq < 0) s1 = -s1;
+      o.qx = (a.qx * s0 + b.qx * s1) * d; o.qy = (a.qy * s0 + b.qy * s1) * d;
+      o.qz = (a.qz * s0 + b.qz * s1) * d; o.qw = (a.qw * s0 + b.qw * s1) * d;
+    } else {
+      o.qx = a.qx; o.qy = a.qy; o.qz = a.qz; o.qw = a.qw;
+    }
+    return o;
+  }
   // PRMMotionCost::addValidMilestone's connection loop (prm_motion_cost.cpp:341-372) for a batch of candidate edges:
   // n_interp[e] = (unsigned)(lateralDistance / max_lateral) interior states, valid_prefix[e] = how many leading ones are
   // valid; the connection holds iff valid_prefix[e] == n_interp[e].
@@ -393,6 +441,19 @@ class MotionCostObjective {
   }
   double motionCostHeuristic(const State*, const State*) const { return 0.0; }   // motion_cost_objective.cpp:99-103
 
+  // PRMMotionCostMaintainer::updateEdges / computeCostForVertexEdges (prm_motion_cost.cpp:27-128) for a batch of graph
+  // edges (source = v1, target = v2): edge matrix -> cost query -> per edge isFeasible ? getCost : +inf, in one device call.
+  // Returns false where the reference's functor would (then the graph is left alone, :69-72 / :124-127).
+  bool updateEdgesBatch(const std::vector<State>& source, const std::vector<State>& target, std::vector<double>* cost,
+                        std::vector<uint8_t>* feasible) const {
+    if (source.size() != target.size()) throw std::invalid_argument("updateEdgesBatch: size mismatch");
+    cost->resize(source.size());
+    feasible->resize(source.size());
+    if (source.empty()) return true;
+    return artp_motion_cost_states(checker_->handle()->get(), &source[0].x, &target[0].x, source.size(), cost->data(),
+                                   feasible->data(), nullptr) == ARTP_OK;
+  }
+
   // getYawFromSO3 (utils.h:80-88): double atan2 returned through float
   static float yaw(const State& s) {
     return static_cast<float>(std::atan2(2 * (s.qw * s.qz + s.qx * s.qy), 1 - 2 * (s.qy * s.qy + s.qz * s.qz)));
@@ -454,9 +515,14 @@ class OmplMotionValidator : public ob::MotionValidator {
     return MotionValidator(c_, si_->getStateSpace()->validSegmentCount(s1, s2)).checkMotion(&a, &b);
   }
   bool checkMotion(const ob::State* s1, const ob::State* s2, std::pair<ob::State*, double>& lastValid) const override {
-    lastValid.second = 0.0;
-    if (lastValid.first) si_->copyState(lastValid.first, s1);
-    return checkMotion(s1, s2);
+    const State a = fromOmpl(s1), b = fromOmpl(s2);
+    double t = 1.0;
+    const bool ok = MotionValidator(c_, si_->getStateSpace()->validSegmentCount(s1, s2)).checkMotion(&a, &b, &t, nullptr);
+    if (!ok) {   // DiscreteMotionValidator: lastValid is only written for invalid motions
+      lastValid.second = t;
+      if (lastValid.first) si_->getStateSpace()->interpolate(s1, s2, t, lastValid.first);
+    }
+    return ok;
   }
  private:
   StateValidityCheckerPtr c_;

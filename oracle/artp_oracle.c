@@ -837,3 +837,27 @@ int orc_check_motions_mt(orc_handle* h, const double* s1, const double* s2, size
   free(th); free(jobs);
   return 0;
 }
+
+int orc_valid_segment_count(const double low[3], const double high[3], double frac, const double* s1, const double* s2, size_t n,
+                            int32_t* nd) {
+  for (size_t i = 0; i < n; ++i) nd[i] = orc_valid_segment_count_1(low, high, frac, s1 + 7 * i, s2 + 7 * i);
+  return 0;
+}
+
+int orc_check_motions_segments(orc_handle* h, const double* s1, const double* s2, size_t n, const int32_t* nd, uint8_t* valid,
+                               double* last_t) {
+  if (!h || !h->g.has_map) return 1;
+  port_ctx c = {h, {0, 0, 0, 0, 0, 0, 0}};
+  for (size_t i = 0; i < n; ++i) {
+    double t = 1.0;
+    valid[i] = (uint8_t)orc_motion_last_valid(&h->p, &h->g, port_collide, &c, s1 + 7 * i, s2 + 7 * i, nd[i], &t);
+    if (last_t) last_t[i] = t;
+  }
+  free(c.sc.tri); free(c.sc.group);
+  return 0;
+}
+
+int orc_edge_matrix(const double* s_start, const double* s_target, size_t n, float* edges) {
+  for (size_t i = 0; i < n; ++i) orc_edge_matrix_row(s_start + 7 * i, s_target + 7 * i, edges + 6 * i);
+  return 0;
+}

@@ -128,6 +128,15 @@ int orc_check_poses_mt(orc_handle* h, const double* states, size_t n, uint8_t* v
 int orc_check_motions_mt(orc_handle* h, const double* s1, const double* s2, size_t n, int n_steps, uint8_t* valid,
                          int n_threads);
 
+/* OMPL 1.4.2 SE3StateSpace::validSegmentCount and DiscreteMotionValidator::checkMotion(s1, s2, lastValid) restated
+ * (artp_wrappers.h; OMPL is not in the reference tree: parity unpinned at this level), and the MotionCostFunc edge-matrix
+ * rows of PRMMotionCostMaintainer::updateEdges (prm_motion_cost.cpp:27-47). last_t[i] = lastValid.second (1.0 if valid). */
+int orc_valid_segment_count(const double low[3], const double high[3], double frac, const double* s1, const double* s2, size_t n,
+                            int32_t* nd);
+int orc_check_motions_segments(orc_handle* h, const double* s1, const double* s2, size_t n, const int32_t* nd, uint8_t* valid,
+                               double* last_t);
+int orc_edge_matrix(const double* s_start, const double* s_target, size_t n, float* edges);
+
 /* Identifies the implementation: "port" or "reference". */
 const char* orc_kind(void);
 

@@ -183,6 +183,46 @@ static inline double orc_path_length(const orc_params* p, const double s1[7], co
   return m > t_yaw ? m : t_yaw;
 }
 
+/* ompl::base::CompoundStateSpace::validSegmentCount for SE3StateSpace (OMPL 1.4.2, not in the reference tree; call
+ * sites via si_->checkMotion, prm_motion_cost.cpp:652, lazy_prm_star_min_update.cpp:725): max over the sub-spaces of
+ * longestValidSegmentCountFactor (1) * (unsigned)ceil(distance / longestValidSegment), longestValidSegment = maximum
+ * extent * fraction; R^3: Euclidean distance, extent |high - low| (bounds of planner.cpp:148-156); SO(3): arc length
+ * acos(|q1.q2|) (0 above 1 - 1e-9), extent pi/2. */
+static inline int32_t orc_valid_segment_count_1(const double low[3], const double high[3], double frac, const double a[7],
+                                                const double b[7]) {
+  double e2 = 0;
+  for (int i = 0; i < 3; ++i) e2 += (high[i] - low[i]) * (high[i] - low[i]);
+  const double seg_r3 = sqrt(e2) * frac, seg_so3 = 0.5 * M_PI * frac;
+  const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+  const double d3 = sqrt(dx * dx + dy * dy + dz * dz);
+  const double dq = fabs(a[3] * b[3] + a[4] * b[4] + a[5] * b[5] + a[6] * b[6]);
+  const double ds = (dq > 1.0 - 1e-9) ? 0.0 : acos(dq);
+  const unsigned n3 = (unsigned)ceil(d3 / seg_r3), ns = (unsigned)ceil(ds / seg_so3);
+  return (int32_t)(n3 > ns ? n3 : ns);
+}
+
+/* ompl::base::DiscreteMotionValidator::checkMotion(s1, s2, lastValid) (OMPL 1.4.2 DiscreteMotionValidator.cpp): interior
+ * states j = 1 .. nd-1 at t = j / nd IN ORDER, the first invalid one sets lastValid.second = (j-1)/nd; then s2, whose
+ * failure sets (nd-1)/nd. Returns validity; *last_t untouched for valid motions. nd < 1 is treated as 1. */
+static inline int orc_motion_last_valid(const orc_params* p, const orc_geom* g, orc_collide_fn collide, void* ctx,
+                                        const double a[7], const double b[7], int32_t nd, double* last_t) {
+  if (nd < 1) nd = 1;
+  for (int32_t j = 1; j < nd; ++j) {
+    double st[7];
+    orc_se3_interpolate(a, b, (double)j / (double)nd, st);
+    if (!orc_state_valid(p, g, collide, ctx, st, NULL)) { *last_t = (double)(j - 1) / (double)nd; return 0; }
+  }
+  if (!orc_state_valid(p, g, collide, ctx, b, NULL)) { *last_t = (double)(nd - 1) / (double)nd; return 0; }
+  return 1;
+}
+
+/* One row [tx, ty, tyaw, sx, sy, syaw] of the MotionCostFunc edge matrix as PRMMotionCostMaintainer::updateEdges fills it
+ * (prm_motion_cost.cpp:27-47): doubles assigned into a float matrix, yaw through getYawFromSO3's float. */
+static inline void orc_edge_matrix_row(const double s_start[7], const double s_target[7], float row[6]) {
+  row[0] = (float)s_target[0]; row[1] = (float)s_target[1]; row[2] = (float)orc_yaw_from_quat(s_target);
+  row[3] = (float)s_start[0]; row[4] = (float)s_start[1]; row[5] = (float)orc_yaw_from_quat(s_start);
+}
+
 #ifdef __cplusplus
 }
 #endif

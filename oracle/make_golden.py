@@ -73,6 +73,19 @@ def main() -> None:
         out[name + "/prefix"] = k.astype(np.int8)
         out[name + "/sha"] = np.array(digest(m.elevation, m.elevation_masked, s1, s2))
         print(f"{name}: prefix histogram {np.bincount(k).tolist()}")
+    for name, mk, pk, n, seed, dmin, dmax in cases.SEGMENT_CASES:
+        m = maps[mk]
+        o = Oracle(cases.PARAMS[pk], "reference")
+        o.set_map(m)
+        s1, s2 = synth.make_edges(m, n, seed, dmin=dmin, dmax=dmax)
+        low, high = cases.se3_bounds(m, cases.PARAMS[pk].reach_z)
+        nd = o.valid_segment_count(low, high, s1, s2)
+        v, t = o.check_motions_segments(s1, s2, nd)
+        out[name + "/mask"] = np.packbits(v)
+        out[name + "/nd"] = nd.astype(np.int32)
+        out[name + "/last_t"] = t
+        out[name + "/sha"] = np.array(digest(m.elevation, m.elevation_masked, s1, s2))
+        print(f"{name}: valid={int(v.sum())}/{n} nd range {nd.min()}..{nd.max()}")
     path = os.path.join(ROOT, "tests", "golden", "reference_masks.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -216,6 +216,36 @@ class Oracle:
         assert f(self.h, s.ctypes.data, n, st.ctypes.data, hit.ctypes.data, zv.ctypes.data) == 0
         return st, hit, zv
 
+    def valid_segment_count(self, low, high, s1, s2, frac=0.01):
+        a, b = _f64(s1), _f64(s2)
+        n = a.shape[0]
+        nd = np.zeros(n, np.int32)
+        f = self.lib.orc_valid_segment_count
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        lo, hi = _f64(low), _f64(high)
+        assert f(lo.ctypes.data, hi.ctypes.data, float(frac), a.ctypes.data, b.ctypes.data, n, nd.ctypes.data) == 0
+        return nd
+
+    def check_motions_segments(self, s1, s2, nd):
+        """DiscreteMotionValidator::checkMotion(s1, s2, lastValid) per edge -> (valid, lastValid.second)."""
+        a, b = _f64(s1), _f64(s2)
+        n = a.shape[0]
+        seg = np.ascontiguousarray(nd, dtype=np.int32)
+        valid = np.zeros(n, np.uint8)
+        t = np.zeros(n, np.float64)
+        f = self.lib.orc_check_motions_segments
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        assert f(self.h, a.ctypes.data, b.ctypes.data, n, seg.ctypes.data, valid.ctypes.data, t.ctypes.data) == 0
+        return valid, t
+
+    def edge_matrix(self, s_start, s_target):
+        a, b = _f64(s_start), _f64(s_target)
+        out = np.zeros((a.shape[0], 6), np.float32)
+        f = self.lib.orc_edge_matrix
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        assert f(a.ctypes.data, b.ctypes.data, a.shape[0], out.ctypes.data) == 0
+        return out
+
     def check_edge_interiors(self, s1, s2, n_interp=None, max_lateral=0.5):
         a, b = _f64(s1), _f64(s2)
         n = a.shape[0]

@@ -183,3 +183,17 @@ EDGE_CASES = [
 ]
 
 
+
+
+# OMPL DiscreteMotionValidator with per-edge validSegmentCount and lastValid: (name, map, params, n, seed, dmin, dmax)
+SEGMENT_CASES = [
+    ("segments_fbm_rough_yaml", "fbm_rough", "yaml", 3000, 51, 0.05, 2.5),
+    ("segments_terraces_header", "terraces", "header", 2000, 52, 0.05, 1.5),
+]
+
+
+def se3_bounds(m, reach_z):
+    """RealVectorBounds of the SE3 space as Planner::setMap sets them (planner.cpp:146-156)."""
+    lx, ly = m.length
+    e = m.elevation[np.isfinite(m.elevation)]
+    return ([m.cx - lx, m.cy - ly, float(e.min()) - reach_z / 2], [m.cx + lx, m.cy + ly, float(e.max()) + reach_z / 2])

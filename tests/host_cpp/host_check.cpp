@@ -50,6 +50,7 @@ int main(int argc, char** argv) {
     params->objectives.custom_path_length.use_directional_cost = true;
     params->planner.prm_motion_cost.risk_threshold = 0.5f;
   }
+  if (hdr[5] == 1) params->planner.prm_motion_cost.risk_threshold = 0.55f;   // seeded random weights give risks around 0.5
   auto checker = std::make_shared<StateValidityChecker>(params);
   if (checker->hasMap()) return 4;
   checker->setMap(map);
@@ -88,6 +89,37 @@ int main(int argc, char** argv) {
   if (n_sampled) wr(out, &sampled[0].x, 7 * n_sampled);
   wr(out, &drawn64[0].x, 7 * drawn64.size()); wr(out, &n_accepted, 1); wr(out, &next_index, 1);
   if (n_accepted) wr(out, &accepted[0].x, 7 * n_accepted);
+  // OMPL's per-edge segment rule + lastValid, then (if the input carries network weights) the learned edge cost:
+  // MotionCostObjective::motionCost with its edge splitting and the updateEdges batch
+  {
+    artp_se3_space sp{};
+    double bnd[6];
+    rd(in, bnd, 6);
+    for (int i = 0; i < 3; ++i) { sp.low[i] = bnd[i]; sp.high[i] = bnd[3 + i]; }
+    sp.longest_valid_segment_fraction = 0.01;
+    std::vector<uint8_t> seg_valid; std::vector<double> seg_t; std::vector<int32_t> nd;
+    mv.checkMotionSegments(s1, s2, sp, &seg_valid, &seg_t, &nd);
+    double t0 = -1.0; State lv{};
+    const uint8_t one = mv.checkMotion(&s1[0], &s2[0], &t0, &lv) ? 1 : 0;      // nseg segments, single edge + lastValid state
+    wr(out, nd.data(), nd.size()); wr(out, seg_valid.data(), seg_valid.size()); wr(out, seg_t.data(), seg_t.size());
+    wr(out, &one, 1); wr(out, &t0, 1); wr(out, &lv.x, 7);
+  }
+  int32_t nw = 0;
+  rd(in, &nw, 1);
+  if (in && nw > 0) {
+    std::vector<float> blob(nw);
+    rd(in, blob.data(), blob.size());
+    int32_t ne = 0;
+    rd(in, &ne, 1);
+    MotionCostObjective mco(checker);
+    mco.setWeights(blob);
+    mco.updateFeatures();
+    std::vector<double> mc(ne);
+    for (int i = 0; i < ne; ++i) mc[i] = mco.motionCost(&s1[i], &s2[i]);        // motion_cost_objective.cpp:36-95
+    std::vector<double> ec; std::vector<uint8_t> ef;
+    const uint8_t ok = mco.updateEdgesBatch(s1, s2, &ec, &ef) ? 1 : 0;          // prm_motion_cost.cpp:27-73
+    wr(out, mc.data(), mc.size()); wr(out, &ok, 1); wr(out, ec.data(), ec.size()); wr(out, ef.data(), ef.size());
+  }
   std::cout << "ok " << valid.size() << " poses, " << motion.size() << " edges\n";
   return 0;
 }

@@ -154,3 +154,26 @@ def test_single_edge_latency_path(maps, make_checker, port_lib):
     ref = o.check_motions(s1, s2, 20)
     mv = ap.MotionValidator(chk, 20)
     assert np.array_equal(np.concatenate([mv.checkMotionBatch(s1[i:i + 3], s2[i:i + 3]) for i in range(0, 300, 3)]), ref)
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["warp+group", "group-only"])
+@pytest.mark.parametrize("case", cases.SEGMENT_CASES, ids=[c[0] for c in cases.SEGMENT_CASES])
+def test_motion_segments_and_last_valid(case, mode, golden, maps, make_checker):
+    """artp_check_motions_segments: OMPL's validSegmentCount rule per edge, verdicts and lastValid.second bit-exact against
+    the compiled reference (golden), with the counts given and with the counts computed from the space parameters."""
+    import art_planner_b200 as ap
+    name, mk, pk, n, seed, dmin, dmax = case
+    m = maps(mk)
+    chk = make_checker(pk, m)
+    chk.setMode(mode)
+    s1, s2 = synth.make_edges(m, n, seed, dmin=dmin, dmax=dmax)
+    mv = ap.MotionValidator(chk)
+    sp = mv.se3Space(m, cases.PARAMS[pk].reach_z)
+    nd = mv.validSegmentCount(sp, s1, s2)
+    assert np.array_equal(nd, golden[name + "/nd"])
+    ref_v, ref_t = unpack(golden, name + "/mask", n), golden[name + "/last_t"]
+    for kw in (dict(nd=nd), dict(space=sp)):
+        v, t = mv.checkMotionSegments(s1, s2, **kw)
+        assert np.array_equal(v, ref_v)
+        assert np.array_equal(t, ref_t)
+    assert 0 < ref_v.sum() < n

@@ -142,3 +142,23 @@ def test_hard_regime_exit_mix(maps, port_lib):
     assert f(o.h, poses.ctypes.data, n, st.ctypes.data, hit.ctypes.data, zv.ctypes.data) == 0
     torso = np.bincount(st.reshape(n, 5)[:, 0], minlength=8)[:8] / n     # ORC_ST_*: 5 vertex, 6 plane, 7 fall-through
     assert torso[5] + torso[6] + torso[7] >= 0.5 and torso[7] >= 0.4, torso
+
+
+@pytest.mark.parametrize("case", cases.SEGMENT_CASES, ids=[c[0] for c in cases.SEGMENT_CASES])
+def test_port_motion_segments_match_reference_golden(case, golden, maps, port_lib):
+    """Per-edge validSegmentCount + DiscreteMotionValidator::checkMotion(s1, s2, lastValid): port == compiled reference."""
+    name, mk, pk, n, seed, dmin, dmax = case
+    m = maps(mk)
+    o = port_lib.Oracle(cases.PARAMS[pk], "port")
+    o.set_map(m)
+    s1, s2 = synth.make_edges(m, n, seed, dmin=dmin, dmax=dmax)
+    assert digest(m.elevation, m.elevation_masked, s1, s2) == str(golden[name + "/sha"])
+    low, high = cases.se3_bounds(m, cases.PARAMS[pk].reach_z)
+    nd = o.valid_segment_count(low, high, s1, s2)
+    assert np.array_equal(nd, golden[name + "/nd"])
+    v, t = o.check_motions_segments(s1, s2, nd)
+    assert np.array_equal(v, unpack(golden, name + "/mask", n)) and np.array_equal(t, golden[name + "/last_t"])
+    # the 2-argument checkMotion (fixed segment count) is the same predicate
+    k = 9
+    vk, _ = o.check_motions_segments(s1, s2, np.full(n, k, np.int32))
+    assert np.array_equal(vk, o.check_motions(s1, s2, k - 1))
