@@ -38,6 +38,12 @@ class ArtpSe3Space(C.Structure):
     _fields_ = [("low", C.c_double * 3), ("high", C.c_double * 3), ("longest_valid_segment_fraction", C.c_double)]
 
 
+class ArtpBasicParams(C.Structure):
+    _fields_ = [("traversability_thres", C.c_float), ("unknown_space_untraversable", C.c_int)] + [(n, C.c_double) for n in (
+        "foothold_margin", "foothold_margin_max_hole_size", "foothold_margin_max_drop", "foothold_margin_max_drop_search_radius",
+        "foothold_margin_min_step", "foothold_size")]
+
+
 class ArtpStats(C.Structure):
     _fields_ = [("poses_checked", C.c_uint64), ("poses_deferred", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("last_deferred", C.c_uint32), ("last_launches", C.c_uint32), ("last_queued_boxes", C.c_uint32),
@@ -96,6 +102,8 @@ def load():
     lib.artp_get_stats.argtypes = [vp, C.POINTER(ArtpStats)]
     lib.artp_set_mode.argtypes = [vp, i32]
     lib.artp_poll_error.argtypes = [vp]
+    lib.artp_process_basic.argtypes = [vp, vp, vp, vp, i32, i32, dbl, C.POINTER(ArtpBasicParams), vp, vp]
+    lib.artp_debug_circular_kernel.argtypes = [i32, vp]
     lib.artp_host_alloc.restype = C.c_void_p
     lib.artp_host_alloc.argtypes = [sz]
     lib.artp_host_free.argtypes = [vp]

@@ -158,6 +158,22 @@ class StateValidityChecker:
                                                             _stream_ptr()))
         return idx, cnt
 
+    def processBasic(self, elevation, traversability, observed, res: float, bp):
+        """processors::Basic::setMaskedElevationAndTraversability (basic.cpp:42-106) on the device, after the inpainting:
+        returns (elevation_masked, traversability_thresholded), float32 Fortran-order. bp: an object with the fields of
+        artp_basic_params (oracle.basic_oracle.BasicParams has them)."""
+        e = np.asfortranarray(elevation, dtype=np.float32)
+        t = np.asfortranarray(traversability, dtype=np.float32)
+        o = None if observed is None else np.asfortranarray(observed, dtype=np.float32)
+        p = capi.ArtpBasicParams(float(bp.traversability_thres), int(bp.unknown_space_untraversable), float(bp.foothold_margin),
+                                 float(bp.foothold_margin_max_hole_size), float(bp.foothold_margin_max_drop),
+                                 float(bp.foothold_margin_max_drop_search_radius), float(bp.foothold_margin_min_step),
+                                 float(bp.foothold_size))
+        masked = np.empty(e.shape, np.float32, order="F"); thr = np.empty(e.shape, np.float32, order="F")
+        self._h.check(self._h.lib.artp_process_basic(self._h.h, e.ctypes.data, t.ctypes.data, None if o is None else o.ctypes.data,
+                                                     e.shape[0], e.shape[1], float(res), C.byref(p), masked.ctypes.data, thr.ctypes.data))
+        return masked, thr
+
     def estimateNormals(self, estimation_radius: float, want_host: bool = True):
         """art_planner::estimateNormals (utils.cpp:213-324) for the current elevation layer, on the device; the layers
         stay resident as the sampler's inputs. Returns (normal_x, normal_y, normal_z, plane_fit_std_dev) float32

@@ -20,6 +20,7 @@
 #include "artp_kernels.cuh"
 #include "artp_tiles.cuh"
 #include "artp_sampler.cuh"
+#include "artp_basic.cuh"
 
 namespace {
 
@@ -1885,6 +1886,97 @@ int artp_sample_valid(artp_handle* hh, uint64_t seed, uint64_t first_sample, siz
     CU_TRY(h, cudaStreamSynchronize(h->stream));
   }
   *n_valid = cnt;      // > capacity means the output was truncated to `capacity` states
+  return ARTP_OK;
+}
+
+// cv::circle(kernel, (r, r), r, 255, FILLED) on a size x size zero image, r = size / 2 (utils.cpp:106-111): OpenCV's
+// integer midpoint circle (imgproc/src/drawing.cpp, Circle()): for every step (dx, dy) of the octant walk the rows
+// cy -+ dy get the span cx -+ dx and the rows cy -+ dx the span cx -+ dy, everything clipped to the image.
+static artp::MorphKernel make_circular_kernel(int size) {
+  artp::MorphKernel k;
+  std::memset(&k, 0, sizeof(k));
+  if (size <= 0) {   // empty element: cv::erode / cv::dilate fall back to the 3 x 3 box, anchor (1, 1)
+    k.size = 3; k.anchor = 1;
+    for (int r = 0; r < 3; ++r) { k.lo[r] = 0; k.hi[r] = 2; }
+    return k;
+  }
+  k.size = size; k.anchor = size / 2;
+  for (int r = 0; r < size; ++r) { k.lo[r] = 127; k.hi[r] = -1; }
+  const int radius = size / 2, cx = radius, cy = radius;
+  auto span = [&](int y, int x0, int x1) {
+    if (y < 0 || y >= size) return;
+    x0 = std::max(x0, 0); x1 = std::min(x1, size - 1);
+    if (x0 > x1) return;
+    k.lo[y] = (int8_t)std::min<int>(k.lo[y], x0); k.hi[y] = (int8_t)std::max<int>(k.hi[y], x1);
+  };
+  int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+  while (dx >= dy) {
+    span(cy - dy, cx - dx, cx + dx); span(cy + dy, cx - dx, cx + dx);
+    span(cy - dx, cx - dy, cx + dy); span(cy + dx, cx - dy, cx + dy);
+    dy++; err += plus; plus += 2;
+    const int mask = (err <= 0) - 1;
+    err -= minus & mask; dx += mask; minus -= mask & 2;
+  }
+  return k;
+}
+
+int artp_debug_circular_kernel(int size, uint8_t* out) {   // test hook: the size x size element as 0 / 1 bytes (row-major)
+  if (size > artp::kMaxMorph || !out) return ARTP_E_INVALID;
+  const artp::MorphKernel k = make_circular_kernel(size);
+  for (int r = 0; r < k.size; ++r) for (int c = 0; c < k.size; ++c) out[r * k.size + c] = (c >= k.lo[r] && c <= k.hi[r]) ? 1 : 0;
+  return k.size;
+}
+
+int artp_process_basic(artp_handle* hh, const float* elevation, const float* traversability, const float* observed, int rows,
+                       int cols, double res, const artp_basic_params* bp, float* elevation_masked, float* traversability_thresholded) {
+  if (!hh) return ARTP_E_INVALID;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::lock_guard<std::recursive_mutex> lk(h->mtx);
+  if (!elevation || !traversability || !bp || !elevation_masked || rows < 1 || cols < 1 || !(res > 0)) {
+    h->err = "bad arguments"; return ARTP_E_INVALID;
+  }
+  if (bp->unknown_space_untraversable && !observed) { h->err = "unknown_space_untraversable needs the observed layer"; return ARTP_E_INVALID; }
+  // basic.cpp:65-74: cell counts of the structuring elements
+  const int foothold = (int)std::ceil(bp->foothold_size / res), margin = (int)std::ceil(2 * bp->foothold_margin / res),
+            hole = (int)std::floor(bp->foothold_margin_max_hole_size / res),
+            search = (int)std::ceil(2 * bp->foothold_margin_max_drop_search_radius / res);
+  if (std::max(std::max(foothold, margin), std::max(hole, search)) > artp::kMaxMorph) {
+    h->err = "structuring element larger than 64 cells"; return ARTP_E_LIMIT;
+  }
+  CU_TRY(h, cudaSetDevice(h->device));
+  const size_t n = (size_t)rows * cols, lb = n * sizeof(float);
+  int rc = chain_begin(h, 0, h->stream);
+  if (rc) return rc;
+  rc = ensure_stage(h, 9 * lb);
+  if (rc) return rc;
+  float* L = (float*)h->d_stage;   // 0 elev, 1 trav, 2 observed, 3 T0, 4 A, 5 B, 6 elev eroded, 7 elev dilated, 8 out
+  cudaStream_t s = h->stream;
+  CU_TRY(h, cudaMemcpyAsync(L, elevation, lb, cudaMemcpyHostToDevice, s));
+  CU_TRY(h, cudaMemcpyAsync(L + n, traversability, lb, cudaMemcpyHostToDevice, s));
+  if (observed) CU_TRY(h, cudaMemcpyAsync(L + 2 * n, observed, lb, cudaMemcpyHostToDevice, s));
+  const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 16);
+  auto morph = [&](bool dil, const float* src, float* dst, int size) {
+    const artp::MorphKernel k = make_circular_kernel(size);
+    if (dil) artp::morph_kernel<true><<<grid, 256, 0, s>>>(src, dst, rows, cols, k);
+    else artp::morph_kernel<false><<<grid, 256, 0, s>>>(src, dst, rows, cols, k);
+  };
+  float *E = L, *T0 = L + 3 * n, *A = L + 4 * n, *B = L + 5 * n, *Elo = L + 6 * n, *Ehi = L + 7 * n, *O = L + 8 * n;
+  artp::basic_threshold_kernel<<<grid, 256, 0, s>>>(L + n, L + 2 * n, bp->unknown_space_untraversable ? 1 : 0, bp->traversability_thres, n, T0);
+  morph(true, T0, A, hole); morph(false, A, B, hole);                    // dilateAndErode: close holes (:72)
+  morph(false, E, Elo, search);                                          // elevation - erode(elevation) (:75-77)
+  morph(true, E, Ehi, margin);                                           // dilate(elevation) - elevation (:84)
+  artp::basic_select_kernel<<<grid, 256, 0, s>>>(0, E, Elo, Ehi, T0, B, (float)bp->foothold_margin_max_drop, (float)bp->foothold_margin_min_step, n, A);
+  morph(false, A, B, margin);                                            // erode by the safety margin (:90)
+  artp::basic_select_kernel<<<grid, 256, 0, s>>>(1, E, Elo, Ehi, T0, B, (float)bp->foothold_margin_max_drop, (float)bp->foothold_margin_min_step, n, A);
+  morph(false, A, B, foothold); morph(true, B, A, foothold);             // erodeAndDilate: remove small patches (:95)
+  artp::basic_final_kernel<<<grid, 256, 0, s>>>(E, T0, A, n, B, O);
+  CU_TRY(h, cudaGetLastError());
+  CU_TRY(h, cudaMemcpyAsync(elevation_masked, O, lb, cudaMemcpyDeviceToHost, s));
+  if (traversability_thresholded) CU_TRY(h, cudaMemcpyAsync(traversability_thresholded, B, lb, cudaMemcpyDeviceToHost, s));
+  CU_TRY(h, cudaStreamSynchronize(s));
+  h->chain_busy[0] = false;
+  h->stats.kernel_launches += 11;
+  h->stats.last_launches = 11;
   return ARTP_OK;
 }
 

@@ -360,3 +360,19 @@ class SamplerParams:
 def sampler_params_for(m: SynthMap, from_distribution: bool = True) -> SamplerParams:
     lx, ly = m.length
     return SamplerParams(sample_from_distribution=from_distribution, low=(m.cx - lx, m.cy - ly), high=(m.cx + lx, m.cy + ly))
+
+
+def make_traversability(m: SynthMap, seed: int = 13):
+    """Synthetic inputs of processors::Basic: a traversability layer in [0, 1] (smooth noise, low where the terrain is
+    steep, a few dead blobs and pin-holes) and an "observed" layer with unobserved patches. float32 F-order."""
+    x, y = m.cell_xy()
+    e = m.elevation.astype(np.float64)
+    gx, gy = np.gradient(e, m.res)
+    slope = np.sqrt(gx * gx + gy * gy)
+    t = 0.85 - 0.9 * slope + 0.25 * fbm_height(seed, x[:, None], y[None, :], 1.0, wavelength=3.0, octaves=3)
+    k = np.arange(e.size).reshape(e.shape)
+    t = np.where(hash_uniform(seed, 41, k) < 0.004, 0.0, t)                      # isolated pin-holes
+    blk = (np.arange(m.rows)[:, None] // 11) * 4096 + (np.arange(m.cols)[None, :] // 7)
+    t = np.where(hash_uniform(seed, 42, blk) < 0.03, 0.05, t)                    # dead blobs
+    obs = (hash_uniform(seed, 43, (np.arange(m.rows)[:, None] // 23) * 4096 + (np.arange(m.cols)[None, :] // 29)) > 0.06)
+    return (np.asfortranarray(np.clip(t, 0.0, 1.0).astype(np.float32)), np.asfortranarray(obs.astype(np.float32)))

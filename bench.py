@@ -527,6 +527,24 @@ def main():
             plo.motionCostBatch(d1, d2, out=c_out)
         bb.record(); torch.cuda.synchronize()
         secondary["path_length_cost"] = {"evals_per_s": 100_000 * 50 / (a.elapsed_time(bb) * 1e-3)}
+        try:   # per-map work (the reference: HeightMapBoxChecker::setHeightField = one layer copy per checker at 1 Hz)
+            from oracle.basic_oracle import BasicParams
+            t_set = []
+            for _ in range(4):
+                t0 = time.perf_counter(); chk.updateHeightField(); torch.cuda.synchronize(); t_set.append(time.perf_counter() - t0)
+            trav, obs = synth.make_traversability(m, seed=13)
+            chk.processBasic(m.elevation, trav, obs, m.res, BasicParams())
+            t_pb = []
+            for _ in range(3):
+                t0 = time.perf_counter(); mk, _thr = chk.processBasic(m.elevation, trav, obs, m.res, BasicParams()); t_pb.append(time.perf_counter() - t0)
+            secondary["map_update"] = {
+                "artp_set_map_ms": 1e3 * min(t_set[1:]), "what_set_map": "H2D of both 1000x1000 layers + column reverse + plane tables "
+                "(hash of 2 M triangle planes) + range tables (levels 1-5 / 1-3), through the Python wrapper",
+                "artp_process_basic_ms": 1e3 * min(t_pb), "what_process_basic": "processors::Basic masking on the device: 3 layers H2D, "
+                "7 morphology passes (elements 3..15 cells), elevation_masked + traversability_thresholded D2H",
+                "masked_traversable_fraction": float(np.isfinite(mk).mean())}
+        except Exception as ex:
+            secondary["map_update"] = {"error": repr(ex)}
         try:   # latency of small batches through the host-buffer API (what a one-state isValid call pays)
             lat = {}
             chk.setTiming(False)   # the one-launch latency path (n <= 16) is bypassed while kernel timing is on

@@ -260,6 +260,25 @@ int artp_get_last_stage_timing(artp_handle* h, float* ms5);
  *            1 = send every in-map box through the exact block-level grouping kernel. */
 int artp_set_mode(artp_handle* h, int mode);
 
+/* ---- processors::Basic::setMaskedElevationAndTraversability (art_planner/src/map/processors/basic.cpp:42-106) ------
+ * The producer of `elevation_masked` on the device: traversability threshold (+ "observed" masking), hole closing,
+ * drop / wall masks, safety-margin erosion, small-patch removal -- grey-scale morphology with OpenCV's circular
+ * structuring element (art_planner/src/utils.cpp:106-209) as exact min / max filters -- then
+ * elevation_masked = traversable ? elevation : -inf. Inputs are the INPAINTED layers (basic.cpp:44-45: TELEA inpainting
+ * is a sequential fast-marching method and stays with the caller); HOST pointers, grid_map layout; `observed` may be NULL
+ * when !unknown_space_untraversable. Outputs: elevation_masked and (nullable) "traversability_thresholded". */
+typedef struct artp_basic_params {
+  float  traversability_thres;                        /* params.h:23 */
+  int    unknown_space_untraversable;                 /* params.h:26 */
+  double foothold_margin, foothold_margin_max_hole_size, foothold_margin_max_drop,
+         foothold_margin_max_drop_search_radius, foothold_margin_min_step, foothold_size;   /* params.h:28-35 */
+} artp_basic_params;
+int artp_process_basic(artp_handle* h, const float* elevation, const float* traversability, const float* observed, int rows,
+                       int cols, double res, const artp_basic_params* bp, float* elevation_masked, float* traversability_thresholded);
+/* Test hook: the size x size structuring element of getCircularKernel(size) (utils.cpp:106-111) as 0/1 bytes; returns its
+ * edge length (3 for size <= 0: OpenCV's default box). */
+int artp_debug_circular_kernel(int size, uint8_t* out);
+
 /* ---- learned motion cost (MotionCostFunc, objectives/motion_cost_objective.h:22-23) ------------------------------
  * Weights: ONE flat fp32 blob in the layer order of the reference's `network` module (network_light.py:9-63):
  * init_conv1..5, init_flatten, tar0_conv1, out0_conv1, out1_conv1..3 -- each conv.weight [Cout][Cin][kh][kw] followed by

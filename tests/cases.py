@@ -197,3 +197,19 @@ def se3_bounds(m, reach_z):
     lx, ly = m.length
     e = m.elevation[np.isfinite(m.elevation)]
     return ([m.cx - lx, m.cy - ly, float(e.min()) - reach_z / 2], [m.cx + lx, m.cy + ly, float(e.max()) + reach_z / 2])
+
+
+# processors::Basic (basic.cpp:42-106): (name, map, resolution scale, parameters). res scale 1.25 makes the element sizes
+# even numbers (asymmetric anchors); the last case has every safety distance 0 (params.h defaults -> OpenCV's 3x3 box).
+def _basic_cases():
+    from oracle.basic_oracle import BasicParams
+    return [
+        ("basic_fbm_rough_yaml", "fbm_rough", 1.0, BasicParams()),
+        ("basic_fixture_yaml", "fixture", 1.0, BasicParams()),
+        ("basic_terraces_even", "terraces", 1.25, BasicParams(foothold_size=0.2, foothold_margin=0.2)),
+        ("basic_fbm_hard_known", "fbm_hard", 1.0, BasicParams(unknown_space_untraversable=False, traversability_thres=0.4)),
+        ("basic_fbm_gentle_defaults", "fbm_gentle", 1.0, BasicParams(0.5, True, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0)),
+    ]
+
+
+BASIC_CASES = _basic_cases()
