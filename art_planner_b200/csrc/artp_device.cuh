@@ -72,29 +72,26 @@ __device__ __forceinline__ float next_up(float x) {
 // __fdiv_rn(1.0f, y), in fewer instructions.
 __device__ __forceinline__ float rsqrt_exact(float x) { return __frcp_rn(__fsqrt_rn(x)); }
 
-// dxSafeNormalize3, ode/ode/src/odemath.cpp:95-161.
+// dxSafeNormalize3, ode/ode/src/odemath.cpp:95-161: scale by the largest component m, then u = lower-index other
+// component / m, v = higher-index other component / m, l = 1 / sqrt(1 + u*u + v*v). Written without a branch per
+// largest-component case (which component is largest depends on the yaw, so a warp would run all three copies): the
+// operands are selected, the arithmetic is the same sequence of correctly rounded operations.
 __device__ __forceinline__ void safe_normalize3(float& a0, float& a1, float& a2) {
   const float b0 = fabsf(a0), b1 = fabsf(a1), b2 = fabsf(a2);
   int idx;
   if (b1 > b0) idx = (b2 > b1) ? 2 : 1;
   else if (b2 > b0) idx = 2;
   else { if (!(b0 > 0.0f)) return; idx = 0; }
-  if (idx == 0) {
-    const float r = __fdiv_rn(1.0f, b0);
-    const float u = a1 * r, v = a2 * r;
-    const float l = rsqrt_exact(1.0f + u * u + v * v);
-    a1 = u * l; a2 = v * l; a0 = copysignf(l, a0);
-  } else if (idx == 1) {
-    const float r = __fdiv_rn(1.0f, b1);
-    const float u = a0 * r, v = a2 * r;
-    const float l = rsqrt_exact(1.0f + u * u + v * v);
-    a0 = u * l; a2 = v * l; a1 = copysignf(l, a1);
-  } else {
-    const float r = __fdiv_rn(1.0f, b2);
-    const float u = a0 * r, v = a1 * r;
-    const float l = rsqrt_exact(1.0f + u * u + v * v);
-    a0 = u * l; a1 = v * l; a2 = copysignf(l, a2);
-  }
+  const float bm = idx == 0 ? b0 : (idx == 1 ? b1 : b2);
+  const float am = idx == 0 ? a0 : (idx == 1 ? a1 : a2);
+  const float au = idx == 0 ? a1 : a0, av = idx == 2 ? a1 : a2;
+  const float r = __fdiv_rn(1.0f, bm);
+  const float u = au * r, v = av * r;
+  const float l = rsqrt_exact(1.0f + u * u + v * v);
+  const float nu = u * l, nv = v * l, nm = copysignf(l, am);
+  a0 = idx == 0 ? nm : nu;
+  a1 = idx == 1 ? nm : (idx == 0 ? nu : nv);
+  a2 = idx == 2 ? nm : nv;
 }
 
 // dBodySetRotation -> dxOrthogonalizeR (ode/ode/src/ode.cpp:358-374, odemath.cpp:260-313) on the 3x3

@@ -721,8 +721,8 @@ classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs_w
   const int lane = threadIdx.x & 31;
   int result = 1;                 // 1 valid so far, 0 invalid
   int n_w = 0, n_f = 0;           // undecided boxes of this item for the big-tile queue / the reach-box queue
-  BoxCtx ub[5];                   // their contexts: big-tile boxes from the front, reach boxes from the back
-  uint32_t uflags[5];
+  struct Pending { float P[3], minB, maxB; int x0, x1, z0, z1; uint32_t fl; };   // R1 is shared by the item's boxes
+  Pending ub[5];                  // big-tile boxes from the front, reach boxes from the back
   float R1[9];
   uint32_t slot = 0;
   if (in_range) {
@@ -752,7 +752,9 @@ classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs_w
         // small tile -- to the big-tile queue
         const bool thread_path = foot && (b.x1 - b.x0) + 4 <= c.reach_tw && (b.z1 - b.z0) + 1 <= c.reach_th;
         const int q = thread_path ? 4 - n_f++ : n_w++;
-        ub[q] = b; uflags[q] = fl;
+        Pending& pd = ub[q];
+        pd.P[0] = b.P[0]; pd.P[1] = b.P[1]; pd.P[2] = b.P[2]; pd.minB = b.minB; pd.maxB = b.maxB;
+        pd.x0 = b.x0; pd.x1 = b.x1; pd.z0 = b.z0; pd.z1 = b.z1; pd.fl = fl;
       }
       else if (!foot) { if (r == R_HIT) result = 0; }      // torso must be free
       else { if (r == R_FREE) result = 0; }                // every reach box must touch
@@ -783,13 +785,13 @@ classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs_w
     const bool fq = q >= n_w;
     const int src = fq ? 4 - (q - n_w) : q;
     BoxRec& o = fq ? recs_f[base_f + (q - n_w)] : recs_w[base_w + q];
-    const BoxCtx& b = ub[src];
+    const Pending& b = ub[src];
 #pragma unroll
     for (int i = 0; i < 9; ++i) o.R1[i] = R1[i];
     o.P[0] = b.P[0]; o.P[1] = b.P[1]; o.P[2] = b.P[2];
     o.minB = b.minB; o.maxB = b.maxB;
     o.x0 = b.x0; o.x1 = b.x1; o.z0 = b.z0; o.z1 = b.z1;
-    o.item = slot; o.flags = uflags[src];      // later stages only need the verdict slot
+    o.item = slot; o.flags = b.fl;             // later stages only need the verdict slot
   }
 }
 

@@ -56,7 +56,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "10", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
             self.t.start()
         except Exception:
@@ -379,6 +379,10 @@ def main():
     def step_e2e_f64():  # the same through the double entry point (56 B/pose on the wire)
         chk.isValidHostPtr(h_poses.data_ptr(), n, h_valid.data_ptr())
 
+    # clocks / throttle reasons are sampled every 10 ms from before the warm-up to the end of the end-to-end region
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     warm_ev = torch.cuda.Event()
     for i in range(max(args.warmup, 3)):
         warm_ev.record()
@@ -390,9 +394,6 @@ def main():
     torch.cuda.synchronize()
 
     # ---- timed region: device-resident inputs --------------------------------------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = chk.stats()["kernel_launches"]
     # one extra window at the end (N > 1): the exchange of the last step
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
@@ -655,46 +656,48 @@ def main():
         _, zv = port.check_poses(poses[:50_000], want_zone=True)
         bytes_per_pose = 56.0 + 1.0 + 4.0 * float(zv.mean())
         peak, peak_src = load_peaks()
-        # dominant kernel = the box warp stage; the roofline is quoted on the whole three-kernel pass as well
-        k0, k1, k2 = float(np.mean(k0_ms)), float(np.mean(k1_ms)), float(np.mean(k2_ms))
-        # Conservative roofline: the algorithmic bytes belong to the whole pass (classify + box warp stage + grouping
-        # stage), so they are divided by the SUM of the three kernels' durations; the per-kernel figure for the
-        # dominant kernel alone is reported next to it (it exceeds HBM peak because the zone reductions are
-        # answered by the range tables instead of being scanned -- see DESIGN.md section 4).
-        achieved = bytes_per_pose * n / ((k0 + k1 + k2) * 1e-3) / 1e9
-        achieved_dom = bytes_per_pose * n / (k1 * 1e-3) / 1e9
+        # Roofline bookkeeping: the algorithmic bytes belong to the whole pass (classify + the two box
+        # queues + grouping), so they are divided by the SUM of the stage durations; the dominant kernel is the reach-box
+        # queue launch of box_tiles_warp_kernel.
+        sm = np.mean(np.array(stage_ms), 0)
+        k0, k_torso, k_reach, k2 = float(sm[0]), float(sm[1]), float(sm[2]), float(sm[4])
+        pass_ms = k0 + k_torso + k_reach + k2
+        achieved = bytes_per_pose * n / (pass_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("box_items_warp_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("box_tiles_warp_kernel_reach_queue_dram_bytes_per_launch")
+        port_mix = exit_mix(port, poses[:20_000])
         out = {
             "metric": "pose-validity checks/s", "value": value, "unit": "poses/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD if args.workload == "c2" else
                        "configs[4]: fBm 4000x4000@0.04m map, 1M samples per GPU inside the GPU's spatial slab, yaml robot geometry",
-                       "poses_per_gpu": n, "map": f"{m.rows}x{m.cols}@{MAP_RES}",
+                       "poses_per_gpu": n, "map": f"{m.rows}x{m.cols}@{MAP_RES}", "map_generator": m.desc,
+                       "roughness": "gentle level of SURVEY 8(d) by its exit mix (torso: %.0f %% above the zone, %.1f %% through the full triangle / plane pass); the rough level is secondary.c2_rough" % (100 * port_mix["torso"]["above"], 100 * port_mix["torso"]["fall_through"]),
+                       "exit_mix": port_mix,
                        "map_seed": MAP_SEED, "pose_seed": POSE_SEED, "l2": "flushed between timed steps (256 MiB write)",
+                       "step": "isValid of the batch (verdict bytes) + bit-packed verdicts + the ordered 32-bit index list of the valid samples",
                        "parallelism": f"pose shards x{world}, replicated 1000x1000 map" + (", one NCCL all-gather of bit-packed masks per step, pipelined: the exchange of step i runs on a side stream inside the timed window of step i+1 (+ one closing window); see exchange.unpipelined_value and c5 (spatial shards)" if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": n,
-                    "ms_per_step": e2e_ms / e2e_steps, "api": "artp_check_poses_f32 (states cast to float by the adapter, exact)",
-                    "f64_api_value": world * n * e2e_steps / e2e64_s, "f64_api_h2d_bytes_per_step": n * 56},
+                    "ms_per_step": e2e_ms / e2e_steps, "api": "artp_check_poses_f32 (states cast to float by the adapter while it gathers them, exact), buffers from artp_host_alloc",
+                    "f64_api_value": world * n * e2e_steps / e2e64_s, "f64_api_h2d_bytes_per_step": n * 56,
+                    "note": "PCIe Gen5 x16 moves 53-55 GB/s here (profiles/pcie_probe.cu): 28 MB = 0.52 ms, 56 MB = 1.04 ms, so the double entry point is copy-bound at <= 0.96e9 poses/s"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "box_items_warp_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "box_tiles_warp_kernel (reach-box queue launch)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_pose": bytes_per_pose, "kernel_ms": k1,
-                         "classify_kernel_ms": k0, "group_kernel_ms": k2, "pass_ms": k0 + k1 + k2,
-                         "achieved_dominant_kernel_alone": achieved_dom,
+                         "algorithmic_bytes_per_pose": bytes_per_pose, "kernel_ms": k_reach,
+                         "classify_kernel_ms": k0, "torso_queue_kernel_ms": k_torso, "group_kernel_ms": k2, "pass_ms": pass_ms,
                          "queued_boxes": int(queued), "deferred_boxes": int(deferred),
-                         "stage_ms": dict(zip(("classify", "torso_queue", "reach_queue", "unused", "group"),
-                                              [float(x) for x in np.mean(np.array(stage_ms), 0)])),
+                         "stage_ms": dict(zip(("classify", "torso_queue", "reach_queue", "unused", "group"), [float(x) for x in sm])),
                          "queued_warp_stage": stats_last["last_queued_warp_stage"],
                          "queued_reach_stage": stats_last["last_queued_reach_stage"],
-                         "actual_dram_GBps_dominant_kernel": (traffic / (k1 * 1e-3) / 1e9) if traffic else None,
-                         "note": "achieved = ALGORITHMIC bytes (the zone vertices the reference scans, SURVEY 8d) / sum of "
-                                 "the three stage durations; the range tables and vertex probes answer most of those scans "
-                                 "without reading them, so frac can exceed 1 while real DRAM traffic (traffic, ncu) stays at "
-                                 "~1-2 % of peak: the pipeline is instruction-issue bound (61 % issue slots busy, profiles/)"},
+                         "actual_dram_GBps_dominant_kernel": (traffic / (k_reach * 1e-3) / 1e9) if traffic else None,
+                         "note": "achieved = ALGORITHMIC bytes (the zone vertices the reference scans, SURVEY 8d) / sum of the stage "
+                                 "durations; the range tables, plane tables and vertex probes answer most of those scans without reading "
+                                 "them, so frac exceeds 1 while real DRAM traffic (traffic, ncu) stays near 1 % of peak: the pipeline is "
+                                 "instruction-issue bound (70 % of issue slots busy, 20 of 32 lanes; profiles/r02_v4_*)"},
             "cpu_baseline": cpu_baseline,
             "clocks": clocks, "wall_s_timed_region": wall, "secondary": secondary, "exchange_ok": exchange_ok,
             "exchange": {"unpipelined_value": world * n * args.steps / (serial_ms * 1e-3), "unpipelined_ms_per_step": serial_ms / args.steps,

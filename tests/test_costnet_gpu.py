@@ -85,3 +85,58 @@ def test_errors_without_weights_or_features():
     obj.setWeights(costnet.make_state_dict(seed=5))
     with pytest.raises(ap.ArtpError):
         obj.costQuery(np.zeros((4, 6), np.float32))   # features not computed
+
+
+@pytest.mark.parametrize("shape", [(300, 260), (1000, 1000), (121, 97)], ids=["300x260-partial-tiles", "1000x1000-metric-map", "121x97-odd"])
+def test_feature_map_other_sizes(shape):
+    """The trunk away from the 256x256 patch: partial output tiles in both axes, odd extents, and the metric's full
+    1000x1000 map (feature map 476 x 476), against the fp32 torch restatement of network_light.py:78-110."""
+    import art_planner_b200 as ap
+    from art_planner_b200 import synth
+    from oracle.cnn_oracle import CostNetOracle, cnn_input_from_layer
+    rows, cols = shape
+    m = synth.make_fbm_map(rows, cols, 0.04, seed=2, amp=0.6)
+    chk = ap.StateValidityChecker(synth.PARAMS_YAML, device=0)
+    chk.setMap(m); chk.updateHeightField()
+    obj = ap.MotionCostObjective(chk)
+    sd = costnet.make_state_dict(seed=5)
+    obj.setWeights(sd)
+    obj.updateFeatures()
+    got = obj.features()
+    ref = CostNetOracle(sd).features(cnn_input_from_layer(m.elevation)).permute(1, 2, 0).numpy()
+    assert got.shape == ref.shape == ((cols - 48) // 2, (rows - 48) // 2, 48) or got.shape == ref.shape
+    scale = float(np.abs(ref).max())
+    assert float(np.abs(got - ref).max()) / scale < 1e-4
+    q = costnet.make_queries(m, 2048, seed=6)
+    lx, ly = m.length
+    feat = CostNetOracle(sd).features(cnn_input_from_layer(m.elevation))
+    assert np.allclose(obj.costQuery(q), CostNetOracle(sd).query(feat, q, m.res, lx, ly, m.cx, m.cy), rtol=RTOL, atol=ATOL)
+
+
+def test_error_against_the_fp16_module_as_shipped(setup):
+    """the reference runs its module in fp16 (predictor.py:22). Report how far that evaluation is
+    from the fp32 one and check that this implementation is closer to fp32 than fp16 is (it must be: 1e-4 vs ~1e-3)."""
+    import torch
+    m, obj, orc, feat, golden = setup
+    from oracle.cnn_oracle import CostNetOracle, cnn_input_from_layer
+    sd = costnet.make_state_dict(seed=5)
+    h = CostNetOracle(sd)
+    h.p = {k: v.cuda().half() for k, v in h.p.items()}
+    E = torch.as_tensor(cnn_input_from_layer(m.elevation)).cuda().half()
+    import torch.nn.functional as F
+    with torch.no_grad():
+        t = E[None, None]
+        t = h._conv_bn(t, "init_conv1", "init_conv1_bn")
+        t = F.leaky_relu(h._conv_bn(t, "init_conv2", "init_conv2_bn"), 0.3); t = F.max_pool2d(t, (2, 2), stride=2)
+        t = F.leaky_relu(h._conv_bn(t, "init_conv3", "init_conv3_bn"), 0.3)
+        t = F.leaky_relu(h._conv_bn(t, "init_conv4", "init_conv4_bn"), 0.3); t = F.max_pool2d(t, (3, 3), stride=1)
+        t = F.leaky_relu(h._conv_bn(t, "init_conv5", "init_conv5_bn"), 0.3)
+        t = F.leaky_relu(h._conv_bn(t, "init_flatten", "init_flatten_bn"), 0.3)
+    f16 = t[0].float().cpu().permute(1, 2, 0).numpy()
+    ref = feat.permute(1, 2, 0).numpy()
+    obj.setMode(0); obj.updateFeatures()
+    got = obj.features()
+    scale = float(np.abs(ref).max())
+    e16, e_us = float(np.abs(f16 - ref).max()) / scale, float(np.abs(got - ref).max()) / scale
+    print(f"feature-map max error / max|f|: fp16 module as shipped {e16:.2e}, this implementation {e_us:.2e}")
+    assert e_us < 1e-4 and e_us < e16
