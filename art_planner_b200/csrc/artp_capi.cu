@@ -35,7 +35,7 @@ struct Handle {
   artp::Checker chk;
   float* d_H[2] = {nullptr, nullptr};
   float2* d_T[2][artp::kMaxLevel + 1] = {};
-  unsigned char* d_NF[2][artp::kMaxLevel + 1] = {};
+  uint32_t* d_NF[2][artp::kMaxLevel + 1] = {};   // bit-packed window flags (2 bits per entry)
   int pitch = 0;
   int rows = 0, cols = 0;           // full map
   int win_row0 = 0, win_rows = 0;   // rows held by this handle (artp_set_map_window); whole map: 0, rows
@@ -233,6 +233,19 @@ __global__ void plane_table_query_kernel(const artp::Field f, int x_off, const P
           }
         }
     if (dup) mergeable[(size_t)z * f.pitch + x] = 2;   // races write the same value
+  }
+}
+
+// 16 flag bytes (values 0..3) -> one word of 2-bit fields; the tail of the last word is zero
+__global__ void pack_flags_kernel(const unsigned char* __restrict__ nf, size_t n, uint32_t* __restrict__ out) {
+  const size_t words = (n + 15) / 16;
+  for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < words; w += (size_t)gridDim.x * blockDim.x) {
+    uint32_t v = 0;
+    for (int i = 0; i < 16; ++i) {
+      const size_t e = w * 16 + i;
+      if (e < n) v |= (uint32_t)(nf[e] & 3) << (2 * i);
+    }
+    out[w] = v;
   }
 }
 
@@ -856,7 +869,7 @@ int artp_set_map_window(artp_handle* hh, const float* elevation, const float* el
     for (int l = 1; l <= kmax[k]; ++l)
       if (!h->d_T[k][l]) {
         CU_TRY(h, cudaMalloc(&h->d_T[k][l], npad * sizeof(float2)));
-        CU_TRY(h, cudaMalloc(&h->d_NF[k][l], npad));
+        CU_TRY(h, cudaMalloc(&h->d_NF[k][l], ((npad + 15) / 16) * sizeof(uint32_t)));
       }
   int rc = ensure_stage(h, ncell * sizeof(float));
   if (rc) return rc;
@@ -865,9 +878,9 @@ int artp_set_map_window(artp_handle* hh, const float* elevation, const float* el
   size_t cap = 1;
   while (cap < 4 * ncell) cap <<= 1;
   PlaneSlot* d_tab = nullptr;
-  unsigned char* d_merge = nullptr;
+  unsigned char* d_merge = nullptr;   // [0, npad): mergeable cells; [npad, 3 npad): two byte-flag levels (ping-pong while building)
   CU_TRY(h, cudaMalloc(&d_tab, cap * sizeof(PlaneSlot)));
-  if (cudaMalloc(&d_merge, npad) != cudaSuccess) { cudaFree(d_tab); h->err = "cudaMalloc (plane tables)"; return ARTP_E_CUDA; }
+  if (cudaMalloc(&d_merge, 3 * npad) != cudaSuccess) { cudaFree(d_tab); h->err = "cudaMalloc (plane tables)"; return ARTP_E_CUDA; }
   for (int k = 0; k < 2; ++k) {
     CU_TRY(h, cudaMemcpyAsync(h->d_stage, src[k], ncell * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     reverse_columns_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>((const float*)h->d_stage, h->d_H[k], nrows, cols, pitch);
@@ -881,11 +894,14 @@ int artp_set_map_window(artp_handle* hh, const float* elevation, const float* el
     CU_TRY(h, cudaGetLastError());
     h->stats.kernel_launches += 4;
     for (int l = 1; l <= kmax[k]; ++l) {
+      unsigned char* nf_prev = d_merge + npad * (size_t)(1 + ((l - 1) & 1));
+      unsigned char* nf_cur = d_merge + npad * (size_t)(1 + (l & 1));
       build_level_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_H[k], l > 1 ? h->d_T[k][l - 1] : nullptr,
-                                                                  l > 1 ? h->d_NF[k][l - 1] : nullptr, d_merge, h->d_T[k][l],
-                                                                  h->d_NF[k][l], nrows, cols, pitch, 1 << (l - 1));
+                                                                  l > 1 ? nf_prev : nullptr, d_merge, h->d_T[k][l], nf_cur, nrows,
+                                                                  cols, pitch, 1 << (l - 1));
+      pack_flags_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(nf_cur, npad, h->d_NF[k][l]);
       CU_TRY(h, cudaGetLastError());
-      h->stats.kernel_launches += 1;
+      h->stats.kernel_launches += 2;
     }
   }
   CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -898,7 +914,7 @@ int artp_set_map_window(artp_handle* hh, const float* elevation, const float* el
     f.kmax = kmax[k];
     for (int l = 0; l <= artp::kMaxLevel; ++l) {
       f.T[l] = (l >= 1 && l <= kmax[k]) ? h->d_T[k][l] - row0 : nullptr;
-      f.NF[l] = (l >= 1 && l <= kmax[k]) ? h->d_NF[k][l] - row0 : nullptr;
+      f.NF[l] = (l >= 1 && l <= kmax[k]) ? h->d_NF[k][l] : nullptr;   // bit-packed: indexed with LOCAL entry numbers, see below
     }
     h->chk.f[k] = f;
   }

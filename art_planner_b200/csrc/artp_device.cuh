@@ -23,10 +23,10 @@ struct Field {
   int pitch;       // row stride in floats (multiple of 4 -> 16 B aligned rows)
   // Range tables (exact, idempotent reductions): level k holds, for every (x,z), the reduction over the
   // 2^k x 2^k vertex window starting there: T[k][x + z*pitch] = (max h, min over finite h or +inf),
-  // NF[k][x + z*pitch]: bit 0 = the window holds a non-finite height, bit 1 = a cell starting in the window has a
+  // NF[k], entry x + z*pitch (bit-packed, see window_flags): bit 0 = the window holds a non-finite height, bit 1 = a cell starting in the window has a
   // triangle whose plane matches (within eps) the plane of another triangle of the map. Built at artp_set_map, k = 1..kmax.
   const float2* T[kMaxLevel + 1];
-  const unsigned char* NF[kMaxLevel + 1];
+  const uint32_t* NF[kMaxLevel + 1];   // 2 flag bits per entry, 16 entries per word: 32x smaller than the (max, min) tables, cache resident
   int kmax;
   float W, D, hW, hD, sW, sD, asp, iW, iD;
   float px, py;    // heightfield body position (float casts of the map centre)
@@ -57,6 +57,12 @@ struct BoxCtx {
   float minB, maxB;
   int x0, x1, z0, z1;
 };
+
+// flags of range-table entry idx (bit 0 non-finite, bit 1 mergeable); idx is LOCAL to the handle's map window
+// (global entry - x_lo: the packed words cannot be shifted by a pointer offset the way the float2 tables are)
+__device__ __forceinline__ int window_flags(const uint32_t* __restrict__ nf, size_t idx) {
+  return (int)((__ldg(nf + (idx >> 4)) >> ((idx & 15) * 2)) & 3u);
+}
 
 // nextafterf(x, -inf) / nextafterf(x, +inf) for finite x (dNextAfter, ode/include/ode/common.h:296), as integer ops.
 __device__ __forceinline__ float next_down(float x) {

@@ -200,7 +200,7 @@ __device__ __forceinline__ void zone_reduce(const Field& f, const BoxCtx& b, int
       const size_t idx = (size_t)zs * f.pitch + xs;
       const float2 v = __ldg(f.T[k] + idx);
       mx = v.x; mn = v.y;
-      fin = (__ldg(f.NF[k] + idx) & 1) == 0;
+      fin = (window_flags(f.NF[k], idx - f.x_lo) & 1) == 0;
     }
   } else {
     const int nV = nX * nZ;
@@ -648,7 +648,7 @@ __device__ __forceinline__ int classify_box(const Checker& c, const float R[9], 
       r = -1; fl |= REC_NEEDS_REDUCE;
     } else {
       const float2* __restrict__ T = f.T[kk];
-      const unsigned char* __restrict__ NF = f.NF[kk];
+      const uint32_t* __restrict__ NF = f.NF[kk];
       const int sW = 1 << kk;
       float mx = -CUDART_INF_F, mn = CUDART_INF_F;
       int nf = 0;
@@ -658,7 +658,7 @@ __device__ __forceinline__ int classify_box(const Checker& c, const float R[9], 
         const size_t i00 = (size_t)zs0 * f.pitch + xs0, i01 = (size_t)zs0 * f.pitch + xs1,
                      i10 = (size_t)zs1 * f.pitch + xs0, i11 = (size_t)zs1 * f.pitch + xs1;
         const float2 v0 = __ldg(T + i00), v1 = __ldg(T + i01), v2 = __ldg(T + i10), v3 = __ldg(T + i11);
-        const int n0 = __ldg(NF + i00), n1 = __ldg(NF + i01), n2 = __ldg(NF + i10), n3 = __ldg(NF + i11);
+        const int n0 = window_flags(NF, i00 - f.x_lo), n1 = window_flags(NF, i01 - f.x_lo), n2 = window_flags(NF, i10 - f.x_lo), n3 = window_flags(NF, i11 - f.x_lo);
         mx = fmaxf(fmaxf(v0.x, v1.x), fmaxf(v2.x, v3.x));
         mn = fminf(fminf(v0.y, v1.y), fminf(v2.y, v3.y));
         nf = n0 | n1 | n2 | n3;
@@ -670,7 +670,7 @@ __device__ __forceinline__ int classify_box(const Checker& c, const float R[9], 
             const size_t idx = (size_t)zs * f.pitch + xs;
             const float2 v = __ldg(T + idx);
             mx = fmaxf(mx, v.x); mn = fminf(mn, v.y);
-            nf |= __ldg(NF + idx);
+            nf |= window_flags(NF, idx - f.x_lo);
           }
         }
       }

@@ -1,8 +1,35 @@
-"""Multi-GPU plumbing of the pose-validity path: poses are independent given the read-only map,
-so every rank checks its own contiguous shard of the sample stream and the ranks exchange only the ordered indices of
-the valid samples -- one count all-gather plus one padded index all-gather (NCCL over NVLink on GPUs; the same code
-runs on gloo/CPU tensors, which is what tests/test_sharding_cpu.py exercises)."""
+"""Multi-GPU plumbing of the pose-validity path: poses are independent given the read-only map.
+Two layouts: (1) pose shards against a replicated map (configs[1]); (2) SPATIAL shards (configs[4]): the map is cut into
+row slabs, rank r holds slab r plus a halo (artp_set_map_window) and checks the samples whose x falls into its slab
+(slab_window / rank_of_x below). Either way the ranks exchange only verdicts: one all-gather of the bit-packed masks (NCCL
+over NVLink on GPUs; the same code runs on gloo/CPU tensors, which is what tests/test_sharding_cpu.py exercises)."""
 from __future__ import annotations
+
+
+def slab_window(rows: int, rank: int, world: int, halo: int, align: int = 4):
+    """Row slab [s0, s1) of rank `rank` and the window [lo, hi) it uploads (slab + halo, clipped to the map; lo aligned down
+    to `align` rows because artp_set_map_window wants row0 % 4 == 0). halo >= largest box half-diagonal + box offsets, in rows."""
+    base, rem = divmod(rows, world)
+    s0 = rank * base + min(rank, rem)
+    s1 = s0 + base + (1 if rank < rem else 0)
+    lo = max(0, s0 - halo)
+    lo -= lo % align
+    return s0, s1, lo, min(rows, s1 + halo)
+
+
+def row_of_x(x, cx: float, length_x: float, res: float, rows: int):
+    """grid_map row index of a position x (rows run towards -x), clamped."""
+    import numpy as np
+    return np.clip(np.floor((cx + 0.5 * length_x - np.asarray(x)) / res).astype(np.int64), 0, rows - 1)
+
+
+def rank_of_x(x, cx: float, length_x: float, res: float, rows: int, world: int):
+    """The rank whose slab holds position x (the routing rule of the spatially sharded path)."""
+    import numpy as np
+    r = row_of_x(x, cx, length_x, res, rows)
+    base, rem = divmod(rows, world)
+    edge = (base + 1) * rem           # first `rem` slabs have base + 1 rows
+    return np.where(r < edge, r // (base + 1), rem + (r - edge) // max(base, 1)).astype(np.int64)
 
 
 def shard_range(n_total: int, rank: int, world: int):

@@ -190,9 +190,8 @@ def run_c5(torch, dist, apb, synth, world, rank, local, flush, steps=5):
     N5, total, halo = 4000, 8_000_000, 40
     n_r = total // world
     m = synth.make_fbm_map(N5, N5, MAP_RES, seed=MAP_SEED, amp=0.6, n_walls=96)
-    rows_per = N5 // world
-    s0, s1 = rank * rows_per, (rank + 1) * rows_per
-    lo, hi = max(0, s0 - halo), min(N5, s1 + halo)
+    from art_planner_b200 import sharding
+    s0, s1, lo, hi = sharding.slab_window(N5, rank, world, halo)
     chk = apb.StateValidityChecker(synth.PARAMS_YAML, device=local)
     chk.setMap(m)
     t0 = time.perf_counter()
@@ -206,6 +205,7 @@ def run_c5(torch, dist, apb, synth, world, rank, local, flush, steps=5):
     x = x_lo + (0.0005 + 0.999 * synth.hash_uniform(7, 1, k)) * (x_hi - x_lo)
     y = m.cy + (synth.hash_uniform(7, 2, k) - 0.5) * ly * 0.999
     poses = synth.make_terrain_poses(m, n_r, seed=7, start=rank * n_r, xy=(x, y))
+    assert (sharding.rank_of_x(poses[:, 0], m.cx, lx, MAP_RES, N5, world) == rank).all()      # every sample is routed here
     d = torch.from_numpy(poses).cuda()
     v = torch.empty(n_r, dtype=torch.uint8, device="cuda")
     words = (n_r + 31) // 32

@@ -87,3 +87,25 @@ def test_bit_packing_reference_roundtrip():
         bits = sharding.pack_bits_reference(v)
         assert bits.numel() == (n + 31) // 32 and bits.dtype == torch.int32
         assert sharding.indices_from_bits(bits, n, 1).tolist() == torch.nonzero(v).reshape(-1).tolist()
+
+
+def test_spatial_slabs_cover_the_map_and_route_every_sample():
+    """slab_window / rank_of_x (configs[4] layout): slabs tile the rows, windows are slab + halo with 4-aligned starts, and
+    every position is routed to the rank whose slab holds its grid_map row."""
+    import numpy as np
+    from art_planner_b200 import sharding, synth
+    for rows, world in ((4000, 8), (4000, 4), (1001, 3), (600, 7)):
+        covered = np.zeros(rows, int)
+        for r in range(world):
+            s0, s1, lo, hi = sharding.slab_window(rows, r, world, halo=40)
+            covered[s0:s1] += 1
+            assert lo % 4 == 0 and lo <= max(0, s0 - 40) and hi == min(rows, s1 + 40) and lo >= 0
+        assert (covered == 1).all()
+        res, cx = 0.04, 1.5
+        lx = rows * res
+        x = cx + (synth.hash_uniform(3, 1, np.arange(20000)) - 0.5) * lx * 0.9999
+        rk = sharding.rank_of_x(x, cx, lx, res, rows, world)
+        row = sharding.row_of_x(x, cx, lx, res, rows)
+        for r in range(world):
+            s0, s1, _, _ = sharding.slab_window(rows, r, world, halo=40)
+            assert ((row[rk == r] >= s0) & (row[rk == r] < s1)).all()
