@@ -261,7 +261,8 @@ class StateValidityChecker:
         return float(ms[0]), float(ms[1]), float(ms[2])
 
     def lastStageTimesMs(self):
-        """(classify, big-tile queue, reach-box queue, 0, plane grouping) ms of the most recent check call."""
+        """(classify, big-tile queue, reach queue (warp per box), reach queue (8-lane groups), plane grouping) ms of the most recent
+        check call."""
         ms = (C.c_float * 5)()
         self._h.check(self._h.lib.artp_get_last_stage_timing(self._h.h, ms))
         return tuple(float(x) for x in ms)

@@ -41,12 +41,14 @@ struct Handle {
   int win_row0 = 0, win_rows = 0;   // rows held by this handle (artp_set_map_window); whole map: 0, rows
   bool has_map = false;
   // [0] warp-stage claim counter, [1] defer count, [2] reach-vertex claim counter, [3] warp-queue count,
-  // [4] reach-queue count, [5] plane-list count, [6] reach-plane claim counter, [7] scratch (sampler CDF validation)
+  // [4] reach-queue count, [5], [6] unused, [7] scratch (sampler CDF validation), [8] group-queue count, [9] its claim counter
   uint32_t* d_ctr = nullptr;
   uint32_t* d_defer = nullptr;      // deferred record list (bit 31: reach-box queue)
   size_t defer_cap = 0;
   artp::BoxRec* d_recs = nullptr;   // classify -> warp-stage box queue (torso boxes, reach boxes of unusual size)
-  artp::BoxRec* d_recs_f = nullptr; // classify -> thread-level reach-box queue
+  artp::BoxRec* d_recs_f = nullptr; // classify -> reach-box queue (one warp per box: zones with -inf or mergeable planes)
+  artp::BoxRec* d_recs_g = nullptr; // classify -> reach-box queue of the 8-lane-group kernel (all-finite, merge-free zones)
+  int group_grid = 0, group_smem = 0;
   size_t recs_cap = 0;
   uint32_t* d_block_counts = nullptr;
   size_t block_counts_cap = 0;
@@ -361,11 +363,12 @@ int ensure_queues(Handle* h, size_t n_items, cudaStream_t s) {
   const size_t need = 5 * std::min(n_items, kChunkItems);
   if (h->recs_cap >= need) return ARTP_OK;
   CU_TRY(h, cudaDeviceSynchronize());   // rare (growth only): users on any stream must be done before the free
-  cudaFree(h->d_defer); cudaFree(h->d_recs); cudaFree(h->d_recs_f);
-  h->d_defer = nullptr; h->d_recs = nullptr; h->d_recs_f = nullptr; h->recs_cap = 0;
+  cudaFree(h->d_defer); cudaFree(h->d_recs); cudaFree(h->d_recs_f); cudaFree(h->d_recs_g);
+  h->d_defer = nullptr; h->d_recs = nullptr; h->d_recs_f = nullptr; h->d_recs_g = nullptr; h->recs_cap = 0;
   const size_t cap = std::max<size_t>(need, 1u << 16);
   CU_TRY(h, cudaMalloc(&h->d_recs, cap * sizeof(artp::BoxRec)));
   CU_TRY(h, cudaMalloc(&h->d_recs_f, cap * sizeof(artp::BoxRec)));
+  CU_TRY(h, cudaMalloc(&h->d_recs_g, cap * sizeof(artp::BoxRec)));
   CU_TRY(h, cudaMalloc(&h->d_defer, cap * sizeof(uint32_t)));
   h->recs_cap = cap; h->defer_cap = cap;
   return ARTP_OK;
@@ -430,13 +433,13 @@ struct HostFeed {
 // The claim counters of the consumer stages restart where the next slice's producers will append (the persistent
 // consumers of the previous slice overshoot their counters).
 __global__ void restart_claims_kernel(uint32_t* ctr) {
-  ctr[0] = ctr[3]; ctr[2] = ctr[4];
+  ctr[0] = ctr[3]; ctr[2] = ctr[4]; ctr[9] = ctr[8];
 }
 
 // Slice i of a piped round is closed: its box stages consume the queue entries [end of slice i-1, current count).
 __global__ void close_slice_kernel(const uint32_t* ctr, uint32_t* slices, int i) {
   const uint32_t w0 = i ? slices[4 * (i - 1)] : 0u, f0 = i ? slices[4 * (i - 1) + 2] : 0u;
-  slices[4 * i] = ctr[3]; slices[4 * i + 1] = w0;        // big-tile queue: end, claim counter (starts at the slice's begin)
+  slices[4 * i] = ctr[8]; slices[4 * i + 1] = w0;        // group queue: end, claim counter (starts at the slice's begin)
   slices[4 * i + 2] = ctr[4]; slices[4 * i + 3] = f0;    // reach-box queue
 }
 
@@ -448,7 +451,7 @@ __global__ void close_slice_kernel(const uint32_t* ctr, uint32_t* slices, int i)
 // so the copy, the classify stage and the box stages of three consecutive slices overlap; s waits for box_stream at the end.
 int run_round_piped(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed, size_t base, size_t end, size_t slice,
                     uint32_t& launches, size_t& ev_i) {
-  CU_TRY(h, cudaMemsetAsync(h->d_ctr, 0, 7 * sizeof(uint32_t), s));
+  CU_TRY(h, cudaMemsetAsync(h->d_ctr, 0, 16 * sizeof(uint32_t), s));
   // slice boundaries
   size_t cut[kMaxSlices + 1];
   int ncut = 0;
@@ -476,7 +479,8 @@ int run_round_piped(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* fee
     w.item_base = (uint32_t)lo;
     w.n_items = (uint32_t)hi;
     artp::classify_items_kernel<<<(unsigned)((hi - lo + 127) / 128), 128, 0, s>>>(
-        h->chk, w, h->d_recs, h->d_recs_f, h->d_ctr + 3, h->d_ctr + 4, (h->mode == 1 ? 1 : 0) | h->k0_flags);
+        h->chk, w, h->d_recs, h->d_recs_f, h->group_grid ? h->d_recs_g : nullptr, h->d_ctr + 3, h->d_ctr + 4, h->d_ctr + 8,
+        (h->mode == 1 ? 1 : 0) | h->k0_flags);
     close_slice_kernel<<<1, 1, 0, s>>>(h->d_ctr, h->d_slices, si);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->slice_ev[si], s));
@@ -488,6 +492,12 @@ int run_round_piped(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* fee
       artp::box_tiles_warp_kernel<<<grid_f, wpc * 32, h->tile_smem[1], h->box_stream>>>(
           h->chk, h->tile_map[1][1], h->tile_map[1][1], h->tile_cfg[1], w, h->d_recs_f, h->d_slices + 4 * si + 2, h->d_slices + 4 * si + 3,
           h->d_ctr + 1, h->d_defer, artp::kDeferReachBit, h->mode == 1);
+      launches += 1;
+    }
+    if (h->group_grid) {
+      const unsigned grid_g = (unsigned)std::min<size_t>((size_t)h->group_grid, (nb + 7) / 8);
+      artp::reach_groups_kernel<<<grid_g, artp::kMaxTileWarps * 32, h->group_smem, h->box_stream>>>(
+          h->chk, h->tile_map[1][1], h->tile_cfg[1], w, h->d_recs_g, h->d_slices + 4 * si, h->d_slices + 4 * si + 1);
       launches += 1;
     }
     CU_TRY(h, cudaGetLastError());
@@ -548,7 +558,7 @@ int run_items(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed = nu
       if (rc) return rc;
       continue;
     }
-    CU_TRY(h, cudaMemsetAsync(h->d_ctr, 0, 7 * sizeof(uint32_t), s));
+    CU_TRY(h, cudaMemsetAsync(h->d_ctr, 0, 16 * sizeof(uint32_t), s));
     const size_t slice = (feed && feed->slice_items < end - base) ? feed->slice_items : (end - base);
     for (size_t lo = base; lo < end; lo += slice) {
       const size_t hi = std::min(end, lo + slice);
@@ -569,7 +579,8 @@ int run_items(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed = nu
       if (lo != base) { restart_claims_kernel<<<1, 1, 0, s>>>(h->d_ctr); launches += 1; }
       if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[0], s));
       artp::classify_items_kernel<<<(unsigned)((hi - lo + 127) / 128), 128, 0, s>>>(
-          h->chk, w, h->d_recs, h->d_recs_f, h->d_ctr + 3, h->d_ctr + 4, (h->mode == 1 ? 1 : 0) | h->k0_flags);
+          h->chk, w, h->d_recs, h->d_recs_f, h->group_grid ? h->d_recs_g : nullptr, h->d_ctr + 3, h->d_ctr + 4, h->d_ctr + 8,
+        (h->mode == 1 ? 1 : 0) | h->k0_flags);
       CU_TRY(h, cudaGetLastError());
       if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[1], s));
       // small batches (the planner's one-state isValid calls): no more CTAs than there can be boxes
@@ -592,7 +603,15 @@ int run_items(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed = nu
         CU_TRY(h, cudaGetLastError());
         launches += 1;
       }
-      if (h->timing && last) { CU_TRY(h, cudaEventRecord(h->ev[3], s)); CU_TRY(h, cudaEventRecord(h->ev[4], s)); }
+      if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[3], s));
+      if (h->group_grid) {
+        const unsigned grid_g = (unsigned)std::min<size_t>((size_t)h->group_grid, (nb + 7) / 8);
+        artp::reach_groups_kernel<<<grid_g, artp::kMaxTileWarps * 32, h->group_smem, s>>>(h->chk, h->tile_map[1][1], h->tile_cfg[1], w,
+                                                                                           h->d_recs_g, h->d_ctr + 8, h->d_ctr + 9);
+        CU_TRY(h, cudaGetLastError());
+        launches += 1;
+      }
+      if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[4], s));
       launches += 2;
     }
     w.item_base = (uint32_t)base;
@@ -666,7 +685,7 @@ int artp_create(const artp_params* params, artp_handle** out) {
   if ((e = cudaMalloc(&h->d_slices, kMaxSlices * 4 * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc", e);
   for (int i = 0; i < kCopyEvents; ++i)
     if ((e = cudaEventCreateWithFlags(&h->copy_ev[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
-  if ((e = cudaMalloc(&h->d_ctr, 8 * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc", e);
+  if ((e = cudaMalloc(&h->d_ctr, 16 * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc", e);
   for (int g = 0; g < 2; ++g)
     if ((e = cudaEventCreateWithFlags(&h->chain_ev[g], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaHostAlloc((void**)&h->h_err, 64, cudaHostAllocMapped)) != cudaSuccess) return fail("cudaHostAlloc", e);
@@ -705,7 +724,7 @@ void artp_destroy(artp_handle* hh) {
   cudaFree(h->d_slices);
   for (int k = 0; k < 2; ++k) for (int l = 0; l <= artp::kMaxLevel; ++l) { cudaFree(h->d_T[k][l]); cudaFree(h->d_NF[k][l]); }
   cudaFree(h->d_H[0]); cudaFree(h->d_H[1]); cudaFree(h->d_ctr); cudaFree(h->d_defer); cudaFree(h->d_stage);
-  cudaFree(h->d_block_counts); cudaFree(h->d_recs); cudaFree(h->d_recs_f); cudaFree(h->d_samp_layers); cudaFree(h->d_samp_scratch);
+  cudaFree(h->d_block_counts); cudaFree(h->d_recs); cudaFree(h->d_recs_f); cudaFree(h->d_recs_g); cudaFree(h->d_samp_layers); cudaFree(h->d_samp_scratch);
   if (h->h_small_out) cudaFreeHost(h->h_small_out);
   if (h->h_err) cudaFreeHost(h->h_err);
   for (int g = 0; g < 2; ++g) if (h->chain_ev[g]) cudaEventDestroy(h->chain_ev[g]);
@@ -790,10 +809,12 @@ int artp_get_stats(artp_handle* hh, artp_stats* out) {
   uint32_t ctr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   CU_TRY(h, cudaMemcpy(ctr, h->d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost));   // synchronises the device
   h->stats.last_deferred = ctr[1];
-  h->stats.last_queued_boxes = ctr[3] + ctr[4];
+  uint32_t cg = 0;
+  CU_TRY(h, cudaMemcpy(&cg, h->d_ctr + 8, sizeof(cg), cudaMemcpyDeviceToHost));
+  h->stats.last_queued_boxes = ctr[3] + ctr[4] + cg;
   h->stats.last_queued_warp_stage = ctr[3];
   h->stats.last_queued_reach_stage = ctr[4];
-  h->stats.last_reach_plane_stage = 0;
+  h->stats.last_reach_plane_stage = cg;
   if (h->deferred_unread) { h->stats.poses_deferred += ctr[1]; h->deferred_unread = false; }
   *out = h->stats;
   return take_sticky_error(h);
@@ -964,6 +985,17 @@ int artp_set_map_window(artp_handle* hh, const float* elevation, const float* el
       h->tile_cfg[q] = tc; h->tile_warps[q] = wpc;
       h->tile_smem[q] = (int)((size_t)wpc * tc.slots * tc.stride + 128);
       if (q == 1) { h->chk.reach_tw = tc.tw; h->chk.reach_th = tc.th; }
+    }
+    h->group_grid = 0;
+    if (h->chk.reach_tw && h->tile_cfg[1].tw <= 127 && h->tile_cfg[1].th <= 255) {   // task packing: 7 + 8 bits of cell coordinates
+      const int gsm = artp::kMaxTileWarps * 8 * (int)h->tile_cfg[1].stride + 128;
+      if (gsm <= 160 * 1024 && std::getenv("ARTP_GROUPS")) {   // opt-in until validated on hardware
+        CU_TRY(h, cudaFuncSetAttribute(artp::reach_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm));
+        int ps = 0;
+        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, artp::reach_groups_kernel, artp::kMaxTileWarps * 32, gsm));
+        h->group_grid = h->sm_count * std::max(ps, 1);
+        h->group_smem = gsm;
+      }
     }
     const int smax = std::max(h->tile_smem[0], h->tile_smem[1]);
     CU_TRY(h, cudaFuncSetAttribute(artp::box_tiles_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));

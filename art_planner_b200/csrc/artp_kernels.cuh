@@ -588,6 +588,7 @@ struct alignas(16) BoxRec {
 };
 static_assert(sizeof(BoxRec) == 80, "BoxRec is read as five 16-byte words");
 enum { REC_ALLFINITE = 8, REC_NEEDS_REDUCE = 16, REC_MERGEFREE = 32 };
+constexpr uint32_t kPendingGroup = 0x80000000u;   // classify-internal tag: the reach box goes to the 8-lane-group queue
 
 __device__ __forceinline__ void rec_to_ctx(const Checker& c, const BoxRec& r, BoxCtx& b) {
 #pragma unroll
@@ -711,7 +712,8 @@ __device__ __forceinline__ int classify_box(const Checker& c, const float R[9], 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 8)
 classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs_w, BoxRec* __restrict__ recs_f,
-                      uint32_t* __restrict__ count_w, uint32_t* __restrict__ count_f, int flags) {
+                      BoxRec* __restrict__ recs_g, uint32_t* __restrict__ count_w, uint32_t* __restrict__ count_f,
+                      uint32_t* __restrict__ count_g, int flags) {
   const int force_all = flags & 1;      // every in-map box goes to the grouping stage (artp_set_mode 1)
   // Vertex probes here only for reach boxes (one cell, most lanes busy); an undecided torso is rare (a few lanes of a
   // warp) and its probes run lane-parallel at the head of the warp stage instead. ARTP_K0_FLAGS=2 turns probes off.
@@ -720,7 +722,7 @@ classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs_w
   const bool in_range = item < w.n_items;
   const int lane = threadIdx.x & 31;
   int result = 1;                 // 1 valid so far, 0 invalid
-  int n_w = 0, n_f = 0;           // undecided boxes of this item for the big-tile queue / the reach-box queue
+  int n_w = 0, n_f = 0, n_g = 0;  // undecided boxes of this item: big-tile queue / reach-box queue (of which n_g for the group kernel)
   struct Pending { float P[3], minB, maxB; int x0, x1, z0, z1; uint32_t fl; };   // R1 is shared by the item's boxes
   Pending ub[5];                  // big-tile boxes from the front, reach boxes from the back
   float R1[9];
@@ -751,47 +753,55 @@ classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs_w
         // reach boxes go to their own queue (small TMA tiles); the torso -- and a reach box whose zone would not fit the
         // small tile -- to the big-tile queue
         const bool thread_path = foot && (b.x1 - b.x0) + 4 <= c.reach_tw && (b.z1 - b.z0) + 1 <= c.reach_th;
+        // ... and of those, the common kind (all-finite, merge-free zone, reduced by the tables) to the 8-lane-group kernel
+        const bool group_path = thread_path && recs_g != nullptr &&
+                                (fl & (REC_ALLFINITE | REC_MERGEFREE | REC_NEEDS_REDUCE)) == (REC_ALLFINITE | REC_MERGEFREE);
         const int q = thread_path ? 4 - n_f++ : n_w++;
+        if (group_path) ++n_g;
         Pending& pd = ub[q];
         pd.P[0] = b.P[0]; pd.P[1] = b.P[1]; pd.P[2] = b.P[2]; pd.minB = b.minB; pd.maxB = b.maxB;
-        pd.x0 = b.x0; pd.x1 = b.x1; pd.z0 = b.z0; pd.z1 = b.z1; pd.fl = fl;
+        pd.x0 = b.x0; pd.x1 = b.x1; pd.z0 = b.z0; pd.z1 = b.z1; pd.fl = fl | (group_path ? kPendingGroup : 0u);
       }
       else if (!foot) { if (r == R_HIT) result = 0; }      // torso must be free
       else { if (r == R_FREE) result = 0; }                // every reach box must touch
     }
-    if (!result) { n_w = 0; n_f = 0; }
+    if (!result) { n_w = 0; n_f = 0; n_g = 0; }
     // provisional result; the later stages clear it if an undecided box fails
     if (w.edge_mode) { if (!result) w.valid[slot] = 0; }
     else w.valid[slot] = (uint8_t)result;
   }
-  // queue the undecided boxes: one atomic per warp and queue (inclusive scan of the per-lane counts)
-  int incl_w = n_w, incl_f = n_f;
+  // queue the undecided boxes: one atomic per warp and queue (inclusive scans of the per-lane counts)
+  const int n_fp = n_f - n_g;     // reach boxes for the one-warp-per-box kernel
+  int incl_w = n_w, incl_f = n_fp, incl_g = n_g;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const int yw = __shfl_up_sync(kFull, incl_w, o), yf = __shfl_up_sync(kFull, incl_f, o);
-    if (lane >= o) { incl_w += yw; incl_f += yf; }
+    const int yw = __shfl_up_sync(kFull, incl_w, o), yf = __shfl_up_sync(kFull, incl_f, o), yg = __shfl_up_sync(kFull, incl_g, o);
+    if (lane >= o) { incl_w += yw; incl_f += yf; incl_g += yg; }
   }
-  const int total_w = __shfl_sync(kFull, incl_w, 31), total_f = __shfl_sync(kFull, incl_f, 31);
-  if (total_w == 0 && total_f == 0) return;
-  uint32_t base_w = 0, base_f = 0;
+  const int total_w = __shfl_sync(kFull, incl_w, 31), total_f = __shfl_sync(kFull, incl_f, 31), total_g = __shfl_sync(kFull, incl_g, 31);
+  if (total_w == 0 && total_f == 0 && total_g == 0) return;
+  uint32_t base_w = 0, base_f = 0, base_g = 0;
   if (lane == 31) {
     if (total_w) base_w = atomicAdd(count_w, (uint32_t)total_w);
     if (total_f) base_f = atomicAdd(count_f, (uint32_t)total_f);
+    if (total_g) base_g = atomicAdd(count_g, (uint32_t)total_g);
   }
   base_w = __shfl_sync(kFull, base_w, 31) + (uint32_t)(incl_w - n_w);
-  base_f = __shfl_sync(kFull, base_f, 31) + (uint32_t)(incl_f - n_f);
+  base_f = __shfl_sync(kFull, base_f, 31) + (uint32_t)(incl_f - n_fp);
+  base_g = __shfl_sync(kFull, base_g, 31) + (uint32_t)(incl_g - n_g);
 #pragma unroll 1
   for (int q = 0; q < n_w + n_f; ++q) {
     const bool fq = q >= n_w;
     const int src = fq ? 4 - (q - n_w) : q;
-    BoxRec& o = fq ? recs_f[base_f + (q - n_w)] : recs_w[base_w + q];
+    const bool gq = fq && (ub[src].fl & kPendingGroup);
+    BoxRec& o = gq ? recs_g[base_g++] : (fq ? recs_f[base_f++] : recs_w[base_w + q]);
     const Pending& b = ub[src];
 #pragma unroll
     for (int i = 0; i < 9; ++i) o.R1[i] = R1[i];
     o.P[0] = b.P[0]; o.P[1] = b.P[1]; o.P[2] = b.P[2];
     o.minB = b.minB; o.maxB = b.maxB;
     o.x0 = b.x0; o.x1 = b.x1; o.z0 = b.z0; o.z1 = b.z1;
-    o.item = slot; o.flags = b.fl;             // later stages only need the verdict slot
+    o.item = slot; o.flags = b.fl & ~kPendingGroup;   // later stages only need the verdict slot
   }
 }
 

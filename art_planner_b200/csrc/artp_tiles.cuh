@@ -137,4 +137,172 @@ box_tiles_warp_kernel(const Checker c, const __grid_constant__ CUtensorMap map0,
   }
 }
 
+// -------------------------------------------------------------------------------------------------------------------
+// Reach boxes, the common kind: all-finite, merge-free zone (no screen, no grouping), reduced by the tables. A reach
+// box's 81 vertices / 8 corners do not fill a warp (the one-warp-per-box kernel above runs them at 20 of 32 lanes and pays
+// its per-box overhead 1 : 1), so here a warp decides FOUR boxes at a time, 8 lanes each: lane = vertex in the vertex
+// stage, lane = corner when the candidate cells are collected, lane = (cell, triangle) task when their planes are tested.
+// All four groups run in lock-step through the same loops (trip counts = the maximum over the groups, finished groups are
+// predicated off), so every ballot is a full-warp ballot and the group result is a byte of it.
+// -------------------------------------------------------------------------------------------------------------------
+constexpr int kGroupRounds = 8;      // a warp claims 4 * kGroupRounds records per atomic
+constexpr int kGroupTasks = 64;      // candidate (cell, triangle) tasks per box: 8 corners x 4 cells x 2
+
+__global__ void __launch_bounds__(kMaxTileWarps * 32, 3)
+reach_groups_kernel(const Checker c, const __grid_constant__ CUtensorMap map1, const TileCfg tc, const Work w,
+                    const BoxRec* __restrict__ recs, const uint32_t* __restrict__ rec_count, uint32_t* __restrict__ work_counter) {
+  extern __shared__ __align__(128) unsigned char tile_smem[];
+  __shared__ uint64_t bars[kMaxTileWarps][2];
+  __shared__ uint16_t tasks_all[kMaxTileWarps][4][kGroupTasks];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 3, gl = lane & 7;
+  const Field& f = c.f[1];
+  unsigned char* slots = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tile_smem) + 127) & ~(uintptr_t)127) +
+                         (size_t)wid * 8 * tc.stride;   // [slot 0/1][group 0..3]
+  uint16_t* tasks = tasks_all[wid][g];
+  if (lane == 0) { mbar_init(&bars[wid][0], 1); mbar_init(&bars[wid][1], 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  uint32_t phase[2] = {0u, 0u};
+  const uint32_t total = *rec_count;
+  const unsigned gshift = (unsigned)g * 8u;
+  // lanes 0, 8, 16, 24 read the zone origins of the four records of a round, lane 0 starts their copies
+  auto prefetch = [&](uint32_t first, int slot) {
+    const uint32_t ri = first + (uint32_t)g;
+    int x0 = 0, z0 = 0;
+    const bool act = ri < total;
+    if (act && gl == 0) {
+      x0 = (int)__ldg(reinterpret_cast<const uint4*>(recs + ri) + 3).z;
+      z0 = (int)__ldg(reinterpret_cast<const uint4*>(recs + ri) + 4).x;
+    }
+    const int nact = (int)min(4u, total - first);
+    if (lane == 0) mbar_expect_tx(&bars[wid][slot], (uint32_t)nact * tc.bytes);
+#pragma unroll 1
+    for (int q = 0; q < nact; ++q) {
+      const int sx = __shfl_sync(kFull, x0, q * 8), sz = __shfl_sync(kFull, z0, q * 8);
+      if (lane == 0) tma_tile_2d(slots + (size_t)(slot * 4 + q) * tc.stride, &map1, &bars[wid][slot], (sx & ~3) - tc.x_off, sz);
+    }
+  };
+  for (;;) {
+    uint32_t r0 = 0;
+    if (lane == 0) r0 = atomicAdd(work_counter, 4u * kGroupRounds);
+    r0 = __shfl_sync(kFull, r0, 0);
+    if (r0 >= total) break;
+    const int nrounds = (int)((min(r0 + 4u * kGroupRounds, total) - r0 + 3u) / 4u);
+    __syncwarp();                          // every lane is done with both slots
+    prefetch(r0, 0);
+#pragma unroll 1
+    for (int round = 0; round < nrounds; ++round) {
+      const int slot = round & 1;
+      const uint32_t ri = r0 + 4u * (uint32_t)round + (uint32_t)g;
+      const bool act = ri < total;
+      BoxRec r;
+      if (act) {
+        const uint4* rp = reinterpret_cast<const uint4*>(recs + ri);
+        uint4* dst = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) dst[i] = __ldg(rp + i);
+      }
+      if (round + 1 < nrounds) { __syncwarp(); prefetch(r0 + 4u * (uint32_t)(round + 1), slot ^ 1); }
+      int alive = 0;
+      if (act && gl == 0) alive = (*(volatile const uint8_t*)(w.valid + r.item) != 0);
+      alive = __shfl_sync(kFull, alive, 0, 8);
+      mbar_wait(&bars[wid][slot], phase[slot]);
+      phase[slot] ^= 1u;
+      bool gdone = !(act && alive);        // group-uniform
+      BoxCtx b;
+      if (!gdone) rec_to_ctx(c, r, b);
+      else { b.x0 = b.z0 = 0; b.x1 = b.z1 = 1; }
+      const float* tile = reinterpret_cast<const float*>(slots + (size_t)(slot * 4 + g) * tc.stride) + (b.x0 & 3);
+      const int nX = b.x1 - b.x0 + 1, nZ = b.z1 - b.z0 + 1, nV = nX * nZ, nCZ = nZ - 1;
+      const float top = b.maxB + (1e-4f + 4e-6f * fabsf(b.maxB));
+      bool ghit = false;
+      // vertex stage, lane = vertex
+      {
+        int maxNV = gdone ? 0 : nV;
+        maxNV = max(maxNV, __shfl_xor_sync(kFull, maxNV, 8));
+        maxNV = max(maxNV, __shfl_xor_sync(kFull, maxNV, 16));
+        const uint32_t magicX = magic_for(nX);
+#pragma unroll 1
+        for (int t0 = 0; t0 < maxNV; t0 += 8) {
+          const int t = t0 + gl;
+          bool hit = false;
+          if (!gdone && t < nV) {
+            const int zi = (int)__umulhi((uint32_t)t, magicX), xi = t - zi * nX;
+            const float h = tile[zi * tc.tw + xi];
+            hit = h > b.minB && h < top && vertex_inside(b, (b.x0 + xi) * f.sW, h, (b.z0 + zi) * f.sD);
+          }
+          if ((__ballot_sync(kFull, hit) >> gshift) & 0xffu) { ghit = true; gdone = true; }
+          if (__all_sync(kFull, gdone)) break;
+        }
+      }
+      // plane stage: collect the candidate (cell, triangle) tasks, lane = corner
+      int nt = 0;
+      {
+        float px = b.P[0], pz = b.P[2];
+        const float h0 = 0.5f * b.side[0], h1 = 0.5f * b.side[1], h2 = 0.5f * b.side[2];
+        if (gl & 1) { px += h0 * b.R1[0]; pz += h0 * b.R1[6]; } else { px -= h0 * b.R1[0]; pz -= h0 * b.R1[6]; }
+        if (gl & 2) { px += h1 * b.R1[1]; pz += h1 * b.R1[7]; } else { px -= h1 * b.R1[1]; pz -= h1 * b.R1[7]; }
+        if (gl & 4) { px += h2 * b.R1[2]; pz += h2 * b.R1[8]; } else { px -= h2 * b.R1[2]; pz -= h2 * b.R1[8]; }
+        const float gx = px * f.iW, gz = pz * f.iD;
+        const int cxl = (int)floorf(gx - c.cell_margin), cxh = (int)floorf(gx + c.cell_margin);
+        const int czl = (int)floorf(gz - c.cell_margin), czh = (int)floorf(gz + c.cell_margin);
+        // an upright box projects its top corners into the cells of the bottom corners: the same cells twice
+        const bool same = __shfl_xor_sync(kFull, cxl, 4) == cxl && __shfl_xor_sync(kFull, cxh, 4) == cxh &&
+                          __shfl_xor_sync(kFull, czl, 4) == czl && __shfl_xor_sync(kFull, czh, 4) == czh;
+        int cells[4], ncell = 0;
+        if (!gdone && !((gl & 4) && same)) {
+#pragma unroll
+          for (int sub = 0; sub < 4; ++sub) {
+            if (((sub & 1) && cxh == cxl) || ((sub & 2) && czh == czl)) continue;
+            const int ccx = (sub & 1) ? cxh : cxl, ccz = (sub & 2) ? czh : czl;
+            if (ccx < b.x0 || ccx >= b.x1 || ccz < b.z0 || ccz >= b.z1) continue;
+            cells[ncell++] = ((ccx - b.x0) << 8) | (ccz - b.z0);
+          }
+        }
+        int incl = 2 * ncell;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          const int y = __shfl_up_sync(kFull, incl, o, 8);
+          if (gl >= o) incl += y;
+        }
+        nt = __shfl_sync(kFull, incl, 7, 8);
+        int pos = incl - 2 * ncell;
+        for (int i = 0; i < ncell; ++i) { tasks[pos++] = (uint16_t)(cells[i] << 1); tasks[pos++] = (uint16_t)((cells[i] << 1) | 1); }
+      }
+      __syncwarp();
+      // ... and test them, lane = task: the triangle's own plane, its contact points, point-in-triangle
+      {
+        int maxNT = nt;
+        maxNT = max(maxNT, __shfl_xor_sync(kFull, maxNT, 8));
+        maxNT = max(maxNT, __shfl_xor_sync(kFull, maxNT, 16));
+        bool hit_own = false;
+#pragma unroll 1
+        for (int q0 = 0; q0 < maxNT; q0 += 8) {
+          const int q = q0 + gl;
+          if (q < nt) {
+            const int tk = tasks[q];
+            const bool isUp = (tk & 1) == 0;
+            const int lx = tk >> 9, lz = (tk >> 1) & 0xff, ccx = b.x0 + lx, ccz = b.z0 + lz;
+            const float* p = tile + lz * tc.tw + lx;
+            const float hA = p[0], hB = p[1], hC = p[tc.tw], hD = p[tc.tw + 1];   // all finite (REC_ALLFINITE)
+            const bool keep = isUp ? (hA > b.minB || hB > b.minB || hC > b.minB) : (hB > b.minB || hC > b.minB || hD > b.minB);
+            if (keep) {
+              float pl[4], cx[4], cz[4];
+              cell_plane(f, isUp, ccx, ccz, hA, hB, hC, hD, pl);
+              const int nc = box_plane(b, pl, 4, cx, cz);
+              const int tcx = isUp ? ccx : ccx + 1, tcz = isUp ? ccz : ccz + 1;
+#pragma unroll 1
+              for (int i = 0; i < nc; ++i) hit_own = hit_own || on_tri(f, isUp, tcx, tcz, cx[i], cz[i]);
+            }
+          }
+        }
+        if ((__ballot_sync(kFull, hit_own) >> gshift) & 0xffu) ghit = true;
+      }
+      // a reach box that does not touch: pose invalid
+      if (gl == 0 && act && alive && !ghit) w.valid[r.item] = 0;
+      (void)nCZ;
+    }
+  }
+}
+
 }  // namespace artp

@@ -170,10 +170,11 @@ def pose_workload(torch, chk, flush, m, poses, steps, ref, kind, port, n_mt=400_
     t0 = time.perf_counter(); vm = ref.check_poses_mt(poses[:n_mt], cores); tm = time.perf_counter() - t0
     _, zv = port.check_poses(poses[:50_000], want_zone=True)
     return {"map": m.desc, "poses": n, "poses_per_s": n * steps / (tot * 1e-3), "ms_per_step": tot / steps,
-            "classify_ms": float(k[0]), "torso_queue_ms": float(k[1]), "reach_queue_ms": float(k[2]),
+            "classify_ms": float(k[0]), "torso_queue_ms": float(k[1]), "reach_queue_ms": float(k[2] + k[3]),
+            "reach_queue_warp_ms": float(k[2]), "reach_queue_groups_ms": float(k[3]),
             "group_stage_ms": float(k[4]), "pass_ms": float(k.sum()),
             "queued_boxes": st["last_queued_boxes"], "queued_warp_stage": st["last_queued_warp_stage"],
-            "queued_reach_stage": st["last_queued_reach_stage"],
+            "queued_reach_stage": st["last_queued_reach_stage"], "queued_reach_groups": st["last_reach_plane_stage"],
             "deferred_boxes": st["last_deferred"],
             "valid_fraction": float(got.mean()), "exit_mix": exit_mix(port, poses[:20_000]),
             "algorithmic_bytes_per_pose": 57.0 + 4.0 * float(zv.mean()),
@@ -249,7 +250,7 @@ def run_c5(torch, dist, apb, synth, world, rank, local, flush, steps=5):
                "poses_per_s": total * steps / (float(t[0]) * 1e-3), "ms_per_step": float(t[0]) / steps, "steps": steps,
                "samples_per_gpu": n_r, "map_rows_on_gpu": hi - lo if world > 1 else N5,
                "set_map_s": set_map_s, "valid_fraction": float(got.mean()),
-               "stage_ms_last_round": dict(zip(("classify", "torso_queue", "reach_queue", "unused", "group"), [float(z) for z in sm])),
+               "stage_ms_last_round": dict(zip(("classify", "torso_queue", "reach_queue_warp", "reach_queue_groups", "group"), [float(z) for z in sm])),
                "queued_boxes_last_round": st["last_queued_boxes"],
                "exchange": "one NCCL all-gather of the bit masks per step, inside the timed step (not pipelined)" if world > 1 else "none (N = 1)",
                "mask_equals_reference": bool(np.array_equal(got[sel], ref)),
@@ -660,7 +661,7 @@ def main():
         # queues + grouping), so they are divided by the SUM of the stage durations; the dominant kernel is the reach-box
         # queue launch of box_tiles_warp_kernel.
         sm = np.mean(np.array(stage_ms), 0)
-        k0, k_torso, k_reach, k2 = float(sm[0]), float(sm[1]), float(sm[2]), float(sm[4])
+        k0, k_torso, k_reach, k2 = float(sm[0]), float(sm[1]), float(sm[2] + sm[3]), float(sm[4])
         pass_ms = k0 + k_torso + k_reach + k2
         achieved = bytes_per_pose * n / (pass_ms * 1e-3) / 1e9
         traffic = None
@@ -685,14 +686,15 @@ def main():
                     "f64_api_value": world * n * e2e_steps / e2e64_s, "f64_api_h2d_bytes_per_step": n * 56,
                     "note": "PCIe Gen5 x16 moves 53-55 GB/s here (profiles/pcie_probe.cu): 28 MB = 0.52 ms, 56 MB = 1.04 ms, so the double entry point is copy-bound at <= 0.96e9 poses/s"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "box_tiles_warp_kernel (reach-box queue launch)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "reach_groups_kernel + box_tiles_warp_kernel (the two reach-box queues)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_pose": bytes_per_pose, "kernel_ms": k_reach,
                          "classify_kernel_ms": k0, "torso_queue_kernel_ms": k_torso, "group_kernel_ms": k2, "pass_ms": pass_ms,
                          "queued_boxes": int(queued), "deferred_boxes": int(deferred),
-                         "stage_ms": dict(zip(("classify", "torso_queue", "reach_queue", "unused", "group"), [float(x) for x in sm])),
+                         "stage_ms": dict(zip(("classify", "torso_queue", "reach_queue_warp", "reach_queue_groups", "group"), [float(x) for x in sm])),
                          "queued_warp_stage": stats_last["last_queued_warp_stage"],
                          "queued_reach_stage": stats_last["last_queued_reach_stage"],
+                         "queued_reach_groups": stats_last["last_reach_plane_stage"],
                          "actual_dram_GBps_dominant_kernel": (traffic / (k_reach * 1e-3) / 1e9) if traffic else None,
                          "note": "achieved = ALGORITHMIC bytes (the zone vertices the reference scans, SURVEY 8d) / sum of the stage "
                                  "durations; the range tables, plane tables and vertex probes answer most of those scans without reading "

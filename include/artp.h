@@ -82,8 +82,8 @@ typedef struct artp_stats {
   uint32_t last_launches;      /* kernels launched by the most recent call */
   uint32_t last_queued_boxes;  /* boxes the classify stage queued for the later stages in the most recent call's last round */
   uint32_t last_queued_warp_stage;   /* ... of which in the big-tile queue (torso boxes, reach boxes of unusual size) */
-  uint32_t last_queued_reach_stage;  /* ... of which in the reach-box queue (small tiles) */
-  uint32_t last_reach_plane_stage;   /* reserved (0) */
+  uint32_t last_queued_reach_stage;  /* ... of which in the one-warp-per-box reach queue (zones with -inf or mergeable planes) */
+  uint32_t last_reach_plane_stage;   /* ... of which in the 8-lane-group reach queue (all-finite, merge-free zones) */
 } artp_stats;
 
 int  artp_create(const artp_params* params, artp_handle** out);
@@ -253,7 +253,8 @@ int artp_debug_set_group_capacity(artp_handle* h, int max_triangles);
  * ms3[0..2] = classify (thread/item), box stages (warp stage + reach-box stages), plane-grouping block stage, in ms. */
 int artp_set_timing(artp_handle* h, int enable);
 int artp_get_last_timing(artp_handle* h, float* ms3);
-/* Per-stage form: ms5 = classify, big-tile queue (torso boxes), reach-box queue, 0, plane grouping. */
+/* Per-stage form: ms5 = classify, big-tile queue (torso boxes), reach-box queue (warp per box), reach-box queue (8-lane
+ * groups), plane grouping. */
 int artp_get_last_stage_timing(artp_handle* h, float* ms5);
 
 /* Test hook: 0 = normal (classify -> warp stage -> grouping stage for deferred boxes),
