@@ -989,7 +989,7 @@ int artp_set_map_window(artp_handle* hh, const float* elevation, const float* el
     h->group_grid = 0;
     if (h->chk.reach_tw && h->tile_cfg[1].tw <= 127 && h->tile_cfg[1].th <= 255) {   // task packing: 7 + 8 bits of cell coordinates
       const int gsm = artp::kMaxTileWarps * 8 * (int)h->tile_cfg[1].stride + 128;
-      if (gsm <= 160 * 1024 && std::getenv("ARTP_GROUPS")) {   // opt-in until validated on hardware
+      if (gsm <= 160 * 1024 && !std::getenv("ARTP_NO_GROUPS")) {   // ARTP_NO_GROUPS: every reach box takes the one-warp-per-box queue
         CU_TRY(h, cudaFuncSetAttribute(artp::reach_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm));
         int ps = 0;
         CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, artp::reach_groups_kernel, artp::kMaxTileWarps * 32, gsm));

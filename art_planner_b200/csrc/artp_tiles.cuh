@@ -196,6 +196,11 @@ reach_groups_kernel(const Checker c, const __grid_constant__ CUtensorMap map1, c
       const uint32_t ri = r0 + 4u * (uint32_t)round + (uint32_t)g;
       const bool act = ri < total;
       BoxRec r;
+      {
+        uint4* dst = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
       if (act) {
         const uint4* rp = reinterpret_cast<const uint4*>(recs + ri);
         uint4* dst = reinterpret_cast<uint4*>(&r);
@@ -208,10 +213,11 @@ reach_groups_kernel(const Checker c, const __grid_constant__ CUtensorMap map1, c
       alive = __shfl_sync(kFull, alive, 0, 8);
       mbar_wait(&bars[wid][slot], phase[slot]);
       phase[slot] ^= 1u;
+      __syncwarp();                        // lanes leave the barrier poll at different times
       bool gdone = !(act && alive);        // group-uniform
       BoxCtx b;
-      if (!gdone) rec_to_ctx(c, r, b);
-      else { b.x0 = b.z0 = 0; b.x1 = b.z1 = 1; }
+      rec_to_ctx(c, r, b);                 // an all-zero record for idle groups: every field defined
+      if (gdone) { b.x0 = b.z0 = 0; b.x1 = b.z1 = 1; }
       const float* tile = reinterpret_cast<const float*>(slots + (size_t)(slot * 4 + g) * tc.stride) + (b.x0 & 3);
       const int nX = b.x1 - b.x0 + 1, nZ = b.z1 - b.z0 + 1, nV = nX * nZ, nCZ = nZ - 1;
       const float top = b.maxB + (1e-4f + 4e-6f * fabsf(b.maxB));
@@ -219,8 +225,7 @@ reach_groups_kernel(const Checker c, const __grid_constant__ CUtensorMap map1, c
       // vertex stage, lane = vertex
       {
         int maxNV = gdone ? 0 : nV;
-        maxNV = max(maxNV, __shfl_xor_sync(kFull, maxNV, 8));
-        maxNV = max(maxNV, __shfl_xor_sync(kFull, maxNV, 16));
+        maxNV = __reduce_max_sync(kFull, maxNV);
         const uint32_t magicX = magic_for(nX);
 #pragma unroll 1
         for (int t0 = 0; t0 < maxNV; t0 += 8) {
@@ -235,6 +240,7 @@ reach_groups_kernel(const Checker c, const __grid_constant__ CUtensorMap map1, c
           if (__all_sync(kFull, gdone)) break;
         }
       }
+      __syncwarp();
       // plane stage: collect the candidate (cell, triangle) tasks, lane = corner
       int nt = 0;
       {
@@ -247,34 +253,40 @@ reach_groups_kernel(const Checker c, const __grid_constant__ CUtensorMap map1, c
         const int cxl = (int)floorf(gx - c.cell_margin), cxh = (int)floorf(gx + c.cell_margin);
         const int czl = (int)floorf(gz - c.cell_margin), czh = (int)floorf(gz + c.cell_margin);
         // an upright box projects its top corners into the cells of the bottom corners: the same cells twice
-        const bool same = __shfl_xor_sync(kFull, cxl, 4) == cxl && __shfl_xor_sync(kFull, cxh, 4) == cxh &&
-                          __shfl_xor_sync(kFull, czl, 4) == czl && __shfl_xor_sync(kFull, czh, 4) == czh;
-        int cells[4], ncell = 0;
-        if (!gdone && !((gl & 4) && same)) {
+        // (four unconditional exchanges: inside a short-circuit && the later ones would run in only some of the lanes)
+        const int oxl = __shfl_xor_sync(kFull, cxl, 4), oxh = __shfl_xor_sync(kFull, cxh, 4);
+        const int ozl = __shfl_xor_sync(kFull, czl, 4), ozh = __shfl_xor_sync(kFull, czh, 4);
+        const bool same = (oxl == cxl) & (oxh == cxh) & (ozl == czl) & (ozh == czh);
+        // the (up to four) cells of this corner that lie inside the zone: sub-cell s uses cxh for s & 1, czh for s & 2
+        const bool mine = !gdone && !((gl & 4) && same);
+        bool ok[4];
 #pragma unroll
-          for (int sub = 0; sub < 4; ++sub) {
-            if (((sub & 1) && cxh == cxl) || ((sub & 2) && czh == czl)) continue;
+        for (int sub = 0; sub < 4; ++sub) {
+          const int ccx = (sub & 1) ? cxh : cxl, ccz = (sub & 2) ? czh : czl;
+          ok[sub] = mine && !((sub & 1) && cxh == cxl) && !((sub & 2) && czh == czl) && ccx >= b.x0 && ccx < b.x1 && ccz >= b.z0 &&
+                    ccz < b.z1;
+        }
+        // task slots by ballots (order within the list is irrelevant): sub-cell s of lane gl sits behind all sub-cells < s
+        // of the group and behind sub-cell s of the lower lanes
+        int base = 0;
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub) {
+          const unsigned gm = (__ballot_sync(kFull, ok[sub]) >> gshift) & 0xffu;
+          if (ok[sub]) {
+            const int slot_i = base + __popc(gm & ((1u << gl) - 1u));
             const int ccx = (sub & 1) ? cxh : cxl, ccz = (sub & 2) ? czh : czl;
-            if (ccx < b.x0 || ccx >= b.x1 || ccz < b.z0 || ccz >= b.z1) continue;
-            cells[ncell++] = ((ccx - b.x0) << 8) | (ccz - b.z0);
+            const int code = (((ccx - b.x0) << 8) | (ccz - b.z0)) << 1;
+            tasks[2 * slot_i] = (uint16_t)code; tasks[2 * slot_i + 1] = (uint16_t)(code | 1);
           }
+          base += __popc(gm);
         }
-        int incl = 2 * ncell;
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          const int y = __shfl_up_sync(kFull, incl, o, 8);
-          if (gl >= o) incl += y;
-        }
-        nt = __shfl_sync(kFull, incl, 7, 8);
-        int pos = incl - 2 * ncell;
-        for (int i = 0; i < ncell; ++i) { tasks[pos++] = (uint16_t)(cells[i] << 1); tasks[pos++] = (uint16_t)((cells[i] << 1) | 1); }
+        nt = 2 * base;      // <= 64
       }
       __syncwarp();
       // ... and test them, lane = task: the triangle's own plane, its contact points, point-in-triangle
       {
         int maxNT = nt;
-        maxNT = max(maxNT, __shfl_xor_sync(kFull, maxNT, 8));
-        maxNT = max(maxNT, __shfl_xor_sync(kFull, maxNT, 16));
+        maxNT = __reduce_max_sync(kFull, maxNT);
         bool hit_own = false;
 #pragma unroll 1
         for (int q0 = 0; q0 < maxNT; q0 += 8) {
@@ -296,11 +308,13 @@ reach_groups_kernel(const Checker c, const __grid_constant__ CUtensorMap map1, c
             }
           }
         }
+        __syncwarp();
         if ((__ballot_sync(kFull, hit_own) >> gshift) & 0xffu) ghit = true;
       }
       // a reach box that does not touch: pose invalid
       if (gl == 0 && act && alive && !ghit) w.valid[r.item] = 0;
       (void)nCZ;
+      __syncwarp();
     }
   }
 }
