@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -56,13 +57,16 @@ struct Handle {
   size_t stage_cap = 0;
   cudaStream_t stream = nullptr;    // internal compute stream for the host-buffer API
   cudaStream_t copy_stream = nullptr;   // H2D slices of the host-buffer API
+  cudaStream_t group_stream = nullptr;  // the 8-lane-group kernel of slice i (host-fed rounds), beside the other box kernels
+  cudaEvent_t group_ev = nullptr;
   cudaStream_t box_stream = nullptr;    // box stages of slice i, concurrent with the copy + classify of slice i + 1
   cudaEvent_t copy_ev[16] = {};
   cudaEvent_t slice_ev[kMaxSlices] = {};   // classify of slice i done (box_stream waits on it)
   cudaEvent_t box_ev = nullptr;            // box stages of a round done (stream waits on it)
   int trace = 0;                           // env ARTP_TRACE: print the timeline of host-fed rounds (debug)
   cudaEvent_t tr_ev[6] = {};
-  uint32_t* d_slices = nullptr;            // per slice: {big-queue end, big-queue claim, reach-queue end, reach-queue claim}
+  cudaEvent_t tr_slice[8][4] = {};   // ARTP_TRACE: per slice: copy landed, classify start, classify done, box stages done
+  uint32_t* d_slices = nullptr;            // per slice, 8 words: {group-queue end, claim, reach-queue end, claim, big-tile-queue end, claim}
   int k1_grid = 0, k2_grid = 0, k2_smem = 0, k2_tcap = 0;
   // stage B (artp_tiles.cuh): [0] big tiles (torso queue, 4 warps per CTA), [1] small tiles (reach-box queue, 8 warps)
   artp::TileCfg tile_cfg[2] = {};
@@ -70,6 +74,7 @@ struct Handle {
   CUtensorMap tile_map[2][2];       // [cfg][layer]: 2-D tile maps over elevation / elevation_masked
   int k0_flags = 0;                 // tuning switch of the classify stage (env ARTP_K0_FLAGS: 2 = no vertex probes)
   bool slice_override = false;
+  float sched_override[9] = {0};    // env ARTP_SLICE_SCHEDULE="0.1,0.3,0.6": slice fractions of the host-fed rounds
   size_t slice_items_f64 = 128 * 1024, slice_items_f32 = 256 * 1024;   // H2D pipeline slices of the host-buffer calls (env ARTP_SLICE_ITEMS)
   int mode = 0;
   artp_cnn::State* cnn = nullptr;
@@ -438,17 +443,19 @@ __global__ void restart_claims_kernel(uint32_t* ctr) {
 
 // Slice i of a piped round is closed: its box stages consume the queue entries [end of slice i-1, current count).
 __global__ void close_slice_kernel(const uint32_t* ctr, uint32_t* slices, int i) {
-  const uint32_t w0 = i ? slices[4 * (i - 1)] : 0u, f0 = i ? slices[4 * (i - 1) + 2] : 0u;
-  slices[4 * i] = ctr[8]; slices[4 * i + 1] = w0;        // group queue: end, claim counter (starts at the slice's begin)
-  slices[4 * i + 2] = ctr[4]; slices[4 * i + 3] = f0;    // reach-box queue
+  const uint32_t g0 = i ? slices[8 * (i - 1)] : 0u, f0 = i ? slices[8 * (i - 1) + 2] : 0u, w0 = i ? slices[8 * (i - 1) + 4] : 0u;
+  slices[8 * i] = ctr[8]; slices[8 * i + 1] = g0;        // group queue: end, claim counter (starts at the slice's begin)
+  slices[8 * i + 2] = ctr[4]; slices[8 * i + 3] = f0;    // reach-box queue
+  slices[8 * i + 4] = ctr[3]; slices[8 * i + 5] = w0;    // big-tile queue
 }
 
-// Host-fed round (the host-buffer entry points): the states arrive in slices over PCIe. Three streams:
-//   copy_stream   H2D of slice i+1
-//   s             classify of slice i as soon as its copy has landed (appends to the two box queues)
-//   box_stream    box stages of slice i over exactly the queue entries its classify appended (own claim counters), then
-//                 the grouping stage once per round
-// so the copy, the classify stage and the box stages of three consecutive slices overlap; s waits for box_stream at the end.
+// Host-fed round (the host-buffer entry points): the states arrive in slices over PCIe. Four streams:
+//   copy_stream    H2D of slice i+1
+//   s              classify of slice i as soon as its copy has landed (appends to the three box queues)
+//   box_stream     one-warp-per-box kernels of slice i (reach-box queue, then big-tile queue) over exactly the queue entries
+//                  its classify appended (per-slice claim counters, close_slice_kernel), then the grouping stage once per round
+//   group_stream   the 8-lane-group kernel of slice i, beside them
+// so the copy, the classify stage and the box stages of consecutive slices overlap; s waits for box_stream at the end.
 int run_round_piped(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed, size_t base, size_t end, size_t slice,
                     uint32_t& launches, size_t& ev_i) {
   CU_TRY(h, cudaMemsetAsync(h->d_ctr, 0, 16 * sizeof(uint32_t), s));
@@ -456,10 +463,12 @@ int run_round_piped(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* fee
   size_t cut[kMaxSlices + 1];
   int ncut = 0;
   cut[0] = base;
-  if (feed->schedule[0] > 0.0f && end - base >= (1u << 18) && !h->slice_override) {
+  const float* sched = feed->schedule;
+  if (h->sched_override[0] > 0.0f) sched = h->sched_override;          // ARTP_SLICE_SCHEDULE (experiments)
+  if (sched[0] > 0.0f && end - base >= (1u << 18) && !h->slice_override) {
     double acc = 0.0;
-    for (int i = 0; i < 8 && feed->schedule[i] > 0.0f; ++i) {
-      acc += feed->schedule[i];
+    for (int i = 0; i < 8 && sched[i] > 0.0f; ++i) {
+      acc += sched[i];
       size_t c = base + (size_t)((double)(end - base) * acc);
       c = std::min(end, (c + 127) & ~(size_t)127);
       if (c > cut[ncut]) cut[++ncut] = c;
@@ -468,6 +477,8 @@ int run_round_piped(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* fee
   } else {
     for (size_t lo = base; lo < end; lo += slice) cut[++ncut] = std::min(end, lo + slice);
   }
+  const auto cpu_t0 = std::chrono::steady_clock::now();
+  double cpu_ms[kMaxSlices + 2] = {0};
   if (h->trace) { cudaEventRecord(h->tr_ev[0], s); cudaStreamWaitEvent(h->copy_stream, h->tr_ev[0], 0); cudaEventRecord(h->tr_ev[1], h->copy_stream); }
   for (int si = 0; si < ncut; ++si) {
     const size_t lo = cut[si], hi = cut[si + 1];
@@ -476,6 +487,7 @@ int run_round_piped(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* fee
     cudaEvent_t ev = h->copy_ev[ev_i++ % kCopyEvents];
     CU_TRY(h, cudaEventRecord(ev, h->copy_stream));
     CU_TRY(h, cudaStreamWaitEvent(s, ev, 0));
+    if (h->trace && si < 8) { cudaEventRecord(h->tr_slice[si][0], h->copy_stream); cudaEventRecord(h->tr_slice[si][1], s); }
     w.item_base = (uint32_t)lo;
     w.n_items = (uint32_t)hi;
     artp::classify_items_kernel<<<(unsigned)((hi - lo + 127) / 128), 128, 0, s>>>(
@@ -483,39 +495,43 @@ int run_round_piped(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* fee
         (h->mode == 1 ? 1 : 0) | h->k0_flags);
     close_slice_kernel<<<1, 1, 0, s>>>(h->d_ctr, h->d_slices, si);
     CU_TRY(h, cudaGetLastError());
+    if (h->trace && si < 8) cudaEventRecord(h->tr_slice[si][2], s);
     CU_TRY(h, cudaEventRecord(h->slice_ev[si], s));
     CU_TRY(h, cudaStreamWaitEvent(h->box_stream, h->slice_ev[si], 0));
     const size_t nb = hi - lo;
+    if (h->group_grid) {
+      CU_TRY(h, cudaStreamWaitEvent(h->group_stream, h->slice_ev[si], 0));
+      const unsigned grid_g = (unsigned)std::min<size_t>((size_t)h->group_grid, (nb + 7) / 8);
+      artp::reach_groups_kernel<<<grid_g, artp::kMaxTileWarps * 32, h->group_smem, h->group_stream>>>(
+          h->chk, h->tile_map[1][1], h->tile_cfg[1], w, h->d_recs_g, h->d_slices + 8 * si, h->d_slices + 8 * si + 1);
+      launches += 1;
+    }
     if (h->chk.reach_tw) {
       const int wpc = h->tile_warps[1];
       const unsigned grid_f = (unsigned)std::min<size_t>((size_t)h->tile_grid[1], (4 * nb + wpc - 1) / wpc);
       artp::box_tiles_warp_kernel<<<grid_f, wpc * 32, h->tile_smem[1], h->box_stream>>>(
-          h->chk, h->tile_map[1][1], h->tile_map[1][1], h->tile_cfg[1], w, h->d_recs_f, h->d_slices + 4 * si + 2, h->d_slices + 4 * si + 3,
+          h->chk, h->tile_map[1][1], h->tile_map[1][1], h->tile_cfg[1], w, h->d_recs_f, h->d_slices + 8 * si + 2, h->d_slices + 8 * si + 3,
           h->d_ctr + 1, h->d_defer, artp::kDeferReachBit, h->mode == 1);
       launches += 1;
     }
-    if (h->group_grid) {
-      const unsigned grid_g = (unsigned)std::min<size_t>((size_t)h->group_grid, (nb + 7) / 8);
-      artp::reach_groups_kernel<<<grid_g, artp::kMaxTileWarps * 32, h->group_smem, h->box_stream>>>(
-          h->chk, h->tile_map[1][1], h->tile_cfg[1], w, h->d_recs_g, h->d_slices + 4 * si, h->d_slices + 4 * si + 1);
+    {
+      // the big-tile queue (torso boxes: few) of this slice, behind its reach-box queue
+      const int wpc = h->tile_warps[0];
+      const unsigned grid_w = (unsigned)std::min<size_t>((size_t)h->tile_grid[0], (nb + wpc - 1) / wpc);
+      artp::box_tiles_warp_kernel<<<grid_w, wpc * 32, h->tile_smem[0], h->box_stream>>>(
+          h->chk, h->tile_map[0][0], h->tile_map[0][1], h->tile_cfg[0], w, h->d_recs, h->d_slices + 8 * si + 4, h->d_slices + 8 * si + 5,
+          h->d_ctr + 1, h->d_defer, 0u, h->mode == 1);
       launches += 1;
     }
     CU_TRY(h, cudaGetLastError());
     launches += 2;
+    if (h->trace && si < 8) cudaEventRecord(h->tr_slice[si][3], h->box_stream);
+    if (h->trace) cpu_ms[si] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - cpu_t0).count();
   }
-  {
-    // the big-tile queue (torso boxes: few) is drained ONCE per round, on s, concurrently with the reach-box queue of the
-    // last slices on box_stream; claim counter ctr[0] starts at 0 (memset above), count = ctr[3]
-    const int wpc = h->tile_warps[0];
-    const unsigned grid_w = (unsigned)std::min<size_t>((size_t)h->tile_grid[0], (end - base + wpc - 1) / wpc);
-    artp::box_tiles_warp_kernel<<<grid_w, wpc * 32, h->tile_smem[0], s>>>(h->chk, h->tile_map[0][0], h->tile_map[0][1], h->tile_cfg[0], w,
-                                                                           h->d_recs, h->d_ctr + 3, h->d_ctr, h->d_ctr + 1, h->d_defer, 0u,
-                                                                           h->mode == 1);
-    CU_TRY(h, cudaGetLastError());
-    launches += 1;
-    // the grouping stage (box_stream) needs the deferrals of both queues
-    CU_TRY(h, cudaEventRecord(h->slice_ev[kMaxSlices - 1], s));
-    CU_TRY(h, cudaStreamWaitEvent(h->box_stream, h->slice_ev[kMaxSlices - 1], 0));
+  if (h->group_grid) {
+    // the grouping stage (box_stream) runs last: the group kernels must not clear a verdict after it has been copied out
+    CU_TRY(h, cudaEventRecord(h->group_ev, h->group_stream));
+    CU_TRY(h, cudaStreamWaitEvent(h->box_stream, h->group_ev, 0));
   }
   if (h->trace) { cudaEventRecord(h->tr_ev[2], h->copy_stream); cudaEventRecord(h->tr_ev[3], s); cudaEventRecord(h->tr_ev[4], h->box_stream); }
   w.item_base = (uint32_t)base;
@@ -532,8 +548,16 @@ int run_round_piped(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* fee
     cudaEventSynchronize(h->tr_ev[5]);
     float t[5];
     for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], h->tr_ev[0], h->tr_ev[i + 1]);
-    std::fprintf(stderr, "[artp trace] copies start %.3f end %.3f | classify end %.3f | box stages end %.3f | grouping end %.3f ms\n", t[0], t[1],
-                 t[2], t[3], t[4]);
+    std::fprintf(stderr, "[artp trace] copies start %.3f end %.3f | classify end %.3f | box stages end %.3f | grouping end %.3f ms | cpu submit",
+                 t[0], t[1], t[2], t[3], t[4]);
+    for (int i = 0; i < ncut; ++i) std::fprintf(stderr, " %.3f", cpu_ms[i]);
+    std::fprintf(stderr, "\n[artp trace]   per slice (copy landed, classify start, classify done, box done):");
+    for (int i = 0; i < ncut && i < 8; ++i) {
+      float u[4];
+      for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&u[j], h->tr_ev[0], h->tr_slice[i][j]);
+      std::fprintf(stderr, "  [%.3f %.3f %.3f %.3f]", u[0], u[1], u[2], u[3]);
+    }
+    std::fprintf(stderr, "\n");
   }
   return ARTP_OK;
 }
@@ -679,10 +703,12 @@ int artp_create(const artp_params* params, artp_handle** out) {
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&h->box_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&h->group_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaEventCreateWithFlags(&h->group_ev, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   for (int i = 0; i < kMaxSlices; ++i)
     if ((e = cudaEventCreateWithFlags(&h->slice_ev[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreateWithFlags(&h->box_ev, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
-  if ((e = cudaMalloc(&h->d_slices, kMaxSlices * 4 * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc", e);
+  if ((e = cudaMalloc(&h->d_slices, kMaxSlices * 8 * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc", e);
   for (int i = 0; i < kCopyEvents; ++i)
     if ((e = cudaEventCreateWithFlags(&h->copy_ev[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaMalloc(&h->d_ctr, 16 * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc", e);
@@ -692,10 +718,24 @@ int artp_create(const artp_params* params, artp_handle** out) {
   *h->h_err = 0;
   if ((e = cudaHostGetDevicePointer((void**)&h->d_err, h->h_err, 0)) != cudaSuccess) return fail("cudaHostGetDevicePointer", e);
   if (const char* kf = std::getenv("ARTP_K0_FLAGS")) h->k0_flags = std::atoi(kf) & 2;
-  if (std::getenv("ARTP_TRACE")) { h->trace = 1; for (auto& te : h->tr_ev) cudaEventCreate(&te); }
+  if (std::getenv("ARTP_TRACE")) {
+    h->trace = 1;
+    for (auto& te : h->tr_ev) cudaEventCreate(&te);
+    for (auto& ts : h->tr_slice) for (auto& te : ts) cudaEventCreate(&te);
+  }
   if (const char* sl = std::getenv("ARTP_SLICE_ITEMS")) {
     const long v = std::atol(sl);
     if (v >= 1024) { h->slice_items_f64 = (size_t)v; h->slice_items_f32 = (size_t)v; h->slice_override = true; }
+  }
+  if (const char* sc = std::getenv("ARTP_SLICE_SCHEDULE")) {
+    int i = 0;
+    for (const char* p = sc; *p && i < 8;) {
+      char* q = nullptr;
+      const float v = std::strtof(p, &q);
+      if (q == p) break;
+      if (v > 0.0f) h->sched_override[i++] = v;
+      p = (*q == ',') ? q + 1 : q;
+    }
   }
   h->cnn = artp_cnn::create(h->device, h->sm_count);
   // checker constants (float casts as the reference's ctor/Pose3FromXYZ arguments make them)
@@ -719,6 +759,8 @@ void artp_destroy(artp_handle* hh) {
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   for (int i = 0; i < kCopyEvents; ++i) if (h->copy_ev[i]) cudaEventDestroy(h->copy_ev[i]);
   if (h->box_stream) { cudaStreamSynchronize(h->box_stream); cudaStreamDestroy(h->box_stream); }
+  if (h->group_stream) { cudaStreamSynchronize(h->group_stream); cudaStreamDestroy(h->group_stream); }
+  if (h->group_ev) cudaEventDestroy(h->group_ev);
   for (int i = 0; i < kMaxSlices; ++i) if (h->slice_ev[i]) cudaEventDestroy(h->slice_ev[i]);
   if (h->box_ev) cudaEventDestroy(h->box_ev);
   cudaFree(h->d_slices);
@@ -1141,7 +1183,7 @@ int artp_check_poses_f32(artp_handle* hh, const float* states, size_t n, uint8_t
   artp::Work w;
   w.s1 = nullptr; w.s2 = nullptr; w.s2f = d_states; w.valid = d_valid; w.item_base = 0; w.n_items = (uint32_t)n;
   w.steps = 0; w.edge_mode = 0;
-  HostFeed feed{(const char*)states, (char*)d_states, 7 * sizeof(float), h->slice_items_f32, {0.10f, 0.30f, 0.60f, 0.f, 0.f, 0.f, 0.f, 0.f}};
+  HostFeed feed{(const char*)states, (char*)d_states, 7 * sizeof(float), h->slice_items_f32, {0.08f, 0.17f, 0.25f, 0.25f, 0.25f, 0.f, 0.f, 0.f}};
   rc = chain_begin(h, 0, h->stream);
   if (rc) return rc;
   rc = run_items(h, w, h->stream, &feed);

@@ -88,12 +88,31 @@ box_tiles_warp_kernel(const Checker c, const __grid_constant__ CUtensorMap map0,
       tma_tile_2d(slots + (size_t)slot * tc.stride, (fl & 7u) ? &map1 : &map0, &bars[wid][slot], (x0 & ~3) - tc.x_off, z0);
     }
   };
+  // Guided claims: a share of what is left (1 .. kTileChunk records), so that a short queue spreads over all warps
+  // instead of keeping a few of them busy with kTileChunk boxes each (one box is ~5 us of dependent latency); the next
+  // claim is issued before the current one is worked on, so its round trip hides behind the boxes.
+  const uint32_t nwarps2 = 2u * gridDim.x * (blockDim.x >> 5);
+  uint32_t next_r0 = 0, next_n = 0;     // lane 0's
+  // (a long queue keeps fixed claims: measured, the guided sizes cost this kernel 15-20 % there -- a claim restarts the
+  //  tile pipeline -- while they halve its time on short queues)
+  const uint32_t first_seen = *(volatile const uint32_t*)work_counter;   // ~ where this launch's share of the queue begins
+  const bool fixed_claims = total - min(first_seen, total) >= (nwarps2 >> 2) * (uint32_t)kTileChunk;
+  auto claim = [&]() {
+    if (lane == 0) {
+      next_n = (uint32_t)kTileChunk;
+      if (!fixed_claims) {
+        const uint32_t cur = *(volatile const uint32_t*)work_counter;   // fresh: a stale value would hand out big claims at the end
+        next_n = cur < total ? min(max((total - cur) / nwarps2, 1u), (uint32_t)kTileChunk) : 1u;
+      }
+      next_r0 = atomicAdd(work_counter, next_n);
+    }
+  };
+  claim();
   for (;;) {
-    uint32_t r0 = 0;
-    if (lane == 0) r0 = atomicAdd(work_counter, (uint32_t)kTileChunk);
-    r0 = __shfl_sync(kFull, r0, 0);
+    const uint32_t r0 = __shfl_sync(kFull, next_r0, 0), nclaim = __shfl_sync(kFull, next_n, 0);
     if (r0 >= total) break;
-    const uint32_t r1 = min(r0 + (uint32_t)kTileChunk, total);
+    claim();
+    const uint32_t r1 = min(r0 + nclaim, total);
     if (force_defer) {
       if (lane == 0) for (uint32_t ri = r0; ri < r1; ++ri) defer_list[atomicAdd(defer_count, 1u)] = ri | queue_bit;
       continue;
@@ -182,12 +201,22 @@ reach_groups_kernel(const Checker c, const __grid_constant__ CUtensorMap map1, c
       if (lane == 0) tma_tile_2d(slots + (size_t)(slot * 4 + q) * tc.stride, &map1, &bars[wid][slot], (sx & ~3) - tc.x_off, sz);
     }
   };
+  // guided, software-pipelined claims (1 .. kGroupRounds rounds of four records), see box_tiles_warp_kernel
+  const uint32_t nwarps8 = 8u * gridDim.x * (blockDim.x >> 5);
+  uint32_t next_r0 = 0, next_n = 0;     // lane 0's
+  auto claim = [&]() {
+    if (lane == 0) {
+      const uint32_t cur = *(volatile const uint32_t*)work_counter;
+      next_n = 4u * (cur < total ? min(max((total - cur) / nwarps8, 1u), (uint32_t)kGroupRounds) : 1u);
+      next_r0 = atomicAdd(work_counter, next_n);
+    }
+  };
+  claim();
   for (;;) {
-    uint32_t r0 = 0;
-    if (lane == 0) r0 = atomicAdd(work_counter, 4u * kGroupRounds);
-    r0 = __shfl_sync(kFull, r0, 0);
+    const uint32_t r0 = __shfl_sync(kFull, next_r0, 0), nclaim = __shfl_sync(kFull, next_n, 0);
     if (r0 >= total) break;
-    const int nrounds = (int)((min(r0 + 4u * kGroupRounds, total) - r0 + 3u) / 4u);
+    claim();
+    const int nrounds = (int)((min(r0 + nclaim, total) - r0 + 3u) / 4u);
     __syncwarp();                          // every lane is done with both slots
     prefetch(r0, 0);
 #pragma unroll 1

@@ -449,6 +449,8 @@ def main():
 
     # ---- timed region: end to end through the host-buffer C-ABI call ---------------------------
     e2e_steps = args.steps
+    chk.setTiming(False)     # per-stage event timing makes the host-fed call run its slices back to back (no copy/compute overlap)
+    step_e2e(); step_e2e_f64()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -463,7 +465,37 @@ def main():
         step_e2e_f64()
     torch.cuda.synchronize()
     e2e64_s = time.perf_counter() - t0
+    e2e_mask = hb_valid.array.copy()
     clocks = sampler.stop() if rank == 0 else None
+    # Two caller threads, each with its own handle and pinned buffers (what a multi-threaded planner does): the copy of one
+    # call overlaps the kernels of the other. Reported beside the single-caller number, never instead of it.
+    two_callers = None
+    if world == 1:
+        try:
+            import threading
+            chk2 = apb.StateValidityChecker(synth.PARAMS_YAML, device=local)
+            chk2.setMap(m); chk2.updateHeightField()
+            hb2_p, hb2_v = capi.HostBuffer((n, 7), np.float32), capi.HostBuffer((n,), np.uint8)
+            hb2_p.array[:] = hb_poses32.array
+            jobs = [(chk, hb_poses32.array.ctypes.data, hb_valid.array.ctypes.data), (chk2, hb2_p.array.ctypes.data, hb2_v.array.ctypes.data)]
+            for c_, p_, v_ in jobs:
+                c_.isValidHostPtr(p_, n, v_, f32=True)
+
+            def caller(c_, p_, v_):
+                for _ in range(e2e_steps):
+                    c_.isValidHostPtr(p_, n, v_, f32=True)
+            th = [threading.Thread(target=caller, args=j) for j in jobs]
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for t_ in th: t_.start()
+            for t_ in th: t_.join()
+            torch.cuda.synchronize(); dt2 = time.perf_counter() - t0
+            two_callers = {"value": 2 * n * e2e_steps / dt2, "unit": "poses/s", "callers": 2,
+                           "masks_equal": bool(np.array_equal(hb2_v.array, e2e_mask) and np.array_equal(hb_valid.array, e2e_mask)),
+                           "note": "two threads, one handle + pinned buffer pair each, float32 states; same bytes per call as e2e"}
+            del chk2
+        except Exception as ex:
+            two_callers = {"error": repr(ex)}
+    chk.setTiming(True)
 
     # ---- secondary workloads of the same hot path (BASELINE configs[2] and [3]); N = 1 only, short -------------
     secondary = None
@@ -637,6 +669,7 @@ def main():
         n1 = 20_000
         t0 = time.perf_counter(); v1 = o.check_poses(poses[:n1]); t_single = time.perf_counter() - t0
         got = d_valid.cpu().numpy()
+        e2e_mask_ok = bool(np.array_equal(e2e_mask, got))   # the host-fed (sliced) path returns the device path's mask
         if world == 1:   # the timed all-threads CPU baseline belongs to the N = 1 line only
             cores = best_thread_count(o, poses, os.cpu_count() or 1, m.rows * m.cols > 4_000_000)
             n_mt = 400_000
@@ -681,9 +714,9 @@ def main():
                        "map_seed": MAP_SEED, "pose_seed": POSE_SEED, "l2": "flushed between timed steps (256 MiB write)",
                        "step": "isValid of the batch (verdict bytes) + bit-packed verdicts + the ordered 32-bit index list of the valid samples",
                        "parallelism": f"pose shards x{world}, replicated 1000x1000 map" + (", one NCCL all-gather of bit-packed masks per step, pipelined: the exchange of step i runs on a side stream inside the timed window of step i+1 (+ one closing window); see exchange.unpipelined_value and c5 (spatial shards)" if world > 1 else "")},
-            "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": n,
+            "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": n, "mask_equals_device_path": e2e_mask_ok,
                     "ms_per_step": e2e_ms / e2e_steps, "api": "artp_check_poses_f32 (states cast to float by the adapter while it gathers them, exact), buffers from artp_host_alloc",
-                    "f64_api_value": world * n * e2e_steps / e2e64_s, "f64_api_h2d_bytes_per_step": n * 56,
+                    "f64_api_value": world * n * e2e_steps / e2e64_s, "f64_api_h2d_bytes_per_step": n * 56, "two_callers": two_callers,
                     "note": "PCIe Gen5 x16 moves 53-55 GB/s here (profiles/pcie_probe.cu): 28 MB = 0.52 ms, 56 MB = 1.04 ms, so the double entry point is copy-bound at <= 0.96e9 poses/s"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "reach_groups_kernel + box_tiles_warp_kernel (the two reach-box queues)", "achieved": achieved, "peak": peak,

@@ -367,3 +367,34 @@ def test_u32_compaction_and_fused_bits(maps, checkers):
     assert torch.equal(bits.cpu(), sharding.pack_bits_reference(v.cpu()))
     want = torch.nonzero(v).reshape(-1).to(torch.int32) + 5
     assert int(cnt.item()) == want.numel() and torch.equal(idx[: want.numel()], want)
+
+
+@pytest.mark.parametrize("mk", ["fbm_rough", "fbm_gentle", "fixture", "terraces"])
+def test_both_reach_box_kernels_agree_with_the_oracle(maps, port_lib, mk):
+    """Reach boxes over all-finite, merge-free zones take the 8-lane-group kernel (four boxes per warp), the others the
+    one-warp-per-box kernel; ARTP_NO_GROUPS (read at artp_set_map) sends every reach box to the latter. Same masks,
+    equal to the oracle, and the group kernel must actually have run in the default configuration."""
+    import os
+    import art_planner_b200 as ap
+    m = maps(mk)
+    poses = synth.make_terrain_poses(m, 30000, seed=77)
+    o = port_lib.Oracle(cases.PARAMS["yaml"], "port")
+    o.set_map(m)
+    ref = o.check_poses(poses)
+    masks, grouped = [], []
+    for no_groups in (False, True):
+        if no_groups:
+            os.environ["ARTP_NO_GROUPS"] = "1"
+        try:
+            chk = ap.StateValidityChecker(cases.PARAMS["yaml"], device=0)
+            set_map(chk, m)
+            masks.append(chk.isValidBatch(poses))
+            grouped.append(chk.stats()["last_reach_plane_stage"])
+        finally:
+            os.environ.pop("ARTP_NO_GROUPS", None)
+    assert grouped[1] == 0
+    if mk.startswith("fbm"):                  # flat / piecewise-constant terrain has mergeable planes nearly everywhere
+        assert grouped[0] > 0, grouped
+    for k in (0, 1):
+        bad = np.nonzero(masks[k] != ref)[0]
+        assert bad.size == 0, f"no_groups={k}: {bad.size} mismatches, first {bad[:8]}, grouped={grouped}"
