@@ -598,7 +598,8 @@ conv15_two_phase_kernel(const __grid_constant__ CUtensorMap map_ahi, const __gri
 }
 
 // First layer (Cin = 1, no activation after its BN) on CUDA cores, reading the map layer directly and writing the
-// fp16 hi/lo NHWC-64 input of the second layer.
+// fp16 hi/lo NHWC-64 input of the second layer. One thread per (pixel, group of 8 output channels): the eight threads of
+// a pixel write its two 128-byte rows as sixteen 16-byte stores; channels 24..63 are zero.
 __global__ void __launch_bounds__(256) conv1_split_kernel(const float* __restrict__ layer, int H, int W, int pitch,
                                                           const float* __restrict__ wf /*[9][1][24]*/, const float* __restrict__ bias,
                                                           __half* __restrict__ hi, __half* __restrict__ lo) {
@@ -606,59 +607,74 @@ __global__ void __launch_bounds__(256) conv1_split_kernel(const float* __restric
   for (int i = threadIdx.x; i < 9 * 24 + 24; i += blockDim.x) sw[i] = i < 216 ? wf[i] : bias[i - 216];
   __syncthreads();
   const int OH = H - 2, OW = W - 2;
-  const size_t total = (size_t)OH * OW;
-  // consecutive threads take consecutive image rows (oy): the map layer is contiguous along that axis
-  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
+  const size_t total = (size_t)OH * OW * 8;
+  // consecutive pixels take consecutive image rows (oy): the map layer is contiguous along that axis
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v4 = (int)(i & 7);
+    const size_t p = i >> 3;
     const int oy = (int)(p % OH), ox = (int)(p / OH);
-    float in[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) in[t] = __ldg(layer + (size_t)(ox + t % 3) * pitch + (H - 1 - (oy + t / 3)));   // E[r][c]
     const size_t pix = (size_t)oy * OW + ox;
-    uint4* ph = reinterpret_cast<uint4*>(hi + pix * 64);
-    uint4* pl = reinterpret_cast<uint4*>(lo + pix * 64);
+    __half2 hh[4], ll[4];
+    if (v4 < 3) {
+      float in[9];
 #pragma unroll
-    for (int v4 = 0; v4 < 8; ++v4) {          // 8 channels (one 16-byte store) at a time; channels 24..63 are zero
-      __half2 hh[4], ll[4];
+      for (int t = 0; t < 9; ++t) in[t] = __ldg(layer + (size_t)(ox + t % 3) * pitch + (H - 1 - (oy + t / 3)));   // E[r][c]
 #pragma unroll
       for (int e2 = 0; e2 < 4; ++e2) {
-        float f[2] = {0.0f, 0.0f};
-        if (v4 < 3) {
+        float f[2];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int n = 8 * v4 + 2 * e2 + e;
-            float a = sw[216 + n];
+        for (int e = 0; e < 2; ++e) {
+          const int n = 8 * v4 + 2 * e2 + e;
+          float a = sw[216 + n];
 #pragma unroll
-            for (int t = 0; t < 9; ++t) a = fmaf(in[t], sw[t * 24 + n], a);
-            f[e] = a;
-          }
+          for (int t = 0; t < 9; ++t) a = fmaf(in[t], sw[t * 24 + n], a);
+          f[e] = a;
         }
         const __half h0 = __float2half_rn(f[0]), h1 = __float2half_rn(f[1]);
         hh[e2] = __halves2half2(h0, h1);
         ll[e2] = __halves2half2(__float2half_rn(f[0] - __half2float(h0)), __float2half_rn(f[1] - __half2float(h1)));
       }
-      ph[v4] = *reinterpret_cast<uint4*>(hh);
-      pl[v4] = *reinterpret_cast<uint4*>(ll);
+    } else {
+#pragma unroll
+      for (int e2 = 0; e2 < 4; ++e2) { hh[e2] = __float2half2_rn(0.0f); ll[e2] = __float2half2_rn(0.0f); }
     }
+    reinterpret_cast<uint4*>(hi + pix * 64)[v4] = *reinterpret_cast<uint4*>(hh);
+    reinterpret_cast<uint4*>(lo + pix * 64)[v4] = *reinterpret_cast<uint4*>(ll);
   }
 }
 
-// max pooling (K x K, stride S) of an fp32 NHWC [H][W][C] activation into fp16 hi/lo NHWC-64.
+// max pooling (K x K, stride S) of an fp32 NHWC [H][W][C] activation (C a multiple of 8) into fp16 hi/lo NHWC-64.
+// One thread per (pixel, 8 channels): two 16-byte loads per tap, one 16-byte store per output array.
 __global__ void maxpool_split_kernel(const float* __restrict__ in, int H, int W, int C, int K, int S, __half* __restrict__ hi,
                                      __half* __restrict__ lo, int OH, int OW) {
-  const size_t total = (size_t)OH * OW * 64;
+  const size_t total = (size_t)OH * OW * 8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i & 63);
-    const size_t p = i >> 6;
+    const int v8 = (int)(i & 7);
+    const size_t p = i >> 3;
     const int ox = (int)(p % OW), oy = (int)(p / OW);
-    float m = 0.0f;
-    if (c < C) {
-      m = -INFINITY;
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = 0.0f;
+    if (8 * v8 < C) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
       for (int dy = 0; dy < K; ++dy)
-        for (int dx = 0; dx < K; ++dx) m = fmaxf(m, in[((size_t)(oy * S + dy) * W + ox * S + dx) * C + c]);
+        for (int dx = 0; dx < K; ++dx) {
+          const float4* q = reinterpret_cast<const float4*>(in + ((size_t)(oy * S + dy) * W + ox * S + dx) * C + 8 * v8);
+          const float4 a = __ldg(q), b = __ldg(q + 1);
+          m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], a.z); m[3] = fmaxf(m[3], a.w);
+          m[4] = fmaxf(m[4], b.x); m[5] = fmaxf(m[5], b.y); m[6] = fmaxf(m[6], b.z); m[7] = fmaxf(m[7], b.w);
+        }
     }
-    const __half h = __float2half_rn(m);
-    hi[i] = h;
-    lo[i] = __float2half_rn(m - __half2float(h));
+    __half2 hh[4], ll[4];
+#pragma unroll
+    for (int e2 = 0; e2 < 4; ++e2) {
+      const __half h0 = __float2half_rn(m[2 * e2]), h1 = __float2half_rn(m[2 * e2 + 1]);
+      hh[e2] = __halves2half2(h0, h1);
+      ll[e2] = __halves2half2(__float2half_rn(m[2 * e2] - __half2float(h0)), __float2half_rn(m[2 * e2 + 1] - __half2float(h1)));
+    }
+    reinterpret_cast<uint4*>(hi + p * 64)[v8] = *reinterpret_cast<uint4*>(hh);
+    reinterpret_cast<uint4*>(lo + p * 64)[v8] = *reinterpret_cast<uint4*>(ll);
   }
 }
 

@@ -107,11 +107,14 @@ box_tiles_warp_kernel(const Checker c, const __grid_constant__ CUtensorMap map0,
       next_r0 = atomicAdd(work_counter, next_n);
     }
   };
-  claim();
+  // guided claims are issued one ahead (their round trip hides behind the boxes; the sizes account for the chunk in hand),
+  // fixed ones when needed (a warp holding two 8-box chunks would unbalance a queue of a few boxes per warp)
+  if (!fixed_claims) claim();
   for (;;) {
+    if (fixed_claims) claim();
     const uint32_t r0 = __shfl_sync(kFull, next_r0, 0), nclaim = __shfl_sync(kFull, next_n, 0);
     if (r0 >= total) break;
-    claim();
+    if (!fixed_claims) claim();
     const uint32_t r1 = min(r0 + nclaim, total);
     if (force_defer) {
       if (lane == 0) for (uint32_t ri = r0; ri < r1; ++ri) defer_list[atomicAdd(defer_count, 1u)] = ri | queue_bit;
@@ -173,6 +176,7 @@ reach_groups_kernel(const Checker c, const __grid_constant__ CUtensorMap map1, c
   extern __shared__ __align__(128) unsigned char tile_smem[];
   __shared__ uint64_t bars[kMaxTileWarps][2];
   __shared__ uint16_t tasks_all[kMaxTileWarps][4][kGroupTasks];
+  __shared__ __align__(16) float ctx_all[kMaxTileWarps][4][16];   // per box of the round: R1[9], P[3], minB, x0, z0 (task stage)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 3, gl = lane & 7;
   const Field& f = c.f[1];
   unsigned char* slots = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tile_smem) + 127) & ~(uintptr_t)127) +
@@ -247,6 +251,13 @@ reach_groups_kernel(const Checker c, const __grid_constant__ CUtensorMap map1, c
       BoxCtx b;
       rec_to_ctx(c, r, b);                 // an all-zero record for idle groups: every field defined
       if (gdone) { b.x0 = b.z0 = 0; b.x1 = b.z1 = 1; }
+      if (gl == 0) {          // the box as the pooled task stage reads it (any lane may test any group's task)
+        float* cx = ctx_all[wid][g];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) cx[i] = b.R1[i];
+        cx[9] = b.P[0]; cx[10] = b.P[1]; cx[11] = b.P[2]; cx[12] = b.minB;
+        cx[13] = __int_as_float(b.x0); cx[14] = __int_as_float(b.z0);
+      }
       const float* tile = reinterpret_cast<const float*>(slots + (size_t)(slot * 4 + g) * tc.stride) + (b.x0 & 3);
       const int nX = b.x1 - b.x0 + 1, nZ = b.z1 - b.z0 + 1, nV = nX * nZ, nCZ = nZ - 1;
       const float top = b.maxB + (1e-4f + 4e-6f * fabsf(b.maxB));
@@ -312,33 +323,46 @@ reach_groups_kernel(const Checker c, const __grid_constant__ CUtensorMap map1, c
         nt = 2 * base;      // <= 64
       }
       __syncwarp();
-      // ... and test them, lane = task: the triangle's own plane, its contact points, point-in-triangle
+      // ... and test them, lane = task, the four lists pooled: a round's ~40 tasks fill the warp once or twice, where four
+      // separate 8-lane loops ran as long as the longest list (measured: 12 of 32 lanes). The task's box comes from ctx_all.
       {
-        int maxNT = nt;
-        maxNT = __reduce_max_sync(kFull, maxNT);
-        bool hit_own = false;
+        const int n0 = __shfl_sync(kFull, nt, 0), n1 = __shfl_sync(kFull, nt, 8), n2 = __shfl_sync(kFull, nt, 16), n3 = __shfl_sync(kFull, nt, 24);
+        const int o1 = n0, o2 = n0 + n1, o3 = o2 + n2, NT = o3 + n3;
+        unsigned hit_groups = 0u;
 #pragma unroll 1
-        for (int q0 = 0; q0 < maxNT; q0 += 8) {
-          const int q = q0 + gl;
-          if (q < nt) {
-            const int tk = tasks[q];
+        for (int j0 = 0; j0 < NT; j0 += 32) {
+          const int j = j0 + lane;
+          if (j < NT) {
+            const int gi = (j >= o1) + (j >= o2) + (j >= o3);
+            const int q = j - (gi == 0 ? 0 : gi == 1 ? o1 : gi == 2 ? o2 : o3);
+            const int tk = tasks_all[wid][gi][q];
+            const float4* cx = reinterpret_cast<const float4*>(ctx_all[wid][gi]);
+            const float4 c0 = cx[0], c1 = cx[1], c2 = cx[2], c3 = cx[3];
+            BoxCtx tb;
+            tb.R1[0] = c0.x; tb.R1[1] = c0.y; tb.R1[2] = c0.z; tb.R1[3] = c0.w; tb.R1[4] = c1.x; tb.R1[5] = c1.y; tb.R1[6] = c1.z;
+            tb.R1[7] = c1.w; tb.R1[8] = c2.x; tb.P[0] = c2.y; tb.P[1] = c2.z; tb.P[2] = c2.w; tb.minB = c3.x;
+            tb.side[0] = c.side[1][0]; tb.side[1] = c.side[1][1]; tb.side[2] = c.side[1][2];
+            const int tx0 = __float_as_int(c3.y), tz0 = __float_as_int(c3.z);
             const bool isUp = (tk & 1) == 0;
-            const int lx = tk >> 9, lz = (tk >> 1) & 0xff, ccx = b.x0 + lx, ccz = b.z0 + lz;
-            const float* p = tile + lz * tc.tw + lx;
+            const int lx = tk >> 9, lz = (tk >> 1) & 0xff, ccx = tx0 + lx, ccz = tz0 + lz;
+            const float* p = reinterpret_cast<const float*>(slots + (size_t)(slot * 4 + gi) * tc.stride) + (tx0 & 3) + lz * tc.tw + lx;
             const float hA = p[0], hB = p[1], hC = p[tc.tw], hD = p[tc.tw + 1];   // all finite (REC_ALLFINITE)
-            const bool keep = isUp ? (hA > b.minB || hB > b.minB || hC > b.minB) : (hB > b.minB || hC > b.minB || hD > b.minB);
+            const bool keep = isUp ? (hA > tb.minB || hB > tb.minB || hC > tb.minB) : (hB > tb.minB || hC > tb.minB || hD > tb.minB);
             if (keep) {
-              float pl[4], cx[4], cz[4];
+              float pl[4], cxs[4], czs[4];
               cell_plane(f, isUp, ccx, ccz, hA, hB, hC, hD, pl);
-              const int nc = box_plane(b, pl, 4, cx, cz);
+              const int nc = box_plane(tb, pl, 4, cxs, czs);
               const int tcx = isUp ? ccx : ccx + 1, tcz = isUp ? ccz : ccz + 1;
+              bool hit = false;
 #pragma unroll 1
-              for (int i = 0; i < nc; ++i) hit_own = hit_own || on_tri(f, isUp, tcx, tcz, cx[i], cz[i]);
+              for (int i = 0; i < nc; ++i) hit = hit || on_tri(f, isUp, tcx, tcz, cxs[i], czs[i]);
+              if (hit) hit_groups |= 1u << gi;
             }
           }
         }
         __syncwarp();
-        if ((__ballot_sync(kFull, hit_own) >> gshift) & 0xffu) ghit = true;
+        hit_groups = __reduce_or_sync(kFull, hit_groups);
+        if ((hit_groups >> g) & 1u) ghit = true;
       }
       // a reach box that does not touch: pose invalid
       if (gl == 0 && act && alive && !ghit) w.valid[r.item] = 0;

@@ -382,7 +382,7 @@ def main():
 
     # clocks / throttle reasons are sampled every 10 ms from before the warm-up to the end of the end-to-end region
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("ARTP_BENCH_NO_SAMPLER"):   # (experiment switch: how much the 10 ms nvidia-smi polling costs)
         sampler.start()
     warm_ev = torch.cuda.Event()
     for i in range(max(args.warmup, 3)):
