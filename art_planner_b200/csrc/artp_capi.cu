@@ -72,6 +72,8 @@ struct Handle {
   artp::TileCfg tile_cfg[2] = {};
   int tile_grid[2] = {0, 0}, tile_smem[2] = {0, 0}, tile_warps[2] = {8, 8};
   CUtensorMap tile_map[2][2];       // [cfg][layer]: 2-D tile maps over elevation / elevation_masked
+  int pipe_tune = 0;                // env ARTP_PIPE_TUNE (experiments on the host-fed pipeline)
+  int pipe_cap_g = 4, pipe_cap_f = 4;   // host-fed slices: grid caps of the group / one-warp-per-box reach kernels, in half SM counts (0: none)
   int k0_flags = 0;                 // tuning switch of the classify stage (env ARTP_K0_FLAGS: 2 = no vertex probes)
   bool slice_override = false;
   float sched_override[9] = {0};    // env ARTP_SLICE_SCHEDULE="0.1,0.3,0.6": slice fractions of the host-fed rounds
@@ -429,9 +431,10 @@ struct HostFeed {
   char* dev;               // device destination (same layout)
   size_t bytes_per_item;
   size_t slice_items;      // classic equal slices (small calls, env override)
-  // Slice schedule of a full round as fractions (0-terminated; empty: equal slices). Copy-bound feeds (doubles) start
-  // big and end small so that little compute is left once the last byte has landed; compute-bound feeds (floats) start
-  // small so that the kernels start early, and use few slices (every slice costs ~65 us of launch tails).
+  // Slice schedule of a full round as fractions (0-terminated; empty: equal slices): a small first slice so that the
+  // kernels start early, then equal ones. Every slice costs its kernels' latency floors (~0.1 ms of chain per slice,
+  // profiles/stage_vs_n.py), which is why five or six slices beat both fewer (long tail after the last byte) and more, and
+  // why shrinking the last slices below ~15 % buys nothing (measured with ARTP_SLICE_SCHEDULE / ARTP_TRACE).
   float schedule[8];
 };
 
@@ -501,14 +504,16 @@ int run_round_piped(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* fee
     const size_t nb = hi - lo;
     if (h->group_grid) {
       CU_TRY(h, cudaStreamWaitEvent(h->group_stream, h->slice_ev[si], 0));
-      const unsigned grid_g = (unsigned)std::min<size_t>((size_t)h->group_grid, (nb + 7) / 8);
+      unsigned grid_g = (unsigned)std::min<size_t>((size_t)h->group_grid, (nb + 7) / 8);
+      if (h->pipe_cap_g) grid_g = std::min<unsigned>(grid_g, (unsigned)(h->pipe_cap_g * h->sm_count / 2));
       artp::reach_groups_kernel<<<grid_g, artp::kMaxTileWarps * 32, h->group_smem, h->group_stream>>>(
           h->chk, h->tile_map[1][1], h->tile_cfg[1], w, h->d_recs_g, h->d_slices + 8 * si, h->d_slices + 8 * si + 1);
       launches += 1;
     }
     if (h->chk.reach_tw) {
       const int wpc = h->tile_warps[1];
-      const unsigned grid_f = (unsigned)std::min<size_t>((size_t)h->tile_grid[1], (4 * nb + wpc - 1) / wpc);
+      unsigned grid_f = (unsigned)std::min<size_t>((size_t)h->tile_grid[1], (4 * nb + wpc - 1) / wpc);
+      if (h->pipe_cap_f) grid_f = std::min<unsigned>(grid_f, (unsigned)(h->pipe_cap_f * h->sm_count / 2));
       artp::box_tiles_warp_kernel<<<grid_f, wpc * 32, h->tile_smem[1], h->box_stream>>>(
           h->chk, h->tile_map[1][1], h->tile_map[1][1], h->tile_cfg[1], w, h->d_recs_f, h->d_slices + 8 * si + 2, h->d_slices + 8 * si + 3,
           h->d_ctr + 1, h->d_defer, artp::kDeferReachBit, h->mode == 1);
@@ -700,10 +705,19 @@ int artp_create(const artp_params* params, artp_handle** out) {
   cudaFuncAttributes fa;
   if ((e = cudaFuncGetAttributes(&fa, artp::box_tiles_warp_kernel)) != cudaSuccess)
     return fail("no usable kernel image (built for sm_100a)", e);
-  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
-  if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
-  if ((e = cudaStreamCreateWithFlags(&h->box_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
-  if ((e = cudaStreamCreateWithFlags(&h->group_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  {
+    // experiment switch ARTP_PIPE_TUNE: bit 0 = the call's own stream (classify) gets the highest priority, the box-stage
+    // streams the lowest (measured: no effect); ARTP_PIPE_CAPS: see pipe_cap_g / pipe_cap_f
+    if (const char* pt = std::getenv("ARTP_PIPE_TUNE")) h->pipe_tune = std::atoi(pt);
+    if (const char* pc = std::getenv("ARTP_PIPE_CAPS")) std::sscanf(pc, "%d,%d", &h->pipe_cap_g, &h->pipe_cap_f);   // "g,f" in half SM counts
+    int lo_p = 0, hi_p = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+    const bool prio = (h->pipe_tune & 1) != 0;
+    if ((e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio ? hi_p : 0)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, prio ? hi_p : 0)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithPriority(&h->box_stream, cudaStreamNonBlocking, prio ? lo_p : 0)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithPriority(&h->group_stream, cudaStreamNonBlocking, prio ? lo_p : 0)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  }
   if ((e = cudaEventCreateWithFlags(&h->group_ev, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   for (int i = 0; i < kMaxSlices; ++i)
     if ((e = cudaEventCreateWithFlags(&h->slice_ev[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -1127,7 +1141,7 @@ int artp_check_poses(artp_handle* hh, const double* states, size_t n, uint8_t* v
   artp::Work w;
   w.s1 = nullptr; w.s2 = d_states; w.s2f = nullptr; w.valid = d_valid; w.item_base = 0; w.n_items = (uint32_t)n;
   w.steps = 0; w.edge_mode = 0;
-  HostFeed feed{(const char*)states, (char*)d_states, 7 * sizeof(double), h->slice_items_f64, {0.30f, 0.25f, 0.20f, 0.13f, 0.08f, 0.04f, 0.f, 0.f}};
+  HostFeed feed{(const char*)states, (char*)d_states, 7 * sizeof(double), h->slice_items_f64, {0.06f, 0.14f, 0.20f, 0.20f, 0.20f, 0.20f, 0.f, 0.f}};
   rc = chain_begin(h, 0, h->stream);
   if (rc) return rc;
   rc = run_items(h, w, h->stream, &feed);
