@@ -700,7 +700,7 @@ def main():
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("box_tiles_warp_kernel_reach_queue_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("reach_queues_dram_bytes_per_pass")   # group kernel + one-warp-per-box launch
         port_mix = exit_mix(port, poses[:20_000])
         out = {
             "metric": "pose-validity checks/s", "value": value, "unit": "poses/s", "n_gpus": world,
@@ -732,7 +732,7 @@ def main():
                          "note": "achieved = ALGORITHMIC bytes (the zone vertices the reference scans, SURVEY 8d) / sum of the stage "
                                  "durations; the range tables, plane tables and vertex probes answer most of those scans without reading "
                                  "them, so frac exceeds 1 while real DRAM traffic (traffic, ncu) stays near 1 % of peak: the pipeline is "
-                                 "instruction-issue bound (70 % of issue slots busy, 20 of 32 lanes; profiles/r02_v4_*)"},
+                                 "instruction-issue bound (group kernel: 68 % of issue slots busy, 20 of 32 lanes; profiles/r02_v6_*)"},
             "cpu_baseline": cpu_baseline,
             "clocks": clocks, "wall_s_timed_region": wall, "secondary": secondary, "exchange_ok": exchange_ok,
             "exchange": {"unpipelined_value": world * n * args.steps / (serial_ms * 1e-3), "unpipelined_ms_per_step": serial_ms / args.steps,
