@@ -299,28 +299,55 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView&
   // Regions: the active 8 x 8-vertex windows of a big all-finite zone (bit w of `act`), else the whole zone.
   const int nWx = (nX + 5) / 7, nWz = (nZ + 5) / 7;       // windows advance by 7 cells
   const bool windowed = allFinite && nV > 256 && f.kmax >= 3 && nX >= 8 && nZ >= 8 && nWx * nWz <= 64;
-  unsigned long long act = 1ull;
+  // ... and, for the vertex stage only, `actv`: the windows that can hold a vertex INSIDE the box. A window is the
+  // axis-aligned block [xs, xs+7] x [min h, max h] x [zs, zs+7] (level-3 table: max and min of its 64 heights); if
+  // that block lies entirely beyond one of the box's six faces -- its extent along the face normal, evaluated at the
+  // block's corners, stays outside +-side/2 by more than 2 mm (>> the rounding of vertex_inside's fp32 arithmetic at
+  // map coordinates of a few hundred metres) -- no vertex of it passes dGeomBoxPointDepth. For a tilted torso over rough
+  // ground this is far tighter than "window max > box bottom": the AABB bottom lies below most of the zone, the
+  // box's own bottom face does not. Kept triangles are a different question (h > minB): the plane stage keeps `act`.
+  unsigned long long act = 1ull, actv = 1ull;
   if (windowed) {
     const float2* __restrict__ T3 = f.T[3];
-    act = 0ull;
+    act = 0ull; actv = 0ull;
 #pragma unroll 1
     for (int w0 = 0; w0 < nWx * nWz; w0 += 32) {
       const int wi = w0 + lane;
-      bool a = false;
+      bool a = false, av = false;
       if (wi < nWx * nWz) {
         const int wz = wi / nWx, wx = wi - wz * nWx;
         const int xs = min(b.x0 + 7 * wx, b.x1 - 7), zs = min(b.z0 + 7 * wz, b.z1 - 7);
-        a = __ldg(T3 + (size_t)zs * f.pitch + xs).x > b.minB;
+        const float2 mm = __ldg(T3 + (size_t)zs * f.pitch + xs);
+        a = mm.x > b.minB;
+        if (a) {
+          const float xlo = xs * f.sW - b.P[0], xhi = (xs + 7) * f.sW - b.P[0];
+          const float zlo = zs * f.sD - b.P[2], zhi = (zs + 7) * f.sD - b.P[2];
+          const float ylo = mm.y - b.P[1], yhi = mm.x - b.P[1];
+          bool sep = false;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float ax = b.R1[j], ay = b.R1[3 + j], az = b.R1[6 + j];
+            const float x0 = ax * xlo, x1 = ax * xhi, y0 = ay * ylo, y1 = ay * yhi, z0 = az * zlo, z1 = az * zhi;
+            const float qmax = fmaxf(x0, x1) + fmaxf(y0, y1) + fmaxf(z0, z1);
+            const float qmin = fminf(x0, x1) + fminf(y0, y1) + fminf(z0, z1);
+            const float hs = 0.5f * b.side[j] + 2e-3f;
+            sep = sep || qmax < -hs || qmin > hs;
+          }
+          av = !sep;
+        }
       }
       act |= (unsigned long long)__ballot_sync(kFull, a) << w0;
+      actv |= (unsigned long long)__ballot_sync(kFull, av) << w0;
     }
     if (act == 0ull) return R_FREE;   // no vertex above the box bottom: no colliding vertex, no kept triangle
   }
   // neighbouring windows share a row / column of vertices: when most of them are active one pass over the zone is cheaper
   const bool by_window = windowed && 3 * __popcll(act) <= 2 * nWx * nWz;
+  const bool by_window_v = windowed && 3 * __popcll(actv) <= 2 * nWx * nWz;
   if (!by_window) act = 1ull;
+  if (!by_window_v) actv = 1ull;          // (windowed && actv == 0 stays 0: the vertex stage has nothing to scan)
   // region r of the walk: origin (lx0, lz0) and extent (rw, rh) in vertices
-  auto region = [&](int wi, int& lx0, int& lz0, int& rw, int& rh) {
+  auto region = [&](bool by_window, int wi, int& lx0, int& lz0, int& rw, int& rh) {
     if (by_window) {
       const int wz = wi / nWx, wx = wi - wz * nWx;
       lx0 = min(7 * wx, nX - 8); lz0 = min(7 * wz, nZ - 8); rw = 8; rh = 8;
@@ -342,9 +369,9 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView&
       if (__any_sync(kFull, hit)) return R_HIT;
     }
 #pragma unroll 1
-    for (unsigned long long m = act; m; m &= m - 1) {
+    for (unsigned long long m = actv; m; m &= m - 1) {
       int lx0, lz0, rw, rh;
-      region(__ffsll((long long)m) - 1, lx0, lz0, rw, rh);
+      region(by_window_v, __ffsll((long long)m) - 1, lx0, lz0, rw, rh);
       const uint32_t magicW = magic_for(rw);
       const int n = rw * rh;
 #pragma unroll 1
@@ -521,7 +548,7 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView&
 #pragma unroll 1
   for (unsigned long long m = act; m; m &= m - 1) {
     int lx0, lz0, rw, rh;
-    region(__ffsll((long long)m) - 1, lx0, lz0, rw, rh);
+    region(by_window, __ffsll((long long)m) - 1, lx0, lz0, rw, rh);
     if ((lx0 * nCZ + lz0) * 2 >= max_live) continue;       // the whole region is emitted after the last live candidate
     const int cw = rw - 1, n = cw * (rh - 1);
     const uint32_t magicW = magic_for(cw);

@@ -398,3 +398,24 @@ def test_both_reach_box_kernels_agree_with_the_oracle(maps, port_lib, mk):
     for k in (0, 1):
         bad = np.nonzero(masks[k] != ref)[0]
         assert bad.size == 0, f"no_groups={k}: {bad.size} mismatches, first {bad[:8]}, grouped={grouped}"
+
+
+def test_host_fed_rounds_equal_the_device_path_across_round_boundaries(maps, checkers):
+    """A host-buffer call slices its batch (copy of slice i+1 under the kernels of slice i, per-slice queue segments, four
+    streams) and processes more than 2^20 states in several rounds: the mask must equal the device-resident path's, for
+    float and double states, from plain and from artp_host_alloc'd buffers."""
+    import torch
+    from art_planner_b200 import capi
+    m = maps("fbm_rough")
+    chk = checkers("yaml")
+    set_map(chk, m)
+    n = (1 << 20) + 300_001                                  # two rounds, the second one sliced as well
+    poses = synth.make_terrain_poses(m, n, seed=123)
+    dev = chk.isValidBatch(torch.from_numpy(poses).cuda()).cpu().numpy()
+    assert 0.05 < dev.mean() < 0.95
+    assert np.array_equal(chk.isValidBatch(poses), dev)
+    hb_p, hb_v = capi.HostBuffer((n, 7), np.float32), capi.HostBuffer((n,), np.uint8)
+    hb_p.array[:] = poses.astype(np.float32)
+    hb_v.array[:] = 7
+    chk.isValidHostPtr(hb_p.array.ctypes.data, n, hb_v.array.ctypes.data, f32=True)
+    assert np.array_equal(hb_v.array, dev)
