@@ -310,12 +310,13 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView&
   if (windowed) {
     const float2* __restrict__ T3 = f.T[3];
     act = 0ull; actv = 0ull;
+    const uint32_t magicWx = magic_for(nWx);
 #pragma unroll 1
     for (int w0 = 0; w0 < nWx * nWz; w0 += 32) {
       const int wi = w0 + lane;
       bool a = false, av = false;
       if (wi < nWx * nWz) {
-        const int wz = wi / nWx, wx = wi - wz * nWx;
+        const int wz = (nWx > 1) ? (int)__umulhi((uint32_t)wi, magicWx) : wi, wx = wi - wz * nWx;
         const int xs = min(b.x0 + 7 * wx, b.x1 - 7), zs = min(b.z0 + 7 * wz, b.z1 - 7);
         const float2 mm = __ldg(T3 + (size_t)zs * f.pitch + xs);
         a = mm.x > b.minB;
