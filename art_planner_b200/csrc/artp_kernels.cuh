@@ -431,13 +431,21 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView&
   // t >> 4. A corner has a second / third / fourth candidate cell only when it lies within cell_margin of a cell
   // boundary, so pass 0 is normally 16 busy lanes and pass 1 is skipped by the whole warp.
   const int corner = (lane >> 1) & 7, u = lane & 1;
-  float px = b.P[0], pz = b.P[2];
+  float px = b.P[0], py = b.P[1], pz = b.P[2];
   {
     const float h0 = 0.5f * b.side[0], h1 = 0.5f * b.side[1], h2 = 0.5f * b.side[2];
-    if (corner & 1) { px += h0 * b.R1[0]; pz += h0 * b.R1[6]; } else { px -= h0 * b.R1[0]; pz -= h0 * b.R1[6]; }
-    if (corner & 2) { px += h1 * b.R1[1]; pz += h1 * b.R1[7]; } else { px -= h1 * b.R1[1]; pz -= h1 * b.R1[7]; }
-    if (corner & 4) { px += h2 * b.R1[2]; pz += h2 * b.R1[8]; } else { px -= h2 * b.R1[2]; pz -= h2 * b.R1[8]; }
+    if (corner & 1) { px += h0 * b.R1[0]; py += h0 * b.R1[3]; pz += h0 * b.R1[6]; } else { px -= h0 * b.R1[0]; py -= h0 * b.R1[3]; pz -= h0 * b.R1[6]; }
+    if (corner & 2) { px += h1 * b.R1[1]; py += h1 * b.R1[4]; pz += h1 * b.R1[7]; } else { px -= h1 * b.R1[1]; py -= h1 * b.R1[4]; pz -= h1 * b.R1[7]; }
+    if (corner & 4) { px += h2 * b.R1[2]; py += h2 * b.R1[5]; pz += h2 * b.R1[8]; } else { px -= h2 * b.R1[2]; py -= h2 * b.R1[5]; pz -= h2 * b.R1[8]; }
   }
+  // Height of this lane's corner (the lower one of the vertical pair that may be folded into one lane below). Every
+  // contact dCollideBoxPlane returns is a box corner lying BELOW the plane; if it also lies on the triangle, the plane
+  // there is no higher than the triangle's highest vertex. So in a merge-free zone (each triangle is tested against its
+  // own plane only) a candidate triangle whose vertices all lie more than 1 mm below the corner that selected it
+  // cannot be hit through that corner -- and the lane of any other corner over the same cell tests it for itself.
+  // A torso hovering over rough ground keeps nearly all candidates by the h > minB rule (its AABB bottom is low) and
+  // drops nearly all of them by this one.
+  const float py_pair = fminf(py, __shfl_xor_sync(kFull, py, 8));
   const float gx = px * f.iW, gz = pz * f.iD;
   const int cxl = (int)floorf(gx - cell_margin), cxh = (int)floorf(gx + cell_margin);
   const int czl = (int)floorf(gz - cell_margin), czh = (int)floorf(gz + cell_margin);
@@ -465,7 +473,11 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView&
       const bool fA = finitef(hA), fB = finitef(hB), fC = finitef(hC), fD = finitef(hD);
       const bool cA = fA && hA > b.minB, cB = fB && hB > b.minB, cC = fC && hC > b.minB, cD = fD && hD > b.minB;
       const bool isUp = (u == 0);
-      const bool keep = isUp ? ((cA || cB || cC) && (fA && fB && fC)) : ((cB || cC || cD) && (fB && fC && fD));
+      bool keep = isUp ? ((cA || cB || cC) && (fA && fB && fC)) : ((cB || cC || cD) && (fB && fC && fD));
+      if (merge_free && keep) {
+        const float hT = isUp ? fmaxf(hA, fmaxf(hB, hC)) : fmaxf(hD, fmaxf(hB, hC));
+        keep = hT > py_pair - 1e-3f;
+      }
       if (keep) {
         cell_plane(f, isUp, ccx, ccz, hA, hB, hC, hD, pl);
         // Liveness: any plane within eps of this one changes the box-plane depth by far less than tau.
