@@ -311,6 +311,12 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView&
     const float2* __restrict__ T3 = f.T[3];
     act = 0ull; actv = 0ull;
     const uint32_t magicWx = magic_for(nWx);
+    // per face axis j: centre offset and the block's half extents along it (the x / z half extents are the same for
+    // every window: 3.5 cells), in centre / radius form
+    const float hx = 3.5f * f.sW, hz = 3.5f * f.sD;
+    const float rxz0 = fabsf(b.R1[0]) * hx + fabsf(b.R1[6]) * hz, rxz1 = fabsf(b.R1[1]) * hx + fabsf(b.R1[7]) * hz,
+                rxz2 = fabsf(b.R1[2]) * hx + fabsf(b.R1[8]) * hz;
+    const float lim0 = 0.5f * b.side[0] + 2e-3f, lim1 = 0.5f * b.side[1] + 2e-3f, lim2 = 0.5f * b.side[2] + 2e-3f;
 #pragma unroll 1
     for (int w0 = 0; w0 < nWx * nWz; w0 += 32) {
       const int wi = w0 + lane;
@@ -321,19 +327,12 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView&
         const float2 mm = __ldg(T3 + (size_t)zs * f.pitch + xs);
         a = mm.x > b.minB;
         if (a) {
-          const float xlo = xs * f.sW - b.P[0], xhi = (xs + 7) * f.sW - b.P[0];
-          const float zlo = zs * f.sD - b.P[2], zhi = (zs + 7) * f.sD - b.P[2];
-          const float ylo = mm.y - b.P[1], yhi = mm.x - b.P[1];
-          bool sep = false;
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const float ax = b.R1[j], ay = b.R1[3 + j], az = b.R1[6 + j];
-            const float x0 = ax * xlo, x1 = ax * xhi, y0 = ay * ylo, y1 = ay * yhi, z0 = az * zlo, z1 = az * zhi;
-            const float qmax = fmaxf(x0, x1) + fmaxf(y0, y1) + fmaxf(z0, z1);
-            const float qmin = fminf(x0, x1) + fminf(y0, y1) + fminf(z0, z1);
-            const float hs = 0.5f * b.side[j] + 2e-3f;
-            sep = sep || qmax < -hs || qmin > hs;
-          }
+          const float dx = ((float)xs + 3.5f) * f.sW - b.P[0], dz = ((float)zs + 3.5f) * f.sD - b.P[2];
+          const float dy = 0.5f * (mm.x + mm.y) - b.P[1], hy = 0.5f * (mm.x - mm.y);
+          const float c0 = b.R1[0] * dx + b.R1[3] * dy + b.R1[6] * dz, c1 = b.R1[1] * dx + b.R1[4] * dy + b.R1[7] * dz,
+                      c2 = b.R1[2] * dx + b.R1[5] * dy + b.R1[8] * dz;
+          const bool sep = fabsf(c0) - (rxz0 + fabsf(b.R1[3]) * hy) > lim0 || fabsf(c1) - (rxz1 + fabsf(b.R1[4]) * hy) > lim1 ||
+                           fabsf(c2) - (rxz2 + fabsf(b.R1[5]) * hy) > lim2;
           av = !sep;
         }
       }
@@ -358,7 +357,7 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView&
   // (3) vertex-in-box test of every colliding vertex of a kept triangle (heightfield.cpp:1306-1441)
   if (allFinite) {
     // every colliding vertex belongs to some kept triangle (all finite, >= 1 cell)
-    if (nV > 128) {
+    if (nV > 128 && actv != 0ull) {
       // Probe pass: one vertex per lane on an 8 x 4 lattice over the box footprint (a hit anywhere in the zone is the
       // reference's answer) -- finds most intersecting torso boxes in one step.
       const float u0 = (((float)(lane & 7) + 0.5f) * 0.25f - 1.0f) * (0.5f * b.side[0]);
