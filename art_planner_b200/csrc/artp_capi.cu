@@ -72,6 +72,7 @@ struct Handle {
   artp::TileCfg tile_cfg[2] = {};
   int tile_grid[2] = {0, 0}, tile_smem[2] = {0, 0}, tile_warps[2] = {8, 8};
   CUtensorMap tile_map[2][2];       // [cfg][layer]: 2-D tile maps over elevation / elevation_masked
+  size_t fork_items = (size_t)1 << 30;   // rounds up to this size run their box kernels side by side (env ARTP_FORK_ITEMS; 0 = serial)
   int pipe_tune = 0;                // env ARTP_PIPE_TUNE (experiments on the host-fed pipeline)
   int pipe_cap_g = 4, pipe_cap_f = 4;   // host-fed slices: grid caps of the group / one-warp-per-box reach kernels, in half SM counts (0: none)
   int k0_flags = 0;                 // tuning switch of the classify stage (env ARTP_K0_FLAGS: 2 = no vertex probes)
@@ -614,6 +615,16 @@ int run_items(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed = nu
       if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[1], s));
       // small batches (the planner's one-state isValid calls): no more CTAs than there can be boxes
       const size_t nb = hi - lo;
+      // The three box kernels are independent of each other (each only clears verdicts). Batches too small to fill the GPU
+      // with any one of them (each has a latency floor of 20-30 us) run them side by side: the two reach-box kernels fork
+      // onto box_stream / group_stream after the classify stage and join before the grouping stage.
+      const bool fork = !h->timing && nb <= h->fork_items && h->chk.reach_tw;
+      cudaStream_t s_f = fork ? h->box_stream : s, s_g = fork ? h->group_stream : s;
+      if (fork) {
+        CU_TRY(h, cudaEventRecord(h->slice_ev[0], s));
+        CU_TRY(h, cudaStreamWaitEvent(h->box_stream, h->slice_ev[0], 0));
+        if (h->group_grid) CU_TRY(h, cudaStreamWaitEvent(h->group_stream, h->slice_ev[0], 0));
+      }
       {
         const int wpc = h->tile_warps[0];
         const unsigned grid_w = (unsigned)std::min<size_t>((size_t)h->tile_grid[0], (5 * nb + wpc - 1) / wpc);
@@ -626,19 +637,27 @@ int run_items(Handle* h, artp::Work w, cudaStream_t s, const HostFeed* feed = nu
       if (h->chk.reach_tw) {
         const int wpc = h->tile_warps[1];
         const unsigned grid_f = (unsigned)std::min<size_t>((size_t)h->tile_grid[1], (4 * nb + wpc - 1) / wpc);
-        artp::box_tiles_warp_kernel<<<grid_f, wpc * 32, h->tile_smem[1], s>>>(h->chk, h->tile_map[1][1], h->tile_map[1][1], h->tile_cfg[1],
-                                                                               w, h->d_recs_f, h->d_ctr + 4, h->d_ctr + 2, h->d_ctr + 1,
-                                                                               h->d_defer, artp::kDeferReachBit, h->mode == 1);
+        artp::box_tiles_warp_kernel<<<grid_f, wpc * 32, h->tile_smem[1], s_f>>>(h->chk, h->tile_map[1][1], h->tile_map[1][1], h->tile_cfg[1],
+                                                                                 w, h->d_recs_f, h->d_ctr + 4, h->d_ctr + 2, h->d_ctr + 1,
+                                                                                 h->d_defer, artp::kDeferReachBit, h->mode == 1);
         CU_TRY(h, cudaGetLastError());
         launches += 1;
       }
       if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[3], s));
       if (h->group_grid) {
         const unsigned grid_g = (unsigned)std::min<size_t>((size_t)h->group_grid, (nb + 7) / 8);
-        artp::reach_groups_kernel<<<grid_g, artp::kMaxTileWarps * 32, h->group_smem, s>>>(h->chk, h->tile_map[1][1], h->tile_cfg[1], w,
-                                                                                           h->d_recs_g, h->d_ctr + 8, h->d_ctr + 9);
+        artp::reach_groups_kernel<<<grid_g, artp::kMaxTileWarps * 32, h->group_smem, s_g>>>(h->chk, h->tile_map[1][1], h->tile_cfg[1], w,
+                                                                                             h->d_recs_g, h->d_ctr + 8, h->d_ctr + 9);
         CU_TRY(h, cudaGetLastError());
         launches += 1;
+      }
+      if (fork) {
+        CU_TRY(h, cudaEventRecord(h->box_ev, h->box_stream));
+        CU_TRY(h, cudaStreamWaitEvent(s, h->box_ev, 0));
+        if (h->group_grid) {
+          CU_TRY(h, cudaEventRecord(h->group_ev, h->group_stream));
+          CU_TRY(h, cudaStreamWaitEvent(s, h->group_ev, 0));
+        }
       }
       if (h->timing && last) CU_TRY(h, cudaEventRecord(h->ev[4], s));
       launches += 2;
@@ -709,6 +728,7 @@ int artp_create(const artp_params* params, artp_handle** out) {
     // experiment switch ARTP_PIPE_TUNE: bit 0 = the call's own stream (classify) gets the highest priority, the box-stage
     // streams the lowest (measured: no effect); ARTP_PIPE_CAPS: see pipe_cap_g / pipe_cap_f
     if (const char* pt = std::getenv("ARTP_PIPE_TUNE")) h->pipe_tune = std::atoi(pt);
+    if (const char* fi = std::getenv("ARTP_FORK_ITEMS")) h->fork_items = (size_t)std::atoll(fi);
     if (const char* pc = std::getenv("ARTP_PIPE_CAPS")) std::sscanf(pc, "%d,%d", &h->pipe_cap_g, &h->pipe_cap_f);   // "g,f" in half SM counts
     int lo_p = 0, hi_p = 0;
     cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);

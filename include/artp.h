@@ -254,7 +254,10 @@ int artp_debug_set_group_capacity(artp_handle* h, int max_triangles);
  *   ARTP_SLICE_ITEMS=n      host-buffer calls: equal H2D slices of n states instead of the built-in schedules
  *   ARTP_SLICE_SCHEDULE=a,b,...  host-buffer calls: slice fractions of a round (e.g. 0.1,0.2,0.3,0.4)
  *   ARTP_TRACE=1            host-buffer calls print the GPU timeline of their slices (copy landed, classify, box stages)
- *   ARTP_K0_FLAGS=2         classify stage also probes the torso footprint (off by default: measured slower)
+ *   ARTP_K0_FLAGS=2         classify stage without its reach-box vertex probes (measured slower: the boxes land in the queues)
+ *   ARTP_FORK_ITEMS=n       rounds of up to n items run their three box kernels side by side on internal streams
+ *                           (default: always; 0 = serial order)
+ *   ARTP_PIPE_CAPS=g,f      host-buffer calls: grid caps of the per-slice reach kernels in half SM counts (default 4,4)
  * artp_set_timing(h, 1) makes the host-buffer calls run their slices back to back (the per-stage events need one stream):
  * leave it off when measuring end-to-end throughput. */
 
