@@ -5,13 +5,19 @@
 
 A "step" is one pass of the hot path over one batch of synthetic input: BASELINE.json configs[1] -- a
 1 000 000-pose validity batch (torso + 4 feet, yaml robot geometry) on the fBm ("Perlin") 1000x1000 @0.04 m map.
-  value  poses/s with the inputs already resident in HBM (artp_check_poses_device), CUDA events, L2 flushed
-         between timed steps, max over ranks.
-  e2e    the same metric through the host-buffer C-ABI call (artp_check_poses) with pinned HOST buffers:
-         H2D of the 56 B/pose states and D2H of the 1 B/pose mask are inside the timed region.
+  value  poses/s with the inputs already resident in HBM (artp_check_poses_bits_device + the ordered index list), CUDA
+         events around every step, L2 flushed between timed steps, max over ranks; the library in its shipped default
+         (per-stage timing off: the three box kernels of a round run side by side).
+  roofline  per-stage kernel durations from a SECOND pass of the same steps with artp_set_timing on (CUDA events recorded
+         by the library on the launch stream; the stages then run one after the other) + that pass's throughput
+         (serial_order_value).
+  e2e    the same metric through the host-buffer C-ABI call (artp_check_poses_f32) with HOST buffers from
+         artp_host_alloc: H2D of the 28 B/pose states and D2H of the 1 B/pose mask are inside the timed region; the
+         56 B/pose double entry point and a two-caller run are reported beside it; the returned mask is compared with
+         the device path's.
   N > 1  weak scaling: every rank checks its own 1 M-pose shard of the seeded sample stream against its replica of
-         the map and the ranks exchange the ordered valid-sample indices with one NCCL all-gather (+ a count
-         all-gather) inside the timed region.
+         the map and the ranks exchange the bit-packed verdicts with one NCCL all-gather inside the timed region
+         (pipelined; the un-pipelined step is reported too); c5 = configs[4] on spatial map shards (strong scaling).
   --impl reference   the reference's own CPU path (oracle/_ref = its compiled ODE when present, else the C port)
          on all host threads, on a bounded sample of the same workload per step.
 """
