@@ -10,10 +10,13 @@
 // out of tile slot i & 1, the tile of box i + 1 is already in flight into the other slot (one mbarrier per slot).
 // No address arithmetic, L1 wavefronts or registers are spent on the gather, and all later reads are shared-memory reads.
 //
-// Two queues feed two launches of the same kernel: reach boxes (small tiles, 8 warps per CTA) and torso boxes (big
-// tiles, 4 warps per CTA). A box whose zone does not fit its tile (cannot happen for the sizes the tiles are derived
-// from) goes to the exact grouping stage. Round 2 also tried one THREAD per reach box over the staged tiles (no
-// cross-lane traffic at all): SIMT divergence left 8-10 of 32 lanes busy and it was slower (profiles/r02_v1_reach_*).
+// Three queues feed three launches: box_tiles_warp_kernel once over the big-tile queue (torso boxes; one tile slot per
+// warp) and once over the reach boxes that need the merge screen or non-finite handling (small tiles, two slots), and
+// reach_groups_kernel over the common reach boxes (all-finite, merge-free: four boxes per warp, below). A box whose zone
+// does not fit its tile (cannot happen for the sizes the tiles are derived from) goes to the exact grouping stage.
+// Queue records are claimed with guided chunk sizes (a share of what is left), one claim ahead of the work.
+// Round 2 also tried one THREAD per reach box over the staged tiles (no cross-lane traffic at all): SIMT divergence
+// left 8-10 of 32 lanes busy and it was slower (profiles/r02_v1_reach_*).
 #pragma once
 
 #include <cuda.h>
@@ -23,7 +26,7 @@
 namespace artp {
 
 constexpr uint32_t kDeferReachBit = 0x80000000u;   // defer-list entry refers to the reach-box queue
-constexpr int kTileChunk = 8;                      // records claimed per atomic (the tile pipeline restarts per chunk)
+constexpr int kTileChunk = 8;                      // most records claimed per atomic (the tile pipeline restarts per claim)
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -163,9 +166,12 @@ box_tiles_warp_kernel(const Checker c, const __grid_constant__ CUtensorMap map0,
 // Reach boxes, the common kind: all-finite, merge-free zone (no screen, no grouping), reduced by the tables. A reach
 // box's 81 vertices / 8 corners do not fill a warp (the one-warp-per-box kernel above runs them at 20 of 32 lanes and pays
 // its per-box overhead 1 : 1), so here a warp decides FOUR boxes at a time, 8 lanes each: lane = vertex in the vertex
-// stage, lane = corner when the candidate cells are collected, lane = (cell, triangle) task when their planes are tested.
-// All four groups run in lock-step through the same loops (trip counts = the maximum over the groups, finished groups are
-// predicated off), so every ballot is a full-warp ballot and the group result is a byte of it.
+// stage, lane = corner when the candidate cells are collected; the candidate (cell, triangle) tasks of the four boxes are
+// then POOLED: lane = one task of any of the four boxes (its box read from shared memory), so the test loop runs
+// ceil(total / 32) times instead of as long as the longest of four 8-lane lists.
+// The vertex and collection stages run the four groups in lock-step through the same loops (trip counts = the maximum over
+// the groups, finished groups predicated off), so every ballot is a full-warp ballot and a group's result is a byte of it.
+// Every warp-wide exchange here must be executed by all 32 lanes: never inside a short-circuit && / || or a ?: arm.
 // -------------------------------------------------------------------------------------------------------------------
 constexpr int kGroupRounds = 8;      // a warp claims 4 * kGroupRounds records per atomic
 constexpr int kGroupTasks = 64;      // candidate (cell, triangle) tasks per box: 8 corners x 4 cells x 2
