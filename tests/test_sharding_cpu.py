@@ -109,3 +109,33 @@ def test_spatial_slabs_cover_the_map_and_route_every_sample():
         for r in range(world):
             s0, s1, _, _ = sharding.slab_window(rows, r, world, halo=40)
             assert ((row[rk == r] >= s0) & (row[rk == r] < s1)).all()
+
+
+def test_slab_windows_cover_the_map_for_every_world_size():
+    """Spatial shards (configs[4]): for every world size the slabs partition the rows, each window holds its slab plus the
+    halo (clipped at the map border), starts on a multiple of 4 rows (artp_set_map_window / TMA alignment), and rank_of_x
+    routes a sample to the rank whose slab holds its row."""
+    from art_planner_b200 import sharding
+    rng = np.random.default_rng(5)
+    for rows in (4000, 1000, 1003, 257):
+        res, cx = 0.04, 1.5
+        length_x = rows * res
+        for world in (1, 2, 3, 4, 5, 8):
+            halo = 40
+            covered = np.zeros(rows, dtype=np.int32)
+            slabs = []
+            for r in range(world):
+                s0, s1, lo, hi = sharding.slab_window(rows, r, world, halo)
+                assert 0 <= lo <= s0 < s1 <= hi <= rows
+                assert lo % 4 == 0
+                assert lo <= max(0, s0 - halo) and hi == min(rows, s1 + halo)
+                covered[s0:s1] += 1
+                slabs.append((s0, s1))
+            assert np.all(covered == 1)
+            x = cx + (rng.random(20000) - 0.5) * length_x * 1.1            # some outside the map: clamped to the edge rows
+            row = sharding.row_of_x(x, cx, length_x, res, rows)
+            rk = sharding.rank_of_x(x, cx, length_x, res, rows, world)
+            assert rk.min() >= 0 and rk.max() < world
+            for r, (s0, s1) in enumerate(slabs):
+                sel = rk == r
+                assert np.all((row[sel] >= s0) & (row[sel] < s1))
