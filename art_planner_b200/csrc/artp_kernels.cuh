@@ -777,8 +777,11 @@ classify_items_kernel(const Checker c, const Work w, BoxRec* __restrict__ recs_w
     orthogonalize_r(Rb);          // dBodySetRotation of the same matrix for all five boxes
 #pragma unroll
     for (int j = 0; j < 3; ++j) { R1[j] = -Rb[j]; R1[3 + j] = Rb[6 + j]; R1[6 + j] = Rb[3 + j]; }
+    // Reach boxes first: this stage can only INVALIDATE an item through a reach box that touches nothing (a torso box is
+    // decided free here or queued, never found colliding), so on an invalid pose the torso box is usually never looked at.
 #pragma unroll 1
-    for (int k = 0; k < 5 && result; ++k) {
+    for (int kk = 0; kk < 5 && result; ++kk) {
+      const int k = kk == 4 ? 0 : kk + 1;
       BoxCtx b;
       uint32_t fl;
       const bool foot = k > 0;
