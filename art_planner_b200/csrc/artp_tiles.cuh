@@ -268,19 +268,28 @@ reach_groups_kernel(const Checker c, const __grid_constant__ CUtensorMap map1, c
       const int nX = b.x1 - b.x0 + 1, nZ = b.z1 - b.z0 + 1, nV = nX * nZ, nCZ = nZ - 1;
       const float top = b.maxB + (1e-4f + 4e-6f * fabsf(b.maxB));
       bool ghit = false;
-      // vertex stage, lane = vertex
+      // vertex stage, lane = vertex. Only the vertices inside the box's own xz extent are scanned: a point inside the box
+      // has |x - P.x| <= xr = sum_j |R1[0][j]| side_j / 2 (and likewise in z), while the zone is that extent padded to whole
+      // cells on every side (heightfield.cpp:1880-1892) -- its outer ring, 81 -> ~49 vertices for a reach box, cannot hold
+      // one (margin 1e-4 m, far above the rounding of the fp32 inside test).
       {
-        int maxNV = gdone ? 0 : nV;
+        const float xr = 0.5f * (fabsf(b.R1[0] * b.side[0]) + fabsf(b.R1[1] * b.side[1]) + fabsf(b.R1[2] * b.side[2])) + 1e-4f;
+        const float zr = 0.5f * (fabsf(b.R1[6] * b.side[0]) + fabsf(b.R1[7] * b.side[1]) + fabsf(b.R1[8] * b.side[2])) + 1e-4f;
+        const int vx0 = max(b.x0, (int)ceilf((b.P[0] - xr) * f.iW)), vx1 = min(b.x1, (int)floorf((b.P[0] + xr) * f.iW));
+        const int vz0 = max(b.z0, (int)ceilf((b.P[2] - zr) * f.iD)), vz1 = min(b.z1, (int)floorf((b.P[2] + zr) * f.iD));
+        const int nXi = max(vx1 - vx0 + 1, 0), nZi = max(vz1 - vz0 + 1, 0), nVi = nXi * nZi;
+        const float* tin = tile + (vz0 - b.z0) * tc.tw + (vx0 - b.x0);
+        int maxNV = gdone ? 0 : nVi;
         maxNV = __reduce_max_sync(kFull, maxNV);
-        const uint32_t magicX = magic_for(nX);
+        const uint32_t magicX = magic_for(nXi);
 #pragma unroll 1
         for (int t0 = 0; t0 < maxNV; t0 += 8) {
           const int t = t0 + gl;
           bool hit = false;
-          if (!gdone && t < nV) {
-            const int zi = (int)__umulhi((uint32_t)t, magicX), xi = t - zi * nX;
-            const float h = tile[zi * tc.tw + xi];
-            hit = h > b.minB && h < top && vertex_inside(b, (b.x0 + xi) * f.sW, h, (b.z0 + zi) * f.sD);
+          if (!gdone && t < nVi) {
+            const int zi = (nXi > 1) ? (int)__umulhi((uint32_t)t, magicX) : t, xi = t - zi * nXi;
+            const float h = tin[zi * tc.tw + xi];
+            hit = h > b.minB && h < top && vertex_inside(b, (vx0 + xi) * f.sW, h, (vz0 + zi) * f.sD);
           }
           if ((__ballot_sync(kFull, hit) >> gshift) & 0xffu) { ghit = true; gdone = true; }
           if (__all_sync(kFull, gdone)) break;
