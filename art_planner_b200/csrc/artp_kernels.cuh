@@ -368,10 +368,21 @@ __device__ int box_collide_warp(const Field& f, const BoxCtx& b, const ZoneView&
       const bool hit = h > b.minB && h < top && vertex_inside(b, vx * f.sW, h, vz * f.sD);
       if (__any_sync(kFull, hit)) return R_HIT;
     }
+    // the whole-zone walk covers only the box's own xz extent: a point inside the box has |x - P.x| <= sum_j |R1[0][j]|
+    // side_j / 2 (likewise z); the zone is that extent padded to whole cells, its outer ring cannot hold an inside vertex
+    int ix0 = 0, iz0 = 0, iw = nX, ih = nZ;
+    if (!by_window_v) {
+      const float xr = 0.5f * (fabsf(b.R1[0] * b.side[0]) + fabsf(b.R1[1] * b.side[1]) + fabsf(b.R1[2] * b.side[2])) + 1e-4f;
+      const float zr = 0.5f * (fabsf(b.R1[6] * b.side[0]) + fabsf(b.R1[7] * b.side[1]) + fabsf(b.R1[8] * b.side[2])) + 1e-4f;
+      const int vx0 = max(b.x0, (int)ceilf((b.P[0] - xr) * f.iW)), vx1 = min(b.x1, (int)floorf((b.P[0] + xr) * f.iW));
+      const int vz0 = max(b.z0, (int)ceilf((b.P[2] - zr) * f.iD)), vz1 = min(b.z1, (int)floorf((b.P[2] + zr) * f.iD));
+      ix0 = vx0 - b.x0; iz0 = vz0 - b.z0; iw = max(vx1 - vx0 + 1, 0); ih = max(vz1 - vz0 + 1, 0);
+    }
 #pragma unroll 1
     for (unsigned long long m = actv; m; m &= m - 1) {
       int lx0, lz0, rw, rh;
       region(by_window_v, __ffsll((long long)m) - 1, lx0, lz0, rw, rh);
+      if (!by_window_v) { lx0 = ix0; lz0 = iz0; rw = iw; rh = ih; }
       const uint32_t magicW = magic_for(rw);
       const int n = rw * rh;
 #pragma unroll 1
